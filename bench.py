@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py - subject-iterations/s of the mvJointModelBayes MCMC hot path (lap_rwm_C loop).
+
+One "step" = one MCMC iteration over the whole cohort (every subject's b_i update, the
+survival-block step, the Gibbs draws and the adaptation): n subject-iterations.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config4_shard|config3|config2]
+  python bench.py --impl reference ...      # restated reference CPU path on the host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "subject-iterations/sec of mvJointModelBayes MCMC"
+UNIT = "subject-iterations/s"
+# algorithmic bytes per subject-iteration (compact fp64 layout, one chain)
+ALG_BYTES = {"config2": 2588.0, "config3": 6892.0, "config4": 12128.0}
+WORKLOADS = {
+    # name: (cohort config, subjects per GPU)
+    "config4_shard": ("config4", 125000),   # 1M-subject config 4 split over 8 GPUs: 125k per GPU
+    "config3": ("config3", 100000),
+    "config2": ("config2", 100000),
+}
+CPU_SAMPLE_N = 20000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="config4_shard", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-per-gpu", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md: sample nvidia-smi DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for j, nm in enumerate(names) if any(len(r) >= 6 and r[2 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/): restated reference chain on host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    cfg, n, iters, chain_id = args
+    from jmbayes_b200.cohorts import make_cohort
+    from oracle import oracle
+    c = make_cohort(cfg, n=n)
+    ctl = dict(c["control"])
+    oracle.set_rowsum_mode(0)        # the reference's own cumsum-difference rowsum
+    t0 = time.perf_counter()
+    oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"],
+                     chain_id=chain_id, max_iters=iters)
+    return time.perf_counter() - t0
+
+
+def cpu_reference(cfg: str, n: int, iters: int, workers: int):
+    """Independent chains, one per worker, like the reference's foreach over n_cores
+    (R/mvJointModelBayes.R:860-905).  Returns subject-iterations/s over all workers."""
+    import multiprocessing as mp
+    if workers <= 1:
+        dt = _cpu_worker((cfg, n, iters, 0))
+        return n * iters / dt, dt
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(cfg, n, iters, w) for w in range(workers)])
+        wall = time.perf_counter() - t0
+    # wall includes each worker's cohort generation; use the slowest worker's chain time instead
+    with ctx.Pool(workers) as pool:
+        times = pool.map(_cpu_worker, [(cfg, n, iters, w) for w in range(workers)])
+    dt = max(times)
+    return workers * n * iters / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, _ = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    workers = max(1, cores - 1)          # n_cores = detectCores() - 1 (R/mvJointModelBayes.R:14)
+    n = CPU_SAMPLE_N
+    from oracle import oracle
+    oracle.build()
+    # size one step so that warmup + steps finish within a few minutes
+    t_probe = _cpu_worker((cfg, n, 2, 0)) / 2
+    per_step = max(1, int(2.0 / max(t_probe, 1e-3)))          # ~2 s of CPU work per step
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(cfg, n, per_step, workers)
+    iters_total = per_step * max(1, min(args.steps, 10))
+    val, dt = cpu_reference(cfg, n, iters_total, workers)
+    sample = f"{workers} independent chains x {iters_total} iterations x {n} subjects of {cfg} (restated lap_rwm_C, gcc -O3 -march=native)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / iters_total, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "cohort": cfg, "subjects": n, "note": "reference CPU path restated in C (R/Rcpp/Armadillo absent from the image); one chain per worker"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from jmbayes_b200 import api, build
+    from jmbayes_b200.cohorts import make_cohort, shared_model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not os.path.exists(build.LIB):
+        raise RuntimeError("libjmb200.so missing: run __graft_entry__.build()")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the hot path has no CPU fallback")
+
+    cfg, n_default = WORKLOADS[args.workload]
+    n = args.n_per_gpu or n_default
+    n_total = n * world
+    shared = shared_model(cfg, n_total)
+    c = make_cohort(cfg, n=n, seed=1000 + rank, shared=shared)
+    Data = c["Data"]
+    fit = api.Fit(Data, c["Covs"]["b"], c["interval_cens"], device=local, subject_offset=rank * n)
+    if world > 1:
+        uid = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        fit.comm_init(world, rank, uid[0])
+    info = fit.layout_info()
+    ctl = dict(c["control"])
+    total_needed = args.warmup + args.steps
+    ctl.update(n_burnin=max(total_needed * 2, 100), n_iter=50, n_thin=50)   # never reaches a kept iteration
+    fit.set_draw(Data)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing: K iterations, inputs in HBM, CUDA events on the library's stream ----
+    fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    fit.chain_iterate(args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = fit.launch_count()
+    ms, _ = fit.chain_iterate(args.steps)
+    l1 = fit.launch_count()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    fit.chain_end(fetch=False)
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = n_total * args.steps / (ms_max * 1e-3)
+
+    # ---- per-launch duration of the step kernel (events around every launch) ----
+    fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    fit.chain_iterate(args.warmup)
+    ksteps = min(args.steps, 50)
+    _, kms = fit.chain_iterate(ksteps, time_kernels=True)
+    fit.chain_end(fetch=False)
+    k_ms = kms / ksteps
+
+    # ---- end to end through the public API with host buffers: set_draw (H2D of the per-draw
+    #      records), chain_begin (H2D of b/scales/params), K iterations, chain_end (D2H of outputs) ----
+    ctl_e = dict(c["control"])
+    ctl_e.update(n_burnin=max(args.steps - 50, 0), n_iter=min(50, args.steps), n_thin=min(50, args.steps), n_block=min(50, max(1, args.steps)))
+    e2e_total = -(-(ctl_e["n_burnin"] + ctl_e["n_iter"]) // ctl_e["n_block"]) * ctl_e["n_block"]
+    barrier()
+    t0 = time.perf_counter()
+    fit.set_draw(Data)
+    res = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl_e)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * e2e_total / float(te.item())
+    h2d = info["chain_bytes_per_subject"] * n - 2 * 8 * (fit.q + 5) * n + 8 * n * (fit.q + 1)
+    d2h = sum(v.nbytes for v in res["mcmc"].values()) + res["scales"]["sigma"]["b"].nbytes + 8 * n + 16 * e2e_total
+
+    alg = ALG_BYTES[cfg]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg * n / (k_ms * 1e-3) / 1e9
+    moved = (info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"]) * n / (k_ms * 1e-3) / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "cohort": cfg, "subjects_per_gpu": n, "subjects_total": n_total,
+                   "outcomes": fit.O, "q": fit.q, "terms": fit.T, "K": fit.K, "interval_cens": bool(c["interval_cens"]),
+                   "parallelism": f"subject-shards x{world}", "chains_per_launch": 1,
+                   "l2": "per-iteration working set %.2f GB per GPU >> 126 MB L2 (inputs larger than L2)" % ((info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"]) * n / 1e9)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "jmb_step_kernel", "kernel_ms": k_ms,
+                     "alg_bytes_per_subject_iteration": alg, "alg_source": "SURVEY.md 8(d)",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "layout_bytes_per_subject_iteration": info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"],
+                     "achieved_layout_gbs": moved, "frac_layout": moved / peak},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_total, "d2h_bytes_per_step": d2h / e2e_total,
+                "what": f"set_draw + lap_rwm_C({e2e_total} iterations) through the C ABI with host buffers, wall clock"},
+        "gpu_launches": int(l1 - l0),
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        t_probe = _cpu_worker((cfg, CPU_SAMPLE_N, 2, 0)) / 2
+        iters = max(2, int(12.0 / max(t_probe, 1e-3)))
+        val, dt = cpu_reference(cfg, CPU_SAMPLE_N, iters, 1)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{iters} iterations x {CPU_SAMPLE_N} subjects of {cfg}, single thread, restated lap_rwm_C ({dt:.1f} s)"}
+    fit.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

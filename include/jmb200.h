@@ -1,0 +1,231 @@
+/*
+ * jmb200.h - C ABI of the B200-native mvJointModelBayes MCMC hot path.
+ *
+ * This is the drop-in boundary an Rcpp shim binds instead of the reference's compiled bodies.
+ * Each entry point cites the reference interface it replaces (paths relative to the JMbayes
+ * source tree).  Conventions:
+ *   - plain pointers and sizes only; every matrix is column-major double (R layout);
+ *   - every index is 0-based int32 (the shim subtracts 1 where R is 1-based, exactly where
+ *     List2Field_uvec does, src/fast_LAPRWM.cpp:45-56);
+ *   - inputs are read-only and only need to stay valid for the duration of the call
+ *     (the reference deep-copies its SEXPs, src/fast_LAPRWM.cpp:434-505);
+ *   - outputs are caller-allocated;
+ *   - every function returns 0 on success, non-zero on failure; jmb_last_error() gives the
+ *     message (the shim turns it into Rcpp::stop, mirroring BEGIN_RCPP/END_RCPP,
+ *     src/RcppExports.cpp:12,25).  There is NO CPU fallback: without a CUDA device every
+ *     compute entry point fails.
+ */
+#ifndef JMB200_H
+#define JMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Data$fams / Data$links (src/fast_LAPRWM.cpp:177-199) */
+enum { JMB_FAM_GAUSSIAN = 0, JMB_FAM_BINOMIAL = 1, JMB_FAM_POISSON = 2 };
+enum { JMB_LINK_IDENTITY = 0, JMB_LINK_LOGIT = 1, JMB_LINK_PROBIT = 2, JMB_LINK_CLOGLOG = 3,
+       JMB_LINK_LOG = 4 };
+/* Data$trans_Funs (src/fast_LAPRWM.cpp:91-106) */
+enum { JMB_TF_IDENTITY = 0, JMB_TF_EXPIT = 1, JMB_TF_EXP = 2, JMB_TF_LOG = 3, JMB_TF_LOG2 = 4,
+       JMB_TF_LOG10 = 5, JMB_TF_SQRT = 6 };
+
+/* compile-time limits of the device model descriptor */
+#define JMB_MAX_OUTCOMES 8
+#define JMB_MAX_TERMS 16
+#define JMB_MAX_Q 16
+#define JMB_MAX_RT 8     /* columns of one ZZ[[t]] */
+#define JMB_MAX_UT 8     /* columns of one U[[t]]  */
+#define JMB_MAX_BS 64
+#define JMB_MAX_GAMMAS 32
+#define JMB_MAX_ALPHAS 32
+
+typedef struct jmb_handle_s* jmb_handle;
+
+/*
+ * The static part of the reference's `Data` list: everything that is identical for all the
+ * M chains of one fit (built at R/mvJointModelBayes.R:651-714, read at
+ * src/fast_LAPRWM.cpp:434-505).  Rows of each longitudinal outcome must be grouped by subject
+ * (as extractFrames produces them, R/extractFrames.R:19), every subject needs >= 1 row per
+ * outcome (R/mv_glmer.R:21); jmb_create() validates idL/idL2/idGK_fast against that.
+ */
+typedef struct jmb_data {
+    int32_t n;              /* subjects held by this handle (this rank's shard) */
+    int32_t n_outcomes;     /* length(Data$y) */
+    int32_t q;              /* ncol(initials$b) */
+    int32_t n_terms;        /* length(Data$XXbetas) */
+    int32_t n_alphas;       /* ncol(Wlong) */
+    int32_t n_Bs;           /* ncol(W1) */
+    int32_t n_gammas;       /* ncol(W2) (0 -> the *_nogammas flavour) */
+    int32_t K;              /* quadrature points per subject (15 or 7) */
+    int32_t interval_cens;  /* lap_rwm_C argument `interval_cens` */
+    int32_t multi_state;    /* lap_rwm_C argument `multiState`; must be 0 (out of scope) */
+    int64_t subject_offset; /* global index of local subject 0: keys the counter RNG so that a
+                               sharded run reproduces the single-GPU chain */
+    /* longitudinal part, per outcome k */
+    const int64_t* N;               /* [n_outcomes] rows of outcome k */
+    const int32_t* fams;            /* [n_outcomes] JMB_FAM_* */
+    const int32_t* links;           /* [n_outcomes] JMB_LINK_* */
+    const int32_t* q_k;             /* [n_outcomes] length(RE_inds[[k]]) */
+    const int32_t* const* RE_inds;  /* [n_outcomes][q_k] columns of b used by outcome k */
+    const double* const* y;         /* [n_outcomes][N_k] */
+    const double* const* Z;         /* [n_outcomes] N_k x q_k */
+    const int32_t* const* idL;      /* [n_outcomes][N_k] subject of each row */
+    const int32_t* const* idL2;     /* [n_outcomes][n] last row of each subject */
+    /* survival part */
+    const double* event;            /* [n] 0/1, or 0/1/2/3 with interval censoring */
+    const double* W1;               /* n x n_Bs */
+    const double* W1s;              /* nK x n_Bs */
+    const double* W1s_int;          /* nK x n_Bs (interval_cens only, else NULL) */
+    const double* W2;               /* n x n_gammas */
+    const double* W2s;              /* nK x n_gammas */
+    const double* W2s_int;          /* nK x n_gammas (interval_cens only) */
+    const double* Pw;               /* [nK] */
+    const double* Pw_int;           /* [nK] (interval_cens only) */
+    const int32_t* idGK_fast;       /* [n] last quadrature row of each subject, (i+1)K-1 */
+    /* association terms t */
+    const int32_t* r_t;             /* [n_terms] ncol(ZZ[[t]]) = length(RE_inds2[[t]]) */
+    const int32_t* const* RE_inds2; /* [n_terms][r_t] */
+    const int32_t* u_t;             /* [n_terms] ncol(U[[t]]) = length(col_inds[[t]]) */
+    const int32_t* const* col_inds; /* [n_terms][u_t] columns of Wlong owned by term t */
+    const int32_t* trans_Funs;      /* [n_terms] JMB_TF_* */
+    const double* const* ZZ;        /* [n_terms] n x r_t */
+    const double* const* ZZs;       /* [n_terms] nK x r_t */
+    const double* const* ZZs_int;   /* [n_terms] nK x r_t (interval_cens only) */
+    const double* const* U;         /* [n_terms] n x u_t */
+    const double* const* Us;        /* [n_terms] nK x u_t */
+    const double* const* Us_int;    /* [n_terms] nK x u_t (interval_cens only) */
+    /* Covs$b: q x q x n upper Cholesky factors (R/mvJointModelBayes.R:728-729) */
+    const double* Covs_b;
+} jmb_data;
+
+/* The per-draw part of `Data` (R/mvJointModelBayes.R:760-770). */
+typedef struct jmb_draw {
+    const double* const* Xbetas;       /* [n_outcomes][N_k] */
+    const double* const* XXbetas;      /* [n_terms][n] */
+    const double* const* XXsbetas;     /* [n_terms][nK] */
+    const double* const* XXsbetas_int; /* [n_terms][nK] (interval_cens only) */
+    const double* sigmas;              /* [n_outcomes] (ignored unless gaussian) */
+    const double* invD;                /* q x q */
+} jmb_draw;
+
+/* `priors` (src/fast_LAPRWM.cpp:531-569) */
+typedef struct jmb_priors {
+    const double* mean_Bs_gammas; const double* Tau_Bs_gammas;  /* [B], B x B */
+    const double* mean_gammas;    const double* Tau_gammas;     /* [p], p x p */
+    const double* mean_alphas;    const double* Tau_alphas;     /* [A], A x A */
+    double A_tau_Bs_gammas, B_tau_Bs_gammas, rank_Tau_Bs_gammas;
+    int32_t shrink_gammas;
+    double A_tau_gammas, B_tau_gammas, rank_Tau_gammas, A_phi_gammas, B_phi_gammas;
+    int32_t shrink_alphas, double_gamma_alphas;
+    double A_tau_alphas, B_tau_alphas, rank_Tau_alphas, A_phi_alphas, B_phi_alphas;
+    double A_xi_alphas, B_xi_alphas, A_nu_alphas, B_nu_alphas;
+    int32_t n_td;                    /* length(td_cols) */
+    const int32_t* td_len;           /* [n_td] */
+    const int32_t* const* td_cols;   /* [n_td][td_len] */
+    double rank_Tau_td_alphas;
+} jmb_priors;
+
+/* `control` (src/fast_LAPRWM.cpp:572-582) plus the RNG key */
+typedef struct jmb_control {
+    int32_t n_iter, n_burnin, n_block, n_thin;
+    double target_acc, eps1, eps2, eps3, c0, c1;
+    int32_t adaptCov;
+    uint32_t seed;       /* control$seed */
+    uint32_t chain_id;   /* index of the mvglmer draw: second half of the Philox key */
+} jmb_control;
+
+/* `initials` + `scales` + `Covs` (src/fast_LAPRWM.cpp:507-518,594-601) */
+typedef struct jmb_chain_in {
+    const double* b;              /* n x q */
+    const double* Bs_gammas; const double* gammas; const double* alphas;
+    const double* tau_Bs_gammas;  /* [1] */
+    double tau_gammas, tau_alphas;
+    const double* phi_gammas;     /* [p] */
+    const double* phi_alphas;     /* [A] */
+    const double* tau_td_alphas;  /* [n_td] */
+    const double* sigma_b;        /* scales$b [n] */
+    double sigma_Bs_gammas, sigma_gammas, sigma_alphas;
+    const double* Sigma_Bs_gammas; const double* Sigma_gammas; const double* Sigma_alphas;
+} jmb_chain_in;
+
+/* The list lap_rwm_C returns (src/fast_LAPRWM.cpp:870-895); n_out = floor(n_iter/n_thin). */
+typedef struct jmb_chain_out {
+    double* b;               /* n x q x n_out */
+    double* Bs_gammas;       /* B x n_out */
+    double* gammas;          /* p x n_out */
+    double* alphas;          /* A x n_out */
+    double* phi_gammas;      /* p x n_out */
+    double* phi_alphas;      /* A x n_out */
+    double* tau_Bs_gammas;   /* 1 x n_out */
+    double* tau_gammas;      /* [n_out] */
+    double* tau_alphas;      /* [n_out] */
+    double* tau_td_alphas;   /* n_td x n_out */
+    double* logWeights;      /* [n_out] */
+    double* sigma_b;         /* [n] adapted scales */
+    double* sigma_surv;      /* [3] sigma_Bs_gammas, sigma_gammas, sigma_alphas */
+    double* Sigma_Bs_gammas; double* Sigma_gammas; double* Sigma_alphas;
+    /* additive extras (not in the reference's list; may be NULL) */
+    double* accept_b;        /* [n] overall acceptance rate of each subject's b-step */
+    double* accept_surv;     /* [1] overall acceptance rate of the survival block */
+    double* trace_surv;      /* [2 * total iterations] (sum log_ptb current, proposed) per iteration */
+} jmb_chain_out;
+
+/* Per-subject pieces of the b-step target for given (b, Bs_gammas, gammas, alphas): the
+ * quantities initialised at src/fast_LAPRWM.cpp:619-650 (== log_postREF, :219-248). */
+typedef struct jmb_eval_out {
+    double* log_pyb;  /* [n] */
+    double* log_pb;   /* [n] */
+    double* log_h;    /* [n] */
+    double* H;        /* [n] */
+    double* HL;       /* [n] (interval_cens only; may be NULL) */
+    double* log_ptb;  /* [n] */
+} jmb_eval_out;
+
+const char* jmb_last_error(void);
+int jmb_device_count(int* count);
+
+/* Upload the static designs of one fit (replaces the unpacking at src/fast_LAPRWM.cpp:434-505,
+ * done once per fit instead of once per chain).  `device` is the CUDA ordinal. */
+int jmb_create(const jmb_data* data, int device, jmb_handle* out);
+int jmb_destroy(jmb_handle h);
+
+/* Per-draw vectors of one chain (R/mvJointModelBayes.R:760-770). */
+int jmb_set_draw(jmb_handle h, const jmb_draw* draw);
+
+/* lap_rwm_C (src/fast_LAPRWM.cpp:431-896) for the current draw. */
+int jmb_lap_rwm(jmb_handle h, const jmb_priors* priors, const jmb_control* control,
+                const jmb_chain_in* in, jmb_chain_out* out);
+
+/* Per-subject log-posterior pieces at (b, params) for the current draw
+ * (src/fast_LAPRWM.cpp:619-650); the 1e-10 parity probe. */
+int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* Bs_gammas,
+                        const double* gammas, const double* alphas, jmb_eval_out* out);
+
+/* Layout facts for the parity tests: the CSR row pointers the device layout was built with
+ * (must equal idL2-derived segments bit for bit) and bytes moved per subject-iteration. */
+int jmb_get_row_ptr(jmb_handle h, int outcome, int64_t* row_ptr /* [n+1] */);
+int jmb_layout_info(jmb_handle h, double* shared_bytes_per_subject,
+                    double* chain_bytes_per_subject, int32_t* w1_band, int32_t* group_lanes);
+
+/* Multi-GPU: one process per GPU, contiguous subject shards, one all-reduce of the
+ * survival-block partial sums per iteration.  The 128-byte NCCL unique id
+ * is created on rank 0 and distributed by the host language (torch.distributed / Rmpi). */
+int jmb_comm_unique_id(char id[128]);
+int jmb_comm_init(jmb_handle h, int nranks, int rank, const char id[128]);
+
+/* Benchmark hooks: run `iters` iterations of the current chain state entirely on the device
+ * (no host copies) and report the device time of the loop; jmb_chain_begin uploads state. */
+int jmb_chain_begin(jmb_handle h, const jmb_priors* priors, const jmb_control* control,
+                    const jmb_chain_in* in);
+int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, float* step_kernel_ms);
+int jmb_chain_end(jmb_handle h, jmb_chain_out* out);
+int jmb_launch_count(jmb_handle h, int64_t* launches);
+void* jmb_stream(jmb_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JMB200_H */

@@ -1,0 +1,223 @@
+"""Host-side mirror of the reference's Rcpp interface for the mvJointModelBayes hot path.
+
+The reference's callers are R functions; R is not available in this image, so this module plays
+the role of the Rcpp shim for the tests and the benchmark: same entry-point names, same argument
+lists (R lists become dicts with the reference's field names, see ``cohorts.py``), same returned
+structure and the same error behaviour (a failing call raises, like ``Rcpp::stop``).  All compute
+goes through the C ABI of ``libjmb200.so`` (``include/jmb200.h``); there is no CPU fallback - if
+the CUDA library is missing or no GPU is usable, calls raise ``RuntimeError``.
+
+reference: R/RcppExports.R:4-42, src/RcppExports.cpp:216-228, src/fast_LAPRWM.cpp:431-896.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from .build import LIB
+
+_lib_cache = None
+
+
+class JmbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load ``libjmb200.so`` (fails loudly when it has not been built)."""
+    global _lib_cache
+    if _lib_cache is not None:
+        return _lib_cache
+    if not os.path.exists(LIB):
+        raise JmbError(f"{LIB} is missing: build it with __graft_entry__.build() "
+                       "(nvcc, sm_100a); there is no CPU fallback")
+    L = C.CDLL(LIB)
+    L.jmb_last_error.restype = C.c_char_p
+    L.jmb_stream.restype = C.c_void_p
+    L.jmb_stream.argtypes = [C.c_void_p]
+    vp = C.c_void_p
+    L.jmb_create.argtypes = [C.POINTER(_abi.JmbData), C.c_int, C.POINTER(vp)]
+    L.jmb_destroy.argtypes = [vp]
+    L.jmb_set_draw.argtypes = [vp, C.POINTER(_abi.JmbDraw)]
+    L.jmb_lap_rwm.argtypes = [vp, C.POINTER(_abi.JmbPriors), C.POINTER(_abi.JmbControl),
+                              C.POINTER(_abi.JmbChainIn), C.POINTER(_abi.JmbChainOut)]
+    L.jmb_chain_begin.argtypes = [vp, C.POINTER(_abi.JmbPriors), C.POINTER(_abi.JmbControl),
+                                  C.POINTER(_abi.JmbChainIn)]
+    L.jmb_chain_iterate.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.jmb_chain_end.argtypes = [vp, C.POINTER(_abi.JmbChainOut)]
+    L.jmb_eval_logpost_re.argtypes = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p,
+                                      _abi.c_double_p, C.POINTER(_abi.JmbEvalOut)]
+    L.jmb_get_row_ptr.argtypes = [vp, C.c_int, _abi.c_int64_p]
+    L.jmb_layout_info.argtypes = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p, _abi.c_int32_p]
+    L.jmb_launch_count.argtypes = [vp, _abi.c_int64_p]
+    L.jmb_comm_unique_id.argtypes = [C.c_char_p]
+    L.jmb_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.jmb_device_count.argtypes = [C.POINTER(C.c_int)]
+    _lib_cache = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise JmbError(lib().jmb_last_error().decode())
+
+
+def device_count() -> int:
+    c = C.c_int(0)
+    _check(lib().jmb_device_count(C.byref(c)))
+    return c.value
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_abi.c_double_p)
+
+
+class Fit:
+    """The static designs of one ``mvJointModelBayes`` fit, resident on one GPU.
+
+    Plays the role of the ``Data`` unpacking at src/fast_LAPRWM.cpp:434-505, done once per fit
+    instead of once per chain.
+    """
+
+    def __init__(self, Data: dict, Covs_b, interval_cens: bool = False, multiState: bool = False,
+                 device: int = 0, subject_offset: int = 0):
+        self._h = C.c_void_p()
+        self.interval_cens = bool(interval_cens)
+        d, keep = _abi.marshal_data(Data, Covs_b, interval_cens, multiState, subject_offset)
+        self.n, self.q = d.n, d.q
+        self.B, self.p, self.A = d.n_Bs, d.n_gammas, d.n_alphas
+        self.O, self.T, self.K = d.n_outcomes, d.n_terms, d.K
+        _check(lib().jmb_create(C.byref(d), device, C.byref(self._h)))
+        del keep
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            lib().jmb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- per-draw data (R/mvJointModelBayes.R:760-770) ------------------------------------------
+    def set_draw(self, Data: dict):
+        w, keep = _abi.marshal_draw(Data, self.interval_cens)
+        _check(lib().jmb_set_draw(self._h, C.byref(w)))
+        del keep
+
+    # -- lap_rwm_C --------------------------------------------------------------------------------
+    def _marshal_chain(self, initials, priors, scales, Covs, control, chain_id):
+        pr, k1 = _abi.marshal_priors(priors)
+        ct = _abi.marshal_control(control, chain_id)
+        ci, k2 = _abi.marshal_chain_in(initials, scales, Covs)
+        return pr, ct, ci, (k1, k2)
+
+    def _result(self, bufs, n_out):
+        mcmc = {k: bufs[k] for k in ("b", "Bs_gammas", "gammas", "alphas", "phi_gammas", "phi_alphas",
+                                     "tau_Bs_gammas", "tau_gammas", "tau_alphas", "tau_td_alphas")}
+        return dict(
+            mcmc=mcmc, logWeights=bufs["logWeights"],
+            scales=dict(sigma=dict(b=bufs["sigma_b"], Bs_gammas=float(bufs["sigma_surv"][0]),
+                                   gammas=float(bufs["sigma_surv"][1]), alphas=float(bufs["sigma_surv"][2])),
+                        Sigma=dict(Bs_gammas=bufs["Sigma_Bs_gammas"], gammas=bufs["Sigma_gammas"],
+                                   alphas=bufs["Sigma_alphas"])),
+            extras=dict(accept_b=bufs.get("accept_b"), accept_surv=bufs.get("accept_surv"),
+                        trace_surv=bufs.get("trace_surv")))
+
+    def lap_rwm_C(self, initials, priors, scales, Covs, control, chain_id: int = 0):
+        """One chain for the current draw; returns the list ``lap_rwm_C`` returns
+        (src/fast_LAPRWM.cpp:870-895) plus ``extras`` (acceptance rates, per-iteration sums)."""
+        pr, ct, ci, keep = self._marshal_chain(initials, priors, scales, Covs, control, chain_id)
+        total, n_out = _abi.chain_dims(control)
+        out, bufs = _abi.alloc_chain_out(self.n, self.q, self.B, self.p, self.A, pr.n_td, n_out, total)
+        _check(lib().jmb_lap_rwm(self._h, C.byref(pr), C.byref(ct), C.byref(ci), C.byref(out)))
+        del keep
+        return self._result(bufs, n_out)
+
+    # -- stepwise driver (benchmark / tests) ----------------------------------------------------------
+    def chain_begin(self, initials, priors, scales, Covs, control, chain_id: int = 0):
+        pr, ct, ci, keep = self._marshal_chain(initials, priors, scales, Covs, control, chain_id)
+        self._chain_meta = (pr.n_td,) + _abi.chain_dims(control)
+        _check(lib().jmb_chain_begin(self._h, C.byref(pr), C.byref(ct), C.byref(ci)))
+        del keep
+
+    def chain_iterate(self, iters: int, time_kernels: bool = False):
+        """Run ``iters`` iterations on the device; returns (loop ms, step-kernel ms or None)."""
+        ms, kms = C.c_float(0), C.c_float(0)
+        _check(lib().jmb_chain_iterate(self._h, int(iters), C.byref(ms),
+                                       C.byref(kms) if time_kernels else None))
+        return ms.value, (kms.value if time_kernels else None)
+
+    def chain_end(self, fetch: bool = True):
+        if not fetch:
+            _check(lib().jmb_chain_end(self._h, None))
+            return None
+        n_td, total, n_out = self._chain_meta
+        out, bufs = _abi.alloc_chain_out(self.n, self.q, self.B, self.p, self.A, n_td, n_out, total)
+        _check(lib().jmb_chain_end(self._h, C.byref(out)))
+        return self._result(bufs, n_out)
+
+    # -- parity probes -------------------------------------------------------------------------------
+    def eval_logpost_re(self, b, Bs_gammas, gammas, alphas):
+        """Per-subject log p(y|b), log p(b), log h, H, HL, log p(T|b) at (b, params)
+        (src/fast_LAPRWM.cpp:619-650)."""
+        n = self.n
+        b = np.asfortranarray(np.asarray(b, dtype=np.float64))
+        res = {k: np.zeros(n) for k in ("log_pyb", "log_pb", "log_h", "H", "HL", "log_ptb")}
+        out = _abi.JmbEvalOut()
+        for k, a in res.items():
+            setattr(out, k, _dptr(a))
+        g = np.ascontiguousarray(np.atleast_1d(np.asarray(gammas, dtype=np.float64)))
+        if g.size == 0:
+            g = np.zeros(1)
+        Bs = np.ascontiguousarray(np.asarray(Bs_gammas, dtype=np.float64))
+        al = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64))
+        _check(lib().jmb_eval_logpost_re(self._h, _dptr(b), _dptr(Bs), _dptr(g), _dptr(al), C.byref(out)))
+        return res
+
+    def row_ptr(self, outcome: int):
+        rp = np.zeros(self.n + 1, dtype=np.int64)
+        _check(lib().jmb_get_row_ptr(self._h, outcome, rp.ctypes.data_as(_abi.c_int64_p)))
+        return rp
+
+    def layout_info(self):
+        sb, cb = C.c_double(0), C.c_double(0)
+        wb, g = C.c_int32(0), C.c_int32(0)
+        _check(lib().jmb_layout_info(self._h, C.byref(sb), C.byref(cb), C.byref(wb), C.byref(g)))
+        return dict(shared_bytes_per_subject=sb.value, chain_bytes_per_subject=cb.value,
+                    w1_band=wb.value, group_lanes=g.value)
+
+    def launch_count(self) -> int:
+        c = C.c_int64(0)
+        _check(lib().jmb_launch_count(self._h, C.byref(c)))
+        return c.value
+
+    # -- multi-GPU ---------------------------------------------------------------------------------
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        _check(lib().jmb_comm_init(self._h, nranks, rank, unique_id))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(lib().jmb_comm_unique_id(buf))
+    return buf.raw
+
+
+def lap_rwm_C(initials, Data, priors, scales, Covs, control, interval_cens=False, multiState=False,
+              device: int = 0, chain_id: int = 0):
+    """Same argument list as the reference's ``lap_rwm_C`` (R/RcppExports.R; src/fast_LAPRWM.cpp:431)."""
+    with Fit(Data, Covs["b"], interval_cens, multiState, device) as fit:
+        fit.set_draw(Data)
+        return fit.lap_rwm_C(initials, priors, scales, Covs, control, chain_id)

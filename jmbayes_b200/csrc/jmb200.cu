@@ -1,0 +1,753 @@
+// jmb200.cu - host runtime + C ABI (include/jmb200.h) of the B200-native mvJointModelBayes
+// MCMC hot path.  Product code: never includes or links anything under oracle/; every compute
+// entry point fails loudly when no CUDA device is usable (no CPU fallback).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and enums only: the library itself is resolved with dlopen
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "jmb_kernels.cuh"
+
+using namespace jmb;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+extern "C" const char* jmb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int jmb_device_count(int* count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *count = 0; return fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *count = c;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen (reuses the copy torch already loaded when there is one)
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.lib) return 0;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(std::string("cannot load libnccl: ") + dlerror());
+    g_nccl.lib = lib;
+    *(void**)&g_nccl.GetUniqueId = dlsym(lib, "ncclGetUniqueId");
+    *(void**)&g_nccl.CommInitRank = dlsym(lib, "ncclCommInitRank");
+    *(void**)&g_nccl.AllReduce = dlsym(lib, "ncclAllReduce");
+    *(void**)&g_nccl.CommDestroy = dlsym(lib, "ncclCommDestroy");
+    *(void**)&g_nccl.GetErrorString = dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) return fail("libnccl lacks required symbols");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct jmb_handle_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    ModelMeta mm{};
+    ParamLayout pl{};
+    ChainConst cc{};
+    int n = 0;
+    long long subject_offset = 0;
+    int n_block_cap = 1024;
+    std::vector<long long> N;                       // rows per outcome
+    std::vector<std::vector<int>> rowptr;           // host CSR per outcome
+    std::vector<long long> doff, coff;              // host offsets
+    // device
+    double* d_drec = nullptr; long long* d_doff = nullptr;
+    double* d_crec = nullptr; long long* d_coff = nullptr;
+    int* d_rowptr = nullptr;
+    double* d_state = nullptr; double* d_par = nullptr; Ctl* d_ctl = nullptr;
+    double* d_partials = nullptr; double* d_eval = nullptr; double* d_tmp = nullptr;  // d_tmp: n*(q+1)
+    double* h_crec = nullptr;                       // pinned staging for the per-draw records
+    double* h_par = nullptr;                        // pinned staging for the parameter block
+    double* h_tmp = nullptr;                        // pinned staging n*(q+1)
+    bool draw_set = false;
+    // chain
+    bool chain_open = false;
+    int iter_host = 0, total_iters = 0, keep_host = 0, check_host = 0, n_out = 0, n_td = 0;
+    double *o_b = nullptr, *o_par = nullptr, *o_trace = nullptr;   // device outputs
+    FinalizeArgs fa{};
+    bool want_trace = false;
+    // launch configuration
+    int grid = 0, subjects_per_cta = 0, smem_bytes = 0;
+    long long launches = 0;
+    // multi-GPU
+    ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+};
+
+static int roundup(int x, int m) { return (x + m - 1) / m * m; }
+
+template <typename F>
+static void parallel_for(int n, F f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
+    if (n < 4096) nt = 1;
+    std::vector<std::thread> th;
+    int chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        int lo = t * chunk, hi = std::min(n, lo + chunk);
+        if (lo >= hi) break;
+        th.emplace_back([=] { f(lo, hi); });
+    }
+    for (auto& x : th) x.join();
+}
+
+static void build_param_layout(const ModelMeta& mm, int n_td, int n_block_cap, ParamLayout& pl) {
+    int o = 0;
+    auto take = [&](int len) { int r = o; o += std::max(len, 1); return r; };
+    pl.cur = take(mm.P); pl.prop = take(mm.P);
+    pl.invD = take(mm.q * mm.q); pl.sigmas = take(mm.O);
+    pl.tau_Bs = take(1); pl.tau_g = take(1); pl.tau_a = take(1); pl.xi_a = take(1);
+    pl.phi_g = take(mm.p); pl.phi_a = take(mm.A); pl.nu_a = take(mm.A); pl.tau_td = take(n_td);
+    pl.Tau_g = take(mm.p * mm.p); pl.Tau_a = take(mm.A * mm.A); pl.Tau_a_pen = take(mm.A * mm.A);
+    pl.sig = take(3);
+    pl.S_Bs = take(mm.B * mm.B); pl.S_g = take(mm.p * mm.p); pl.S_a = take(mm.A * mm.A);
+    pl.H_Bs = take(mm.B * mm.B); pl.H_g = take(mm.p * mm.p); pl.H_a = take(mm.A * mm.A);
+    pl.mean_Bs = take(mm.B); pl.Tau_Bs = take(mm.B * mm.B); pl.mean_g = take(mm.p); pl.mean_a = take(mm.A);
+    pl.block_par = take(mm.P * n_block_cap);
+    pl.sums = take(4);
+    pl.total = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// jmb_create: validate, compact and repack the static designs into per-subject records
+// ---------------------------------------------------------------------------------------------
+extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
+    if (!d || !out) return fail("jmb_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (jmb_device_count(&ndev) || ndev == 0)
+        return fail("jmb_create: no CUDA device available (this library has no CPU fallback): " + g_err);
+    if (device < 0 || device >= ndev) return fail("jmb_create: bad device ordinal");
+    if (d->multi_state) return fail("jmb_create: multiState = TRUE is not supported by the CUDA path");
+    if (d->n <= 0 || d->n_outcomes <= 0 || d->n_outcomes > JMB_MAX_OUTCOMES) return fail("jmb_create: bad n / n_outcomes");
+    if (d->q <= 0 || d->q > JMB_MAX_Q) return fail("jmb_create: q out of range");
+    if (d->n_terms <= 0 || d->n_terms > JMB_MAX_TERMS) return fail("jmb_create: n_terms out of range");
+    if (d->n_Bs <= 0 || d->n_Bs > JMB_MAX_BS || d->n_gammas < 0 || d->n_gammas > JMB_MAX_GAMMAS ||
+        d->n_alphas <= 0 || d->n_alphas > JMB_MAX_ALPHAS) return fail("jmb_create: parameter block sizes out of range");
+    const int S = d->interval_cens ? 2 : 1;
+    if (d->K <= 0 || 1 + d->K * S > 32) return fail("jmb_create: 1 + K * (1 + interval_cens) must be <= 32");
+    if (S == 2 && (!d->W1s_int || !d->Pw_int || !d->ZZs_int || !d->Us_int || (d->n_gammas && !d->W2s_int)))
+        return fail("jmb_create: interval_cens needs the *_int designs");
+
+    auto* h = new jmb_handle_s();
+    h->device = device;
+    h->n = d->n;
+    h->subject_offset = d->subject_offset;
+    const int n = d->n, O = d->n_outcomes, q = d->q, T = d->n_terms, B = d->n_Bs, p = d->n_gammas, K = d->K;
+    const long long ns = (long long)n * K;
+    ModelMeta& mm = h->mm;
+    mm.O = O; mm.q = q; mm.T = T; mm.A = d->n_alphas; mm.B = B; mm.p = p; mm.K = K; mm.S = S;
+    mm.P = B + p + d->n_alphas;
+    mm.G = (1 + K * S <= 16) ? 16 : 32;
+    mm.RP = mm.G;
+    mm.state_stride = q + 5;
+    int qsum = 0;
+    for (int k = 0; k < O; ++k) {
+        mm.fam[k] = d->fams[k]; mm.link[k] = d->links[k]; mm.qk[k] = d->q_k[k];
+        if (mm.qk[k] < 0 || mm.qk[k] > JMB_MAX_Q) { delete h; return fail("jmb_create: q_k out of range"); }
+        for (int j = 0; j < mm.qk[k]; ++j) {
+            mm.re_inds[k][j] = d->RE_inds[k][j];
+            if (mm.re_inds[k][j] < 0 || mm.re_inds[k][j] >= q) { delete h; return fail("jmb_create: RE_inds out of range"); }
+        }
+        qsum += mm.qk[k];
+    }
+    (void)qsum;
+    for (int t = 0; t < T; ++t) {
+        mm.rt[t] = d->r_t[t]; mm.ut[t] = d->u_t[t]; mm.tf[t] = d->trans_Funs[t];
+        if (mm.rt[t] < 0 || mm.rt[t] > JMB_MAX_RT || mm.ut[t] <= 0 || mm.ut[t] > JMB_MAX_UT) { delete h; return fail("jmb_create: term sizes out of range"); }
+        for (int j = 0; j < mm.rt[t]; ++j) {
+            mm.re2[t][j] = d->RE_inds2[t][j];
+            if (mm.re2[t][j] < 0 || mm.re2[t][j] >= q) { delete h; return fail("jmb_create: RE_inds2 out of range"); }
+        }
+        for (int u = 0; u < mm.ut[t]; ++u) {
+            mm.col[t][u] = d->col_inds[t][u];
+            if (mm.col[t][u] < 0 || mm.col[t][u] >= d->n_alphas) { delete h; return fail("jmb_create: col_inds out of range"); }
+        }
+    }
+
+    // ---- segment boundaries: rows grouped by subject, idL2 = last row, idGK_fast = (i+1)K-1 ----
+    h->N.assign(d->N, d->N + O);
+    h->rowptr.resize(O);
+    for (int k = 0; k < O; ++k) {
+        const long long Nk = d->N[k];
+        if (Nk < n || Nk > 2147483000LL) { delete h; return fail("jmb_create: N_k out of range"); }
+        std::vector<int>& rp = h->rowptr[k];
+        rp.assign(n + 1, 0);
+        const int32_t* id = d->idL[k];
+        int prev = -1;
+        for (long long r = 0; r < Nk; ++r) {
+            int s = id[r];
+            if (s < 0 || s >= n || s < prev || s > prev + 1) { delete h; return fail("jmb_create: idL must be 0-based, grouped by subject, every subject present"); }
+            prev = s;
+            rp[s + 1] += 1;
+        }
+        if (prev != n - 1) { delete h; return fail("jmb_create: idL does not cover every subject"); }
+        for (int i = 0; i < n; ++i) rp[i + 1] += rp[i];
+        for (int i = 0; i < n; ++i)
+            if (d->idL2[k][i] != rp[i + 1] - 1) { delete h; return fail("jmb_create: idL2 is not the last row of each subject"); }
+    }
+    if (d->idGK_fast)
+        for (int i = 0; i < n; ++i)
+            if (d->idGK_fast[i] != (i + 1) * K - 1) { delete h; return fail("jmb_create: idGK_fast must be (i+1)K-1"); }
+
+    // ---- band of the B-spline basis rows (splineDesign rows have `ord` contiguous non-zeros) ----
+    auto band_of = [&](const double* W, long long rows, long long r, int& first, int& last) {
+        first = B; last = -1;
+        for (int j = 0; j < B; ++j)
+            if (W[r + (long long)j * rows] != 0.0) { if (first == B) first = j; last = j; }
+    };
+    int WB = 1;
+    {
+        std::atomic<int> wmax{1};
+        auto scan = [&](const double* W, long long rows) {
+            parallel_for((int)std::min<long long>(rows, 2147483647LL), [&, W, rows](int lo, int hi) {
+                int m = 1;
+                for (long long r = lo; r < hi; ++r) { int f, l; band_of(W, rows, r, f, l); if (l >= f) m = std::max(m, l - f + 1); }
+                int cur = wmax.load();
+                while (m > cur && !wmax.compare_exchange_weak(cur, m)) {}
+            });
+        };
+        scan(d->W1, n); scan(d->W1s, ns);
+        if (S == 2) scan(d->W1s_int, ns);
+        WB = wmax.load();
+        if (WB > 8) WB = B;                 // not banded: keep the dense rows
+        WB = std::min(WB, B);
+    }
+    mm.WB = WB;
+
+    // ---- record layout ----
+    const int RP = mm.RP;
+    mm.o_R = 2;
+    int o = roundup(2 + q * (q + 1) / 2, 2);
+    mm.o_Pw = o; o += RP;
+    mm.o_W1off = o; o += RP / 2;
+    mm.o_W1v = o; o += WB * RP;
+    mm.o_W2 = o; o += p * RP;
+    for (int t = 0; t < T; ++t) { mm.o_ZZ[t] = o; o += mm.rt[t] * RP; mm.o_U[t] = o; o += mm.ut[t] * RP; }
+    mm.o_long = o;
+    mm.c_long = T * RP;
+
+    h->doff.assign(n + 1, 0);
+    h->coff.assign(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        long long dl = mm.o_long, cl = mm.c_long;
+        for (int k = 0; k < O; ++k) {
+            int v = h->rowptr[k][i + 1] - h->rowptr[k][i];
+            dl += (long long)v * (1 + mm.qk[k]);
+            cl += v;
+        }
+        h->doff[i + 1] = h->doff[i] + ((dl + 1) / 2) * 2;
+        h->coff[i + 1] = h->coff[i] + ((cl + 1) / 2) * 2;
+    }
+
+    // ---- pack the design records ----
+    std::vector<double> drec((size_t)h->doff[n], 0.0);
+    parallel_for(n, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            double* rec = drec.data() + h->doff[i];
+            rec[0] = d->event[i];
+            const double* Rm = d->Covs_b + (long long)i * q * q;
+            for (int j = 0; j < q; ++j)
+                for (int l = 0; l <= j; ++l) rec[mm.o_R + j * (j + 1) / 2 + l] = Rm[l + j * q];
+            int* w1off = reinterpret_cast<int*>(rec + mm.o_W1off);
+            for (int r = 0; r < RP; ++r) {
+                int cls = (r == 0) ? 0 : (r <= K ? 1 : ((S == 2 && r <= 2 * K) ? 2 : 3));
+                w1off[r] = 0;
+                if (cls == 3) continue;
+                const long long rows = cls == 0 ? n : ns;
+                const long long src = cls == 0 ? i : (cls == 1 ? (long long)i * K + (r - 1) : (long long)i * K + (r - 1 - K));
+                const double* W1x = cls == 0 ? d->W1 : (cls == 1 ? d->W1s : d->W1s_int);
+                const double* W2x = cls == 0 ? d->W2 : (cls == 1 ? d->W2s : d->W2s_int);
+                if (cls == 1) rec[mm.o_Pw + r] = d->Pw[src];
+                if (cls == 2) rec[mm.o_Pw + r] = d->Pw_int[src];
+                int f, l;
+                band_of(W1x, rows, src, f, l);
+                int off = (l < f) ? 0 : std::min(f, B - WB);
+                if (WB == B) off = 0;
+                w1off[r] = off;
+                for (int j = 0; j < WB; ++j) rec[mm.o_W1v + j * RP + r] = W1x[src + (long long)(off + j) * rows];
+                for (int j = 0; j < p; ++j) rec[mm.o_W2 + j * RP + r] = W2x[src + (long long)j * rows];
+                for (int t = 0; t < T; ++t) {
+                    const double* ZZx = cls == 0 ? d->ZZ[t] : (cls == 1 ? d->ZZs[t] : d->ZZs_int[t]);
+                    const double* Ux = cls == 0 ? d->U[t] : (cls == 1 ? d->Us[t] : d->Us_int[t]);
+                    for (int j = 0; j < mm.rt[t]; ++j) rec[mm.o_ZZ[t] + j * RP + r] = ZZx[src + (long long)j * rows];
+                    for (int u = 0; u < mm.ut[t]; ++u) rec[mm.o_U[t] + u * RP + r] = Ux[src + (long long)u * rows];
+                }
+            }
+            double* lrec = rec + mm.o_long;
+            for (int k = 0; k < O; ++k) {
+                const int r0 = h->rowptr[k][i], v = h->rowptr[k][i + 1] - r0;
+                const long long Nk = d->N[k];
+                for (int r = 0; r < v; ++r) lrec[r] = d->y[k][r0 + r];
+                for (int j = 0; j < mm.qk[k]; ++j)
+                    for (int r = 0; r < v; ++r) lrec[(1 + j) * v + r] = d->Z[k][r0 + r + (long long)j * Nk];
+                lrec += (1 + mm.qk[k]) * v;
+            }
+        }
+    });
+
+    // ---- device allocations ----
+    cudaError_t e;
+#define CUH(call) do { e = (call); if (e != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e); jmb_destroy(h); return fail(m_); } } while (0)
+    CUH(cudaSetDevice(device));
+    CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUH(cudaMalloc(&h->d_drec, sizeof(double) * std::max<size_t>(drec.size(), 2)));
+    CUH(cudaMalloc(&h->d_doff, sizeof(long long) * (n + 1)));
+    CUH(cudaMalloc(&h->d_crec, sizeof(double) * std::max<long long>(h->coff[n], 2)));
+    CUH(cudaMalloc(&h->d_coff, sizeof(long long) * (n + 1)));
+    CUH(cudaMalloc(&h->d_rowptr, sizeof(int) * (size_t)O * (n + 1)));
+    CUH(cudaMalloc(&h->d_state, sizeof(double) * (size_t)n * mm.state_stride));
+    CUH(cudaMalloc(&h->d_eval, sizeof(double) * (size_t)n * 6));
+    CUH(cudaMalloc(&h->d_tmp, sizeof(double) * (size_t)n * (q + 1)));
+    CUH(cudaMalloc(&h->d_ctl, sizeof(Ctl)));
+    CUH(cudaHostAlloc(&h->h_crec, sizeof(double) * std::max<long long>(h->coff[n], 2), cudaHostAllocDefault));
+    CUH(cudaHostAlloc(&h->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaHostAllocDefault));
+    CUH(cudaMemcpy(h->d_drec, drec.data(), sizeof(double) * drec.size(), cudaMemcpyHostToDevice));
+    CUH(cudaMemcpy(h->d_doff, h->doff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
+    CUH(cudaMemcpy(h->d_coff, h->coff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
+    for (int k = 0; k < O; ++k)
+        CUH(cudaMemcpy(h->d_rowptr + (size_t)k * (n + 1), h->rowptr[k].data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+    CUH(cudaMemset(h->d_state, 0, sizeof(double) * (size_t)n * mm.state_stride));
+    CUH(cudaMemset(h->d_ctl, 0, sizeof(Ctl)));
+
+    // parameter block (n_td capacity = JMB_MAX_TERMS)
+    build_param_layout(mm, JMB_MAX_TERMS, h->n_block_cap, h->pl);
+    CUH(cudaMalloc(&h->d_par, sizeof(double) * h->pl.total));
+    CUH(cudaMemset(h->d_par, 0, sizeof(double) * h->pl.total));
+    CUH(cudaHostAlloc(&h->h_par, sizeof(double) * h->pl.total, cudaHostAllocDefault));
+    memset(h->h_par, 0, sizeof(double) * h->pl.total);
+
+    // launch configuration: G lanes per subject, 256 threads, a few subjects per group per CTA
+    const int groups = 256 / mm.G;
+    h->subjects_per_cta = groups * 4;
+    h->grid = (n + h->subjects_per_cta - 1) / h->subjects_per_cta;
+    h->smem_bytes = (int)sizeof(double) * (2 * mm.P + q * q + O + groups * 3 * (q + 5) + groups * 3);
+    CUH(cudaMalloc(&h->d_partials, sizeof(double) * 3 * (size_t)h->grid));
+    CUH(cudaEventCreate(&h->ev0)); CUH(cudaEventCreate(&h->ev1));
+    CUH(cudaEventCreate(&h->evk0)); CUH(cudaEventCreate(&h->evk1));
+#undef CUH
+    *out = h;
+    return 0;
+}
+
+extern "C" int jmb_destroy(jmb_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    cudaFree(h->d_drec); cudaFree(h->d_doff); cudaFree(h->d_crec); cudaFree(h->d_coff); cudaFree(h->d_rowptr);
+    cudaFree(h->d_state); cudaFree(h->d_par); cudaFree(h->d_ctl); cudaFree(h->d_partials); cudaFree(h->d_eval);
+    cudaFree(h->d_tmp); cudaFree(h->o_b); cudaFree(h->o_par); cudaFree(h->o_trace);
+    if (h->h_crec) cudaFreeHost(h->h_crec);
+    if (h->h_par) cudaFreeHost(h->h_par);
+    if (h->h_tmp) cudaFreeHost(h->h_tmp);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evk0) cudaEventDestroy(h->evk0);
+    if (h->evk1) cudaEventDestroy(h->evk1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-draw vectors
+// ---------------------------------------------------------------------------------------------
+extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
+    if (!h || !w) return fail("jmb_set_draw: null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));        // the staging buffer may still be in flight
+    const ModelMeta& mm = h->mm;
+    const int n = h->n, K = mm.K, RP = mm.RP, S = mm.S, T = mm.T, O = mm.O;
+    if (S == 2 && !w->XXsbetas_int) return fail("jmb_set_draw: XXsbetas_int required with interval censoring");
+    double* base = h->h_crec;
+    parallel_for(n, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            double* rec = base + h->coff[i];
+            for (int t = 0; t < T; ++t) {
+                double* x = rec + t * RP;
+                x[0] = w->XXbetas[t][i];
+                for (int r = 1; r <= K; ++r) x[r] = w->XXsbetas[t][(long long)i * K + r - 1];
+                if (S == 2) for (int r = 1; r <= K; ++r) x[K + r] = w->XXsbetas_int[t][(long long)i * K + r - 1];
+                for (int r = 1 + K * S; r < RP; ++r) x[r] = 0.0;
+            }
+            double* l = rec + mm.c_long;
+            for (int k = 0; k < O; ++k) {
+                const int r0 = h->rowptr[k][i], v = h->rowptr[k][i + 1] - r0;
+                memcpy(l, w->Xbetas[k] + r0, sizeof(double) * v);
+                l += v;
+            }
+        }
+    });
+    CU(cudaMemcpyAsync(h->d_crec, h->h_crec, sizeof(double) * h->coff[n], cudaMemcpyHostToDevice, h->stream));
+    for (int j = 0; j < mm.q * mm.q; ++j) h->h_par[h->pl.invD + j] = w->invD[j];
+    for (int k = 0; k < O; ++k) h->h_par[h->pl.sigmas + k] = (mm.fam[k] == JMB_FAM_GAUSSIAN) ? w->sigmas[k] : 1.0;
+    CU(cudaMemcpyAsync(h->d_par + h->pl.invD, h->h_par + h->pl.invD, sizeof(double) * (mm.q * mm.q + O), cudaMemcpyHostToDevice, h->stream));
+    h->draw_set = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+static int launch_step(jmb_handle h, int mode) {
+    StepArgs a{};
+    a.drec = h->d_drec; a.doff = h->d_doff; a.crec = h->d_crec; a.coff = h->d_coff; a.rowptr = h->d_rowptr;
+    a.state = h->d_state; a.par = h->d_par; a.ctl = h->d_ctl; a.partials = h->d_partials; a.eval_out = h->d_eval;
+    a.n = h->n; a.subject_offset = h->subject_offset; a.mode = mode; a.subjects_per_cta = h->subjects_per_cta;
+    if (h->mm.G == 16)
+        jmb_step_kernel<16><<<h->grid, 256, h->smem_bytes, h->stream>>>(h->mm, h->pl, h->cc, a);
+    else
+        jmb_step_kernel<32><<<h->grid, 256, h->smem_bytes, h->stream>>>(h->mm, h->pl, h->cc, a);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int launch_finalize(jmb_handle h, int phase) {
+    FinalizeArgs a = h->fa;
+    a.par = h->d_par; a.ctl = h->d_ctl; a.partials = h->d_partials; a.n_partials = h->grid;
+    a.use_reduced = (h->nranks > 1) ? 1 : 0; a.phase = phase;
+    if (phase == 0 && h->nranks > 1) {
+        jmb_reduce_partials_kernel<<<1, 128, 0, h->stream>>>(h->d_partials, h->grid, h->d_par + h->pl.sums);
+        h->launches += 1;
+        CU(cudaGetLastError());
+        ncclResult_t rc = g_nccl.AllReduce(h->d_par + h->pl.sums, h->d_par + h->pl.sums, 3, ncclDouble, ncclSum, h->comm, h->stream);
+        if (rc != ncclSuccess) return fail(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    }
+    jmb_finalize_kernel<<<1, 128, 0, h->stream>>>(h->mm, h->pl, h->cc, a);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// chain
+// ---------------------------------------------------------------------------------------------
+extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_control* ct, const jmb_chain_in* in) {
+    if (!h || !pr || !ct || !in) return fail("jmb_chain_begin: null argument");
+    if (!h->draw_set) return fail("jmb_chain_begin: call jmb_set_draw first");
+    CU(cudaSetDevice(h->device));
+    const ModelMeta& mm = h->mm;
+    const ParamLayout& pl = h->pl;
+    const int n = h->n, q = mm.q, B = mm.B, p = mm.p, A = mm.A;
+    if (ct->n_block <= 0 || ct->n_block > h->n_block_cap) return fail("jmb_chain_begin: n_block out of range (1..1024)");
+    if (ct->n_iter < 0 || ct->n_burnin < 0 || ct->n_thin <= 0) return fail("jmb_chain_begin: bad control");
+    if (pr->n_td < 0 || pr->n_td > JMB_MAX_TERMS) return fail("jmb_chain_begin: too many td effects");
+    ChainConst& cc = h->cc;
+    memset(&cc, 0, sizeof(cc));
+    cc.n_iter = ct->n_iter; cc.n_burnin = ct->n_burnin; cc.n_block = ct->n_block; cc.n_thin = ct->n_thin;
+    const int total_it = ct->n_iter + ct->n_burnin;
+    const int its = (int)std::ceil((double)total_it / ct->n_block);
+    cc.n_out = (int)std::floor((double)ct->n_iter / ct->n_thin);
+    cc.n_keep = 0;
+    for (int v = ct->n_burnin + 1; v <= total_it; v += ct->n_thin) cc.n_keep += 1;
+    cc.start_cov_update = (int)std::floor((double)ct->n_burnin / ct->n_block) - 1;
+    cc.adaptCov = ct->adaptCov;
+    cc.target_acc = ct->target_acc; cc.eps1 = ct->eps1; cc.eps2 = ct->eps2; cc.eps3 = ct->eps3;
+    cc.c0 = ct->c0; cc.mc1 = -ct->c1; cc.seed = ct->seed; cc.chain_id = ct->chain_id;
+    cc.B_tau_Bs = pr->B_tau_Bs_gammas; cc.Apost_tau_Bs = pr->A_tau_Bs_gammas + 0.5 * pr->rank_Tau_Bs_gammas;
+    cc.shrink_gammas = pr->shrink_gammas; cc.B_tau_g = pr->B_tau_gammas;
+    cc.Apost_tau_g = pr->A_tau_gammas + 0.5 * pr->rank_Tau_gammas;
+    cc.B_phi_g = pr->B_phi_gammas; cc.Apost_phi_g = pr->A_phi_gammas + 0.5;
+    cc.shrink_alphas = pr->shrink_alphas; cc.double_gamma_alphas = pr->double_gamma_alphas;
+    cc.B_tau_a = pr->B_tau_alphas; cc.Apost_tau_a = pr->A_tau_alphas + 0.5 * pr->rank_Tau_alphas;
+    cc.B_phi_a = pr->B_phi_alphas; cc.Apost_phi_a = pr->A_phi_alphas + 0.5;
+    cc.B_xi_a = pr->B_xi_alphas; cc.Apost_xi_a = pr->A_xi_alphas + 0.5;
+    cc.B_nu_a = pr->B_nu_alphas; cc.Apost_nu_a = pr->A_nu_alphas + 0.5;
+    cc.n_td = pr->n_td; cc.B_tau_td = pr->B_tau_Bs_gammas;
+    cc.Apost_tau_td = pr->A_tau_Bs_gammas + 0.5 * pr->rank_Tau_td_alphas;
+    for (int k = 0; k < pr->n_td; ++k) {
+        cc.td_len[k] = pr->td_len[k];
+        if (cc.td_len[k] > JMB_MAX_UT) return fail("jmb_chain_begin: td block too wide");
+        for (int j = 0; j < cc.td_len[k]; ++j) cc.td_cols[k][j] = pr->td_cols[k][j];
+    }
+    h->n_out = cc.n_out; h->n_td = pr->n_td;
+    h->total_iters = its * ct->n_block;
+    h->iter_host = 0; h->keep_host = 0; h->check_host = 0;
+
+    CU(cudaStreamSynchronize(h->stream));
+    double* hp = h->h_par;
+    memcpy(hp + pl.cur, in->Bs_gammas, sizeof(double) * B);
+    if (p) memcpy(hp + pl.cur + B, in->gammas, sizeof(double) * p);
+    memcpy(hp + pl.cur + B + p, in->alphas, sizeof(double) * A);
+    memcpy(hp + pl.prop, hp + pl.cur, sizeof(double) * mm.P);
+    hp[pl.tau_Bs] = in->tau_Bs_gammas[0]; hp[pl.tau_g] = in->tau_gammas; hp[pl.tau_a] = in->tau_alphas;
+    hp[pl.xi_a] = in->tau_alphas;                                        // src/fast_LAPRWM.cpp:518
+    for (int j = 0; j < p; ++j) hp[pl.phi_g + j] = in->phi_gammas[j];
+    for (int j = 0; j < A; ++j) { hp[pl.phi_a + j] = in->phi_alphas[j]; hp[pl.nu_a + j] = in->phi_alphas[j]; }   // :513
+    for (int j = 0; j < pr->n_td; ++j) hp[pl.tau_td + j] = in->tau_td_alphas[j];
+    if (p) memcpy(hp + pl.Tau_g, pr->Tau_gammas, sizeof(double) * p * p);
+    memcpy(hp + pl.Tau_a, pr->Tau_alphas, sizeof(double) * A * A);
+    memcpy(hp + pl.Tau_a_pen, pr->Tau_alphas, sizeof(double) * A * A);
+    hp[pl.sig] = in->sigma_Bs_gammas; hp[pl.sig + 1] = in->sigma_gammas; hp[pl.sig + 2] = in->sigma_alphas;
+    memcpy(hp + pl.S_Bs, in->Sigma_Bs_gammas, sizeof(double) * B * B);
+    if (p) memcpy(hp + pl.S_g, in->Sigma_gammas, sizeof(double) * p * p);
+    memcpy(hp + pl.S_a, in->Sigma_alphas, sizeof(double) * A * A);
+    memcpy(hp + pl.mean_Bs, pr->mean_Bs_gammas, sizeof(double) * B);
+    memcpy(hp + pl.Tau_Bs, pr->Tau_Bs_gammas, sizeof(double) * B * B);
+    if (p) memcpy(hp + pl.mean_g, pr->mean_gammas, sizeof(double) * p);
+    memcpy(hp + pl.mean_a, pr->mean_alphas, sizeof(double) * A);
+    CU(cudaMemcpyAsync(h->d_par, hp, sizeof(double) * pl.block_par, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->d_ctl, 0, sizeof(Ctl), h->stream));
+
+    // outputs on the device
+    cudaFree(h->o_b); cudaFree(h->o_par); cudaFree(h->o_trace);
+    h->o_b = h->o_par = h->o_trace = nullptr;
+    const int no = std::max(cc.n_out, 1);
+    const size_t par_out = (size_t)no * (B + 2 * p + 2 * A + 4 + JMB_MAX_TERMS);
+    CU(cudaMalloc(&h->o_b, sizeof(double) * (size_t)n * q * no));
+    CU(cudaMalloc(&h->o_par, sizeof(double) * par_out));
+    CU(cudaMemsetAsync(h->o_b, 0, sizeof(double) * (size_t)n * q * no, h->stream));
+    CU(cudaMemsetAsync(h->o_par, 0, sizeof(double) * par_out, h->stream));
+    CU(cudaMalloc(&h->o_trace, sizeof(double) * 2 * (size_t)std::max(h->total_iters, 1)));
+    CU(cudaMemsetAsync(h->o_trace, 0, sizeof(double) * 2 * (size_t)std::max(h->total_iters, 1), h->stream));
+    FinalizeArgs& fa = h->fa;
+    memset(&fa, 0, sizeof(fa));
+    double* o = h->o_par;
+    fa.o_Bs = o; o += (size_t)no * B;
+    fa.o_g = o; o += (size_t)no * p;
+    fa.o_a = o; o += (size_t)no * A;
+    fa.o_phi_g = o; o += (size_t)no * p;
+    fa.o_phi_a = o; o += (size_t)no * A;
+    fa.o_tau_Bs = o; o += no; fa.o_tau_g = o; o += no; fa.o_tau_a = o; o += no;
+    fa.o_tau_td = o; o += (size_t)no * JMB_MAX_TERMS;
+    fa.o_lw = o;
+    fa.trace = h->o_trace;
+
+    // state <- initials$b, scales$b
+    memcpy(h->h_tmp, in->b, sizeof(double) * (size_t)n * q);
+    memcpy(h->h_tmp + (size_t)n * q, in->sigma_b, sizeof(double) * n);
+    CU(cudaMemcpyAsync(h->d_tmp, h->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaMemcpyHostToDevice, h->stream));
+    {
+        const long long tot = (long long)n * mm.state_stride;
+        jmb_load_state_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.state_stride, n, q, h->d_tmp, h->d_tmp + (size_t)n * q);
+        h->launches += 1;
+        CU(cudaGetLastError());
+    }
+    if (launch_finalize(h, 1)) return 1;            // Cholesky factors + proposal of iteration 0
+    if (launch_step(h, MODE_INIT)) return 1;        // log_pyb / log_pb at the initial b (:619-621)
+    h->chain_open = true;
+    return 0;
+}
+
+static bool is_keep_iter(const jmb_handle h, int iter) {
+    const ChainConst& cc = h->cc;
+    return h->check_host < cc.n_keep && h->keep_host < cc.n_out && iter == cc.n_burnin + 1 + h->check_host * cc.n_thin;
+}
+
+extern "C" int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, float* step_kernel_ms) {
+    if (!h || !h->chain_open) return fail("jmb_chain_iterate: no open chain");
+    CU(cudaSetDevice(h->device));
+    const ModelMeta& mm = h->mm;
+    float kms = 0.f;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    for (int k = 0; k < iters; ++k) {
+        if (step_kernel_ms) CU(cudaEventRecord(h->evk0, h->stream));
+        if (launch_step(h, MODE_STEP)) return 1;
+        if (step_kernel_ms) {
+            CU(cudaEventRecord(h->evk1, h->stream));
+            CU(cudaEventSynchronize(h->evk1));
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, h->evk0, h->evk1));
+            kms += t;
+        }
+        if (launch_finalize(h, 0)) return 1;
+        if (is_keep_iter(h, h->iter_host)) {
+            const long long tot = (long long)h->n * mm.q;
+            jmb_extract_b_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
+                h->d_state, mm.state_stride, h->n, mm.q, 0, h->o_b + (size_t)h->keep_host * h->n * mm.q);
+            h->launches += 1;
+            CU(cudaGetLastError());
+            h->keep_host += 1; h->check_host += 1;
+        }
+        h->iter_host += 1;
+    }
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+    if (step_kernel_ms) *step_kernel_ms = kms;
+    Ctl c;
+    CU(cudaMemcpy(&c, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    if (c.error) return fail("jmb_chain_iterate: proposal covariance is not positive definite");
+    return 0;
+}
+
+extern "C" int jmb_chain_end(jmb_handle h, jmb_chain_out* out) {
+    if (!h || !h->chain_open) return fail("jmb_chain_end: no open chain");
+    CU(cudaSetDevice(h->device));
+    const ModelMeta& mm = h->mm;
+    const ParamLayout& pl = h->pl;
+    const int n = h->n, q = mm.q, B = mm.B, p = mm.p, A = mm.A, no = h->n_out;
+    CU(cudaStreamSynchronize(h->stream));
+    h->chain_open = false;
+    if (!out) return 0;
+    const FinalizeArgs& fa = h->fa;
+    auto d2h = [&](double* dst, const double* src, size_t len) -> cudaError_t {
+        if (!dst || len == 0) return cudaSuccess;
+        return cudaMemcpy(dst, src, sizeof(double) * len, cudaMemcpyDeviceToHost);
+    };
+    CU(d2h(out->b, h->o_b, (size_t)n * q * no));
+    CU(d2h(out->Bs_gammas, fa.o_Bs, (size_t)B * no));
+    CU(d2h(out->gammas, fa.o_g, (size_t)p * no));
+    CU(d2h(out->alphas, fa.o_a, (size_t)A * no));
+    CU(d2h(out->phi_gammas, fa.o_phi_g, (size_t)p * no));
+    CU(d2h(out->phi_alphas, fa.o_phi_a, (size_t)A * no));
+    CU(d2h(out->tau_Bs_gammas, fa.o_tau_Bs, no));
+    CU(d2h(out->tau_gammas, fa.o_tau_g, no));
+    CU(d2h(out->tau_alphas, fa.o_tau_a, no));
+    CU(d2h(out->tau_td_alphas, fa.o_tau_td, (size_t)h->n_td * no));
+    CU(d2h(out->logWeights, fa.o_lw, no));
+    CU(d2h(out->sigma_surv, h->d_par + pl.sig, 3));
+    CU(d2h(out->Sigma_Bs_gammas, h->d_par + pl.S_Bs, (size_t)B * B));
+    CU(d2h(out->Sigma_gammas, h->d_par + pl.S_g, (size_t)p * p));
+    CU(d2h(out->Sigma_alphas, h->d_par + pl.S_a, (size_t)A * A));
+    CU(d2h(out->trace_surv, h->o_trace, 2 * (size_t)h->iter_host));
+    if (out->sigma_b || out->accept_b) {
+        // columns q (sigma_b) and q+4 (total accepts) of the state
+        jmb_extract_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.state_stride, n, 1, q, h->d_tmp);
+        jmb_extract_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.state_stride, n, 1, q + 4, h->d_tmp + n);
+        h->launches += 2;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        CU(d2h(out->sigma_b, h->d_tmp, n));
+        if (out->accept_b) {
+            CU(d2h(out->accept_b, h->d_tmp + n, n));
+            for (int i = 0; i < n; ++i) out->accept_b[i] /= std::max(h->iter_host, 1);
+        }
+    }
+    if (out->accept_surv) {
+        Ctl c;
+        CU(cudaMemcpy(&c, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+        out->accept_surv[0] = (double)c.accept_s_total / std::max(h->iter_host, 1);
+    }
+    return 0;
+}
+
+extern "C" int jmb_lap_rwm(jmb_handle h, const jmb_priors* pr, const jmb_control* ct, const jmb_chain_in* in, jmb_chain_out* out) {
+    if (jmb_chain_begin(h, pr, ct, in)) return 1;
+    if (jmb_chain_iterate(h, h->total_iters, nullptr, nullptr)) return 1;
+    return jmb_chain_end(h, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity probe
+// ---------------------------------------------------------------------------------------------
+extern "C" int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* Bs, const double* gam,
+                                   const double* alp, jmb_eval_out* out) {
+    if (!h || !b || !out) return fail("jmb_eval_logpost_re: null argument");
+    if (!h->draw_set) return fail("jmb_eval_logpost_re: call jmb_set_draw first");
+    if (h->chain_open) return fail("jmb_eval_logpost_re: a chain is open on this handle");
+    CU(cudaSetDevice(h->device));
+    const ModelMeta& mm = h->mm;
+    const ParamLayout& pl = h->pl;
+    const int n = h->n, q = mm.q, B = mm.B, p = mm.p, A = mm.A;
+    CU(cudaStreamSynchronize(h->stream));
+    double* hp = h->h_par;
+    memcpy(hp + pl.cur, Bs, sizeof(double) * B);
+    if (p) memcpy(hp + pl.cur + B, gam, sizeof(double) * p);
+    memcpy(hp + pl.cur + B + p, alp, sizeof(double) * A);
+    memcpy(hp + pl.prop, hp + pl.cur, sizeof(double) * mm.P);
+    CU(cudaMemcpyAsync(h->d_par + pl.cur, hp + pl.cur, sizeof(double) * 2 * mm.P, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->d_ctl, 0, sizeof(Ctl), h->stream));
+    memcpy(h->h_tmp, b, sizeof(double) * (size_t)n * q);
+    for (int i = 0; i < n; ++i) h->h_tmp[(size_t)n * q + i] = 1.0;
+    CU(cudaMemcpyAsync(h->d_tmp, h->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaMemcpyHostToDevice, h->stream));
+    const long long tot = (long long)n * mm.state_stride;
+    jmb_load_state_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.state_stride, n, q, h->d_tmp, h->d_tmp + (size_t)n * q);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    memset(&h->cc, 0, sizeof(h->cc));
+    h->cc.n_block = 1;
+    if (launch_step(h, MODE_EVAL)) return 1;
+    CU(cudaStreamSynchronize(h->stream));
+    double* dst[6] = {out->log_pyb, out->log_pb, out->log_h, out->H, out->HL, out->log_ptb};
+    for (int k = 0; k < 6; ++k)
+        if (dst[k]) CU(cudaMemcpy(dst[k], h->d_eval + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int jmb_get_row_ptr(jmb_handle h, int outcome, int64_t* row_ptr) {
+    if (!h || outcome < 0 || outcome >= h->mm.O) return fail("jmb_get_row_ptr: bad argument");
+    std::vector<int> rp(h->n + 1);
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpy(rp.data(), h->d_rowptr + (size_t)outcome * (h->n + 1), sizeof(int) * (h->n + 1), cudaMemcpyDeviceToHost));
+    for (int i = 0; i <= h->n; ++i) row_ptr[i] = rp[i];
+    return 0;
+}
+
+extern "C" int jmb_layout_info(jmb_handle h, double* shared_bytes, double* chain_bytes, int32_t* w1_band, int32_t* group_lanes) {
+    if (!h) return fail("jmb_layout_info: null handle");
+    const double n = h->n;
+    if (shared_bytes) *shared_bytes = (8.0 * h->doff[h->n] + 8.0 * 2 * (h->n + 1) + 4.0 * h->mm.O * (h->n + 1)) / n;
+    if (chain_bytes) *chain_bytes = 8.0 * h->coff[h->n] / n + 2.0 * 8.0 * h->mm.state_stride;
+    if (w1_band) *w1_band = h->mm.WB;
+    if (group_lanes) *group_lanes = h->mm.G;
+    return 0;
+}
+
+extern "C" int jmb_launch_count(jmb_handle h, int64_t* launches) {
+    if (!h) return fail("jmb_launch_count: null handle");
+    *launches = h->launches;
+    return 0;
+}
+
+extern "C" void* jmb_stream(jmb_handle h) { return h ? (void*)h->stream : nullptr; }
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------------------------
+extern "C" int jmb_comm_unique_id(char id[128]) {
+    if (load_nccl()) return 1;
+    ncclUniqueId uid;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (g_nccl.GetUniqueId(&uid) != ncclSuccess) return fail("ncclGetUniqueId failed");
+    memcpy(id, &uid, 128);
+    return 0;
+}
+
+extern "C" int jmb_comm_init(jmb_handle h, int nranks, int rank, const char id[128]) {
+    if (!h) return fail("jmb_comm_init: null handle");
+    if (nranks <= 1) { h->nranks = 1; h->rank = 0; return 0; }
+    if (load_nccl()) return 1;
+    CU(cudaSetDevice(h->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    ncclResult_t rc = g_nccl.CommInitRank(&h->comm, nranks, uid, rank);
+    if (rc != ncclSuccess) return fail(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    h->nranks = nranks; h->rank = rank;
+    return 0;
+}

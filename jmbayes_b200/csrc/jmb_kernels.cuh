@@ -1,0 +1,516 @@
+// jmb_kernels.cuh - the sm_100a kernels of the mvJointModelBayes MCMC iteration.
+//
+// One MCMC iteration (src/fast_LAPRWM.cpp:666-851) is two launches:
+//   jmb_step_kernel     - per subject: proposal, GLMM log-density over the visit segment, log-hazard
+//                         and Gauss-Kronrod cumulative hazard under the current AND the proposed
+//                         survival parameters, accept/reject, scale adaptation, and the subject's
+//                         contribution to the three global sums.  b_i lives in shared memory /
+//                         registers between proposal and acceptance; nothing but the new state
+//                         (q + 5 doubles) is written back.
+//   jmb_finalize_kernel - one CTA: deterministic reduction of the per-CTA partial sums, the
+//                         survival-block accept/reject, the Gibbs draws of the precisions, output
+//                         of kept iterations, adaptation at block ends, next survival proposal.
+// No host round trip is needed inside a chain.
+#pragma once
+#include "jmb_device.cuh"
+
+namespace jmb {
+
+enum { MODE_STEP = 0, MODE_INIT = 1, MODE_EVAL = 2 };
+
+struct StepArgs {
+    const double* drec;      // per-subject design records (shared by all chains of a fit)
+    const long long* doff;   // [n+1] offsets into drec (doubles)
+    const double* crec;      // per-subject per-draw records
+    const long long* coff;   // [n+1]
+    const int* rowptr;       // [O][n+1] CSR row pointers of the longitudinal outcomes
+    double* state;           // [n][state_stride]
+    const double* par;       // chain parameter block
+    const Ctl* ctl;
+    double* partials;        // [gridDim.x][3]
+    double* eval_out;        // MODE_EVAL: [6][n] log_pyb, log_pb, log_h, H, HL, log_ptb
+    int n;
+    long long subject_offset;
+    int mode;
+    int subjects_per_cta;
+};
+
+// -------------------------------------------------------------------------------------------
+// step kernel: G lanes per subject
+// -------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ ParamLayout pl,
+                const __grid_constant__ ChainConst cc, const __grid_constant__ StepArgs a) {
+    constexpr int THREADS = 256;
+    constexpr int GROUPS = THREADS / G;
+    // [cur P][prop P][invD q*q][inv_sigma O]
+    extern __shared__ double smem[];
+    double* s_cur = smem;
+    double* s_prop = s_cur + mm.P;
+    double* s_invD = s_prop + mm.P;
+    double* s_isig = s_invD + mm.q * mm.q;
+    double* s_grp = s_isig + mm.O;                         // per group: b_old[QS], b_new[QS], z[QS]
+    const int QS = mm.q + 5;
+    double* s_red = s_grp + GROUPS * 3 * QS;                // [GROUPS][3]
+
+    const int tid = threadIdx.x;
+    for (int j = tid; j < mm.P; j += THREADS) { s_cur[j] = a.par[pl.cur + j]; s_prop[j] = a.par[pl.prop + j]; }
+    for (int j = tid; j < mm.q * mm.q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
+    for (int j = tid; j < mm.O; j += THREADS) s_isig[j] = 1.0 / a.par[pl.sigmas + j];
+    const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i;
+    __syncthreads();
+
+    const int grp = tid / G, lane = tid % G;
+    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (0xFFFFu << (16 * ((tid & 31) >> 4)));
+    double* bo = s_grp + grp * 3 * QS;
+    double* bn = bo + QS;
+    double* zb = bn + QS;
+    const int q = mm.q, RP = mm.RP, K = mm.K, S = mm.S;
+    const bool last_in_block = (i_blk == cc.n_block - 1);
+
+    double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;     // lane 0 of each group
+    const int s_begin = blockIdx.x * a.subjects_per_cta;
+    const int s_end = min(a.n, s_begin + a.subjects_per_cta);
+
+    for (int s = s_begin + grp; s < s_end; s += GROUPS) {
+        const double* rec = a.drec + a.doff[s];
+        const double* crec = a.crec + a.coff[s];
+        double* st = a.state + (long long)s * mm.state_stride;
+        const uint32_t gid = (uint32_t)(a.subject_offset + s);
+
+        // ---- state + proposal (mvrnorm_cube / extract_b, src/fast_LAPRWM.cpp:123-146,670) ----
+        for (int j = lane; j < QS; j += G) bo[j] = st[j];
+        if (a.mode == MODE_STEP) {
+            for (int j = lane; j < q; j += G) {
+                double z0, z1;
+                rnorm_pair(cc.seed, cc.chain_id, gid, (uint32_t)iter, (uint32_t)(j >> 1), ST_B_PROP, z0, z1);
+                zb[j] = (j & 1) ? z1 : z0;
+            }
+        }
+        __syncwarp(gmask);
+        const double sigma_b = bo[q], pyb_old = bo[q + 1], pb_old = bo[q + 2];
+        if (a.mode == MODE_STEP) {
+            const double sd = sqrt(sigma_b);
+            for (int j = lane; j < q; j += G) {
+                const double* Rj = rec + mm.o_R + (j * (j + 1)) / 2;    // column j of the upper factor
+                double pj = 0.0;
+                for (int l = 0; l <= j; ++l) pj += zb[l] * Rj[l];
+                bn[j] = bo[j] + sd * pj;
+            }
+        } else {
+            for (int j = lane; j < q; j += G) bn[j] = bo[j];
+        }
+        __syncwarp(gmask);
+
+        // ---- log p(b) for the proposal: -0.5 b' invD b (src/fast_LAPRWM.cpp:673) ----
+        double v_pb = 0.0;
+        for (int j = lane; j < q; j += G) {
+            double t = 0.0;
+            for (int l = 0; l < q; ++l) t += bn[l] * s_invD[l + j * q];
+            v_pb += t * bn[j];
+        }
+
+        // ---- GLMM log-density over the visit segment (lin_predF + log_longF, :67-78,168-202) ----
+        double v_pyb = 0.0;
+        {
+            const double* lrec = rec + mm.o_long;
+            const double* lcrec = crec + mm.c_long;
+            for (int k = 0; k < mm.O; ++k) {
+                const int* rp = a.rowptr + (long long)k * (a.n + 1);
+                const int v = rp[s + 1] - rp[s];
+                const int qk = mm.qk[k], fam = mm.fam[k], link = mm.link[k];
+                const double isg = s_isig[k];
+                for (int r = lane; r < v; r += G) {
+                    double eta_z = 0.0;
+                    for (int j = 0; j < qk; ++j) eta_z += lrec[(1 + j) * v + r] * bn[mm.re_inds[k][j]];
+                    v_pyb += row_logdens(fam, link, lrec[r], lcrec[r] + eta_z, isg);
+                }
+                lrec += (1 + qk) * v;
+                lcrec += v;
+            }
+        }
+
+        // ---- hazard rows: row 0 = event time, 1..K quadrature, K+1..2K lower-interval quadrature
+        //      (lin_pred_matF :80-109, log_h :684, H/HL :685-691; survival step :735-741) ----
+        // One row per lane (RP == G is enforced at jmb_create).
+        const int r = lane;
+        const int cls = (r == 0) ? 0 : (r <= K ? 1 : ((S == 2 && r <= 2 * K) ? 2 : 3));
+        double l_co, l_cn, l_po, l_pn;                       // current/proposed params x old/new b
+        {
+            const int off = reinterpret_cast<const int*>(rec + mm.o_W1off)[r];
+            double s1c = 0.0, s1p = 0.0;
+            for (int j = 0; j < mm.WB; ++j) {
+                const double wv = rec[mm.o_W1v + j * RP + r];
+                s1c += wv * s_cur[off + j];
+                s1p += wv * s_prop[off + j];
+            }
+            double s2c = 0.0, s2p = 0.0;
+            for (int j = 0; j < mm.p; ++j) {
+                const double wv = rec[mm.o_W2 + j * RP + r];
+                s2c += wv * s_cur[mm.B + j];
+                s2p += wv * s_prop[mm.B + j];
+            }
+            double a_co = 0.0, a_cn = 0.0, a_po = 0.0, a_pn = 0.0;
+            const double* alc = s_cur + mm.B + mm.p;
+            const double* alp = s_prop + mm.B + mm.p;
+            for (int t = 0; t < mm.T; ++t) {
+                const double xxb = crec[t * RP + r];
+                double zo = 0.0, zn = 0.0;
+                for (int j = 0; j < mm.rt[t]; ++j) {
+                    const double zz = rec[mm.o_ZZ[t] + j * RP + r];
+                    zo += zz * bo[mm.re2[t][j]];
+                    zn += zz * bn[mm.re2[t][j]];
+                }
+                const double vo = trans_fun(mm.tf[t], xxb + zo), vn = trans_fun(mm.tf[t], xxb + zn);
+                for (int u = 0; u < mm.ut[t]; ++u) {
+                    const double uu = rec[mm.o_U[t] + u * RP + r];
+                    const int c = mm.col[t][u];
+                    const double wo = uu * vo, wn = uu * vn;
+                    a_co += wo * alc[c]; a_cn += wn * alc[c];
+                    a_po += wo * alp[c]; a_pn += wn * alp[c];
+                }
+            }
+            l_co = (s1c + s2c) + a_co; l_cn = (s1c + s2c) + a_cn;
+            l_po = (s1p + s2p) + a_po; l_pn = (s1p + s2p) + a_pn;
+        }
+        const double pw = (cls == 1 || cls == 2) ? rec[mm.o_Pw + r] : 0.0;
+        double H_co = 0.0, H_cn = 0.0, HL_co = 0.0, HL_cn = 0.0;
+        if (cls == 1) { H_co = pw * exp(l_co); H_cn = pw * exp(l_cn); }
+        else if (cls == 2) { HL_co = pw * exp(l_co); HL_cn = pw * exp(l_cn); }
+        double h_co = l_co, h_cn = l_cn, h_po = l_po, h_pn = l_pn;   // meaningful on lane 0 only
+        v_pyb = group_sum<G>(v_pyb, gmask);
+        v_pb = -0.5 * group_sum<G>(v_pb, gmask);
+        H_co = group_sum<G>(H_co, gmask);
+        H_cn = group_sum<G>(H_cn, gmask);
+        if (S == 2) { HL_co = group_sum<G>(HL_co, gmask); HL_cn = group_sum<G>(HL_cn, gmask); }
+        const int src0 = (tid & 31) - lane;                 // lane 0 of this group inside the warp
+        h_co = __shfl_sync(gmask, h_co, src0); h_cn = __shfl_sync(gmask, h_cn, src0);
+        h_po = __shfl_sync(gmask, h_po, src0); h_pn = __shfl_sync(gmask, h_pn, src0);
+
+        const double event = rec[0];
+        const double ptb_co = log_ptb_term(S, event, h_co, H_co, HL_co);
+        const double ptb_cn = log_ptb_term(S, event, h_cn, H_cn, HL_cn);
+
+        bool accept;
+        double pyb_new = v_pyb, pb_new = v_pb;
+        if (a.mode == MODE_STEP) {
+            const double cur_lp = pyb_old + ptb_co + pb_old;          // :669
+            const double new_lp = pyb_new + ptb_cn + pb_new;          // :703
+            const double lu = log_unif(cc.seed, cc.chain_id, gid, (uint32_t)iter, 0u, ST_B_ACC);
+            accept = lu < (new_lp - cur_lp);                          // :706 (NaN rejects)
+        } else {
+            accept = true;
+        }
+        // ---- proposed survival parameters at the accepted b (:735-752) ----
+        double Hp = 0.0, HLp = 0.0;
+        if (cls == 1) Hp = pw * exp(accept ? l_pn : l_po);
+        else if (cls == 2) HLp = pw * exp(accept ? l_pn : l_po);
+        Hp = group_sum<G>(Hp, gmask);
+        if (S == 2) HLp = group_sum<G>(HLp, gmask);
+        const double ptb_c = accept ? ptb_cn : ptb_co;
+        const double ptb_p = log_ptb_term(S, event, accept ? h_pn : h_po, Hp, HLp);
+        const double pyb_acc = accept ? pyb_new : pyb_old;
+        const double pb_acc = accept ? pb_new : pb_old;
+        acc_cur += ptb_c; acc_prop += ptb_p; acc_lw += pyb_acc + pb_acc;
+
+        // ---- write back (:707-724) + per-subject scale adaptation at block ends (:853-859) ----
+        if (a.mode == MODE_EVAL) {
+            if (lane == 0) {
+                a.eval_out[s] = pyb_new; a.eval_out[a.n + s] = pb_new;
+                a.eval_out[2LL * a.n + s] = h_cn; a.eval_out[3LL * a.n + s] = H_cn;
+                a.eval_out[4LL * a.n + s] = (S == 2) ? HL_cn : H_cn;
+                a.eval_out[5LL * a.n + s] = ptb_cn;
+            }
+        } else {
+            double accb = bo[q + 3] + ((a.mode == MODE_STEP && accept) ? 1.0 : 0.0);
+            double acct = bo[q + 4] + ((a.mode == MODE_STEP && accept) ? 1.0 : 0.0);
+            double sig_new = sigma_b;
+            if (a.mode == MODE_STEP && last_in_block) {
+                const double g2 = cc.c0 * pow((double)(it_blk + 1), cc.mc1);
+                const double rate = accb / cc.n_block;
+                sig_new = exp(log(sigma_b) + g2 * (rate - cc.target_acc));
+                sig_new = fmin(fmax(sig_new, cc.eps1), cc.eps3);       // bounds_sigma :411-419
+                accb = 0.0;
+            }
+            for (int j = lane; j < QS; j += G) {
+                double val;
+                if (j < q) val = accept ? bn[j] : bo[j];
+                else if (j == q) val = sig_new;
+                else if (j == q + 1) val = pyb_acc;
+                else if (j == q + 2) val = pb_acc;
+                else if (j == q + 3) val = accb;
+                else val = acct;
+                st[j] = val;
+            }
+        }
+        __syncwarp(gmask);
+    }
+
+    // ---- deterministic per-CTA partial sums ----
+    if (lane == 0) { s_red[grp * 3] = acc_cur; s_red[grp * 3 + 1] = acc_prop; s_red[grp * 3 + 2] = acc_lw; }
+    __syncthreads();
+    if (tid < 3) {
+        double t = 0.0;
+        for (int g = 0; g < GROUPS; ++g) t += s_red[g * 3 + tid];
+        a.partials[blockIdx.x * 3 + tid] = t;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// helpers for the finalize kernel (single CTA, thread 0 does the scalar logic)
+// -------------------------------------------------------------------------------------------
+__device__ inline double quad_form_dev(const double* x, const double* mean, const double* Tau, int m) {
+    double s = 0.0;
+    for (int j = 0; j < m; ++j) {
+        double t = 0.0;
+        for (int l = 0; l < m; ++l) t += (x[l] - (mean ? mean[l] : 0.0)) * Tau[l + j * m];
+        s += t * (x[j] - (mean ? mean[j] : 0.0));
+    }
+    return s;
+}
+
+__device__ inline int chol_upper_dev(const double* Sg, int m, double* H) {
+    for (int e = 0; e < m * m; ++e) H[e] = 0.0;
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i <= j; ++i) {
+            double s = Sg[i + j * m];
+            for (int k = 0; k < i; ++k) s -= H[k + i * m] * H[k + j * m];
+            if (i == j) { if (!(s > 0.0)) return 1; H[i + j * m] = sqrt(s); }
+            else H[i + j * m] = s / H[i + i * m];
+        }
+    return 0;
+}
+
+// Sigma <- bounds_Cov(Sigma + g1 (cov(block') - Sigma)): src/fast_LAPRWM.cpp:421-428,863-867
+__device__ inline void adapt_cov_dev(double* Sg, double* Hwork, int m, const double* block, int stride,
+                                     int nb, double g1, double eps2, double eps3) {
+    if (m == 0) return;
+    for (int a = 0; a < m; ++a)
+        for (int c = 0; c < m; ++c) {
+            double ma = 0.0, mc = 0.0;
+            for (int i = 0; i < nb; ++i) { ma += block[a + i * stride]; mc += block[c + i * stride]; }
+            ma /= nb; mc /= nb;
+            double s = 0.0;
+            for (int i = 0; i < nb; ++i) s += (block[a + i * stride] - ma) * (block[c + i * stride] - mc);
+            const double cv = s / (nb - 1);
+            Hwork[a + c * m] = Sg[a + c * m] + g1 * (cv - Sg[a + c * m]);
+        }
+    for (int e = 0; e < m * m; ++e) Sg[e] = Hwork[e];
+    double det = 0.0;
+    if (chol_upper_dev(Sg, m, Hwork) == 0) { det = 1.0; for (int j = 0; j < m; ++j) det *= Hwork[j + j * m] * Hwork[j + j * m]; }
+    if (det > eps3) for (int e = 0; e < m * m; ++e) Sg[e] *= eps3 / det;
+    for (int j = 0; j < m; ++j) Sg[j + j * m] += eps2;
+}
+
+struct FinalizeArgs {
+    double* par;
+    Ctl* ctl;
+    const double* partials;   // [n_partials][3]; ignored when use_reduced
+    int n_partials;
+    int use_reduced;          // multi-GPU: par[pl.sums..] already holds the all-reduced sums
+    int phase;                // 0: regular iteration, 1: chain start (Cholesky + first proposal only)
+    // outputs of kept iterations (device buffers laid out like jmb_chain_out)
+    double* o_Bs; double* o_g; double* o_a; double* o_phi_g; double* o_phi_a; double* o_tau_Bs;
+    double* o_tau_g; double* o_tau_a; double* o_tau_td; double* o_lw; double* trace;
+};
+
+// survival proposal for iteration `iter`: cur + sqrt(sigma) * z' chol(Sigma)  (:659-661,732-734)
+__device__ inline void make_proposal(const ModelMeta& mm, const ParamLayout& pl, const ChainConst& cc,
+                                     double* par, int iter, int tid, int nthreads, double* s_z) {
+    const int B = mm.B, p = mm.p, A = mm.A;
+    for (int s = tid; s < (mm.P + 1) / 2; s += nthreads) {
+        double z0, z1;
+        rnorm_pair(cc.seed, cc.chain_id, 0u, (uint32_t)iter, (uint32_t)s, ST_SURV, z0, z1);
+        s_z[2 * s] = z0; s_z[2 * s + 1] = z1;
+    }
+    __syncthreads();
+    for (int j = tid; j < mm.P; j += nthreads) {
+        int base, m, jj, Ho, sg;
+        if (j < B) { base = 0; m = B; jj = j; Ho = pl.H_Bs; sg = 0; }
+        else if (j < B + p) { base = B; m = p; jj = j - B; Ho = pl.H_g; sg = 1; }
+        else { base = B + p; m = A; jj = j - B - p; Ho = pl.H_a; sg = 2; }
+        double pj = 0.0;
+        for (int l = 0; l <= jj; ++l) pj += s_z[base + l] * par[Ho + l + jj * m];
+        par[pl.prop + j] = par[pl.cur + j] + sqrt(par[pl.sig + sg]) * pj;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ ParamLayout pl,
+                    const __grid_constant__ ChainConst cc, const __grid_constant__ FinalizeArgs a) {
+    __shared__ double s_sum[128 * 3];
+    __shared__ double s_tot[3];
+    __shared__ int s_next_iter;
+    __shared__ double s_z[JMB_MAX_BS + JMB_MAX_GAMMAS + JMB_MAX_ALPHAS + 2];
+    const int tid = threadIdx.x;
+    double* par = a.par;
+    const int B = mm.B, p = mm.p, A = mm.A;
+
+    if (a.phase == 1) {
+        if (tid == 0) {
+            int e = chol_upper_dev(par + pl.S_Bs, B, par + pl.H_Bs);
+            if (p) e |= chol_upper_dev(par + pl.S_g, p, par + pl.H_g);
+            e |= chol_upper_dev(par + pl.S_a, A, par + pl.H_a);
+            if (e) a.ctl->error = 2;
+        }
+        __syncthreads();
+        make_proposal(mm, pl, cc, par, a.ctl->iter, tid, blockDim.x, s_z);
+        return;
+    }
+
+    // ---- deterministic reduction of the per-CTA partials ----
+    if (a.use_reduced) {
+        if (tid < 3) s_tot[tid] = par[pl.sums + tid];
+    } else {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int i = tid; i < a.n_partials; i += 128) { t0 += a.partials[i * 3]; t1 += a.partials[i * 3 + 1]; t2 += a.partials[i * 3 + 2]; }
+        s_sum[tid] = t0; s_sum[128 + tid] = t1; s_sum[256 + tid] = t2;
+        __syncthreads();
+        for (int w = 64; w > 0; w >>= 1) {
+            if (tid < w) { s_sum[tid] += s_sum[tid + w]; s_sum[128 + tid] += s_sum[128 + tid + w]; s_sum[256 + tid] += s_sum[256 + tid + w]; }
+            __syncthreads();
+        }
+        if (tid < 3) s_tot[tid] = s_sum[tid * 128];
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        Ctl* ctl = a.ctl;
+        const int iter = ctl->iter;
+        double* cur = par + pl.cur;
+        double* prop = par + pl.prop;
+        if (a.trace) { a.trace[2LL * iter] = s_tot[0]; a.trace[2LL * iter + 1] = s_tot[1]; }
+        // ---- survival-block RWM (:727-770); tau = 1 for Bs_gammas (reference behaviour) ----
+        const double tau_g = par[pl.tau_g], tau_a = par[pl.tau_a];
+        const double cur_lp = s_tot[0] - 0.5 * quad_form_dev(cur, par + pl.mean_Bs, par + pl.Tau_Bs, B)
+            - 0.5 * tau_g * quad_form_dev(cur + B, par + pl.mean_g, par + pl.Tau_g, p)
+            - 0.5 * tau_a * quad_form_dev(cur + B + p, par + pl.mean_a, par + pl.Tau_a, A);
+        const double new_lp = s_tot[1] - 0.5 * quad_form_dev(prop, par + pl.mean_Bs, par + pl.Tau_Bs, B)
+            - 0.5 * tau_g * quad_form_dev(prop + B, par + pl.mean_g, par + pl.Tau_g, p)
+            - 0.5 * tau_a * quad_form_dev(prop + B + p, par + pl.mean_a, par + pl.Tau_a, A);
+        const double lu = log_unif(cc.seed, cc.chain_id, 0u, (uint32_t)iter, 0xFFFFFFFFu, ST_SURV);
+        if (lu < new_lp - cur_lp) {
+            for (int j = 0; j < mm.P; ++j) cur[j] = prop[j];
+            ctl->accept_s_block += 1; ctl->accept_s_total += 1;
+        }
+        if (cc.adaptCov) for (int j = 0; j < mm.P; ++j) par[pl.block_par + j + ctl->i * mm.P] = cur[j];
+        // ---- Gibbs draws of the precisions (:776-834) ----
+        uint32_t draw = 0;
+        {
+            const double Bpost = cc.B_tau_Bs + 0.5 * quad_form_dev(cur, nullptr, par + pl.Tau_Bs, B);
+            par[pl.tau_Bs] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_tau_Bs, 1.0 / Bpost)));
+        }
+        double* alp = cur + B + p;
+        double* gam = cur + B;
+        for (int kk = 0; kk < cc.n_td; ++kk) {
+            const int L = cc.td_len[kk];
+            double s = 0.0;
+            for (int a1 = 0; a1 < L; ++a1) for (int a2 = 0; a2 < L; ++a2)
+                s += alp[cc.td_cols[kk][a1]] * par[pl.Tau_a_pen + cc.td_cols[kk][a1] + cc.td_cols[kk][a2] * A] * alp[cc.td_cols[kk][a2]];
+            const double tv = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_tau_td, 1.0 / (cc.B_tau_td + 0.5 * s))));
+            par[pl.tau_td + kk] = tv;
+            for (int a1 = 0; a1 < L; ++a1) for (int a2 = 0; a2 < L; ++a2)
+                par[pl.Tau_a + cc.td_cols[kk][a1] + cc.td_cols[kk][a2] * A] = tv * par[pl.Tau_a_pen + cc.td_cols[kk][a1] + cc.td_cols[kk][a2] * A];
+        }
+        if (cc.shrink_gammas) {
+            for (int k1 = 0; k1 < p; ++k1) {
+                const double v = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_phi_g, 1.0 / (cc.B_phi_g + 0.5 * par[pl.tau_g] * gam[k1] * gam[k1]))));
+                par[pl.phi_g + k1] = v; par[pl.Tau_g + k1 + k1 * p] = v;
+            }
+            const double s = quad_form_dev(gam, nullptr, par + pl.Tau_g, p);
+            par[pl.tau_g] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_tau_g, 1.0 / (cc.B_tau_g + 0.5 * s))));
+        }
+        if (cc.shrink_alphas) {
+            for (int k2 = 0; k2 < A; ++k2) {
+                const double Bp = (cc.double_gamma_alphas ? par[pl.nu_a + k2] : cc.B_phi_a) + 0.5 * par[pl.tau_a] * alp[k2] * alp[k2];
+                const double v = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_phi_a, 1.0 / Bp)));
+                par[pl.phi_a + k2] = v; par[pl.Tau_a + k2 + k2 * A] = v;
+            }
+            const double s = quad_form_dev(alp, nullptr, par + pl.Tau_a, A);
+            const double Bp = (cc.double_gamma_alphas ? par[pl.xi_a] : cc.B_tau_a) + 0.5 * s;
+            par[pl.tau_a] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_tau_a, 1.0 / Bp)));
+            if (cc.double_gamma_alphas) {
+                for (int k2 = 0; k2 < A; ++k2)
+                    par[pl.nu_a + k2] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_nu_a, 1.0 / (cc.B_nu_a + par[pl.phi_a + k2]))));
+                par[pl.xi_a] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_xi_a, 1.0 / (cc.B_xi_a + par[pl.tau_a]))));
+            }
+        }
+        // ---- kept iterations (:836-851; 0-based iter against the 1-based keep sequence) ----
+        if (ctl->check_iterator < cc.n_keep && ctl->keep_iterator < cc.n_out &&
+            iter == cc.n_burnin + 1 + ctl->check_iterator * cc.n_thin) {
+            const int ko = ctl->keep_iterator;
+            for (int j = 0; j < B; ++j) a.o_Bs[j + ko * B] = cur[j];
+            for (int j = 0; j < p; ++j) { a.o_g[j + ko * p] = gam[j]; a.o_phi_g[j + ko * p] = par[pl.phi_g + j]; }
+            for (int j = 0; j < A; ++j) { a.o_a[j + ko * A] = alp[j]; a.o_phi_a[j + ko * A] = par[pl.phi_a + j]; }
+            a.o_tau_Bs[ko] = par[pl.tau_Bs]; a.o_tau_g[ko] = par[pl.tau_g]; a.o_tau_a[ko] = par[pl.tau_a];
+            for (int j = 0; j < cc.n_td; ++j) a.o_tau_td[j + ko * cc.n_td] = par[pl.tau_td + j];
+            a.o_lw[ko] = -s_tot[2];                                  // log_weightsREF :359-369,847
+            ctl->keep_iterator += 1; ctl->check_iterator += 1;
+        }
+        // ---- block end: adapt the global scales (:853-867) ----
+        if (ctl->i == cc.n_block - 1) {
+            const double g1 = pow((double)(ctl->it + 1), cc.mc1), g2 = cc.c0 * g1;
+            const double rate_s = (double)ctl->accept_s_block / cc.n_block;
+            for (int k = 0; k < 3; ++k) {
+                double sv = exp(log(par[pl.sig + k]) + g2 * (rate_s - cc.target_acc));
+                par[pl.sig + k] = fmin(fmax(sv, cc.eps1), cc.eps3);
+            }
+            if (cc.adaptCov && ctl->it > cc.start_cov_update) {
+                // H_* double as scratch here; they are rebuilt right below
+                adapt_cov_dev(par + pl.S_Bs, par + pl.H_Bs, B, par + pl.block_par, mm.P, cc.n_block, g1, cc.eps2, cc.eps3);
+                adapt_cov_dev(par + pl.S_g, par + pl.H_g, p, par + pl.block_par + B, mm.P, cc.n_block, g1, cc.eps2, cc.eps3);
+                adapt_cov_dev(par + pl.S_a, par + pl.H_a, A, par + pl.block_par + B + p, mm.P, cc.n_block, g1, cc.eps2, cc.eps3);
+                int e = chol_upper_dev(par + pl.S_Bs, B, par + pl.H_Bs);
+                if (p) e |= chol_upper_dev(par + pl.S_g, p, par + pl.H_g);
+                e |= chol_upper_dev(par + pl.S_a, A, par + pl.H_a);
+                if (e) ctl->error = 2;
+            }
+            ctl->accept_s_block = 0; ctl->i = 0; ctl->it += 1;
+        } else {
+            ctl->i += 1;
+        }
+        ctl->iter = iter + 1;
+        s_next_iter = iter + 1;
+    }
+    __syncthreads();
+    make_proposal(mm, pl, cc, par, s_next_iter, tid, blockDim.x, s_z);
+}
+
+// sum the per-CTA partials into par[pl.sums] (multi-GPU path, followed by an NCCL all-reduce)
+__global__ void __launch_bounds__(128)
+jmb_reduce_partials_kernel(const double* partials, int n_partials, double* sums) {
+    __shared__ double s_sum[128 * 3];
+    const int tid = threadIdx.x;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int i = tid; i < n_partials; i += 128) { t0 += partials[i * 3]; t1 += partials[i * 3 + 1]; t2 += partials[i * 3 + 2]; }
+    s_sum[tid] = t0; s_sum[128 + tid] = t1; s_sum[256 + tid] = t2;
+    __syncthreads();
+    for (int w = 64; w > 0; w >>= 1) {
+        if (tid < w) { s_sum[tid] += s_sum[tid + w]; s_sum[128 + tid] += s_sum[128 + tid + w]; s_sum[256 + tid] += s_sum[256 + tid + w]; }
+        __syncthreads();
+    }
+    if (tid < 3) sums[tid] = s_sum[tid * 128];
+}
+
+// out_b slice (n x q column-major) <- state (kept iterations, :837)
+__global__ void jmb_extract_b_kernel(const double* state, int stride, int n, int q, int col0, double* out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * q) return;
+    const int i = (int)(idx % n), j = (int)(idx / n);
+    out[idx] = state[(long long)i * stride + col0 + j];
+}
+
+// state <- initial b (n x q column-major) and scales$b
+__global__ void jmb_load_state_kernel(double* state, int stride, int n, int q, const double* b,
+                                      const double* sigma_b) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * stride) return;
+    const int i = (int)(idx / stride), j = (int)(idx % stride);
+    double v = 0.0;
+    if (j < q) v = b[(long long)j * n + i];
+    else if (j == q) v = sigma_b[i];
+    state[idx] = v;
+}
+
+}  // namespace jmb

@@ -1,0 +1,140 @@
+"""ctypes front-end of the CPU oracle (oracle/jmb_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs, never by the product package.  PARITY UNPINNED (see jmb_oracle.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from jmbayes_b200 import _abi   # struct layout shared by specification (same field order)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libjmb_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(HERE, f) for f in ("jmb_oracle.c", "jmb_oracle.h")]
+    stale = force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src)
+    if stale:
+        subprocess.run(["make", "-C", HERE, "-s", "-B"], check=True)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        L.orc_u01.restype = C.c_double
+        L.orc_u01.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_rgamma.restype = C.c_double
+        L.orc_rgamma.argtypes = [C.c_uint32] * 4 + [C.c_double, C.c_double]
+        L.orc_philox4x32.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
+        L.orc_rnorm_pair.argtypes = [C.c_uint32] * 6 + [_abi.c_double_p]
+        L.orc_rowsum.argtypes = [_abi.c_double_p, C.c_int64, _abi.c_int32_p, C.c_int32, _abi.c_double_p]
+        L.orc_eval_logpost_re.argtypes = [C.POINTER(_abi.JmbData), C.POINTER(_abi.JmbDraw)] + [_abi.c_double_p] * 4 + [C.POINTER(_abi.JmbEvalOut)]
+        L.orc_lap_rwm.argtypes = [C.POINTER(_abi.JmbData), C.POINTER(_abi.JmbDraw), C.POINTER(_abi.JmbPriors),
+                                  C.POINTER(_abi.JmbControl), C.POINTER(_abi.JmbChainIn),
+                                  C.POINTER(_abi.JmbChainOut), C.c_int]
+        L.orc_wlong.argtypes = [C.POINTER(_abi.JmbData), C.POINTER(_abi.JmbDraw), _abi.c_double_p, C.c_int, _abi.c_double_p]
+        L.orc_logPosterior.restype = C.c_double
+        L.orc_set_allreduce.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_abi.c_double_p)
+
+
+def set_rowsum_mode(mode: int):
+    """0 = literal cumsum difference (reference), 1 = exact per-segment sums."""
+    lib().orc_set_rowsum_mode(int(mode))
+
+
+def philox(seed, chain, c0, c1, c2, c3):
+    out = (C.c_uint32 * 4)()
+    lib().orc_philox4x32(seed, chain, c0, c1, c2, c3, out)
+    return [int(x) for x in out]
+
+
+def rowsum(x, last):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    last = np.ascontiguousarray(last, dtype=np.int32)
+    out = np.zeros(last.size)
+    lib().orc_rowsum(_p(x), x.size, last.ctypes.data_as(_abi.c_int32_p), last.size, _p(out))
+    return out
+
+
+def eval_logpost_re(Data, Covs_b, interval_cens, b, Bs_gammas, gammas, alphas):
+    d, k1 = _abi.marshal_data(Data, Covs_b, interval_cens)
+    w, k2 = _abi.marshal_draw(Data, interval_cens)
+    n = d.n
+    res = {k: np.zeros(n) for k in ("log_pyb", "log_pb", "log_h", "H", "HL", "log_ptb")}
+    out = _abi.JmbEvalOut()
+    for k, a in res.items():
+        setattr(out, k, _p(a))
+    b = np.asfortranarray(np.asarray(b, dtype=np.float64))
+    g = np.ascontiguousarray(np.atleast_1d(np.asarray(gammas, dtype=np.float64)))
+    if g.size == 0:
+        g = np.zeros(1)
+    Bs = np.ascontiguousarray(np.asarray(Bs_gammas, dtype=np.float64))
+    al = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64))
+    rc = lib().orc_eval_logpost_re(C.byref(d), C.byref(w), _p(b), _p(Bs), _p(g), _p(al), C.byref(out))
+    assert rc == 0
+    return res
+
+
+def wlong(Data, Covs_b, interval_cens, b, which):
+    d, k1 = _abi.marshal_data(Data, Covs_b, interval_cens)
+    w, k2 = _abi.marshal_draw(Data, interval_cens)
+    rows = d.n if which == 0 else d.n * d.K
+    out = np.zeros((rows, d.n_alphas), order="F")
+    b = np.asfortranarray(np.asarray(b, dtype=np.float64))
+    lib().orc_wlong(C.byref(d), C.byref(w), _p(b), which, _p(out))
+    return out
+
+
+def lap_rwm_C(initials, Data, priors, scales, Covs, control, interval_cens=False, multiState=False,
+              chain_id: int = 0, max_iters: int = 0, subject_offset: int = 0, allreduce=None):
+    """Restated reference chain (src/fast_LAPRWM.cpp:431-896) with the DESIGN.md random streams.
+
+    ``allreduce(buf: np.ndarray)`` (in place) is the hook for sharded runs."""
+    d, k1 = _abi.marshal_data(Data, Covs["b"], interval_cens, multiState, subject_offset)
+    w, k2 = _abi.marshal_draw(Data, interval_cens)
+    pr, k3 = _abi.marshal_priors(priors)
+    ct = _abi.marshal_control(control, chain_id)
+    ci, k4 = _abi.marshal_chain_in(initials, scales, Covs)
+    total, n_out = _abi.chain_dims(control)
+    out, bufs = _abi.alloc_chain_out(d.n, d.q, d.n_Bs, d.n_gammas, d.n_alphas, pr.n_td, n_out, total)
+    L = lib()
+    cb = None
+    if allreduce is not None:
+        CB = C.CFUNCTYPE(None, _abi.c_double_p, C.c_int, C.c_void_p)
+
+        def _hook(ptr, ln, _ctx):
+            arr = np.ctypeslib.as_array(ptr, shape=(ln,))
+            allreduce(arr)
+        cb = CB(_hook)
+        L.orc_set_allreduce(C.cast(cb, C.c_void_p), None)
+    try:
+        rc = L.orc_lap_rwm(C.byref(d), C.byref(w), C.byref(pr), C.byref(ct), C.byref(ci), C.byref(out), int(max_iters))
+    finally:
+        if allreduce is not None:
+            L.orc_set_allreduce(None, None)
+    if rc != 0:
+        raise RuntimeError(f"oracle lap_rwm failed with code {rc}")
+    mcmc = {k: bufs[k] for k in ("b", "Bs_gammas", "gammas", "alphas", "phi_gammas", "phi_alphas",
+                                 "tau_Bs_gammas", "tau_gammas", "tau_alphas", "tau_td_alphas")}
+    return dict(mcmc=mcmc, logWeights=bufs["logWeights"],
+                scales=dict(sigma=dict(b=bufs["sigma_b"], Bs_gammas=float(bufs["sigma_surv"][0]),
+                                       gammas=float(bufs["sigma_surv"][1]), alphas=float(bufs["sigma_surv"][2])),
+                            Sigma=dict(Bs_gammas=bufs["Sigma_Bs_gammas"], gammas=bufs["Sigma_gammas"],
+                                       alphas=bufs["Sigma_alphas"])),
+                extras=dict(accept_b=bufs["accept_b"], accept_surv=bufs["accept_surv"], trace_surv=bufs["trace_surv"]))

@@ -1,0 +1,119 @@
+"""CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerance: 1e-10 relative in fp64 on every per-subject piece of the b-step target
+(BASELINE.json north_star), measured against the exact-rowsum oracle (the
+reference's own cumsum-difference rowsum is less accurate than that at scale); segment boundaries
+bit-exact.
+"""
+import numpy as np
+import pytest
+
+from jmbayes_b200.cohorts import make_cohort
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def _rel(a, b, floor=1e-12):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def _variant(c, links=None, trans=None):
+    D = c["Data"]
+    if links:
+        D["links"] = list(links)
+    if trans:
+        D["trans_Funs"] = list(trans)
+    return c
+
+
+@pytest.mark.parametrize("cfg,n", [("config2", 3000), ("config3", 3000), ("config4", 3000), ("config3", 37)])
+def test_logpost_pieces_match_oracle(cuda_lib, oracle, cfg, n):
+    c = make_cohort(cfg, n=n)
+    D, ini = c["Data"], c["inits"]
+    oracle.set_rowsum_mode(1)
+    ref = oracle.eval_logpost_re(D, c["Covs"]["b"], c["interval_cens"], ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+    with cuda_lib.Fit(D, c["Covs"]["b"], c["interval_cens"]) as fit:
+        fit.set_draw(D)
+        got = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+        for k in range(len(D["y"])):   # segment boundaries bit-exact
+            rp = fit.row_ptr(k)
+            assert np.array_equal(rp[1:] - 1, np.asarray(D["idL2"][k], dtype=np.int64))
+            assert rp[0] == 0
+    for key in ("log_pyb", "log_pb", "log_h", "H", "HL", "log_ptb"):
+        assert np.isfinite(got[key]).all(), key
+        assert _rel(got[key], ref[key]) <= RTOL, (key, _rel(got[key], ref[key]))
+    tot_ref = ref["log_pyb"] + ref["log_ptb"] + ref["log_pb"]
+    tot = got["log_pyb"] + got["log_ptb"] + got["log_pb"]
+    assert _rel(tot, tot_ref) <= RTOL
+
+
+def test_links_and_transforms(cuda_lib, oracle):
+    c = make_cohort("config3", n=500)
+    # probit + cloglog links, expit/exp/sqrt/log-type transforms of positive terms
+    c["Data"]["fams"] = ["binomial", "binomial", "poisson"]
+    c["Data"]["links"] = ["probit", "cloglog", "log"]
+    c["Data"]["y"][0] = (c["Data"]["y"][0] > 1.0).astype(float)
+    c["Data"]["trans_Funs"] = ["expit", "exp", "identity", "identity", "exp", "identity"]
+    D, ini = c["Data"], c["inits"]
+    b = 0.3 * np.asarray(ini["b"])
+    oracle.set_rowsum_mode(1)
+    ref = oracle.eval_logpost_re(D, c["Covs"]["b"], False, b, ini["Bs_gammas"], ini["gammas"], 0.1 * ini["alphas"])
+    with cuda_lib.Fit(D, c["Covs"]["b"], False) as fit:
+        fit.set_draw(D)
+        got = fit.eval_logpost_re(b, ini["Bs_gammas"], ini["gammas"], 0.1 * ini["alphas"])
+    for key in ("log_pyb", "log_pb", "log_h", "H", "log_ptb"):
+        assert np.isfinite(ref[key]).all(), key
+        assert _rel(got[key], ref[key]) <= RTOL, (key, _rel(got[key], ref[key]))
+
+
+@pytest.mark.parametrize("cfg", ["config2", "config3", "config4"])
+def test_chain_matches_oracle_draw_for_draw(cuda_lib, oracle, cfg):
+    """Same counter-RNG specification on both sides: the whole trajectory must agree."""
+    c = make_cohort(cfg, n=400)
+    ctl = dict(c["control"]); ctl.update(n_burnin=60, n_iter=40, n_block=20, n_thin=10)
+    oracle.set_rowsum_mode(1)
+    ref = oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"], chain_id=3)
+    got = cuda_lib.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"], chain_id=3)
+    tr_ref, tr = ref["extras"]["trace_surv"], got["extras"]["trace_surv"]
+    assert tr.shape == tr_ref.shape
+    assert _rel(tr, tr_ref) <= 1e-9, _rel(tr, tr_ref)
+    for key in ("Bs_gammas", "gammas", "alphas", "tau_Bs_gammas", "b"):
+        assert ref["mcmc"][key].shape == got["mcmc"][key].shape
+        assert np.allclose(got["mcmc"][key], ref["mcmc"][key], rtol=1e-8, atol=1e-10), key
+    assert np.allclose(got["logWeights"], ref["logWeights"], rtol=1e-10)
+    assert np.allclose(got["scales"]["sigma"]["b"], ref["scales"]["sigma"]["b"], rtol=1e-9)
+    for key in ("Bs_gammas", "gammas", "alphas"):
+        assert np.isclose(got["scales"]["sigma"][key], ref["scales"]["sigma"][key], rtol=1e-9)
+    assert np.allclose(got["extras"]["accept_b"], ref["extras"]["accept_b"])
+    assert np.allclose(got["extras"]["accept_surv"], ref["extras"]["accept_surv"])
+    assert got["mcmc"]["b"].shape[2] == 4 and np.abs(got["mcmc"]["b"][:, :, -1]).sum() > 0
+
+
+def test_adapt_cov_and_shrinkage_chain(cuda_lib, oracle):
+    c = make_cohort("config3", n=200)
+    ctl = dict(c["control"]); ctl.update(n_burnin=40, n_iter=40, n_block=10, n_thin=7, adaptCov=True)
+    pr = dict(c["priors"]); pr.update(shrink_gammas=True, shrink_alphas=True, double_gamma_alphas=True)
+    oracle.set_rowsum_mode(1)
+    ref = oracle.lap_rwm_C(c["inits"], c["Data"], pr, c["scales"], c["Covs"], ctl, False, chain_id=1)
+    got = cuda_lib.lap_rwm_C(c["inits"], c["Data"], pr, c["scales"], c["Covs"], ctl, False, chain_id=1)
+    assert _rel(got["extras"]["trace_surv"], ref["extras"]["trace_surv"]) <= 1e-8
+    for key in ("phi_gammas", "phi_alphas", "tau_gammas", "tau_alphas", "alphas"):
+        assert np.allclose(got["mcmc"][key], ref["mcmc"][key], rtol=1e-7, atol=1e-10), key
+    for key in ("Bs_gammas", "gammas", "alphas"):
+        assert np.allclose(got["scales"]["Sigma"][key], ref["scales"]["Sigma"][key], rtol=1e-6, atol=1e-12), key
+
+
+def test_errors_are_loud(cuda_lib):
+    c = make_cohort("config2", n=50)
+    D = dict(c["Data"])
+    bad = [np.array(x) for x in D["idL2"]]
+    bad[0] = bad[0].copy(); bad[0][3] += 1
+    D["idL2"] = bad
+    with pytest.raises(cuda_lib.JmbError):
+        cuda_lib.Fit(D, c["Covs"]["b"], False)
+    with cuda_lib.Fit(c["Data"], c["Covs"]["b"], False) as fit:
+        with pytest.raises(cuda_lib.JmbError):   # no draw set yet
+            fit.eval_logpost_re(c["inits"]["b"], c["inits"]["Bs_gammas"], c["inits"]["gammas"], c["inits"]["alphas"])
+    with pytest.raises(cuda_lib.JmbError):
+        cuda_lib.Fit(c["Data"], c["Covs"]["b"], False, multiState=True)
