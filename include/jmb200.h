@@ -223,6 +223,8 @@ int jmb_chain_begin(jmb_handle h, const jmb_priors* priors, const jmb_control* c
 int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, float* step_kernel_ms);
 int jmb_chain_end(jmb_handle h, jmb_chain_out* out);
 int jmb_launch_count(jmb_handle h, int64_t* launches);
+/* "static:<shape>" when a compile-time-specialised step kernel serves this model, else "generic" */
+const char* jmb_kernel_name(jmb_handle h);
 void* jmb_stream(jmb_handle h);
 
 #ifdef __cplusplus

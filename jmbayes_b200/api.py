@@ -37,6 +37,8 @@ def lib():
     L = C.CDLL(LIB)
     L.jmb_last_error.restype = C.c_char_p
     L.jmb_stream.restype = C.c_void_p
+    L.jmb_kernel_name.restype = C.c_char_p
+    L.jmb_kernel_name.argtypes = [C.c_void_p]
     L.jmb_stream.argtypes = [C.c_void_p]
     vp = C.c_void_p
     L.jmb_create.argtypes = [C.POINTER(_abi.JmbData), C.c_int, C.POINTER(vp)]
@@ -197,7 +199,8 @@ class Fit:
         wb, g = C.c_int32(0), C.c_int32(0)
         _check(lib().jmb_layout_info(self._h, C.byref(sb), C.byref(cb), C.byref(wb), C.byref(g)))
         return dict(shared_bytes_per_subject=sb.value, chain_bytes_per_subject=cb.value,
-                    w1_band=wb.value, group_lanes=g.value)
+                    w1_band=wb.value, group_lanes=g.value,
+                    kernel=lib().jmb_kernel_name(self._h).decode())
 
     def launch_count(self) -> int:
         c = C.c_int64(0)

@@ -23,7 +23,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale(LIB, SOURCES + HEADERS):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB, SOURCES[0], "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -9,12 +9,13 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
 #include <vector>
 
-#include "jmb_kernels.cuh"
+#include "jmb_step_static.cuh"
 
 using namespace jmb;
 
@@ -102,12 +103,27 @@ struct jmb_handle_s {
     // launch configuration
     int grid = 0, subjects_per_cta = 0, smem_bytes = 0;
     long long launches = 0;
+    // step kernel chosen for this model: a precompiled static specialisation or the generic one
+    void (*static_kernel)(int, ParamLayout, ChainConst, StepArgs) = nullptr;
+    const char* kernel_name = "generic";
+    int static_smem = 0;
+    bool force_generic = false;
+    void select_kernel();
     // multi-GPU
     ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
 };
 
-static int roundup(int x, int m) { return (x + m - 1) / m * m; }
+void jmb_handle_s::select_kernel() {
+    static_kernel = nullptr; kernel_name = "generic";
+    const ModelDesc& md = mm.d;
+    if (same_desc(md, SpecValueGaussian::d)) { static_kernel = jmb_step_static<SpecValueGaussian>; kernel_name = "static:value_gaussian"; }
+    else if (same_desc(md, SpecThreeOutcomes::d)) { static_kernel = jmb_step_static<SpecThreeOutcomes>; kernel_name = "static:three_outcomes"; }
+    else if (same_desc(md, SpecThreeOutcomesIC::d)) { static_kernel = jmb_step_static<SpecThreeOutcomesIC>; kernel_name = "static:three_outcomes_ic"; }
+    static_smem = (int)sizeof(double) * (2 * mm.P + md.q * md.q + (256 / md.G) * 3);
+    const char* env = getenv("JMB_FORCE_GENERIC");
+    if (env && env[0] == '1') force_generic = true;
+}
 
 template <typename F>
 static void parallel_for(int n, F f) {
@@ -128,14 +144,14 @@ static void build_param_layout(const ModelMeta& mm, int n_td, int n_block_cap, P
     int o = 0;
     auto take = [&](int len) { int r = o; o += std::max(len, 1); return r; };
     pl.cur = take(mm.P); pl.prop = take(mm.P);
-    pl.invD = take(mm.q * mm.q); pl.sigmas = take(mm.O);
+    pl.invD = take(mm.d.q * mm.d.q); pl.sigmas = take(mm.d.O);
     pl.tau_Bs = take(1); pl.tau_g = take(1); pl.tau_a = take(1); pl.xi_a = take(1);
-    pl.phi_g = take(mm.p); pl.phi_a = take(mm.A); pl.nu_a = take(mm.A); pl.tau_td = take(n_td);
-    pl.Tau_g = take(mm.p * mm.p); pl.Tau_a = take(mm.A * mm.A); pl.Tau_a_pen = take(mm.A * mm.A);
+    pl.phi_g = take(mm.d.p); pl.phi_a = take(mm.d.A); pl.nu_a = take(mm.d.A); pl.tau_td = take(n_td);
+    pl.Tau_g = take(mm.d.p * mm.d.p); pl.Tau_a = take(mm.d.A * mm.d.A); pl.Tau_a_pen = take(mm.d.A * mm.d.A);
     pl.sig = take(3);
-    pl.S_Bs = take(mm.B * mm.B); pl.S_g = take(mm.p * mm.p); pl.S_a = take(mm.A * mm.A);
-    pl.H_Bs = take(mm.B * mm.B); pl.H_g = take(mm.p * mm.p); pl.H_a = take(mm.A * mm.A);
-    pl.mean_Bs = take(mm.B); pl.Tau_Bs = take(mm.B * mm.B); pl.mean_g = take(mm.p); pl.mean_a = take(mm.A);
+    pl.S_Bs = take(mm.B * mm.B); pl.S_g = take(mm.d.p * mm.d.p); pl.S_a = take(mm.d.A * mm.d.A);
+    pl.H_Bs = take(mm.B * mm.B); pl.H_g = take(mm.d.p * mm.d.p); pl.H_a = take(mm.d.A * mm.d.A);
+    pl.mean_Bs = take(mm.B); pl.Tau_Bs = take(mm.B * mm.B); pl.mean_g = take(mm.d.p); pl.mean_a = take(mm.d.A);
     pl.block_par = take(mm.P * n_block_cap);
     pl.sums = take(4);
     pl.total = o;
@@ -159,6 +175,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
         d->n_alphas <= 0 || d->n_alphas > JMB_MAX_ALPHAS) return fail("jmb_create: parameter block sizes out of range");
     const int S = d->interval_cens ? 2 : 1;
     if (d->K <= 0 || 1 + d->K * S > 32) return fail("jmb_create: 1 + K * (1 + interval_cens) must be <= 32");
+    if (d->q + 5 > 32) return fail("jmb_create: q + 5 must be <= 32");
     if (S == 2 && (!d->W1s_int || !d->Pw_int || !d->ZZs_int || !d->Us_int || (d->n_gammas && !d->W2s_int)))
         return fail("jmb_create: interval_cens needs the *_int designs");
 
@@ -169,32 +186,31 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     const int n = d->n, O = d->n_outcomes, q = d->q, T = d->n_terms, B = d->n_Bs, p = d->n_gammas, K = d->K;
     const long long ns = (long long)n * K;
     ModelMeta& mm = h->mm;
-    mm.O = O; mm.q = q; mm.T = T; mm.A = d->n_alphas; mm.B = B; mm.p = p; mm.K = K; mm.S = S;
+    ModelDesc& md = mm.d;
+    memset(&mm, 0, sizeof(mm));
+    md.O = O; md.q = q; md.T = T; md.A = d->n_alphas; md.p = p; md.K = K; md.S = S;
+    mm.B = B;
     mm.P = B + p + d->n_alphas;
-    mm.G = (1 + K * S <= 16) ? 16 : 32;
-    mm.RP = mm.G;
-    mm.state_stride = q + 5;
-    int qsum = 0;
+    md.G = (1 + K * S <= 16) ? 16 : 32;
+    if (q + 5 > md.G) md.G = 32;
     for (int k = 0; k < O; ++k) {
-        mm.fam[k] = d->fams[k]; mm.link[k] = d->links[k]; mm.qk[k] = d->q_k[k];
-        if (mm.qk[k] < 0 || mm.qk[k] > JMB_MAX_Q) { delete h; return fail("jmb_create: q_k out of range"); }
-        for (int j = 0; j < mm.qk[k]; ++j) {
-            mm.re_inds[k][j] = d->RE_inds[k][j];
-            if (mm.re_inds[k][j] < 0 || mm.re_inds[k][j] >= q) { delete h; return fail("jmb_create: RE_inds out of range"); }
+        md.fam[k] = d->fams[k]; md.link[k] = d->links[k]; md.qk[k] = d->q_k[k];
+        if (md.qk[k] < 0 || md.qk[k] > JMB_MAX_Q) { delete h; return fail("jmb_create: q_k out of range"); }
+        for (int j = 0; j < md.qk[k]; ++j) {
+            md.re_inds[k][j] = d->RE_inds[k][j];
+            if (md.re_inds[k][j] < 0 || md.re_inds[k][j] >= q) { delete h; return fail("jmb_create: RE_inds out of range"); }
         }
-        qsum += mm.qk[k];
     }
-    (void)qsum;
     for (int t = 0; t < T; ++t) {
-        mm.rt[t] = d->r_t[t]; mm.ut[t] = d->u_t[t]; mm.tf[t] = d->trans_Funs[t];
-        if (mm.rt[t] < 0 || mm.rt[t] > JMB_MAX_RT || mm.ut[t] <= 0 || mm.ut[t] > JMB_MAX_UT) { delete h; return fail("jmb_create: term sizes out of range"); }
-        for (int j = 0; j < mm.rt[t]; ++j) {
-            mm.re2[t][j] = d->RE_inds2[t][j];
-            if (mm.re2[t][j] < 0 || mm.re2[t][j] >= q) { delete h; return fail("jmb_create: RE_inds2 out of range"); }
+        md.rt[t] = d->r_t[t]; md.ut[t] = d->u_t[t]; md.tf[t] = d->trans_Funs[t];
+        if (md.rt[t] < 0 || md.rt[t] > JMB_MAX_RT || md.ut[t] <= 0 || md.ut[t] > JMB_MAX_UT) { delete h; return fail("jmb_create: term sizes out of range"); }
+        for (int j = 0; j < md.rt[t]; ++j) {
+            md.re2[t][j] = d->RE_inds2[t][j];
+            if (md.re2[t][j] < 0 || md.re2[t][j] >= q) { delete h; return fail("jmb_create: RE_inds2 out of range"); }
         }
-        for (int u = 0; u < mm.ut[t]; ++u) {
-            mm.col[t][u] = d->col_inds[t][u];
-            if (mm.col[t][u] < 0 || mm.col[t][u] >= d->n_alphas) { delete h; return fail("jmb_create: col_inds out of range"); }
+        for (int u = 0; u < md.ut[t]; ++u) {
+            md.col[t][u] = d->col_inds[t][u];
+            if (md.col[t][u] < 0 || md.col[t][u] >= d->n_alphas) { delete h; return fail("jmb_create: col_inds out of range"); }
         }
     }
 
@@ -246,27 +262,52 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
         if (WB > 8) WB = B;                 // not banded: keep the dense rows
         WB = std::min(WB, B);
     }
-    mm.WB = WB;
+    md.WB = WB;
+
+    // ---- constant design columns that need not be stored (decided from the data) ----
+    auto all_ones = [&](const double* col, long long rows) {
+        std::atomic<int> ok{1};
+        parallel_for((int)rows, [&, col](int lo, int hi) {
+            for (long long r = lo; r < hi; ++r) if (col[r] != 1.0) { ok.store(0); return; }
+        });
+        return ok.load() == 1;
+    };
+    for (int k = 0; k < O; ++k) md.z_ones0[k] = (md.qk[k] >= 1 && all_ones(d->Z[k], d->N[k])) ? 1 : 0;
+    for (int t = 0; t < T; ++t) {
+        bool zo = md.rt[t] >= 1 && all_ones(d->ZZ[t], n) && all_ones(d->ZZs[t], ns) && (S == 1 || all_ones(d->ZZs_int[t], ns));
+        md.zz_ones0[t] = zo ? 1 : 0;
+        bool uo = all_ones(d->U[t], (long long)n * md.ut[t]) && all_ones(d->Us[t], ns * md.ut[t]) &&
+                  (S == 1 || all_ones(d->Us_int[t], ns * md.ut[t]));
+        md.u_ones[t] = uo ? 1 : 0;
+    }
+    {
+        std::atomic<int> ok{p > 0 ? 1 : 0};
+        if (p > 0)
+            parallel_for(n, [&](int lo, int hi) {
+                for (int i = lo; i < hi; ++i)
+                    for (int j = 0; j < p; ++j) {
+                        const double w = d->W2[i + (long long)j * n];
+                        for (int k = 0; k < K; ++k) {
+                            if (d->W2s[(long long)i * K + k + (long long)j * ns] != w) { ok.store(0); return; }
+                            if (S == 2 && d->W2s_int[(long long)i * K + k + (long long)j * ns] != w) { ok.store(0); return; }
+                        }
+                    }
+            });
+        md.w2_const = ok.load();
+    }
 
     // ---- record layout ----
-    const int RP = mm.RP;
-    mm.o_R = 2;
-    int o = roundup(2 + q * (q + 1) / 2, 2);
-    mm.o_Pw = o; o += RP;
-    mm.o_W1off = o; o += RP / 2;
-    mm.o_W1v = o; o += WB * RP;
-    mm.o_W2 = o; o += p * RP;
-    for (int t = 0; t < T; ++t) { mm.o_ZZ[t] = o; o += mm.rt[t] * RP; mm.o_U[t] = o; o += mm.ut[t] * RP; }
-    mm.o_long = o;
-    mm.c_long = T * RP;
+    mm.L = make_layout(md);
+    const RecordLayout& L = mm.L;
+    const int RP = L.RP;
 
     h->doff.assign(n + 1, 0);
     h->coff.assign(n + 1, 0);
     for (int i = 0; i < n; ++i) {
-        long long dl = mm.o_long, cl = mm.c_long;
+        long long dl = L.o_long, cl = L.c_long;
         for (int k = 0; k < O; ++k) {
             int v = h->rowptr[k][i + 1] - h->rowptr[k][i];
-            dl += (long long)v * (1 + mm.qk[k]);
+            dl += (long long)v * L.long_cols[k];
             cl += v;
         }
         h->doff[i + 1] = h->doff[i] + ((dl + 1) / 2) * 2;
@@ -281,8 +322,9 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
             rec[0] = d->event[i];
             const double* Rm = d->Covs_b + (long long)i * q * q;
             for (int j = 0; j < q; ++j)
-                for (int l = 0; l <= j; ++l) rec[mm.o_R + j * (j + 1) / 2 + l] = Rm[l + j * q];
-            int* w1off = reinterpret_cast<int*>(rec + mm.o_W1off);
+                for (int l = 0; l <= j; ++l) rec[L.o_R + j * (j + 1) / 2 + l] = Rm[l + j * q];
+            if (md.w2_const) for (int j = 0; j < p; ++j) rec[L.o_W2c + j] = d->W2[i + (long long)j * n];
+            int* w1off = reinterpret_cast<int*>(rec + L.o_W1off);
             for (int r = 0; r < RP; ++r) {
                 int cls = (r == 0) ? 0 : (r <= K ? 1 : ((S == 2 && r <= 2 * K) ? 2 : 3));
                 w1off[r] = 0;
@@ -291,30 +333,32 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
                 const long long src = cls == 0 ? i : (cls == 1 ? (long long)i * K + (r - 1) : (long long)i * K + (r - 1 - K));
                 const double* W1x = cls == 0 ? d->W1 : (cls == 1 ? d->W1s : d->W1s_int);
                 const double* W2x = cls == 0 ? d->W2 : (cls == 1 ? d->W2s : d->W2s_int);
-                if (cls == 1) rec[mm.o_Pw + r] = d->Pw[src];
-                if (cls == 2) rec[mm.o_Pw + r] = d->Pw_int[src];
+                if (cls == 1) rec[L.o_Pw + r] = d->Pw[src];
+                if (cls == 2) rec[L.o_Pw + r] = d->Pw_int[src];
                 int f, l;
                 band_of(W1x, rows, src, f, l);
                 int off = (l < f) ? 0 : std::min(f, B - WB);
                 if (WB == B) off = 0;
                 w1off[r] = off;
-                for (int j = 0; j < WB; ++j) rec[mm.o_W1v + j * RP + r] = W1x[src + (long long)(off + j) * rows];
-                for (int j = 0; j < p; ++j) rec[mm.o_W2 + j * RP + r] = W2x[src + (long long)j * rows];
+                for (int j = 0; j < WB; ++j) rec[L.o_W1v + j * RP + r] = W1x[src + (long long)(off + j) * rows];
+                if (!md.w2_const) for (int j = 0; j < p; ++j) rec[L.o_W2 + j * RP + r] = W2x[src + (long long)j * rows];
                 for (int t = 0; t < T; ++t) {
                     const double* ZZx = cls == 0 ? d->ZZ[t] : (cls == 1 ? d->ZZs[t] : d->ZZs_int[t]);
                     const double* Ux = cls == 0 ? d->U[t] : (cls == 1 ? d->Us[t] : d->Us_int[t]);
-                    for (int j = 0; j < mm.rt[t]; ++j) rec[mm.o_ZZ[t] + j * RP + r] = ZZx[src + (long long)j * rows];
-                    for (int u = 0; u < mm.ut[t]; ++u) rec[mm.o_U[t] + u * RP + r] = Ux[src + (long long)u * rows];
+                    const int z0 = md.zz_ones0[t];
+                    for (int j = z0; j < md.rt[t]; ++j) rec[L.o_ZZ[t] + (j - z0) * RP + r] = ZZx[src + (long long)j * rows];
+                    if (!md.u_ones[t]) for (int u = 0; u < md.ut[t]; ++u) rec[L.o_U[t] + u * RP + r] = Ux[src + (long long)u * rows];
                 }
             }
-            double* lrec = rec + mm.o_long;
+            double* lrec = rec + L.o_long;
             for (int k = 0; k < O; ++k) {
                 const int r0 = h->rowptr[k][i], v = h->rowptr[k][i + 1] - r0;
                 const long long Nk = d->N[k];
+                const int z0 = md.z_ones0[k];
                 for (int r = 0; r < v; ++r) lrec[r] = d->y[k][r0 + r];
-                for (int j = 0; j < mm.qk[k]; ++j)
-                    for (int r = 0; r < v; ++r) lrec[(1 + j) * v + r] = d->Z[k][r0 + r + (long long)j * Nk];
-                lrec += (1 + mm.qk[k]) * v;
+                for (int j = z0; j < md.qk[k]; ++j)
+                    for (int r = 0; r < v; ++r) lrec[(1 + j - z0) * v + r] = d->Z[k][r0 + r + (long long)j * Nk];
+                lrec += L.long_cols[k] * v;
             }
         }
     });
@@ -329,7 +373,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     CUH(cudaMalloc(&h->d_crec, sizeof(double) * std::max<long long>(h->coff[n], 2)));
     CUH(cudaMalloc(&h->d_coff, sizeof(long long) * (n + 1)));
     CUH(cudaMalloc(&h->d_rowptr, sizeof(int) * (size_t)O * (n + 1)));
-    CUH(cudaMalloc(&h->d_state, sizeof(double) * (size_t)n * mm.state_stride));
+    CUH(cudaMalloc(&h->d_state, sizeof(double) * (size_t)n * mm.L.state_stride));
     CUH(cudaMalloc(&h->d_eval, sizeof(double) * (size_t)n * 6));
     CUH(cudaMalloc(&h->d_tmp, sizeof(double) * (size_t)n * (q + 1)));
     CUH(cudaMalloc(&h->d_ctl, sizeof(Ctl)));
@@ -340,7 +384,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     CUH(cudaMemcpy(h->d_coff, h->coff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
     for (int k = 0; k < O; ++k)
         CUH(cudaMemcpy(h->d_rowptr + (size_t)k * (n + 1), h->rowptr[k].data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
-    CUH(cudaMemset(h->d_state, 0, sizeof(double) * (size_t)n * mm.state_stride));
+    CUH(cudaMemset(h->d_state, 0, sizeof(double) * (size_t)n * mm.L.state_stride));
     CUH(cudaMemset(h->d_ctl, 0, sizeof(Ctl)));
 
     // parameter block (n_td capacity = JMB_MAX_TERMS)
@@ -351,10 +395,11 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     memset(h->h_par, 0, sizeof(double) * h->pl.total);
 
     // launch configuration: G lanes per subject, 256 threads, a few subjects per group per CTA
-    const int groups = 256 / mm.G;
+    const int groups = 256 / md.G;
     h->subjects_per_cta = groups * 4;
     h->grid = (n + h->subjects_per_cta - 1) / h->subjects_per_cta;
     h->smem_bytes = (int)sizeof(double) * (2 * mm.P + q * q + O + groups * 3 * (q + 5) + groups * 3);
+    h->select_kernel();
     CUH(cudaMalloc(&h->d_partials, sizeof(double) * 3 * (size_t)h->grid));
     CUH(cudaEventCreate(&h->ev0)); CUH(cudaEventCreate(&h->ev1));
     CUH(cudaEventCreate(&h->evk0)); CUH(cudaEventCreate(&h->evk1));
@@ -391,7 +436,7 @@ extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));        // the staging buffer may still be in flight
     const ModelMeta& mm = h->mm;
-    const int n = h->n, K = mm.K, RP = mm.RP, S = mm.S, T = mm.T, O = mm.O;
+    const int n = h->n, K = mm.d.K, RP = mm.L.RP, S = mm.d.S, T = mm.d.T, O = mm.d.O;
     if (S == 2 && !w->XXsbetas_int) return fail("jmb_set_draw: XXsbetas_int required with interval censoring");
     double* base = h->h_crec;
     parallel_for(n, [&](int lo, int hi) {
@@ -404,7 +449,7 @@ extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
                 if (S == 2) for (int r = 1; r <= K; ++r) x[K + r] = w->XXsbetas_int[t][(long long)i * K + r - 1];
                 for (int r = 1 + K * S; r < RP; ++r) x[r] = 0.0;
             }
-            double* l = rec + mm.c_long;
+            double* l = rec + mm.L.c_long;
             for (int k = 0; k < O; ++k) {
                 const int r0 = h->rowptr[k][i], v = h->rowptr[k][i + 1] - r0;
                 memcpy(l, w->Xbetas[k] + r0, sizeof(double) * v);
@@ -413,9 +458,9 @@ extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
         }
     });
     CU(cudaMemcpyAsync(h->d_crec, h->h_crec, sizeof(double) * h->coff[n], cudaMemcpyHostToDevice, h->stream));
-    for (int j = 0; j < mm.q * mm.q; ++j) h->h_par[h->pl.invD + j] = w->invD[j];
-    for (int k = 0; k < O; ++k) h->h_par[h->pl.sigmas + k] = (mm.fam[k] == JMB_FAM_GAUSSIAN) ? w->sigmas[k] : 1.0;
-    CU(cudaMemcpyAsync(h->d_par + h->pl.invD, h->h_par + h->pl.invD, sizeof(double) * (mm.q * mm.q + O), cudaMemcpyHostToDevice, h->stream));
+    for (int j = 0; j < mm.d.q * mm.d.q; ++j) h->h_par[h->pl.invD + j] = w->invD[j];
+    for (int k = 0; k < O; ++k) h->h_par[h->pl.sigmas + k] = (mm.d.fam[k] == JMB_FAM_GAUSSIAN) ? w->sigmas[k] : 1.0;
+    CU(cudaMemcpyAsync(h->d_par + h->pl.invD, h->h_par + h->pl.invD, sizeof(double) * (mm.d.q * mm.d.q + O), cudaMemcpyHostToDevice, h->stream));
     h->draw_set = true;
     return 0;
 }
@@ -428,7 +473,9 @@ static int launch_step(jmb_handle h, int mode) {
     a.drec = h->d_drec; a.doff = h->d_doff; a.crec = h->d_crec; a.coff = h->d_coff; a.rowptr = h->d_rowptr;
     a.state = h->d_state; a.par = h->d_par; a.ctl = h->d_ctl; a.partials = h->d_partials; a.eval_out = h->d_eval;
     a.n = h->n; a.subject_offset = h->subject_offset; a.mode = mode; a.subjects_per_cta = h->subjects_per_cta;
-    if (h->mm.G == 16)
+    if (mode == MODE_STEP && h->static_kernel && !h->force_generic)
+        h->static_kernel<<<h->grid, 256, h->static_smem, h->stream>>>(h->mm.B, h->pl, h->cc, a);
+    else if (h->mm.d.G == 16)
         jmb_step_kernel<16><<<h->grid, 256, h->smem_bytes, h->stream>>>(h->mm, h->pl, h->cc, a);
     else
         jmb_step_kernel<32><<<h->grid, 256, h->smem_bytes, h->stream>>>(h->mm, h->pl, h->cc, a);
@@ -463,7 +510,7 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     CU(cudaSetDevice(h->device));
     const ModelMeta& mm = h->mm;
     const ParamLayout& pl = h->pl;
-    const int n = h->n, q = mm.q, B = mm.B, p = mm.p, A = mm.A;
+    const int n = h->n, q = mm.d.q, B = mm.B, p = mm.d.p, A = mm.d.A;
     if (ct->n_block <= 0 || ct->n_block > h->n_block_cap) return fail("jmb_chain_begin: n_block out of range (1..1024)");
     if (ct->n_iter < 0 || ct->n_burnin < 0 || ct->n_thin <= 0) return fail("jmb_chain_begin: bad control");
     if (pr->n_td < 0 || pr->n_td > JMB_MAX_TERMS) return fail("jmb_chain_begin: too many td effects");
@@ -553,8 +600,8 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     memcpy(h->h_tmp + (size_t)n * q, in->sigma_b, sizeof(double) * n);
     CU(cudaMemcpyAsync(h->d_tmp, h->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaMemcpyHostToDevice, h->stream));
     {
-        const long long tot = (long long)n * mm.state_stride;
-        jmb_load_state_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.state_stride, n, q, h->d_tmp, h->d_tmp + (size_t)n * q);
+        const long long tot = (long long)n * mm.L.state_stride;
+        jmb_load_state_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.L.state_stride, n, q, h->d_tmp, h->d_tmp + (size_t)n * q);
         h->launches += 1;
         CU(cudaGetLastError());
     }
@@ -587,9 +634,9 @@ extern "C" int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, flo
         }
         if (launch_finalize(h, 0)) return 1;
         if (is_keep_iter(h, h->iter_host)) {
-            const long long tot = (long long)h->n * mm.q;
+            const long long tot = (long long)h->n * mm.d.q;
             jmb_extract_b_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
-                h->d_state, mm.state_stride, h->n, mm.q, 0, h->o_b + (size_t)h->keep_host * h->n * mm.q);
+                h->d_state, mm.L.state_stride, h->n, mm.d.q, 0, h->o_b + (size_t)h->keep_host * h->n * mm.d.q);
             h->launches += 1;
             CU(cudaGetLastError());
             h->keep_host += 1; h->check_host += 1;
@@ -611,7 +658,7 @@ extern "C" int jmb_chain_end(jmb_handle h, jmb_chain_out* out) {
     CU(cudaSetDevice(h->device));
     const ModelMeta& mm = h->mm;
     const ParamLayout& pl = h->pl;
-    const int n = h->n, q = mm.q, B = mm.B, p = mm.p, A = mm.A, no = h->n_out;
+    const int n = h->n, q = mm.d.q, B = mm.B, p = mm.d.p, A = mm.d.A, no = h->n_out;
     CU(cudaStreamSynchronize(h->stream));
     h->chain_open = false;
     if (!out) return 0;
@@ -638,8 +685,8 @@ extern "C" int jmb_chain_end(jmb_handle h, jmb_chain_out* out) {
     CU(d2h(out->trace_surv, h->o_trace, 2 * (size_t)h->iter_host));
     if (out->sigma_b || out->accept_b) {
         // columns q (sigma_b) and q+4 (total accepts) of the state
-        jmb_extract_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.state_stride, n, 1, q, h->d_tmp);
-        jmb_extract_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.state_stride, n, 1, q + 4, h->d_tmp + n);
+        jmb_extract_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.L.state_stride, n, 1, q, h->d_tmp);
+        jmb_extract_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.L.state_stride, n, 1, q + 4, h->d_tmp + n);
         h->launches += 2;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(h->stream));
@@ -674,7 +721,7 @@ extern "C" int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* 
     CU(cudaSetDevice(h->device));
     const ModelMeta& mm = h->mm;
     const ParamLayout& pl = h->pl;
-    const int n = h->n, q = mm.q, B = mm.B, p = mm.p, A = mm.A;
+    const int n = h->n, q = mm.d.q, B = mm.B, p = mm.d.p, A = mm.d.A;
     CU(cudaStreamSynchronize(h->stream));
     double* hp = h->h_par;
     memcpy(hp + pl.cur, Bs, sizeof(double) * B);
@@ -686,8 +733,8 @@ extern "C" int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* 
     memcpy(h->h_tmp, b, sizeof(double) * (size_t)n * q);
     for (int i = 0; i < n; ++i) h->h_tmp[(size_t)n * q + i] = 1.0;
     CU(cudaMemcpyAsync(h->d_tmp, h->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaMemcpyHostToDevice, h->stream));
-    const long long tot = (long long)n * mm.state_stride;
-    jmb_load_state_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.state_stride, n, q, h->d_tmp, h->d_tmp + (size_t)n * q);
+    const long long tot = (long long)n * mm.L.state_stride;
+    jmb_load_state_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.L.state_stride, n, q, h->d_tmp, h->d_tmp + (size_t)n * q);
     h->launches += 1;
     CU(cudaGetLastError());
     memset(&h->cc, 0, sizeof(h->cc));
@@ -701,7 +748,7 @@ extern "C" int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* 
 }
 
 extern "C" int jmb_get_row_ptr(jmb_handle h, int outcome, int64_t* row_ptr) {
-    if (!h || outcome < 0 || outcome >= h->mm.O) return fail("jmb_get_row_ptr: bad argument");
+    if (!h || outcome < 0 || outcome >= h->mm.d.O) return fail("jmb_get_row_ptr: bad argument");
     std::vector<int> rp(h->n + 1);
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpy(rp.data(), h->d_rowptr + (size_t)outcome * (h->n + 1), sizeof(int) * (h->n + 1), cudaMemcpyDeviceToHost));
@@ -712,10 +759,10 @@ extern "C" int jmb_get_row_ptr(jmb_handle h, int outcome, int64_t* row_ptr) {
 extern "C" int jmb_layout_info(jmb_handle h, double* shared_bytes, double* chain_bytes, int32_t* w1_band, int32_t* group_lanes) {
     if (!h) return fail("jmb_layout_info: null handle");
     const double n = h->n;
-    if (shared_bytes) *shared_bytes = (8.0 * h->doff[h->n] + 8.0 * 2 * (h->n + 1) + 4.0 * h->mm.O * (h->n + 1)) / n;
-    if (chain_bytes) *chain_bytes = 8.0 * h->coff[h->n] / n + 2.0 * 8.0 * h->mm.state_stride;
-    if (w1_band) *w1_band = h->mm.WB;
-    if (group_lanes) *group_lanes = h->mm.G;
+    if (shared_bytes) *shared_bytes = (8.0 * h->doff[h->n] + 8.0 * 2 * (h->n + 1) + 4.0 * h->mm.d.O * (h->n + 1)) / n;
+    if (chain_bytes) *chain_bytes = 8.0 * h->coff[h->n] / n + 2.0 * 8.0 * h->mm.L.state_stride;
+    if (w1_band) *w1_band = h->mm.d.WB;
+    if (group_lanes) *group_lanes = h->mm.d.G;
     return 0;
 }
 
@@ -723,6 +770,11 @@ extern "C" int jmb_launch_count(jmb_handle h, int64_t* launches) {
     if (!h) return fail("jmb_launch_count: null handle");
     *launches = h->launches;
     return 0;
+}
+
+extern "C" const char* jmb_kernel_name(jmb_handle h) {
+    if (!h) return "";
+    return (h->static_kernel && !h->force_generic) ? h->kernel_name : "generic";
 }
 
 extern "C" void* jmb_stream(jmb_handle h) { return h ? (void*)h->stream : nullptr; }

@@ -6,26 +6,16 @@
 #pragma once
 #include <cstdint>
 #include "../../include/jmb200.h"
+#include "jmb_model.h"
 
 namespace jmb {
 
 // ---- model descriptor passed to the kernels as a __grid_constant__ parameter -----------------
 struct ModelMeta {
-    int O, q, T, A, B, p, K, S;     // S = 1, or 2 with interval censoring
-    int RP;                         // padded number of "hazard rows" per subject: 1 + K*S -> multiple of G
-    int G;                          // lanes per subject (16 or 32)
-    int WB;                         // stored band of the B-spline basis rows (n_Bs when dense)
+    ModelDesc d;                    // what the model is (jmb_model.h)
+    RecordLayout L;                 // where each field lives inside a subject's records
+    int B;                          // n_Bs (only shifts indices into the parameter block)
     int P;                          // B + p + A
-    int fam[JMB_MAX_OUTCOMES], link[JMB_MAX_OUTCOMES], qk[JMB_MAX_OUTCOMES];
-    int re_inds[JMB_MAX_OUTCOMES][JMB_MAX_Q];
-    int rt[JMB_MAX_TERMS], ut[JMB_MAX_TERMS], tf[JMB_MAX_TERMS];
-    int re2[JMB_MAX_TERMS][JMB_MAX_RT];
-    int col[JMB_MAX_TERMS][JMB_MAX_UT];
-    // offsets (in doubles) inside one subject's design record
-    int o_R, o_Pw, o_W1off, o_W1v, o_W2, o_ZZ[JMB_MAX_TERMS], o_U[JMB_MAX_TERMS], o_long;
-    // offsets inside one subject's per-draw record: XXb[T][RP] first, then Xbetas rows
-    int c_long;
-    int state_stride;               // q + 5 doubles: b, sigma_b, log_pyb, log_pb, acc_block, acc_total
 };
 
 // ---- per-chain parameter block in global memory (all doubles; offsets in ParamLayout) ---------
@@ -89,9 +79,9 @@ __device__ __forceinline__ void rnorm_pair(uint32_t seed, uint32_t chain, uint32
     uint32_t r[4];
     philox4x32(seed, chain, c0, c1, c2, c3, r);
     double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
-    double rad = sqrt(-2.0 * log(u1)), ang = 6.283185307179586476925286766559 * u2;
+    double rad = sqrt(-2.0 * log(u1));
     double s, c;
-    sincos(ang, &s, &c);
+    sincospi(2.0 * u2, &s, &c);
     z0 = rad * c;
     z1 = rad * s;
 }

@@ -36,7 +36,8 @@ struct StepArgs {
 };
 
 // -------------------------------------------------------------------------------------------
-// step kernel: G lanes per subject
+// generic step kernel: runtime model descriptor, G lanes per subject.  Fallback for model shapes
+// without a precompiled specialisation (jmb_step_static.cuh); same results.
 // -------------------------------------------------------------------------------------------
 template <int G>
 __global__ void __launch_bounds__(256)
@@ -44,20 +45,22 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
                 const __grid_constant__ ChainConst cc, const __grid_constant__ StepArgs a) {
     constexpr int THREADS = 256;
     constexpr int GROUPS = THREADS / G;
+    const ModelDesc& md = mm.d;
+    const RecordLayout& L = mm.L;
     // [cur P][prop P][invD q*q][inv_sigma O]
     extern __shared__ double smem[];
     double* s_cur = smem;
     double* s_prop = s_cur + mm.P;
     double* s_invD = s_prop + mm.P;
-    double* s_isig = s_invD + mm.q * mm.q;
-    double* s_grp = s_isig + mm.O;                         // per group: b_old[QS], b_new[QS], z[QS]
-    const int QS = mm.q + 5;
+    double* s_isig = s_invD + md.q * md.q;
+    double* s_grp = s_isig + md.O;                         // per group: b_old[QS], b_new[QS], z[QS]
+    const int QS = md.q + 5;
     double* s_red = s_grp + GROUPS * 3 * QS;                // [GROUPS][3]
 
     const int tid = threadIdx.x;
     for (int j = tid; j < mm.P; j += THREADS) { s_cur[j] = a.par[pl.cur + j]; s_prop[j] = a.par[pl.prop + j]; }
-    for (int j = tid; j < mm.q * mm.q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
-    for (int j = tid; j < mm.O; j += THREADS) s_isig[j] = 1.0 / a.par[pl.sigmas + j];
+    for (int j = tid; j < md.q * md.q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
+    for (int j = tid; j < md.O; j += THREADS) s_isig[j] = 1.0 / a.par[pl.sigmas + j];
     const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i;
     __syncthreads();
 
@@ -66,7 +69,7 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
     double* bo = s_grp + grp * 3 * QS;
     double* bn = bo + QS;
     double* zb = bn + QS;
-    const int q = mm.q, RP = mm.RP, K = mm.K, S = mm.S;
+    const int q = md.q, RP = L.RP, K = md.K, S = md.S;
     const bool last_in_block = (i_blk == cc.n_block - 1);
 
     double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;     // lane 0 of each group
@@ -76,7 +79,7 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
     for (int s = s_begin + grp; s < s_end; s += GROUPS) {
         const double* rec = a.drec + a.doff[s];
         const double* crec = a.crec + a.coff[s];
-        double* st = a.state + (long long)s * mm.state_stride;
+        double* st = a.state + (long long)s * L.state_stride;
         const uint32_t gid = (uint32_t)(a.subject_offset + s);
 
         // ---- state + proposal (mvrnorm_cube / extract_b, src/fast_LAPRWM.cpp:123-146,670) ----
@@ -93,7 +96,7 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         if (a.mode == MODE_STEP) {
             const double sd = sqrt(sigma_b);
             for (int j = lane; j < q; j += G) {
-                const double* Rj = rec + mm.o_R + (j * (j + 1)) / 2;    // column j of the upper factor
+                const double* Rj = rec + L.o_R + (j * (j + 1)) / 2;    // column j of the upper factor
                 double pj = 0.0;
                 for (int l = 0; l <= j; ++l) pj += zb[l] * Rj[l];
                 bn[j] = bo[j] + sd * pj;
@@ -114,19 +117,19 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         // ---- GLMM log-density over the visit segment (lin_predF + log_longF, :67-78,168-202) ----
         double v_pyb = 0.0;
         {
-            const double* lrec = rec + mm.o_long;
-            const double* lcrec = crec + mm.c_long;
-            for (int k = 0; k < mm.O; ++k) {
+            const double* lrec = rec + L.o_long;
+            const double* lcrec = crec + L.c_long;
+            for (int k = 0; k < md.O; ++k) {
                 const int* rp = a.rowptr + (long long)k * (a.n + 1);
                 const int v = rp[s + 1] - rp[s];
-                const int qk = mm.qk[k], fam = mm.fam[k], link = mm.link[k];
+                const int qk = md.qk[k], fam = md.fam[k], link = md.link[k], ones0 = md.z_ones0[k];
                 const double isg = s_isig[k];
                 for (int r = lane; r < v; r += G) {
-                    double eta_z = 0.0;
-                    for (int j = 0; j < qk; ++j) eta_z += lrec[(1 + j) * v + r] * bn[mm.re_inds[k][j]];
+                    double eta_z = ones0 ? bn[md.re_inds[k][0]] : 0.0;
+                    for (int j = ones0; j < qk; ++j) eta_z += lrec[(1 + j - ones0) * v + r] * bn[md.re_inds[k][j]];
                     v_pyb += row_logdens(fam, link, lrec[r], lcrec[r] + eta_z, isg);
                 }
-                lrec += (1 + qk) * v;
+                lrec += L.long_cols[k] * v;
                 lcrec += v;
             }
         }
@@ -138,34 +141,35 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         const int cls = (r == 0) ? 0 : (r <= K ? 1 : ((S == 2 && r <= 2 * K) ? 2 : 3));
         double l_co, l_cn, l_po, l_pn;                       // current/proposed params x old/new b
         {
-            const int off = reinterpret_cast<const int*>(rec + mm.o_W1off)[r];
+            const int off = reinterpret_cast<const int*>(rec + L.o_W1off)[r];
             double s1c = 0.0, s1p = 0.0;
-            for (int j = 0; j < mm.WB; ++j) {
-                const double wv = rec[mm.o_W1v + j * RP + r];
+            for (int j = 0; j < md.WB; ++j) {
+                const double wv = rec[L.o_W1v + j * RP + r];
                 s1c += wv * s_cur[off + j];
                 s1p += wv * s_prop[off + j];
             }
             double s2c = 0.0, s2p = 0.0;
-            for (int j = 0; j < mm.p; ++j) {
-                const double wv = rec[mm.o_W2 + j * RP + r];
+            for (int j = 0; j < md.p; ++j) {
+                const double wv = md.w2_const ? rec[L.o_W2c + j] : rec[L.o_W2 + j * RP + r];
                 s2c += wv * s_cur[mm.B + j];
                 s2p += wv * s_prop[mm.B + j];
             }
             double a_co = 0.0, a_cn = 0.0, a_po = 0.0, a_pn = 0.0;
-            const double* alc = s_cur + mm.B + mm.p;
-            const double* alp = s_prop + mm.B + mm.p;
-            for (int t = 0; t < mm.T; ++t) {
+            const double* alc = s_cur + mm.B + md.p;
+            const double* alp = s_prop + mm.B + md.p;
+            for (int t = 0; t < md.T; ++t) {
                 const double xxb = crec[t * RP + r];
-                double zo = 0.0, zn = 0.0;
-                for (int j = 0; j < mm.rt[t]; ++j) {
-                    const double zz = rec[mm.o_ZZ[t] + j * RP + r];
-                    zo += zz * bo[mm.re2[t][j]];
-                    zn += zz * bn[mm.re2[t][j]];
+                const int ones0 = md.zz_ones0[t];
+                double zo = ones0 ? bo[md.re2[t][0]] : 0.0, zn = ones0 ? bn[md.re2[t][0]] : 0.0;
+                for (int j = ones0; j < md.rt[t]; ++j) {
+                    const double zz = rec[L.o_ZZ[t] + (j - ones0) * RP + r];
+                    zo += zz * bo[md.re2[t][j]];
+                    zn += zz * bn[md.re2[t][j]];
                 }
-                const double vo = trans_fun(mm.tf[t], xxb + zo), vn = trans_fun(mm.tf[t], xxb + zn);
-                for (int u = 0; u < mm.ut[t]; ++u) {
-                    const double uu = rec[mm.o_U[t] + u * RP + r];
-                    const int c = mm.col[t][u];
+                const double vo = trans_fun(md.tf[t], xxb + zo), vn = trans_fun(md.tf[t], xxb + zn);
+                for (int u = 0; u < md.ut[t]; ++u) {
+                    const double uu = md.u_ones[t] ? 1.0 : rec[L.o_U[t] + u * RP + r];
+                    const int c = md.col[t][u];
                     const double wo = uu * vo, wn = uu * vn;
                     a_co += wo * alc[c]; a_cn += wn * alc[c];
                     a_po += wo * alp[c]; a_pn += wn * alp[c];
@@ -174,7 +178,7 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
             l_co = (s1c + s2c) + a_co; l_cn = (s1c + s2c) + a_cn;
             l_po = (s1p + s2p) + a_po; l_pn = (s1p + s2p) + a_pn;
         }
-        const double pw = (cls == 1 || cls == 2) ? rec[mm.o_Pw + r] : 0.0;
+        const double pw = (cls == 1 || cls == 2) ? rec[L.o_Pw + r] : 0.0;
         double H_co = 0.0, H_cn = 0.0, HL_co = 0.0, HL_cn = 0.0;
         if (cls == 1) { H_co = pw * exp(l_co); H_cn = pw * exp(l_cn); }
         else if (cls == 2) { HL_co = pw * exp(l_co); HL_cn = pw * exp(l_cn); }
@@ -318,7 +322,7 @@ struct FinalizeArgs {
 // survival proposal for iteration `iter`: cur + sqrt(sigma) * z' chol(Sigma)  (:659-661,732-734)
 __device__ inline void make_proposal(const ModelMeta& mm, const ParamLayout& pl, const ChainConst& cc,
                                      double* par, int iter, int tid, int nthreads, double* s_z) {
-    const int B = mm.B, p = mm.p, A = mm.A;
+    const int B = mm.B, p = mm.d.p, A = mm.d.A;
     for (int s = tid; s < (mm.P + 1) / 2; s += nthreads) {
         double z0, z1;
         rnorm_pair(cc.seed, cc.chain_id, 0u, (uint32_t)iter, (uint32_t)s, ST_SURV, z0, z1);
@@ -345,7 +349,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     __shared__ double s_z[JMB_MAX_BS + JMB_MAX_GAMMAS + JMB_MAX_ALPHAS + 2];
     const int tid = threadIdx.x;
     double* par = a.par;
-    const int B = mm.B, p = mm.p, A = mm.A;
+    const int B = mm.B, p = mm.d.p, A = mm.d.A;
 
     if (a.phase == 1) {
         if (tid == 0) {

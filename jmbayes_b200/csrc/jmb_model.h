@@ -1,0 +1,128 @@
+// jmb_model.h - model descriptor and per-subject record layout, usable at compile time (static
+// step kernels) and at run time (host packer, generic step kernel).
+//
+// A subject's designs live in two contiguous records (units: doubles):
+//
+//   design record (shared by all chains of a fit)
+//     [0] event  [1] pad  [o_R ..] upper Cholesky factor of Covs$b[,,i], packed by column
+//     [o_W2c ..] W2 row when the W2s rows repeat within the subject (w2_const)
+//     hazard rows, one per lane r = 0..RP-1 (0: event time, 1..K: quadrature, K+1..2K: lower-
+//     interval quadrature), each field stored as [column][RP]:
+//       Pw | int32 band offsets of the B-spline rows | WB band values | W2 columns (unless
+//       w2_const) | per term: stored ZZ columns, stored U columns
+//     longitudinal rows, per outcome: y[v] | stored Z columns [v] each
+//   per-draw record: XXbetas/XXsbetas rows [T][RP] | Xbetas rows per outcome
+//
+// "Stored" columns: an all-ones first column of Z / ZZ (random intercept) and an all-ones U
+// (default interaction design ~1) are not stored; the flags below say so.  jmb_create() decides
+// the flags by scanning the data, so they never change results.
+#pragma once
+#include "../../include/jmb200.h"
+
+#if defined(__CUDACC__)
+#define JMB_HD __host__ __device__
+#else
+#define JMB_HD
+#endif
+
+namespace jmb {
+
+constexpr int kMaxO = JMB_MAX_OUTCOMES, kMaxT = JMB_MAX_TERMS, kMaxQ = JMB_MAX_Q;
+constexpr int kMaxRT = JMB_MAX_RT, kMaxUT = JMB_MAX_UT;
+
+struct ModelDesc {
+    int O, q, T, A, p, K, S;        // S = 1, or 2 with interval censoring
+    int WB;                         // stored band of the B-spline basis rows (n_Bs when dense)
+    int G;                          // lanes per subject (16 or 32); RP == G
+    int w2_const;                   // W2s rows equal the W2 row within each subject
+    int fam[kMaxO], link[kMaxO], qk[kMaxO], z_ones0[kMaxO];
+    int re_inds[kMaxO][kMaxQ];
+    int rt[kMaxT], ut[kMaxT], tf[kMaxT], zz_ones0[kMaxT], u_ones[kMaxT];
+    int re2[kMaxT][kMaxRT];
+    int col[kMaxT][kMaxUT];
+};
+
+struct RecordLayout {
+    int RP, o_R, o_W2c, o_Pw, o_W1off, o_W1v, o_W2, o_ZZ[kMaxT], o_U[kMaxT], o_long, c_long;
+    int long_cols[kMaxO];           // stored doubles per longitudinal row of outcome k (y + Z cols)
+    int state_stride;               // q + 5: b, sigma_b, log_pyb, log_pb, acc_block, acc_total
+};
+
+JMB_HD constexpr RecordLayout make_layout(const ModelDesc& d) {
+    RecordLayout L{};
+    L.RP = d.G;
+    L.o_R = 2;
+    int o = 2 + d.q * (d.q + 1) / 2;
+    L.o_W2c = o;
+    if (d.w2_const) o += d.p;
+    o = (o + 1) / 2 * 2;
+    L.o_Pw = o; o += L.RP;
+    L.o_W1off = o; o += L.RP / 2;
+    L.o_W1v = o; o += d.WB * L.RP;
+    L.o_W2 = o;
+    if (!d.w2_const) o += d.p * L.RP;
+    for (int t = 0; t < d.T; ++t) {
+        L.o_ZZ[t] = o; o += (d.rt[t] - d.zz_ones0[t]) * L.RP;
+        L.o_U[t] = o; o += (d.u_ones[t] ? 0 : d.ut[t]) * L.RP;
+    }
+    L.o_long = o;
+    L.c_long = d.T * L.RP;
+    for (int k = 0; k < d.O; ++k) L.long_cols[k] = 1 + d.qk[k] - d.z_ones0[k];
+    L.state_stride = d.q + 5;
+    return L;
+}
+
+JMB_HD constexpr bool same_desc(const ModelDesc& a, const ModelDesc& b) {
+    if (a.O != b.O || a.q != b.q || a.T != b.T || a.A != b.A || a.p != b.p || a.K != b.K || a.S != b.S ||
+        a.WB != b.WB || a.G != b.G || a.w2_const != b.w2_const) return false;
+    for (int k = 0; k < a.O; ++k) {
+        if (a.fam[k] != b.fam[k] || a.link[k] != b.link[k] || a.qk[k] != b.qk[k] || a.z_ones0[k] != b.z_ones0[k]) return false;
+        for (int j = 0; j < a.qk[k]; ++j) if (a.re_inds[k][j] != b.re_inds[k][j]) return false;
+    }
+    for (int t = 0; t < a.T; ++t) {
+        if (a.rt[t] != b.rt[t] || a.ut[t] != b.ut[t] || a.tf[t] != b.tf[t] || a.zz_ones0[t] != b.zz_ones0[t] ||
+            a.u_ones[t] != b.u_ones[t]) return false;
+        for (int j = 0; j < a.rt[t]; ++j) if (a.re2[t][j] != b.re2[t][j]) return false;
+        for (int u = 0; u < a.ut[t]; ++u) if (a.col[t][u] != b.col[t][u]) return false;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Precompiled model shapes (BASELINE.json configs).  Any other model runs the generic kernel.
+// ---------------------------------------------------------------------------------------------
+// configs 1 and 2: one gaussian outcome, random intercept + slope, current-value association
+JMB_HD constexpr ModelDesc desc_value_gaussian() {
+    ModelDesc d{};
+    d.O = 1; d.q = 2; d.T = 1; d.A = 1; d.p = 2; d.K = 15; d.S = 1; d.WB = 4; d.G = 16; d.w2_const = 1;
+    d.fam[0] = JMB_FAM_GAUSSIAN; d.link[0] = JMB_LINK_IDENTITY; d.qk[0] = 2; d.z_ones0[0] = 1;
+    d.re_inds[0][0] = 0; d.re_inds[0][1] = 1;
+    d.rt[0] = 2; d.ut[0] = 1; d.tf[0] = JMB_TF_IDENTITY; d.zz_ones0[0] = 1; d.u_ones[0] = 1;
+    d.re2[0][0] = 0; d.re2[0][1] = 1; d.col[0][0] = 0;
+    return d;
+}
+
+// configs 3 and 4: gaussian + binomial(logit) + poisson(log), q = 6, value + slope per outcome
+JMB_HD constexpr ModelDesc desc_three_outcomes(int S) {
+    ModelDesc d{};
+    d.O = 3; d.q = 6; d.T = 6; d.A = 6; d.p = 2; d.K = 15; d.S = S; d.WB = 4; d.G = (S == 2) ? 32 : 16;
+    d.w2_const = 1;
+    d.fam[0] = JMB_FAM_GAUSSIAN; d.link[0] = JMB_LINK_IDENTITY;
+    d.fam[1] = JMB_FAM_BINOMIAL; d.link[1] = JMB_LINK_LOGIT;
+    d.fam[2] = JMB_FAM_POISSON; d.link[2] = JMB_LINK_LOG;
+    for (int k = 0; k < 3; ++k) {
+        d.qk[k] = 2; d.z_ones0[k] = 1; d.re_inds[k][0] = 2 * k; d.re_inds[k][1] = 2 * k + 1;
+        const int tv = 2 * k, ts = 2 * k + 1;
+        d.rt[tv] = 2; d.ut[tv] = 1; d.tf[tv] = JMB_TF_IDENTITY; d.zz_ones0[tv] = 1; d.u_ones[tv] = 1;
+        d.re2[tv][0] = 2 * k; d.re2[tv][1] = 2 * k + 1; d.col[tv][0] = tv;
+        d.rt[ts] = 1; d.ut[ts] = 1; d.tf[ts] = JMB_TF_IDENTITY; d.zz_ones0[ts] = 1; d.u_ones[ts] = 1;
+        d.re2[ts][0] = 2 * k + 1; d.col[ts][0] = ts;
+    }
+    return d;
+}
+
+struct SpecValueGaussian { static constexpr ModelDesc d = desc_value_gaussian(); static constexpr RecordLayout L = make_layout(d); };
+struct SpecThreeOutcomes { static constexpr ModelDesc d = desc_three_outcomes(1); static constexpr RecordLayout L = make_layout(d); };
+struct SpecThreeOutcomesIC { static constexpr ModelDesc d = desc_three_outcomes(2); static constexpr RecordLayout L = make_layout(d); };
+
+}  // namespace jmb

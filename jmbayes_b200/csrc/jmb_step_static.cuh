@@ -1,0 +1,322 @@
+// jmb_step_static.cuh - compile-time-specialised step kernel (sm_100a).
+//
+// Same work as jmb_step_kernel (one full b-step + the subject's share of the survival step per
+// subject and iteration; src/fast_LAPRWM.cpp:666-757), but the model shape (outcomes, families,
+// terms, column maps, compaction flags) is a constexpr descriptor (jmb_model.h), so every loop
+// over outcomes / terms / columns is unrolled, b_i (old and proposed) lives in registers from
+// proposal to acceptance, and the only runtime loop is the ragged visit segment.  One lane per
+// hazard row (event time + K quadrature nodes [+ K lower-interval nodes]); G = 16 or 32 lanes
+// per subject.  Reductions are xor-butterflies inside the lane group.
+#pragma once
+#include <utility>
+
+#include "jmb_kernels.cuh"
+
+namespace jmb {
+
+template <class F, int... I>
+__device__ __forceinline__ void sfor_impl(F&& f, std::integer_sequence<int, I...>) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+// compile-time loop: f(integral_constant<int, 0>) ... f(integral_constant<int, N-1>)
+template <int N, class F>
+__device__ __forceinline__ void sfor(F&& f) {
+    sfor_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
+
+template <int TF>
+__device__ __forceinline__ double trans_static(double x) {
+    if constexpr (TF == JMB_TF_IDENTITY) return x;
+    else return trans_fun(TF, x);
+}
+
+// Per-row log-density (src/fast_LAPRWM.cpp:177-199).  For 0/1 responses the logit/probit/cloglog
+// branch evaluates only the live logarithm and reproduces the naive formula's NaN when the dead
+// term would be 0 * (-inf); the Poisson branch uses y*eta for y*log(exp(eta)) with the same
+// overflow / underflow outcomes.  Anything else goes through the literal formulas.
+template <int FAM, int LINK>
+__device__ __forceinline__ double logdens_static(double y, double eta, double inv_sigma) {
+    if constexpr (FAM == JMB_FAM_GAUSSIAN) {
+        const double t = (y - eta) * inv_sigma;
+        return -0.5 * (t * t);
+    } else if constexpr (FAM == JMB_FAM_BINOMIAL) {
+        double pr;
+        if constexpr (LINK == JMB_LINK_LOGIT) { const double e = exp(eta); pr = e / (1.0 + e); }
+        else if constexpr (LINK == JMB_LINK_PROBIT) pr = 0.5 * erfc(-eta * 0.70710678118654752440);
+        else pr = -exp(-exp(eta)) + 1.0;
+        const bool one = (y == 1.0), zero = (y == 0.0);
+        if (one || zero) {
+            const double ld = log(one ? pr : 1.0 - pr);
+            const bool dead_inf = one ? (pr == 1.0) : (pr == 0.0);      // 0 * log(0) in the naive formula
+            return dead_inf ? __longlong_as_double(0x7ff8000000000000LL) : ld;
+        }
+        return y * log(pr) + (1.0 - y) * log(1.0 - pr);
+    } else {
+        if constexpr (LINK == JMB_LINK_LOG) {
+            const double mu = exp(eta);
+            double ld = y * eta - mu;
+            if (mu == 0.0) ld = (y == 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : (y > 0.0 ? -INFINITY : INFINITY);
+            return ld;                                                   // mu == inf gives inf - inf = NaN already
+        } else {
+            return row_logdens(FAM, LINK, y, eta, inv_sigma);
+        }
+    }
+}
+
+// event / censoring term for a lane group (uniform across its lanes), src/fast_LAPRWM.cpp:640-650
+template <int S>
+__device__ __forceinline__ double log_ptb_static(double event, double lh, double H, double HL) {
+    if constexpr (S == 2) {
+        if (event == 1.0) return lh - H;
+        if (event == 0.0) return 0.0 - H;
+        if (event == 2.0) return log(1.0 - exp(-H));
+        if (event == 3.0) return log(exp(-HL) - exp(-H));
+        return 0.0;
+    } else {
+        return event * lh - H;
+    }
+}
+
+#ifndef JMB_STATIC_MIN_CTAS
+#define JMB_STATIC_MIN_CTAS 2
+#endif
+
+template <class Spec>
+__global__ void __launch_bounds__(256, JMB_STATIC_MIN_CTAS)
+jmb_step_static(const int B, const __grid_constant__ ParamLayout pl, const __grid_constant__ ChainConst cc,
+                const __grid_constant__ StepArgs a) {
+    constexpr int G = Spec::d.G, q = Spec::d.q, O = Spec::d.O, T = Spec::d.T, A = Spec::d.A, p = Spec::d.p;
+    constexpr int K = Spec::d.K, S = Spec::d.S, WB = Spec::d.WB, RP = Spec::L.RP, QS = q + 5;
+    constexpr int THREADS = 256, GROUPS = THREADS / G, NP = (q + 1) / 2;
+    constexpr int oR = Spec::L.o_R, oLong = Spec::L.o_long, cLong = Spec::L.c_long, oW1off = Spec::L.o_W1off;
+    constexpr int oW1v = Spec::L.o_W1v, oW2c = Spec::L.o_W2c, oW2 = Spec::L.o_W2, oPw = Spec::L.o_Pw;
+    constexpr bool W2C = Spec::d.w2_const != 0;
+    static_assert(RP == G && 1 + K * S <= G && NP < G && QS <= G, "one hazard row per lane");
+    const int P = B + p + A;
+
+    extern __shared__ double smem[];
+    double* s_cur = smem;                 // [P] current Bs_gammas | gammas | alphas
+    double* s_prop = s_cur + P;           // [P] proposed
+    double* s_invD = s_prop + P;          // [q*q]
+    double* s_red = s_invD + q * q;       // [GROUPS][3]
+
+    const int tid = threadIdx.x;
+    for (int j = tid; j < P; j += THREADS) { s_cur[j] = a.par[pl.cur + j]; s_prop[j] = a.par[pl.prop + j]; }
+    for (int j = tid; j < q * q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
+    const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i;
+    double isig[O];
+    sfor<O>([&](auto kc) { isig[kc] = 1.0 / a.par[pl.sigmas + kc]; });
+    __syncthreads();
+    // loop-invariant small parameter vectors in registers
+    double gc[p > 0 ? p : 1], gp[p > 0 ? p : 1], alc[A], alp[A];
+    sfor<p>([&](auto j) { gc[j] = s_cur[B + j]; gp[j] = s_prop[B + j]; });
+    sfor<A>([&](auto j) { alc[j] = s_cur[B + p + j]; alp[j] = s_prop[B + p + j]; });
+
+    const int grp = tid / G, lane = tid % G;
+    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (0xFFFFu << (16 * ((tid & 31) >> 4)));
+    const bool last_in_block = (i_blk == cc.n_block - 1);
+    const int cls = (lane == 0) ? 0 : (lane <= K ? 1 : ((S == 2 && lane <= 2 * K) ? 2 : 3));
+    const bool quad = (cls == 1 || cls == 2);
+
+    double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;
+    const int s_begin = blockIdx.x * a.subjects_per_cta;
+    const int s_end = min(a.n, s_begin + a.subjects_per_cta);
+
+    for (int s = s_begin + grp; s < s_end; s += GROUPS) {
+        const double* __restrict__ rec = a.drec + a.doff[s];
+        const double* __restrict__ crec = a.crec + a.coff[s];
+        double* st = a.state + (long long)s * QS;
+        const uint32_t gid = (uint32_t)(a.subject_offset + s);
+
+        // ---- current state (uniform loads) ----
+        double bo[q], bn[q];
+        sfor<q>([&](auto j) { bo[j] = st[j]; });
+        const double sigma_b = st[q], pyb_old = st[q + 1], pb_old = st[q + 2];
+        double accb = st[q + 3], acct = st[q + 4];
+
+        // ---- random draws: lanes 0..NP-1 one Box-Muller pair each, lane NP the accept uniform ----
+        double log_u;
+        {
+            const uint32_t slot = (lane < NP) ? (uint32_t)lane : 0u;
+            const uint32_t stream = (lane < NP) ? ST_B_PROP : ST_B_ACC;
+            uint32_t rr[4];
+            philox4x32(cc.seed, cc.chain_id, gid, (uint32_t)iter, slot, stream, rr);
+            const double u1 = u01(rr[0], rr[1]), u2 = u01(rr[2], rr[3]);
+            const double lg = log(u1);
+            const double rad = sqrt(-2.0 * lg);
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            const double z0 = rad * cs, z1 = rad * sn;
+            log_u = __shfl_sync(gmask, lg, NP, G);
+            // proposal: b + sqrt(sigma_b) * z' R_i  (mvrnorm_cube / extract_b, :123-146,670)
+            double z[q];
+            sfor<q>([&](auto j) { z[j] = __shfl_sync(gmask, (j & 1) ? z1 : z0, j >> 1, G); });
+            const double sd = sqrt(sigma_b);
+            sfor<q>([&](auto jc) {
+                constexpr int j = jc;
+                double pj = 0.0;
+                sfor<j + 1>([&](auto l) { pj += z[l] * rec[oR + (j * (j + 1)) / 2 + l]; });
+                bn[j] = bo[j] + sd * pj;
+            });
+        }
+
+        // ---- log p(b) at the proposal (:673) ----
+        double pb_new = 0.0;
+        sfor<q>([&](auto jc) {
+            constexpr int j = jc;
+            double t = 0.0;
+            sfor<q>([&](auto l) { t += bn[l] * s_invD[l + j * q]; });
+            pb_new += t * bn[j];
+        });
+        pb_new *= -0.5;
+
+        // ---- GLMM log-density over the visit segment (lin_predF + log_longF, :67-78,168-202) ----
+        double v_pyb = 0.0;
+        {
+            const double* __restrict__ lrec = rec + oLong;
+            const double* __restrict__ lcrec = crec + cLong;
+            sfor<O>([&](auto kc) {
+                constexpr int k = kc;
+                constexpr int ones0 = Spec::d.z_ones0[k], qk = Spec::d.qk[k];
+                const int* rp = a.rowptr + (long long)k * (a.n + 1);
+                const int v = rp[s + 1] - rp[s];
+                for (int r = lane; r < v; r += G) {
+                    double eta = lcrec[r];
+                    if constexpr (ones0 == 1) { constexpr int c0 = Spec::d.re_inds[k][0]; eta += bn[c0]; }
+                    sfor<qk - ones0>([&](auto jc) {
+                        constexpr int j = jc;
+                        constexpr int cj = Spec::d.re_inds[k][j + ones0];
+                        eta += lrec[(1 + j) * v + r] * bn[cj];
+                    });
+                    v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta, isig[k]);
+                }
+                constexpr int lcols = Spec::L.long_cols[k];
+                lrec += lcols * v;
+                lcrec += v;
+            });
+        }
+
+        // ---- hazard row of this lane under current / proposed parameters and old / new b
+        //      (lin_pred_matF :80-109, log_h :684, H/HL :685-691, survival step :735-741) ----
+        double l_co, l_cn, l_po, l_pn;
+        {
+            const int off = reinterpret_cast<const int*>(rec + oW1off)[lane];
+            double s1c = 0.0, s1p = 0.0;
+            sfor<WB>([&](auto j) {
+                const double wv = rec[oW1v + j * RP + lane];
+                s1c += wv * s_cur[off + j];
+                s1p += wv * s_prop[off + j];
+            });
+            double s2c = 0.0, s2p = 0.0;
+            sfor<p>([&](auto j) {
+                const double wv = W2C ? rec[oW2c + j] : rec[oW2 + j * RP + lane];
+                s2c += wv * gc[j];
+                s2p += wv * gp[j];
+            });
+            double a_co = 0.0, a_cn = 0.0, a_po = 0.0, a_pn = 0.0;
+            sfor<T>([&](auto tc) {
+                constexpr int t = tc;
+                constexpr int ones0 = Spec::d.zz_ones0[t], rt = Spec::d.rt[t];
+                const double xxb = crec[t * RP + lane];
+                double zo = 0.0, zn = 0.0;
+                if constexpr (ones0 == 1) { constexpr int c0 = Spec::d.re2[t][0]; zo = bo[c0]; zn = bn[c0]; }
+                constexpr int oZZ = Spec::L.o_ZZ[t], oU = Spec::L.o_U[t];
+                sfor<rt - ones0>([&](auto jc) {
+                    constexpr int j = jc;
+                    constexpr int cj = Spec::d.re2[t][j + ones0];
+                    const double zz = rec[oZZ + j * RP + lane];
+                    zo += zz * bo[cj];
+                    zn += zz * bn[cj];
+                });
+                const double vo = trans_static<Spec::d.tf[t]>(xxb + zo), vn = trans_static<Spec::d.tf[t]>(xxb + zn);
+                sfor<Spec::d.ut[t]>([&](auto uc) {
+                    constexpr int u = uc;
+                    constexpr int c = Spec::d.col[t][u];
+                    double wo = vo, wn = vn;
+                    if constexpr (Spec::d.u_ones[t] == 0) {
+                        const double uu = rec[oU + u * RP + lane];
+                        wo *= uu; wn *= uu;
+                    }
+                    a_co += wo * alc[c]; a_cn += wn * alc[c];
+                    a_po += wo * alp[c]; a_pn += wn * alp[c];
+                });
+            });
+            l_co = (s1c + s2c) + a_co; l_cn = (s1c + s2c) + a_cn;
+            l_po = (s1p + s2p) + a_po; l_pn = (s1p + s2p) + a_pn;
+        }
+        const double pw = quad ? rec[oPw + lane] : 0.0;
+        const double event = rec[0];
+
+        // ---- reductions: visit segment over the group; quadrature rows inside 16-lane halves ----
+        double e_co = quad ? pw * exp(l_co) : 0.0, e_cn = quad ? pw * exp(l_cn) : 0.0;
+        double H_co, H_cn, HL_co = 0.0, HL_cn = 0.0;
+        if constexpr (S == 1 || K == 15) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                e_co += __shfl_xor_sync(gmask, e_co, o, 16);
+                e_cn += __shfl_xor_sync(gmask, e_cn, o, 16);
+            }
+            if constexpr (S == 2) {
+                H_co = __shfl_sync(gmask, e_co, 0, G); HL_co = __shfl_sync(gmask, e_co, 16, G);
+                H_cn = __shfl_sync(gmask, e_cn, 0, G); HL_cn = __shfl_sync(gmask, e_cn, 16, G);
+            } else { H_co = e_co; H_cn = e_cn; }
+        } else {
+            H_co = group_sum<G>(cls == 1 ? e_co : 0.0, gmask); HL_co = group_sum<G>(cls == 2 ? e_co : 0.0, gmask);
+            H_cn = group_sum<G>(cls == 1 ? e_cn : 0.0, gmask); HL_cn = group_sum<G>(cls == 2 ? e_cn : 0.0, gmask);
+        }
+        const double pyb_new = group_sum<G>(v_pyb, gmask);
+        const double h_co = __shfl_sync(gmask, l_co, 0, G), h_cn = __shfl_sync(gmask, l_cn, 0, G);
+        const double h_po = __shfl_sync(gmask, l_po, 0, G), h_pn = __shfl_sync(gmask, l_pn, 0, G);
+
+        const double ptb_co = log_ptb_static<S>(event, h_co, H_co, HL_co);
+        const double ptb_cn = log_ptb_static<S>(event, h_cn, H_cn, HL_cn);
+        const double cur_lp = pyb_old + ptb_co + pb_old;                 // :669
+        const double new_lp = pyb_new + ptb_cn + pb_new;                 // :703
+        const bool accept = log_u < (new_lp - cur_lp);                   // :706 (NaN rejects)
+
+        // ---- proposed survival parameters at the accepted b (:735-752) ----
+        double e_p = quad ? pw * exp(accept ? l_pn : l_po) : 0.0;
+        double Hp, HLp = 0.0;
+        if constexpr (S == 1 || K == 15) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) e_p += __shfl_xor_sync(gmask, e_p, o, 16);
+            if constexpr (S == 2) { Hp = __shfl_sync(gmask, e_p, 0, G); HLp = __shfl_sync(gmask, e_p, 16, G); }
+            else Hp = e_p;
+        } else {
+            Hp = group_sum<G>(cls == 1 ? e_p : 0.0, gmask); HLp = group_sum<G>(cls == 2 ? e_p : 0.0, gmask);
+        }
+        const double ptb_c = accept ? ptb_cn : ptb_co;
+        const double ptb_p = log_ptb_static<S>(event, accept ? h_pn : h_po, Hp, HLp);
+        const double pyb_acc = accept ? pyb_new : pyb_old;
+        const double pb_acc = accept ? pb_new : pb_old;
+        acc_cur += ptb_c; acc_prop += ptb_p; acc_lw += pyb_acc + pb_acc;
+
+        // ---- state write-back (:707-724) + per-subject scale adaptation at block ends (:853-859) ----
+        accb += accept ? 1.0 : 0.0;
+        acct += accept ? 1.0 : 0.0;
+        double sig_new = sigma_b;
+        if (last_in_block) {
+            const double g2 = cc.c0 * pow((double)(it_blk + 1), cc.mc1);
+            sig_new = exp(log(sigma_b) + g2 * (accb / cc.n_block - cc.target_acc));
+            sig_new = fmin(fmax(sig_new, cc.eps1), cc.eps3);              // bounds_sigma :411-419
+            accb = 0.0;
+        }
+        double outv = acct;
+        sfor<q>([&](auto j) { if (lane == j) outv = accept ? bn[j] : bo[j]; });
+        if (lane == q) outv = sig_new;
+        if (lane == q + 1) outv = pyb_acc;
+        if (lane == q + 2) outv = pb_acc;
+        if (lane == q + 3) outv = accb;
+        if (lane < QS && (accept || lane >= q)) st[lane] = outv;
+    }
+
+    if (lane == 0) { s_red[grp * 3] = acc_cur; s_red[grp * 3 + 1] = acc_prop; s_red[grp * 3 + 2] = acc_lw; }
+    __syncthreads();
+    if (tid < 3) {
+        double t = 0.0;
+        for (int g = 0; g < GROUPS; ++g) t += s_red[g * 3 + tid];
+        a.partials[blockIdx.x * 3 + tid] = t;
+    }
+}
+
+}  // namespace jmb

@@ -54,7 +54,20 @@ double orc_u01(uint32_t hi, uint32_t lo) {
     return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-#define ORC_2PI 6.283185307179586476925286766559
+#define ORC_PI 3.14159265358979323846264338327950288
+
+/* sin(pi x), cos(pi x) for x in [0, 2] with exact range reduction (the CUDA path uses sincospi) */
+static void orc_sincospi(double x, double* s, double* c) {
+    double qd = rint(2.0 * x);            /* nearest multiple of 1/2 */
+    double t = x - 0.5 * qd;              /* exact, |t| <= 1/4 */
+    double st = sin(ORC_PI * t), ct = cos(ORC_PI * t);
+    switch (((int)qd) & 3) {
+        case 0: *s = st; *c = ct; break;
+        case 1: *s = ct; *c = -st; break;
+        case 2: *s = -st; *c = -ct; break;
+        default: *s = -ct; *c = st; break;
+    }
+}
 
 /* Box-Muller pair from one Philox block */
 void orc_rnorm_pair(uint32_t seed, uint32_t chain, uint32_t c0, uint32_t c1, uint32_t c2,
@@ -62,9 +75,10 @@ void orc_rnorm_pair(uint32_t seed, uint32_t chain, uint32_t c0, uint32_t c1, uin
     uint32_t r[4];
     orc_philox4x32(seed, chain, c0, c1, c2, c3, r);
     double u1 = orc_u01(r[0], r[1]), u2 = orc_u01(r[2], r[3]);
-    double rad = sqrt(-2.0 * log(u1)), ang = ORC_2PI * u2;
-    z[0] = rad * cos(ang);
-    z[1] = rad * sin(ang);
+    double rad = sqrt(-2.0 * log(u1)), sn, cs;
+    orc_sincospi(2.0 * u2, &sn, &cs);
+    z[0] = rad * cs;
+    z[1] = rad * sn;
 }
 
 enum { ST_B_PROP = 0, ST_B_ACC = 1, ST_SURV = 2, ST_GIBBS_N = 3, ST_GIBBS_U = 4, ST_GIBBS_B = 5 };

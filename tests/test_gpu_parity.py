@@ -90,6 +90,52 @@ def test_chain_matches_oracle_draw_for_draw(cuda_lib, oracle, cfg):
     assert got["mcmc"]["b"].shape[2] == 4 and np.abs(got["mcmc"]["b"][:, :, -1]).sum() > 0
 
 
+@pytest.mark.parametrize("cfg", ["config2", "config3", "config4"])
+def test_static_and_generic_kernels_agree(cuda_lib, cfg, monkeypatch):
+    """The BASELINE shapes get a compile-time-specialised step kernel; the generic kernel must
+    produce the same chain."""
+    c = make_cohort(cfg, n=300)
+    ctl = dict(c["control"]); ctl.update(n_burnin=30, n_iter=20, n_block=10, n_thin=10)
+    with cuda_lib.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
+        assert fit.layout_info()["kernel"].startswith("static:")
+        fit.set_draw(c["Data"])
+        a = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    monkeypatch.setenv("JMB_FORCE_GENERIC", "1")
+    with cuda_lib.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
+        assert fit.layout_info()["kernel"] == "generic"
+        fit.set_draw(c["Data"])
+        b = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    assert _rel(a["extras"]["trace_surv"], b["extras"]["trace_surv"]) <= 1e-10
+    assert np.allclose(a["mcmc"]["b"], b["mcmc"]["b"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(a["scales"]["sigma"]["b"], b["scales"]["sigma"]["b"], rtol=1e-10)
+
+
+def test_uncompacted_designs_use_generic_layout(cuda_lib, oracle):
+    """Non-constant U, time-varying W2s and no intercept columns: nothing is compacted."""
+    c = make_cohort("config3", n=300)
+    D = c["Data"]
+    rng = np.random.default_rng(5)
+    n, K = 300, 15
+    D["U"] = [np.asfortranarray(1.0 + 0.1 * rng.normal(size=u.shape)) for u in D["U"]]
+    D["Us"] = [np.asfortranarray(1.0 + 0.1 * rng.normal(size=u.shape)) for u in D["Us"]]
+    D["W2s"] = np.asfortranarray(np.asarray(D["W2s"]) + 0.05 * rng.normal(size=D["W2s"].shape))
+    D["ZZs"] = [np.asfortranarray(np.asarray(z) * (1.0 + 0.01 * rng.normal(size=(z.shape[0], 1)))) for z in D["ZZs"]]
+    D["Z"] = [np.asfortranarray(np.asarray(z) * 1.5) for z in D["Z"]]
+    ini = c["inits"]
+    oracle.set_rowsum_mode(1)
+    ref = oracle.eval_logpost_re(D, c["Covs"]["b"], False, ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+    with cuda_lib.Fit(D, c["Covs"]["b"], False) as fit:
+        assert fit.layout_info()["kernel"] == "generic"
+        fit.set_draw(D)
+        got = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+    for key in ("log_pyb", "log_pb", "log_h", "H", "log_ptb"):
+        assert _rel(got[key], ref[key]) <= RTOL, (key, _rel(got[key], ref[key]))
+    ctl = dict(c["control"]); ctl.update(n_burnin=20, n_iter=20, n_block=10, n_thin=10)
+    r1 = oracle.lap_rwm_C(c["inits"], D, c["priors"], c["scales"], c["Covs"], ctl, False)
+    r2 = cuda_lib.lap_rwm_C(c["inits"], D, c["priors"], c["scales"], c["Covs"], ctl, False)
+    assert _rel(r2["extras"]["trace_surv"], r1["extras"]["trace_surv"]) <= 1e-9
+
+
 def test_adapt_cov_and_shrinkage_chain(cuda_lib, oracle):
     c = make_cohort("config3", n=200)
     ctl = dict(c["control"]); ctl.update(n_burnin=40, n_iter=40, n_block=10, n_thin=7, adaptCov=True)
