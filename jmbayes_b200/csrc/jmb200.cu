@@ -105,24 +105,65 @@ struct jmb_handle_s {
     long long launches = 0;
     // step kernel chosen for this model: a precompiled static specialisation or the generic one
     void (*static_kernel)(int, ParamLayout, ChainConst, StepArgs) = nullptr;
+    void (*tma_kernel)(int, ParamLayout, ChainConst, StepArgs, TmaArgs) = nullptr;
     const char* kernel_name = "generic";
-    int static_smem = 0;
-    bool force_generic = false;
-    void select_kernel();
+    std::string kernel_label;
+    int static_smem = 0, tma_smem = 0, tma_grid = 0, num_sms = 148;
+    TmaArgs ta{};
+    int kernel_mode = 0;            // 0 generic, 1 static direct, 2 static TMA-staged
+    int select_kernel();
     // multi-GPU
     ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
 };
 
-void jmb_handle_s::select_kernel() {
-    static_kernel = nullptr; kernel_name = "generic";
+int jmb_handle_s::select_kernel() {
+    static_kernel = nullptr; tma_kernel = nullptr; kernel_name = "generic"; kernel_mode = 0;
     const ModelDesc& md = mm.d;
-    if (same_desc(md, SpecValueGaussian::d)) { static_kernel = jmb_step_static<SpecValueGaussian>; kernel_name = "static:value_gaussian"; }
-    else if (same_desc(md, SpecThreeOutcomes::d)) { static_kernel = jmb_step_static<SpecThreeOutcomes>; kernel_name = "static:three_outcomes"; }
-    else if (same_desc(md, SpecThreeOutcomesIC::d)) { static_kernel = jmb_step_static<SpecThreeOutcomesIC>; kernel_name = "static:three_outcomes_ic"; }
-    static_smem = (int)sizeof(double) * (2 * mm.P + md.q * md.q + (256 / md.G) * 3);
-    const char* env = getenv("JMB_FORCE_GENERIC");
-    if (env && env[0] == '1') force_generic = true;
+    if (same_desc(md, SpecValueGaussian::d)) {
+        static_kernel = jmb_step_static<SpecValueGaussian>; tma_kernel = jmb_step_tma<SpecValueGaussian>; kernel_name = "value_gaussian";
+    } else if (same_desc(md, SpecThreeOutcomes::d)) {
+        static_kernel = jmb_step_static<SpecThreeOutcomes>; tma_kernel = jmb_step_tma<SpecThreeOutcomes>; kernel_name = "three_outcomes";
+    } else if (same_desc(md, SpecThreeOutcomesIC::d)) {
+        static_kernel = jmb_step_static<SpecThreeOutcomesIC>; tma_kernel = jmb_step_tma<SpecThreeOutcomesIC>; kernel_name = "three_outcomes_ic";
+    }
+    const int groups = 256 / md.G, spw = 32 / md.G, SS = mm.L.state_stride;
+    static_smem = (int)sizeof(double) * (2 * mm.P + md.q * md.q + groups * 3);
+    if (static_kernel) kernel_mode = 1;
+    if (tma_kernel) {
+        // per-warp stage capacity: the largest run of `spw` consecutive records
+        long long max_d = 0, max_c = 0;
+        for (int i = 0; i + spw <= n || i == 0; i += 1) {
+            const int j = std::min(n, i + spw);
+            max_d = std::max(max_d, doff[j] - doff[i]);
+            max_c = std::max(max_c, coff[j] - coff[i]);
+            if (j == n) break;
+        }
+        ta.cap_d = (int)((max_d + 1) / 2 * 2);
+        ta.cap_c = (int)((max_c + 1) / 2 * 2);
+        const int head = (2 * mm.P + md.q * md.q + groups * 3 + 8 * 2 + 1) / 2 * 2;
+        const long long stage = (long long)ta.cap_d + ta.cap_c + spw * SS;
+        const long long bytes = 8LL * (head + 8LL * 2 * stage);
+        if (bytes <= 113 * 1024) {
+            tma_smem = (int)bytes;
+            const int unit = 8 * spw;
+            int g = std::min((n + unit - 1) / unit, 2 * num_sms);
+            int spc = ((n + g - 1) / g + unit - 1) / unit * unit;
+            ta.subjects_per_cta = spc;
+            tma_grid = (n + spc - 1) / spc;
+            cudaError_t e = cudaFuncSetAttribute((const void*)tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem);
+            if (e != cudaSuccess) { g_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
+            kernel_mode = 2;
+        }
+    }
+    const char* env = getenv("JMB_KERNEL");   // generic | direct | tma : force a slower variant (tests, A/B runs)
+    if (env) {
+        if (!strcmp(env, "generic")) kernel_mode = 0;
+        else if (!strcmp(env, "direct") && static_kernel) kernel_mode = 1;
+    }
+    if (getenv("JMB_FORCE_GENERIC") && getenv("JMB_FORCE_GENERIC")[0] == '1') kernel_mode = 0;
+    kernel_label = kernel_mode == 0 ? std::string("generic") : (kernel_mode == 1 ? std::string("static:") : std::string("static-tma:")) + (kernel_mode ? kernel_name : "");
+    return 0;
 }
 
 template <typename F>
@@ -320,6 +361,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
         for (int i = lo; i < hi; ++i) {
             double* rec = drec.data() + h->doff[i];
             rec[0] = d->event[i];
+            for (int k = 0; k < O; ++k) reinterpret_cast<int*>(rec + L.o_V)[k] = h->rowptr[k][i + 1] - h->rowptr[k][i];
             const double* Rm = d->Covs_b + (long long)i * q * q;
             for (int j = 0; j < q; ++j)
                 for (int l = 0; l <= j; ++l) rec[L.o_R + j * (j + 1) / 2 + l] = Rm[l + j * q];
@@ -399,8 +441,13 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     h->subjects_per_cta = groups * 4;
     h->grid = (n + h->subjects_per_cta - 1) / h->subjects_per_cta;
     h->smem_bytes = (int)sizeof(double) * (2 * mm.P + q * q + O + groups * 3 * (q + 5) + groups * 3);
-    h->select_kernel();
-    CUH(cudaMalloc(&h->d_partials, sizeof(double) * 3 * (size_t)h->grid));
+    {
+        cudaDeviceProp prop;
+        CUH(cudaGetDeviceProperties(&prop, device));
+        h->num_sms = prop.multiProcessorCount;
+        if (h->select_kernel()) { std::string m_ = g_err; jmb_destroy(h); return fail(m_); }
+    }
+    CUH(cudaMalloc(&h->d_partials, sizeof(double) * 3 * (size_t)std::max(h->grid, h->tma_grid)));
     CUH(cudaEventCreate(&h->ev0)); CUH(cudaEventCreate(&h->ev1));
     CUH(cudaEventCreate(&h->evk0)); CUH(cudaEventCreate(&h->evk1));
 #undef CUH
@@ -473,7 +520,9 @@ static int launch_step(jmb_handle h, int mode) {
     a.drec = h->d_drec; a.doff = h->d_doff; a.crec = h->d_crec; a.coff = h->d_coff; a.rowptr = h->d_rowptr;
     a.state = h->d_state; a.par = h->d_par; a.ctl = h->d_ctl; a.partials = h->d_partials; a.eval_out = h->d_eval;
     a.n = h->n; a.subject_offset = h->subject_offset; a.mode = mode; a.subjects_per_cta = h->subjects_per_cta;
-    if (mode == MODE_STEP && h->static_kernel && !h->force_generic)
+    if (mode == MODE_STEP && h->kernel_mode == 2)
+        h->tma_kernel<<<h->tma_grid, 256, h->tma_smem, h->stream>>>(h->mm.B, h->pl, h->cc, a, h->ta);
+    else if (mode == MODE_STEP && h->kernel_mode == 1)
         h->static_kernel<<<h->grid, 256, h->static_smem, h->stream>>>(h->mm.B, h->pl, h->cc, a);
     else if (h->mm.d.G == 16)
         jmb_step_kernel<16><<<h->grid, 256, h->smem_bytes, h->stream>>>(h->mm, h->pl, h->cc, a);
@@ -488,8 +537,9 @@ static int launch_finalize(jmb_handle h, int phase) {
     FinalizeArgs a = h->fa;
     a.par = h->d_par; a.ctl = h->d_ctl; a.partials = h->d_partials; a.n_partials = h->grid;
     a.use_reduced = (h->nranks > 1) ? 1 : 0; a.phase = phase;
+    a.n_partials = (h->kernel_mode == 2) ? h->tma_grid : h->grid;
     if (phase == 0 && h->nranks > 1) {
-        jmb_reduce_partials_kernel<<<1, 128, 0, h->stream>>>(h->d_partials, h->grid, h->d_par + h->pl.sums);
+        jmb_reduce_partials_kernel<<<1, 128, 0, h->stream>>>(h->d_partials, a.n_partials, h->d_par + h->pl.sums);
         h->launches += 1;
         CU(cudaGetLastError());
         ncclResult_t rc = g_nccl.AllReduce(h->d_par + h->pl.sums, h->d_par + h->pl.sums, 3, ncclDouble, ncclSum, h->comm, h->stream);
@@ -774,7 +824,7 @@ extern "C" int jmb_launch_count(jmb_handle h, int64_t* launches) {
 
 extern "C" const char* jmb_kernel_name(jmb_handle h) {
     if (!h) return "";
-    return (h->static_kernel && !h->force_generic) ? h->kernel_name : "generic";
+    return h->kernel_label.c_str();
 }
 
 extern "C" void* jmb_stream(jmb_handle h) { return h ? (void*)h->stream : nullptr; }

@@ -4,7 +4,8 @@
 // A subject's designs live in two contiguous records (units: doubles):
 //
 //   design record (shared by all chains of a fit)
-//     [0] event  [1] pad  [o_R ..] upper Cholesky factor of Covs$b[,,i], packed by column
+//     [0] event  [o_V ..] int32 visit counts per outcome  [o_R ..] upper Cholesky factor of
+//     Covs$b[,,i], packed by column
 //     [o_W2c ..] W2 row when the W2s rows repeat within the subject (w2_const)
 //     hazard rows, one per lane r = 0..RP-1 (0: event time, 1..K: quadrature, K+1..2K: lower-
 //     interval quadrature), each field stored as [column][RP]:
@@ -43,16 +44,17 @@ struct ModelDesc {
 };
 
 struct RecordLayout {
-    int RP, o_R, o_W2c, o_Pw, o_W1off, o_W1v, o_W2, o_ZZ[kMaxT], o_U[kMaxT], o_long, c_long;
+    int RP, o_V, o_R, o_W2c, o_Pw, o_W1off, o_W1v, o_W2, o_ZZ[kMaxT], o_U[kMaxT], o_long, c_long;
     int long_cols[kMaxO];           // stored doubles per longitudinal row of outcome k (y + Z cols)
-    int state_stride;               // q + 5: b, sigma_b, log_pyb, log_pb, acc_block, acc_total
+    int state_stride;               // q + 5 (b, sigma_b, log_pyb, log_pb, acc_block, acc_total), padded to even
 };
 
 JMB_HD constexpr RecordLayout make_layout(const ModelDesc& d) {
     RecordLayout L{};
     L.RP = d.G;
-    L.o_R = 2;
-    int o = 2 + d.q * (d.q + 1) / 2;
+    L.o_V = 1;
+    L.o_R = 1 + (d.O + 1) / 2;
+    int o = L.o_R + d.q * (d.q + 1) / 2;
     L.o_W2c = o;
     if (d.w2_const) o += d.p;
     o = (o + 1) / 2 * 2;
@@ -68,7 +70,7 @@ JMB_HD constexpr RecordLayout make_layout(const ModelDesc& d) {
     L.o_long = o;
     L.c_long = d.T * L.RP;
     for (int k = 0; k < d.O; ++k) L.long_cols[k] = 1 + d.qk[k] - d.z_ones0[k];
-    L.state_stride = d.q + 5;
+    L.state_stride = (d.q + 5 + 1) / 2 * 2;
     return L;
 }
 

@@ -81,19 +81,234 @@ __device__ __forceinline__ double log_ptb_static(double event, double lh, double
 #define JMB_STATIC_MIN_CTAS 2
 #endif
 
+// loop-invariant parameters a thread keeps in registers
+template <class Spec>
+struct StepRegs {
+    double gc[Spec::d.p > 0 ? Spec::d.p : 1], gp[Spec::d.p > 0 ? Spec::d.p : 1];
+    double alc[Spec::d.A], alp[Spec::d.A], isig[Spec::d.O];
+};
+
+// One b-step of one subject by one lane group, plus the subject's share of the survival step.
+// rec / crec / st_in may point to global or to (TMA-staged) shared memory.
+template <class Spec>
+__device__ __forceinline__ void subject_step(const double* __restrict__ rec, const double* __restrict__ crec,
+                                             const double* __restrict__ st_in, double* __restrict__ st_out,
+                                             const double* s_cur, const double* s_prop, const double* s_invD,
+                                             const StepRegs<Spec>& pr, const ChainConst& cc, const uint32_t gid,
+                                             const int iter, const int it_blk, const bool last_in_block,
+                                             const int lane, const unsigned gmask,
+                                             double& acc_cur, double& acc_prop, double& acc_lw) {
+    constexpr int G = Spec::d.G, q = Spec::d.q, O = Spec::d.O, T = Spec::d.T, p = Spec::d.p;
+    constexpr int K = Spec::d.K, S = Spec::d.S, WB = Spec::d.WB, RP = Spec::L.RP, QS = q + 5;
+    constexpr int NP = (q + 1) / 2;
+    constexpr int oV = Spec::L.o_V, oR = Spec::L.o_R, oLong = Spec::L.o_long, cLong = Spec::L.c_long, oW1off = Spec::L.o_W1off;
+    constexpr int oW1v = Spec::L.o_W1v, oW2c = Spec::L.o_W2c, oW2 = Spec::L.o_W2, oPw = Spec::L.o_Pw;
+    constexpr bool W2C = Spec::d.w2_const != 0;
+    static_assert(RP == G && 1 + K * S <= G && NP < G && QS <= G, "one hazard row per lane");
+    const int cls = (lane == 0) ? 0 : (lane <= K ? 1 : ((S == 2 && lane <= 2 * K) ? 2 : 3));
+    const bool quad = (cls == 1 || cls == 2);
+
+    // ---- current state (uniform loads) ----
+    double bo[q], bn[q];
+    sfor<q>([&](auto j) { bo[j] = st_in[j]; });
+    const double sigma_b = st_in[q], pyb_old = st_in[q + 1], pb_old = st_in[q + 2];
+    double accb = st_in[q + 3], acct = st_in[q + 4];
+
+    // ---- random draws: lanes 0..NP-1 one Box-Muller pair each, lane NP the accept uniform ----
+    double log_u;
+    {
+        const uint32_t slot = (lane < NP) ? (uint32_t)lane : 0u;
+        const uint32_t stream = (lane < NP) ? ST_B_PROP : ST_B_ACC;
+        uint32_t rr[4];
+        philox4x32(cc.seed, cc.chain_id, gid, (uint32_t)iter, slot, stream, rr);
+        const double u1 = u01(rr[0], rr[1]), u2 = u01(rr[2], rr[3]);
+        const double lg = log(u1);
+        const double rad = sqrt(-2.0 * lg);
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        const double z0 = rad * cs, z1 = rad * sn;
+        log_u = __shfl_sync(gmask, lg, NP, G);
+        // proposal: b + sqrt(sigma_b) * z' R_i  (mvrnorm_cube / extract_b, :123-146,670)
+        double z[q];
+        sfor<q>([&](auto j) { z[j] = __shfl_sync(gmask, (j & 1) ? z1 : z0, j >> 1, G); });
+        const double sd = sqrt(sigma_b);
+        sfor<q>([&](auto jc) {
+            constexpr int j = jc;
+            double pj = 0.0;
+            sfor<j + 1>([&](auto l) { pj += z[l] * rec[oR + (j * (j + 1)) / 2 + l]; });
+            bn[j] = bo[j] + sd * pj;
+        });
+    }
+
+    // ---- log p(b) at the proposal (:673) ----
+    double pb_new = 0.0;
+    sfor<q>([&](auto jc) {
+        constexpr int j = jc;
+        double t = 0.0;
+        sfor<q>([&](auto l) { t += bn[l] * s_invD[l + j * q]; });
+        pb_new += t * bn[j];
+    });
+    pb_new *= -0.5;
+
+    // ---- GLMM log-density over the visit segment (lin_predF + log_longF, :67-78,168-202) ----
+    double v_pyb = 0.0;
+    {
+        const double* __restrict__ lrec = rec + oLong;
+        const double* __restrict__ lcrec = crec + cLong;
+        const int* vcount = reinterpret_cast<const int*>(rec + oV);
+        sfor<O>([&](auto kc) {
+            constexpr int k = kc;
+            constexpr int ones0 = Spec::d.z_ones0[k], qk = Spec::d.qk[k];
+            const int v = vcount[k];
+            for (int r = lane; r < v; r += G) {
+                double eta = lcrec[r];
+                if constexpr (ones0 == 1) { constexpr int c0 = Spec::d.re_inds[k][0]; eta += bn[c0]; }
+                sfor<qk - ones0>([&](auto jc) {
+                    constexpr int j = jc;
+                    constexpr int cj = Spec::d.re_inds[k][j + ones0];
+                    eta += lrec[(1 + j) * v + r] * bn[cj];
+                });
+                v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta, pr.isig[k]);
+            }
+            constexpr int lcols = Spec::L.long_cols[k];
+            lrec += lcols * v;
+            lcrec += v;
+        });
+    }
+
+    // ---- hazard row of this lane under current / proposed parameters and old / new b
+    //      (lin_pred_matF :80-109, log_h :684, H/HL :685-691, survival step :735-741) ----
+    double l_co, l_cn, l_po, l_pn;
+    {
+        const int off = reinterpret_cast<const int*>(rec + oW1off)[lane];
+        double s1c = 0.0, s1p = 0.0;
+        sfor<WB>([&](auto j) {
+            const double wv = rec[oW1v + j * RP + lane];
+            s1c += wv * s_cur[off + j];
+            s1p += wv * s_prop[off + j];
+        });
+        double s2c = 0.0, s2p = 0.0;
+        sfor<p>([&](auto j) {
+            const double wv = W2C ? rec[oW2c + j] : rec[oW2 + j * RP + lane];
+            s2c += wv * pr.gc[j];
+            s2p += wv * pr.gp[j];
+        });
+        double a_co = 0.0, a_cn = 0.0, a_po = 0.0, a_pn = 0.0;
+        sfor<T>([&](auto tc) {
+            constexpr int t = tc;
+            constexpr int ones0 = Spec::d.zz_ones0[t], rt = Spec::d.rt[t];
+            const double xxb = crec[t * RP + lane];
+            double zo = 0.0, zn = 0.0;
+            if constexpr (ones0 == 1) { constexpr int c0 = Spec::d.re2[t][0]; zo = bo[c0]; zn = bn[c0]; }
+            constexpr int oZZ = Spec::L.o_ZZ[t], oU = Spec::L.o_U[t];
+            sfor<rt - ones0>([&](auto jc) {
+                constexpr int j = jc;
+                constexpr int cj = Spec::d.re2[t][j + ones0];
+                const double zz = rec[oZZ + j * RP + lane];
+                zo += zz * bo[cj];
+                zn += zz * bn[cj];
+            });
+            const double vo = trans_static<Spec::d.tf[t]>(xxb + zo), vn = trans_static<Spec::d.tf[t]>(xxb + zn);
+            sfor<Spec::d.ut[t]>([&](auto uc) {
+                constexpr int u = uc;
+                constexpr int c = Spec::d.col[t][u];
+                double wo = vo, wn = vn;
+                if constexpr (Spec::d.u_ones[t] == 0) {
+                    const double uu = rec[oU + u * RP + lane];
+                    wo *= uu; wn *= uu;
+                }
+                a_co += wo * pr.alc[c]; a_cn += wn * pr.alc[c];
+                a_po += wo * pr.alp[c]; a_pn += wn * pr.alp[c];
+            });
+        });
+        l_co = (s1c + s2c) + a_co; l_cn = (s1c + s2c) + a_cn;
+        l_po = (s1p + s2p) + a_po; l_pn = (s1p + s2p) + a_pn;
+    }
+    const double pw = quad ? rec[oPw + lane] : 0.0;
+    const double event = rec[0];
+
+    // ---- reductions: visit segment over the group; quadrature rows inside 16-lane halves ----
+    double e_co = quad ? pw * exp(l_co) : 0.0, e_cn = quad ? pw * exp(l_cn) : 0.0;
+    double H_co, H_cn, HL_co = 0.0, HL_cn = 0.0;
+    if constexpr (S == 1 || K == 15) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            e_co += __shfl_xor_sync(gmask, e_co, o, 16);
+            e_cn += __shfl_xor_sync(gmask, e_cn, o, 16);
+        }
+        if constexpr (S == 2) {
+            H_co = __shfl_sync(gmask, e_co, 0, G); HL_co = __shfl_sync(gmask, e_co, 16, G);
+            H_cn = __shfl_sync(gmask, e_cn, 0, G); HL_cn = __shfl_sync(gmask, e_cn, 16, G);
+        } else { H_co = e_co; H_cn = e_cn; }
+    } else {
+        H_co = group_sum<G>(cls == 1 ? e_co : 0.0, gmask); HL_co = group_sum<G>(cls == 2 ? e_co : 0.0, gmask);
+        H_cn = group_sum<G>(cls == 1 ? e_cn : 0.0, gmask); HL_cn = group_sum<G>(cls == 2 ? e_cn : 0.0, gmask);
+    }
+    const double pyb_new = group_sum<G>(v_pyb, gmask);
+    const double h_co = __shfl_sync(gmask, l_co, 0, G), h_cn = __shfl_sync(gmask, l_cn, 0, G);
+    const double h_po = __shfl_sync(gmask, l_po, 0, G), h_pn = __shfl_sync(gmask, l_pn, 0, G);
+
+    const double ptb_co = log_ptb_static<S>(event, h_co, H_co, HL_co);
+    const double ptb_cn = log_ptb_static<S>(event, h_cn, H_cn, HL_cn);
+    const double cur_lp = pyb_old + ptb_co + pb_old;                 // :669
+    const double new_lp = pyb_new + ptb_cn + pb_new;                 // :703
+    const bool accept = log_u < (new_lp - cur_lp);                   // :706 (NaN rejects)
+
+    // ---- proposed survival parameters at the accepted b (:735-752) ----
+    double e_p = quad ? pw * exp(accept ? l_pn : l_po) : 0.0;
+    double Hp, HLp = 0.0;
+    if constexpr (S == 1 || K == 15) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) e_p += __shfl_xor_sync(gmask, e_p, o, 16);
+        if constexpr (S == 2) { Hp = __shfl_sync(gmask, e_p, 0, G); HLp = __shfl_sync(gmask, e_p, 16, G); }
+        else Hp = e_p;
+    } else {
+        Hp = group_sum<G>(cls == 1 ? e_p : 0.0, gmask); HLp = group_sum<G>(cls == 2 ? e_p : 0.0, gmask);
+    }
+    const double ptb_c = accept ? ptb_cn : ptb_co;
+    const double ptb_p = log_ptb_static<S>(event, accept ? h_pn : h_po, Hp, HLp);
+    const double pyb_acc = accept ? pyb_new : pyb_old;
+    const double pb_acc = accept ? pb_new : pb_old;
+    acc_cur += ptb_c; acc_prop += ptb_p; acc_lw += pyb_acc + pb_acc;
+
+    // ---- state write-back (:707-724) + per-subject scale adaptation at block ends (:853-859) ----
+    accb += accept ? 1.0 : 0.0;
+    acct += accept ? 1.0 : 0.0;
+    double sig_new = sigma_b;
+    if (last_in_block) {
+        const double g2 = cc.c0 * pow((double)(it_blk + 1), cc.mc1);
+        sig_new = exp(log(sigma_b) + g2 * (accb / cc.n_block - cc.target_acc));
+        sig_new = fmin(fmax(sig_new, cc.eps1), cc.eps3);              // bounds_sigma :411-419
+        accb = 0.0;
+    }
+    double outv = acct;
+    sfor<q>([&](auto j) { if (lane == j) outv = accept ? bn[j] : bo[j]; });
+    if (lane == q) outv = sig_new;
+    if (lane == q + 1) outv = pyb_acc;
+    if (lane == q + 2) outv = pb_acc;
+    if (lane == q + 3) outv = accb;
+    if (lane < QS && (accept || lane >= q)) st_out[lane] = outv;
+}
+
+template <class Spec>
+__device__ __forceinline__ void load_step_regs(StepRegs<Spec>& pr, const double* s_cur, const double* s_prop,
+                                               const double* par, const ParamLayout& pl, int B) {
+    constexpr int p = Spec::d.p, A = Spec::d.A, O = Spec::d.O;
+    sfor<O>([&](auto kc) { pr.isig[kc] = 1.0 / par[pl.sigmas + kc]; });
+    sfor<p>([&](auto j) { pr.gc[j] = s_cur[B + j]; pr.gp[j] = s_prop[B + j]; });
+    sfor<A>([&](auto j) { pr.alc[j] = s_cur[B + p + j]; pr.alp[j] = s_prop[B + p + j]; });
+}
+
+// -------------------------------------------------------------------------------------------
+// direct variant: every lane group reads its subject's records straight from global memory
+// -------------------------------------------------------------------------------------------
 template <class Spec>
 __global__ void __launch_bounds__(256, JMB_STATIC_MIN_CTAS)
 jmb_step_static(const int B, const __grid_constant__ ParamLayout pl, const __grid_constant__ ChainConst cc,
                 const __grid_constant__ StepArgs a) {
-    constexpr int G = Spec::d.G, q = Spec::d.q, O = Spec::d.O, T = Spec::d.T, A = Spec::d.A, p = Spec::d.p;
-    constexpr int K = Spec::d.K, S = Spec::d.S, WB = Spec::d.WB, RP = Spec::L.RP, QS = q + 5;
-    constexpr int THREADS = 256, GROUPS = THREADS / G, NP = (q + 1) / 2;
-    constexpr int oR = Spec::L.o_R, oLong = Spec::L.o_long, cLong = Spec::L.c_long, oW1off = Spec::L.o_W1off;
-    constexpr int oW1v = Spec::L.o_W1v, oW2c = Spec::L.o_W2c, oW2 = Spec::L.o_W2, oPw = Spec::L.o_Pw;
-    constexpr bool W2C = Spec::d.w2_const != 0;
-    static_assert(RP == G && 1 + K * S <= G && NP < G && QS <= G, "one hazard row per lane");
+    constexpr int G = Spec::d.G, q = Spec::d.q, p = Spec::d.p, A = Spec::d.A, SS = Spec::L.state_stride;
+    constexpr int THREADS = 256, GROUPS = THREADS / G;
     const int P = B + p + A;
-
     extern __shared__ double smem[];
     double* s_cur = smem;                 // [P] current Bs_gammas | gammas | alphas
     double* s_prop = s_cur + P;           // [P] proposed
@@ -104,212 +319,151 @@ jmb_step_static(const int B, const __grid_constant__ ParamLayout pl, const __gri
     for (int j = tid; j < P; j += THREADS) { s_cur[j] = a.par[pl.cur + j]; s_prop[j] = a.par[pl.prop + j]; }
     for (int j = tid; j < q * q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
     const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i;
-    double isig[O];
-    sfor<O>([&](auto kc) { isig[kc] = 1.0 / a.par[pl.sigmas + kc]; });
     __syncthreads();
-    // loop-invariant small parameter vectors in registers
-    double gc[p > 0 ? p : 1], gp[p > 0 ? p : 1], alc[A], alp[A];
-    sfor<p>([&](auto j) { gc[j] = s_cur[B + j]; gp[j] = s_prop[B + j]; });
-    sfor<A>([&](auto j) { alc[j] = s_cur[B + p + j]; alp[j] = s_prop[B + p + j]; });
+    StepRegs<Spec> pr;
+    load_step_regs<Spec>(pr, s_cur, s_prop, a.par, pl, B);
 
     const int grp = tid / G, lane = tid % G;
     const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (0xFFFFu << (16 * ((tid & 31) >> 4)));
     const bool last_in_block = (i_blk == cc.n_block - 1);
-    const int cls = (lane == 0) ? 0 : (lane <= K ? 1 : ((S == 2 && lane <= 2 * K) ? 2 : 3));
-    const bool quad = (cls == 1 || cls == 2);
-
     double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;
     const int s_begin = blockIdx.x * a.subjects_per_cta;
     const int s_end = min(a.n, s_begin + a.subjects_per_cta);
-
     for (int s = s_begin + grp; s < s_end; s += GROUPS) {
-        const double* __restrict__ rec = a.drec + a.doff[s];
-        const double* __restrict__ crec = a.crec + a.coff[s];
-        double* st = a.state + (long long)s * QS;
-        const uint32_t gid = (uint32_t)(a.subject_offset + s);
-
-        // ---- current state (uniform loads) ----
-        double bo[q], bn[q];
-        sfor<q>([&](auto j) { bo[j] = st[j]; });
-        const double sigma_b = st[q], pyb_old = st[q + 1], pb_old = st[q + 2];
-        double accb = st[q + 3], acct = st[q + 4];
-
-        // ---- random draws: lanes 0..NP-1 one Box-Muller pair each, lane NP the accept uniform ----
-        double log_u;
-        {
-            const uint32_t slot = (lane < NP) ? (uint32_t)lane : 0u;
-            const uint32_t stream = (lane < NP) ? ST_B_PROP : ST_B_ACC;
-            uint32_t rr[4];
-            philox4x32(cc.seed, cc.chain_id, gid, (uint32_t)iter, slot, stream, rr);
-            const double u1 = u01(rr[0], rr[1]), u2 = u01(rr[2], rr[3]);
-            const double lg = log(u1);
-            const double rad = sqrt(-2.0 * lg);
-            double sn, cs;
-            sincospi(2.0 * u2, &sn, &cs);
-            const double z0 = rad * cs, z1 = rad * sn;
-            log_u = __shfl_sync(gmask, lg, NP, G);
-            // proposal: b + sqrt(sigma_b) * z' R_i  (mvrnorm_cube / extract_b, :123-146,670)
-            double z[q];
-            sfor<q>([&](auto j) { z[j] = __shfl_sync(gmask, (j & 1) ? z1 : z0, j >> 1, G); });
-            const double sd = sqrt(sigma_b);
-            sfor<q>([&](auto jc) {
-                constexpr int j = jc;
-                double pj = 0.0;
-                sfor<j + 1>([&](auto l) { pj += z[l] * rec[oR + (j * (j + 1)) / 2 + l]; });
-                bn[j] = bo[j] + sd * pj;
-            });
-        }
-
-        // ---- log p(b) at the proposal (:673) ----
-        double pb_new = 0.0;
-        sfor<q>([&](auto jc) {
-            constexpr int j = jc;
-            double t = 0.0;
-            sfor<q>([&](auto l) { t += bn[l] * s_invD[l + j * q]; });
-            pb_new += t * bn[j];
-        });
-        pb_new *= -0.5;
-
-        // ---- GLMM log-density over the visit segment (lin_predF + log_longF, :67-78,168-202) ----
-        double v_pyb = 0.0;
-        {
-            const double* __restrict__ lrec = rec + oLong;
-            const double* __restrict__ lcrec = crec + cLong;
-            sfor<O>([&](auto kc) {
-                constexpr int k = kc;
-                constexpr int ones0 = Spec::d.z_ones0[k], qk = Spec::d.qk[k];
-                const int* rp = a.rowptr + (long long)k * (a.n + 1);
-                const int v = rp[s + 1] - rp[s];
-                for (int r = lane; r < v; r += G) {
-                    double eta = lcrec[r];
-                    if constexpr (ones0 == 1) { constexpr int c0 = Spec::d.re_inds[k][0]; eta += bn[c0]; }
-                    sfor<qk - ones0>([&](auto jc) {
-                        constexpr int j = jc;
-                        constexpr int cj = Spec::d.re_inds[k][j + ones0];
-                        eta += lrec[(1 + j) * v + r] * bn[cj];
-                    });
-                    v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta, isig[k]);
-                }
-                constexpr int lcols = Spec::L.long_cols[k];
-                lrec += lcols * v;
-                lcrec += v;
-            });
-        }
-
-        // ---- hazard row of this lane under current / proposed parameters and old / new b
-        //      (lin_pred_matF :80-109, log_h :684, H/HL :685-691, survival step :735-741) ----
-        double l_co, l_cn, l_po, l_pn;
-        {
-            const int off = reinterpret_cast<const int*>(rec + oW1off)[lane];
-            double s1c = 0.0, s1p = 0.0;
-            sfor<WB>([&](auto j) {
-                const double wv = rec[oW1v + j * RP + lane];
-                s1c += wv * s_cur[off + j];
-                s1p += wv * s_prop[off + j];
-            });
-            double s2c = 0.0, s2p = 0.0;
-            sfor<p>([&](auto j) {
-                const double wv = W2C ? rec[oW2c + j] : rec[oW2 + j * RP + lane];
-                s2c += wv * gc[j];
-                s2p += wv * gp[j];
-            });
-            double a_co = 0.0, a_cn = 0.0, a_po = 0.0, a_pn = 0.0;
-            sfor<T>([&](auto tc) {
-                constexpr int t = tc;
-                constexpr int ones0 = Spec::d.zz_ones0[t], rt = Spec::d.rt[t];
-                const double xxb = crec[t * RP + lane];
-                double zo = 0.0, zn = 0.0;
-                if constexpr (ones0 == 1) { constexpr int c0 = Spec::d.re2[t][0]; zo = bo[c0]; zn = bn[c0]; }
-                constexpr int oZZ = Spec::L.o_ZZ[t], oU = Spec::L.o_U[t];
-                sfor<rt - ones0>([&](auto jc) {
-                    constexpr int j = jc;
-                    constexpr int cj = Spec::d.re2[t][j + ones0];
-                    const double zz = rec[oZZ + j * RP + lane];
-                    zo += zz * bo[cj];
-                    zn += zz * bn[cj];
-                });
-                const double vo = trans_static<Spec::d.tf[t]>(xxb + zo), vn = trans_static<Spec::d.tf[t]>(xxb + zn);
-                sfor<Spec::d.ut[t]>([&](auto uc) {
-                    constexpr int u = uc;
-                    constexpr int c = Spec::d.col[t][u];
-                    double wo = vo, wn = vn;
-                    if constexpr (Spec::d.u_ones[t] == 0) {
-                        const double uu = rec[oU + u * RP + lane];
-                        wo *= uu; wn *= uu;
-                    }
-                    a_co += wo * alc[c]; a_cn += wn * alc[c];
-                    a_po += wo * alp[c]; a_pn += wn * alp[c];
-                });
-            });
-            l_co = (s1c + s2c) + a_co; l_cn = (s1c + s2c) + a_cn;
-            l_po = (s1p + s2p) + a_po; l_pn = (s1p + s2p) + a_pn;
-        }
-        const double pw = quad ? rec[oPw + lane] : 0.0;
-        const double event = rec[0];
-
-        // ---- reductions: visit segment over the group; quadrature rows inside 16-lane halves ----
-        double e_co = quad ? pw * exp(l_co) : 0.0, e_cn = quad ? pw * exp(l_cn) : 0.0;
-        double H_co, H_cn, HL_co = 0.0, HL_cn = 0.0;
-        if constexpr (S == 1 || K == 15) {
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                e_co += __shfl_xor_sync(gmask, e_co, o, 16);
-                e_cn += __shfl_xor_sync(gmask, e_cn, o, 16);
-            }
-            if constexpr (S == 2) {
-                H_co = __shfl_sync(gmask, e_co, 0, G); HL_co = __shfl_sync(gmask, e_co, 16, G);
-                H_cn = __shfl_sync(gmask, e_cn, 0, G); HL_cn = __shfl_sync(gmask, e_cn, 16, G);
-            } else { H_co = e_co; H_cn = e_cn; }
-        } else {
-            H_co = group_sum<G>(cls == 1 ? e_co : 0.0, gmask); HL_co = group_sum<G>(cls == 2 ? e_co : 0.0, gmask);
-            H_cn = group_sum<G>(cls == 1 ? e_cn : 0.0, gmask); HL_cn = group_sum<G>(cls == 2 ? e_cn : 0.0, gmask);
-        }
-        const double pyb_new = group_sum<G>(v_pyb, gmask);
-        const double h_co = __shfl_sync(gmask, l_co, 0, G), h_cn = __shfl_sync(gmask, l_cn, 0, G);
-        const double h_po = __shfl_sync(gmask, l_po, 0, G), h_pn = __shfl_sync(gmask, l_pn, 0, G);
-
-        const double ptb_co = log_ptb_static<S>(event, h_co, H_co, HL_co);
-        const double ptb_cn = log_ptb_static<S>(event, h_cn, H_cn, HL_cn);
-        const double cur_lp = pyb_old + ptb_co + pb_old;                 // :669
-        const double new_lp = pyb_new + ptb_cn + pb_new;                 // :703
-        const bool accept = log_u < (new_lp - cur_lp);                   // :706 (NaN rejects)
-
-        // ---- proposed survival parameters at the accepted b (:735-752) ----
-        double e_p = quad ? pw * exp(accept ? l_pn : l_po) : 0.0;
-        double Hp, HLp = 0.0;
-        if constexpr (S == 1 || K == 15) {
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) e_p += __shfl_xor_sync(gmask, e_p, o, 16);
-            if constexpr (S == 2) { Hp = __shfl_sync(gmask, e_p, 0, G); HLp = __shfl_sync(gmask, e_p, 16, G); }
-            else Hp = e_p;
-        } else {
-            Hp = group_sum<G>(cls == 1 ? e_p : 0.0, gmask); HLp = group_sum<G>(cls == 2 ? e_p : 0.0, gmask);
-        }
-        const double ptb_c = accept ? ptb_cn : ptb_co;
-        const double ptb_p = log_ptb_static<S>(event, accept ? h_pn : h_po, Hp, HLp);
-        const double pyb_acc = accept ? pyb_new : pyb_old;
-        const double pb_acc = accept ? pb_new : pb_old;
-        acc_cur += ptb_c; acc_prop += ptb_p; acc_lw += pyb_acc + pb_acc;
-
-        // ---- state write-back (:707-724) + per-subject scale adaptation at block ends (:853-859) ----
-        accb += accept ? 1.0 : 0.0;
-        acct += accept ? 1.0 : 0.0;
-        double sig_new = sigma_b;
-        if (last_in_block) {
-            const double g2 = cc.c0 * pow((double)(it_blk + 1), cc.mc1);
-            sig_new = exp(log(sigma_b) + g2 * (accb / cc.n_block - cc.target_acc));
-            sig_new = fmin(fmax(sig_new, cc.eps1), cc.eps3);              // bounds_sigma :411-419
-            accb = 0.0;
-        }
-        double outv = acct;
-        sfor<q>([&](auto j) { if (lane == j) outv = accept ? bn[j] : bo[j]; });
-        if (lane == q) outv = sig_new;
-        if (lane == q + 1) outv = pyb_acc;
-        if (lane == q + 2) outv = pb_acc;
-        if (lane == q + 3) outv = accb;
-        if (lane < QS && (accept || lane >= q)) st[lane] = outv;
+        double* st = a.state + (long long)s * SS;
+        subject_step<Spec>(a.drec + a.doff[s], a.crec + a.coff[s], st, st, s_cur, s_prop, s_invD, pr, cc,
+                           (uint32_t)(a.subject_offset + s), iter, it_blk, last_in_block, lane, gmask,
+                           acc_cur, acc_prop, acc_lw);
     }
+    if (lane == 0) { s_red[grp * 3] = acc_cur; s_red[grp * 3 + 1] = acc_prop; s_red[grp * 3 + 2] = acc_lw; }
+    __syncthreads();
+    if (tid < 3) {
+        double t = 0.0;
+        for (int g = 0; g < GROUPS; ++g) t += s_red[g * 3 + tid];
+        a.partials[blockIdx.x * 3 + tid] = t;
+    }
+}
 
+// -------------------------------------------------------------------------------------------
+// TMA variant: each warp runs a two-stage cp.async.bulk + mbarrier pipeline over its contiguous
+// run of subjects; while it computes subject(s) t the records and state of t+1 are already in
+// flight into its other shared-memory stage.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+struct TmaArgs {
+    int cap_d, cap_c;        // per-stage capacity (doubles) for the design / per-draw records of one warp step
+    int subjects_per_cta;    // multiple of 8 * SPW
+};
+
+template <class Spec>
+__global__ void __launch_bounds__(256, JMB_STATIC_MIN_CTAS)
+jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_constant__ ChainConst cc,
+             const __grid_constant__ StepArgs a, const TmaArgs ta) {
+    constexpr int G = Spec::d.G, q = Spec::d.q, p = Spec::d.p, A = Spec::d.A, SS = Spec::L.state_stride;
+    constexpr int THREADS = 256, WARPS = THREADS / 32, GROUPS = THREADS / G, SPW = 32 / G;
+    const int P = B + p + A;
+    extern __shared__ double smem[];
+    double* s_cur = smem;                          // [P]
+    double* s_prop = s_cur + P;                    // [P]
+    double* s_invD = s_prop + P;                   // [q*q]
+    double* s_red = s_invD + q * q;                // [GROUPS][3]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + GROUPS * 3);   // [WARPS][2]
+    const int head = (2 * P + q * q + GROUPS * 3 + WARPS * 2 + 1) / 2 * 2;   // keep 16-byte alignment
+    const int stage_doubles = ta.cap_d + ta.cap_c + SPW * SS;
+    double* s_stage = smem + head;                 // [WARPS][2][stage_doubles]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
+    for (int j = tid; j < P; j += THREADS) { s_cur[j] = a.par[pl.cur + j]; s_prop[j] = a.par[pl.prop + j]; }
+    for (int j = tid; j < q * q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
+    if (tid < WARPS * 2) mbar_init(&s_bar[tid], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i;
+    __syncthreads();
+    StepRegs<Spec> pr;
+    load_step_regs<Spec>(pr, s_cur, s_prop, a.par, pl, B);
+
+    const int half = (G == 16) ? (lane32 >> 4) : 0, lane = lane32 % G;
+    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (0xFFFFu << (16 * half));
+    const bool last_in_block = (i_blk == cc.n_block - 1);
+    double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;
+
+    // this warp's contiguous run of subjects
+    const int c_begin = blockIdx.x * ta.subjects_per_cta;
+    const int per_warp = ta.subjects_per_cta / WARPS;
+    const int w_begin = min(a.n, c_begin + warp * per_warp);
+    const int w_end = min(a.n, w_begin + per_warp);
+    const int steps = (w_end - w_begin + SPW - 1) / SPW;
+    uint64_t* bar = s_bar + warp * 2;
+    double* stage0 = s_stage + (size_t)warp * 2 * stage_doubles;
+
+    // Offsets of warp step t (subjects [sA, sB)): loaded two steps ahead by every lane (uniform
+    // loads that complete under the compute of the steps in between).
+    struct Off { long long d0, dm, d1, c0, cm, c1; int sA, sB; };
+    auto load_off = [&](int t) {
+        Off o;
+        o.sA = w_begin + t * SPW; o.sB = min(w_end, o.sA + SPW);
+        const int sM = min(o.sB, o.sA + 1);
+        o.d0 = a.doff[o.sA]; o.dm = a.doff[sM]; o.d1 = a.doff[o.sB];
+        o.c0 = a.coff[o.sA]; o.cm = a.coff[sM]; o.c1 = a.coff[o.sB];
+        return o;
+    };
+    auto issue = [&](const Off& o, int stg) {     // lane32 == 0 only
+        double* dst = stage0 + (size_t)stg * stage_doubles;
+        const uint32_t bd = (uint32_t)(o.d1 - o.d0) * 8u, bc = (uint32_t)(o.c1 - o.c0) * 8u, bs = (uint32_t)(o.sB - o.sA) * SS * 8u;
+        mbar_expect_tx(&bar[stg], bd + bc + bs);
+        bulk_g2s(dst, a.drec + o.d0, bd, &bar[stg]);
+        bulk_g2s(dst + ta.cap_d, a.crec + o.c0, bc, &bar[stg]);
+        bulk_g2s(dst + ta.cap_d + ta.cap_c, a.state + (long long)o.sA * SS, bs, &bar[stg]);
+    };
+    // second-subject offsets inside the staged chunk, per stage (G == 16 only)
+    int dmid0 = 0, cmid0 = 0, dmid1 = 0, cmid1 = 0;
+    if (steps > 0) { const Off o = load_off(0); dmid0 = (int)(o.dm - o.d0); cmid0 = (int)(o.cm - o.c0); if (lane32 == 0) issue(o, 0); }
+    if (steps > 1) { const Off o = load_off(1); dmid1 = (int)(o.dm - o.d0); cmid1 = (int)(o.cm - o.c0); if (lane32 == 0) issue(o, 1); }
+    for (int t = 0; t < steps; ++t) {
+        const int stg = t & 1;
+        const bool more = (t + 2 < steps);
+        Off nxt{};
+        if (more) nxt = load_off(t + 2);
+        const int s = w_begin + t * SPW + half;
+        const int dmid = (half == 1) ? (stg ? dmid1 : dmid0) : 0, cmid = (half == 1) ? (stg ? cmid1 : cmid0) : 0;
+        mbar_wait(&bar[stg], (uint32_t)((t >> 1) & 1));
+        const double* stage = stage0 + (size_t)stg * stage_doubles;
+        if (s < w_end) {
+            subject_step<Spec>(stage + dmid, stage + ta.cap_d + cmid, stage + ta.cap_d + ta.cap_c + half * SS,
+                               a.state + (long long)s * SS, s_cur, s_prop, s_invD, pr, cc,
+                               (uint32_t)(a.subject_offset + s), iter, it_blk, last_in_block, lane, gmask,
+                               acc_cur, acc_prop, acc_lw);
+        }
+        __syncwarp();
+        if (more) {
+            if (stg) { dmid1 = (int)(nxt.dm - nxt.d0); cmid1 = (int)(nxt.cm - nxt.c0); }
+            else { dmid0 = (int)(nxt.dm - nxt.d0); cmid0 = (int)(nxt.cm - nxt.c0); }
+            if (lane32 == 0) issue(nxt, stg);
+        }
+    }
+    const int grp = tid / G;
     if (lane == 0) { s_red[grp * 3] = acc_cur; s_red[grp * 3 + 1] = acc_prop; s_red[grp * 3 + 2] = acc_lw; }
     __syncthreads();
     if (tid < 3) {

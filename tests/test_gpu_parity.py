@@ -97,10 +97,18 @@ def test_static_and_generic_kernels_agree(cuda_lib, cfg, monkeypatch):
     c = make_cohort(cfg, n=300)
     ctl = dict(c["control"]); ctl.update(n_burnin=30, n_iter=20, n_block=10, n_thin=10)
     with cuda_lib.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
-        assert fit.layout_info()["kernel"].startswith("static:")
+        assert fit.layout_info()["kernel"].startswith("static-tma:")
         fit.set_draw(c["Data"])
         a = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
-    monkeypatch.setenv("JMB_FORCE_GENERIC", "1")
+    monkeypatch.setenv("JMB_KERNEL", "direct")
+    with cuda_lib.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
+        assert fit.layout_info()["kernel"].startswith("static:")
+        fit.set_draw(c["Data"])
+        d = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    # same per-subject arithmetic, different partial-sum grouping only
+    assert _rel(a["extras"]["trace_surv"], d["extras"]["trace_surv"]) <= 1e-12
+    assert np.array_equal(a["mcmc"]["b"], d["mcmc"]["b"])
+    monkeypatch.setenv("JMB_KERNEL", "generic")
     with cuda_lib.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
         assert fit.layout_info()["kernel"] == "generic"
         fit.set_draw(c["Data"])
