@@ -139,13 +139,23 @@ int jmb_handle_s::select_kernel() {
             max_c = std::max(max_c, coff[j] - coff[i]);
             if (j == n) break;
         }
-        ta.cap_d = (int)((max_d + 1) / 2 * 2);
-        ta.cap_c = (int)((max_c + 1) / 2 * 2);
         const int head = (2 * mm.P + md.q * md.q + groups * 3 + 8 * 2 + 1) / 2 * 2;
-        const long long stage = (long long)ta.cap_d + ta.cap_c + spw * SS;
-        const long long bytes = 8LL * (head + 8LL * 2 * stage);
-        if (bytes <= 113 * 1024) {
-            tma_smem = (int)bytes;
+        // two CTAs per SM: 113 KB each; 8 warps x 2 stages per CTA
+        const long long budget = ((113LL * 1024) / 8 - head) / 16 - spw * SS;
+        long long cap_d = (max_d + 1) / 2 * 2, cap_c = (max_c + 1) / 2 * 2;
+        if (cap_d + cap_c > budget) {
+            // keep the split proportional; oversize steps fall back to direct global loads
+            const double f = (double)budget / (double)(cap_d + cap_c);
+            cap_d = (long long)(cap_d * f) / 2 * 2;
+            cap_c = (budget - cap_d) / 2 * 2;
+        }
+        ta.cap_d = (int)cap_d;
+        ta.cap_c = (int)cap_c;
+        // the typical step must fit, otherwise staging is pointless
+        long long mean_d = (doff[n] / std::max(n, 1)) * spw, mean_c = (coff[n] / std::max(n, 1)) * spw;
+        if (cap_d >= mean_d && cap_c >= mean_c && budget > 0) {
+            const long long stage = (long long)ta.cap_d + ta.cap_c + spw * SS;
+            tma_smem = (int)(8LL * (head + 8LL * 2 * stage));
             const int unit = 8 * spw;
             int g = std::min((n + unit - 1) / unit, 2 * num_sms);
             int spc = ((n + g - 1) / g + unit - 1) / unit * unit;
@@ -216,7 +226,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
         d->n_alphas <= 0 || d->n_alphas > JMB_MAX_ALPHAS) return fail("jmb_create: parameter block sizes out of range");
     const int S = d->interval_cens ? 2 : 1;
     if (d->K <= 0 || 1 + d->K * S > 32) return fail("jmb_create: 1 + K * (1 + interval_cens) must be <= 32");
-    if (d->q + 5 > 32) return fail("jmb_create: q + 5 must be <= 32");
+    if (d->q + kStateExtra > 32) return fail("jmb_create: q + 7 must be <= 32");
     if (S == 2 && (!d->W1s_int || !d->Pw_int || !d->ZZs_int || !d->Us_int || (d->n_gammas && !d->W2s_int)))
         return fail("jmb_create: interval_cens needs the *_int designs");
 
@@ -233,7 +243,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     mm.B = B;
     mm.P = B + p + d->n_alphas;
     md.G = (1 + K * S <= 16) ? 16 : 32;
-    if (q + 5 > md.G) md.G = 32;
+    if (q + kStateExtra > md.G) md.G = 32;
     for (int k = 0; k < O; ++k) {
         md.fam[k] = d->fams[k]; md.link[k] = d->links[k]; md.qk[k] = d->q_k[k];
         if (md.qk[k] < 0 || md.qk[k] > JMB_MAX_Q) { delete h; return fail("jmb_create: q_k out of range"); }
@@ -440,7 +450,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     const int groups = 256 / md.G;
     h->subjects_per_cta = groups * 4;
     h->grid = (n + h->subjects_per_cta - 1) / h->subjects_per_cta;
-    h->smem_bytes = (int)sizeof(double) * (2 * mm.P + q * q + O + groups * 3 * (q + 5) + groups * 3);
+    h->smem_bytes = (int)sizeof(double) * (2 * mm.P + q * q + O + groups * 3 * (q + kStateExtra) + groups * 3);
     {
         cudaDeviceProp prop;
         CUH(cudaGetDeviceProperties(&prop, device));

@@ -36,6 +36,7 @@ struct ParamLayout {
 
 struct Ctl {                        // device-resident loop control (ints)
     int iter, it, i, keep_iterator, check_iterator, accept_s_block, accept_s_total, error;
+    int last_accept;                // 1 when the previous iteration accepted the survival proposal
 };
 
 struct ChainConst {                 // scalar constants of one chain (kernel parameter)

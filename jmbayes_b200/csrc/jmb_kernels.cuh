@@ -54,14 +54,14 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
     double* s_invD = s_prop + mm.P;
     double* s_isig = s_invD + md.q * md.q;
     double* s_grp = s_isig + md.O;                         // per group: b_old[QS], b_new[QS], z[QS]
-    const int QS = md.q + 5;
+    const int QS = md.q + kStateExtra;
     double* s_red = s_grp + GROUPS * 3 * QS;                // [GROUPS][3]
 
     const int tid = threadIdx.x;
     for (int j = tid; j < mm.P; j += THREADS) { s_cur[j] = a.par[pl.cur + j]; s_prop[j] = a.par[pl.prop + j]; }
     for (int j = tid; j < md.q * md.q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
     for (int j = tid; j < md.O; j += THREADS) s_isig[j] = 1.0 / a.par[pl.sigmas + j];
-    const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i;
+    const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i, last_acc = a.ctl->last_accept;
     __syncthreads();
 
     const int grp = tid / G, lane = tid % G;
@@ -193,7 +193,10 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         h_po = __shfl_sync(gmask, h_po, src0); h_pn = __shfl_sync(gmask, h_pn, src0);
 
         const double event = rec[0];
-        const double ptb_co = log_ptb_term(S, event, h_co, H_co, HL_co);
+        // log p(T|b_old) under the current parameters is carried in the state: slot q+5 when the
+        // last survival proposal was rejected, slot q+6 (evaluated at that proposal) when accepted
+        const double ptb_co = (a.mode == MODE_STEP) ? (last_acc ? bo[q + 6] : bo[q + 5])
+                                                    : log_ptb_term(S, event, h_co, H_co, HL_co);
         const double ptb_cn = log_ptb_term(S, event, h_cn, H_cn, HL_cn);
 
         bool accept;
@@ -244,7 +247,9 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
                 else if (j == q + 1) val = pyb_acc;
                 else if (j == q + 2) val = pb_acc;
                 else if (j == q + 3) val = accb;
-                else val = acct;
+                else if (j == q + 4) val = acct;
+                else if (j == q + 5) val = ptb_c;
+                else val = (a.mode == MODE_INIT) ? ptb_c : ptb_p;
                 st[j] = val;
             }
         }
@@ -347,6 +352,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     __shared__ double s_tot[3];
     __shared__ int s_next_iter;
     __shared__ double s_z[JMB_MAX_BS + JMB_MAX_GAMMAS + JMB_MAX_ALPHAS + 2];
+    __shared__ double s_q[4][JMB_MAX_BS + JMB_MAX_GAMMAS + JMB_MAX_ALPHAS];
     const int tid = threadIdx.x;
     double* par = a.par;
     const int B = mm.B, p = mm.d.p, A = mm.d.A;
@@ -379,6 +385,33 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     }
     __syncthreads();
 
+    // ---- quadratic forms of the three Gaussian priors, one coordinate per thread ----
+    // thread j < P handles coordinate j of (Bs_gammas | gammas | alphas) against its block's Tau:
+    //   s_q[0][j] = ((cur - mean)' Tau)_j (cur - mean)_j   s_q[1][j]: same at the proposal
+    //   s_q[2][j] / s_q[3][j]: (x' Tau_Bs)_j x_j without the mean, for the tau_Bs_gammas draw
+    {
+        double* cur = par + pl.cur;
+        double* prop = par + pl.prop;
+        if (tid < mm.P) {
+            int base, m, To, Mo;
+            if (tid < B) { base = 0; m = B; To = pl.Tau_Bs; Mo = pl.mean_Bs; }
+            else if (tid < B + p) { base = B; m = p; To = pl.Tau_g; Mo = pl.mean_g; }
+            else { base = B + p; m = A; To = pl.Tau_a; Mo = pl.mean_a; }
+            const int jj = tid - base;
+            double tc = 0.0, tp = 0.0, rc = 0.0, rp = 0.0;
+            for (int l = 0; l < m; ++l) {
+                const double tau = par[To + l + jj * m], mu = par[Mo + l];
+                const double xc = cur[base + l], xp = prop[base + l];
+                tc += (xc - mu) * tau; tp += (xp - mu) * tau;
+                rc += xc * tau; rp += xp * tau;
+            }
+            const double mu = par[Mo + jj];
+            s_q[0][tid] = tc * (cur[tid] - mu); s_q[1][tid] = tp * (prop[tid] - mu);
+            s_q[2][tid] = rc * cur[tid]; s_q[3][tid] = rp * prop[tid];
+        }
+    }
+    __syncthreads();
+
     if (tid == 0) {
         Ctl* ctl = a.ctl;
         const int iter = ctl->iter;
@@ -387,22 +420,26 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         if (a.trace) { a.trace[2LL * iter] = s_tot[0]; a.trace[2LL * iter + 1] = s_tot[1]; }
         // ---- survival-block RWM (:727-770); tau = 1 for Bs_gammas (reference behaviour) ----
         const double tau_g = par[pl.tau_g], tau_a = par[pl.tau_a];
-        const double cur_lp = s_tot[0] - 0.5 * quad_form_dev(cur, par + pl.mean_Bs, par + pl.Tau_Bs, B)
-            - 0.5 * tau_g * quad_form_dev(cur + B, par + pl.mean_g, par + pl.Tau_g, p)
-            - 0.5 * tau_a * quad_form_dev(cur + B + p, par + pl.mean_a, par + pl.Tau_a, A);
-        const double new_lp = s_tot[1] - 0.5 * quad_form_dev(prop, par + pl.mean_Bs, par + pl.Tau_Bs, B)
-            - 0.5 * tau_g * quad_form_dev(prop + B, par + pl.mean_g, par + pl.Tau_g, p)
-            - 0.5 * tau_a * quad_form_dev(prop + B + p, par + pl.mean_a, par + pl.Tau_a, A);
+        double qc[3] = {0.0, 0.0, 0.0}, qp[3] = {0.0, 0.0, 0.0}, rawc = 0.0, rawp = 0.0;
+        for (int j = 0; j < B; ++j) { qc[0] += s_q[0][j]; qp[0] += s_q[1][j]; rawc += s_q[2][j]; rawp += s_q[3][j]; }
+        for (int j = B; j < B + p; ++j) { qc[1] += s_q[0][j]; qp[1] += s_q[1][j]; }
+        for (int j = B + p; j < mm.P; ++j) { qc[2] += s_q[0][j]; qp[2] += s_q[1][j]; }
+        const double cur_lp = s_tot[0] - 0.5 * qc[0] - 0.5 * tau_g * qc[1] - 0.5 * tau_a * qc[2];
+        const double new_lp = s_tot[1] - 0.5 * qp[0] - 0.5 * tau_g * qp[1] - 0.5 * tau_a * qp[2];
         const double lu = log_unif(cc.seed, cc.chain_id, 0u, (uint32_t)iter, 0xFFFFFFFFu, ST_SURV);
+        ctl->last_accept = 0;
+        double raw_Bs = rawc;
         if (lu < new_lp - cur_lp) {
             for (int j = 0; j < mm.P; ++j) cur[j] = prop[j];
             ctl->accept_s_block += 1; ctl->accept_s_total += 1;
+            ctl->last_accept = 1;
+            raw_Bs = rawp;
         }
         if (cc.adaptCov) for (int j = 0; j < mm.P; ++j) par[pl.block_par + j + ctl->i * mm.P] = cur[j];
         // ---- Gibbs draws of the precisions (:776-834) ----
         uint32_t draw = 0;
         {
-            const double Bpost = cc.B_tau_Bs + 0.5 * quad_form_dev(cur, nullptr, par + pl.Tau_Bs, B);
+            const double Bpost = cc.B_tau_Bs + 0.5 * raw_Bs;           // B_tau + 0.5 Bs' Tau Bs (:778-779)
             par[pl.tau_Bs] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_tau_Bs, 1.0 / Bpost)));
         }
         double* alp = cur + B + p;

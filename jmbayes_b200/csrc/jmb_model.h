@@ -30,6 +30,9 @@ namespace jmb {
 
 constexpr int kMaxO = JMB_MAX_OUTCOMES, kMaxT = JMB_MAX_TERMS, kMaxQ = JMB_MAX_Q;
 constexpr int kMaxRT = JMB_MAX_RT, kMaxUT = JMB_MAX_UT;
+// per-subject per-chain state after b[q]: sigma_b, log_pyb, log_pb, accepts in the current block,
+// accepts in total, log p(T|b) under the current and under the last proposed survival parameters
+constexpr int kStateExtra = 7;
 
 struct ModelDesc {
     int O, q, T, A, p, K, S;        // S = 1, or 2 with interval censoring
@@ -46,7 +49,7 @@ struct ModelDesc {
 struct RecordLayout {
     int RP, o_V, o_R, o_W2c, o_Pw, o_W1off, o_W1v, o_W2, o_ZZ[kMaxT], o_U[kMaxT], o_long, c_long;
     int long_cols[kMaxO];           // stored doubles per longitudinal row of outcome k (y + Z cols)
-    int state_stride;               // q + 5 (b, sigma_b, log_pyb, log_pb, acc_block, acc_total), padded to even
+    int state_stride;               // q + kStateExtra, padded to even
 };
 
 JMB_HD constexpr RecordLayout make_layout(const ModelDesc& d) {
@@ -70,7 +73,7 @@ JMB_HD constexpr RecordLayout make_layout(const ModelDesc& d) {
     L.o_long = o;
     L.c_long = d.T * L.RP;
     for (int k = 0; k < d.O; ++k) L.long_cols[k] = 1 + d.qk[k] - d.z_ones0[k];
-    L.state_stride = (d.q + 5 + 1) / 2 * 2;
+    L.state_stride = (d.q + kStateExtra + 1) / 2 * 2;
     return L;
 }
 

@@ -96,10 +96,10 @@ __device__ __forceinline__ void subject_step(const double* __restrict__ rec, con
                                              const double* s_cur, const double* s_prop, const double* s_invD,
                                              const StepRegs<Spec>& pr, const ChainConst& cc, const uint32_t gid,
                                              const int iter, const int it_blk, const bool last_in_block,
-                                             const int lane, const unsigned gmask,
+                                             const bool last_acc, const int lane, const unsigned gmask,
                                              double& acc_cur, double& acc_prop, double& acc_lw) {
     constexpr int G = Spec::d.G, q = Spec::d.q, O = Spec::d.O, T = Spec::d.T, p = Spec::d.p;
-    constexpr int K = Spec::d.K, S = Spec::d.S, WB = Spec::d.WB, RP = Spec::L.RP, QS = q + 5;
+    constexpr int K = Spec::d.K, S = Spec::d.S, WB = Spec::d.WB, RP = Spec::L.RP, QS = q + kStateExtra;
     constexpr int NP = (q + 1) / 2;
     constexpr int oV = Spec::L.o_V, oR = Spec::L.o_R, oLong = Spec::L.o_long, cLong = Spec::L.c_long, oW1off = Spec::L.o_W1off;
     constexpr int oW1v = Spec::L.o_W1v, oW2c = Spec::L.o_W2c, oW2 = Spec::L.o_W2, oPw = Spec::L.o_Pw;
@@ -113,6 +113,9 @@ __device__ __forceinline__ void subject_step(const double* __restrict__ rec, con
     sfor<q>([&](auto j) { bo[j] = st_in[j]; });
     const double sigma_b = st_in[q], pyb_old = st_in[q + 1], pb_old = st_in[q + 2];
     double accb = st_in[q + 3], acct = st_in[q + 4];
+    // log p(T | b_old) under the current survival parameters, carried from the previous iteration:
+    // slot q+5 if its survival proposal was rejected, slot q+6 (evaluated at that proposal) if accepted
+    const double ptb_co = last_acc ? st_in[q + 6] : st_in[q + 5];
 
     // ---- random draws: lanes 0..NP-1 one Box-Muller pair each, lane NP the accept uniform ----
     double log_u;
@@ -178,7 +181,7 @@ __device__ __forceinline__ void subject_step(const double* __restrict__ rec, con
 
     // ---- hazard row of this lane under current / proposed parameters and old / new b
     //      (lin_pred_matF :80-109, log_h :684, H/HL :685-691, survival step :735-741) ----
-    double l_co, l_cn, l_po, l_pn;
+    double l_cn, l_po, l_pn;
     {
         const int off = reinterpret_cast<const int*>(rec + oW1off)[lane];
         double s1c = 0.0, s1p = 0.0;
@@ -193,7 +196,7 @@ __device__ __forceinline__ void subject_step(const double* __restrict__ rec, con
             s2c += wv * pr.gc[j];
             s2p += wv * pr.gp[j];
         });
-        double a_co = 0.0, a_cn = 0.0, a_po = 0.0, a_pn = 0.0;
+        double a_cn = 0.0, a_po = 0.0, a_pn = 0.0;
         sfor<T>([&](auto tc) {
             constexpr int t = tc;
             constexpr int ones0 = Spec::d.zz_ones0[t], rt = Spec::d.rt[t];
@@ -217,38 +220,31 @@ __device__ __forceinline__ void subject_step(const double* __restrict__ rec, con
                     const double uu = rec[oU + u * RP + lane];
                     wo *= uu; wn *= uu;
                 }
-                a_co += wo * pr.alc[c]; a_cn += wn * pr.alc[c];
+                a_cn += wn * pr.alc[c];
                 a_po += wo * pr.alp[c]; a_pn += wn * pr.alp[c];
             });
         });
-        l_co = (s1c + s2c) + a_co; l_cn = (s1c + s2c) + a_cn;
+        l_cn = (s1c + s2c) + a_cn;
         l_po = (s1p + s2p) + a_po; l_pn = (s1p + s2p) + a_pn;
     }
     const double pw = quad ? rec[oPw + lane] : 0.0;
     const double event = rec[0];
 
     // ---- reductions: visit segment over the group; quadrature rows inside 16-lane halves ----
-    double e_co = quad ? pw * exp(l_co) : 0.0, e_cn = quad ? pw * exp(l_cn) : 0.0;
-    double H_co, H_cn, HL_co = 0.0, HL_cn = 0.0;
+    double e_cn = quad ? pw * exp(l_cn) : 0.0;
+    double H_cn, HL_cn = 0.0;
     if constexpr (S == 1 || K == 15) {
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            e_co += __shfl_xor_sync(gmask, e_co, o, 16);
-            e_cn += __shfl_xor_sync(gmask, e_cn, o, 16);
-        }
-        if constexpr (S == 2) {
-            H_co = __shfl_sync(gmask, e_co, 0, G); HL_co = __shfl_sync(gmask, e_co, 16, G);
-            H_cn = __shfl_sync(gmask, e_cn, 0, G); HL_cn = __shfl_sync(gmask, e_cn, 16, G);
-        } else { H_co = e_co; H_cn = e_cn; }
+        for (int o = 8; o > 0; o >>= 1) e_cn += __shfl_xor_sync(gmask, e_cn, o, 16);
+        if constexpr (S == 2) { H_cn = __shfl_sync(gmask, e_cn, 0, G); HL_cn = __shfl_sync(gmask, e_cn, 16, G); }
+        else H_cn = e_cn;
     } else {
-        H_co = group_sum<G>(cls == 1 ? e_co : 0.0, gmask); HL_co = group_sum<G>(cls == 2 ? e_co : 0.0, gmask);
         H_cn = group_sum<G>(cls == 1 ? e_cn : 0.0, gmask); HL_cn = group_sum<G>(cls == 2 ? e_cn : 0.0, gmask);
     }
     const double pyb_new = group_sum<G>(v_pyb, gmask);
-    const double h_co = __shfl_sync(gmask, l_co, 0, G), h_cn = __shfl_sync(gmask, l_cn, 0, G);
+    const double h_cn = __shfl_sync(gmask, l_cn, 0, G);
     const double h_po = __shfl_sync(gmask, l_po, 0, G), h_pn = __shfl_sync(gmask, l_pn, 0, G);
 
-    const double ptb_co = log_ptb_static<S>(event, h_co, H_co, HL_co);
     const double ptb_cn = log_ptb_static<S>(event, h_cn, H_cn, HL_cn);
     const double cur_lp = pyb_old + ptb_co + pb_old;                 // :669
     const double new_lp = pyb_new + ptb_cn + pb_new;                 // :703
@@ -281,12 +277,15 @@ __device__ __forceinline__ void subject_step(const double* __restrict__ rec, con
         sig_new = fmin(fmax(sig_new, cc.eps1), cc.eps3);              // bounds_sigma :411-419
         accb = 0.0;
     }
-    double outv = acct;
+    double outv = 0.0;
     sfor<q>([&](auto j) { if (lane == j) outv = accept ? bn[j] : bo[j]; });
     if (lane == q) outv = sig_new;
     if (lane == q + 1) outv = pyb_acc;
     if (lane == q + 2) outv = pb_acc;
     if (lane == q + 3) outv = accb;
+    if (lane == q + 4) outv = acct;
+    if (lane == q + 5) outv = ptb_c;
+    if (lane == q + 6) outv = ptb_p;
     if (lane < QS && (accept || lane >= q)) st_out[lane] = outv;
 }
 
@@ -319,6 +318,7 @@ jmb_step_static(const int B, const __grid_constant__ ParamLayout pl, const __gri
     for (int j = tid; j < P; j += THREADS) { s_cur[j] = a.par[pl.cur + j]; s_prop[j] = a.par[pl.prop + j]; }
     for (int j = tid; j < q * q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
     const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i;
+    const bool last_acc = a.ctl->last_accept != 0;
     __syncthreads();
     StepRegs<Spec> pr;
     load_step_regs<Spec>(pr, s_cur, s_prop, a.par, pl, B);
@@ -332,7 +332,7 @@ jmb_step_static(const int B, const __grid_constant__ ParamLayout pl, const __gri
     for (int s = s_begin + grp; s < s_end; s += GROUPS) {
         double* st = a.state + (long long)s * SS;
         subject_step<Spec>(a.drec + a.doff[s], a.crec + a.coff[s], st, st, s_cur, s_prop, s_invD, pr, cc,
-                           (uint32_t)(a.subject_offset + s), iter, it_blk, last_in_block, lane, gmask,
+                           (uint32_t)(a.subject_offset + s), iter, it_blk, last_in_block, last_acc, lane, gmask,
                            acc_cur, acc_prop, acc_lw);
     }
     if (lane == 0) { s_red[grp * 3] = acc_cur; s_red[grp * 3 + 1] = acc_prop; s_red[grp * 3 + 2] = acc_lw; }
@@ -400,6 +400,7 @@ jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_c
     if (tid < WARPS * 2) mbar_init(&s_bar[tid], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i;
+    const bool last_acc = a.ctl->last_accept != 0;
     __syncthreads();
     StepRegs<Spec> pr;
     load_step_regs<Spec>(pr, s_cur, s_prop, a.par, pl, B);
@@ -437,30 +438,42 @@ jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_c
         bulk_g2s(dst + ta.cap_d, a.crec + o.c0, bc, &bar[stg]);
         bulk_g2s(dst + ta.cap_d + ta.cap_c, a.state + (long long)o.sA * SS, bs, &bar[stg]);
     };
-    // second-subject offsets inside the staged chunk, per stage (G == 16 only)
-    int dmid0 = 0, cmid0 = 0, dmid1 = 0, cmid1 = 0;
-    if (steps > 0) { const Off o = load_off(0); dmid0 = (int)(o.dm - o.d0); cmid0 = (int)(o.cm - o.c0); if (lane32 == 0) issue(o, 0); }
-    if (steps > 1) { const Off o = load_off(1); dmid1 = (int)(o.dm - o.d0); cmid1 = (int)(o.cm - o.c0); if (lane32 == 0) issue(o, 1); }
+    // A step whose records exceed the stage capacity (rare subjects with very many visits) is not
+    // staged: its lane groups read global memory directly.
+    auto fits = [&](const Off& o) { return (o.d1 - o.d0) <= ta.cap_d && (o.c1 - o.c0) <= ta.cap_c; };
+    struct Pending { long long d0, c0; int dmid, cmid; bool staged; };
+    auto pend = [&](const Off& o) { return Pending{o.d0, o.c0, (int)(o.dm - o.d0), (int)(o.cm - o.c0), fits(o)}; };
+    Pending pd0{}, pd1{};
+    uint32_t ph0 = 0, ph1 = 0;                      // mbarrier phase parity per stage
+    if (steps > 0) { const Off o = load_off(0); pd0 = pend(o); if (lane32 == 0 && pd0.staged) issue(o, 0); }
+    if (steps > 1) { const Off o = load_off(1); pd1 = pend(o); if (lane32 == 0 && pd1.staged) issue(o, 1); }
     for (int t = 0; t < steps; ++t) {
         const int stg = t & 1;
         const bool more = (t + 2 < steps);
         Off nxt{};
         if (more) nxt = load_off(t + 2);
+        const Pending cur = stg ? pd1 : pd0;
         const int s = w_begin + t * SPW + half;
-        const int dmid = (half == 1) ? (stg ? dmid1 : dmid0) : 0, cmid = (half == 1) ? (stg ? cmid1 : cmid0) : 0;
-        mbar_wait(&bar[stg], (uint32_t)((t >> 1) & 1));
-        const double* stage = stage0 + (size_t)stg * stage_doubles;
+        const int dmid = (half == 1) ? cur.dmid : 0, cmid = (half == 1) ? cur.cmid : 0;
+        const double *rec, *crec, *stin;
+        if (cur.staged) {
+            mbar_wait(&bar[stg], stg ? ph1 : ph0);
+            if (stg) ph1 ^= 1u; else ph0 ^= 1u;
+            const double* stage = stage0 + (size_t)stg * stage_doubles;
+            rec = stage + dmid; crec = stage + ta.cap_d + cmid; stin = stage + ta.cap_d + ta.cap_c + half * SS;
+        } else {
+            rec = a.drec + cur.d0 + dmid; crec = a.crec + cur.c0 + cmid; stin = a.state + (long long)s * SS;
+        }
         if (s < w_end) {
-            subject_step<Spec>(stage + dmid, stage + ta.cap_d + cmid, stage + ta.cap_d + ta.cap_c + half * SS,
-                               a.state + (long long)s * SS, s_cur, s_prop, s_invD, pr, cc,
-                               (uint32_t)(a.subject_offset + s), iter, it_blk, last_in_block, lane, gmask,
+            subject_step<Spec>(rec, crec, stin, a.state + (long long)s * SS, s_cur, s_prop, s_invD, pr, cc,
+                               (uint32_t)(a.subject_offset + s), iter, it_blk, last_in_block, last_acc, lane, gmask,
                                acc_cur, acc_prop, acc_lw);
         }
         __syncwarp();
         if (more) {
-            if (stg) { dmid1 = (int)(nxt.dm - nxt.d0); cmid1 = (int)(nxt.cm - nxt.c0); }
-            else { dmid0 = (int)(nxt.dm - nxt.d0); cmid0 = (int)(nxt.cm - nxt.c0); }
-            if (lane32 == 0) issue(nxt, stg);
+            const Pending np = pend(nxt);
+            if (stg) pd1 = np; else pd0 = np;
+            if (lane32 == 0 && np.staged) issue(nxt, stg);
         }
     }
     const int grp = tid / G;
