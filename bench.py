@@ -41,7 +41,7 @@ CPU_SAMPLE_N = 20000
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="config4_shard", choices=sorted(WORKLOADS))
@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -219,7 +219,7 @@ def run_cuda(args):
     # ---- per-launch duration of the step kernel (events around every launch) ----
     fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
     fit.chain_iterate(args.warmup)
-    ksteps = min(args.steps, 50)
+    ksteps = min(args.steps, 100)
     _, kms = fit.chain_iterate(ksteps, time_kernels=True)
     fit.chain_end(fetch=False)
     k_ms = kms / ksteps
