@@ -113,11 +113,7 @@ def cpu_reference(cfg: str, n: int, iters: int, workers: int):
         dt = _cpu_worker((cfg, n, iters, 0))
         return n * iters / dt, dt
     ctx = mp.get_context("fork")
-    with ctx.Pool(workers) as pool:
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(cfg, n, iters, w) for w in range(workers)])
-        wall = time.perf_counter() - t0
-    # wall includes each worker's cohort generation; use the slowest worker's chain time instead
+    # each worker times its own chain (cohort generation excluded); the slowest worker bounds the job
     with ctx.Pool(workers) as pool:
         times = pool.map(_cpu_worker, [(cfg, n, iters, w) for w in range(workers)])
     dt = max(times)
