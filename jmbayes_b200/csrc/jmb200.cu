@@ -604,6 +604,14 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     }
     h->n_out = cc.n_out; h->n_td = pr->n_td;
     h->total_iters = its * ct->n_block;
+    {   // the reference stores a sample whenever iter == keep[k] (src/fast_LAPRWM.cpp:836-850); when that
+        // happens more than n_out times it indexes past its output arrays and fails ("index out of bounds")
+        int hits = 0;
+        for (int v = ct->n_burnin + 1; v <= total_it && v <= h->total_iters - 1; v += ct->n_thin) ++hits;
+        if (hits > cc.n_out)
+            return fail("jmb_chain_begin: control would store more than floor(n_iter / n_thin) samples "
+                        "(the reference fails with 'index out of bounds' for this n_iter / n_thin / n_block)");
+    }
     h->iter_host = 0; h->keep_host = 0; h->check_host = 0;
 
     CU(cudaStreamSynchronize(h->stream));

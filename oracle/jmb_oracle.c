@@ -1,9 +1,9 @@
 /*
  * jmb_oracle.c - CPU restatement of the reference's mvJointModelBayes hot path (plain C11).
  *
- * TEST INFRASTRUCTURE ONLY (see jmb_oracle.h).  PARITY UNPINNED: no reference golden vectors
- * exist and the reference cannot be built in this image; validated against an independent NumPy
- * twin and analytic self-checks instead.
+ * TEST INFRASTRUCTURE ONLY (see jmb_oracle.h).  Pinned against the reference's own sources
+ * compiled in oracle/_ref against a stand-in Armadillo/Rcpp header (no reference golden vectors
+ * exist; R/Rcpp/Armadillo are absent), plus an independent NumPy twin and analytic self-checks.
  *
  * Every function cites the reference lines it follows (paths relative to the JMbayes tree).
  * The algorithm and the data layout are the reference's: dense column-major W1/W1s/W2s,
@@ -396,6 +396,11 @@ int orc_lap_rwm(const orc_data* d, const orc_draw* w, const orc_priors* pr, cons
     const int start_cov_update = (int)floor((double)ct->n_burnin / ct->n_block) - 1;
     int n_keep = 0;
     for (int v = ct->n_burnin + 1; v <= total_it; v += ct->n_thin) ++n_keep;
+    {   /* more hits of iter == keep[k] than output slots: the reference indexes out of bounds (:836-850) */
+        int hits = 0;
+        for (int v = ct->n_burnin + 1; v <= total_it && v <= its * ct->n_block - 1; v += ct->n_thin) ++hits;
+        if (hits > n_out && max_iters <= 0) return 3;
+    }
     const uint32_t seed = ct->seed, chain = ct->chain_id;
     const double mc1 = -ct->c1;
 

@@ -5,12 +5,16 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build, load or
  * call it, and only as the checker / the CPU baseline.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
- *  and cannot be built here (no R, Rcpp, RcppArmadillo or BLAS in the
- * image), so this restatement is validated by construction: every function cites the reference
- * lines it follows, an independently written NumPy twin (oracle/np_twin.py) must agree with it to
- * <= 1e-12, and analytic self-checks (score vs finite differences, GK-15 polynomial exactness)
- * are part of the CPU test-suite.
+ * PARITY PIN: the reference ships no tests, golden vectors or fixtures for this path (SURVEY.md
+ * section 4 / 8c) and R, Rcpp and RcppArmadillo are absent from the image.  The pin is therefore
+ * built here: the reference's OWN sources (/root/reference/src/fast_LAPRWM.cpp, fast_logPost.cpp,
+ * fast_score.cpp) are compiled, unmodified and where they lie, against a stand-in for the missing
+ * Armadillo/Rcpp headers (oracle/ref_shim/RcppArmadillo.h) into oracle/_ref/, and driven with the
+ * same random streams; this restatement reproduces that build's lap_rwm_C chains, logPosterior
+ * and score to <= 1e-11 (tests/test_reference_golden.py, fixtures in tests/golden/).  What the pin
+ * does not cover: the real Armadillo/BLAS summation order and R's RNG (both unavailable).  It is
+ * additionally checked against an independently written NumPy twin (oracle/np_twin.py), Random123
+ * Philox known-answer vectors and analytic self-checks.
  *
  * The input structs mirror the reference's `Data`/`priors`/`initials`/`scales`/`Covs`/`control`
  * lists in the reference's own dense column-major layout (the oracle keeps that layout: dense

@@ -1,5 +1,5 @@
 """Independent NumPy restatement of the per-subject target of the b-step and of the survival-block
-log-posterior / score.  TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see jmb_oracle.h).
+log-posterior / score.  TEST INFRASTRUCTURE ONLY (see jmb_oracle.h for the parity pin).
 
 Written from the reference's formulas (src/fast_LAPRWM.cpp:67-109,168-202,619-650;
 src/fast_logPost.cpp:8-26; src/fast_score.cpp:8-50) directly on the ``Data`` dicts, without the C

@@ -1,11 +1,13 @@
 """ctypes front-end of the CPU oracle (oracle/jmb_oracle.c).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
-legs, never by the product package.  PARITY UNPINNED (see jmb_oracle.h).
+legs, never by the product package.  Pinned against the reference's own sources compiled in
+oracle/_ref (see jmb_oracle.h for what that pin does and does not cover).
 """
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import os
 import subprocess
 
@@ -18,11 +20,27 @@ LIB = os.path.join(HERE, "_build", "libjmb_oracle.so")
 _lib = None
 
 
+def _cpu_stamp() -> str:
+    """-march=native objects must not travel between hosts with different CPUs."""
+    try:
+        txt = open("/proc/cpuinfo").read()
+        flags = next((ln for ln in txt.splitlines() if ln.startswith("flags")), "")
+        model = next((ln for ln in txt.splitlines() if ln.startswith("model name")), "")
+        return hashlib.sha1((model + flags).encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(force: bool = False) -> str:
     src = [os.path.join(HERE, f) for f in ("jmb_oracle.c", "jmb_oracle.h")]
-    stale = force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src)
+    stamp_file = os.path.join(HERE, "_build", "cpu.stamp")
+    stamp = _cpu_stamp()
+    old = open(stamp_file).read() if os.path.exists(stamp_file) else ""
+    stale = (force or not os.path.exists(LIB) or old != stamp
+             or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src))
     if stale:
-        subprocess.run(["make", "-C", HERE, "-s", "-B"], check=True)
+        subprocess.run(["make", "-C", HERE, "-s", "-B", "all"], check=True)
+        open(stamp_file, "w").write(stamp)
     return LIB
 
 

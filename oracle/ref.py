@@ -1,0 +1,76 @@
+"""ctypes front-end of oracle/_ref/libjmb_ref.so: the reference's OWN C++ sources
+(/root/reference/src/fast_LAPRWM.cpp, fast_logPost.cpp, fast_score.cpp), compiled where they lie
+against the stand-in header oracle/ref_shim/RcppArmadillo.h.
+
+TEST INFRASTRUCTURE ONLY.  Available only where the reference tree is present (this container);
+the GPU box uses the prebuilt .so when it travelled with the snapshot.  Used to check the restated
+oracle (jmb_oracle.c) against the reference's actual code, and to generate tests/golden/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from jmbayes_b200 import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libjmb_ref.so")
+REF = os.environ.get("JMB_REFERENCE", "/root/reference")
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB) or os.path.exists(os.path.join(REF, "src", "fast_LAPRWM.cpp"))
+
+
+def build(force: bool = False) -> str | None:
+    have_src = os.path.exists(os.path.join(REF, "src", "fast_LAPRWM.cpp"))
+    if not have_src:
+        return LIB if os.path.exists(LIB) else None
+    deps = [os.path.join(HERE, f) for f in ("ref_driver.cpp", "ref_shim/RcppArmadillo.h", "jmb_oracle.c", "jmb_oracle.h")]
+    stale = force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps)
+    if stale:
+        subprocess.run(["make", "-C", HERE, "-s", "ref", f"REF={REF}"] + (["-B"] if force else []), check=True)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if build() is None:
+            raise RuntimeError("oracle/_ref is not available (no reference tree and no prebuilt library)")
+        L = C.CDLL(LIB)
+        L.jmbref_last_error.restype = C.c_char_p
+        L.jmbref_lap_rwm.argtypes = [C.POINTER(_abi.JmbData), C.POINTER(_abi.JmbDraw), C.POINTER(_abi.JmbPriors),
+                                     C.POINTER(_abi.JmbControl), C.POINTER(_abi.JmbChainIn), C.POINTER(_abi.JmbChainOut)]
+        L.jmbref_logPosterior.restype = C.c_double
+        L.jmbref_logPosterior.argtypes = [C.c_double, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [_abi.c_double_p] * 17 + [C.c_double] * 3
+        L.jmbref_gradient_logPosterior.restype = None
+        L.jmbref_gradient_logPosterior.argtypes = [C.c_double, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [_abi.c_double_p] * 16 + [C.c_double] * 3 + [_abi.c_double_p]
+        _lib = L
+    return _lib
+
+
+def lap_rwm_C(initials, Data, priors, scales, Covs, control, interval_cens=False, multiState=False,
+              chain_id: int = 0, subject_offset: int = 0):
+    """The reference's lap_rwm_C (src/fast_LAPRWM.cpp:431-896), fed the DESIGN.md random streams."""
+    d, k1 = _abi.marshal_data(Data, Covs["b"], interval_cens, multiState, subject_offset)
+    w, k2 = _abi.marshal_draw(Data, interval_cens)
+    pr, k3 = _abi.marshal_priors(priors)
+    ct = _abi.marshal_control(control, chain_id)
+    ci, k4 = _abi.marshal_chain_in(initials, scales, Covs)
+    total, n_out = _abi.chain_dims(control)
+    out, bufs = _abi.alloc_chain_out(d.n, d.q, d.n_Bs, d.n_gammas, d.n_alphas, pr.n_td, n_out, total, extras=False)
+    rc = lib().jmbref_lap_rwm(C.byref(d), C.byref(w), C.byref(pr), C.byref(ct), C.byref(ci), C.byref(out))
+    if rc != 0:
+        raise RuntimeError("reference lap_rwm_C: " + lib().jmbref_last_error().decode())
+    mcmc = {k: bufs[k] for k in ("b", "Bs_gammas", "gammas", "alphas", "phi_gammas", "phi_alphas",
+                                 "tau_Bs_gammas", "tau_gammas", "tau_alphas", "tau_td_alphas")}
+    return dict(mcmc=mcmc, logWeights=bufs["logWeights"],
+                scales=dict(sigma=dict(b=bufs["sigma_b"], Bs_gammas=float(bufs["sigma_surv"][0]),
+                                       gammas=float(bufs["sigma_surv"][1]), alphas=float(bufs["sigma_surv"][2])),
+                            Sigma=dict(Bs_gammas=bufs["Sigma_Bs_gammas"], gammas=bufs["Sigma_gammas"],
+                                       alphas=bufs["Sigma_alphas"])))

@@ -1,0 +1,78 @@
+"""Generates tests/golden/*.npz from the reference's OWN sources (oracle/_ref: /root/reference/src
+compiled against the stand-in Armadillo/Rcpp header).  Run in the build container, where the
+reference tree is mounted:  python tests/golden/make_golden.py
+
+Each fixture stores the control overrides, the chain id and the outputs of the reference's
+lap_rwm_C / logPosterior / gradient_logPosterior for a small seeded cohort (cohorts.make_cohort is
+deterministic, so the inputs are regenerated from (config, n) by the tests).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from jmbayes_b200 import _abi  # noqa: E402
+from jmbayes_b200.cohorts import make_cohort  # noqa: E402
+from oracle import np_twin, ref  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (config, n, control overrides, prior overrides, chain id)
+    "chain_config2": ("config2", 120, dict(n_burnin=40, n_iter=20, n_block=10, n_thin=5), {}, 1),
+    "chain_config3": ("config3", 120, dict(n_burnin=40, n_iter=20, n_block=10, n_thin=5), {}, 2),
+    "chain_config4": ("config4", 120, dict(n_burnin=40, n_iter=20, n_block=10, n_thin=5), {}, 3),
+    "chain_config3_shrink_adapt": ("config3", 90, dict(n_burnin=30, n_iter=30, n_block=10, n_thin=6, adaptCov=True),
+                                   dict(shrink_gammas=True, shrink_alphas=True, double_gamma_alphas=True), 4),
+    "chain_config2_thin1": ("config2", 60, dict(n_burnin=10, n_iter=10, n_block=5, n_thin=1), {}, 5),
+}
+
+
+def run_case(name):
+    cfg, n, ctl_over, pr_over, chain = CASES[name]
+    c = make_cohort(cfg, n=n)
+    ctl = dict(c["control"]); ctl.update(ctl_over)
+    pr = dict(c["priors"]); pr.update(pr_over)
+    r = ref.lap_rwm_C(c["inits"], c["Data"], pr, c["scales"], c["Covs"], ctl, c["interval_cens"], chain_id=chain)
+    out = {f"mcmc_{k}": v for k, v in r["mcmc"].items()}
+    out["logWeights"] = r["logWeights"]
+    out["sigma_b"] = r["scales"]["sigma"]["b"]
+    out["sigma_surv"] = np.array([r["scales"]["sigma"][k] for k in ("Bs_gammas", "gammas", "alphas")])
+    for k in ("Bs_gammas", "gammas", "alphas"):
+        out[f"Sigma_{k}"] = r["scales"]["Sigma"][k]
+    return out
+
+
+def surv_case():
+    c = make_cohort("config3", n=200)
+    D, ini, pr = c["Data"], c["inits"], c["priors"]
+    b = np.asarray(ini["b"])
+    Wl, Wls = np.asfortranarray(np_twin.wlong(D, b, 0)), np.asfortranarray(np_twin.wlong(D, b, 1))
+    L = ref.lib()
+    Bs, g, a = np.array(ini["Bs_gammas"]), np.array(ini["gammas"]), np.array(ini["alphas"])
+    tau, temp = 3.5, 0.7
+    P = lambda x: np.asfortranarray(np.asarray(x, dtype=np.float64))  # noqa: E731
+    keep = [P(x) for x in (D["event"], D["W1"], D["W1s"], Bs, D["W2"], D["W2s"], g, Wl, Wls, a, D["Pw"], pr["mean_Bs_gammas"],
+                           pr["Tau_Bs_gammas"], pr["mean_gammas"], pr["Tau_gammas"], pr["mean_alphas"], pr["Tau_alphas"])]
+    lp = L.jmbref_logPosterior(temp, Wl.shape[0], Wls.shape[0], len(Bs), len(g), len(a),
+                               *[k.ctypes.data_as(_abi.c_double_p) for k in keep], tau, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"])
+    ev = np.asarray(D["event"])
+    ecs = [np.ascontiguousarray(ev @ np.asarray(M)) for M in (D["W1"], D["W2"], Wl)]
+    keep2 = [P(x) for x in (ecs[0], D["W1s"], Bs, ecs[1], D["W2s"], g, ecs[2], Wls, a, D["Pw"], pr["mean_Bs_gammas"],
+                            pr["Tau_Bs_gammas"], pr["mean_gammas"], pr["Tau_gammas"], pr["mean_alphas"], pr["Tau_alphas"])]
+    sc = np.zeros(len(Bs) + len(g) + len(a) + 1)
+    L.jmbref_gradient_logPosterior(temp, Wls.shape[0], len(Bs), len(g), len(a), *[k.ctypes.data_as(_abi.c_double_p) for k in keep2],
+                                   tau, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"], sc.ctypes.data_as(_abi.c_double_p))
+    return dict(logPosterior=np.array([lp]), score=sc, tau=np.array([tau]), temp=np.array([temp]))
+
+
+if __name__ == "__main__":
+    ref.build(force=True)
+    for name in CASES:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_case(name))
+        print("wrote", name)
+    np.savez_compressed(os.path.join(HERE, "surv_config3.npz"), **surv_case())
+    print("wrote surv_config3")
