@@ -146,7 +146,7 @@ def test_uncompacted_designs_use_generic_layout(cuda_lib, oracle):
 
 def test_adapt_cov_and_shrinkage_chain(cuda_lib, oracle):
     c = make_cohort("config3", n=200)
-    ctl = dict(c["control"]); ctl.update(n_burnin=40, n_iter=40, n_block=10, n_thin=7, adaptCov=True)
+    ctl = dict(c["control"]); ctl.update(n_burnin=40, n_iter=40, n_block=10, n_thin=8, adaptCov=True)
     pr = dict(c["priors"]); pr.update(shrink_gammas=True, shrink_alphas=True, double_gamma_alphas=True)
     oracle.set_rowsum_mode(1)
     ref = oracle.lap_rwm_C(c["inits"], c["Data"], pr, c["scales"], c["Covs"], ctl, False, chain_id=1)
@@ -171,3 +171,7 @@ def test_errors_are_loud(cuda_lib):
             fit.eval_logpost_re(c["inits"]["b"], c["inits"]["Bs_gammas"], c["inits"]["gammas"], c["inits"]["alphas"])
     with pytest.raises(cuda_lib.JmbError):
         cuda_lib.Fit(c["Data"], c["Covs"]["b"], False, multiState=True)
+    # a control for which the reference indexes past its output arrays (src/fast_LAPRWM.cpp:836-850)
+    ctl = dict(c["control"]); ctl.update(n_burnin=40, n_iter=40, n_block=10, n_thin=7)
+    with pytest.raises(cuda_lib.JmbError):
+        cuda_lib.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, False)
