@@ -204,6 +204,23 @@ int jmb_lap_rwm(jmb_handle h, const jmb_priors* priors, const jmb_control* contr
 int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* Bs_gammas,
                         const double* gammas, const double* alphas, jmb_eval_out* out);
 
+/* Survival-block Laplace step on fixed Wlong (n x A) / Wlongs (nK x A), the functions marglogLik2
+ * drives through optim(BFGS) (R/margLogLik2.R:42-65,95):
+ *   jmb_set_wlong           uploads the two association designs (Data$Wlong, Data$Wlongs);
+ *   jmb_logPosterior        logPosterior[_nogammas]         (src/fast_logPost.cpp:8-26,30-46)
+ *   jmb_gradient_logPosterior  gradient_logPosterior[_nogammas] (src/fast_score.cpp:8-50,53-84),
+ *                           out has n_Bs + n_gammas + n_alphas + 1 entries.
+ * event_colSums* are derived from the handle's own event/W1/W2/Wlong (R/mvJointModelBayes.R:677-681).
+ * Only the mean_* / Tau_* fields of `priors` are read.  With several ranks the data sums are
+ * all-reduced, every rank returns the full-cohort value. */
+int jmb_set_wlong(jmb_handle h, const double* Wlong, const double* Wlongs);
+int jmb_logPosterior(jmb_handle h, double temp, const double* Bs_gammas, const double* gammas,
+                     const double* alphas, const jmb_priors* priors, double tauBs, double A_tauBs,
+                     double B_tauBs, double* out);
+int jmb_gradient_logPosterior(jmb_handle h, double temp, const double* Bs_gammas,
+                              const double* gammas, const double* alphas, const jmb_priors* priors,
+                              double tauBs, double A_tauBs, double B_tauBs, double* out);
+
 /* Layout facts for the parity tests: the CSR row pointers the device layout was built with
  * (must equal idL2-derived segments bit for bit) and bytes moved per subject-iteration. */
 int jmb_get_row_ptr(jmb_handle h, int outcome, int64_t* row_ptr /* [n+1] */);

@@ -53,6 +53,11 @@ def lib():
     L.jmb_eval_logpost_re.argtypes = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p,
                                       _abi.c_double_p, C.POINTER(_abi.JmbEvalOut)]
     L.jmb_get_row_ptr.argtypes = [vp, C.c_int, _abi.c_int64_p]
+    L.jmb_set_wlong.argtypes = [vp, _abi.c_double_p, _abi.c_double_p]
+    post = [vp, C.c_double, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p, C.POINTER(_abi.JmbPriors),
+            C.c_double, C.c_double, C.c_double, _abi.c_double_p]
+    L.jmb_logPosterior.argtypes = post
+    L.jmb_gradient_logPosterior.argtypes = post
     L.jmb_layout_info.argtypes = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p, _abi.c_int32_p]
     L.jmb_launch_count.argtypes = [vp, _abi.c_int64_p]
     L.jmb_comm_unique_id.argtypes = [C.c_char_p]
@@ -188,6 +193,40 @@ class Fit:
         al = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64))
         _check(lib().jmb_eval_logpost_re(self._h, _dptr(b), _dptr(Bs), _dptr(g), _dptr(al), C.byref(out)))
         return res
+
+    # -- survival-block Laplace step (marglogLik2's fn / gr, R/margLogLik2.R:42-65) --------------------
+    def set_wlong(self, Wlong, Wlongs):
+        """Data$Wlong (n x A) and Data$Wlongs (nK x A) for logPosterior / gradient_logPosterior."""
+        a = np.asfortranarray(np.asarray(Wlong, dtype=np.float64))
+        b = np.asfortranarray(np.asarray(Wlongs, dtype=np.float64))
+        if a.shape != (self.n, self.A) or b.shape != (self.n * self.K, self.A):
+            raise JmbError("set_wlong: Wlong must be n x n_alphas and Wlongs nK x n_alphas")
+        _check(lib().jmb_set_wlong(self._h, _dptr(a), _dptr(b)))
+
+    def _post_args(self, Bs_gammas, gammas, alphas, priors):
+        g = np.ascontiguousarray(np.atleast_1d(np.asarray(gammas, dtype=np.float64)))
+        if g.size == 0:
+            g = np.zeros(1)
+        Bs = np.ascontiguousarray(np.asarray(Bs_gammas, dtype=np.float64))
+        al = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64))
+        pr, keep = _abi.marshal_priors(priors)
+        return Bs, g, al, pr, keep
+
+    def logPosterior(self, temp, Bs_gammas, gammas, alphas, priors, tauBs, A_tauBs, B_tauBs) -> float:
+        """logPosterior[_nogammas] (src/fast_logPost.cpp:8-46) on the designs of this fit."""
+        Bs, g, al, pr, keep = self._post_args(Bs_gammas, gammas, alphas, priors)
+        out = np.zeros(1)
+        _check(lib().jmb_logPosterior(self._h, float(temp), _dptr(Bs), _dptr(g), _dptr(al), C.byref(pr),
+                                      float(tauBs), float(A_tauBs), float(B_tauBs), _dptr(out)))
+        return float(out[0])
+
+    def gradient_logPosterior(self, temp, Bs_gammas, gammas, alphas, priors, tauBs, A_tauBs, B_tauBs):
+        """gradient_logPosterior[_nogammas] (src/fast_score.cpp:8-84): score of (Bs, gammas, alphas, log tauBs)."""
+        Bs, g, al, pr, keep = self._post_args(Bs_gammas, gammas, alphas, priors)
+        out = np.zeros(self.B + self.p + self.A + 1)
+        _check(lib().jmb_gradient_logPosterior(self._h, float(temp), _dptr(Bs), _dptr(g), _dptr(al), C.byref(pr),
+                                               float(tauBs), float(A_tauBs), float(B_tauBs), _dptr(out)))
+        return out
 
     def row_ptr(self, outcome: int):
         rp = np.zeros(self.n + 1, dtype=np.int64)

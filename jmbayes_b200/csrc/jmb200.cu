@@ -100,6 +100,12 @@ struct jmb_handle_s {
     double *o_b = nullptr, *o_par = nullptr, *o_trace = nullptr;   // device outputs
     FinalizeArgs fa{};
     bool want_trace = false;
+    // survival-block Laplace step (logPosterior / gradient_logPosterior)
+    double *d_Wlong = nullptr, *d_Wlongs = nullptr, *d_sp_partials = nullptr, *d_sp_out = nullptr, *d_theta = nullptr;
+    std::vector<double> ecs;                        // event_colSums of [W1 | W2 | Wlong]
+    std::vector<double> h_event;                    // host copy of Data$event
+    std::vector<double> sp_last_theta, sp_last_out; // cache: optim() asks for fn and gr at the same point
+    bool wlong_set = false;
     // launch configuration
     int grid = 0, subjects_per_cta = 0, smem_bytes = 0;
     long long launches = 0;
@@ -415,6 +421,12 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
         }
     });
 
+    // event_colSums of W1 and W2 (R/mvJointModelBayes.R:677-679) for gradient_logPosterior
+    h->h_event.assign(d->event, d->event + n);
+    h->ecs.assign(B + p + d->n_alphas, 0.0);
+    for (int j = 0; j < B; ++j) { double t = 0.0; for (int i = 0; i < n; ++i) t += d->event[i] * d->W1[i + (long long)j * n]; h->ecs[j] = t; }
+    for (int j = 0; j < p; ++j) { double t = 0.0; for (int i = 0; i < n; ++i) t += d->event[i] * d->W2[i + (long long)j * n]; h->ecs[B + j] = t; }
+
     // ---- device allocations ----
     cudaError_t e;
 #define CUH(call) do { e = (call); if (e != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e); jmb_destroy(h); return fail(m_); } } while (0)
@@ -473,6 +485,7 @@ extern "C" int jmb_destroy(jmb_handle h) {
     cudaFree(h->d_drec); cudaFree(h->d_doff); cudaFree(h->d_crec); cudaFree(h->d_coff); cudaFree(h->d_rowptr);
     cudaFree(h->d_state); cudaFree(h->d_par); cudaFree(h->d_ctl); cudaFree(h->d_partials); cudaFree(h->d_eval);
     cudaFree(h->d_tmp); cudaFree(h->o_b); cudaFree(h->o_par); cudaFree(h->o_trace);
+    cudaFree(h->d_Wlong); cudaFree(h->d_Wlongs); cudaFree(h->d_sp_partials); cudaFree(h->d_sp_out); cudaFree(h->d_theta);
     if (h->h_crec) cudaFreeHost(h->h_crec);
     if (h->h_par) cudaFreeHost(h->h_par);
     if (h->h_tmp) cudaFreeHost(h->h_tmp);
@@ -812,6 +825,128 @@ extern "C" int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* 
     double* dst[6] = {out->log_pyb, out->log_pb, out->log_h, out->H, out->HL, out->log_ptb};
     for (int k = 0; k < 6; ++k)
         if (dst[k]) CU(cudaMemcpy(dst[k], h->d_eval + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// survival-block Laplace step: logPosterior / gradient_logPosterior on fixed Wlong / Wlongs
+// ---------------------------------------------------------------------------------------------
+extern "C" int jmb_set_wlong(jmb_handle h, const double* Wlong, const double* Wlongs) {
+    if (!h || !Wlong || !Wlongs) return fail("jmb_set_wlong: null argument");
+    CU(cudaSetDevice(h->device));
+    const int n = h->n, A = h->mm.d.A, K = h->mm.d.K, B = h->mm.B, p = h->mm.d.p;
+    const size_t ns = (size_t)n * K;
+    if (!h->d_Wlong) {
+        CU(cudaMalloc(&h->d_Wlong, sizeof(double) * (size_t)n * A));
+        CU(cudaMalloc(&h->d_Wlongs, sizeof(double) * ns * A));
+        CU(cudaMalloc(&h->d_sp_partials, sizeof(double) * (size_t)h->grid * (h->mm.P + 2)));
+        CU(cudaMalloc(&h->d_sp_out, sizeof(double) * (h->mm.P + 2)));
+        CU(cudaMalloc(&h->d_theta, sizeof(double) * h->mm.P));
+    }
+    CU(cudaMemcpy(h->d_Wlong, Wlong, sizeof(double) * (size_t)n * A, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_Wlongs, Wlongs, sizeof(double) * ns * A, cudaMemcpyHostToDevice));
+    for (int c = 0; c < A; ++c) {      // event_colSumsWlong (R/mvJointModelBayes.R:681)
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += h->h_event[i] * Wlong[i + (size_t)c * n];
+        h->ecs[B + p + c] = t;
+    }
+    h->wlong_set = true;
+    h->sp_last_theta.clear();
+    return 0;
+}
+
+// data sums [sum event*log_h, sum Pw exp(lin), score sums...] at theta; cached for the last theta
+static int surv_post_sums(jmb_handle h, const double* Bs, const double* gam, const double* alp, std::vector<double>& out) {
+    if (!h->wlong_set) return fail("jmb_logPosterior: call jmb_set_wlong first");
+    const ModelMeta& mm = h->mm;
+    const int B = mm.B, p = mm.d.p, A = mm.d.A, P = mm.P, NA = P + 2;
+    std::vector<double> theta(P);
+    memcpy(theta.data(), Bs, sizeof(double) * B);
+    if (p) memcpy(theta.data() + B, gam, sizeof(double) * p);
+    memcpy(theta.data() + B + p, alp, sizeof(double) * A);
+    if (h->sp_last_theta.size() == theta.size() && !memcmp(h->sp_last_theta.data(), theta.data(), sizeof(double) * P)) {
+        out = h->sp_last_out;
+        return 0;
+    }
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->d_theta, theta.data(), sizeof(double) * P, cudaMemcpyHostToDevice, h->stream));
+    SurvPostArgs a{};
+    a.drec = h->d_drec; a.doff = h->d_doff; a.Wlong = h->d_Wlong; a.Wlongs = h->d_Wlongs; a.theta = h->d_theta;
+    a.partials = h->d_sp_partials; a.n = h->n; a.subjects_per_cta = h->subjects_per_cta;
+    const int groups = 256 / mm.d.G;
+    const int smem = (int)sizeof(double) * (P + groups * NA);
+    if (mm.d.G == 16) jmb_surv_post_kernel<16><<<h->grid, 256, smem, h->stream>>>(mm, a);
+    else jmb_surv_post_kernel<32><<<h->grid, 256, smem, h->stream>>>(mm, a);
+    jmb_colsum_kernel<<<NA, 128, 0, h->stream>>>(h->d_sp_partials, h->grid, NA, h->d_sp_out);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    if (h->nranks > 1) {
+        ncclResult_t rc = g_nccl.AllReduce(h->d_sp_out, h->d_sp_out, NA, ncclDouble, ncclSum, h->comm, h->stream);
+        if (rc != ncclSuccess) return fail("ncclAllReduce failed in jmb_logPosterior");
+    }
+    out.assign(NA, 0.0);
+    CU(cudaMemcpyAsync(out.data(), h->d_sp_out, sizeof(double) * NA, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->sp_last_theta = theta;
+    h->sp_last_out = out;
+    return 0;
+}
+
+static double host_quad(const double* x, const double* mean, const double* Tau, int m) {
+    double s = 0.0;
+    for (int j = 0; j < m; ++j) {
+        double t = 0.0;
+        for (int l = 0; l < m; ++l) t += (x[l] - mean[l]) * Tau[l + j * m];
+        s += t * (x[j] - mean[j]);
+    }
+    return s;
+}
+
+extern "C" int jmb_logPosterior(jmb_handle h, double temp, const double* Bs, const double* gam, const double* alp,
+                                const jmb_priors* pr, double tauBs, double A_tauBs, double B_tauBs, double* out) {
+    if (!h || !Bs || !alp || !pr || !out) return fail("jmb_logPosterior: null argument");
+    std::vector<double> s;
+    if (surv_post_sums(h, Bs, gam, alp, s)) return 1;
+    const int B = h->mm.B, p = h->mm.d.p, A = h->mm.d.A;
+    double v = temp * (s[0] - s[1]) - 0.5 * tauBs * host_quad(Bs, pr->mean_Bs_gammas, pr->Tau_Bs_gammas, B);
+    if (p) v -= 0.5 * host_quad(gam, pr->mean_gammas, pr->Tau_gammas, p);
+    v -= 0.5 * host_quad(alp, pr->mean_alphas, pr->Tau_alphas, A);
+    v += (A_tauBs - 1.0) * std::log(tauBs) - B_tauBs * tauBs;
+    *out = v;
+    return 0;
+}
+
+extern "C" int jmb_gradient_logPosterior(jmb_handle h, double temp, const double* Bs, const double* gam, const double* alp,
+                                         const jmb_priors* pr, double tauBs, double A_tauBs, double B_tauBs, double* out) {
+    if (!h || !Bs || !alp || !pr || !out) return fail("jmb_gradient_logPosterior: null argument");
+    std::vector<double> s;
+    if (surv_post_sums(h, Bs, gam, alp, s)) return 1;
+    const int B = h->mm.B, p = h->mm.d.p, A = h->mm.d.A;
+    std::vector<double> ecs = h->ecs;
+    if (h->nranks > 1) {   // event_colSums over the whole cohort
+        CU(cudaMemcpyAsync(h->d_sp_out, ecs.data(), sizeof(double) * (B + p + A), cudaMemcpyHostToDevice, h->stream));
+        if (g_nccl.AllReduce(h->d_sp_out, h->d_sp_out, B + p + A, ncclDouble, ncclSum, h->comm, h->stream) != ncclSuccess)
+            return fail("ncclAllReduce failed in jmb_gradient_logPosterior");
+        CU(cudaMemcpyAsync(ecs.data(), h->d_sp_out, sizeof(double) * (B + p + A), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->sp_last_theta.clear();
+    }
+    const double* par[3] = {Bs, gam, alp};
+    const double* mean[3] = {pr->mean_Bs_gammas, pr->mean_gammas, pr->mean_alphas};
+    const double* Tau[3] = {pr->Tau_Bs_gammas, pr->Tau_gammas, pr->Tau_alphas};
+    const int dims[3] = {B, p, A};
+    const double mult[3] = {tauBs, 1.0, 1.0};
+    int o = 0;
+    for (int blk = 0; blk < 3; ++blk) {
+        const int m = dims[blk];
+        for (int i = 0; i < m; ++i) {
+            double pen = 0.0;
+            for (int l = 0; l < m; ++l) pen += Tau[blk][i + l * m] * (par[blk][l] - mean[blk][l]);
+            out[o + i] = temp * (ecs[o + i] - s[2 + o + i]) - mult[blk] * pen;     // src/fast_score.cpp:21-41
+        }
+        o += m;
+    }
+    out[o] = tauBs * (-0.5 * host_quad(Bs, pr->mean_Bs_gammas, pr->Tau_Bs_gammas, B) + (A_tauBs - 1.0) / tauBs - B_tauBs);  // :44
     return 0;
 }
 

@@ -518,6 +518,114 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     make_proposal(mm, pl, cc, par, s_next_iter, tid, blockDim.x, s_z);
 }
 
+// -------------------------------------------------------------------------------------------
+// Survival-block log-posterior data terms and score sums for FIXED Wlong / Wlongs:
+// logPosterior (src/fast_logPost.cpp:8-26) and gradient_logPosterior (src/fast_score.cpp:8-50).
+//   out[0] = sum_i event_i * log_h_i        out[1] = sum_k Pw_k exp(lin_k)   (all nK rows, no
+//   per-subject rowsum: the reference does not segment-sum H here either)
+//   out[2 + j] = sum_k W[k, j] * Pw_k exp(lin_k),  W = [W1s | W2s | Wlongs]
+// One lane per hazard row like the step kernel; lower-interval rows are not part of these
+// functions.  Per-warp accumulators are updated in lane order and combined in warp / CTA order, so
+// the result is reproducible.
+// -------------------------------------------------------------------------------------------
+struct SurvPostArgs {
+    const double* drec; const long long* doff;
+    const double* Wlong;     // n x A column-major
+    const double* Wlongs;    // nK x A column-major
+    const double* theta;     // [P] Bs_gammas | gammas | alphas
+    double* partials;        // [gridDim.x][P + 2]
+    int n, subjects_per_cta;
+};
+
+template <int G>
+__global__ void __launch_bounds__(256)
+jmb_surv_post_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ SurvPostArgs a) {
+    constexpr int THREADS = 256, GROUPS = THREADS / G;
+    const ModelDesc& md = mm.d;
+    const RecordLayout& L = mm.L;
+    const int P = mm.P, B = mm.B, p = md.p, A = md.A, K = md.K, RP = L.RP, NA = P + 2;
+    extern __shared__ double smem[];
+    double* s_theta = smem;              // [P]
+    double* s_acc = s_theta + P;         // [GROUPS][NA]
+    const int tid = threadIdx.x, grp = tid / G, lane = tid % G;
+    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (0xFFFFu << (16 * ((tid & 31) >> 4)));
+    for (int j = tid; j < P; j += THREADS) s_theta[j] = a.theta[j];
+    for (int j = tid; j < GROUPS * NA; j += THREADS) s_acc[j] = 0.0;
+    __syncthreads();
+    double* acc = s_acc + grp * NA;
+    const long long ns = (long long)a.n * K;
+    const int s_begin = blockIdx.x * a.subjects_per_cta, s_end = min(a.n, s_begin + a.subjects_per_cta);
+    for (int s = s_begin + grp; s < s_end; s += GROUPS) {
+        const double* rec = a.drec + a.doff[s];
+        const int r = lane;
+        const int cls = (r == 0) ? 0 : (r <= K ? 1 : 3);
+        const int off = reinterpret_cast<const int*>(rec + L.o_W1off)[r];
+        double lin = 0.0, w1[8], wl[JMB_MAX_ALPHAS];
+        if (cls != 3) {
+            for (int j = 0; j < md.WB && md.WB <= 8; ++j) { w1[j] = rec[L.o_W1v + j * RP + r]; lin += w1[j] * s_theta[off + j]; }
+            if (md.WB > 8) for (int j = 0; j < md.WB; ++j) lin += rec[L.o_W1v + j * RP + r] * s_theta[off + j];
+            double l2 = 0.0;
+            for (int j = 0; j < p; ++j) l2 += (md.w2_const ? rec[L.o_W2c + j] : rec[L.o_W2 + j * RP + r]) * s_theta[B + j];
+            double l3 = 0.0;
+            for (int c = 0; c < A; ++c) {
+                wl[c] = (cls == 0) ? a.Wlong[s + (long long)c * a.n] : a.Wlongs[(long long)s * K + (r - 1) + (long long)c * ns];
+                l3 += wl[c] * s_theta[B + p + c];
+            }
+            lin = (lin + l2) + l3;
+        }
+        const double event = rec[0];
+        const double pw = (cls == 1) ? rec[L.o_Pw + r] : 0.0;
+        const double Int = (cls == 1) ? pw * exp(lin) : 0.0;
+        // value terms
+        const double Hsum = group_sum<G>(Int, gmask);
+        const double lh = __shfl_sync(gmask, lin, 0, G);
+        if (lane == 0) { acc[0] += event * lh; acc[1] += Hsum; }
+        // score sums: baseline-hazard band, lane by lane in fixed order
+        for (int l = 1; l <= K; ++l) {
+            const int offl = __shfl_sync(gmask, off, l, G);
+            if (md.WB <= 8) {
+                for (int j = 0; j < md.WB; ++j) {
+                    const double v = __shfl_sync(gmask, w1[j] * Int, l, G);
+                    if (lane == 0) acc[2 + offl + j] += v;
+                }
+            } else {
+                for (int j = 0; j < md.WB; ++j) {
+                    const double v = __shfl_sync(gmask, (lane == l) ? rec[L.o_W1v + j * RP + r] * Int : 0.0, l, G);
+                    if (lane == 0) acc[2 + offl + j] += v;
+                }
+            }
+        }
+        for (int j = 0; j < p; ++j) {
+            const double wv = md.w2_const ? rec[L.o_W2c + j] : rec[L.o_W2 + j * RP + r];
+            const double v = group_sum<G>(wv * Int, gmask);
+            if (lane == 0) acc[2 + B + j] += v;
+        }
+        for (int c = 0; c < A; ++c) {
+            const double v = group_sum<G>((cls == 1) ? wl[c] * Int : 0.0, gmask);
+            if (lane == 0) acc[2 + B + p + c] += v;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < NA; j += THREADS) {
+        double t = 0.0;
+        for (int g = 0; g < GROUPS; ++g) t += s_acc[g * NA + j];
+        a.partials[(long long)blockIdx.x * NA + j] = t;
+    }
+}
+
+// fixed-order column sums of a [rows][cols] partials matrix
+__global__ void __launch_bounds__(128)
+jmb_colsum_kernel(const double* partials, int rows, int cols, double* out) {
+    const int j = blockIdx.x;
+    __shared__ double s[128];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < rows; i += 128) t += partials[(long long)i * cols + j];
+    s[threadIdx.x] = t;
+    __syncthreads();
+    for (int w = 64; w > 0; w >>= 1) { if (threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w]; __syncthreads(); }
+    if (threadIdx.x == 0) out[j] = s[0];
+}
+
 // sum the per-CTA partials into par[pl.sums] (multi-GPU path, followed by an NCCL all-reduce)
 __global__ void __launch_bounds__(128)
 jmb_reduce_partials_kernel(const double* partials, int n_partials, double* sums) {

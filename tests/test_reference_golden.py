@@ -112,3 +112,33 @@ def test_cuda_reproduces_reference_golden(cuda_lib, name):
     c, ctl, pr, chain = _inputs(name)
     r = cuda_lib.lap_rwm_C(c["inits"], c["Data"], pr, c["scales"], c["Covs"], ctl, c["interval_cens"], chain_id=chain)
     _check_chain(r, _load(name), rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.gpu
+def test_cuda_logposterior_and_score_match_reference_golden(cuda_lib):
+    """jmb_logPosterior / jmb_gradient_logPosterior against the reference's own fast_logPost.cpp /
+    fast_score.cpp output (tolerance 1e-10 relative, BASELINE.json north_star)."""
+    g = _load("surv_config3")
+    c = make_cohort("config3", n=200)
+    D, ini, pr = c["Data"], c["inits"], c["priors"]
+    b = np.asarray(ini["b"])
+    Wl, Wls = np_twin.wlong(D, b, 0), np_twin.wlong(D, b, 1)
+    tau, temp = float(g["tau"][0]), float(g["temp"][0])
+    with cuda_lib.Fit(D, c["Covs"]["b"], False) as fit:
+        fit.set_wlong(Wl, Wls)
+        lp = fit.logPosterior(temp, ini["Bs_gammas"], ini["gammas"], ini["alphas"], pr, tau, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"])
+        sc = fit.gradient_logPosterior(temp, ini["Bs_gammas"], ini["gammas"], ini["alphas"], pr, tau, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"])
+        # a second point (cache must not be reused) and finite differences of the device value
+        Bs2 = np.asarray(ini["Bs_gammas"]) + 0.01
+        lp2 = fit.logPosterior(temp, Bs2, ini["gammas"], ini["alphas"], pr, tau, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"])
+        sc2 = fit.gradient_logPosterior(temp, Bs2, ini["gammas"], ini["alphas"], pr, tau, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"])
+        h = 1e-5
+        a_p = np.asarray(ini["alphas"]).copy(); a_p[0] += h
+        a_m = np.asarray(ini["alphas"]).copy(); a_m[0] -= h
+        fd = (fit.logPosterior(temp, Bs2, ini["gammas"], a_p, pr, tau, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"])
+              - fit.logPosterior(temp, Bs2, ini["gammas"], a_m, pr, tau, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"])) / (2 * h)
+    assert abs(lp - g["logPosterior"][0]) <= 1e-10 * abs(g["logPosterior"][0])
+    assert np.allclose(sc, g["score"], rtol=1e-10, atol=1e-9)
+    assert lp2 != lp and not np.allclose(sc2, sc)
+    B, p = len(ini["Bs_gammas"]), len(ini["gammas"])
+    assert np.isclose(sc2[B + p], fd, rtol=1e-5)
