@@ -90,6 +90,9 @@ struct jmb_handle_s {
     int* d_rowptr = nullptr;
     double* d_state = nullptr; double* d_par = nullptr; Ctl* d_ctl = nullptr;
     double* d_partials = nullptr; double* d_eval = nullptr; double* d_tmp = nullptr;  // d_tmp: n*(q+1)
+    double* d_Rchol = nullptr;                      // [n][q(q+1)/2] proposal factors (Covs$b)
+    double* d_rng = nullptr;                        // [rng_chunk][n][rng_stride] draws of the b-step
+    size_t rng_capacity = 0; int rng_chunk = 1, rng_stride = 2;
     double* h_crec = nullptr;                       // pinned staging for the per-draw records
     double* h_par = nullptr;                        // pinned staging for the parameter block
     double* h_tmp = nullptr;                        // pinned staging n*(q+1)
@@ -147,7 +150,8 @@ int jmb_handle_s::select_kernel() {
         }
         const int head = (2 * mm.P + md.q * md.q + groups * 3 + 8 * 2 + 1) / 2 * 2;
         // two CTAs per SM: 113 KB each; 8 warps x 2 stages per CTA
-        const long long budget = ((113LL * 1024) / 8 - head) / 16 - spw * SS;
+        const int RS = (md.q + 2) / 2 * 2;     // rng stride (q increments + log u)
+        const long long budget = ((113LL * 1024) / 8 - head) / 16 - spw * (SS + RS);
         long long cap_d = (max_d + 1) / 2 * 2, cap_c = (max_c + 1) / 2 * 2;
         if (cap_d + cap_c > budget) {
             // keep the split proportional; oversize steps fall back to direct global loads
@@ -160,7 +164,7 @@ int jmb_handle_s::select_kernel() {
         // the typical step must fit, otherwise staging is pointless
         long long mean_d = (doff[n] / std::max(n, 1)) * spw, mean_c = (coff[n] / std::max(n, 1)) * spw;
         if (cap_d >= mean_d && cap_c >= mean_c && budget > 0) {
-            const long long stage = (long long)ta.cap_d + ta.cap_c + spw * SS;
+            const long long stage = (long long)ta.cap_d + ta.cap_c + spw * (SS + RS);
             tma_smem = (int)(8LL * (head + 8LL * 2 * stage));
             const int unit = 8 * spw;
             int g = std::min((n + unit - 1) / unit, 2 * num_sms);
@@ -378,9 +382,6 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
             double* rec = drec.data() + h->doff[i];
             rec[0] = d->event[i];
             for (int k = 0; k < O; ++k) reinterpret_cast<int*>(rec + L.o_V)[k] = h->rowptr[k][i + 1] - h->rowptr[k][i];
-            const double* Rm = d->Covs_b + (long long)i * q * q;
-            for (int j = 0; j < q; ++j)
-                for (int l = 0; l <= j; ++l) rec[L.o_R + j * (j + 1) / 2 + l] = Rm[l + j * q];
             if (md.w2_const) for (int j = 0; j < p; ++j) rec[L.o_W2c + j] = d->W2[i + (long long)j * n];
             int* w1off = reinterpret_cast<int*>(rec + L.o_W1off);
             for (int r = 0; r < RP; ++r) {
@@ -421,6 +422,18 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
         }
     });
 
+    // proposal factors: upper Cholesky factors of Covs$b packed by column (R/mvJointModelBayes.R:728-729)
+    const int rlen = q * (q + 1) / 2;
+    std::vector<double> rchol((size_t)n * rlen);
+    parallel_for(n, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            const double* Rm = d->Covs_b + (long long)i * q * q;
+            for (int j = 0; j < q; ++j)
+                for (int l = 0; l <= j; ++l) rchol[(size_t)i * rlen + j * (j + 1) / 2 + l] = Rm[l + j * q];
+        }
+    });
+    h->rng_stride = (q + 2) / 2 * 2;
+
     // event_colSums of W1 and W2 (R/mvJointModelBayes.R:677-679) for gradient_logPosterior
     h->h_event.assign(d->event, d->event + n);
     h->ecs.assign(B + p + d->n_alphas, 0.0);
@@ -444,6 +457,8 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     CUH(cudaHostAlloc(&h->h_crec, sizeof(double) * std::max<long long>(h->coff[n], 2), cudaHostAllocDefault));
     CUH(cudaHostAlloc(&h->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaHostAllocDefault));
     CUH(cudaMemcpy(h->d_drec, drec.data(), sizeof(double) * drec.size(), cudaMemcpyHostToDevice));
+    CUH(cudaMalloc(&h->d_Rchol, sizeof(double) * rchol.size()));
+    CUH(cudaMemcpy(h->d_Rchol, rchol.data(), sizeof(double) * rchol.size(), cudaMemcpyHostToDevice));
     CUH(cudaMemcpy(h->d_doff, h->doff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
     CUH(cudaMemcpy(h->d_coff, h->coff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
     for (int k = 0; k < O; ++k)
@@ -485,6 +500,7 @@ extern "C" int jmb_destroy(jmb_handle h) {
     cudaFree(h->d_drec); cudaFree(h->d_doff); cudaFree(h->d_crec); cudaFree(h->d_coff); cudaFree(h->d_rowptr);
     cudaFree(h->d_state); cudaFree(h->d_par); cudaFree(h->d_ctl); cudaFree(h->d_partials); cudaFree(h->d_eval);
     cudaFree(h->d_tmp); cudaFree(h->o_b); cudaFree(h->o_par); cudaFree(h->o_trace);
+    cudaFree(h->d_Rchol); cudaFree(h->d_rng);
     cudaFree(h->d_Wlong); cudaFree(h->d_Wlongs); cudaFree(h->d_sp_partials); cudaFree(h->d_sp_out); cudaFree(h->d_theta);
     if (h->h_crec) cudaFreeHost(h->h_crec);
     if (h->h_par) cudaFreeHost(h->h_par);
@@ -543,6 +559,7 @@ static int launch_step(jmb_handle h, int mode) {
     a.drec = h->d_drec; a.doff = h->d_doff; a.crec = h->d_crec; a.coff = h->d_coff; a.rowptr = h->d_rowptr;
     a.state = h->d_state; a.par = h->d_par; a.ctl = h->d_ctl; a.partials = h->d_partials; a.eval_out = h->d_eval;
     a.n = h->n; a.subject_offset = h->subject_offset; a.mode = mode; a.subjects_per_cta = h->subjects_per_cta;
+    a.rng = h->d_rng; a.rng_chunk = h->rng_chunk; a.rng_stride = h->rng_stride;
     if (mode == MODE_STEP && h->kernel_mode == 2)
         h->tma_kernel<<<h->tma_grid, 256, h->tma_smem, h->stream>>>(h->mm.B, h->pl, h->cc, a, h->ta);
     else if (mode == MODE_STEP && h->kernel_mode == 1)
@@ -686,6 +703,20 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
         h->launches += 1;
         CU(cudaGetLastError());
     }
+    {   // draws of the b-step: one buffer per chunk of iterations that divides n_block
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_iter = (size_t)n * h->rng_stride * sizeof(double);
+        const size_t budget = std::max<size_t>(per_iter, std::min<size_t>(free_b / 4 + h->rng_capacity, (size_t)8 << 30));
+        int chunk = ct->n_block;
+        while (chunk > 1 && ((size_t)chunk * per_iter > budget || ct->n_block % chunk != 0)) --chunk;
+        h->rng_chunk = chunk;
+        if ((size_t)chunk * per_iter > h->rng_capacity) {
+            cudaFree(h->d_rng); h->d_rng = nullptr;
+            CU(cudaMalloc(&h->d_rng, (size_t)chunk * per_iter));
+            h->rng_capacity = (size_t)chunk * per_iter;
+        }
+    }
     if (launch_finalize(h, 1)) return 1;            // Cholesky factors + proposal of iteration 0
     if (launch_step(h, MODE_INIT)) return 1;        // log_pyb / log_pb at the initial b (:619-621)
     h->chain_open = true;
@@ -704,6 +735,17 @@ extern "C" int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, flo
     float kms = 0.f;
     CU(cudaEventRecord(h->ev0, h->stream));
     for (int k = 0; k < iters; ++k) {
+        const int i_blk = h->iter_host % h->cc.n_block;
+        if (i_blk % h->rng_chunk == 0) {            // draws for the next rng_chunk iterations (:658)
+            PrepArgs pa{};
+            pa.Rchol = h->d_Rchol; pa.state = h->d_state; pa.rng = h->d_rng; pa.n = h->n; pa.q = mm.d.q;
+            pa.state_stride = mm.L.state_stride; pa.rng_stride = h->rng_stride; pa.iter0 = h->iter_host; pa.count = h->rng_chunk;
+            pa.subject_offset = h->subject_offset;
+            const long long tot = (long long)h->n * h->rng_chunk;
+            jmb_block_prep_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->cc, pa);
+            h->launches += 1;
+            CU(cudaGetLastError());
+        }
         if (step_kernel_ms) CU(cudaEventRecord(h->evk0, h->stream));
         if (launch_step(h, MODE_STEP)) return 1;
         if (step_kernel_ms) {
@@ -714,6 +756,11 @@ extern "C" int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, flo
             kms += t;
         }
         if (launch_finalize(h, 0)) return 1;
+        if (i_blk == h->cc.n_block - 1) {           // block end: per-subject scale adaptation (:853-859)
+            jmb_adapt_sigma_kernel<<<(h->n + 255) / 256, 256, 0, h->stream>>>(h->cc, h->d_state, h->n, mm.d.q, mm.L.state_stride, h->d_ctl);
+            h->launches += 1;
+            CU(cudaGetLastError());
+        }
         if (is_keep_iter(h, h->iter_host)) {
             const long long tot = (long long)h->n * mm.d.q;
             jmb_extract_b_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
@@ -963,7 +1010,8 @@ extern "C" int jmb_layout_info(jmb_handle h, double* shared_bytes, double* chain
     if (!h) return fail("jmb_layout_info: null handle");
     const double n = h->n;
     if (shared_bytes) *shared_bytes = (8.0 * h->doff[h->n] + 8.0 * 2 * (h->n + 1) + 4.0 * h->mm.d.O * (h->n + 1)) / n;
-    if (chain_bytes) *chain_bytes = 8.0 * h->coff[h->n] / n + 2.0 * 8.0 * h->mm.L.state_stride;
+    // per-draw record + state read/write + b-step draws (written once per block, read once)
+    if (chain_bytes) *chain_bytes = 8.0 * h->coff[h->n] / n + 2.0 * 8.0 * h->mm.L.state_stride + 2.0 * 8.0 * h->rng_stride;
     if (w1_band) *w1_band = h->mm.d.WB;
     if (group_lanes) *group_lanes = h->mm.d.G;
     return 0;

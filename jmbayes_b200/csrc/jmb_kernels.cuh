@@ -33,6 +33,9 @@ struct StepArgs {
     long long subject_offset;
     int mode;
     int subjects_per_cta;
+    const double* rng;       // [rng_chunk][n][rng_stride]: proposal increments b_new - b (q) and log u
+    int rng_chunk;           // iterations covered by the buffer (the block position i indexes it)
+    int rng_stride;          // q + 1 rounded up to even
 };
 
 // -------------------------------------------------------------------------------------------
@@ -61,17 +64,14 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
     for (int j = tid; j < mm.P; j += THREADS) { s_cur[j] = a.par[pl.cur + j]; s_prop[j] = a.par[pl.prop + j]; }
     for (int j = tid; j < md.q * md.q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
     for (int j = tid; j < md.O; j += THREADS) s_isig[j] = 1.0 / a.par[pl.sigmas + j];
-    const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i, last_acc = a.ctl->last_accept;
+    const int i_blk = a.ctl->i, last_acc = a.ctl->last_accept;
     __syncthreads();
 
     const int grp = tid / G, lane = tid % G;
     const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (0xFFFFu << (16 * ((tid & 31) >> 4)));
     double* bo = s_grp + grp * 3 * QS;
     double* bn = bo + QS;
-    double* zb = bn + QS;
     const int q = md.q, RP = L.RP, K = md.K, S = md.S;
-    const bool last_in_block = (i_blk == cc.n_block - 1);
-
     double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;     // lane 0 of each group
     const int s_begin = blockIdx.x * a.subjects_per_cta;
     const int s_end = min(a.n, s_begin + a.subjects_per_cta);
@@ -80,30 +80,13 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         const double* rec = a.drec + a.doff[s];
         const double* crec = a.crec + a.coff[s];
         double* st = a.state + (long long)s * L.state_stride;
-        const uint32_t gid = (uint32_t)(a.subject_offset + s);
-
         // ---- state + proposal (mvrnorm_cube / extract_b, src/fast_LAPRWM.cpp:123-146,670) ----
+        // the draws of this iteration were produced by jmb_block_prep_kernel
+        const double* rg = a.rng + ((long long)(i_blk % a.rng_chunk) * a.n + s) * a.rng_stride;
         for (int j = lane; j < QS; j += G) bo[j] = st[j];
-        if (a.mode == MODE_STEP) {
-            for (int j = lane; j < q; j += G) {
-                double z0, z1;
-                rnorm_pair(cc.seed, cc.chain_id, gid, (uint32_t)iter, (uint32_t)(j >> 1), ST_B_PROP, z0, z1);
-                zb[j] = (j & 1) ? z1 : z0;
-            }
-        }
         __syncwarp(gmask);
-        const double sigma_b = bo[q], pyb_old = bo[q + 1], pb_old = bo[q + 2];
-        if (a.mode == MODE_STEP) {
-            const double sd = sqrt(sigma_b);
-            for (int j = lane; j < q; j += G) {
-                const double* Rj = rec + L.o_R + (j * (j + 1)) / 2;    // column j of the upper factor
-                double pj = 0.0;
-                for (int l = 0; l <= j; ++l) pj += zb[l] * Rj[l];
-                bn[j] = bo[j] + sd * pj;
-            }
-        } else {
-            for (int j = lane; j < q; j += G) bn[j] = bo[j];
-        }
+        const double pyb_old = bo[q + 1], pb_old = bo[q + 2];
+        for (int j = lane; j < q; j += G) bn[j] = (a.mode == MODE_STEP) ? bo[j] + rg[j] : bo[j];   // :670
         __syncwarp(gmask);
 
         // ---- log p(b) for the proposal: -0.5 b' invD b (src/fast_LAPRWM.cpp:673) ----
@@ -204,7 +187,7 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         if (a.mode == MODE_STEP) {
             const double cur_lp = pyb_old + ptb_co + pb_old;          // :669
             const double new_lp = pyb_new + ptb_cn + pb_new;          // :703
-            const double lu = log_unif(cc.seed, cc.chain_id, gid, (uint32_t)iter, 0u, ST_B_ACC);
+            const double lu = rg[q];
             accept = lu < (new_lp - cur_lp);                          // :706 (NaN rejects)
         } else {
             accept = true;
@@ -232,18 +215,10 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         } else {
             double accb = bo[q + 3] + ((a.mode == MODE_STEP && accept) ? 1.0 : 0.0);
             double acct = bo[q + 4] + ((a.mode == MODE_STEP && accept) ? 1.0 : 0.0);
-            double sig_new = sigma_b;
-            if (a.mode == MODE_STEP && last_in_block) {
-                const double g2 = cc.c0 * pow((double)(it_blk + 1), cc.mc1);
-                const double rate = accb / cc.n_block;
-                sig_new = exp(log(sigma_b) + g2 * (rate - cc.target_acc));
-                sig_new = fmin(fmax(sig_new, cc.eps1), cc.eps3);       // bounds_sigma :411-419
-                accb = 0.0;
-            }
             for (int j = lane; j < QS; j += G) {
                 double val;
                 if (j < q) val = accept ? bn[j] : bo[j];
-                else if (j == q) val = sig_new;
+                else if (j == q) val = bo[q];
                 else if (j == q + 1) val = pyb_acc;
                 else if (j == q + 2) val = pb_acc;
                 else if (j == q + 3) val = accb;
@@ -516,6 +491,59 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     }
     __syncthreads();
     make_proposal(mm, pl, cc, par, s_next_iter, tid, blockDim.x, s_z);
+}
+
+// -------------------------------------------------------------------------------------------
+// Once per block of iterations (src/fast_LAPRWM.cpp:651-661): the random draws of the b-step.
+// The reference materialises rand_b = mvrnorm_cube(n_block, Sigma_b, sigma_b) per block (:658) and
+// all accept uniforms up front (:618); here one thread per (iteration-in-chunk, subject) writes
+// the proposal increment sqrt(sigma_b[i]) z'R_i (q doubles) and log u into the rng buffer that the
+// step kernels stream.  sigma_b only changes at block ends, so a chunk never straddles a block.
+// -------------------------------------------------------------------------------------------
+struct PrepArgs {
+    const double* Rchol;     // [n][q(q+1)/2] upper Cholesky factors of Covs$b, packed by column
+    const double* state; double* rng;
+    int n, q, state_stride, rng_stride, iter0, count;
+    long long subject_offset;
+};
+
+__global__ void __launch_bounds__(256)
+jmb_block_prep_kernel(const __grid_constant__ ChainConst cc, const __grid_constant__ PrepArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)a.n * a.count) return;
+    const int k = (int)(t / a.n), s = (int)(t % a.n);
+    const uint32_t gid = (uint32_t)(a.subject_offset + s), iter = (uint32_t)(a.iter0 + k);
+    const double* R = a.Rchol + (long long)s * (a.q * (a.q + 1) / 2);
+    const double sd = sqrt(a.state[(long long)s * a.state_stride + a.q]);
+    double* out = a.rng + ((long long)k * a.n + s) * a.rng_stride;
+    double z[JMB_MAX_Q];
+    for (int sl = 0; sl < (a.q + 1) / 2; ++sl) {
+        double z0, z1;
+        rnorm_pair(cc.seed, cc.chain_id, gid, iter, (uint32_t)sl, ST_B_PROP, z0, z1);
+        z[2 * sl] = z0;
+        if (2 * sl + 1 < JMB_MAX_Q) z[2 * sl + 1] = z1;
+    }
+    for (int j = 0; j < a.q; ++j) {
+        const double* Rj = R + (j * (j + 1)) / 2;      // column j of the upper factor
+        double pj = 0.0;
+        for (int l = 0; l <= j; ++l) pj += z[l] * Rj[l];
+        out[j] = sd * pj;
+    }
+    out[a.q] = log_unif(cc.seed, cc.chain_id, gid, iter, 0u, ST_B_ACC);
+}
+
+// per-subject Robbins-Monro update of sigma_b at the end of block `it` (:853-859, bounds_sigma :411-419)
+__global__ void __launch_bounds__(256)
+jmb_adapt_sigma_kernel(const __grid_constant__ ChainConst cc, double* state, int n, int q, int stride, const Ctl* ctl) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    // launched after the finalize kernel of the block's last iteration: ctl->it already counts it
+    const double g2 = cc.c0 * pow((double)ctl->it, cc.mc1);
+    double* st = state + (long long)s * stride;
+    const double rate = st[q + 3] / cc.n_block;
+    double sg = exp(log(st[q]) + g2 * (rate - cc.target_acc));
+    st[q] = fmin(fmax(sg, cc.eps1), cc.eps3);
+    st[q + 3] = 0.0;
 }
 
 // -------------------------------------------------------------------------------------------

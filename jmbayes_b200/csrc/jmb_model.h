@@ -4,8 +4,7 @@
 // A subject's designs live in two contiguous records (units: doubles):
 //
 //   design record (shared by all chains of a fit)
-//     [0] event  [o_V ..] int32 visit counts per outcome  [o_R ..] upper Cholesky factor of
-//     Covs$b[,,i], packed by column
+//     [0] event  [o_V ..] int32 visit counts per outcome
 //     [o_W2c ..] W2 row when the W2s rows repeat within the subject (w2_const)
 //     hazard rows, one per lane r = 0..RP-1 (0: event time, 1..K: quadrature, K+1..2K: lower-
 //     interval quadrature), each field stored as [column][RP]:
@@ -13,6 +12,9 @@
 //       w2_const) | per term: stored ZZ columns, stored U columns
 //     longitudinal rows, per outcome: y[v] | stored Z columns [v] each
 //   per-draw record: XXbetas/XXsbetas rows [T][RP] | Xbetas rows per outcome
+//
+// The upper Cholesky factors of Covs$b (packed by column, q(q+1)/2 doubles per subject) live in
+// their own array: only the once-per-block proposal kernel reads them.
 //
 // "Stored" columns: an all-ones first column of Z / ZZ (random intercept) and an all-ones U
 // (default interaction design ~1) are not stored; the flags below say so.  jmb_create() decides
@@ -47,7 +49,7 @@ struct ModelDesc {
 };
 
 struct RecordLayout {
-    int RP, o_V, o_R, o_W2c, o_Pw, o_W1off, o_W1v, o_W2, o_ZZ[kMaxT], o_U[kMaxT], o_long, c_long;
+    int RP, o_V, o_W2c, o_Pw, o_W1off, o_W1v, o_W2, o_ZZ[kMaxT], o_U[kMaxT], o_long, c_long;
     int long_cols[kMaxO];           // stored doubles per longitudinal row of outcome k (y + Z cols)
     int state_stride;               // q + kStateExtra, padded to even
 };
@@ -56,8 +58,7 @@ JMB_HD constexpr RecordLayout make_layout(const ModelDesc& d) {
     RecordLayout L{};
     L.RP = d.G;
     L.o_V = 1;
-    L.o_R = 1 + (d.O + 1) / 2;
-    int o = L.o_R + d.q * (d.q + 1) / 2;
+    int o = 1 + (d.O + 1) / 2;
     L.o_W2c = o;
     if (d.w2_const) o += d.p;
     o = (o + 1) / 2 * 2;

@@ -92,56 +92,32 @@ struct StepRegs {
 // rec / crec / st_in may point to global or to (TMA-staged) shared memory.
 template <class Spec>
 __device__ __forceinline__ void subject_step(const double* __restrict__ rec, const double* __restrict__ crec,
-                                             const double* __restrict__ st_in, double* __restrict__ st_out,
+                                             const double* __restrict__ st_in, const double* __restrict__ rg,
+                                             double* __restrict__ st_out,
                                              const double* s_cur, const double* s_prop, const double* s_invD,
-                                             const StepRegs<Spec>& pr, const ChainConst& cc, const uint32_t gid,
-                                             const int iter, const int it_blk, const bool last_in_block,
+                                             const StepRegs<Spec>& pr,
                                              const bool last_acc, const int lane, const unsigned gmask,
                                              double& acc_cur, double& acc_prop, double& acc_lw) {
     constexpr int G = Spec::d.G, q = Spec::d.q, O = Spec::d.O, T = Spec::d.T, p = Spec::d.p;
     constexpr int K = Spec::d.K, S = Spec::d.S, WB = Spec::d.WB, RP = Spec::L.RP, QS = q + kStateExtra;
-    constexpr int NP = (q + 1) / 2;
-    constexpr int oV = Spec::L.o_V, oR = Spec::L.o_R, oLong = Spec::L.o_long, cLong = Spec::L.c_long, oW1off = Spec::L.o_W1off;
+    constexpr int oV = Spec::L.o_V, oLong = Spec::L.o_long, cLong = Spec::L.c_long, oW1off = Spec::L.o_W1off;
     constexpr int oW1v = Spec::L.o_W1v, oW2c = Spec::L.o_W2c, oW2 = Spec::L.o_W2, oPw = Spec::L.o_Pw;
     constexpr bool W2C = Spec::d.w2_const != 0;
-    static_assert(RP == G && 1 + K * S <= G && NP < G && QS <= G, "one hazard row per lane");
+    static_assert(RP == G && 1 + K * S <= G && QS <= G, "one hazard row per lane");
     const int cls = (lane == 0) ? 0 : (lane <= K ? 1 : ((S == 2 && lane <= 2 * K) ? 2 : 3));
     const bool quad = (cls == 1 || cls == 2);
 
     // ---- current state (uniform loads) ----
     double bo[q], bn[q];
     sfor<q>([&](auto j) { bo[j] = st_in[j]; });
-    const double sigma_b = st_in[q], pyb_old = st_in[q + 1], pb_old = st_in[q + 2];
+    const double pyb_old = st_in[q + 1], pb_old = st_in[q + 2];
     double accb = st_in[q + 3], acct = st_in[q + 4];
     // log p(T | b_old) under the current survival parameters, carried from the previous iteration:
     // slot q+5 if its survival proposal was rejected, slot q+6 (evaluated at that proposal) if accepted
     const double ptb_co = last_acc ? st_in[q + 6] : st_in[q + 5];
-
-    // ---- random draws: lanes 0..NP-1 one Box-Muller pair each, lane NP the accept uniform ----
-    double log_u;
-    {
-        const uint32_t slot = (lane < NP) ? (uint32_t)lane : 0u;
-        const uint32_t stream = (lane < NP) ? ST_B_PROP : ST_B_ACC;
-        uint32_t rr[4];
-        philox4x32(cc.seed, cc.chain_id, gid, (uint32_t)iter, slot, stream, rr);
-        const double u1 = u01(rr[0], rr[1]), u2 = u01(rr[2], rr[3]);
-        const double lg = log(u1);
-        const double rad = sqrt(-2.0 * lg);
-        double sn, cs;
-        sincospi(2.0 * u2, &sn, &cs);
-        const double z0 = rad * cs, z1 = rad * sn;
-        log_u = __shfl_sync(gmask, lg, NP, G);
-        // proposal: b + sqrt(sigma_b) * z' R_i  (mvrnorm_cube / extract_b, :123-146,670)
-        double z[q];
-        sfor<q>([&](auto j) { z[j] = __shfl_sync(gmask, (j & 1) ? z1 : z0, j >> 1, G); });
-        const double sd = sqrt(sigma_b);
-        sfor<q>([&](auto jc) {
-            constexpr int j = jc;
-            double pj = 0.0;
-            sfor<j + 1>([&](auto l) { pj += z[l] * rec[oR + (j * (j + 1)) / 2 + l]; });
-            bn[j] = bo[j] + sd * pj;
-        });
-    }
+    // proposal increment sqrt(sigma_b) z'R_i and log u of this iteration (jmb_block_prep_kernel; :658,670,706)
+    sfor<q>([&](auto j) { bn[j] = bo[j] + rg[j]; });
+    const double log_u = rg[q];
 
     // ---- log p(b) at the proposal (:673) ----
     double pb_new = 0.0;
@@ -267,26 +243,18 @@ __device__ __forceinline__ void subject_step(const double* __restrict__ rec, con
     const double pb_acc = accept ? pb_new : pb_old;
     acc_cur += ptb_c; acc_prop += ptb_p; acc_lw += pyb_acc + pb_acc;
 
-    // ---- state write-back (:707-724) + per-subject scale adaptation at block ends (:853-859) ----
+    // ---- state write-back (:707-724); sigma_b is adapted by jmb_adapt_sigma_kernel at block ends ----
     accb += accept ? 1.0 : 0.0;
     acct += accept ? 1.0 : 0.0;
-    double sig_new = sigma_b;
-    if (last_in_block) {
-        const double g2 = cc.c0 * pow((double)(it_blk + 1), cc.mc1);
-        sig_new = exp(log(sigma_b) + g2 * (accb / cc.n_block - cc.target_acc));
-        sig_new = fmin(fmax(sig_new, cc.eps1), cc.eps3);              // bounds_sigma :411-419
-        accb = 0.0;
-    }
     double outv = 0.0;
     sfor<q>([&](auto j) { if (lane == j) outv = accept ? bn[j] : bo[j]; });
-    if (lane == q) outv = sig_new;
     if (lane == q + 1) outv = pyb_acc;
     if (lane == q + 2) outv = pb_acc;
     if (lane == q + 3) outv = accb;
     if (lane == q + 4) outv = acct;
     if (lane == q + 5) outv = ptb_c;
     if (lane == q + 6) outv = ptb_p;
-    if (lane < QS && (accept || lane >= q)) st_out[lane] = outv;
+    if (lane < QS && lane != q && (accept || lane > q)) st_out[lane] = outv;     // slot q (sigma_b) is the adapt kernel's
 }
 
 template <class Spec>
@@ -317,7 +285,7 @@ jmb_step_static(const int B, const __grid_constant__ ParamLayout pl, const __gri
     const int tid = threadIdx.x;
     for (int j = tid; j < P; j += THREADS) { s_cur[j] = a.par[pl.cur + j]; s_prop[j] = a.par[pl.prop + j]; }
     for (int j = tid; j < q * q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
-    const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i;
+    const int i_blk = a.ctl->i;
     const bool last_acc = a.ctl->last_accept != 0;
     __syncthreads();
     StepRegs<Spec> pr;
@@ -325,15 +293,14 @@ jmb_step_static(const int B, const __grid_constant__ ParamLayout pl, const __gri
 
     const int grp = tid / G, lane = tid % G;
     const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (0xFFFFu << (16 * ((tid & 31) >> 4)));
-    const bool last_in_block = (i_blk == cc.n_block - 1);
+    const double* rng_it = a.rng + (long long)(i_blk % a.rng_chunk) * a.n * a.rng_stride;
     double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;
     const int s_begin = blockIdx.x * a.subjects_per_cta;
     const int s_end = min(a.n, s_begin + a.subjects_per_cta);
     for (int s = s_begin + grp; s < s_end; s += GROUPS) {
         double* st = a.state + (long long)s * SS;
-        subject_step<Spec>(a.drec + a.doff[s], a.crec + a.coff[s], st, st, s_cur, s_prop, s_invD, pr, cc,
-                           (uint32_t)(a.subject_offset + s), iter, it_blk, last_in_block, last_acc, lane, gmask,
-                           acc_cur, acc_prop, acc_lw);
+        subject_step<Spec>(a.drec + a.doff[s], a.crec + a.coff[s], st, rng_it + (long long)s * a.rng_stride, st,
+                           s_cur, s_prop, s_invD, pr, last_acc, lane, gmask, acc_cur, acc_prop, acc_lw);
     }
     if (lane == 0) { s_red[grp * 3] = acc_cur; s_red[grp * 3 + 1] = acc_prop; s_red[grp * 3 + 2] = acc_lw; }
     __syncthreads();
@@ -391,7 +358,8 @@ jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_c
     double* s_red = s_invD + q * q;                // [GROUPS][3]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + GROUPS * 3);   // [WARPS][2]
     const int head = (2 * P + q * q + GROUPS * 3 + WARPS * 2 + 1) / 2 * 2;   // keep 16-byte alignment
-    const int stage_doubles = ta.cap_d + ta.cap_c + SPW * SS;
+    constexpr int RS = (q + 2) / 2 * 2;            // rng stride: q increments + log u, padded to even
+    const int stage_doubles = ta.cap_d + ta.cap_c + SPW * (SS + RS);
     double* s_stage = smem + head;                 // [WARPS][2][stage_doubles]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
@@ -399,15 +367,15 @@ jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_c
     for (int j = tid; j < q * q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
     if (tid < WARPS * 2) mbar_init(&s_bar[tid], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const int iter = a.ctl->iter, it_blk = a.ctl->it, i_blk = a.ctl->i;
+    const int i_blk = a.ctl->i;
     const bool last_acc = a.ctl->last_accept != 0;
     __syncthreads();
     StepRegs<Spec> pr;
     load_step_regs<Spec>(pr, s_cur, s_prop, a.par, pl, B);
+    const double* rng_it = a.rng + (long long)(i_blk % a.rng_chunk) * a.n * RS;
 
     const int half = (G == 16) ? (lane32 >> 4) : 0, lane = lane32 % G;
     const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (0xFFFFu << (16 * half));
-    const bool last_in_block = (i_blk == cc.n_block - 1);
     double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;
 
     // this warp's contiguous run of subjects
@@ -433,10 +401,12 @@ jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_c
     auto issue = [&](const Off& o, int stg) {     // lane32 == 0 only
         double* dst = stage0 + (size_t)stg * stage_doubles;
         const uint32_t bd = (uint32_t)(o.d1 - o.d0) * 8u, bc = (uint32_t)(o.c1 - o.c0) * 8u, bs = (uint32_t)(o.sB - o.sA) * SS * 8u;
-        mbar_expect_tx(&bar[stg], bd + bc + bs);
+        const uint32_t br = (uint32_t)(o.sB - o.sA) * RS * 8u;
+        mbar_expect_tx(&bar[stg], bd + bc + bs + br);
         bulk_g2s(dst, a.drec + o.d0, bd, &bar[stg]);
         bulk_g2s(dst + ta.cap_d, a.crec + o.c0, bc, &bar[stg]);
         bulk_g2s(dst + ta.cap_d + ta.cap_c, a.state + (long long)o.sA * SS, bs, &bar[stg]);
+        bulk_g2s(dst + ta.cap_d + ta.cap_c + SPW * SS, rng_it + (long long)o.sA * RS, br, &bar[stg]);
     };
     // A step whose records exceed the stage capacity (rare subjects with very many visits) is not
     // staged: its lane groups read global memory directly.
@@ -455,19 +425,20 @@ jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_c
         const Pending cur = stg ? pd1 : pd0;
         const int s = w_begin + t * SPW + half;
         const int dmid = (half == 1) ? cur.dmid : 0, cmid = (half == 1) ? cur.cmid : 0;
-        const double *rec, *crec, *stin;
+        const double *rec, *crec, *stin, *rg;
         if (cur.staged) {
             mbar_wait(&bar[stg], stg ? ph1 : ph0);
             if (stg) ph1 ^= 1u; else ph0 ^= 1u;
             const double* stage = stage0 + (size_t)stg * stage_doubles;
             rec = stage + dmid; crec = stage + ta.cap_d + cmid; stin = stage + ta.cap_d + ta.cap_c + half * SS;
+            rg = stage + ta.cap_d + ta.cap_c + SPW * SS + half * RS;
         } else {
             rec = a.drec + cur.d0 + dmid; crec = a.crec + cur.c0 + cmid; stin = a.state + (long long)s * SS;
+            rg = rng_it + (long long)s * RS;
         }
         if (s < w_end) {
-            subject_step<Spec>(rec, crec, stin, a.state + (long long)s * SS, s_cur, s_prop, s_invD, pr, cc,
-                               (uint32_t)(a.subject_offset + s), iter, it_blk, last_in_block, last_acc, lane, gmask,
-                               acc_cur, acc_prop, acc_lw);
+            subject_step<Spec>(rec, crec, stin, rg, a.state + (long long)s * SS, s_cur, s_prop, s_invD, pr,
+                               last_acc, lane, gmask, acc_cur, acc_prop, acc_lw);
         }
         __syncwarp();
         if (more) {
