@@ -109,6 +109,7 @@ struct jmb_handle_s {
     std::vector<double> h_event;                    // host copy of Data$event
     std::vector<double> sp_last_theta, sp_last_out; // cache: optim() asks for fn and gr at the same point
     bool wlong_set = false;
+    bool fin_attr_set = false;
     // launch configuration
     int grid = 0, subjects_per_cta = 0, smem_bytes = 0;
     long long launches = 0;
@@ -585,7 +586,13 @@ static int launch_finalize(jmb_handle h, int phase) {
         ncclResult_t rc = g_nccl.AllReduce(h->d_par + h->pl.sums, h->d_par + h->pl.sums, 3, ncclDouble, ncclSum, h->comm, h->stream);
         if (rc != ncclSuccess) return fail(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
     }
-    jmb_finalize_kernel<<<1, 128, 0, h->stream>>>(h->mm, h->pl, h->cc, a);
+    const size_t fin_smem = sizeof(double) * (size_t)h->pl.block_par;
+    a.use_smem = (fin_smem <= 200 * 1024) ? 1 : 0;
+    if (a.use_smem && fin_smem > 48 * 1024 && !h->fin_attr_set) {
+        CU(cudaFuncSetAttribute((const void*)jmb_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+        h->fin_attr_set = true;
+    }
+    jmb_finalize_kernel<<<1, 128, a.use_smem ? fin_smem : 0, h->stream>>>(h->mm, h->pl, h->cc, a);
     h->launches += 1;
     CU(cudaGetLastError());
     return 0;
@@ -742,7 +749,11 @@ extern "C" int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, flo
             pa.state_stride = mm.L.state_stride; pa.rng_stride = h->rng_stride; pa.iter0 = h->iter_host; pa.count = h->rng_chunk;
             pa.subject_offset = h->subject_offset;
             const long long tot = (long long)h->n * h->rng_chunk;
-            jmb_block_prep_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->cc, pa);
+            const unsigned pg = (unsigned)((tot + 255) / 256);
+            if (mm.d.q == 2) jmb_block_prep_kernel<2><<<pg, 256, 0, h->stream>>>(h->cc, pa);
+            else if (mm.d.q == 4) jmb_block_prep_kernel<4><<<pg, 256, 0, h->stream>>>(h->cc, pa);
+            else if (mm.d.q == 6) jmb_block_prep_kernel<6><<<pg, 256, 0, h->stream>>>(h->cc, pa);
+            else jmb_block_prep_kernel<0><<<pg, 256, 0, h->stream>>>(h->cc, pa);
             h->launches += 1;
             CU(cudaGetLastError());
         }

@@ -294,6 +294,7 @@ struct FinalizeArgs {
     int n_partials;
     int use_reduced;          // multi-GPU: par[pl.sums..] already holds the all-reduced sums
     int phase;                // 0: regular iteration, 1: chain start (Cholesky + first proposal only)
+    int use_smem;             // the parameter block fits the kernel's dynamic shared memory
     // outputs of kept iterations (device buffers laid out like jmb_chain_out)
     double* o_Bs; double* o_g; double* o_a; double* o_phi_g; double* o_phi_a; double* o_tau_Bs;
     double* o_tau_g; double* o_tau_a; double* o_tau_td; double* o_lw; double* trace;
@@ -329,8 +330,16 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     __shared__ double s_z[JMB_MAX_BS + JMB_MAX_GAMMAS + JMB_MAX_ALPHAS + 2];
     __shared__ double s_q[4][JMB_MAX_BS + JMB_MAX_GAMMAS + JMB_MAX_ALPHAS];
     const int tid = threadIdx.x;
-    double* par = a.par;
+    double* gpar = a.par;
     const int B = mm.B, p = mm.d.p, A = mm.d.A;
+    // work on a shared-memory copy of the parameter block (everything before the adaptCov history):
+    // the scalar logic below makes dozens of dependent accesses, each a 600-cycle trip in global memory
+    extern __shared__ double s_par[];
+    double* par = a.use_smem ? s_par : gpar;
+    if (a.use_smem) {
+        for (int j = tid; j < pl.block_par; j += blockDim.x) s_par[j] = gpar[j];
+        __syncthreads();
+    }
 
     if (a.phase == 1) {
         if (tid == 0) {
@@ -341,12 +350,16 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         }
         __syncthreads();
         make_proposal(mm, pl, cc, par, a.ctl->iter, tid, blockDim.x, s_z);
+        if (a.use_smem) {
+            __syncthreads();
+            for (int j = tid; j < pl.block_par; j += blockDim.x) gpar[j] = s_par[j];
+        }
         return;
     }
 
     // ---- deterministic reduction of the per-CTA partials ----
     if (a.use_reduced) {
-        if (tid < 3) s_tot[tid] = par[pl.sums + tid];
+        if (tid < 3) s_tot[tid] = gpar[pl.sums + tid];
     } else {
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
         for (int i = tid; i < a.n_partials; i += 128) { t0 += a.partials[i * 3]; t1 += a.partials[i * 3 + 1]; t2 += a.partials[i * 3 + 2]; }
@@ -410,7 +423,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
             ctl->last_accept = 1;
             raw_Bs = rawp;
         }
-        if (cc.adaptCov) for (int j = 0; j < mm.P; ++j) par[pl.block_par + j + ctl->i * mm.P] = cur[j];
+        if (cc.adaptCov) for (int j = 0; j < mm.P; ++j) gpar[pl.block_par + j + ctl->i * mm.P] = cur[j];
         // ---- Gibbs draws of the precisions (:776-834) ----
         uint32_t draw = 0;
         {
@@ -474,9 +487,9 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
             }
             if (cc.adaptCov && ctl->it > cc.start_cov_update) {
                 // H_* double as scratch here; they are rebuilt right below
-                adapt_cov_dev(par + pl.S_Bs, par + pl.H_Bs, B, par + pl.block_par, mm.P, cc.n_block, g1, cc.eps2, cc.eps3);
-                adapt_cov_dev(par + pl.S_g, par + pl.H_g, p, par + pl.block_par + B, mm.P, cc.n_block, g1, cc.eps2, cc.eps3);
-                adapt_cov_dev(par + pl.S_a, par + pl.H_a, A, par + pl.block_par + B + p, mm.P, cc.n_block, g1, cc.eps2, cc.eps3);
+                adapt_cov_dev(par + pl.S_Bs, par + pl.H_Bs, B, gpar + pl.block_par, mm.P, cc.n_block, g1, cc.eps2, cc.eps3);
+                adapt_cov_dev(par + pl.S_g, par + pl.H_g, p, gpar + pl.block_par + B, mm.P, cc.n_block, g1, cc.eps2, cc.eps3);
+                adapt_cov_dev(par + pl.S_a, par + pl.H_a, A, gpar + pl.block_par + B + p, mm.P, cc.n_block, g1, cc.eps2, cc.eps3);
                 int e = chol_upper_dev(par + pl.S_Bs, B, par + pl.H_Bs);
                 if (p) e |= chol_upper_dev(par + pl.S_g, p, par + pl.H_g);
                 e |= chol_upper_dev(par + pl.S_a, A, par + pl.H_a);
@@ -491,6 +504,10 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     }
     __syncthreads();
     make_proposal(mm, pl, cc, par, s_next_iter, tid, blockDim.x, s_z);
+    if (a.use_smem) {
+        __syncthreads();
+        for (int j = tid; j < pl.block_par; j += blockDim.x) gpar[j] = s_par[j];
+    }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -507,29 +524,33 @@ struct PrepArgs {
     long long subject_offset;
 };
 
+template <int Q>   // Q > 0: q known at compile time (draws stay in registers); Q == 0: runtime q
 __global__ void __launch_bounds__(256)
 jmb_block_prep_kernel(const __grid_constant__ ChainConst cc, const __grid_constant__ PrepArgs a) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)a.n * a.count) return;
+    const int q = Q > 0 ? Q : a.q;
     const int k = (int)(t / a.n), s = (int)(t % a.n);
     const uint32_t gid = (uint32_t)(a.subject_offset + s), iter = (uint32_t)(a.iter0 + k);
-    const double* R = a.Rchol + (long long)s * (a.q * (a.q + 1) / 2);
-    const double sd = sqrt(a.state[(long long)s * a.state_stride + a.q]);
+    const double* R = a.Rchol + (long long)s * (q * (q + 1) / 2);
+    const double sd = sqrt(a.state[(long long)s * a.state_stride + q]);
     double* out = a.rng + ((long long)k * a.n + s) * a.rng_stride;
-    double z[JMB_MAX_Q];
-    for (int sl = 0; sl < (a.q + 1) / 2; ++sl) {
-        double z0, z1;
-        rnorm_pair(cc.seed, cc.chain_id, gid, iter, (uint32_t)sl, ST_B_PROP, z0, z1);
-        z[2 * sl] = z0;
-        if (2 * sl + 1 < JMB_MAX_Q) z[2 * sl + 1] = z1;
+    double z[Q > 0 ? Q + 1 : JMB_MAX_Q];
+#pragma unroll
+    for (int sl = 0; sl < (Q > 0 ? (Q + 1) / 2 : JMB_MAX_Q / 2); ++sl) {
+        if (sl < (q + 1) / 2) rnorm_pair(cc.seed, cc.chain_id, gid, iter, (uint32_t)sl, ST_B_PROP, z[2 * sl], z[2 * sl + 1]);
     }
-    for (int j = 0; j < a.q; ++j) {
-        const double* Rj = R + (j * (j + 1)) / 2;      // column j of the upper factor
-        double pj = 0.0;
-        for (int l = 0; l <= j; ++l) pj += z[l] * Rj[l];
-        out[j] = sd * pj;
+#pragma unroll
+    for (int j = 0; j < (Q > 0 ? Q : JMB_MAX_Q); ++j) {
+        if (j < q) {
+            const double* Rj = R + (j * (j + 1)) / 2;      // column j of the upper factor
+            double pj = 0.0;
+#pragma unroll
+            for (int l = 0; l < (Q > 0 ? Q : JMB_MAX_Q); ++l) if (l <= j) pj += z[l] * Rj[l];
+            out[j] = sd * pj;
+        }
     }
-    out[a.q] = log_unif(cc.seed, cc.chain_id, gid, iter, 0u, ST_B_ACC);
+    out[q] = log_unif(cc.seed, cc.chain_id, gid, iter, 0u, ST_B_ACC);
 }
 
 // per-subject Robbins-Monro update of sigma_b at the end of block `it` (:853-859, bounds_sigma :411-419)

@@ -266,6 +266,24 @@ __device__ __forceinline__ void load_step_regs(StepRegs<Spec>& pr, const double*
     sfor<A>([&](auto j) { pr.alc[j] = s_cur[B + p + j]; pr.alp[j] = s_prop[B + p + j]; });
 }
 
+// cold path of the TMA kernel (records larger than a stage): kept out of line; takes and returns
+// everything by value so that the caller's registers are not forced into local memory
+struct StepSums { double cur, prop, lw; };
+template <class Spec>
+__device__ __noinline__ StepSums subject_step_direct(const double* rec, const double* crec, double* st, const double* rg,
+                                                     const double* s_cur, const double* s_prop, const double* s_invD,
+                                                     const double* par, const int o_sigmas, const int B,
+                                                     const bool last_acc, const int lane, const unsigned gmask) {
+    StepRegs<Spec> pr;
+    constexpr int p = Spec::d.p, A = Spec::d.A, O = Spec::d.O;
+    sfor<O>([&](auto kc) { pr.isig[kc] = 1.0 / par[o_sigmas + kc]; });
+    sfor<p>([&](auto j) { pr.gc[j] = s_cur[B + j]; pr.gp[j] = s_prop[B + j]; });
+    sfor<A>([&](auto j) { pr.alc[j] = s_cur[B + p + j]; pr.alp[j] = s_prop[B + p + j]; });
+    StepSums r{0.0, 0.0, 0.0};
+    subject_step<Spec>(rec, crec, st, rg, st, s_cur, s_prop, s_invD, pr, last_acc, lane, gmask, r.cur, r.prop, r.lw);
+    return r;
+}
+
 // -------------------------------------------------------------------------------------------
 // direct variant: every lane group reads its subject's records straight from global memory
 // -------------------------------------------------------------------------------------------
@@ -425,20 +443,20 @@ jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_c
         const Pending cur = stg ? pd1 : pd0;
         const int s = w_begin + t * SPW + half;
         const int dmid = (half == 1) ? cur.dmid : 0, cmid = (half == 1) ? cur.cmid : 0;
-        const double *rec, *crec, *stin, *rg;
         if (cur.staged) {
             mbar_wait(&bar[stg], stg ? ph1 : ph0);
             if (stg) ph1 ^= 1u; else ph0 ^= 1u;
-            const double* stage = stage0 + (size_t)stg * stage_doubles;
-            rec = stage + dmid; crec = stage + ta.cap_d + cmid; stin = stage + ta.cap_d + ta.cap_c + half * SS;
-            rg = stage + ta.cap_d + ta.cap_c + SPW * SS + half * RS;
-        } else {
-            rec = a.drec + cur.d0 + dmid; crec = a.crec + cur.c0 + cmid; stin = a.state + (long long)s * SS;
-            rg = rng_it + (long long)s * RS;
-        }
-        if (s < w_end) {
-            subject_step<Spec>(rec, crec, stin, rg, a.state + (long long)s * SS, s_cur, s_prop, s_invD, pr,
-                               last_acc, lane, gmask, acc_cur, acc_prop, acc_lw);
+            // addresses derived from the shared-memory window so that the loads compile to LDS
+            const double* stage = smem + head + ((size_t)warp * 2 + stg) * stage_doubles;
+            if (s < w_end)
+                subject_step<Spec>(stage + dmid, stage + ta.cap_d + cmid, stage + ta.cap_d + ta.cap_c + half * SS,
+                                   stage + ta.cap_d + ta.cap_c + SPW * SS + half * RS, a.state + (long long)s * SS,
+                                   s_cur, s_prop, s_invD, pr, last_acc, lane, gmask, acc_cur, acc_prop, acc_lw);
+        } else if (s < w_end) {
+            const StepSums r = subject_step_direct<Spec>(a.drec + cur.d0 + dmid, a.crec + cur.c0 + cmid,
+                                                         a.state + (long long)s * SS, rng_it + (long long)s * RS, s_cur, s_prop,
+                                                         s_invD, a.par, pl.sigmas, B, last_acc, lane, gmask);
+            acc_cur += r.cur; acc_prop += r.prop; acc_lw += r.lw;
         }
         __syncwarp();
         if (more) {
