@@ -31,10 +31,11 @@ def lib():
     global _lib_cache
     if _lib_cache is not None:
         return _lib_cache
-    if not os.path.exists(LIB):
-        raise JmbError(f"{LIB} is missing: build it with __graft_entry__.build() "
+    path = os.environ.get("JMB_LIB", LIB)      # A/B builds of the same library (experiments only)
+    if not os.path.exists(path):
+        raise JmbError(f"{path} is missing: build it with __graft_entry__.build() "
                        "(nvcc, sm_100a); there is no CPU fallback")
-    L = C.CDLL(LIB)
+    L = C.CDLL(path)
     L.jmb_last_error.restype = C.c_char_p
     L.jmb_stream.restype = C.c_void_p
     L.jmb_kernel_name.restype = C.c_char_p
