@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--workload", default="config4_shard", choices=sorted(WORKLOADS))
     ap.add_argument("--n-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chains", type=int, default=4, help="chains in flight for the extra multi_chain measurement (0: skip)")
     return ap.parse_args()
 
 
@@ -248,6 +249,29 @@ def run_cuda(args):
     fit.chain_end(fetch=False)
     k_ms = kms / ksteps
 
+    # ---- several chains of the fit in flight (the reference's parallel axis); reported next to the C = 1 headline ----
+    multi = None
+    if args.chains > 1:
+        fit.chain_slots(args.chains)
+        for k in range(args.chains):
+            fit.select_chain(k)
+            fit.set_draw(Data)
+            fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl, chain_id=k)
+        fit.chains_iterate(args.chains, args.warmup)
+        barrier()
+        msm = fit.chains_iterate(args.chains, args.steps)
+        barrier()
+        for k in range(args.chains):
+            fit.select_chain(k)
+            fit.chain_end(fetch=False)
+        fit.select_chain(0)
+        tm = torch.tensor([msm], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        multi = {"chains": args.chains, "value": args.chains * n_total * args.steps / (float(tm.item()) * 1e-3), "unit": UNIT,
+                 "ms_per_step_all_chains": float(tm.item()) / args.steps,
+                 "what": "independent chains (draws) of the same fit advanced together on their own streams"}
+
     # ---- end to end through the public API with host buffers: set_draw (H2D of the per-draw
     #      records), chain_begin (H2D of b/scales/params), K iterations, chain_end (D2H of outputs) ----
     ctl_e = dict(c["control"])
@@ -295,6 +319,8 @@ def run_cuda(args):
         "gpu_launches": int(l1 - l0),
         "clocks": clocks,
     }
+    if multi:
+        line["multi_chain"] = multi
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         oracle.build()

@@ -240,6 +240,15 @@ int jmb_chain_begin(jmb_handle h, const jmb_priors* priors, const jmb_control* c
 int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, float* step_kernel_ms);
 int jmb_chain_end(jmb_handle h, jmb_chain_out* out);
 int jmb_launch_count(jmb_handle h, int64_t* launches);
+
+/* Several chains (mvglmer draws) of one fit in flight on one device - the reference's chain
+ * parallelism (foreach over blocks of draws, R/mvJointModelBayes.R:860-905).  jmb_chain_slots makes
+ * `count` chain slots (slot 0 always exists); jmb_select_chain chooses the slot that jmb_set_draw,
+ * jmb_chain_begin, jmb_chain_iterate, jmb_chain_end and jmb_lap_rwm act on; jmb_chains_iterate
+ * advances slots 0..nslots-1 together, round-robin on their own streams. */
+int jmb_chain_slots(jmb_handle h, int count);
+int jmb_select_chain(jmb_handle h, int slot);
+int jmb_chains_iterate(jmb_handle h, int nslots, int iters, float* elapsed_ms);
 /* "static:<shape>" when a compile-time-specialised step kernel serves this model, else "generic" */
 const char* jmb_kernel_name(jmb_handle h);
 void* jmb_stream(jmb_handle h);

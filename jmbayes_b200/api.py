@@ -54,6 +54,9 @@ def lib():
     L.jmb_eval_logpost_re.argtypes = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p,
                                       _abi.c_double_p, C.POINTER(_abi.JmbEvalOut)]
     L.jmb_get_row_ptr.argtypes = [vp, C.c_int, _abi.c_int64_p]
+    L.jmb_chain_slots.argtypes = [vp, C.c_int]
+    L.jmb_select_chain.argtypes = [vp, C.c_int]
+    L.jmb_chains_iterate.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.jmb_set_wlong.argtypes = [vp, _abi.c_double_p, _abi.c_double_p]
     post = [vp, C.c_double, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p, C.POINTER(_abi.JmbPriors),
             C.c_double, C.c_double, C.c_double, _abi.c_double_p]
@@ -157,7 +160,7 @@ class Fit:
     # -- stepwise driver (benchmark / tests) ----------------------------------------------------------
     def chain_begin(self, initials, priors, scales, Covs, control, chain_id: int = 0):
         pr, ct, ci, keep = self._marshal_chain(initials, priors, scales, Covs, control, chain_id)
-        self._chain_meta = (pr.n_td,) + _abi.chain_dims(control)
+        self._chain_meta = (pr.n_td,) + _abi.chain_dims(control)   # same control for every slot of a fit
         _check(lib().jmb_chain_begin(self._h, C.byref(pr), C.byref(ct), C.byref(ci)))
         del keep
 
@@ -167,6 +170,20 @@ class Fit:
         _check(lib().jmb_chain_iterate(self._h, int(iters), C.byref(ms),
                                        C.byref(kms) if time_kernels else None))
         return ms.value, (kms.value if time_kernels else None)
+
+    # -- several chains (draws) of the fit in flight (R/mvJointModelBayes.R:860-905) ---------------------
+    def chain_slots(self, count: int):
+        _check(lib().jmb_chain_slots(self._h, int(count)))
+
+    def select_chain(self, slot: int):
+        """Slot that set_draw / chain_begin / chain_iterate / chain_end / lap_rwm_C act on."""
+        _check(lib().jmb_select_chain(self._h, int(slot)))
+
+    def chains_iterate(self, nslots: int, iters: int) -> float:
+        """Advance slots 0..nslots-1 together by ``iters`` iterations; returns the device ms."""
+        ms = C.c_float(0)
+        _check(lib().jmb_chains_iterate(self._h, int(nslots), int(iters), C.byref(ms)))
+        return ms.value
 
     def chain_end(self, fetch: bool = True):
         if not fetch:

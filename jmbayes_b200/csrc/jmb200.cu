@@ -72,44 +72,52 @@ static int load_nccl() {
 // ---------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------
+// everything that belongs to one chain (one mvglmer draw): several chains of the same fit can be in
+// flight on their own streams, sharing the design records
+struct ChainCtx {
+    cudaStream_t stream = nullptr;
+    ChainConst cc{};
+    double* d_crec = nullptr;                       // per-draw records
+    double* d_state = nullptr; double* d_par = nullptr; Ctl* d_ctl = nullptr;
+    double* d_partials = nullptr; double* d_tmp = nullptr;  // d_tmp: n*(q+1)
+    double* d_rng = nullptr;                        // [rng_chunk][n][rng_stride] draws of the b-step
+    size_t rng_capacity = 0; int rng_chunk = 1;
+    double* h_crec = nullptr;                       // pinned staging for the per-draw records
+    double* h_par = nullptr;                        // pinned staging for the parameter block
+    double* h_tmp = nullptr;                        // pinned staging n*(q+1)
+    bool draw_set = false, chain_open = false, fin_attr_set = false;
+    int iter_host = 0, total_iters = 0, keep_host = 0, check_host = 0, n_out = 0, n_td = 0;
+    double *o_b = nullptr, *o_par = nullptr, *o_trace = nullptr;   // device outputs
+    FinalizeArgs fa{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+};
+
 struct jmb_handle_s {
     int device = 0;
-    cudaStream_t stream = nullptr;
     ModelMeta mm{};
     ParamLayout pl{};
-    ChainConst cc{};
     int n = 0;
     long long subject_offset = 0;
     int n_block_cap = 1024;
     std::vector<long long> N;                       // rows per outcome
     std::vector<std::vector<int>> rowptr;           // host CSR per outcome
     std::vector<long long> doff, coff;              // host offsets
-    // device
-    double* d_drec = nullptr; long long* d_doff = nullptr;
-    double* d_crec = nullptr; long long* d_coff = nullptr;
+    // device data shared by all chains
+    double* d_drec = nullptr; long long* d_doff = nullptr; long long* d_coff = nullptr;
     int* d_rowptr = nullptr;
-    double* d_state = nullptr; double* d_par = nullptr; Ctl* d_ctl = nullptr;
-    double* d_partials = nullptr; double* d_eval = nullptr; double* d_tmp = nullptr;  // d_tmp: n*(q+1)
+    double* d_eval = nullptr;
     double* d_Rchol = nullptr;                      // [n][q(q+1)/2] proposal factors (Covs$b)
-    double* d_rng = nullptr;                        // [rng_chunk][n][rng_stride] draws of the b-step
-    size_t rng_capacity = 0; int rng_chunk = 1, rng_stride = 2;
-    double* h_crec = nullptr;                       // pinned staging for the per-draw records
-    double* h_par = nullptr;                        // pinned staging for the parameter block
-    double* h_tmp = nullptr;                        // pinned staging n*(q+1)
-    bool draw_set = false;
-    // chain
-    bool chain_open = false;
-    int iter_host = 0, total_iters = 0, keep_host = 0, check_host = 0, n_out = 0, n_td = 0;
-    double *o_b = nullptr, *o_par = nullptr, *o_trace = nullptr;   // device outputs
-    FinalizeArgs fa{};
-    bool want_trace = false;
+    int rng_stride = 2;
+    // chains
+    std::vector<ChainCtx*> slots;
+    ChainCtx* c = nullptr;                          // current slot
+    int grid_cap = 0;                               // partials per chain
     // survival-block Laplace step (logPosterior / gradient_logPosterior)
     double *d_Wlong = nullptr, *d_Wlongs = nullptr, *d_sp_partials = nullptr, *d_sp_out = nullptr, *d_theta = nullptr;
     std::vector<double> ecs;                        // event_colSums of [W1 | W2 | Wlong]
     std::vector<double> h_event;                    // host copy of Data$event
     std::vector<double> sp_last_theta, sp_last_out; // cache: optim() asks for fn and gr at the same point
     bool wlong_set = false;
-    bool fin_attr_set = false;
     // launch configuration
     int grid = 0, subjects_per_cta = 0, smem_bytes = 0;
     long long launches = 0;
@@ -122,9 +130,9 @@ struct jmb_handle_s {
     TmaArgs ta{};
     int kernel_mode = 0;            // 0 generic, 1 static direct, 2 static TMA-staged
     int select_kernel();
+    int add_slot();
     // multi-GPU
     ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
 };
 
 int jmb_handle_s::select_kernel() {
@@ -445,18 +453,11 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     cudaError_t e;
 #define CUH(call) do { e = (call); if (e != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e); jmb_destroy(h); return fail(m_); } } while (0)
     CUH(cudaSetDevice(device));
-    CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUH(cudaMalloc(&h->d_drec, sizeof(double) * std::max<size_t>(drec.size(), 2)));
     CUH(cudaMalloc(&h->d_doff, sizeof(long long) * (n + 1)));
-    CUH(cudaMalloc(&h->d_crec, sizeof(double) * std::max<long long>(h->coff[n], 2)));
     CUH(cudaMalloc(&h->d_coff, sizeof(long long) * (n + 1)));
     CUH(cudaMalloc(&h->d_rowptr, sizeof(int) * (size_t)O * (n + 1)));
-    CUH(cudaMalloc(&h->d_state, sizeof(double) * (size_t)n * mm.L.state_stride));
     CUH(cudaMalloc(&h->d_eval, sizeof(double) * (size_t)n * 6));
-    CUH(cudaMalloc(&h->d_tmp, sizeof(double) * (size_t)n * (q + 1)));
-    CUH(cudaMalloc(&h->d_ctl, sizeof(Ctl)));
-    CUH(cudaHostAlloc(&h->h_crec, sizeof(double) * std::max<long long>(h->coff[n], 2), cudaHostAllocDefault));
-    CUH(cudaHostAlloc(&h->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaHostAllocDefault));
     CUH(cudaMemcpy(h->d_drec, drec.data(), sizeof(double) * drec.size(), cudaMemcpyHostToDevice));
     CUH(cudaMalloc(&h->d_Rchol, sizeof(double) * rchol.size()));
     CUH(cudaMemcpy(h->d_Rchol, rchol.data(), sizeof(double) * rchol.size(), cudaMemcpyHostToDevice));
@@ -464,15 +465,9 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     CUH(cudaMemcpy(h->d_coff, h->coff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
     for (int k = 0; k < O; ++k)
         CUH(cudaMemcpy(h->d_rowptr + (size_t)k * (n + 1), h->rowptr[k].data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
-    CUH(cudaMemset(h->d_state, 0, sizeof(double) * (size_t)n * mm.L.state_stride));
-    CUH(cudaMemset(h->d_ctl, 0, sizeof(Ctl)));
 
     // parameter block (n_td capacity = JMB_MAX_TERMS)
     build_param_layout(mm, JMB_MAX_TERMS, h->n_block_cap, h->pl);
-    CUH(cudaMalloc(&h->d_par, sizeof(double) * h->pl.total));
-    CUH(cudaMemset(h->d_par, 0, sizeof(double) * h->pl.total));
-    CUH(cudaHostAlloc(&h->h_par, sizeof(double) * h->pl.total, cudaHostAllocDefault));
-    memset(h->h_par, 0, sizeof(double) * h->pl.total);
 
     // launch configuration: G lanes per subject, 256 threads, a few subjects per group per CTA
     const int groups = 256 / md.G;
@@ -485,32 +480,74 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
         h->num_sms = prop.multiProcessorCount;
         if (h->select_kernel()) { std::string m_ = g_err; jmb_destroy(h); return fail(m_); }
     }
-    CUH(cudaMalloc(&h->d_partials, sizeof(double) * 3 * (size_t)std::max(h->grid, h->tma_grid)));
-    CUH(cudaEventCreate(&h->ev0)); CUH(cudaEventCreate(&h->ev1));
-    CUH(cudaEventCreate(&h->evk0)); CUH(cudaEventCreate(&h->evk1));
+    h->grid_cap = std::max(h->grid, h->tma_grid);
+    if (h->add_slot()) { std::string m_ = g_err; jmb_destroy(h); return fail(m_); }   // chain slot 0
 #undef CUH
     *out = h;
+    return 0;
+}
+
+// one more chain slot (own stream, per-draw records, state, parameter block, staging)
+int jmb_handle_s::add_slot() {
+    ChainCtx* x = new ChainCtx();
+    slots.push_back(x);
+    if (!c) c = x;
+    const size_t crec_len = (size_t)std::max<long long>(coff[n], 2);
+    const int q = mm.d.q;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&x->d_crec, sizeof(double) * crec_len));
+    CU(cudaMalloc(&x->d_state, sizeof(double) * (size_t)n * mm.L.state_stride));
+    CU(cudaMalloc(&x->d_tmp, sizeof(double) * (size_t)n * (q + 1)));
+    CU(cudaMalloc(&x->d_ctl, sizeof(Ctl)));
+    CU(cudaMalloc(&x->d_par, sizeof(double) * pl.total));
+    CU(cudaMalloc(&x->d_partials, sizeof(double) * 3 * (size_t)grid_cap));
+    CU(cudaHostAlloc(&x->h_crec, sizeof(double) * crec_len, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&x->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&x->h_par, sizeof(double) * pl.total, cudaHostAllocDefault));
+    memset(x->h_par, 0, sizeof(double) * pl.total);
+    CU(cudaMemset(x->d_state, 0, sizeof(double) * (size_t)n * mm.L.state_stride));
+    CU(cudaMemset(x->d_ctl, 0, sizeof(Ctl)));
+    CU(cudaMemset(x->d_par, 0, sizeof(double) * pl.total));
+    CU(cudaEventCreate(&x->ev0)); CU(cudaEventCreate(&x->ev1));
+    CU(cudaEventCreate(&x->evk0)); CU(cudaEventCreate(&x->evk1));
+    return 0;
+}
+
+extern "C" int jmb_chain_slots(jmb_handle h, int count) {
+    if (!h || count < 1 || count > 64) return fail("jmb_chain_slots: bad argument");
+    while ((int)h->slots.size() < count)
+        if (h->add_slot()) return 1;
+    return 0;
+}
+
+extern "C" int jmb_select_chain(jmb_handle h, int slot) {
+    if (!h || slot < 0 || slot >= (int)h->slots.size()) return fail("jmb_select_chain: no such chain slot (call jmb_chain_slots)");
+    h->c = h->slots[slot];
     return 0;
 }
 
 extern "C" int jmb_destroy(jmb_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (ChainCtx* x : h->slots) if (x->stream) cudaStreamSynchronize(x->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    cudaFree(h->d_drec); cudaFree(h->d_doff); cudaFree(h->d_crec); cudaFree(h->d_coff); cudaFree(h->d_rowptr);
-    cudaFree(h->d_state); cudaFree(h->d_par); cudaFree(h->d_ctl); cudaFree(h->d_partials); cudaFree(h->d_eval);
-    cudaFree(h->d_tmp); cudaFree(h->o_b); cudaFree(h->o_par); cudaFree(h->o_trace);
-    cudaFree(h->d_Rchol); cudaFree(h->d_rng);
+    cudaFree(h->d_drec); cudaFree(h->d_doff); cudaFree(h->d_coff); cudaFree(h->d_rowptr); cudaFree(h->d_eval);
+    cudaFree(h->d_Rchol);
     cudaFree(h->d_Wlong); cudaFree(h->d_Wlongs); cudaFree(h->d_sp_partials); cudaFree(h->d_sp_out); cudaFree(h->d_theta);
-    if (h->h_crec) cudaFreeHost(h->h_crec);
-    if (h->h_par) cudaFreeHost(h->h_par);
-    if (h->h_tmp) cudaFreeHost(h->h_tmp);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->evk0) cudaEventDestroy(h->evk0);
-    if (h->evk1) cudaEventDestroy(h->evk1);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    for (ChainCtx* x : h->slots) {
+        cudaFree(x->d_crec); cudaFree(x->d_state); cudaFree(x->d_par); cudaFree(x->d_ctl); cudaFree(x->d_partials);
+        cudaFree(x->d_tmp); cudaFree(x->o_b); cudaFree(x->o_par); cudaFree(x->o_trace); cudaFree(x->d_rng);
+        if (x->h_crec) cudaFreeHost(x->h_crec);
+        if (x->h_par) cudaFreeHost(x->h_par);
+        if (x->h_tmp) cudaFreeHost(x->h_tmp);
+        if (x->ev0) cudaEventDestroy(x->ev0);
+        if (x->ev1) cudaEventDestroy(x->ev1);
+        if (x->evk0) cudaEventDestroy(x->evk0);
+        if (x->evk1) cudaEventDestroy(x->evk1);
+        if (x->stream) cudaStreamDestroy(x->stream);
+        delete x;
+    }
     delete h;
     return 0;
 }
@@ -521,11 +558,11 @@ extern "C" int jmb_destroy(jmb_handle h) {
 extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
     if (!h || !w) return fail("jmb_set_draw: null argument");
     CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->stream));        // the staging buffer may still be in flight
+    CU(cudaStreamSynchronize(h->c->stream));        // the staging buffer may still be in flight
     const ModelMeta& mm = h->mm;
     const int n = h->n, K = mm.d.K, RP = mm.L.RP, S = mm.d.S, T = mm.d.T, O = mm.d.O;
     if (S == 2 && !w->XXsbetas_int) return fail("jmb_set_draw: XXsbetas_int required with interval censoring");
-    double* base = h->h_crec;
+    double* base = h->c->h_crec;
     parallel_for(n, [&](int lo, int hi) {
         for (int i = lo; i < hi; ++i) {
             double* rec = base + h->coff[i];
@@ -544,11 +581,11 @@ extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
             }
         }
     });
-    CU(cudaMemcpyAsync(h->d_crec, h->h_crec, sizeof(double) * h->coff[n], cudaMemcpyHostToDevice, h->stream));
-    for (int j = 0; j < mm.d.q * mm.d.q; ++j) h->h_par[h->pl.invD + j] = w->invD[j];
-    for (int k = 0; k < O; ++k) h->h_par[h->pl.sigmas + k] = (mm.d.fam[k] == JMB_FAM_GAUSSIAN) ? w->sigmas[k] : 1.0;
-    CU(cudaMemcpyAsync(h->d_par + h->pl.invD, h->h_par + h->pl.invD, sizeof(double) * (mm.d.q * mm.d.q + O), cudaMemcpyHostToDevice, h->stream));
-    h->draw_set = true;
+    CU(cudaMemcpyAsync(h->c->d_crec, h->c->h_crec, sizeof(double) * h->coff[n], cudaMemcpyHostToDevice, h->c->stream));
+    for (int j = 0; j < mm.d.q * mm.d.q; ++j) h->c->h_par[h->pl.invD + j] = w->invD[j];
+    for (int k = 0; k < O; ++k) h->c->h_par[h->pl.sigmas + k] = (mm.d.fam[k] == JMB_FAM_GAUSSIAN) ? w->sigmas[k] : 1.0;
+    CU(cudaMemcpyAsync(h->c->d_par + h->pl.invD, h->c->h_par + h->pl.invD, sizeof(double) * (mm.d.q * mm.d.q + O), cudaMemcpyHostToDevice, h->c->stream));
+    h->c->draw_set = true;
     return 0;
 }
 
@@ -557,42 +594,42 @@ extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
 // ---------------------------------------------------------------------------------------------
 static int launch_step(jmb_handle h, int mode) {
     StepArgs a{};
-    a.drec = h->d_drec; a.doff = h->d_doff; a.crec = h->d_crec; a.coff = h->d_coff; a.rowptr = h->d_rowptr;
-    a.state = h->d_state; a.par = h->d_par; a.ctl = h->d_ctl; a.partials = h->d_partials; a.eval_out = h->d_eval;
+    a.drec = h->d_drec; a.doff = h->d_doff; a.crec = h->c->d_crec; a.coff = h->d_coff; a.rowptr = h->d_rowptr;
+    a.state = h->c->d_state; a.par = h->c->d_par; a.ctl = h->c->d_ctl; a.partials = h->c->d_partials; a.eval_out = h->d_eval;
     a.n = h->n; a.subject_offset = h->subject_offset; a.mode = mode; a.subjects_per_cta = h->subjects_per_cta;
-    a.rng = h->d_rng; a.rng_chunk = h->rng_chunk; a.rng_stride = h->rng_stride;
+    a.rng = h->c->d_rng; a.rng_chunk = h->c->rng_chunk; a.rng_stride = h->rng_stride;
     if (mode == MODE_STEP && h->kernel_mode == 2)
-        h->tma_kernel<<<h->tma_grid, 256, h->tma_smem, h->stream>>>(h->mm.B, h->pl, h->cc, a, h->ta);
+        h->tma_kernel<<<h->tma_grid, 256, h->tma_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a, h->ta);
     else if (mode == MODE_STEP && h->kernel_mode == 1)
-        h->static_kernel<<<h->grid, 256, h->static_smem, h->stream>>>(h->mm.B, h->pl, h->cc, a);
+        h->static_kernel<<<h->grid, 256, h->static_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a);
     else if (h->mm.d.G == 16)
-        jmb_step_kernel<16><<<h->grid, 256, h->smem_bytes, h->stream>>>(h->mm, h->pl, h->cc, a);
+        jmb_step_kernel<16><<<h->grid, 256, h->smem_bytes, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
     else
-        jmb_step_kernel<32><<<h->grid, 256, h->smem_bytes, h->stream>>>(h->mm, h->pl, h->cc, a);
+        jmb_step_kernel<32><<<h->grid, 256, h->smem_bytes, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
     h->launches += 1;
     CU(cudaGetLastError());
     return 0;
 }
 
 static int launch_finalize(jmb_handle h, int phase) {
-    FinalizeArgs a = h->fa;
-    a.par = h->d_par; a.ctl = h->d_ctl; a.partials = h->d_partials; a.n_partials = h->grid;
+    FinalizeArgs a = h->c->fa;
+    a.par = h->c->d_par; a.ctl = h->c->d_ctl; a.partials = h->c->d_partials; a.n_partials = h->grid;
     a.use_reduced = (h->nranks > 1) ? 1 : 0; a.phase = phase;
     a.n_partials = (h->kernel_mode == 2) ? h->tma_grid : h->grid;
     if (phase == 0 && h->nranks > 1) {
-        jmb_reduce_partials_kernel<<<1, 128, 0, h->stream>>>(h->d_partials, a.n_partials, h->d_par + h->pl.sums);
+        jmb_reduce_partials_kernel<<<1, 128, 0, h->c->stream>>>(h->c->d_partials, a.n_partials, h->c->d_par + h->pl.sums);
         h->launches += 1;
         CU(cudaGetLastError());
-        ncclResult_t rc = g_nccl.AllReduce(h->d_par + h->pl.sums, h->d_par + h->pl.sums, 3, ncclDouble, ncclSum, h->comm, h->stream);
+        ncclResult_t rc = g_nccl.AllReduce(h->c->d_par + h->pl.sums, h->c->d_par + h->pl.sums, 3, ncclDouble, ncclSum, h->comm, h->c->stream);
         if (rc != ncclSuccess) return fail(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
     }
     const size_t fin_smem = sizeof(double) * (size_t)h->pl.block_par;
     a.use_smem = (fin_smem <= 200 * 1024) ? 1 : 0;
-    if (a.use_smem && fin_smem > 48 * 1024 && !h->fin_attr_set) {
+    if (a.use_smem && fin_smem > 48 * 1024 && !h->c->fin_attr_set) {
         CU(cudaFuncSetAttribute((const void*)jmb_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-        h->fin_attr_set = true;
+        h->c->fin_attr_set = true;
     }
-    jmb_finalize_kernel<<<1, 128, a.use_smem ? fin_smem : 0, h->stream>>>(h->mm, h->pl, h->cc, a);
+    jmb_finalize_kernel<<<1, 128, a.use_smem ? fin_smem : 0, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
     h->launches += 1;
     CU(cudaGetLastError());
     return 0;
@@ -603,7 +640,7 @@ static int launch_finalize(jmb_handle h, int phase) {
 // ---------------------------------------------------------------------------------------------
 extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_control* ct, const jmb_chain_in* in) {
     if (!h || !pr || !ct || !in) return fail("jmb_chain_begin: null argument");
-    if (!h->draw_set) return fail("jmb_chain_begin: call jmb_set_draw first");
+    if (!h->c->draw_set) return fail("jmb_chain_begin: call jmb_set_draw first");
     CU(cudaSetDevice(h->device));
     const ModelMeta& mm = h->mm;
     const ParamLayout& pl = h->pl;
@@ -611,7 +648,7 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     if (ct->n_block <= 0 || ct->n_block > h->n_block_cap) return fail("jmb_chain_begin: n_block out of range (1..1024)");
     if (ct->n_iter < 0 || ct->n_burnin < 0 || ct->n_thin <= 0) return fail("jmb_chain_begin: bad control");
     if (pr->n_td < 0 || pr->n_td > JMB_MAX_TERMS) return fail("jmb_chain_begin: too many td effects");
-    ChainConst& cc = h->cc;
+    ChainConst& cc = h->c->cc;
     memset(&cc, 0, sizeof(cc));
     cc.n_iter = ct->n_iter; cc.n_burnin = ct->n_burnin; cc.n_block = ct->n_block; cc.n_thin = ct->n_thin;
     const int total_it = ct->n_iter + ct->n_burnin;
@@ -639,20 +676,20 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
         if (cc.td_len[k] > JMB_MAX_UT) return fail("jmb_chain_begin: td block too wide");
         for (int j = 0; j < cc.td_len[k]; ++j) cc.td_cols[k][j] = pr->td_cols[k][j];
     }
-    h->n_out = cc.n_out; h->n_td = pr->n_td;
-    h->total_iters = its * ct->n_block;
+    h->c->n_out = cc.n_out; h->c->n_td = pr->n_td;
+    h->c->total_iters = its * ct->n_block;
     {   // the reference stores a sample whenever iter == keep[k] (src/fast_LAPRWM.cpp:836-850); when that
         // happens more than n_out times it indexes past its output arrays and fails ("index out of bounds")
         int hits = 0;
-        for (int v = ct->n_burnin + 1; v <= total_it && v <= h->total_iters - 1; v += ct->n_thin) ++hits;
+        for (int v = ct->n_burnin + 1; v <= total_it && v <= h->c->total_iters - 1; v += ct->n_thin) ++hits;
         if (hits > cc.n_out)
             return fail("jmb_chain_begin: control would store more than floor(n_iter / n_thin) samples "
                         "(the reference fails with 'index out of bounds' for this n_iter / n_thin / n_block)");
     }
-    h->iter_host = 0; h->keep_host = 0; h->check_host = 0;
+    h->c->iter_host = 0; h->c->keep_host = 0; h->c->check_host = 0;
 
-    CU(cudaStreamSynchronize(h->stream));
-    double* hp = h->h_par;
+    CU(cudaStreamSynchronize(h->c->stream));
+    double* hp = h->c->h_par;
     memcpy(hp + pl.cur, in->Bs_gammas, sizeof(double) * B);
     if (p) memcpy(hp + pl.cur + B, in->gammas, sizeof(double) * p);
     memcpy(hp + pl.cur + B + p, in->alphas, sizeof(double) * A);
@@ -673,23 +710,23 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     memcpy(hp + pl.Tau_Bs, pr->Tau_Bs_gammas, sizeof(double) * B * B);
     if (p) memcpy(hp + pl.mean_g, pr->mean_gammas, sizeof(double) * p);
     memcpy(hp + pl.mean_a, pr->mean_alphas, sizeof(double) * A);
-    CU(cudaMemcpyAsync(h->d_par, hp, sizeof(double) * pl.block_par, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(h->d_ctl, 0, sizeof(Ctl), h->stream));
+    CU(cudaMemcpyAsync(h->c->d_par, hp, sizeof(double) * pl.block_par, cudaMemcpyHostToDevice, h->c->stream));
+    CU(cudaMemsetAsync(h->c->d_ctl, 0, sizeof(Ctl), h->c->stream));
 
     // outputs on the device
-    cudaFree(h->o_b); cudaFree(h->o_par); cudaFree(h->o_trace);
-    h->o_b = h->o_par = h->o_trace = nullptr;
+    cudaFree(h->c->o_b); cudaFree(h->c->o_par); cudaFree(h->c->o_trace);
+    h->c->o_b = h->c->o_par = h->c->o_trace = nullptr;
     const int no = std::max(cc.n_out, 1);
     const size_t par_out = (size_t)no * (B + 2 * p + 2 * A + 4 + JMB_MAX_TERMS);
-    CU(cudaMalloc(&h->o_b, sizeof(double) * (size_t)n * q * no));
-    CU(cudaMalloc(&h->o_par, sizeof(double) * par_out));
-    CU(cudaMemsetAsync(h->o_b, 0, sizeof(double) * (size_t)n * q * no, h->stream));
-    CU(cudaMemsetAsync(h->o_par, 0, sizeof(double) * par_out, h->stream));
-    CU(cudaMalloc(&h->o_trace, sizeof(double) * 2 * (size_t)std::max(h->total_iters, 1)));
-    CU(cudaMemsetAsync(h->o_trace, 0, sizeof(double) * 2 * (size_t)std::max(h->total_iters, 1), h->stream));
-    FinalizeArgs& fa = h->fa;
+    CU(cudaMalloc(&h->c->o_b, sizeof(double) * (size_t)n * q * no));
+    CU(cudaMalloc(&h->c->o_par, sizeof(double) * par_out));
+    CU(cudaMemsetAsync(h->c->o_b, 0, sizeof(double) * (size_t)n * q * no, h->c->stream));
+    CU(cudaMemsetAsync(h->c->o_par, 0, sizeof(double) * par_out, h->c->stream));
+    CU(cudaMalloc(&h->c->o_trace, sizeof(double) * 2 * (size_t)std::max(h->c->total_iters, 1)));
+    CU(cudaMemsetAsync(h->c->o_trace, 0, sizeof(double) * 2 * (size_t)std::max(h->c->total_iters, 1), h->c->stream));
+    FinalizeArgs& fa = h->c->fa;
     memset(&fa, 0, sizeof(fa));
-    double* o = h->o_par;
+    double* o = h->c->o_par;
     fa.o_Bs = o; o += (size_t)no * B;
     fa.o_g = o; o += (size_t)no * p;
     fa.o_a = o; o += (size_t)no * A;
@@ -698,15 +735,15 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     fa.o_tau_Bs = o; o += no; fa.o_tau_g = o; o += no; fa.o_tau_a = o; o += no;
     fa.o_tau_td = o; o += (size_t)no * JMB_MAX_TERMS;
     fa.o_lw = o;
-    fa.trace = h->o_trace;
+    fa.trace = h->c->o_trace;
 
     // state <- initials$b, scales$b
-    memcpy(h->h_tmp, in->b, sizeof(double) * (size_t)n * q);
-    memcpy(h->h_tmp + (size_t)n * q, in->sigma_b, sizeof(double) * n);
-    CU(cudaMemcpyAsync(h->d_tmp, h->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaMemcpyHostToDevice, h->stream));
+    memcpy(h->c->h_tmp, in->b, sizeof(double) * (size_t)n * q);
+    memcpy(h->c->h_tmp + (size_t)n * q, in->sigma_b, sizeof(double) * n);
+    CU(cudaMemcpyAsync(h->c->d_tmp, h->c->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaMemcpyHostToDevice, h->c->stream));
     {
         const long long tot = (long long)n * mm.L.state_stride;
-        jmb_load_state_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.L.state_stride, n, q, h->d_tmp, h->d_tmp + (size_t)n * q);
+        jmb_load_state_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->c->stream>>>(h->c->d_state, mm.L.state_stride, n, q, h->c->d_tmp, h->c->d_tmp + (size_t)n * q);
         h->launches += 1;
         CU(cudaGetLastError());
     }
@@ -714,99 +751,140 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         const size_t per_iter = (size_t)n * h->rng_stride * sizeof(double);
-        const size_t budget = std::max<size_t>(per_iter, std::min<size_t>(free_b / 4 + h->rng_capacity, (size_t)8 << 30));
+        const size_t budget = std::max<size_t>(per_iter, std::min<size_t>(free_b / 4 + h->c->rng_capacity, (size_t)8 << 30));
         int chunk = ct->n_block;
         while (chunk > 1 && ((size_t)chunk * per_iter > budget || ct->n_block % chunk != 0)) --chunk;
-        h->rng_chunk = chunk;
-        if ((size_t)chunk * per_iter > h->rng_capacity) {
-            cudaFree(h->d_rng); h->d_rng = nullptr;
-            CU(cudaMalloc(&h->d_rng, (size_t)chunk * per_iter));
-            h->rng_capacity = (size_t)chunk * per_iter;
+        h->c->rng_chunk = chunk;
+        if ((size_t)chunk * per_iter > h->c->rng_capacity) {
+            cudaFree(h->c->d_rng); h->c->d_rng = nullptr;
+            CU(cudaMalloc(&h->c->d_rng, (size_t)chunk * per_iter));
+            h->c->rng_capacity = (size_t)chunk * per_iter;
         }
     }
     if (launch_finalize(h, 1)) return 1;            // Cholesky factors + proposal of iteration 0
     if (launch_step(h, MODE_INIT)) return 1;        // log_pyb / log_pb at the initial b (:619-621)
-    h->chain_open = true;
+    h->c->chain_open = true;
     return 0;
 }
 
 static bool is_keep_iter(const jmb_handle h, int iter) {
-    const ChainConst& cc = h->cc;
-    return h->check_host < cc.n_keep && h->keep_host < cc.n_out && iter == cc.n_burnin + 1 + h->check_host * cc.n_thin;
+    const ChainConst& cc = h->c->cc;
+    return h->c->check_host < cc.n_keep && h->c->keep_host < cc.n_out && iter == cc.n_burnin + 1 + h->c->check_host * cc.n_thin;
+}
+
+// enqueue one iteration of the current chain slot on its stream
+static int enqueue_iteration(jmb_handle h, float* kernel_ms) {
+    const ModelMeta& mm = h->mm;
+    const int i_blk = h->c->iter_host % h->c->cc.n_block;
+    if (i_blk % h->c->rng_chunk == 0) {            // draws for the next rng_chunk iterations (:658)
+        PrepArgs pa{};
+        pa.Rchol = h->d_Rchol; pa.state = h->c->d_state; pa.rng = h->c->d_rng; pa.n = h->n; pa.q = mm.d.q;
+        pa.state_stride = mm.L.state_stride; pa.rng_stride = h->rng_stride; pa.iter0 = h->c->iter_host; pa.count = h->c->rng_chunk;
+        pa.subject_offset = h->subject_offset;
+        const long long tot = (long long)h->n * h->c->rng_chunk;
+        const unsigned pg = (unsigned)((tot + 255) / 256);
+        if (mm.d.q == 2) jmb_block_prep_kernel<2><<<pg, 256, 0, h->c->stream>>>(h->c->cc, pa);
+        else if (mm.d.q == 4) jmb_block_prep_kernel<4><<<pg, 256, 0, h->c->stream>>>(h->c->cc, pa);
+        else if (mm.d.q == 6) jmb_block_prep_kernel<6><<<pg, 256, 0, h->c->stream>>>(h->c->cc, pa);
+        else jmb_block_prep_kernel<0><<<pg, 256, 0, h->c->stream>>>(h->c->cc, pa);
+        h->launches += 1;
+        CU(cudaGetLastError());
+    }
+    if (kernel_ms) CU(cudaEventRecord(h->c->evk0, h->c->stream));
+    if (launch_step(h, MODE_STEP)) return 1;
+    if (kernel_ms) {
+        CU(cudaEventRecord(h->c->evk1, h->c->stream));
+        CU(cudaEventSynchronize(h->c->evk1));
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, h->c->evk0, h->c->evk1));
+        *kernel_ms += t;
+    }
+    if (launch_finalize(h, 0)) return 1;
+    if (i_blk == h->c->cc.n_block - 1) {           // block end: per-subject scale adaptation (:853-859)
+        jmb_adapt_sigma_kernel<<<(h->n + 255) / 256, 256, 0, h->c->stream>>>(h->c->cc, h->c->d_state, h->n, mm.d.q, mm.L.state_stride, h->c->d_ctl);
+        h->launches += 1;
+        CU(cudaGetLastError());
+    }
+    if (is_keep_iter(h, h->c->iter_host)) {
+        const long long tot = (long long)h->n * mm.d.q;
+        jmb_extract_b_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->c->stream>>>(
+            h->c->d_state, mm.L.state_stride, h->n, mm.d.q, 0, h->c->o_b + (size_t)h->c->keep_host * h->n * mm.d.q);
+        h->launches += 1;
+        CU(cudaGetLastError());
+        h->c->keep_host += 1; h->c->check_host += 1;
+    }
+    h->c->iter_host += 1;
+    return 0;
 }
 
 extern "C" int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, float* step_kernel_ms) {
-    if (!h || !h->chain_open) return fail("jmb_chain_iterate: no open chain");
+    if (!h || !h->c->chain_open) return fail("jmb_chain_iterate: no open chain");
     CU(cudaSetDevice(h->device));
-    const ModelMeta& mm = h->mm;
     float kms = 0.f;
-    CU(cudaEventRecord(h->ev0, h->stream));
-    for (int k = 0; k < iters; ++k) {
-        const int i_blk = h->iter_host % h->cc.n_block;
-        if (i_blk % h->rng_chunk == 0) {            // draws for the next rng_chunk iterations (:658)
-            PrepArgs pa{};
-            pa.Rchol = h->d_Rchol; pa.state = h->d_state; pa.rng = h->d_rng; pa.n = h->n; pa.q = mm.d.q;
-            pa.state_stride = mm.L.state_stride; pa.rng_stride = h->rng_stride; pa.iter0 = h->iter_host; pa.count = h->rng_chunk;
-            pa.subject_offset = h->subject_offset;
-            const long long tot = (long long)h->n * h->rng_chunk;
-            const unsigned pg = (unsigned)((tot + 255) / 256);
-            if (mm.d.q == 2) jmb_block_prep_kernel<2><<<pg, 256, 0, h->stream>>>(h->cc, pa);
-            else if (mm.d.q == 4) jmb_block_prep_kernel<4><<<pg, 256, 0, h->stream>>>(h->cc, pa);
-            else if (mm.d.q == 6) jmb_block_prep_kernel<6><<<pg, 256, 0, h->stream>>>(h->cc, pa);
-            else jmb_block_prep_kernel<0><<<pg, 256, 0, h->stream>>>(h->cc, pa);
-            h->launches += 1;
-            CU(cudaGetLastError());
-        }
-        if (step_kernel_ms) CU(cudaEventRecord(h->evk0, h->stream));
-        if (launch_step(h, MODE_STEP)) return 1;
-        if (step_kernel_ms) {
-            CU(cudaEventRecord(h->evk1, h->stream));
-            CU(cudaEventSynchronize(h->evk1));
-            float t = 0.f;
-            CU(cudaEventElapsedTime(&t, h->evk0, h->evk1));
-            kms += t;
-        }
-        if (launch_finalize(h, 0)) return 1;
-        if (i_blk == h->cc.n_block - 1) {           // block end: per-subject scale adaptation (:853-859)
-            jmb_adapt_sigma_kernel<<<(h->n + 255) / 256, 256, 0, h->stream>>>(h->cc, h->d_state, h->n, mm.d.q, mm.L.state_stride, h->d_ctl);
-            h->launches += 1;
-            CU(cudaGetLastError());
-        }
-        if (is_keep_iter(h, h->iter_host)) {
-            const long long tot = (long long)h->n * mm.d.q;
-            jmb_extract_b_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
-                h->d_state, mm.L.state_stride, h->n, mm.d.q, 0, h->o_b + (size_t)h->keep_host * h->n * mm.d.q);
-            h->launches += 1;
-            CU(cudaGetLastError());
-            h->keep_host += 1; h->check_host += 1;
-        }
-        h->iter_host += 1;
-    }
-    CU(cudaEventRecord(h->ev1, h->stream));
-    CU(cudaEventSynchronize(h->ev1));
-    if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+    CU(cudaEventRecord(h->c->ev0, h->c->stream));
+    for (int k = 0; k < iters; ++k)
+        if (enqueue_iteration(h, step_kernel_ms ? &kms : nullptr)) return 1;
+    CU(cudaEventRecord(h->c->ev1, h->c->stream));
+    CU(cudaEventSynchronize(h->c->ev1));
+    if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, h->c->ev0, h->c->ev1));
     if (step_kernel_ms) *step_kernel_ms = kms;
     Ctl c;
-    CU(cudaMemcpy(&c, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&c, h->c->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
     if (c.error) return fail("jmb_chain_iterate: proposal covariance is not positive definite");
     return 0;
 }
 
+// Several chains of the same fit in flight: slots 0..nslots-1 (each begun with jmb_chain_begin after
+// jmb_select_chain) advance `iters` iterations, enqueued round-robin on their own streams so that one
+// chain's survival-block bookkeeping overlaps the other chains' subject kernels.  This is the
+// reference's chain parallelism (foreach over draws, R/mvJointModelBayes.R:871-905) on one device.
+extern "C" int jmb_chains_iterate(jmb_handle h, int nslots, int iters, float* elapsed_ms) {
+    if (!h || nslots < 1 || nslots > (int)h->slots.size()) return fail("jmb_chains_iterate: bad slot count");
+    CU(cudaSetDevice(h->device));
+    ChainCtx* keep = h->c;
+    for (int s = 0; s < nslots; ++s)
+        if (!h->slots[s]->chain_open) return fail("jmb_chains_iterate: a slot has no open chain");
+    ChainCtx* first = h->slots[0];
+    // common start: every stream waits for slot 0's start event
+    CU(cudaEventRecord(first->ev0, first->stream));
+    for (int s = 1; s < nslots; ++s) CU(cudaStreamWaitEvent(h->slots[s]->stream, first->ev0, 0));
+    for (int k = 0; k < iters; ++k)
+        for (int s = 0; s < nslots; ++s) {
+            h->c = h->slots[s];
+            if (enqueue_iteration(h, nullptr)) { h->c = keep; return 1; }
+        }
+    // common end: slot 0's stream waits for all the others
+    for (int s = 1; s < nslots; ++s) {
+        CU(cudaEventRecord(h->slots[s]->ev1, h->slots[s]->stream));
+        CU(cudaStreamWaitEvent(first->stream, h->slots[s]->ev1, 0));
+    }
+    CU(cudaEventRecord(first->ev1, first->stream));
+    CU(cudaEventSynchronize(first->ev1));
+    if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, first->ev0, first->ev1));
+    for (int s = 0; s < nslots; ++s) {
+        Ctl c;
+        CU(cudaMemcpy(&c, h->slots[s]->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+        if (c.error) { h->c = keep; return fail("jmb_chains_iterate: proposal covariance is not positive definite"); }
+    }
+    h->c = keep;
+    return 0;
+}
+
 extern "C" int jmb_chain_end(jmb_handle h, jmb_chain_out* out) {
-    if (!h || !h->chain_open) return fail("jmb_chain_end: no open chain");
+    if (!h || !h->c->chain_open) return fail("jmb_chain_end: no open chain");
     CU(cudaSetDevice(h->device));
     const ModelMeta& mm = h->mm;
     const ParamLayout& pl = h->pl;
-    const int n = h->n, q = mm.d.q, B = mm.B, p = mm.d.p, A = mm.d.A, no = h->n_out;
-    CU(cudaStreamSynchronize(h->stream));
-    h->chain_open = false;
+    const int n = h->n, q = mm.d.q, B = mm.B, p = mm.d.p, A = mm.d.A, no = h->c->n_out;
+    CU(cudaStreamSynchronize(h->c->stream));
+    h->c->chain_open = false;
     if (!out) return 0;
-    const FinalizeArgs& fa = h->fa;
+    const FinalizeArgs& fa = h->c->fa;
     auto d2h = [&](double* dst, const double* src, size_t len) -> cudaError_t {
         if (!dst || len == 0) return cudaSuccess;
         return cudaMemcpy(dst, src, sizeof(double) * len, cudaMemcpyDeviceToHost);
     };
-    CU(d2h(out->b, h->o_b, (size_t)n * q * no));
+    CU(d2h(out->b, h->c->o_b, (size_t)n * q * no));
     CU(d2h(out->Bs_gammas, fa.o_Bs, (size_t)B * no));
     CU(d2h(out->gammas, fa.o_g, (size_t)p * no));
     CU(d2h(out->alphas, fa.o_a, (size_t)A * no));
@@ -815,37 +893,37 @@ extern "C" int jmb_chain_end(jmb_handle h, jmb_chain_out* out) {
     CU(d2h(out->tau_Bs_gammas, fa.o_tau_Bs, no));
     CU(d2h(out->tau_gammas, fa.o_tau_g, no));
     CU(d2h(out->tau_alphas, fa.o_tau_a, no));
-    CU(d2h(out->tau_td_alphas, fa.o_tau_td, (size_t)h->n_td * no));
+    CU(d2h(out->tau_td_alphas, fa.o_tau_td, (size_t)h->c->n_td * no));
     CU(d2h(out->logWeights, fa.o_lw, no));
-    CU(d2h(out->sigma_surv, h->d_par + pl.sig, 3));
-    CU(d2h(out->Sigma_Bs_gammas, h->d_par + pl.S_Bs, (size_t)B * B));
-    CU(d2h(out->Sigma_gammas, h->d_par + pl.S_g, (size_t)p * p));
-    CU(d2h(out->Sigma_alphas, h->d_par + pl.S_a, (size_t)A * A));
-    CU(d2h(out->trace_surv, h->o_trace, 2 * (size_t)h->iter_host));
+    CU(d2h(out->sigma_surv, h->c->d_par + pl.sig, 3));
+    CU(d2h(out->Sigma_Bs_gammas, h->c->d_par + pl.S_Bs, (size_t)B * B));
+    CU(d2h(out->Sigma_gammas, h->c->d_par + pl.S_g, (size_t)p * p));
+    CU(d2h(out->Sigma_alphas, h->c->d_par + pl.S_a, (size_t)A * A));
+    CU(d2h(out->trace_surv, h->c->o_trace, 2 * (size_t)h->c->iter_host));
     if (out->sigma_b || out->accept_b) {
         // columns q (sigma_b) and q+4 (total accepts) of the state
-        jmb_extract_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.L.state_stride, n, 1, q, h->d_tmp);
-        jmb_extract_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.L.state_stride, n, 1, q + 4, h->d_tmp + n);
+        jmb_extract_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->c->stream>>>(h->c->d_state, mm.L.state_stride, n, 1, q, h->c->d_tmp);
+        jmb_extract_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->c->stream>>>(h->c->d_state, mm.L.state_stride, n, 1, q + 4, h->c->d_tmp + n);
         h->launches += 2;
         CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(h->stream));
-        CU(d2h(out->sigma_b, h->d_tmp, n));
+        CU(cudaStreamSynchronize(h->c->stream));
+        CU(d2h(out->sigma_b, h->c->d_tmp, n));
         if (out->accept_b) {
-            CU(d2h(out->accept_b, h->d_tmp + n, n));
-            for (int i = 0; i < n; ++i) out->accept_b[i] /= std::max(h->iter_host, 1);
+            CU(d2h(out->accept_b, h->c->d_tmp + n, n));
+            for (int i = 0; i < n; ++i) out->accept_b[i] /= std::max(h->c->iter_host, 1);
         }
     }
     if (out->accept_surv) {
         Ctl c;
-        CU(cudaMemcpy(&c, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
-        out->accept_surv[0] = (double)c.accept_s_total / std::max(h->iter_host, 1);
+        CU(cudaMemcpy(&c, h->c->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+        out->accept_surv[0] = (double)c.accept_s_total / std::max(h->c->iter_host, 1);
     }
     return 0;
 }
 
 extern "C" int jmb_lap_rwm(jmb_handle h, const jmb_priors* pr, const jmb_control* ct, const jmb_chain_in* in, jmb_chain_out* out) {
     if (jmb_chain_begin(h, pr, ct, in)) return 1;
-    if (jmb_chain_iterate(h, h->total_iters, nullptr, nullptr)) return 1;
+    if (jmb_chain_iterate(h, h->c->total_iters, nullptr, nullptr)) return 1;
     return jmb_chain_end(h, out);
 }
 
@@ -855,31 +933,31 @@ extern "C" int jmb_lap_rwm(jmb_handle h, const jmb_priors* pr, const jmb_control
 extern "C" int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* Bs, const double* gam,
                                    const double* alp, jmb_eval_out* out) {
     if (!h || !b || !out) return fail("jmb_eval_logpost_re: null argument");
-    if (!h->draw_set) return fail("jmb_eval_logpost_re: call jmb_set_draw first");
-    if (h->chain_open) return fail("jmb_eval_logpost_re: a chain is open on this handle");
+    if (!h->c->draw_set) return fail("jmb_eval_logpost_re: call jmb_set_draw first");
+    if (h->c->chain_open) return fail("jmb_eval_logpost_re: a chain is open on this handle");
     CU(cudaSetDevice(h->device));
     const ModelMeta& mm = h->mm;
     const ParamLayout& pl = h->pl;
     const int n = h->n, q = mm.d.q, B = mm.B, p = mm.d.p, A = mm.d.A;
-    CU(cudaStreamSynchronize(h->stream));
-    double* hp = h->h_par;
+    CU(cudaStreamSynchronize(h->c->stream));
+    double* hp = h->c->h_par;
     memcpy(hp + pl.cur, Bs, sizeof(double) * B);
     if (p) memcpy(hp + pl.cur + B, gam, sizeof(double) * p);
     memcpy(hp + pl.cur + B + p, alp, sizeof(double) * A);
     memcpy(hp + pl.prop, hp + pl.cur, sizeof(double) * mm.P);
-    CU(cudaMemcpyAsync(h->d_par + pl.cur, hp + pl.cur, sizeof(double) * 2 * mm.P, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(h->d_ctl, 0, sizeof(Ctl), h->stream));
-    memcpy(h->h_tmp, b, sizeof(double) * (size_t)n * q);
-    for (int i = 0; i < n; ++i) h->h_tmp[(size_t)n * q + i] = 1.0;
-    CU(cudaMemcpyAsync(h->d_tmp, h->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->c->d_par + pl.cur, hp + pl.cur, sizeof(double) * 2 * mm.P, cudaMemcpyHostToDevice, h->c->stream));
+    CU(cudaMemsetAsync(h->c->d_ctl, 0, sizeof(Ctl), h->c->stream));
+    memcpy(h->c->h_tmp, b, sizeof(double) * (size_t)n * q);
+    for (int i = 0; i < n; ++i) h->c->h_tmp[(size_t)n * q + i] = 1.0;
+    CU(cudaMemcpyAsync(h->c->d_tmp, h->c->h_tmp, sizeof(double) * (size_t)n * (q + 1), cudaMemcpyHostToDevice, h->c->stream));
     const long long tot = (long long)n * mm.L.state_stride;
-    jmb_load_state_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_state, mm.L.state_stride, n, q, h->d_tmp, h->d_tmp + (size_t)n * q);
+    jmb_load_state_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->c->stream>>>(h->c->d_state, mm.L.state_stride, n, q, h->c->d_tmp, h->c->d_tmp + (size_t)n * q);
     h->launches += 1;
     CU(cudaGetLastError());
-    memset(&h->cc, 0, sizeof(h->cc));
-    h->cc.n_block = 1;
+    memset(&h->c->cc, 0, sizeof(h->c->cc));
+    h->c->cc.n_block = 1;
     if (launch_step(h, MODE_EVAL)) return 1;
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->c->stream));
     double* dst[6] = {out->log_pyb, out->log_pb, out->log_h, out->H, out->HL, out->log_ptb};
     for (int k = 0; k < 6; ++k)
         if (dst[k]) CU(cudaMemcpy(dst[k], h->d_eval + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
@@ -927,24 +1005,24 @@ static int surv_post_sums(jmb_handle h, const double* Bs, const double* gam, con
         return 0;
     }
     CU(cudaSetDevice(h->device));
-    CU(cudaMemcpyAsync(h->d_theta, theta.data(), sizeof(double) * P, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_theta, theta.data(), sizeof(double) * P, cudaMemcpyHostToDevice, h->c->stream));
     SurvPostArgs a{};
     a.drec = h->d_drec; a.doff = h->d_doff; a.Wlong = h->d_Wlong; a.Wlongs = h->d_Wlongs; a.theta = h->d_theta;
     a.partials = h->d_sp_partials; a.n = h->n; a.subjects_per_cta = h->subjects_per_cta;
     const int groups = 256 / mm.d.G;
     const int smem = (int)sizeof(double) * (P + groups * NA);
-    if (mm.d.G == 16) jmb_surv_post_kernel<16><<<h->grid, 256, smem, h->stream>>>(mm, a);
-    else jmb_surv_post_kernel<32><<<h->grid, 256, smem, h->stream>>>(mm, a);
-    jmb_colsum_kernel<<<NA, 128, 0, h->stream>>>(h->d_sp_partials, h->grid, NA, h->d_sp_out);
+    if (mm.d.G == 16) jmb_surv_post_kernel<16><<<h->grid, 256, smem, h->c->stream>>>(mm, a);
+    else jmb_surv_post_kernel<32><<<h->grid, 256, smem, h->c->stream>>>(mm, a);
+    jmb_colsum_kernel<<<NA, 128, 0, h->c->stream>>>(h->d_sp_partials, h->grid, NA, h->d_sp_out);
     h->launches += 2;
     CU(cudaGetLastError());
     if (h->nranks > 1) {
-        ncclResult_t rc = g_nccl.AllReduce(h->d_sp_out, h->d_sp_out, NA, ncclDouble, ncclSum, h->comm, h->stream);
+        ncclResult_t rc = g_nccl.AllReduce(h->d_sp_out, h->d_sp_out, NA, ncclDouble, ncclSum, h->comm, h->c->stream);
         if (rc != ncclSuccess) return fail("ncclAllReduce failed in jmb_logPosterior");
     }
     out.assign(NA, 0.0);
-    CU(cudaMemcpyAsync(out.data(), h->d_sp_out, sizeof(double) * NA, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(out.data(), h->d_sp_out, sizeof(double) * NA, cudaMemcpyDeviceToHost, h->c->stream));
+    CU(cudaStreamSynchronize(h->c->stream));
     h->sp_last_theta = theta;
     h->sp_last_out = out;
     return 0;
@@ -982,11 +1060,11 @@ extern "C" int jmb_gradient_logPosterior(jmb_handle h, double temp, const double
     const int B = h->mm.B, p = h->mm.d.p, A = h->mm.d.A;
     std::vector<double> ecs = h->ecs;
     if (h->nranks > 1) {   // event_colSums over the whole cohort
-        CU(cudaMemcpyAsync(h->d_sp_out, ecs.data(), sizeof(double) * (B + p + A), cudaMemcpyHostToDevice, h->stream));
-        if (g_nccl.AllReduce(h->d_sp_out, h->d_sp_out, B + p + A, ncclDouble, ncclSum, h->comm, h->stream) != ncclSuccess)
+        CU(cudaMemcpyAsync(h->d_sp_out, ecs.data(), sizeof(double) * (B + p + A), cudaMemcpyHostToDevice, h->c->stream));
+        if (g_nccl.AllReduce(h->d_sp_out, h->d_sp_out, B + p + A, ncclDouble, ncclSum, h->comm, h->c->stream) != ncclSuccess)
             return fail("ncclAllReduce failed in jmb_gradient_logPosterior");
-        CU(cudaMemcpyAsync(ecs.data(), h->d_sp_out, sizeof(double) * (B + p + A), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpyAsync(ecs.data(), h->d_sp_out, sizeof(double) * (B + p + A), cudaMemcpyDeviceToHost, h->c->stream));
+        CU(cudaStreamSynchronize(h->c->stream));
         h->sp_last_theta.clear();
     }
     const double* par[3] = {Bs, gam, alp};
@@ -1039,7 +1117,7 @@ extern "C" const char* jmb_kernel_name(jmb_handle h) {
     return h->kernel_label.c_str();
 }
 
-extern "C" void* jmb_stream(jmb_handle h) { return h ? (void*)h->stream : nullptr; }
+extern "C" void* jmb_stream(jmb_handle h) { return h ? (void*)h->c->stream : nullptr; }
 
 // ---------------------------------------------------------------------------------------------
 // multi-GPU

@@ -175,3 +175,31 @@ def test_errors_are_loud(cuda_lib):
     ctl = dict(c["control"]); ctl.update(n_burnin=40, n_iter=40, n_block=10, n_thin=7)
     with pytest.raises(cuda_lib.JmbError):
         cuda_lib.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, False)
+
+
+def test_chains_in_flight_equal_sequential_chains(cuda_lib):
+    """Three chain slots advanced together on their own streams give the chains one gets by running
+    them one after the other (the reference's foreach over draws, R/mvJointModelBayes.R:871-905)."""
+    c = make_cohort("config4", n=300)
+    ctl = dict(c["control"]); ctl.update(n_burnin=30, n_iter=20, n_block=10, n_thin=10)
+    total = 50
+    with cuda_lib.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
+        fit.set_draw(c["Data"])
+        seq = [fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl, chain_id=k) for k in range(3)]
+        fit.chain_slots(3)
+        for k in range(3):
+            fit.select_chain(k)
+            fit.set_draw(c["Data"])
+            fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl, chain_id=k)
+        ms = fit.chains_iterate(3, total)
+        assert ms > 0
+        par = []
+        for k in range(3):
+            fit.select_chain(k)
+            par.append(fit.chain_end())
+    for a, b in zip(seq, par):
+        assert np.array_equal(a["mcmc"]["b"], b["mcmc"]["b"])
+        assert np.array_equal(a["mcmc"]["alphas"], b["mcmc"]["alphas"])
+        assert np.array_equal(a["extras"]["trace_surv"], b["extras"]["trace_surv"])
+        assert np.array_equal(a["scales"]["sigma"]["b"], b["scales"]["sigma"]["b"])
+    assert not np.array_equal(par[0]["mcmc"]["alphas"], par[1]["mcmc"]["alphas"])
