@@ -207,9 +207,7 @@ def run_cuda(args):
     Data = c["Data"]
     fit = api.Fit(Data, c["Covs"]["b"], c["interval_cens"], device=local, subject_offset=rank * n)
     if world > 1:
-        uid = [api.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        fit.comm_init(world, rank, uid[0])
+        api.connect_ranks(fit, world, rank, dist)
     info = fit.layout_info()
     ctl = dict(c["control"])
     total_needed = args.warmup + args.steps

@@ -232,6 +232,14 @@ int jmb_layout_info(jmb_handle h, double* shared_bytes_per_subject,
  * is created on rank 0 and distributed by the host language (torch.distributed / Rmpi). */
 int jmb_comm_unique_id(char id[128]);
 int jmb_comm_init(jmb_handle h, int nranks, int rank, const char id[128]);
+/* Fused compute + collective: after jmb_p2p_attach the finalize kernel all-reduces the three
+ * per-iteration sums itself through NVLink peer memory (each rank stores into every peer's mailbox and
+ * waits for the peers' stores), replacing the reduce kernel + ncclAllReduce of the per-iteration path.
+ * jmb_p2p_export returns the 64-byte CUDA IPC handle of this rank's mailbox; `handles` holds the
+ * nranks handles in rank order (gathered by the host language).  jmb_comm_init is still required (the
+ * Laplace-step sums use NCCL). */
+int jmb_p2p_export(jmb_handle h, int nranks, char handle[64]);
+int jmb_p2p_attach(jmb_handle h, int nranks, int rank, const char* handles);
 
 /* Benchmark hooks: run `iters` iterations of the current chain state entirely on the device
  * (no host copies) and report the device time of the loop; jmb_chain_begin uploads state. */

@@ -66,6 +66,8 @@ def lib():
     L.jmb_launch_count.argtypes = [vp, _abi.c_int64_p]
     L.jmb_comm_unique_id.argtypes = [C.c_char_p]
     L.jmb_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.jmb_p2p_export.argtypes = [vp, C.c_int, C.c_char_p]
+    L.jmb_p2p_attach.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.jmb_device_count.argtypes = [C.POINTER(C.c_int)]
     _lib_cache = L
     return L
@@ -267,6 +269,26 @@ class Fit:
     # -- multi-GPU ---------------------------------------------------------------------------------
     def comm_init(self, nranks: int, rank: int, unique_id: bytes):
         _check(lib().jmb_comm_init(self._h, nranks, rank, unique_id))
+
+    def p2p_export(self, nranks: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().jmb_p2p_export(self._h, nranks, buf))
+        return buf.raw
+
+    def p2p_attach(self, nranks: int, rank: int, handles: bytes):
+        _check(lib().jmb_p2p_attach(self._h, nranks, rank, handles))
+
+
+def connect_ranks(fit: "Fit", world: int, rank: int, dist) -> None:
+    """One process per GPU: NCCL communicator for the library plus the peer-memory mailboxes of the
+    fused per-iteration all-reduce.  ``dist`` is an initialised ``torch.distributed`` module."""
+    uid = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    fit.comm_init(world, rank, uid[0])
+    handles = [None] * world
+    dist.all_gather_object(handles, fit.p2p_export(world))
+    fit.p2p_attach(world, rank, b"".join(handles))
+    dist.barrier()
 
 
 def comm_unique_id() -> bytes:

@@ -88,6 +88,8 @@ struct ChainCtx {
     bool draw_set = false, chain_open = false, fin_attr_set = false;
     int iter_host = 0, total_iters = 0, keep_host = 0, check_host = 0, n_out = 0, n_td = 0;
     double *o_b = nullptr, *o_par = nullptr, *o_trace = nullptr;   // device outputs
+    unsigned long long p2p_seq = 0;                 // stamp of the last fused all-reduce of this slot
+    int slot_index = 0;
     FinalizeArgs fa{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
 };
@@ -133,6 +135,12 @@ struct jmb_handle_s {
     int add_slot();
     // multi-GPU
     ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
+    // peer-memory mailboxes for the fused all-reduce of the per-iteration sums
+    static constexpr int kMboxSlots = 64;
+    double* d_mbox = nullptr;                       // this rank's mailbox [kMboxSlots][2][nranks][4]
+    std::vector<void*> peer_ptrs;                   // peers' mailboxes opened through CUDA IPC
+    double** d_peer_mbox = nullptr;                 // device copy of the pointer table
+    bool p2p = false;
 };
 
 int jmb_handle_s::select_kernel() {
@@ -490,6 +498,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
 // one more chain slot (own stream, per-draw records, state, parameter block, staging)
 int jmb_handle_s::add_slot() {
     ChainCtx* x = new ChainCtx();
+    x->slot_index = (int)slots.size();
     slots.push_back(x);
     if (!c) c = x;
     const size_t crec_len = (size_t)std::max<long long>(coff[n], 2);
@@ -534,6 +543,9 @@ extern "C" int jmb_destroy(jmb_handle h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->d_drec); cudaFree(h->d_doff); cudaFree(h->d_coff); cudaFree(h->d_rowptr); cudaFree(h->d_eval);
     cudaFree(h->d_Rchol);
+    for (size_t r = 0; r < h->peer_ptrs.size(); ++r)
+        if (h->peer_ptrs[r] && (int)r != h->rank) cudaIpcCloseMemHandle(h->peer_ptrs[r]);
+    cudaFree(h->d_mbox); cudaFree(h->d_peer_mbox);
     cudaFree(h->d_Wlong); cudaFree(h->d_Wlongs); cudaFree(h->d_sp_partials); cudaFree(h->d_sp_out); cudaFree(h->d_theta);
     for (ChainCtx* x : h->slots) {
         cudaFree(x->d_crec); cudaFree(x->d_state); cudaFree(x->d_par); cudaFree(x->d_ctl); cudaFree(x->d_partials);
@@ -614,9 +626,13 @@ static int launch_step(jmb_handle h, int mode) {
 static int launch_finalize(jmb_handle h, int phase) {
     FinalizeArgs a = h->c->fa;
     a.par = h->c->d_par; a.ctl = h->c->d_ctl; a.partials = h->c->d_partials; a.n_partials = h->grid;
-    a.use_reduced = (h->nranks > 1) ? 1 : 0; a.phase = phase;
+    a.use_reduced = (h->nranks > 1) ? (h->p2p ? 2 : 1) : 0; a.phase = phase;
     a.n_partials = (h->kernel_mode == 2) ? h->tma_grid : h->grid;
-    if (phase == 0 && h->nranks > 1) {
+    if (phase == 0 && h->nranks > 1 && h->p2p) {
+        a.peer_mbox = h->d_peer_mbox; a.my_mbox = h->d_mbox; a.nranks = h->nranks; a.rank = h->rank;
+        a.slot = h->c->slot_index; a.stamp = ++h->c->p2p_seq;
+    }
+    if (phase == 0 && h->nranks > 1 && !h->p2p) {
         jmb_reduce_partials_kernel<<<1, 128, 0, h->c->stream>>>(h->c->d_partials, a.n_partials, h->c->d_par + h->pl.sums);
         h->launches += 1;
         CU(cudaGetLastError());
@@ -830,6 +846,7 @@ extern "C" int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, flo
     if (step_kernel_ms) *step_kernel_ms = kms;
     Ctl c;
     CU(cudaMemcpy(&c, h->c->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    if (c.error == 3) return fail("jmb_chain_iterate: a peer rank did not deliver its sums (fused all-reduce timed out)");
     if (c.error) return fail("jmb_chain_iterate: proposal covariance is not positive definite");
     return 0;
 }
@@ -864,6 +881,7 @@ extern "C" int jmb_chains_iterate(jmb_handle h, int nslots, int iters, float* el
     for (int s = 0; s < nslots; ++s) {
         Ctl c;
         CU(cudaMemcpy(&c, h->slots[s]->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+        if (c.error == 3) { h->c = keep; return fail("jmb_chains_iterate: a peer rank did not deliver its sums (fused all-reduce timed out)"); }
         if (c.error) { h->c = keep; return fail("jmb_chains_iterate: proposal covariance is not positive definite"); }
     }
     h->c = keep;
@@ -1141,5 +1159,48 @@ extern "C" int jmb_comm_init(jmb_handle h, int nranks, int rank, const char id[1
     ncclResult_t rc = g_nccl.CommInitRank(&h->comm, nranks, uid, rank);
     if (rc != ncclSuccess) return fail(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
     h->nranks = nranks; h->rank = rank;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused all-reduce over NVLink peer memory.  jmb_p2p_export allocates this rank's mailbox and
+// returns its CUDA IPC handle (64 bytes); the host language gathers the handles of all ranks
+// (torch.distributed.all_gather) and passes them to jmb_p2p_attach, after which the finalize kernel
+// exchanges the per-iteration sums itself (stores into every peer's mailbox, waits for the peers'
+// stores) and NCCL is no longer on the per-iteration path.
+// ---------------------------------------------------------------------------------------------
+extern "C" int jmb_p2p_export(jmb_handle h, int nranks, char handle[64]) {
+    if (!h || nranks < 2 || nranks > 64) return fail("jmb_p2p_export: bad argument");
+    CU(cudaSetDevice(h->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!h->d_mbox) {
+        const size_t bytes = sizeof(double) * jmb_handle_s::kMboxSlots * 2 * (size_t)nranks * 4;
+        CU(cudaMalloc(&h->d_mbox, bytes));
+        CU(cudaMemset(h->d_mbox, 0, bytes));
+        CU(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t ih;
+    CU(cudaIpcGetMemHandle(&ih, h->d_mbox));
+    memcpy(handle, &ih, 64);
+    return 0;
+}
+
+extern "C" int jmb_p2p_attach(jmb_handle h, int nranks, int rank, const char* handles) {
+    if (!h || !handles || nranks < 2 || rank < 0 || rank >= nranks) return fail("jmb_p2p_attach: bad argument");
+    if (!h->d_mbox) return fail("jmb_p2p_attach: call jmb_p2p_export first");
+    if ((int)h->slots.size() > jmb_handle_s::kMboxSlots) return fail("jmb_p2p_attach: too many chain slots");
+    CU(cudaSetDevice(h->device));
+    h->peer_ptrs.assign(nranks, nullptr);
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { h->peer_ptrs[r] = h->d_mbox; continue; }
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, handles + (size_t)r * 64, 64);
+        CU(cudaIpcOpenMemHandle(&h->peer_ptrs[r], ih, cudaIpcMemLazyEnablePeerAccess));
+    }
+    CU(cudaMalloc(&h->d_peer_mbox, sizeof(double*) * nranks));
+    CU(cudaMemcpy(h->d_peer_mbox, h->peer_ptrs.data(), sizeof(double*) * nranks, cudaMemcpyHostToDevice));
+    h->nranks = nranks; h->rank = rank; h->p2p = true;
+    const char* env = getenv("JMB_ALLREDUCE");
+    if (env && !strcmp(env, "nccl")) h->p2p = false;     // A/B: keep NCCL on the per-iteration path
     return 0;
 }

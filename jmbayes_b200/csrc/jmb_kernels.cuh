@@ -295,6 +295,12 @@ struct FinalizeArgs {
     int use_reduced;          // multi-GPU: par[pl.sums..] already holds the all-reduced sums
     int phase;                // 0: regular iteration, 1: chain start (Cholesky + first proposal only)
     int use_smem;             // the parameter block fits the kernel's dynamic shared memory
+    // one-shot all-reduce of the three sums over NVLink peer memory (use_reduced == 2): every rank
+    // stores its sums into every peer's mailbox and then waits for all the peers' stores
+    double* const* peer_mbox; // [nranks] mailbox base of each rank as mapped into this process
+    double* my_mbox;          // this rank's own mailbox: [slots][2][nranks][4] (3 sums + stamp)
+    int nranks, rank, slot;
+    unsigned long long stamp; // strictly increasing per slot; parity selects the mailbox half
     // outputs of kept iterations (device buffers laid out like jmb_chain_out)
     double* o_Bs; double* o_g; double* o_a; double* o_phi_g; double* o_phi_a; double* o_tau_Bs;
     double* o_tau_g; double* o_tau_a; double* o_tau_td; double* o_lw; double* trace;
@@ -358,7 +364,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     }
 
     // ---- deterministic reduction of the per-CTA partials ----
-    if (a.use_reduced) {
+    if (a.use_reduced == 1) {
         if (tid < 3) s_tot[tid] = gpar[pl.sums + tid];
     } else {
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
@@ -372,6 +378,36 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         if (tid < 3) s_tot[tid] = s_sum[tid * 128];
     }
     __syncthreads();
+    if (a.use_reduced == 2) {
+        // ---- fused all-reduce over peer memory: compute (local sums) and collective in one kernel ----
+        const int par2 = (int)(a.stamp & 1ull);
+        const long long base = ((long long)(a.slot * 2 + par2) * a.nranks);
+        if (tid < a.nranks) {
+            double* dst = a.peer_mbox[tid] + (base + a.rank) * 4;
+            dst[0] = s_tot[0]; dst[1] = s_tot[1]; dst[2] = s_tot[2];
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(dst + 3) = a.stamp;
+        }
+        __syncthreads();
+        if (tid < a.nranks) {
+            const double* src = a.my_mbox + (base + tid) * 4;
+            const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(src + 3);
+            long long spins = 0;
+            while (*flag != a.stamp) {
+                if (++spins > 200000000LL) { a.ctl->error = 3; break; }     // a peer died: give up instead of hanging
+            }
+            __threadfence_system();
+            const volatile double* vs = src;
+            s_sum[tid * 3] = vs[0]; s_sum[tid * 3 + 1] = vs[1]; s_sum[tid * 3 + 2] = vs[2];
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double t = 0.0;
+            for (int r = 0; r < a.nranks; ++r) t += s_sum[r * 3 + tid];     // rank order: identical on every rank
+            s_tot[tid] = t;
+        }
+        __syncthreads();
+    }
 
     // ---- quadratic forms of the three Gaussian priors, one coordinate per thread ----
     // thread j < P handles coordinate j of (Bs_gammas | gammas | alphas) against its block's Tau:

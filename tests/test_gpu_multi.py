@@ -33,10 +33,8 @@ def _worker(rank, world, port, cfg, n, ret):
     c = make_cohort(cfg, n=n)
     ctl = dict(c["control"]); ctl.update(n_burnin=30, n_iter=20, n_block=10, n_thin=10)
     sh = shard_cohort(c, rank, world)
-    uid = [api.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
     with api.Fit(sh["Data"], sh["Covs"]["b"], c["interval_cens"], device=rank, subject_offset=sh["subject_offset"]) as fit:
-        fit.comm_init(world, rank, uid[0])
+        api.connect_ranks(fit, world, rank, dist)
         fit.set_draw(sh["Data"])
         r = fit.lap_rwm_C(sh["inits"], sh["priors"], sh["scales"], sh["Covs"], ctl)
     parts = [None] * world
