@@ -278,9 +278,16 @@ def run_cuda(args):
     barrier()
     t0 = time.perf_counter()
     fit.set_draw(Data)
-    res = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl_e)
+    ta_ = time.perf_counter()
+    fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl_e)
+    tb_ = time.perf_counter()
+    fit.chain_iterate(e2e_total)
+    tc_ = time.perf_counter()
+    res = fit.chain_end()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    print(f"[rank {rank}] e2e phases: set_draw {ta_ - t0:.3f}s chain_begin {tb_ - ta_:.3f}s iterate {tc_ - tb_:.3f}s chain_end {t1 - tc_:.3f}s",
+          file=sys.stderr, flush=True)
     te = torch.tensor([t1 - t0], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

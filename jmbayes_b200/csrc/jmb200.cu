@@ -88,6 +88,7 @@ struct ChainCtx {
     bool draw_set = false, chain_open = false, fin_attr_set = false;
     int iter_host = 0, total_iters = 0, keep_host = 0, check_host = 0, n_out = 0, n_td = 0;
     double *o_b = nullptr, *o_par = nullptr, *o_trace = nullptr;   // device outputs
+    size_t cap_ob = 0, cap_opar = 0, cap_otr = 0;   // capacities (doubles) of the output buffers
     unsigned long long p2p_seq = 0;                 // stamp of the last fused all-reduce of this slot
     int slot_index = 0;
     FinalizeArgs fa{};
@@ -729,17 +730,17 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     CU(cudaMemcpyAsync(h->c->d_par, hp, sizeof(double) * pl.block_par, cudaMemcpyHostToDevice, h->c->stream));
     CU(cudaMemsetAsync(h->c->d_ctl, 0, sizeof(Ctl), h->c->stream));
 
-    // outputs on the device
-    cudaFree(h->c->o_b); cudaFree(h->c->o_par); cudaFree(h->c->o_trace);
-    h->c->o_b = h->c->o_par = h->c->o_trace = nullptr;
+    // outputs on the device (buffers are kept across chains of the same shape: cudaMalloc / cudaFree
+    // synchronise the device and are slow once peer mappings exist)
     const int no = std::max(cc.n_out, 1);
     const size_t par_out = (size_t)no * (B + 2 * p + 2 * A + 4 + JMB_MAX_TERMS);
-    CU(cudaMalloc(&h->c->o_b, sizeof(double) * (size_t)n * q * no));
-    CU(cudaMalloc(&h->c->o_par, sizeof(double) * par_out));
-    CU(cudaMemsetAsync(h->c->o_b, 0, sizeof(double) * (size_t)n * q * no, h->c->stream));
+    const size_t need_b = (size_t)n * q * no, need_tr = 2 * (size_t)std::max(h->c->total_iters, 1);
+    if (need_b > h->c->cap_ob) { cudaFree(h->c->o_b); h->c->o_b = nullptr; CU(cudaMalloc(&h->c->o_b, sizeof(double) * need_b)); h->c->cap_ob = need_b; }
+    if (par_out > h->c->cap_opar) { cudaFree(h->c->o_par); h->c->o_par = nullptr; CU(cudaMalloc(&h->c->o_par, sizeof(double) * par_out)); h->c->cap_opar = par_out; }
+    if (need_tr > h->c->cap_otr) { cudaFree(h->c->o_trace); h->c->o_trace = nullptr; CU(cudaMalloc(&h->c->o_trace, sizeof(double) * need_tr)); h->c->cap_otr = need_tr; }
+    CU(cudaMemsetAsync(h->c->o_b, 0, sizeof(double) * need_b, h->c->stream));
     CU(cudaMemsetAsync(h->c->o_par, 0, sizeof(double) * par_out, h->c->stream));
-    CU(cudaMalloc(&h->c->o_trace, sizeof(double) * 2 * (size_t)std::max(h->c->total_iters, 1)));
-    CU(cudaMemsetAsync(h->c->o_trace, 0, sizeof(double) * 2 * (size_t)std::max(h->c->total_iters, 1), h->c->stream));
+    CU(cudaMemsetAsync(h->c->o_trace, 0, sizeof(double) * need_tr, h->c->stream));
     FinalizeArgs& fa = h->c->fa;
     memset(&fa, 0, sizeof(fa));
     double* o = h->c->o_par;
