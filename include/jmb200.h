@@ -221,6 +221,12 @@ int jmb_gradient_logPosterior(jmb_handle h, double temp, const double* Bs_gammas
                               const double* gammas, const double* alphas, const jmb_priors* priors,
                               double tauBs, double A_tauBs, double B_tauBs, double* out);
 
+/* lap_rwm_C_woRE / lap_rwm_C_woRE_nogammas (src/fast_LAPRWM.cpp:934-1139,1142-1297; control$update_RE =
+ * FALSE): the survival block alone on the association designs of jmb_set_wlong.  `in->b`, `in->sigma_b`
+ * and the b-related outputs are not used; logPost [n_out] receives the list element `logPost`. */
+int jmb_lap_rwm_woRE(jmb_handle h, const jmb_priors* priors, const jmb_control* control,
+                     const jmb_chain_in* in, jmb_chain_out* out, double* logPost);
+
 /* Layout facts for the parity tests: the CSR row pointers the device layout was built with
  * (must equal idL2-derived segments bit for bit) and bytes moved per subject-iteration. */
 int jmb_get_row_ptr(jmb_handle h, int outcome, int64_t* row_ptr /* [n+1] */);

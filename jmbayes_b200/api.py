@@ -61,6 +61,8 @@ def lib():
     post = [vp, C.c_double, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p, C.POINTER(_abi.JmbPriors),
             C.c_double, C.c_double, C.c_double, _abi.c_double_p]
     L.jmb_logPosterior.argtypes = post
+    L.jmb_lap_rwm_woRE.argtypes = [vp, C.POINTER(_abi.JmbPriors), C.POINTER(_abi.JmbControl), C.POINTER(_abi.JmbChainIn),
+                                   C.POINTER(_abi.JmbChainOut), _abi.c_double_p]
     L.jmb_gradient_logPosterior.argtypes = post
     L.jmb_layout_info.argtypes = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p, _abi.c_int32_p]
     L.jmb_launch_count.argtypes = [vp, _abi.c_int64_p]
@@ -247,6 +249,26 @@ class Fit:
         _check(lib().jmb_gradient_logPosterior(self._h, float(temp), _dptr(Bs), _dptr(g), _dptr(al), C.byref(pr),
                                                float(tauBs), float(A_tauBs), float(B_tauBs), _dptr(out)))
         return out
+
+    def lap_rwm_C_woRE(self, initials, priors, scales, Covs, control, chain_id: int = 0):
+        """lap_rwm_C_woRE[_nogammas] (src/fast_LAPRWM.cpp:934-1297) on the designs of ``set_wlong``."""
+        ini = dict(initials); ini.setdefault("b", np.zeros((1, 1)))
+        sc = dict(scales); sc.setdefault("b", np.zeros(1))
+        pr, k1 = _abi.marshal_priors(priors)
+        ct = _abi.marshal_control(control, chain_id)
+        ci, k2 = _abi.marshal_chain_in(ini, sc, Covs)
+        total, n_out = _abi.chain_dims(control)
+        out, bufs = _abi.alloc_chain_out(1, 1, self.B, self.p, self.A, 0, n_out, total)
+        logPost = np.zeros(max(n_out, 1))
+        _check(lib().jmb_lap_rwm_woRE(self._h, C.byref(pr), C.byref(ct), C.byref(ci), C.byref(out), _dptr(logPost)))
+        mcmc = {k: bufs[k] for k in ("Bs_gammas", "gammas", "alphas", "phi_gammas", "phi_alphas", "tau_Bs_gammas",
+                                     "tau_gammas", "tau_alphas")}
+        return dict(mcmc=mcmc, logPost=logPost[:n_out],
+                    scales=dict(sigma=dict(Bs_gammas=float(bufs["sigma_surv"][0]), gammas=float(bufs["sigma_surv"][1]),
+                                           alphas=float(bufs["sigma_surv"][2])),
+                                Sigma=dict(Bs_gammas=bufs["Sigma_Bs_gammas"], gammas=bufs["Sigma_gammas"],
+                                           alphas=bufs["Sigma_alphas"])),
+                    extras=dict(trace_surv=bufs["trace_surv"], accept_surv=bufs["accept_surv"]))
 
     def row_ptr(self, outcome: int):
         rp = np.zeros(self.n + 1, dtype=np.int64)

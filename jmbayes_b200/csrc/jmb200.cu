@@ -85,7 +85,7 @@ struct ChainCtx {
     double* h_crec = nullptr;                       // pinned staging for the per-draw records
     double* h_par = nullptr;                        // pinned staging for the parameter block
     double* h_tmp = nullptr;                        // pinned staging n*(q+1)
-    bool draw_set = false, chain_open = false, fin_attr_set = false;
+    bool draw_set = false, chain_open = false, fin_attr_set = false, wore = false;
     int iter_host = 0, total_iters = 0, keep_host = 0, check_host = 0, n_out = 0, n_td = 0;
     double *o_b = nullptr, *o_par = nullptr, *o_trace = nullptr;   // device outputs
     size_t cap_ob = 0, cap_opar = 0, cap_otr = 0;   // capacities (doubles) of the output buffers
@@ -231,6 +231,7 @@ static void build_param_layout(const ModelMeta& mm, int n_td, int n_block_cap, P
     pl.S_Bs = take(mm.B * mm.B); pl.S_g = take(mm.d.p * mm.d.p); pl.S_a = take(mm.d.A * mm.d.A);
     pl.H_Bs = take(mm.B * mm.B); pl.H_g = take(mm.d.p * mm.d.p); pl.H_a = take(mm.d.A * mm.d.A);
     pl.mean_Bs = take(mm.B); pl.Tau_Bs = take(mm.B * mm.B); pl.mean_g = take(mm.d.p); pl.mean_a = take(mm.d.A);
+    pl.cur_lp = take(1);
     pl.block_par = take(mm.P * n_block_cap);
     pl.sums = take(4);
     pl.total = o;
@@ -629,11 +630,13 @@ static int launch_finalize(jmb_handle h, int phase) {
     a.par = h->c->d_par; a.ctl = h->c->d_ctl; a.partials = h->c->d_partials; a.n_partials = h->grid;
     a.use_reduced = (h->nranks > 1) ? (h->p2p ? 2 : 1) : 0; a.phase = phase;
     a.n_partials = (h->kernel_mode == 2) ? h->tma_grid : h->grid;
-    if (phase == 0 && h->nranks > 1 && h->p2p) {
+    a.wore = h->c->wore ? 1 : 0; a.sp_out = h->d_sp_out;
+    if (a.wore) a.use_reduced = 3;                  // the data sums come from the survival-block kernels
+    if (!a.wore && phase == 0 && h->nranks > 1 && h->p2p) {
         a.peer_mbox = h->d_peer_mbox; a.my_mbox = h->d_mbox; a.nranks = h->nranks; a.rank = h->rank;
         a.slot = h->c->slot_index; a.stamp = ++h->c->p2p_seq;
     }
-    if (phase == 0 && h->nranks > 1 && !h->p2p) {
+    if (!a.wore && phase == 0 && h->nranks > 1 && !h->p2p) {
         jmb_reduce_partials_kernel<<<1, 128, 0, h->c->stream>>>(h->c->d_partials, a.n_partials, h->c->d_par + h->pl.sums);
         h->launches += 1;
         CU(cudaGetLastError());
@@ -655,9 +658,8 @@ static int launch_finalize(jmb_handle h, int phase) {
 // ---------------------------------------------------------------------------------------------
 // chain
 // ---------------------------------------------------------------------------------------------
-extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_control* ct, const jmb_chain_in* in) {
-    if (!h || !pr || !ct || !in) return fail("jmb_chain_begin: null argument");
-    if (!h->c->draw_set) return fail("jmb_chain_begin: call jmb_set_draw first");
+// parameter block, loop constants and output buffers of a chain (shared by lap_rwm_C and the woRE flavour)
+static int chain_setup(jmb_handle h, const jmb_priors* pr, const jmb_control* ct, const jmb_chain_in* in, bool wore) {
     CU(cudaSetDevice(h->device));
     const ModelMeta& mm = h->mm;
     const ParamLayout& pl = h->pl;
@@ -686,14 +688,15 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     cc.B_phi_a = pr->B_phi_alphas; cc.Apost_phi_a = pr->A_phi_alphas + 0.5;
     cc.B_xi_a = pr->B_xi_alphas; cc.Apost_xi_a = pr->A_xi_alphas + 0.5;
     cc.B_nu_a = pr->B_nu_alphas; cc.Apost_nu_a = pr->A_nu_alphas + 0.5;
-    cc.n_td = pr->n_td; cc.B_tau_td = pr->B_tau_Bs_gammas;
+    if (wore) { cc.double_gamma_alphas = 0; }      // lap_rwm_C_woRE has neither td-effects nor the double-gamma branch
+    cc.n_td = wore ? 0 : pr->n_td; cc.B_tau_td = pr->B_tau_Bs_gammas;
     cc.Apost_tau_td = pr->A_tau_Bs_gammas + 0.5 * pr->rank_Tau_td_alphas;
-    for (int k = 0; k < pr->n_td; ++k) {
+    for (int k = 0; k < cc.n_td; ++k) {
         cc.td_len[k] = pr->td_len[k];
         if (cc.td_len[k] > JMB_MAX_UT) return fail("jmb_chain_begin: td block too wide");
         for (int j = 0; j < cc.td_len[k]; ++j) cc.td_cols[k][j] = pr->td_cols[k][j];
     }
-    h->c->n_out = cc.n_out; h->c->n_td = pr->n_td;
+    h->c->n_out = cc.n_out; h->c->n_td = cc.n_td;
     h->c->total_iters = its * ct->n_block;
     {   // the reference stores a sample whenever iter == keep[k] (src/fast_LAPRWM.cpp:836-850); when that
         // happens more than n_out times it indexes past its output arrays and fails ("index out of bounds")
@@ -715,7 +718,7 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     hp[pl.xi_a] = in->tau_alphas;                                        // src/fast_LAPRWM.cpp:518
     for (int j = 0; j < p; ++j) hp[pl.phi_g + j] = in->phi_gammas[j];
     for (int j = 0; j < A; ++j) { hp[pl.phi_a + j] = in->phi_alphas[j]; hp[pl.nu_a + j] = in->phi_alphas[j]; }   // :513
-    for (int j = 0; j < pr->n_td; ++j) hp[pl.tau_td + j] = in->tau_td_alphas[j];
+    for (int j = 0; j < cc.n_td; ++j) hp[pl.tau_td + j] = in->tau_td_alphas[j];
     if (p) memcpy(hp + pl.Tau_g, pr->Tau_gammas, sizeof(double) * p * p);
     memcpy(hp + pl.Tau_a, pr->Tau_alphas, sizeof(double) * A * A);
     memcpy(hp + pl.Tau_a_pen, pr->Tau_alphas, sizeof(double) * A * A);
@@ -734,7 +737,7 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     // synchronise the device and are slow once peer mappings exist)
     const int no = std::max(cc.n_out, 1);
     const size_t par_out = (size_t)no * (B + 2 * p + 2 * A + 4 + JMB_MAX_TERMS);
-    const size_t need_b = (size_t)n * q * no, need_tr = 2 * (size_t)std::max(h->c->total_iters, 1);
+    const size_t need_b = wore ? 1 : (size_t)n * q * no, need_tr = 2 * (size_t)std::max(h->c->total_iters, 1);
     if (need_b > h->c->cap_ob) { cudaFree(h->c->o_b); h->c->o_b = nullptr; CU(cudaMalloc(&h->c->o_b, sizeof(double) * need_b)); h->c->cap_ob = need_b; }
     if (par_out > h->c->cap_opar) { cudaFree(h->c->o_par); h->c->o_par = nullptr; CU(cudaMalloc(&h->c->o_par, sizeof(double) * par_out)); h->c->cap_opar = par_out; }
     if (need_tr > h->c->cap_otr) { cudaFree(h->c->o_trace); h->c->o_trace = nullptr; CU(cudaMalloc(&h->c->o_trace, sizeof(double) * need_tr)); h->c->cap_otr = need_tr; }
@@ -754,6 +757,15 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
     fa.o_lw = o;
     fa.trace = h->c->o_trace;
 
+    return 0;
+}
+
+extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_control* ct, const jmb_chain_in* in) {
+    if (!h || !pr || !ct || !in) return fail("jmb_chain_begin: null argument");
+    if (!h->c->draw_set) return fail("jmb_chain_begin: call jmb_set_draw first");
+    if (chain_setup(h, pr, ct, in, false)) return 1;
+    const ModelMeta& mm = h->mm;
+    const int n = h->n, q = mm.d.q;
     // state <- initials$b, scales$b
     memcpy(h->c->h_tmp, in->b, sizeof(double) * (size_t)n * q);
     memcpy(h->c->h_tmp + (size_t)n * q, in->sigma_b, sizeof(double) * n);
@@ -1011,6 +1023,27 @@ extern "C" int jmb_set_wlong(jmb_handle h, const double* Wlong, const double* Wl
 }
 
 // data sums [sum event*log_h, sum Pw exp(lin), score sums...] at theta; cached for the last theta
+// enqueue the data sums of the survival-block log-posterior at a device-resident theta
+static int launch_surv_post(jmb_handle h, const double* d_theta, int value_only) {
+    const ModelMeta& mm = h->mm;
+    const int NA = mm.P + 2;
+    SurvPostArgs a{};
+    a.drec = h->d_drec; a.doff = h->d_doff; a.Wlong = h->d_Wlong; a.Wlongs = h->d_Wlongs; a.theta = d_theta;
+    a.partials = h->d_sp_partials; a.n = h->n; a.subjects_per_cta = h->subjects_per_cta; a.value_only = value_only;
+    const int groups = 256 / mm.d.G;
+    const int smem = (int)sizeof(double) * (mm.P + groups * NA);
+    if (mm.d.G == 16) jmb_surv_post_kernel<16><<<h->grid, 256, smem, h->c->stream>>>(mm, a);
+    else jmb_surv_post_kernel<32><<<h->grid, 256, smem, h->c->stream>>>(mm, a);
+    jmb_colsum_kernel<<<value_only ? 2 : NA, 128, 0, h->c->stream>>>(h->d_sp_partials, h->grid, NA, h->d_sp_out);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    if (h->nranks > 1) {
+        ncclResult_t rc = g_nccl.AllReduce(h->d_sp_out, h->d_sp_out, value_only ? 2 : NA, ncclDouble, ncclSum, h->comm, h->c->stream);
+        if (rc != ncclSuccess) return fail("ncclAllReduce failed in the survival-block sums");
+    }
+    return 0;
+}
+
 static int surv_post_sums(jmb_handle h, const double* Bs, const double* gam, const double* alp, std::vector<double>& out) {
     if (!h->wlong_set) return fail("jmb_logPosterior: call jmb_set_wlong first");
     const ModelMeta& mm = h->mm;
@@ -1025,20 +1058,7 @@ static int surv_post_sums(jmb_handle h, const double* Bs, const double* gam, con
     }
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpyAsync(h->d_theta, theta.data(), sizeof(double) * P, cudaMemcpyHostToDevice, h->c->stream));
-    SurvPostArgs a{};
-    a.drec = h->d_drec; a.doff = h->d_doff; a.Wlong = h->d_Wlong; a.Wlongs = h->d_Wlongs; a.theta = h->d_theta;
-    a.partials = h->d_sp_partials; a.n = h->n; a.subjects_per_cta = h->subjects_per_cta;
-    const int groups = 256 / mm.d.G;
-    const int smem = (int)sizeof(double) * (P + groups * NA);
-    if (mm.d.G == 16) jmb_surv_post_kernel<16><<<h->grid, 256, smem, h->c->stream>>>(mm, a);
-    else jmb_surv_post_kernel<32><<<h->grid, 256, smem, h->c->stream>>>(mm, a);
-    jmb_colsum_kernel<<<NA, 128, 0, h->c->stream>>>(h->d_sp_partials, h->grid, NA, h->d_sp_out);
-    h->launches += 2;
-    CU(cudaGetLastError());
-    if (h->nranks > 1) {
-        ncclResult_t rc = g_nccl.AllReduce(h->d_sp_out, h->d_sp_out, NA, ncclDouble, ncclSum, h->comm, h->c->stream);
-        if (rc != ncclSuccess) return fail("ncclAllReduce failed in jmb_logPosterior");
-    }
+    if (launch_surv_post(h, h->d_theta, 0)) return 1;
     out.assign(NA, 0.0);
     CU(cudaMemcpyAsync(out.data(), h->d_sp_out, sizeof(double) * NA, cudaMemcpyDeviceToHost, h->c->stream));
     CU(cudaStreamSynchronize(h->c->stream));
@@ -1102,6 +1122,49 @@ extern "C" int jmb_gradient_logPosterior(jmb_handle h, double temp, const double
         o += m;
     }
     out[o] = tauBs * (-0.5 * host_quad(Bs, pr->mean_Bs_gammas, pr->Tau_Bs_gammas, B) + (A_tauBs - 1.0) / tauBs - B_tauBs);  // :44
+    return 0;
+}
+
+// lap_rwm_C_woRE / lap_rwm_C_woRE_nogammas (src/fast_LAPRWM.cpp:934-1297): the survival block alone on
+// the fixed association designs of jmb_set_wlong (control$update_RE = FALSE)
+extern "C" int jmb_lap_rwm_woRE(jmb_handle h, const jmb_priors* pr, const jmb_control* ct, const jmb_chain_in* in,
+                                jmb_chain_out* out, double* logPost) {
+    if (!h || !pr || !ct || !in || !out) return fail("jmb_lap_rwm_woRE: null argument");
+    if (!h->wlong_set) return fail("jmb_lap_rwm_woRE: call jmb_set_wlong first");
+    if (h->c->chain_open) return fail("jmb_lap_rwm_woRE: a chain is open on this slot");
+    if (chain_setup(h, pr, ct, in, true)) return 1;
+    const ModelMeta& mm = h->mm;
+    const ParamLayout& pl = h->pl;
+    const int B = mm.B, p = mm.d.p, A = mm.d.A, no = h->c->n_out;
+    h->c->wore = true;
+    // current_logpost at the initial values (:1024-1028), Cholesky factors, first proposal
+    if (launch_surv_post(h, h->c->d_par + pl.cur, 1)) { h->c->wore = false; return 1; }
+    if (launch_finalize(h, 1)) { h->c->wore = false; return 1; }
+    for (int k = 0; k < h->c->total_iters; ++k) {
+        if (launch_surv_post(h, h->c->d_par + pl.prop, 1) || launch_finalize(h, 0)) { h->c->wore = false; return 1; }
+        h->c->iter_host += 1;
+    }
+    h->c->wore = false;
+    CU(cudaStreamSynchronize(h->c->stream));
+    Ctl c;
+    CU(cudaMemcpy(&c, h->c->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    if (c.error) return fail("jmb_lap_rwm_woRE: proposal covariance is not positive definite");
+    const FinalizeArgs& fa = h->c->fa;
+    auto d2h = [&](double* dst, const double* src, size_t len) -> cudaError_t {
+        if (!dst || len == 0) return cudaSuccess;
+        return cudaMemcpy(dst, src, sizeof(double) * len, cudaMemcpyDeviceToHost);
+    };
+    CU(d2h(out->Bs_gammas, fa.o_Bs, (size_t)B * no)); CU(d2h(out->gammas, fa.o_g, (size_t)p * no));
+    CU(d2h(out->alphas, fa.o_a, (size_t)A * no)); CU(d2h(out->phi_gammas, fa.o_phi_g, (size_t)p * no));
+    CU(d2h(out->phi_alphas, fa.o_phi_a, (size_t)A * no)); CU(d2h(out->tau_Bs_gammas, fa.o_tau_Bs, no));
+    CU(d2h(out->tau_gammas, fa.o_tau_g, no)); CU(d2h(out->tau_alphas, fa.o_tau_a, no));
+    CU(d2h(logPost, fa.o_lw, no));
+    CU(d2h(out->sigma_surv, h->c->d_par + pl.sig, 3));
+    CU(d2h(out->Sigma_Bs_gammas, h->c->d_par + pl.S_Bs, (size_t)B * B));
+    CU(d2h(out->Sigma_gammas, h->c->d_par + pl.S_g, (size_t)p * p));
+    CU(d2h(out->Sigma_alphas, h->c->d_par + pl.S_a, (size_t)A * A));
+    CU(d2h(out->trace_surv, h->c->o_trace, 2 * (size_t)h->c->iter_host));
+    if (out->accept_surv) out->accept_surv[0] = (double)c.accept_s_total / std::max(h->c->iter_host, 1);
     return 0;
 }
 

@@ -29,6 +29,7 @@ struct ParamLayout {
     int S_Bs, S_g, S_a;             // covariance matrices
     int H_Bs, H_g, H_a;             // their upper Cholesky factors
     int mean_Bs, Tau_Bs, mean_g, mean_a;  // priors
+    int cur_lp;                     // carried current_logpost of the woRE flavour
     int block_par;                  // [P * n_block] states of the current block (adaptCov)
     int sums;                       // [3] reduced partial sums (multi-GPU path)
     int total;

@@ -301,6 +301,9 @@ struct FinalizeArgs {
     double* my_mbox;          // this rank's own mailbox: [slots][2][nranks][4] (3 sums + stamp)
     int nranks, rank, slot;
     unsigned long long stamp; // strictly increasing per slot; parity selects the mailbox half
+    // lap_rwm_C_woRE flavour (use_reduced == 3): sp_out[0] - sp_out[1] is the data term at the proposal
+    // (phase 1: at the initial values); the current log-posterior is carried in par[pl.cur_lp]
+    int wore; const double* sp_out;
     // outputs of kept iterations (device buffers laid out like jmb_chain_out)
     double* o_Bs; double* o_g; double* o_a; double* o_phi_g; double* o_phi_a; double* o_tau_Bs;
     double* o_tau_g; double* o_tau_a; double* o_tau_td; double* o_lw; double* trace;
@@ -355,6 +358,13 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
             if (e) a.ctl->error = 2;
         }
         __syncthreads();
+        if (a.wore && tid == 0) {     // current_logpost at the initial values: logPosterior_woRE, :898-914,1024-1028
+            const double* cur = par + pl.cur;
+            par[pl.cur_lp] = (a.sp_out[0] - a.sp_out[1])
+                - 0.5 * par[pl.tau_Bs] * quad_form_dev(cur, par + pl.mean_Bs, par + pl.Tau_Bs, B)
+                - 0.5 * par[pl.tau_g] * quad_form_dev(cur + B, par + pl.mean_g, par + pl.Tau_g, p)
+                - 0.5 * par[pl.tau_a] * quad_form_dev(cur + B + p, par + pl.mean_a, par + pl.Tau_a, A);
+        }
         make_proposal(mm, pl, cc, par, a.ctl->iter, tid, blockDim.x, s_z);
         if (a.use_smem) {
             __syncthreads();
@@ -366,6 +376,8 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     // ---- deterministic reduction of the per-CTA partials ----
     if (a.use_reduced == 1) {
         if (tid < 3) s_tot[tid] = gpar[pl.sums + tid];
+    } else if (a.use_reduced == 3) {
+        if (tid == 0) { s_tot[0] = 0.0; s_tot[1] = a.sp_out[0] - a.sp_out[1]; s_tot[2] = 0.0; }
     } else {
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
         for (int i = tid; i < a.n_partials; i += 128) { t0 += a.partials[i * 3]; t1 += a.partials[i * 3 + 1]; t2 += a.partials[i * 3 + 2]; }
@@ -441,15 +453,19 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         const int iter = ctl->iter;
         double* cur = par + pl.cur;
         double* prop = par + pl.prop;
-        if (a.trace) { a.trace[2LL * iter] = s_tot[0]; a.trace[2LL * iter + 1] = s_tot[1]; }
+        if (a.trace && !a.wore) { a.trace[2LL * iter] = s_tot[0]; a.trace[2LL * iter + 1] = s_tot[1]; }
         // ---- survival-block RWM (:727-770); tau = 1 for Bs_gammas (reference behaviour) ----
         const double tau_g = par[pl.tau_g], tau_a = par[pl.tau_a];
         double qc[3] = {0.0, 0.0, 0.0}, qp[3] = {0.0, 0.0, 0.0}, rawc = 0.0, rawp = 0.0;
         for (int j = 0; j < B; ++j) { qc[0] += s_q[0][j]; qp[0] += s_q[1][j]; rawc += s_q[2][j]; rawp += s_q[3][j]; }
         for (int j = B; j < B + p; ++j) { qc[1] += s_q[0][j]; qp[1] += s_q[1][j]; }
         for (int j = B + p; j < mm.P; ++j) { qc[2] += s_q[0][j]; qp[2] += s_q[1][j]; }
-        const double cur_lp = s_tot[0] - 0.5 * qc[0] - 0.5 * tau_g * qc[1] - 0.5 * tau_a * qc[2];
-        const double new_lp = s_tot[1] - 0.5 * qp[0] - 0.5 * tau_g * qp[1] - 0.5 * tau_a * qp[2];
+        // lap_rwm_C: tau = 1 for Bs_gammas (:727,753); woRE: the sampled tau_Bs_gammas (:911) and a carried
+        // current value that is only refreshed on acceptance (:1031-1053)
+        const double tBs = a.wore ? par[pl.tau_Bs] : 1.0;
+        const double cur_lp = a.wore ? par[pl.cur_lp] : s_tot[0] - 0.5 * qc[0] - 0.5 * tau_g * qc[1] - 0.5 * tau_a * qc[2];
+        const double new_lp = s_tot[1] - 0.5 * tBs * qp[0] - 0.5 * tau_g * qp[1] - 0.5 * tau_a * qp[2];
+        if (a.wore && a.trace) { a.trace[2LL * iter] = cur_lp; a.trace[2LL * iter + 1] = new_lp; }
         const double lu = log_unif(cc.seed, cc.chain_id, 0u, (uint32_t)iter, 0xFFFFFFFFu, ST_SURV);
         ctl->last_accept = 0;
         double raw_Bs = rawc;
@@ -458,6 +474,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
             ctl->accept_s_block += 1; ctl->accept_s_total += 1;
             ctl->last_accept = 1;
             raw_Bs = rawp;
+            if (a.wore) par[pl.cur_lp] = new_lp;
         }
         if (cc.adaptCov) for (int j = 0; j < mm.P; ++j) gpar[pl.block_par + j + ctl->i * mm.P] = cur[j];
         // ---- Gibbs draws of the precisions (:776-834) ----
@@ -510,7 +527,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
             for (int j = 0; j < A; ++j) { a.o_a[j + ko * A] = alp[j]; a.o_phi_a[j + ko * A] = par[pl.phi_a + j]; }
             a.o_tau_Bs[ko] = par[pl.tau_Bs]; a.o_tau_g[ko] = par[pl.tau_g]; a.o_tau_a[ko] = par[pl.tau_a];
             for (int j = 0; j < cc.n_td; ++j) a.o_tau_td[j + ko * cc.n_td] = par[pl.tau_td + j];
-            a.o_lw[ko] = -s_tot[2];                                  // log_weightsREF :359-369,847
+            a.o_lw[ko] = a.wore ? par[pl.cur_lp] : -s_tot[2];        // log_weightsREF :359-369,847 / out_logPost :1107
             ctl->keep_iterator += 1; ctl->check_iterator += 1;
         }
         // ---- block end: adapt the global scales (:853-867) ----
@@ -620,6 +637,7 @@ struct SurvPostArgs {
     const double* theta;     // [P] Bs_gammas | gammas | alphas
     double* partials;        // [gridDim.x][P + 2]
     int n, subjects_per_cta;
+    int value_only;          // skip the score sums (woRE chain: only the log-posterior is needed)
 };
 
 template <int G>
@@ -665,6 +683,7 @@ jmb_surv_post_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant
         const double Hsum = group_sum<G>(Int, gmask);
         const double lh = __shfl_sync(gmask, lin, 0, G);
         if (lane == 0) { acc[0] += event * lh; acc[1] += Hsum; }
+        if (a.value_only) continue;
         // score sums: baseline-hazard band, lane by lane in fixed order
         for (int l = 1; l <= K; ++l) {
             const int offl = __shfl_sync(gmask, off, l, G);

@@ -741,3 +741,152 @@ void orc_gradient_logPosterior(double temp, int64_t ns, int32_t B, int32_t p, in
     out[o] = tauBs * (logPrior(Bs, mean_Bs, Tau_Bs, B, 1.0) + (A_tauBs - 1.0) / tauBs - B_tauBs);   /* :44 */
     free(Int);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * lap_rwm_C_woRE / lap_rwm_C_woRE_nogammas: src/fast_LAPRWM.cpp:934-1139, 1142-1297
+ * (update_RE = FALSE: survival block only, on fixed Wlong / Wlongs).  Differences from lap_rwm_C
+ * that are reproduced: the sampled tau_Bs_gammas IS applied in the prior (:911); current_logpost is
+ * carried and only refreshed on acceptance (so it keeps the precisions it was computed with);
+ * no td-effects and no double-gamma branch; output logPost instead of logWeights.
+ * trace (optional): [2 * iter] = current_logpost before the step, [2 * iter + 1] = new_logpost.
+ * ---------------------------------------------------------------------------------------- */
+int orc_lap_rwm_woRE(const orc_data* d, const double* Wlong, const double* Wlongs, const orc_priors* pr,
+                     const orc_control* ct, const orc_chain_in* in, orc_chain_out* out, double* logPost) {
+    const int32_t n = d->n, K = d->K, A = d->n_alphas, B = d->n_Bs, p = d->n_gammas;
+    const int64_t ns = (int64_t)n * K;
+    const int total_it = ct->n_iter + ct->n_burnin;
+    const int its = (int)ceil((double)total_it / ct->n_block);
+    const int n_out = (int)floor((double)ct->n_iter / ct->n_thin);
+    const int start_cov_update = (int)floor((double)ct->n_burnin / ct->n_block) - 1;
+    int n_keep = 0;
+    for (int v = ct->n_burnin + 1; v <= total_it; v += ct->n_thin) ++n_keep;
+    {
+        int hits = 0;
+        for (int v = ct->n_burnin + 1; v <= total_it && v <= its * ct->n_block - 1; v += ct->n_thin) ++hits;
+        if (hits > n_out) return 3;
+    }
+    const uint32_t seed = ct->seed, chain = ct->chain_id;
+    const int P = B + p + A;
+    double* Bs = (double*)malloc(sizeof(double) * 2 * (P + 1));
+    double *gam = Bs + B, *alp = gam + p, *nBs = alp + A + 1, *ngam = nBs + B, *nalp = ngam + p;
+    memcpy(Bs, in->Bs_gammas, sizeof(double) * B);
+    if (p) memcpy(gam, in->gammas, sizeof(double) * p);
+    memcpy(alp, in->alphas, sizeof(double) * A);
+    double tau_Bs = in->tau_Bs_gammas[0], tau_g = in->tau_gammas, tau_a = in->tau_alphas;
+    double* phi_g = (double*)malloc(sizeof(double) * (p + 1));
+    double* phi_a = (double*)malloc(sizeof(double) * (A + 1));
+    for (int j = 0; j < p; ++j) phi_g[j] = in->phi_gammas[j];
+    for (int j = 0; j < A; ++j) phi_a[j] = in->phi_alphas[j];
+    double* Tau_g = (double*)malloc(sizeof(double) * (p * p + 1));
+    double* Tau_a = (double*)malloc(sizeof(double) * (A * A + 1));
+    memcpy(Tau_g, pr->Tau_gammas, sizeof(double) * p * p);
+    memcpy(Tau_a, pr->Tau_alphas, sizeof(double) * A * A);
+    const double Apost_tau_Bs = pr->A_tau_Bs_gammas + 0.5 * pr->rank_Tau_Bs_gammas;
+    const double Apost_tau_g = pr->A_tau_gammas + 0.5 * pr->rank_Tau_gammas, Apost_phi_g = pr->A_phi_gammas + 0.5;
+    const double Apost_tau_a = pr->A_tau_alphas + 0.5 * pr->rank_Tau_alphas, Apost_phi_a = pr->A_phi_alphas + 0.5;
+    double sig_Bs = in->sigma_Bs_gammas, sig_g = in->sigma_gammas, sig_a = in->sigma_alphas;
+    double* S_Bs = (double*)malloc(sizeof(double) * (B * B + 1));
+    double* S_g = (double*)malloc(sizeof(double) * (p * p + 1));
+    double* S_a = (double*)malloc(sizeof(double) * (A * A + 1));
+    memcpy(S_Bs, in->Sigma_Bs_gammas, sizeof(double) * B * B);
+    if (p) memcpy(S_g, in->Sigma_gammas, sizeof(double) * p * p);
+    memcpy(S_a, in->Sigma_alphas, sizeof(double) * A * A);
+    double* H_Bs = (double*)malloc(sizeof(double) * (B * B + 1));
+    double* H_g = (double*)malloc(sizeof(double) * (p * p + 1));
+    double* H_a = (double*)malloc(sizeof(double) * (A * A + 1));
+    double* lh = (double*)malloc(sizeof(double) * n);
+    double* lin = (double*)malloc(sizeof(double) * ns);
+    double* block_par = (double*)malloc(sizeof(double) * P * ct->n_block);
+
+#define WORE_LOGPOST(BS, GA, AL, RES)                                                            \
+    do {   /* logPosterior_woRE :898-914 */                                                       \
+        for (int32_t i_ = 0; i_ < n; ++i_) lh[i_] = 0.0;                                           \
+        gemv_acc(d->W1, n, B, BS, lh); gemv_acc(d->W2, n, p, GA, lh); gemv_acc(Wlong, n, A, AL, lh); \
+        for (int64_t r_ = 0; r_ < ns; ++r_) lin[r_] = 0.0;                                         \
+        gemv_acc(d->W1s, ns, B, BS, lin); gemv_acc(d->W2s, ns, p, GA, lin); gemv_acc(Wlongs, ns, A, AL, lin); \
+        double s1_ = 0.0, s2_ = 0.0;                                                               \
+        for (int32_t i_ = 0; i_ < n; ++i_) s1_ += d->event[i_] * lh[i_];                           \
+        for (int64_t r_ = 0; r_ < ns; ++r_) s2_ += d->Pw[r_] * exp(lin[r_]);                       \
+        RES = s1_ - s2_ + logPrior(BS, pr->mean_Bs_gammas, pr->Tau_Bs_gammas, B, tau_Bs) +         \
+              logPrior(GA, pr->mean_gammas, Tau_g, p, tau_g) + logPrior(AL, pr->mean_alphas, Tau_a, A, tau_a); \
+    } while (0)
+
+    double current_logpost;
+    WORE_LOGPOST(Bs, gam, alp, current_logpost);
+    int keep_iterator = 0, check_iterator = 0, rc = 0;
+    for (int it = 0; it < its; ++it) {
+        double accept = 0.0;
+        if (chol_upper(S_Bs, B, H_Bs) || (p && chol_upper(S_g, p, H_g)) || chol_upper(S_a, A, H_a)) { rc = 2; break; }
+        for (int i = 0; i < ct->n_block; ++i) {
+            const uint32_t iter = (uint32_t)(it * ct->n_block + i);
+            double zz[2 * ((JMB_ORC_PMAX + 1) / 2)];
+            for (int s2 = 0; s2 < (P + 1) / 2; ++s2) orc_rnorm_pair(seed, chain, 0u, iter, (uint32_t)s2, ST_SURV, zz + 2 * s2);
+            for (int j = 0; j < B; ++j) { double pj = 0.0; for (int l = 0; l <= j; ++l) pj += zz[l] * H_Bs[l + j * B]; nBs[j] = Bs[j] + sqrt(sig_Bs) * pj; }
+            for (int j = 0; j < p; ++j) { double pj = 0.0; for (int l = 0; l <= j; ++l) pj += zz[B + l] * H_g[l + j * p]; ngam[j] = gam[j] + sqrt(sig_g) * pj; }
+            for (int j = 0; j < A; ++j) { double pj = 0.0; for (int l = 0; l <= j; ++l) pj += zz[B + p + l] * H_a[l + j * A]; nalp[j] = alp[j] + sqrt(sig_a) * pj; }
+            double new_logpost;
+            WORE_LOGPOST(nBs, ngam, nalp, new_logpost);
+            if (out->trace_surv) { out->trace_surv[2 * (int64_t)iter] = current_logpost; out->trace_surv[2 * (int64_t)iter + 1] = new_logpost; }
+            uint32_t r[4];
+            orc_philox4x32(seed, chain, 0u, iter, 0xFFFFFFFFu, ST_SURV, r);
+            if (log(orc_u01(r[0], r[1])) < new_logpost - current_logpost) {
+                accept += 1.0;
+                memcpy(Bs, nBs, sizeof(double) * B);
+                if (p) memcpy(gam, ngam, sizeof(double) * p);
+                memcpy(alp, nalp, sizeof(double) * A);
+                current_logpost = new_logpost;
+            }
+            for (int j = 0; j < p; ++j) block_par[B + j + i * P] = gam[j];
+            for (int j = 0; j < A; ++j) block_par[B + p + j + i * P] = alp[j];
+            for (int j = 0; j < B; ++j) block_par[j + i * P] = Bs[j];
+            uint32_t draw = 0;
+            tau_Bs = clampd(orc_rgamma(seed, chain, draw++, iter, Apost_tau_Bs, 1.0 / (pr->B_tau_Bs_gammas + 0.5 * quad_form(Bs, pr->Tau_Bs_gammas, B))), ct->eps2, ct->eps3);
+            if (pr->shrink_gammas) {
+                for (int k1 = 0; k1 < p; ++k1) {
+                    phi_g[k1] = clampd(orc_rgamma(seed, chain, draw++, iter, Apost_phi_g, 1.0 / (pr->B_phi_gammas + 0.5 * tau_g * gam[k1] * gam[k1])), ct->eps2, ct->eps3);
+                    Tau_g[k1 + k1 * p] = phi_g[k1];
+                }
+                tau_g = clampd(orc_rgamma(seed, chain, draw++, iter, Apost_tau_g, 1.0 / (pr->B_tau_gammas + 0.5 * quad_form(gam, Tau_g, p))), ct->eps2, ct->eps3);
+            }
+            if (pr->shrink_alphas) {
+                for (int k2 = 0; k2 < A; ++k2) {
+                    phi_a[k2] = clampd(orc_rgamma(seed, chain, draw++, iter, Apost_phi_a, 1.0 / (pr->B_phi_alphas + 0.5 * tau_a * alp[k2] * alp[k2])), ct->eps2, ct->eps3);
+                    Tau_a[k2 + k2 * A] = phi_a[k2];
+                }
+                tau_a = clampd(orc_rgamma(seed, chain, draw++, iter, Apost_tau_a, 1.0 / (pr->B_tau_alphas + 0.5 * quad_form(alp, Tau_a, A))), ct->eps2, ct->eps3);
+            }
+            if (check_iterator < n_keep && keep_iterator < n_out && (int)iter == ct->n_burnin + 1 + check_iterator * ct->n_thin) {
+                int ko = keep_iterator;
+                memcpy(out->Bs_gammas + ko * B, Bs, sizeof(double) * B);
+                if (p) { memcpy(out->gammas + ko * p, gam, sizeof(double) * p); memcpy(out->phi_gammas + ko * p, phi_g, sizeof(double) * p); }
+                memcpy(out->alphas + ko * A, alp, sizeof(double) * A);
+                memcpy(out->phi_alphas + ko * A, phi_a, sizeof(double) * A);
+                out->tau_Bs_gammas[ko] = tau_Bs; out->tau_gammas[ko] = tau_g; out->tau_alphas[ko] = tau_a;
+                if (logPost) logPost[ko] = current_logpost;
+                ++keep_iterator; ++check_iterator;
+            }
+        }
+        double g1 = pow((double)(it + 1), -ct->c1), g2 = ct->c0 * g1, rate = accept / ct->n_block;
+        sig_Bs = bounds_sigma(exp(log(sig_Bs) + g2 * (rate - ct->target_acc)), ct->eps1, ct->eps3);
+        sig_g = bounds_sigma(exp(log(sig_g) + g2 * (rate - ct->target_acc)), ct->eps1, ct->eps3);
+        sig_a = bounds_sigma(exp(log(sig_a) + g2 * (rate - ct->target_acc)), ct->eps1, ct->eps3);
+        if (ct->adaptCov && it > start_cov_update) {
+            double* blk = (double*)malloc(sizeof(double) * (P + 1) * ct->n_block);
+            for (int i = 0; i < ct->n_block; ++i) for (int j = 0; j < B; ++j) blk[j + i * B] = block_par[j + i * P];
+            adapt_cov(S_Bs, B, blk, ct->n_block, g1, ct->eps2, ct->eps3);
+            for (int i = 0; i < ct->n_block; ++i) for (int j = 0; j < p; ++j) blk[j + i * p] = block_par[B + j + i * P];
+            adapt_cov(S_g, p, blk, ct->n_block, g1, ct->eps2, ct->eps3);
+            for (int i = 0; i < ct->n_block; ++i) for (int j = 0; j < A; ++j) blk[j + i * A] = block_par[B + p + j + i * P];
+            adapt_cov(S_a, A, blk, ct->n_block, g1, ct->eps2, ct->eps3);
+            free(blk);
+        }
+    }
+#undef WORE_LOGPOST
+    out->sigma_surv[0] = sig_Bs; out->sigma_surv[1] = sig_g; out->sigma_surv[2] = sig_a;
+    memcpy(out->Sigma_Bs_gammas, S_Bs, sizeof(double) * B * B);
+    if (p) memcpy(out->Sigma_gammas, S_g, sizeof(double) * p * p);
+    memcpy(out->Sigma_alphas, S_a, sizeof(double) * A * A);
+    free(Bs); free(phi_g); free(phi_a); free(Tau_g); free(Tau_a); free(S_Bs); free(S_g); free(S_a);
+    free(H_Bs); free(H_g); free(H_a); free(lh); free(lin); free(block_par);
+    return rc;
+}

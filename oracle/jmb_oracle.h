@@ -129,6 +129,10 @@ void orc_gradient_logPosterior(double temp, int64_t ns, int32_t B, int32_t p, in
                                const double* Tau_Bs, const double* mean_g, const double* Tau_g,
                                const double* mean_a, const double* Tau_a, double tauBs,
                                double A_tauBs, double B_tauBs, double* out);
+/* lap_rwm_C_woRE[_nogammas] (src/fast_LAPRWM.cpp:934-1297): survival block only, fixed Wlong / Wlongs;
+ * `logPost` receives out_logPost [n_out]; out->b, logWeights, sigma_b, accept_b are not touched */
+int orc_lap_rwm_woRE(const orc_data* d, const double* Wlong, const double* Wlongs, const orc_priors* pr,
+                     const orc_control* ct, const orc_chain_in* in, orc_chain_out* out, double* logPost);
 /* Wlong (rows x A) for given b: lin_pred_matF, src/fast_LAPRWM.cpp:80-109.
  * which: 0 event-time designs, 1 quadrature designs, 2 interval quadrature designs */
 int orc_wlong(const orc_data* d, const orc_draw* w, const double* b, int which, double* out);

@@ -74,3 +74,33 @@ def lap_rwm_C(initials, Data, priors, scales, Covs, control, interval_cens=False
                                        gammas=float(bufs["sigma_surv"][1]), alphas=float(bufs["sigma_surv"][2])),
                             Sigma=dict(Bs_gammas=bufs["Sigma_Bs_gammas"], gammas=bufs["Sigma_gammas"],
                                        alphas=bufs["Sigma_alphas"])))
+
+
+def lap_rwm_C_woRE(initials, Data, priors, scales, Covs, control, Covs_b, chain_id: int = 0):
+    """lap_rwm_C_woRE / lap_rwm_C_woRE_nogammas (src/fast_LAPRWM.cpp:934-1297) on Data$Wlong / Data$Wlongs."""
+    d, k1 = _abi.marshal_data(Data, Covs_b, False)
+    pr, k3 = _abi.marshal_priors(priors)
+    ct = _abi.marshal_control(control, chain_id)
+    ini = dict(initials)
+    ini.setdefault("b", np.zeros((d.n, d.q)))
+    sc = dict(scales); sc.setdefault("b", np.zeros(d.n))
+    ci, k4 = _abi.marshal_chain_in(ini, sc, Covs)
+    total, n_out = _abi.chain_dims(control)
+    out, bufs = _abi.alloc_chain_out(1, 1, d.n_Bs, d.n_gammas, d.n_alphas, 0, n_out, total)
+    Wl = np.asfortranarray(np.asarray(Data["Wlong"], dtype=np.float64))
+    Wls = np.asfortranarray(np.asarray(Data["Wlongs"], dtype=np.float64))
+    logPost = np.zeros(max(n_out, 1))
+    L = lib()
+    L.jmbref_lap_rwm_woRE.argtypes = [C.POINTER(_abi.JmbData), _abi.c_double_p, _abi.c_double_p, C.POINTER(_abi.JmbPriors),
+                     C.POINTER(_abi.JmbControl), C.POINTER(_abi.JmbChainIn), C.POINTER(_abi.JmbChainOut), _abi.c_double_p]
+    rc = L.jmbref_lap_rwm_woRE(C.byref(d), Wl.ctypes.data_as(_abi.c_double_p), Wls.ctypes.data_as(_abi.c_double_p), C.byref(pr),
+              C.byref(ct), C.byref(ci), C.byref(out), logPost.ctypes.data_as(_abi.c_double_p))
+    if rc != 0:
+        raise RuntimeError(f"jmbref_lap_rwm_woRE failed with code {rc}")
+    mcmc = {k: bufs[k] for k in ("Bs_gammas", "gammas", "alphas", "phi_gammas", "phi_alphas", "tau_Bs_gammas",
+                                 "tau_gammas", "tau_alphas")}
+    return dict(mcmc=mcmc, logPost=logPost[:n_out],
+                scales=dict(sigma=dict(Bs_gammas=float(bufs["sigma_surv"][0]), gammas=float(bufs["sigma_surv"][1]),
+                                       alphas=float(bufs["sigma_surv"][2])),
+                            Sigma=dict(Bs_gammas=bufs["Sigma_Bs_gammas"], gammas=bufs["Sigma_gammas"], alphas=bufs["Sigma_alphas"])),
+                extras=dict(trace_surv=bufs.get("trace_surv")))

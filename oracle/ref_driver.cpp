@@ -21,6 +21,8 @@ using namespace Rcpp;
 // ---- the reference's exported functions (defined in the reference sources) -------------------
 List lap_rwm_C(List initials, List Data, List priors, List scales, List Covs, List control,
                bool interval_cens, bool multiState);
+List lap_rwm_C_woRE(List initials, List Data, List priors, List scales, List Covs, List control);
+List lap_rwm_C_woRE_nogammas(List initials, List Data, List priors, List scales, List Covs, List control);
 double logPosterior(double temp, arma::vec event, arma::uvec idGK_fast, arma::mat W1, arma::mat W1s, arma::vec Bs_gammas,
                     arma::mat W2, arma::mat W2s, arma::vec gammas, arma::mat Wlong, arma::mat Wlongs, arma::vec alphas,
                     arma::vec Pw, arma::vec mean_Bs_gammas, arma::mat Tau_Bs_gammas, arma::vec mean_gammas,
@@ -73,15 +75,20 @@ void provider_fill(int kind, unsigned long long rows, unsigned long long cols, d
     }
     // randn: per outer block n calls of (n_block x q) for mvrnorm_cube (:123-136,658), then
     // (n_block x B), (n_block x p), (n_block x A) for the survival proposals (:659-661)
-    const long long per_block = (long long)g.n + 3;
-    const long long blk = g.randn_calls / per_block, pos = g.randn_calls % per_block;
+    // g.n == -1: lap_rwm_C_woRE_nogammas draws two proposal blocks (Bs_gammas, alphas) per outer block
+    const bool nogam = g.n < 0;
+    const long long nsub = nogam ? 0 : g.n;
+    const long long per_block = nsub + (nogam ? 2 : 3);
+    const long long blk = g.randn_calls / per_block;
+    long long pos = g.randn_calls % per_block;
+    if (nogam && pos == 1) pos = 2;          // second call = alphas
     for (unsigned long long c = 0; c < cols; ++c)
         for (unsigned long long r2 = 0; r2 < rows; ++r2) {
             const uint32_t iter = (uint32_t)(blk * g.n_block + (long long)r2);
             double v;
-            if (pos < g.n) v = normal_at((uint32_t)(g.offset + pos), iter, (int)c, ST_B_PROP);
-            else if (pos == g.n) v = normal_at(0u, iter, (int)c, ST_SURV);
-            else if (pos == g.n + 1) v = normal_at(0u, iter, g.B + (int)c, ST_SURV);
+            if (pos < nsub) v = normal_at((uint32_t)(g.offset + pos), iter, (int)c, ST_B_PROP);
+            else if (pos == nsub) v = normal_at(0u, iter, (int)c, ST_SURV);
+            else if (pos == nsub + 1) v = normal_at(0u, iter, g.B + (int)c, ST_SURV);
             else v = normal_at(0u, iter, g.B + g.p + (int)c, ST_SURV);
             out[r2 + c * rows] = v;
         }
@@ -258,4 +265,62 @@ extern "C" void jmbref_gradient_logPosterior(double temp, int64_t ns, int32_t B,
                                         V(mean_Bs, B), M(Tau_Bs, B, B), V(mean_g, p), M(Tau_g, p, p), V(mean_a, A), M(Tau_a, A, A),
                                         tauBs, A_tauBs, B_tauBs);
     for (arma::uword i = 0; i < r.n_elem; ++i) out[i] = r.mem[i];
+}
+
+// lap_rwm_C_woRE / lap_rwm_C_woRE_nogammas (src/fast_LAPRWM.cpp:934-1297)
+extern "C" int jmbref_lap_rwm_woRE(const orc_data* d, const double* Wlong, const double* Wlongs, const orc_priors* pr,
+                                   const orc_control* ct, const orc_chain_in* in, orc_chain_out* out, double* logPost) {
+    try {
+        const int n = d->n, B = d->n_Bs, p = d->n_gammas, A = d->n_alphas, K = d->K;
+        const arma::uword ns = (arma::uword)n * K;
+        List Data, initials, priors, scales, Covs, control;
+        Data.push("event", num_vec(d->event, n)); Data.push("idGK_fast", int_vec(d->idGK_fast, n, 0));
+        Data.push("W1", num_mat(d->W1, n, B)); Data.push("W1s", num_mat(d->W1s, ns, B));
+        Data.push("W2", num_mat(d->W2, n, p)); Data.push("W2s", num_mat(d->W2s, ns, p));
+        Data.push("Wlong", num_mat(Wlong, n, A)); Data.push("Wlongs", num_mat(Wlongs, ns, A)); Data.push("Pw", num_vec(d->Pw, ns));
+        initials.push("Bs_gammas", num_vec(in->Bs_gammas, B)); initials.push("gammas", num_vec(in->gammas, p));
+        initials.push("alphas", num_vec(in->alphas, A)); initials.push("phi_gammas", num_vec(in->phi_gammas, p));
+        initials.push("phi_alphas", num_vec(in->phi_alphas, A)); initials.push("tau_Bs_gammas", scalar(in->tau_Bs_gammas[0]));
+        initials.push("tau_gammas", scalar(in->tau_gammas)); initials.push("tau_alphas", scalar(in->tau_alphas));
+        priors.push("mean_Bs_gammas", num_vec(pr->mean_Bs_gammas, B)); priors.push("Tau_Bs_gammas", num_mat(pr->Tau_Bs_gammas, B, B));
+        priors.push("mean_gammas", num_vec(pr->mean_gammas, p)); priors.push("Tau_gammas", num_mat(pr->Tau_gammas, p, p));
+        priors.push("mean_alphas", num_vec(pr->mean_alphas, A)); priors.push("Tau_alphas", num_mat(pr->Tau_alphas, A, A));
+#define SC(name) priors.push(#name, scalar((double)pr->name))
+        SC(A_tau_Bs_gammas); SC(B_tau_Bs_gammas); SC(rank_Tau_Bs_gammas); SC(shrink_gammas); SC(A_tau_gammas); SC(B_tau_gammas);
+        SC(rank_Tau_gammas); SC(A_phi_gammas); SC(B_phi_gammas); SC(shrink_alphas); SC(A_tau_alphas);
+        SC(B_tau_alphas); SC(rank_Tau_alphas); SC(A_phi_alphas); SC(B_phi_alphas);
+#undef SC
+        scales.push("Bs_gammas", scalar(in->sigma_Bs_gammas)); scales.push("gammas", scalar(in->sigma_gammas));
+        scales.push("alphas", scalar(in->sigma_alphas));
+        Covs.push("Bs_gammas", num_mat(in->Sigma_Bs_gammas, B, B)); Covs.push("gammas", num_mat(in->Sigma_gammas, p, p));
+        Covs.push("alphas", num_mat(in->Sigma_alphas, A, A));
+#define CT(name) control.push(#name, scalar((double)ct->name))
+        CT(n_iter); CT(n_burnin); CT(n_block); CT(n_thin); CT(target_acc); CT(eps1); CT(eps2); CT(eps3); CT(c0); CT(c1); CT(adaptCov);
+#undef CT
+        g = Provider();
+        g.seed = ct->seed; g.chain = ct->chain_id; g.n = 0; g.B = B; g.p = p; g.A = A; g.n_block = ct->n_block;
+        g.draws_per_iter = 1 + (pr->shrink_gammas ? p + 1 : 0) + (pr->shrink_alphas ? A + 1 : 0);
+        jmbref_fill = provider_fill; jmbref_rgamma = provider_rgamma;
+        List res;
+        if (p > 0) res = lap_rwm_C_woRE(initials, Data, priors, scales, Covs, control);
+        else {
+            // the _nogammas flavour draws only two proposal blocks per outer block
+            g.n = -1;
+            res = lap_rwm_C_woRE_nogammas(initials, Data, priors, scales, Covs, control);
+        }
+        List mc = as<List>(res["mcmc"]);
+        copy_out(mc["Bs_gammas"].v, out->Bs_gammas); copy_out(mc["alphas"].v, out->alphas);
+        copy_out(mc["phi_alphas"].v, out->phi_alphas); copy_out(mc["tau_Bs_gammas"].v, out->tau_Bs_gammas);
+        copy_out(mc["tau_alphas"].v, out->tau_alphas);
+        if (p > 0) { copy_out(mc["gammas"].v, out->gammas); copy_out(mc["phi_gammas"].v, out->phi_gammas); copy_out(mc["tau_gammas"].v, out->tau_gammas); }
+        copy_out(res["logPost"].v, logPost);
+        List sc = as<List>(res["scales"]); List sg = as<List>(sc["sigma"]); List Sg = as<List>(sc["Sigma"]);
+        if (out->sigma_surv) { out->sigma_surv[0] = as<double>(sg["Bs_gammas"]); out->sigma_surv[1] = p > 0 ? as<double>(sg["gammas"]) : in->sigma_gammas; out->sigma_surv[2] = as<double>(sg["alphas"]); }
+        copy_out(Sg["Bs_gammas"].v, out->Sigma_Bs_gammas); copy_out(Sg["alphas"].v, out->Sigma_alphas);
+        if (p > 0) copy_out(Sg["gammas"].v, out->Sigma_gammas);
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return 1;
+    }
 }

@@ -69,10 +69,52 @@ def surv_case():
     return dict(logPosterior=np.array([lp]), score=sc, tau=np.array([tau]), temp=np.array([temp]))
 
 
+WORE_CASES = {
+    # name: (config, n, control overrides, prior overrides, drop gammas, chain id)
+    "wore_config3": ("config3", 150, dict(n_burnin=30, n_iter=20, n_block=10, n_thin=5), {}, False, 3),
+    "wore_config2_shrink_adapt": ("config2", 150, dict(n_burnin=30, n_iter=20, n_block=10, n_thin=5, adaptCov=True),
+                                  dict(shrink_gammas=True, shrink_alphas=True), False, 4),
+    "wore_config3_nogammas": ("config3", 120, dict(n_burnin=20, n_iter=20, n_block=10, n_thin=5), dict(shrink_alphas=True), True, 5),
+}
+
+
+def wore_inputs(name):
+    """Inputs of a woRE case: Wlong / Wlongs at the initial b (designMatLong, R/mvJointModelBayes.R:787-790)."""
+    cfg, n, ctl_over, pr_over, nogam, chain = WORE_CASES[name]
+    c = make_cohort(cfg, n=n)
+    D = dict(c["Data"])
+    b = np.asarray(c["inits"]["b"])
+    D["Wlong"], D["Wlongs"] = np_twin.wlong(D, b, 0), np_twin.wlong(D, b, 1)
+    pr = dict(c["priors"]); pr.update(pr_over)
+    ini, cv = dict(c["inits"]), dict(c["Covs"])
+    if nogam:
+        K = len(D["Pw"]) // n
+        D["W2"], D["W2s"] = np.zeros((n, 0), order="F"), np.zeros((n * K, 0), order="F")
+        pr.update(mean_gammas=np.zeros(0), Tau_gammas=np.zeros((0, 0)), shrink_gammas=False)
+        ini.update(gammas=np.zeros(0), phi_gammas=np.zeros(0))
+        cv["gammas"] = np.zeros((0, 0))
+    ctl = dict(c["control"]); ctl.update(ctl_over)
+    return c, D, ini, pr, cv, ctl, chain
+
+
+def run_wore_case(name):
+    c, D, ini, pr, cv, ctl, chain = wore_inputs(name)
+    r = ref.lap_rwm_C_woRE(ini, D, pr, c["scales"], cv, ctl, c["Covs"]["b"], chain_id=chain)
+    out = {f"mcmc_{k}": v for k, v in r["mcmc"].items()}
+    out["logPost"] = r["logPost"]
+    out["sigma_surv"] = np.array([r["scales"]["sigma"][k] for k in ("Bs_gammas", "gammas", "alphas")])
+    for k in ("Bs_gammas", "gammas", "alphas"):
+        out[f"Sigma_{k}"] = r["scales"]["Sigma"][k]
+    return out
+
+
 if __name__ == "__main__":
     ref.build(force=True)
     for name in CASES:
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_case(name))
+        print("wrote", name)
+    for name in WORE_CASES:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_wore_case(name))
         print("wrote", name)
     np.savez_compressed(os.path.join(HERE, "surv_config3.npz"), **surv_case())
     print("wrote surv_config3")

@@ -142,3 +142,37 @@ def test_cuda_logposterior_and_score_match_reference_golden(cuda_lib):
     assert lp2 != lp and not np.allclose(sc2, sc)
     B, p = len(ini["Bs_gammas"]), len(ini["gammas"])
     assert np.isclose(sc2[B + p], fd, rtol=1e-5)
+
+
+# ---- lap_rwm_C_woRE / lap_rwm_C_woRE_nogammas (control$update_RE = FALSE) ---------------------------------
+def _check_wore(r, gold, rtol, nogam):
+    for k, v in r["mcmc"].items():
+        if nogam and k in ("gammas", "phi_gammas", "tau_gammas"):
+            continue
+        g = gold["mcmc_" + k]
+        assert np.allclose(np.asarray(v).reshape(g.shape), g, rtol=rtol, atol=1e-12), (k, float(np.max(np.abs(np.asarray(v).reshape(g.shape) - g))))
+    assert np.allclose(r["logPost"], gold["logPost"], rtol=rtol)
+    sg = np.array([r["scales"]["sigma"][k] for k in ("Bs_gammas", "gammas", "alphas")])
+    keep = [0, 2] if nogam else [0, 1, 2]
+    assert np.allclose(sg[keep], gold["sigma_surv"][keep], rtol=rtol)
+    for k in ("Bs_gammas", "alphas"):
+        assert np.allclose(r["scales"]["Sigma"][k], gold["Sigma_" + k], rtol=max(rtol, 1e-8), atol=1e-14), k
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.WORE_CASES))
+def test_oracle_wore_reproduces_reference_golden(oracle, name):
+    c, D, ini, pr, cv, ctl, chain = make_golden.wore_inputs(name)
+    r = oracle.lap_rwm_C_woRE(ini, D, pr, c["scales"], cv, ctl, c["Covs"]["b"], chain_id=chain)
+    _check_wore(r, _load(name), 1e-11, make_golden.WORE_CASES[name][4])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(make_golden.WORE_CASES))
+def test_cuda_wore_reproduces_reference_golden(cuda_lib, name):
+    c, D, ini, pr, cv, ctl, chain = make_golden.wore_inputs(name)
+    nogam = make_golden.WORE_CASES[name][4]
+    Dfit = dict(c["Data"]) if not nogam else D        # the fit's designs (W2 dropped for the _nogammas flavour)
+    with cuda_lib.Fit(Dfit if not nogam else D, c["Covs"]["b"], False) as fit:
+        fit.set_wlong(D["Wlong"], D["Wlongs"])
+        r = fit.lap_rwm_C_woRE(ini, pr, c["scales"], cv, ctl, chain_id=chain)
+    _check_wore(r, _load(name), 1e-9, nogam)
