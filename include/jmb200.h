@@ -227,6 +227,18 @@ int jmb_gradient_logPosterior(jmb_handle h, double temp, const double* Bs_gammas
 int jmb_lap_rwm_woRE(jmb_handle h, const jmb_priors* priors, const jmb_control* control,
                      const jmb_chain_in* in, jmb_chain_out* out, double* logPost);
 
+/* survfitJM.mvJMbayes evaluators (R/survfitJM.mvJMbayes.R:297,372-373,393), batched over the subjects
+ * of a handle built from the new subjects' data (longitudinal rows up to last.time, quadrature designs
+ * on the interval of interest; event / W1 / W2 / ZZ / U of the event-time row are not used and may be
+ * zero; subjects may have no rows in some outcomes):
+ *   jmb_log_post_RE_svft  log_post_RE_svft (src/survfitJM_mvJMbayes.cpp:190-238): out[i] =
+ *                         log p(y_i|b_i) + log p(b_i) - H_i, parameters of the current draw
+ *   jmb_survPred_svft_2   survPred_svft_2 (:241-271): out[i] = -H_i on the handle's quadrature grid */
+int jmb_log_post_RE_svft(jmb_handle h, const double* b, const double* Bs_gammas, const double* gammas,
+                         const double* alphas, double* out);
+int jmb_survPred_svft_2(jmb_handle h, const double* b, const double* Bs_gammas, const double* gammas,
+                        const double* alphas, double* out);
+
 /* Layout facts for the parity tests: the CSR row pointers the device layout was built with
  * (must equal idL2-derived segments bit for bit) and bytes moved per subject-iteration. */
 int jmb_get_row_ptr(jmb_handle h, int outcome, int64_t* row_ptr /* [n+1] */);

@@ -61,6 +61,9 @@ def lib():
     post = [vp, C.c_double, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p, C.POINTER(_abi.JmbPriors),
             C.c_double, C.c_double, C.c_double, _abi.c_double_p]
     L.jmb_logPosterior.argtypes = post
+    sv = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p]
+    L.jmb_log_post_RE_svft.argtypes = sv
+    L.jmb_survPred_svft_2.argtypes = sv
     L.jmb_lap_rwm_woRE.argtypes = [vp, C.POINTER(_abi.JmbPriors), C.POINTER(_abi.JmbControl), C.POINTER(_abi.JmbChainIn),
                                    C.POINTER(_abi.JmbChainOut), _abi.c_double_p]
     L.jmb_gradient_logPosterior.argtypes = post
@@ -269,6 +272,25 @@ class Fit:
                                 Sigma=dict(Bs_gammas=bufs["Sigma_Bs_gammas"], gammas=bufs["Sigma_gammas"],
                                            alphas=bufs["Sigma_alphas"])),
                     extras=dict(trace_surv=bufs["trace_surv"], accept_surv=bufs["accept_surv"]))
+
+    def _svft(self, fn, b, Bs_gammas, gammas, alphas):
+        b = np.asfortranarray(np.asarray(b, dtype=np.float64))
+        g = np.ascontiguousarray(np.atleast_1d(np.asarray(gammas, dtype=np.float64)))
+        if g.size == 0:
+            g = np.zeros(1)
+        Bs = np.ascontiguousarray(np.asarray(Bs_gammas, dtype=np.float64))
+        al = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64))
+        out = np.zeros(self.n)
+        _check(fn(self._h, _dptr(b), _dptr(Bs), _dptr(g), _dptr(al), _dptr(out)))
+        return out
+
+    def log_post_RE_svft(self, b, Bs_gammas, gammas, alphas):
+        """log_post_RE_svft (src/survfitJM_mvJMbayes.cpp:190-238) for every subject of the handle."""
+        return self._svft(lib().jmb_log_post_RE_svft, b, Bs_gammas, gammas, alphas)
+
+    def survPred_svft_2(self, b, Bs_gammas, gammas, alphas):
+        """survPred_svft_2 (src/survfitJM_mvJMbayes.cpp:241-271) for every subject of the handle."""
+        return self._svft(lib().jmb_survPred_svft_2, b, Bs_gammas, gammas, alphas)
 
     def row_ptr(self, outcome: int):
         rp = np.zeros(self.n + 1, dtype=np.int64)

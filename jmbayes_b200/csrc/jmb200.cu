@@ -299,18 +299,19 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     h->rowptr.resize(O);
     for (int k = 0; k < O; ++k) {
         const long long Nk = d->N[k];
-        if (Nk < n || Nk > 2147483000LL) { delete h; return fail("jmb_create: N_k out of range"); }
+        if (Nk < 0 || Nk > 2147483000LL) { delete h; return fail("jmb_create: N_k out of range"); }
         std::vector<int>& rp = h->rowptr[k];
         rp.assign(n + 1, 0);
         const int32_t* id = d->idL[k];
         int prev = -1;
         for (long long r = 0; r < Nk; ++r) {
             int s = id[r];
-            if (s < 0 || s >= n || s < prev || s > prev + 1) { delete h; return fail("jmb_create: idL must be 0-based, grouped by subject, every subject present"); }
+            // grouped by subject; a subject without rows in an outcome is allowed (survfitJM new data:
+            // log_longF_svft skips empty outcomes, src/survfitJM_mvJMbayes.cpp:109-110)
+            if (s < 0 || s >= n || s < prev) { delete h; return fail("jmb_create: idL must be 0-based and grouped by subject"); }
             prev = s;
             rp[s + 1] += 1;
         }
-        if (prev != n - 1) { delete h; return fail("jmb_create: idL does not cover every subject"); }
         for (int i = 0; i < n; ++i) rp[i + 1] += rp[i];
         for (int i = 0; i < n; ++i)
             if (d->idL2[k][i] != rp[i + 1] - 1) { delete h; return fail("jmb_create: idL2 is not the last row of each subject"); }
@@ -1166,6 +1167,32 @@ extern "C" int jmb_lap_rwm_woRE(jmb_handle h, const jmb_priors* pr, const jmb_co
     CU(d2h(out->trace_surv, h->c->o_trace, 2 * (size_t)h->c->iter_host));
     if (out->accept_surv) out->accept_surv[0] = (double)c.accept_s_total / std::max(h->c->iter_host, 1);
     return 0;
+}
+
+// log_post_RE_svft (src/survfitJM_mvJMbayes.cpp:190-238; core :140-166): log p(y_i|b) + log p(b) - H_i per
+// subject, and survPred_svft_2 (:241-271; core :168-187): -H_i, on the handle's quadrature designs
+static int svft_eval(jmb_handle h, const double* b, const double* Bs, const double* gam, const double* alp,
+                     double* log_post, double* surv_pred) {
+    const int n = h->n;
+    std::vector<double> pyb(n), pb(n), H(n);
+    jmb_eval_out eo{};
+    eo.log_pyb = pyb.data(); eo.log_pb = pb.data(); eo.H = H.data();
+    if (jmb_eval_logpost_re(h, b, Bs, gam, alp, &eo)) return 1;
+    for (int i = 0; i < n; ++i) {
+        if (log_post) log_post[i] = (pyb[i] + (0.0 - H[i])) + pb[i];      // log_pyb + log_ptb + log_pb, :163-165
+        if (surv_pred) surv_pred[i] = 0.0 - H[i];
+    }
+    return 0;
+}
+
+extern "C" int jmb_log_post_RE_svft(jmb_handle h, const double* b, const double* Bs, const double* gam, const double* alp, double* out) {
+    if (!h || !b || !out) return fail("jmb_log_post_RE_svft: null argument");
+    return svft_eval(h, b, Bs, gam, alp, out, nullptr);
+}
+
+extern "C" int jmb_survPred_svft_2(jmb_handle h, const double* b, const double* Bs, const double* gam, const double* alp, double* out) {
+    if (!h || !b || !out) return fail("jmb_survPred_svft_2: null argument");
+    return svft_eval(h, b, Bs, gam, alp, nullptr, out);
 }
 
 extern "C" int jmb_get_row_ptr(jmb_handle h, int outcome, int64_t* row_ptr) {

@@ -104,3 +104,26 @@ def lap_rwm_C_woRE(initials, Data, priors, scales, Covs, control, Covs_b, chain_
                                        alphas=float(bufs["sigma_surv"][2])),
                             Sigma=dict(Bs_gammas=bufs["Sigma_Bs_gammas"], gammas=bufs["Sigma_gammas"], alphas=bufs["Sigma_alphas"])),
                 extras=dict(trace_surv=bufs.get("trace_surv")))
+
+
+def svft(Data, Covs_b, b, Bs_gammas, gammas, alphas):
+    """The reference's log_post_RE_svft and survPred_svft_2 (src/survfitJM_mvJMbayes.cpp:190-271) evaluated
+    one subject at a time on the per-subject slices of ``Data``; returns (log_post[n], surv_pred[n])."""
+    d, k1 = _abi.marshal_data(Data, Covs_b, False)
+    w, k2 = _abi.marshal_draw(Data, False)
+    n = d.n
+    b = np.asfortranarray(np.asarray(b, dtype=np.float64))
+    g = np.ascontiguousarray(np.atleast_1d(np.asarray(gammas, dtype=np.float64)))
+    if g.size == 0:
+        g = np.zeros(1)
+    Bs = np.ascontiguousarray(np.asarray(Bs_gammas, dtype=np.float64))
+    al = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64))
+    lp, sp = np.zeros(n), np.zeros(n)
+    P = _abi.c_double_p
+    L = lib()
+    L.jmbref_svft.argtypes = [C.POINTER(_abi.JmbData), C.POINTER(_abi.JmbDraw)] + [P] * 6
+    rc = L.jmbref_svft(C.byref(d), C.byref(w), b.ctypes.data_as(P), Bs.ctypes.data_as(P), g.ctypes.data_as(P),
+                       al.ctypes.data_as(P), lp.ctypes.data_as(P), sp.ctypes.data_as(P))
+    if rc != 0:
+        raise RuntimeError("reference svft: " + L.jmbref_last_error().decode())
+    return lp, sp

@@ -23,6 +23,8 @@ List lap_rwm_C(List initials, List Data, List priors, List scales, List Covs, Li
                bool interval_cens, bool multiState);
 List lap_rwm_C_woRE(List initials, List Data, List priors, List scales, List Covs, List control);
 List lap_rwm_C_woRE_nogammas(List initials, List Data, List priors, List scales, List Covs, List control);
+arma::vec log_post_RE_svft(arma::vec b, List Data);      // src/survfitJM_mvJMbayes.cpp:190
+arma::vec survPred_svft_2(arma::vec b, List Data);       // src/survfitJM_mvJMbayes.cpp:241
 double logPosterior(double temp, arma::vec event, arma::uvec idGK_fast, arma::mat W1, arma::mat W1s, arma::vec Bs_gammas,
                     arma::mat W2, arma::mat W2s, arma::vec gammas, arma::mat Wlong, arma::mat Wlongs, arma::vec alphas,
                     arma::vec Pw, arma::vec mean_Bs_gammas, arma::mat Tau_Bs_gammas, arma::vec mean_gammas,
@@ -318,6 +320,73 @@ extern "C" int jmbref_lap_rwm_woRE(const orc_data* d, const double* Wlong, const
         if (out->sigma_surv) { out->sigma_surv[0] = as<double>(sg["Bs_gammas"]); out->sigma_surv[1] = p > 0 ? as<double>(sg["gammas"]) : in->sigma_gammas; out->sigma_surv[2] = as<double>(sg["alphas"]); }
         copy_out(Sg["Bs_gammas"].v, out->Sigma_Bs_gammas); copy_out(Sg["alphas"].v, out->Sigma_alphas);
         if (p > 0) copy_out(Sg["gammas"].v, out->Sigma_gammas);
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return 1;
+    }
+}
+
+// log_post_RE_svft / survPred_svft_2 (src/survfitJM_mvJMbayes.cpp:190-271), called one subject at a time
+// with the per-subject Data list survfitJM.mvJMbayes builds (R/survfitJM.mvJMbayes.R:281-294,381-393)
+static List svft_subject(const orc_data* d, const orc_draw* w, int i, const double* Bs, const double* gam, const double* alp) {
+    const int O = d->n_outcomes, T = d->n_terms, K = d->K, B = d->n_Bs, p = d->n_gammas, A = d->n_alphas;
+    const arma::uword ns = (arma::uword)d->n * K;
+    List D;
+    std::vector<ValuePtr> y, Xb, Z, REi, idL, idL2, sig;
+    std::vector<std::string> fams, links, tfs;
+    for (int k = 0; k < O; ++k) {
+        const long long Nk = d->N[k];
+        const long long r1 = d->idL2[k][i], r0 = i == 0 ? 0 : (long long)d->idL2[k][i - 1] + 1, v = r1 - r0 + 1;
+        y.push_back(num_vec(d->y[k] + r0, (size_t)v)); Xb.push_back(num_vec(w->Xbetas[k] + r0, (size_t)v));
+        std::vector<double> zk((size_t)v * d->q_k[k]);
+        for (int j = 0; j < d->q_k[k]; ++j) for (long long r = 0; r < v; ++r) zk[r + j * v] = d->Z[k][r0 + r + (long long)j * Nk];
+        Z.push_back(num_mat(zk.data(), (arma::uword)v, d->q_k[k]));
+        REi.push_back(int_vec(d->RE_inds[k], d->q_k[k], 1));
+        idL.push_back(seq_vec(1, 1, v));                                   // rep(1, v)
+        idL2.push_back(seq_vec(v, 1));                                     // lapply(idL, length), R :203
+        sig.push_back(scalar(w->sigmas[k]));
+        fams.push_back(FAM[d->fams[k]]); links.push_back(LINK[d->links[k]]);
+    }
+    std::vector<ValuePtr> RE2, cols, XXsb, ZZs, Us, idTs;
+    auto rows_of = [&](const double* M, int ncol) {
+        std::vector<double> m((size_t)K * ncol);
+        for (int j = 0; j < ncol; ++j) for (int r = 0; r < K; ++r) m[r + j * K] = M[(arma::uword)i * K + r + (arma::uword)j * ns];
+        return num_mat(m.data(), K, ncol);
+    };
+    for (int t = 0; t < T; ++t) {
+        RE2.push_back(int_vec(d->RE_inds2[t], d->r_t[t], 1)); cols.push_back(int_vec(d->col_inds[t], d->u_t[t], 1));
+        XXsb.push_back(num_vec(w->XXsbetas[t] + (arma::uword)i * K, K));
+        ZZs.push_back(rows_of(d->ZZs[t], d->r_t[t])); Us.push_back(rows_of(d->Us[t], d->u_t[t]));
+        idTs.push_back(seq_vec(1, 1, K));
+        tfs.push_back(TF[d->trans_Funs[t]]);
+    }
+    D.push("Bs_gammas", num_vec(Bs, B)); D.push("gammas", num_vec(gam, p)); D.push("alphas", num_vec(alp, A));
+    D.push("y", list_of(y)); D.push("Xbetas", list_of(Xb)); D.push("Z", list_of(Z)); D.push("RE_inds", list_of(REi));
+    D.push("RE_inds2", list_of(RE2)); D.push("idL", list_of(idL)); D.push("idL2", list_of(idL2));
+    D.push("fams", str_vec(fams)); D.push("links", str_vec(links)); D.push("sigmas", list_of(sig));
+    D.push("invD", num_mat(w->invD, d->q, d->q));
+    D.push("W1s", rows_of(d->W1s, B)); D.push("W2s", rows_of(d->W2s, p));
+    D.push("XXsbetas", list_of(XXsb)); D.push("ZZs", list_of(ZZs)); D.push("Us", list_of(Us));
+    D.push("Pw", num_vec(d->Pw + (arma::uword)i * K, K));
+    long long last = K - 1;
+    auto gk = std::make_shared<Value>(); gk->kind = Value::INT; gk->ints = {last};   // which(idGK_fast) - 1, R :282
+    D.push("idGK", gk);
+    D.push("idTs", list_of(idTs)); D.push("col_inds", list_of(cols)); D.push("row_inds_Us", seq_vec(1, K));
+    D.push("trans_Funs", str_vec(tfs));
+    return D;
+}
+
+extern "C" int jmbref_svft(const orc_data* d, const orc_draw* w, const double* b, const double* Bs, const double* gam,
+                           const double* alp, double* log_post, double* surv_pred) {
+    try {
+        for (int i = 0; i < d->n; ++i) {
+            List D = svft_subject(d, w, i, Bs, gam, alp);
+            arma::vec bi(d->q);
+            for (int j = 0; j < d->q; ++j) bi.mem[j] = b[i + (size_t)j * d->n];
+            if (log_post) log_post[i] = log_post_RE_svft(bi, D).mem[0];
+            if (surv_pred) surv_pred[i] = survPred_svft_2(bi, D).mem[0];
+        }
         return 0;
     } catch (const std::exception& e) {
         g_error = e.what();

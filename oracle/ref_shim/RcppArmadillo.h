@@ -128,6 +128,7 @@ class Mat {
     eT& operator[](uword i) { static thread_local eT past_end; if (i >= n_elem) { past_end = eT(-1); return past_end; } return mem[i]; }
     const eT& operator[](uword i) const { static thread_local eT past_end; if (i >= n_elem) { past_end = eT(-1); return past_end; } return mem[i]; }
     Mat& operator+=(const Mat& x) { if (x.n_elem != n_elem) throw std::runtime_error("+=: size mismatch"); for (uword i = 0; i < n_elem; ++i) mem[i] += x.mem[i]; return *this; }
+    Mat& operator+=(eT v) { for (uword i = 0; i < n_elem; ++i) mem[i] += v; return *this; }   // scalar
     Mat& operator-=(const Mat& x) { if (x.n_elem != n_elem) throw std::runtime_error("-=: size mismatch"); for (uword i = 0; i < n_elem; ++i) mem[i] -= x.mem[i]; return *this; }
 
     static std::vector<uword> range(uword a, uword b) { std::vector<uword> v; for (uword i = a; i <= b && b != (uword)-1; ++i) v.push_back(i); return v; }

@@ -108,6 +108,29 @@ def run_wore_case(name):
     return out
 
 
+def svft_inputs():
+    """New-subject style data: config 3 cohort where some subjects have no rows in outcome 2."""
+    c = make_cohort("config3", n=160)
+    D = dict(c["Data"])
+    idL = np.asarray(D["idL"][1])
+    keep = ~np.isin(idL, [3, 17, 159])                # subjects without binary measurements
+    D["y"] = list(D["y"]); D["Xbetas"] = list(D["Xbetas"]); D["Z"] = list(D["Z"]); D["idL"] = list(D["idL"]); D["idL2"] = list(D["idL2"])
+    D["y"][1] = np.asarray(D["y"][1])[keep]; D["Xbetas"][1] = np.asarray(D["Xbetas"][1])[keep]
+    D["Z"][1] = np.asfortranarray(np.asarray(D["Z"][1])[keep]); D["idL"][1] = idL[keep].astype(np.int32)
+    cnt = np.bincount(D["idL"][1], minlength=160)
+    D["idL2"][1] = (np.cumsum(cnt) - 1).astype(np.int32)
+    return c, D
+
+
+def svft_case():
+    c, D = svft_inputs()
+    ini = c["inits"]
+    # the reference's per-subject call needs every outcome present: evaluate the complete cohort for the golden
+    # values of the complete subjects, and the three incomplete subjects with outcome 2 removed from their lists
+    lp, sp = ref.svft(c["Data"], c["Covs"]["b"], ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+    return dict(log_post=lp, surv_pred=sp)
+
+
 if __name__ == "__main__":
     ref.build(force=True)
     for name in CASES:
@@ -116,5 +139,7 @@ if __name__ == "__main__":
     for name in WORE_CASES:
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_wore_case(name))
         print("wrote", name)
+    np.savez_compressed(os.path.join(HERE, "svft_config3.npz"), **svft_case())
+    print("wrote svft_config3")
     np.savez_compressed(os.path.join(HERE, "surv_config3.npz"), **surv_case())
     print("wrote surv_config3")

@@ -176,3 +176,39 @@ def test_cuda_wore_reproduces_reference_golden(cuda_lib, name):
         fit.set_wlong(D["Wlong"], D["Wlongs"])
         r = fit.lap_rwm_C_woRE(ini, pr, c["scales"], cv, ctl, chain_id=chain)
     _check_wore(r, _load(name), 1e-9, nogam)
+
+
+# ---- survfitJM evaluators: log_post_RE_svft / survPred_svft_2 ------------------------------------------------
+def test_oracle_svft_pieces_match_reference_golden(oracle):
+    """log_post_RE_svft = log p(y|b) + log p(b) - H and survPred_svft_2 = -H (src/survfitJM_mvJMbayes.cpp:140-187)."""
+    g = _load("svft_config3")
+    c, _ = make_golden.svft_inputs()
+    ini = c["inits"]
+    oracle.set_rowsum_mode(1)
+    r = oracle.eval_logpost_re(c["Data"], c["Covs"]["b"], False, ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+    assert np.allclose(r["log_pyb"] + r["log_pb"] - r["H"], g["log_post"], rtol=1e-11)
+    assert np.allclose(-r["H"], g["surv_pred"], rtol=1e-11)
+
+
+@pytest.mark.gpu
+def test_cuda_svft_matches_reference_golden(cuda_lib, oracle):
+    g = _load("svft_config3")
+    c, Dmiss = make_golden.svft_inputs()
+    ini = c["inits"]
+    with cuda_lib.Fit(c["Data"], c["Covs"]["b"], False) as fit:
+        fit.set_draw(c["Data"])
+        lp = fit.log_post_RE_svft(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+        sp = fit.survPred_svft_2(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+    assert np.max(np.abs(lp - g["log_post"]) / np.abs(g["log_post"])) <= 1e-10
+    assert np.max(np.abs(sp - g["surv_pred"]) / np.abs(g["surv_pred"])) <= 1e-10
+    # new subjects without measurements of one outcome (log_longF_svft skips it, :109-110)
+    with cuda_lib.Fit(Dmiss, c["Covs"]["b"], False) as fit:
+        fit.set_draw(Dmiss)
+        lp2 = fit.log_post_RE_svft(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+        assert np.array_equal(np.diff(fit.row_ptr(1))[[3, 17, 159]], [0, 0, 0])
+    full = np.ones(160, dtype=bool); full[[3, 17, 159]] = False
+    assert np.max(np.abs(lp2[full] - g["log_post"][full]) / np.abs(g["log_post"][full])) <= 1e-10
+    oracle.set_rowsum_mode(1)
+    r = oracle.eval_logpost_re(Dmiss, c["Covs"]["b"], False, ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+    assert np.allclose(lp2, r["log_pyb"] + r["log_pb"] - r["H"], rtol=1e-10)
+    assert np.all(lp2[~full] != g["log_post"][~full])
