@@ -166,10 +166,11 @@ int jmb_handle_s::select_kernel() {
             max_c = std::max(max_c, coff[j] - coff[i]);
             if (j == n) break;
         }
-        const int head = (2 * mm.P + md.q * md.q + groups * 3 + 8 * 2 + 1) / 2 * 2;
-        // two CTAs per SM: 113 KB each; 8 warps x 2 stages per CTA
+        const int tgroups = kTmaThreads / md.G;
+        const int head = (2 * mm.P + md.q * md.q + tgroups * 3 + kTmaWarps * 2 + 1) / 2 * 2;
+        // kTmaCtas CTAs per SM share 226 KB; kTmaWarps warps x 2 stages per CTA
         const int RS = (md.q + 2) / 2 * 2;     // rng stride (q increments + log u)
-        const long long budget = ((113LL * 1024) / 8 - head) / 16 - spw * (SS + RS);
+        const long long budget = (((226LL / kTmaCtas) * 1024) / 8 - head) / (2 * kTmaWarps) - spw * (SS + RS);
         long long cap_d = (max_d + 1) / 2 * 2, cap_c = (max_c + 1) / 2 * 2;
         if (cap_d + cap_c > budget) {
             // keep the split proportional; oversize steps fall back to direct global loads
@@ -183,9 +184,9 @@ int jmb_handle_s::select_kernel() {
         long long mean_d = (doff[n] / std::max(n, 1)) * spw, mean_c = (coff[n] / std::max(n, 1)) * spw;
         if (cap_d >= mean_d && cap_c >= mean_c && budget > 0) {
             const long long stage = (long long)ta.cap_d + ta.cap_c + spw * (SS + RS);
-            tma_smem = (int)(8LL * (head + 8LL * 2 * stage));
-            const int unit = 8 * spw;
-            int g = std::min((n + unit - 1) / unit, 2 * num_sms);
+            tma_smem = (int)(8LL * (head + (long long)kTmaWarps * 2 * stage));
+            const int unit = kTmaWarps * spw;
+            int g = std::min((n + unit - 1) / unit, kTmaCtas * num_sms);
             int spc = ((n + g - 1) / g + unit - 1) / unit * unit;
             ta.subjects_per_cta = spc;
             tma_grid = (n + spc - 1) / spc;
@@ -614,7 +615,7 @@ static int launch_step(jmb_handle h, int mode) {
     a.n = h->n; a.subject_offset = h->subject_offset; a.mode = mode; a.subjects_per_cta = h->subjects_per_cta;
     a.rng = h->c->d_rng; a.rng_chunk = h->c->rng_chunk; a.rng_stride = h->rng_stride;
     if (mode == MODE_STEP && h->kernel_mode == 2)
-        h->tma_kernel<<<h->tma_grid, 256, h->tma_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a, h->ta);
+        h->tma_kernel<<<h->tma_grid, kTmaThreads, h->tma_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a, h->ta);
     else if (mode == MODE_STEP && h->kernel_mode == 1)
         h->static_kernel<<<h->grid, 256, h->static_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a);
     else if (h->mm.d.G == 16)

@@ -80,6 +80,14 @@ __device__ __forceinline__ double log_ptb_static(double event, double lh, double
 #ifndef JMB_STATIC_MIN_CTAS
 #define JMB_STATIC_MIN_CTAS 2
 #endif
+// launch shape of the TMA-staged kernel: threads per CTA and CTAs per SM (registers are capped to fit)
+#ifndef JMB_TMA_THREADS
+#define JMB_TMA_THREADS 256
+#endif
+#ifndef JMB_TMA_CTAS
+#define JMB_TMA_CTAS 2
+#endif
+constexpr int kTmaThreads = JMB_TMA_THREADS, kTmaCtas = JMB_TMA_CTAS, kTmaWarps = JMB_TMA_THREADS / 32;
 
 // loop-invariant parameters a thread keeps in registers
 template <class Spec>
@@ -363,11 +371,11 @@ struct TmaArgs {
 };
 
 template <class Spec>
-__global__ void __launch_bounds__(256, JMB_STATIC_MIN_CTAS)
+__global__ void __launch_bounds__(JMB_TMA_THREADS, JMB_TMA_CTAS)
 jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_constant__ ChainConst cc,
              const __grid_constant__ StepArgs a, const TmaArgs ta) {
     constexpr int G = Spec::d.G, q = Spec::d.q, p = Spec::d.p, A = Spec::d.A, SS = Spec::L.state_stride;
-    constexpr int THREADS = 256, WARPS = THREADS / 32, GROUPS = THREADS / G, SPW = 32 / G;
+    constexpr int THREADS = kTmaThreads, WARPS = THREADS / 32, GROUPS = THREADS / G, SPW = 32 / G;
     const int P = B + p + A;
     extern __shared__ double smem[];
     double* s_cur = smem;                          // [P]
