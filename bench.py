@@ -295,6 +295,14 @@ def run_cuda(args):
     h2d = info["chain_bytes_per_subject"] * n - 2 * 8 * (fit.q + 5) * n + 8 * n * (fit.q + 1)
     d2h = sum(v.nbytes for v in res["mcmc"].values()) + res["scales"]["sigma"]["b"].nbytes + 8 * n + 16 * e2e_total
 
+    traffic, traffic_src = None, None
+    try:   # DRAM bytes of the step kernel from the committed ncu --set full capture (per launch)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if tj and fit.layout_info()["kernel"].startswith("static-tma"):
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * (n / tj["subjects"])
+            traffic_src = tj["source"]
+    except Exception:
+        pass
     alg = ALG_BYTES[cfg]
     peaks = {}
     try:
@@ -314,7 +322,7 @@ def run_cuda(args):
                    "parallelism": f"subject-shards x{world}", "chains_per_launch": 1,
                    "l2": "per-iteration working set %.2f GB per GPU >> 126 MB L2 (inputs larger than L2)" % ((info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"]) * n / 1e9)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "jmb_step_kernel", "kernel_ms": k_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": info["kernel"], "kernel_ms": k_ms,
                      "alg_bytes_per_subject_iteration": alg, "alg_source": "SURVEY.md 8(d)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "layout_bytes_per_subject_iteration": info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"],
