@@ -298,7 +298,7 @@ def run_cuda(args):
     traffic, traffic_src = None, None
     try:   # DRAM bytes of the step kernel from the committed ncu --set full capture (per launch)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        if tj and fit.layout_info()["kernel"].startswith("static-tma"):
+        if tj and info["kernel"].startswith("static-tma"):
             traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * (n / tj["subjects"])
             traffic_src = tj["source"]
     except Exception:
