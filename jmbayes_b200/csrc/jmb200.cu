@@ -15,6 +15,7 @@
 #include <thread>
 #include <vector>
 
+#include "jmb_host.h"
 #include "jmb_step_static.cuh"
 
 using namespace jmb;
@@ -24,6 +25,7 @@ using namespace jmb;
 // ---------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
+int jmb_set_error(const std::string& m) { return fail(m); }     // other translation units of the library (jmb_host.h)
 #define CU(call)                                                                              \
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \

@@ -5,10 +5,22 @@
 // semantics are cited per function (paths relative to the JMbayes source tree).
 #pragma once
 #include <cstdint>
+#include <utility>
 #include "../../include/jmb200.h"
 #include "jmb_model.h"
 
 namespace jmb {
+
+template <class F, int... I>
+__device__ __forceinline__ void sfor_impl(F&& f, std::integer_sequence<int, I...>) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+// compile-time loop: f(integral_constant<int, 0>) ... f(integral_constant<int, N-1>)
+template <int N, class F>
+__device__ __forceinline__ void sfor(F&& f) {
+    sfor_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
+
 
 // ---- model descriptor passed to the kernels as a __grid_constant__ parameter -----------------
 struct ModelMeta {

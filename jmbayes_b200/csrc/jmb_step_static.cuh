@@ -14,16 +14,6 @@
 
 namespace jmb {
 
-template <class F, int... I>
-__device__ __forceinline__ void sfor_impl(F&& f, std::integer_sequence<int, I...>) {
-    (f(std::integral_constant<int, I>{}), ...);
-}
-// compile-time loop: f(integral_constant<int, 0>) ... f(integral_constant<int, N-1>)
-template <int N, class F>
-__device__ __forceinline__ void sfor(F&& f) {
-    sfor_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
-}
-
 template <int TF>
 __device__ __forceinline__ double trans_static(double x) {
     if constexpr (TF == JMB_TF_IDENTITY) return x;

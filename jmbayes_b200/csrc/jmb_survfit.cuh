@@ -1,0 +1,911 @@
+// jmb_survfit.cuh - the survfitJM.mvJMbayes() loop of one new subject, fused into one kernel (sm_100a).
+//
+// Reference (paths in the JMbayes tree): R/survfitJM.mvJMbayes.R:277-414 drives, per subject, optim(BFGS)
+// on -log_post_RE_svft with the central-difference gradient of R/cd.R, optim's numerical Hessian, M
+// independence Metropolis-Hastings steps with t proposals (R/rmvt.R, R/dmvt.R) under the parameters of M
+// posterior draws, and after each step one survPred_svft_2 per prediction interval; every evaluation is
+// a .Call into src/survfitJM_mvJMbayes.cpp:140-187.  optim's BFGS (vmmin) and optimhess are R's own C code
+// (src/appl/optim.c, src/library/stats/src/optim.c), restated here from the published algorithm.
+//
+// Mapping: one 16-lane group per subject (two subjects per warp).  All 16 lanes evaluate log_post_RE_svft /
+// survPred_svft_2 together - one Gauss-Kronrod node per lane, the visit rows lane-strided - and lane 0 of
+// the group is the subject's control thread: it owns a resumable state machine (BFGS line search,
+// central-difference gradient, Hessian, MH loop) that consumes the value of the previous evaluation and
+// posts the next request.  Both groups of a warp therefore always meet in the same evaluation code, no
+// matter where each subject is in its own algorithm; groups fetch new subjects from an atomic counter.
+// The subject's design record is read from HBM once and stays L1/L2-resident for its ~3000 evaluations:
+// the kernel is bound by fp64 issue, not by HBM.
+#pragma once
+#include "../../include/jmb200_survfit.h"
+#include "jmb_device.cuh"
+
+namespace jmb {
+
+constexpr int kSvQ = JMB_SVFT_MAX_Q, kSvPK = JMB_SVFT_MAX_PK, kSvFT = JMB_SVFT_MAX_FT;
+constexpr int kSvG = 16;                     // lanes per subject
+constexpr uint32_t kSvKey = 0x53564654u;     // second half of the Philox key of the survfit streams
+
+// model shape of a survfit handle; constexpr-constructible so that precompiled shapes fold away
+struct SvDesc {
+    int O, q, T, A, p, K, WB, w2_const, NB;  // NB = sum of p_k
+    int fam[kMaxO], link[kMaxO], qk[kMaxO], z_ones0[kMaxO], pk[kMaxO], x_ones0[kMaxO], boff[kMaxO];
+    int re_inds[kMaxO][kSvQ];
+    int rt[kMaxT], ut[kMaxT], tf[kMaxT], zz_ones0[kMaxT], u_ones[kMaxT], ft[kMaxT], xx_ones0[kMaxT], outc[kMaxT];
+    int re2[kMaxT][kMaxRT], col[kMaxT][kMaxUT], indf[kMaxT][kSvFT];
+};
+
+// Record of one subject (doubles): int32 visit counts [O] + number of prediction intervals | W2 row (when the
+// W2s rows repeat) | nh + 1 quadrature blocks (block 0: (0, last.time], block l + 1: interval l), each field
+// stored [column][16 lanes] | longitudinal rows per outcome: y[v] | stored X columns | stored Z columns.
+// All-ones first columns of X / Z / XXs / ZZs and all-ones Us are not stored (decided from the data).
+struct SvLayout {
+    int o_V, o_W2c, o_blk0, blk;
+    int b_Pw, b_W1off, b_W1v, b_W2, b_XX[kMaxT], b_ZZ[kMaxT], b_U[kMaxT];
+    int long_cols[kMaxO];
+    int ps_betas, ps_isig, ps_gam, ps_alp, ps_invD, ps_Bs;   // parameter set: ... | invD q x q | Bs_gammas [B]
+};
+
+JMB_HD constexpr SvLayout sv_make_layout(const SvDesc& d) {
+    SvLayout L{};
+    L.o_V = 0;
+    int o = (d.O + 1 + 1) / 2;
+    L.o_W2c = o;
+    if (d.w2_const) o += d.p;
+    L.o_blk0 = o;
+    int b = 0;
+    L.b_Pw = b; b += kSvG;
+    L.b_W1off = b; b += kSvG / 2;
+    L.b_W1v = b; b += d.WB * kSvG;
+    L.b_W2 = b;
+    if (!d.w2_const) b += d.p * kSvG;
+    for (int t = 0; t < d.T; ++t) {
+        L.b_XX[t] = b; b += (d.ft[t] - d.xx_ones0[t]) * kSvG;
+        L.b_ZZ[t] = b; b += (d.rt[t] - d.zz_ones0[t]) * kSvG;
+        L.b_U[t] = b; b += (d.u_ones[t] ? 0 : d.ut[t]) * kSvG;
+    }
+    L.blk = b;
+    for (int k = 0; k < d.O; ++k) L.long_cols[k] = 1 + (d.pk[k] - d.x_ones0[k]) + (d.qk[k] - d.z_ones0[k]);
+    int s = 0;
+    L.ps_betas = s; s += d.NB;
+    L.ps_isig = s; s += d.O;
+    L.ps_gam = s; s += d.p;
+    L.ps_alp = s; s += d.A;
+    L.ps_invD = s; s += d.q * d.q;
+    L.ps_Bs = s;
+    return L;
+}
+
+JMB_HD constexpr bool sv_same_desc(const SvDesc& a, const SvDesc& b) {
+    if (a.O != b.O || a.q != b.q || a.T != b.T || a.A != b.A || a.p != b.p || a.K != b.K || a.WB != b.WB ||
+        a.w2_const != b.w2_const || a.NB != b.NB) return false;
+    for (int k = 0; k < a.O; ++k) {
+        if (a.fam[k] != b.fam[k] || a.link[k] != b.link[k] || a.qk[k] != b.qk[k] || a.z_ones0[k] != b.z_ones0[k] ||
+            a.pk[k] != b.pk[k] || a.x_ones0[k] != b.x_ones0[k] || a.boff[k] != b.boff[k]) return false;
+        for (int j = 0; j < a.qk[k]; ++j) if (a.re_inds[k][j] != b.re_inds[k][j]) return false;
+    }
+    for (int t = 0; t < a.T; ++t) {
+        if (a.rt[t] != b.rt[t] || a.ut[t] != b.ut[t] || a.tf[t] != b.tf[t] || a.zz_ones0[t] != b.zz_ones0[t] ||
+            a.u_ones[t] != b.u_ones[t] || a.ft[t] != b.ft[t] || a.xx_ones0[t] != b.xx_ones0[t] || a.outc[t] != b.outc[t]) return false;
+        for (int j = 0; j < a.rt[t]; ++j) if (a.re2[t][j] != b.re2[t][j]) return false;
+        for (int u = 0; u < a.ut[t]; ++u) if (a.col[t][u] != b.col[t][u]) return false;
+        for (int f = 0; f < a.ft[t]; ++f) if (a.indf[t][f] != b.indf[t][f]) return false;
+    }
+    return true;
+}
+
+// BASELINE config 5 (and any fit of the config 3 / 4 shape): gaussian + binomial(logit) + poisson(log), random
+// intercept + slope each (q = 6), value + slope association per outcome, X = Z = [1, time]
+JMB_HD constexpr SvDesc sv_desc_three_outcomes() {
+    SvDesc d{};
+    d.O = 3; d.q = 6; d.T = 6; d.A = 6; d.p = 2; d.K = 15; d.WB = 4; d.w2_const = 1; d.NB = 6;
+    d.fam[0] = JMB_FAM_GAUSSIAN; d.link[0] = JMB_LINK_IDENTITY;
+    d.fam[1] = JMB_FAM_BINOMIAL; d.link[1] = JMB_LINK_LOGIT;
+    d.fam[2] = JMB_FAM_POISSON; d.link[2] = JMB_LINK_LOG;
+    for (int k = 0; k < 3; ++k) {
+        d.qk[k] = 2; d.z_ones0[k] = 1; d.pk[k] = 2; d.x_ones0[k] = 1; d.boff[k] = 2 * k;
+        d.re_inds[k][0] = 2 * k; d.re_inds[k][1] = 2 * k + 1;
+        const int tv = 2 * k, ts = 2 * k + 1;
+        d.rt[tv] = 2; d.ut[tv] = 1; d.tf[tv] = JMB_TF_IDENTITY; d.zz_ones0[tv] = 1; d.u_ones[tv] = 1;
+        d.ft[tv] = 2; d.xx_ones0[tv] = 1; d.outc[tv] = k; d.indf[tv][0] = 0; d.indf[tv][1] = 1;
+        d.re2[tv][0] = 2 * k; d.re2[tv][1] = 2 * k + 1; d.col[tv][0] = tv;
+        d.rt[ts] = 1; d.ut[ts] = 1; d.tf[ts] = JMB_TF_IDENTITY; d.zz_ones0[ts] = 1; d.u_ones[ts] = 1;
+        d.ft[ts] = 1; d.xx_ones0[ts] = 1; d.outc[ts] = k; d.indf[ts][0] = 1;
+        d.re2[ts][0] = 2 * k + 1; d.col[ts][0] = ts;
+    }
+    return d;
+}
+
+// one gaussian outcome, random intercept + slope, current-value association (configs 1 / 2)
+JMB_HD constexpr SvDesc sv_desc_value_gaussian() {
+    SvDesc d{};
+    d.O = 1; d.q = 2; d.T = 1; d.A = 1; d.p = 2; d.K = 15; d.WB = 4; d.w2_const = 1; d.NB = 2;
+    d.fam[0] = JMB_FAM_GAUSSIAN; d.link[0] = JMB_LINK_IDENTITY; d.qk[0] = 2; d.z_ones0[0] = 1; d.pk[0] = 2; d.x_ones0[0] = 1;
+    d.re_inds[0][0] = 0; d.re_inds[0][1] = 1;
+    d.rt[0] = 2; d.ut[0] = 1; d.tf[0] = JMB_TF_IDENTITY; d.zz_ones0[0] = 1; d.u_ones[0] = 1; d.ft[0] = 2; d.xx_ones0[0] = 1;
+    d.indf[0][0] = 0; d.indf[0][1] = 1; d.re2[0][0] = 0; d.re2[0][1] = 1; d.col[0][0] = 0;
+    return d;
+}
+
+struct SvSpecThree { static constexpr SvDesc d = sv_desc_three_outcomes(); static constexpr SvLayout L = sv_make_layout(d); };
+struct SvSpecValue { static constexpr SvDesc d = sv_desc_value_gaussian(); static constexpr SvLayout L = sv_make_layout(d); };
+
+struct SvMeta { SvDesc d; SvLayout L; };
+
+struct SvConst {            // jmb_svft_control + sizes
+    double scale, df, ci_lo, ci_hi, parscale, reltol, ndeps, cd_eps;
+    int log, maxit;
+    uint32_t seed;
+};
+
+struct SvArgs {
+    const double* rec; const long long* off;       // subject records and their offsets [n + 1]
+    const double* par_mean; const double* par_draws; // [ps_len], [M][ps_len]
+    int n, M, L, B, ps_len;
+    long long subject_offset;
+    int do_modes, do_sample;
+    SvConst c;
+    double* modes; double* hess; int* conv; int* counts;   // [n][q], [n][q*q], [n], [n][2]
+    double* S;                                     // [n][M][L]
+    double* acc_rate; double* b_last;              // [n], [n][q]
+    int* work;                                     // atomic subject counter
+};
+
+// ---- per-group shared state --------------------------------------------------------------------------
+enum { SC_FMIN = 0, SC_F, SC_GP, SC_STEP, SC_F1, SC_X1, SC_W, SC_U, SC_DMVT_P, SC_DMVT_O, SC_LP_P, SC_CUM, SC_EPS_H, SC_N };
+enum { IC_SUBJ = 0, IC_STATE, IC_ACT, IC_FULL, IC_BLK, IC_GI, IC_RET, IC_COUNT, IC_FUN, IC_GRC, IC_ILAST, IC_ITER,
+       IC_HI, IC_M, IC_L, IC_NACC, IC_NH, IC_CONV, IC_O, IC_N };
+enum { ACT_EVAL = 0, ACT_RNG = 1, ACT_DONE = 2 };
+enum { ST_FETCH = 0, ST_F0, ST_GRAD_P, ST_GRAD_M, ST_LS, ST_MH_RNG, ST_MH_P, ST_MH_O, ST_HZ,
+       PC_LOOP_TOP, PC_LS_TRY, PC_LS_DONE, PC_LOOP_END, PC_VM_DONE, PC_GRAD_DONE, PC_MODE_DONE, PC_SAMPLE_INIT,
+       PC_MH_NEXT, PC_SUBJ_DONE };
+enum { RET_INIT = 0, RET_LS, RET_H1, RET_H2 };
+
+struct SvG {                // views into one group's shared memory
+    double *par, *btry, *x, *grad, *bz, *X, *c, *t, *g, *Bm, *dpar, *df1, *hess, *mode, *Af, *invS, *invV, *Wa, *Wb,
+           *b_old, *b_new, *pb, *z, *sc;
+    int* ic;
+};
+
+__host__ __device__ inline int sv_group_doubles(int q, int ps_len) {
+    const int zq = (q + 2) / 2 * 2;
+    return ps_len + 14 * q + zq + 7 * q * q + SC_N + (IC_N + 1) / 2;
+}
+
+__device__ __forceinline__ void sv_bind(SvG& G, double* base, int q, int ps_len) {
+    const int zq = (q + 2) / 2 * 2, qq = q * q;
+    double* p = base;
+    G.par = p; p += ps_len;
+    G.btry = p; p += q; G.x = p; p += q; G.grad = p; p += q; G.bz = p; p += q; G.X = p; p += q; G.c = p; p += q;
+    G.t = p; p += q; G.g = p; p += q; G.dpar = p; p += q; G.df1 = p; p += q; G.mode = p; p += q;
+    G.b_old = p; p += q; G.b_new = p; p += q; G.pb = p; p += q; G.z = p; p += zq;
+    G.Bm = p; p += qq; G.hess = p; p += qq; G.Af = p; p += qq; G.invS = p; p += qq; G.invV = p; p += qq;
+    G.Wa = p; p += qq; G.Wb = p; p += qq;
+    G.sc = p; p += SC_N;
+    G.ic = reinterpret_cast<int*>(p);
+}
+
+// ---- log_post_RE_svft / survPred_svft_2 by the 16 lanes of a group ---------------------------------------
+// runtime-branch twin of logdens_static (jmb_step_static.cuh): folds when fam / link are compile-time constants
+__device__ __forceinline__ double sv_logdens(int fam, int link, double y, double eta, double inv_sigma) {
+    if (fam == JMB_FAM_GAUSSIAN) {
+        const double t = (y - eta) * inv_sigma;
+        return -0.5 * (t * t);
+    } else if (fam == JMB_FAM_BINOMIAL) {
+        double pr;
+        if (link == JMB_LINK_LOGIT) { const double e = exp(eta); pr = e / (1.0 + e); }
+        else if (link == JMB_LINK_PROBIT) pr = 0.5 * erfc(-eta * 0.70710678118654752440);
+        else pr = -exp(-exp(eta)) + 1.0;
+        const bool one = (y == 1.0), zero = (y == 0.0);
+        if (one || zero) {
+            const double ld = log(one ? pr : 1.0 - pr);
+            const bool dead_inf = one ? (pr == 1.0) : (pr == 0.0);      // 0 * log(0) in the naive formula
+            return dead_inf ? __longlong_as_double(0x7ff8000000000000LL) : ld;
+        }
+        return y * log(pr) + (1.0 - y) * log(1.0 - pr);
+    } else {
+        if (link == JMB_LINK_LOG) {
+            const double mu = exp(eta);
+            double ld = y * eta - mu;
+            if (mu == 0.0) ld = (y == 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : (y > 0.0 ? -INFINITY : INFINITY);
+            return ld;
+        }
+        return row_logdens(fam, link, y, eta, inv_sigma);
+    }
+}
+
+// value of the posted request: full -> log_post_RE_svft(btry) on block 0 (src/survfitJM_mvJMbayes.cpp:140-166),
+// else survPred_svft_2(btry) = -H on block `blk_index` (:168-187).  Generic flavour: runtime descriptor.
+__device__ __forceinline__ double sv_eval_generic(const SvDesc& d, const SvLayout& L, const double* __restrict__ rec,
+                                                  const int blk_index, const bool full, const double* sb, const double* sp,
+                                                  const int lane, const unsigned gmask) {
+    // ---- the lane's quadrature row (lin_pred_matF_svft + the linear predictor of the hazard) ----
+    const double* __restrict__ blk = rec + L.o_blk0 + (long long)blk_index * L.blk;
+    const int off = reinterpret_cast<const int*>(blk + L.b_W1off)[lane];
+    double s1 = 0.0;
+    for (int j = 0; j < d.WB; ++j) s1 += blk[L.b_W1v + j * kSvG + lane] * sp[L.ps_Bs + off + j];
+    double s2 = 0.0;
+    for (int j = 0; j < d.p; ++j) s2 += (d.w2_const ? rec[L.o_W2c + j] : blk[L.b_W2 + j * kSvG + lane]) * sp[L.ps_gam + j];
+    double s3 = 0.0;
+    for (int t = 0; t < d.T; ++t) {
+        const int bo = d.boff[d.outc[t]];
+        double xb = d.xx_ones0[t] ? sp[L.ps_betas + bo + d.indf[t][0]] : 0.0;
+        for (int f = d.xx_ones0[t]; f < d.ft[t]; ++f)
+            xb += blk[L.b_XX[t] + (f - d.xx_ones0[t]) * kSvG + lane] * sp[L.ps_betas + bo + d.indf[t][f]];
+        double zb = d.zz_ones0[t] ? sb[d.re2[t][0]] : 0.0;
+        for (int j = d.zz_ones0[t]; j < d.rt[t]; ++j)
+            zb += blk[L.b_ZZ[t] + (j - d.zz_ones0[t]) * kSvG + lane] * sb[d.re2[t][j]];
+        const double v = trans_fun(d.tf[t], xb + zb);
+        for (int u = 0; u < d.ut[t]; ++u) {
+            const double w = d.u_ones[t] ? v : blk[L.b_U[t] + u * kSvG + lane] * v;
+            s3 += w * sp[L.ps_alp + d.col[t][u]];
+        }
+    }
+    const double e = (lane < d.K) ? blk[L.b_Pw + lane] * exp((s1 + s2) + s3) : 0.0;
+    const double H = group_sum<kSvG>(e, gmask);
+    if (!full) return 0.0 - H;
+
+    // ---- log p(y | b) over the visit rows (lin_predF_svft + log_longF_svft, :57-66,103-135) ----
+    const int* hdr = reinterpret_cast<const int*>(rec + L.o_V);
+    const int nh = hdr[d.O];
+    const double* __restrict__ lrec = rec + L.o_blk0 + (long long)(nh + 1) * L.blk;
+    double acc = 0.0;
+    for (int k = 0; k < d.O; ++k) {
+        const int v = hdr[k];
+        const int xc = d.pk[k] - d.x_ones0[k];
+        for (int r = lane; r < v; r += kSvG) {
+            double xb = d.x_ones0[k] ? sp[L.ps_betas + d.boff[k]] : 0.0;
+            for (int c = d.x_ones0[k]; c < d.pk[k]; ++c) xb += lrec[(1 + c - d.x_ones0[k]) * v + r] * sp[L.ps_betas + d.boff[k] + c];
+            double zb = d.z_ones0[k] ? sb[d.re_inds[k][0]] : 0.0;
+            for (int j = d.z_ones0[k]; j < d.qk[k]; ++j) zb += lrec[(1 + xc + j - d.z_ones0[k]) * v + r] * sb[d.re_inds[k][j]];
+            acc += sv_logdens(d.fam[k], d.link[k], lrec[r], xb + zb, sp[L.ps_isig + k]);
+        }
+        lrec += L.long_cols[k] * v;
+    }
+    // ---- log p(b) = -0.5 b' invD b (:157): lane j takes column j ----
+    double qf = 0.0;
+    if (lane < d.q) {
+        double t = 0.0;
+        for (int l = 0; l < d.q; ++l) t += sb[l] * sp[L.ps_invD + l + lane * d.q];
+        qf = t * sb[lane];
+    }
+    const double log_pyb = group_sum<kSvG>(acc, gmask);
+    const double log_pb = -0.5 * group_sum<kSvG>(qf, gmask);
+    return (log_pyb + (0.0 - H)) + log_pb;                                     // :163
+}
+
+// Static flavour: the model shape is the constexpr descriptor Spec::d, every loop over outcomes / terms /
+// columns is unrolled at compile time and b stays in registers.  Same arithmetic, same order.
+template <class Spec>
+__device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec, const int blk_index, const bool full,
+                                                 const double* sb, const double* sp, const int lane, const unsigned gmask) {
+    constexpr int q = Spec::d.q, O = Spec::d.O, T = Spec::d.T, p = Spec::d.p, K = Spec::d.K, WB = Spec::d.WB;
+    constexpr bool W2C = Spec::d.w2_const != 0;
+    constexpr int oBlk0 = Spec::L.o_blk0, BLK = Spec::L.blk, psB = Spec::L.ps_betas, psG = Spec::L.ps_gam, psA = Spec::L.ps_alp;
+    constexpr int psBs = Spec::L.ps_Bs, psD = Spec::L.ps_invD, psS = Spec::L.ps_isig;
+    double b[q];
+    sfor<q>([&](auto j) { b[j] = sb[j]; });
+
+    const double* __restrict__ blk = rec + oBlk0 + (long long)blk_index * BLK;
+    constexpr int bW1off = Spec::L.b_W1off, bW1v = Spec::L.b_W1v, oW2c = Spec::L.o_W2c, bW2 = Spec::L.b_W2, bPw = Spec::L.b_Pw, oV = Spec::L.o_V;
+    const int off = reinterpret_cast<const int*>(blk + bW1off)[lane];
+    double s1 = 0.0;
+    sfor<WB>([&](auto j) { s1 += blk[bW1v + j * kSvG + lane] * sp[psBs + off + j]; });
+    double s2 = 0.0;
+    sfor<p>([&](auto j) { s2 += (W2C ? rec[oW2c + j] : blk[bW2 + j * kSvG + lane]) * sp[psG + j]; });
+    double s3 = 0.0;
+    sfor<T>([&](auto tc) {
+        constexpr int t = tc;
+        constexpr int bo = Spec::d.boff[Spec::d.outc[t]], x0 = Spec::d.xx_ones0[t], z0 = Spec::d.zz_ones0[t];
+        double xb = 0.0;
+        constexpr int bXX = Spec::L.b_XX[t], bZZ = Spec::L.b_ZZ[t], bU = Spec::L.b_U[t], tf = Spec::d.tf[t];
+        constexpr int if0 = Spec::d.indf[t][0], r20 = Spec::d.re2[t][0];
+        if constexpr (x0 == 1) xb = sp[psB + bo + if0];
+        sfor<Spec::d.ft[t] - x0>([&](auto fc) {
+            constexpr int f = fc + x0;
+            constexpr int idx = Spec::d.indf[t][f];
+            xb += blk[bXX + (f - x0) * kSvG + lane] * sp[psB + bo + idx];
+        });
+        double zb = 0.0;
+        if constexpr (z0 == 1) zb = b[r20];
+        sfor<Spec::d.rt[t] - z0>([&](auto jc) {
+            constexpr int j = jc + z0;
+            constexpr int idx = Spec::d.re2[t][j];
+            zb += blk[bZZ + (j - z0) * kSvG + lane] * b[idx];
+        });
+        double v = xb + zb;
+        if constexpr (tf != JMB_TF_IDENTITY) v = trans_fun(tf, v);
+        sfor<Spec::d.ut[t]>([&](auto uc) {
+            constexpr int u = uc;
+            double w = v;
+            constexpr int cidx = Spec::d.col[t][u];
+            if constexpr (Spec::d.u_ones[t] == 0) w = blk[bU + u * kSvG + lane] * v;
+            s3 += w * sp[psA + cidx];
+        });
+    });
+    const double e = (lane < K) ? blk[bPw + lane] * exp((s1 + s2) + s3) : 0.0;
+    const double H = group_sum<kSvG>(e, gmask);
+    if (!full) return 0.0 - H;
+
+    const int* hdr = reinterpret_cast<const int*>(rec + oV);
+    const int nh = hdr[O];
+    const double* __restrict__ lrec = rec + oBlk0 + (long long)(nh + 1) * BLK;
+    double acc = 0.0;
+    sfor<O>([&](auto kc) {
+        constexpr int k = kc;
+        constexpr int x0 = Spec::d.x_ones0[k], z0 = Spec::d.z_ones0[k], pk = Spec::d.pk[k], qk = Spec::d.qk[k], xc = pk - x0;
+        constexpr int bo = Spec::d.boff[k], ri0 = Spec::d.re_inds[k][0], fam = Spec::d.fam[k], link = Spec::d.link[k], lcols = Spec::L.long_cols[k];
+        const int v = hdr[k];
+        for (int r = lane; r < v; r += kSvG) {
+            double xb = 0.0;
+            if constexpr (x0 == 1) xb = sp[psB + bo];
+            sfor<pk - x0>([&](auto cc) { constexpr int c = cc + x0; xb += lrec[(1 + c - x0) * v + r] * sp[psB + bo + c]; });
+            double zb = 0.0;
+            if constexpr (z0 == 1) zb = b[ri0];
+            sfor<qk - z0>([&](auto jc) { constexpr int j = jc + z0; constexpr int idx = Spec::d.re_inds[k][j]; zb += lrec[(1 + xc + j - z0) * v + r] * b[idx]; });
+            acc += sv_logdens(fam, link, lrec[r], xb + zb, sp[psS + k]);
+        }
+        lrec += lcols * v;
+    });
+    double qf = 0.0;
+    if (lane < q) {
+        double t = 0.0;
+        sfor<q>([&](auto l) { t += b[l] * sp[psD + l + lane * q]; });
+        qf = t * sb[lane];
+    }
+    const double log_pyb = group_sum<kSvG>(acc, gmask);
+    const double log_pb = -0.5 * group_sum<kSvG>(qf, gmask);
+    return (log_pyb + (0.0 - H)) + log_pb;
+}
+
+// ---- small dense helpers of the control thread (same algorithms as oracle/jmb_oracle_svft.c) ---------------
+// solve(A): Gauss-Jordan with partial pivoting; a is destroyed; returns 1 when singular
+__device__ inline int sv_inverse(double* a, int n, double* inv) {
+    for (int j = 0; j < n * n; ++j) inv[j] = 0.0;
+    for (int j = 0; j < n; ++j) inv[j + j * n] = 1.0;
+    for (int c = 0; c < n; ++c) {
+        int piv = c; double best = fabs(a[c + c * n]);
+        for (int r = c + 1; r < n; ++r) if (fabs(a[r + c * n]) > best) { best = fabs(a[r + c * n]); piv = r; }
+        if (!(best > 0.0) || !isfinite(best)) return 1;
+        if (piv != c)
+            for (int j = 0; j < n; ++j) {
+                double t = a[c + j * n]; a[c + j * n] = a[piv + j * n]; a[piv + j * n] = t;
+                t = inv[c + j * n]; inv[c + j * n] = inv[piv + j * n]; inv[piv + j * n] = t;
+            }
+        const double dd = 1.0 / a[c + c * n];
+        for (int j = 0; j < n; ++j) { a[c + j * n] *= dd; inv[c + j * n] *= dd; }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const double f = a[r + c * n];
+            if (f == 0.0) continue;
+            for (int j = 0; j < n; ++j) { a[r + j * n] -= f * a[c + j * n]; inv[r + j * n] -= f * inv[c + j * n]; }
+        }
+    }
+    return 0;
+}
+
+// eigen(S, symmetric = TRUE): cyclic Jacobi (12 sweeps), values decreasing.  a: symmetrised copy of S (destroyed)
+__device__ inline void sv_eigen_sym(double* a, int n, double* val, double* vec) {
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) vec[i + j * n] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 12; ++sweep)
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = a[p + q * n], app = a[p + p * n], aqq = a[q + q * n];
+                if (fabs(apq) <= 1e-20 * (fabs(app) + fabs(aqq))) continue;
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) {
+                    const double akp = a[k + p * n], akq = a[k + q * n];
+                    a[k + p * n] = c * akp - s * akq; a[k + q * n] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double apk = a[p + k * n], aqk = a[q + k * n];
+                    a[p + k * n] = c * apk - s * aqk; a[q + k * n] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double vkp = vec[k + p * n], vkq = vec[k + q * n];
+                    vec[k + p * n] = c * vkp - s * vkq; vec[k + q * n] = s * vkp + c * vkq;
+                }
+            }
+    for (int j = 0; j < n; ++j) val[j] = a[j + j * n];
+    for (int j = 0; j < n - 1; ++j) {
+        int best = j;
+        for (int l = j + 1; l < n; ++l) if (val[l] > val[best]) best = l;
+        if (best != j) {
+            double t = val[j]; val[j] = val[best]; val[best] = t;
+            for (int k = 0; k < n; ++k) { t = vec[k + j * n]; vec[k + j * n] = vec[k + best * n]; vec[k + best * n] = t; }
+        }
+    }
+}
+
+// ---- the subject's control thread: consume `val`, run until the next request is posted -------------------------
+// vmmin (R src/appl/optim.c), fminfn / fmingr / optimhess (R src/library/stats/src/optim.c), cd (R/cd.R) and the
+// MH loop of R/survfitJM.mvJMbayes.R:338-398 as one resumable state machine.
+__device__ __noinline__ void sv_advance(const SvArgs& a, const int q, SvG& G, const double val) {
+    const double ps = a.c.parscale, stepredn = 0.2, acctol = 0.0001, reltest = 10.0;
+    const int n = q;
+    int* ic = G.ic;
+    double* sc = G.sc;
+    int st = ic[IC_STATE];
+    auto post_full = [&](int state) { ic[IC_ACT] = ACT_EVAL; ic[IC_FULL] = 1; ic[IC_BLK] = 0; ic[IC_STATE] = state; };
+    // cd(): request f(x + ex e_i)
+    auto grad_plus = [&]() {
+        const int i = ic[IC_GI];
+        const double ex = a.c.cd_eps * (fabs(G.x[i]) + a.c.cd_eps);
+        for (int j = 0; j < n; ++j) G.btry[j] = G.x[j];
+        G.btry[i] = G.x[i] + ex;
+        sc[SC_X1] = G.btry[i];
+        post_full(ST_GRAD_P);
+    };
+    // fmingr at the optimiser point z: x = z * parscale, then cd()
+    auto start_grad = [&](const double* z, int ret) {
+        for (int j = 0; j < n; ++j) G.x[j] = z[j] * ps;
+        ic[IC_GI] = 0; ic[IC_RET] = ret;
+        grad_plus();
+    };
+    for (;;) {
+        switch (st) {
+        case ST_FETCH: {
+            const int s = atomicAdd(a.work, 1);
+            if (s >= a.n) { ic[IC_SUBJ] = -1; ic[IC_ACT] = ACT_DONE; ic[IC_STATE] = ST_FETCH; return; }
+            ic[IC_SUBJ] = s;
+            ic[IC_NH] = reinterpret_cast<const int*>(a.rec + a.off[s])[ic[IC_O]];      // header: visit counts [O], then nh
+            ic[IC_CONV] = 0; ic[IC_NACC] = 0;
+            for (int j = 0; j < a.ps_len; ++j) G.par[j] = a.par_mean ? a.par_mean[j] : 0.0;
+            if (a.do_modes) {
+                for (int j = 0; j < n; ++j) { G.bz[j] = 0.0 / ps; G.btry[j] = G.bz[j] * ps; }   // start = rep(0, q)
+                post_full(ST_F0);
+                return;
+            }
+            for (int j = 0; j < n; ++j) G.mode[j] = a.modes[(long long)s * n + j];
+            for (int j = 0; j < n * n; ++j) G.hess[j] = a.hess[(long long)s * n * n + j];
+            st = PC_SAMPLE_INIT;
+            break;
+        }
+        case ST_F0: {
+            const double f = 0.0 - val;
+            if (!isfinite(f)) {                      // error("initial value in 'vmmin' is not finite")
+                ic[IC_CONV] = 10; ic[IC_FUN] = 1; ic[IC_GRC] = 0;
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                for (int j = 0; j < n; ++j) G.mode[j] = nan;
+                for (int j = 0; j < n * n; ++j) G.hess[j] = nan;
+                st = PC_MODE_DONE;
+                break;
+            }
+            sc[SC_FMIN] = f; sc[SC_F] = f;
+            ic[IC_FUN] = 1; ic[IC_GRC] = 1; ic[IC_ITER] = 0; ic[IC_COUNT] = 0;
+            start_grad(G.bz, RET_INIT);
+            return;
+        }
+        case ST_GRAD_P: {
+            const int i = ic[IC_GI];
+            sc[SC_F1] = 0.0 - val;                   // ff(x1)
+            const double ex = a.c.cd_eps * (fabs(G.x[i]) + a.c.cd_eps);
+            G.btry[i] = G.x[i] - ex;
+            post_full(ST_GRAD_M);
+            return;
+        }
+        case ST_GRAD_M: {
+            const int i = ic[IC_GI];
+            const double diff_f = sc[SC_F1] - (0.0 - val);
+            const double diff_x = sc[SC_X1] - G.btry[i];
+            G.grad[i] = (diff_f / diff_x) * ps;      // fmingr: gr(x) * parscale
+            ic[IC_GI] = i + 1;
+            if (i + 1 < n) { grad_plus(); return; }
+            st = PC_GRAD_DONE;
+            break;
+        }
+        case PC_GRAD_DONE: {
+            const int ret = ic[IC_RET];
+            if (ret == RET_INIT) {
+                for (int j = 0; j < n; ++j) G.g[j] = G.grad[j];
+                ic[IC_ITER] = 1; ic[IC_ILAST] = ic[IC_GRC];
+                st = PC_LOOP_TOP;
+            } else if (ret == RET_LS) {
+                ic[IC_GRC] += 1; ic[IC_ITER] += 1;
+                const double step = sc[SC_STEP];
+                double D1 = 0.0;
+                for (int i = 0; i < n; ++i) {
+                    G.t[i] = step * G.t[i];
+                    G.c[i] = G.grad[i] - G.c[i];
+                    G.g[i] = G.grad[i];
+                    D1 += G.t[i] * G.c[i];
+                }
+                if (D1 > 0) {
+                    double D2 = 0.0;
+                    for (int i = 0; i < n; ++i) {
+                        double s = 0.0;
+                        for (int j = 0; j <= i; ++j) s += G.Bm[i * n + j] * G.c[j];
+                        for (int j = i + 1; j < n; ++j) s += G.Bm[j * n + i] * G.c[j];
+                        G.X[i] = s;
+                        D2 += s * G.c[i];
+                    }
+                    D2 = 1.0 + D2 / D1;
+                    for (int i = 0; i < n; ++i)
+                        for (int j = 0; j <= i; ++j)
+                            G.Bm[i * n + j] += (D2 * G.t[i] * G.t[j] - G.X[i] * G.t[j] - G.t[i] * G.X[j]) / D1;
+                } else {
+                    ic[IC_ILAST] = ic[IC_GRC];
+                }
+                st = PC_LOOP_END;
+            } else if (ret == RET_H1) {              // optimhess: df1 at dpar + eps e_i
+                const int hi = ic[IC_HI];
+                for (int j = 0; j < n; ++j) G.df1[j] = G.grad[j];
+                G.dpar[hi] = G.dpar[hi] - 2 * sc[SC_EPS_H];
+                start_grad(G.dpar, RET_H2);
+                return;
+            } else {                                 // RET_H2: df2 at dpar - eps e_i
+                const int hi = ic[IC_HI];
+                const double eps = sc[SC_EPS_H];
+                for (int j = 0; j < n; ++j) G.hess[hi * n + j] = (G.df1[j] - G.grad[j]) / (2 * eps * ps * ps);
+                G.dpar[hi] = G.dpar[hi] + eps;
+                if (hi + 1 < n) {
+                    ic[IC_HI] = hi + 1;
+                    G.dpar[hi + 1] = G.dpar[hi + 1] + eps;
+                    start_grad(G.dpar, RET_H1);
+                    return;
+                }
+                for (int i = 0; i < n; ++i)
+                    for (int j = 0; j < i; ++j) {
+                        const double tmp = 0.5 * (G.hess[i * n + j] + G.hess[j * n + i]);
+                        G.hess[i * n + j] = tmp; G.hess[j * n + i] = tmp;
+                    }
+                st = PC_MODE_DONE;
+            }
+            break;
+        }
+        case PC_LOOP_TOP: {
+            if (ic[IC_ILAST] == ic[IC_GRC])
+                for (int i = 0; i < n; ++i) { for (int j = 0; j < i; ++j) G.Bm[i * n + j] = 0.0; G.Bm[i * n + i] = 1.0; }
+            for (int i = 0; i < n; ++i) { G.X[i] = G.bz[i]; G.c[i] = G.g[i]; }
+            double gradproj = 0.0;
+            for (int i = 0; i < n; ++i) {
+                double s = 0.0;
+                for (int j = 0; j <= i; ++j) s -= G.Bm[i * n + j] * G.c[j];
+                for (int j = i + 1; j < n; ++j) s -= G.Bm[j * n + i] * G.c[j];
+                G.t[i] = s;
+                gradproj += s * G.c[i];
+            }
+            sc[SC_GP] = gradproj;
+            if (gradproj < 0.0) {                    // search direction is downhill
+                sc[SC_STEP] = 1.0;
+                st = PC_LS_TRY;
+            } else {                                 // uphill search
+                ic[IC_COUNT] = 0;
+                if (ic[IC_ILAST] == ic[IC_GRC]) ic[IC_COUNT] = n; else ic[IC_ILAST] = ic[IC_GRC];
+                st = PC_LOOP_END;
+            }
+            break;
+        }
+        case PC_LS_TRY: {
+            const double step = sc[SC_STEP];
+            int count = 0;
+            for (int i = 0; i < n; ++i) {
+                G.bz[i] = G.X[i] + step * G.t[i];
+                if (reltest + G.X[i] == reltest + G.bz[i]) count++;
+            }
+            ic[IC_COUNT] = count;
+            if (count < n) {
+                for (int j = 0; j < n; ++j) G.btry[j] = G.bz[j] * ps;
+                post_full(ST_LS);
+                return;
+            }
+            st = PC_LS_DONE;
+            break;
+        }
+        case ST_LS: {
+            const double f = 0.0 - val;
+            sc[SC_F] = f;
+            ic[IC_FUN] += 1;
+            const bool accpoint = isfinite(f) && (f <= sc[SC_FMIN] + sc[SC_GP] * sc[SC_STEP] * acctol);
+            if (!accpoint) { sc[SC_STEP] *= stepredn; st = PC_LS_TRY; }
+            else st = PC_LS_DONE;
+            break;
+        }
+        case PC_LS_DONE: {
+            const double f = sc[SC_F], Fmin = sc[SC_FMIN];
+            const bool enough = fabs(f - Fmin) > a.c.reltol * (fabs(Fmin) + a.c.reltol);   // abstol = -Inf
+            if (!enough) { ic[IC_COUNT] = n; sc[SC_FMIN] = f; }
+            if (ic[IC_COUNT] < n) {                  // making progress
+                sc[SC_FMIN] = f;
+                start_grad(G.bz, RET_LS);
+                return;
+            }
+            if (ic[IC_ILAST] < ic[IC_GRC]) { ic[IC_COUNT] = 0; ic[IC_ILAST] = ic[IC_GRC]; }   // no progress
+            st = PC_LOOP_END;
+            break;
+        }
+        case PC_LOOP_END: {
+            if (ic[IC_ITER] >= a.c.maxit) { st = PC_VM_DONE; break; }
+            if (ic[IC_GRC] - ic[IC_ILAST] > 2 * n) ic[IC_ILAST] = ic[IC_GRC];      // periodic restart
+            st = (ic[IC_COUNT] != n || ic[IC_ILAST] != ic[IC_GRC]) ? PC_LOOP_TOP : PC_VM_DONE;
+            break;
+        }
+        case PC_VM_DONE: {
+            ic[IC_CONV] = (ic[IC_ITER] < a.c.maxit) ? 0 : 1;
+            for (int j = 0; j < n; ++j) G.mode[j] = G.bz[j] * ps;                  // opt$par
+            const double eps = a.c.ndeps / ps;                                    // optimhess
+            sc[SC_EPS_H] = eps;
+            for (int j = 0; j < n; ++j) G.dpar[j] = G.mode[j] / ps;
+            ic[IC_HI] = 0;
+            G.dpar[0] = G.dpar[0] + eps;
+            start_grad(G.dpar, RET_H1);
+            return;
+        }
+        case PC_MODE_DONE: {
+            const long long s = ic[IC_SUBJ];
+            for (int j = 0; j < n; ++j) a.modes[s * n + j] = G.mode[j];
+            for (int j = 0; j < n * n; ++j) a.hess[s * n * n + j] = G.hess[j];
+            a.conv[s] = ic[IC_CONV];
+            a.counts[2 * s] = ic[IC_FUN]; a.counts[2 * s + 1] = ic[IC_GRC];
+            st = a.do_sample ? PC_SAMPLE_INIT : ST_FETCH;
+            break;
+        }
+        case PC_SAMPLE_INIT: {                       // invVars.b, Vars.b (:304-305), eigen for rmvt / dmvt
+            bool bad = false;
+            for (int j = 0; j < n; ++j) if (!isfinite(G.mode[j])) bad = true;
+            for (int j = 0; j < n * n; ++j) {
+                if (!isfinite(G.hess[j])) bad = true;
+                G.invV[j] = G.hess[j] / a.c.scale;
+                G.Wa[j] = G.hess[j];
+            }
+            if (!bad && sv_inverse(G.Wa, n, G.Wb)) bad = true;
+            if (!bad) {
+                for (int i = 0; i < n; ++i)
+                    for (int j = 0; j < n; ++j) G.Wa[i + j * n] = 0.5 * (G.Wb[i + j * n] * a.c.scale + G.Wb[j + i * n] * a.c.scale);
+                sv_eigen_sym(G.Wa, n, G.X, G.Wb);    // values -> X, vectors -> Wb
+                if (!(G.X[n - 1] >= -1e-06 * fabs(G.X[0]))) bad = true;
+                for (int j = 0; j < n; ++j) if (!(G.X[j] > 0.0)) bad = true;
+            }
+            if (bad) {
+                const long long s = ic[IC_SUBJ];
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                for (long long k = 0; k < (long long)a.M * a.L; ++k) a.S[s * a.M * a.L + k] = nan;
+                a.acc_rate[s] = nan;
+                for (int j = 0; j < n; ++j) a.b_last[s * n + j] = nan;
+                a.conv[s] = 20;
+                st = ST_FETCH;
+                break;
+            }
+            for (int r = 0; r < n; ++r)
+                for (int c = 0; c < n; ++c) {
+                    G.Af[r + c * n] = G.Wb[r + c * n] * sqrt(G.X[c] > 0.0 ? G.X[c] : 0.0);
+                    double s = 0.0;
+                    for (int k = 0; k < n; ++k) s += G.Wb[r + k * n] * (G.Wb[c + k * n] / G.X[k]);
+                    G.invS[r + c * n] = s;
+                }
+            for (int j = 0; j < n; ++j) { G.b_old[j] = G.mode[j]; G.b_new[j] = G.mode[j]; }
+            ic[IC_M] = 0; ic[IC_NACC] = 0;
+            st = PC_MH_NEXT;
+            break;
+        }
+        case PC_MH_NEXT: {
+            if (ic[IC_M] >= a.M) { st = PC_SUBJ_DONE; break; }
+            ic[IC_ACT] = ACT_RNG; ic[IC_STATE] = ST_MH_RNG;      // all lanes: draws of step m + parameter set m
+            return;
+        }
+        case ST_MH_RNG: {                            // proposal m of rmvt() and its dmvt (:330-337,354-355)
+            const double den = sqrt(sc[SC_W] / a.c.df);
+            for (int r = 0; r < n; ++r) {
+                double s = 0.0;
+                for (int c = 0; c < n; ++c) s += G.Af[r + c * n] * G.z[c];
+                G.pb[r] = G.mode[r] + s / den;
+            }
+            double quad_p = 0.0, quad_o = 0.0;
+            for (int c = 0; c < n; ++c) {
+                double tp = 0.0, to = 0.0;
+                for (int r = 0; r < n; ++r) {
+                    tp += (G.pb[r] - G.mode[r]) * G.invS[r + c * n];
+                    to += (G.b_old[r] - G.mode[r]) * G.invV[r + c * n];
+                }
+                quad_p += tp * (G.pb[c] - G.mode[c]); quad_o += to * (G.b_old[c] - G.mode[c]);
+            }
+            sc[SC_DMVT_P] = -0.5 * (a.c.df + n) * log(1.0 + quad_p / a.c.df);
+            sc[SC_DMVT_O] = -0.5 * (a.c.df + n) * log(1.0 + quad_o / a.c.df);
+            for (int j = 0; j < n; ++j) G.btry[j] = G.pb[j];
+            post_full(ST_MH_P);
+            return;
+        }
+        case ST_MH_P: {
+            sc[SC_LP_P] = val;
+            for (int j = 0; j < n; ++j) G.btry[j] = G.b_old[j];
+            post_full(ST_MH_O);
+            return;
+        }
+        case ST_MH_O: {                              // :372-377
+            const double ea = exp(sc[SC_LP_P] + sc[SC_DMVT_O] - val - sc[SC_DMVT_P]);
+            if (!isnan(ea)) {
+                const double acc = ea < 1.0 ? ea : 1.0;
+                if (sc[SC_U] <= acc) { for (int j = 0; j < n; ++j) G.b_new[j] = G.pb[j]; ic[IC_NACC] += 1; }
+            }
+            sc[SC_CUM] = 0.0; ic[IC_L] = 0;
+            if (ic[IC_NH] > 0) {
+                for (int j = 0; j < n; ++j) G.btry[j] = G.b_new[j];
+                ic[IC_ACT] = ACT_EVAL; ic[IC_FULL] = 0; ic[IC_BLK] = 1; ic[IC_STATE] = ST_HZ;
+                return;
+            }
+            for (int l = 0; l < a.L; ++l) a.S[((long long)ic[IC_SUBJ] * a.M + ic[IC_M]) * a.L + l] = __longlong_as_double(0x7ff8000000000000LL);
+            for (int j = 0; j < n; ++j) G.b_old[j] = G.b_new[j];
+            ic[IC_M] += 1;
+            st = PC_MH_NEXT;
+            break;
+        }
+        case ST_HZ: {                                // :378-395
+            const int l = ic[IC_L];
+            sc[SC_CUM] += val;
+            a.S[((long long)ic[IC_SUBJ] * a.M + ic[IC_M]) * a.L + l] = a.c.log ? val : exp(sc[SC_CUM]);
+            if (l + 1 < ic[IC_NH]) {
+                ic[IC_L] = l + 1; ic[IC_BLK] = l + 2;
+                ic[IC_ACT] = ACT_EVAL; ic[IC_STATE] = ST_HZ;
+                return;
+            }
+            for (int l2 = l + 1; l2 < a.L; ++l2)        // intervals this subject does not have
+                a.S[((long long)ic[IC_SUBJ] * a.M + ic[IC_M]) * a.L + l2] = __longlong_as_double(0x7ff8000000000000LL);
+            for (int j = 0; j < n; ++j) G.b_old[j] = G.b_new[j];
+            ic[IC_M] += 1;
+            st = PC_MH_NEXT;
+            break;
+        }
+        case PC_SUBJ_DONE: {
+            const long long s = ic[IC_SUBJ];
+            a.acc_rate[s] = (double)ic[IC_NACC] / (a.M > 0 ? a.M : 1);
+            for (int j = 0; j < n; ++j) a.b_last[s * n + j] = G.b_new[j];
+            st = ST_FETCH;
+            break;
+        }
+        default:
+            ic[IC_ACT] = ACT_DONE; ic[IC_SUBJ] = -1;
+            return;
+        }
+    }
+}
+
+#ifndef JMB_SVFT_THREADS
+#define JMB_SVFT_THREADS 256
+#endif
+#ifndef JMB_SVFT_MIN_CTAS
+#define JMB_SVFT_MIN_CTAS 2
+#endif
+
+struct SvEvalGeneric {
+    const SvDesc& d; const SvLayout& L;
+    __device__ __forceinline__ double operator()(const double* rec, int blk, bool full, const double* sb, const double* sp,
+                                                 int lane, unsigned gmask) const {
+        return sv_eval_generic(d, L, rec, blk, full, sb, sp, lane, gmask);
+    }
+};
+template <class Spec>
+struct SvEvalStatic {
+    __device__ __forceinline__ double operator()(const double* rec, int blk, bool full, const double* sb, const double* sp,
+                                                 int lane, unsigned gmask) const {
+        return sv_eval_static<Spec>(rec, blk, full, sb, sp, lane, gmask);
+    }
+};
+
+template <class Eval>
+__device__ __forceinline__ void sv_run(const int q, const int O, const SvArgs& a, const Eval& eval) {
+    extern __shared__ double sv_smem[];
+    const int tid = threadIdx.x, lane = tid & (kSvG - 1), grp = tid / kSvG;
+    const unsigned gmask = 0xFFFFu << (16 * ((tid & 31) >> 4));
+    const int gd = (sv_group_doubles(q, a.ps_len) + 1) / 2 * 2;
+    // views derived from the shared-memory window itself, so that the hot loads compile to LDS
+    double* gbase = sv_smem + (size_t)grp * gd;
+    const double* sp = gbase;                        // parameter set in use
+    const double* sb = gbase + a.ps_len;             // point of the posted request
+    SvG G;
+    sv_bind(G, gbase, q, a.ps_len);
+    volatile int* ic = reinterpret_cast<int*>(gbase + (sv_group_doubles(q, a.ps_len) - (IC_N + 1) / 2));
+    if (lane == 0) {
+        for (int j = 0; j < IC_N; ++j) G.ic[j] = 0;
+        G.ic[IC_O] = O;
+        G.ic[IC_STATE] = ST_FETCH; G.ic[IC_SUBJ] = -1;
+        sv_advance(a, q, G, 0.0);
+    }
+    __syncwarp();
+    for (;;) {
+        const int act = ic[IC_ACT];
+        const bool done = (act == ACT_DONE);
+        if (__all_sync(0xFFFFFFFFu, done)) break;
+        double val = 0.0;
+        if (act == ACT_EVAL) {
+            const int s = ic[IC_SUBJ];
+            val = eval(a.rec + a.off[s], ic[IC_BLK], ic[IC_FULL] != 0, sb, sp, lane, gmask);
+        } else if (act == ACT_RNG) {
+            // draws of MH step m (streams of DESIGN.md section 4, key (seed, 'SVFT')) and parameter set m
+            const uint32_t gid = (uint32_t)(a.subject_offset + ic[IC_SUBJ]), m = (uint32_t)ic[IC_M];
+            if (lane < (q + 1) / 2) {
+                double z0, z1;
+                rnorm_pair(a.c.seed, kSvKey, gid, m, (uint32_t)lane, 0u, z0, z1);
+                G.z[2 * lane] = z0; G.z[2 * lane + 1] = z1;
+            } else if (lane == 8) {
+                G.sc[SC_W] = rgamma_dev(a.c.seed, kSvKey, gid, m, 0.5 * a.c.df, 2.0);    // rchisq(df)
+            } else if (lane == 9) {
+                uint32_t r[4];
+                philox4x32(a.c.seed, kSvKey, gid, m, 0u, 1u, r);
+                G.sc[SC_U] = u01(r[0], r[1]);
+            }
+            const double* src = a.par_draws + (size_t)m * a.ps_len;
+            for (int j = lane; j < a.ps_len; j += kSvG) gbase[j] = src[j];
+        }
+        __syncwarp();
+        if (lane == 0 && !done) sv_advance(a, q, G, val);
+        __syncwarp();
+    }
+}
+
+template <class Spec>
+__global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS) jmb_svft_static(const __grid_constant__ SvArgs a) {
+    sv_run(Spec::d.q, Spec::d.O, a, SvEvalStatic<Spec>{});
+}
+
+__global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS)
+jmb_svft_generic(const __grid_constant__ SvMeta mm, const __grid_constant__ SvArgs a) {
+    sv_run(mm.d.q, mm.d.O, a, SvEvalGeneric{mm.d, mm.L});
+}
+
+// ---- Mean / Median / Lower / Upper over the M draws (R/survfitJM.mvJMbayes.R:400-414) ----------------------------
+// one CTA per subject; per interval a bitonic sort of the M values in shared memory (NaN removed, na.rm = TRUE),
+// median.default and quantile(type = 7).  out: [n][4][L] as L x 4 per subject (column-major).
+__global__ void __launch_bounds__(128) jmb_svft_summary(const double* __restrict__ S, const long long* __restrict__ off,
+                                                        const double* __restrict__ rec, const int O, const int n,
+                                                        const int M, const int L, const int Mp, const double p_lo,
+                                                        const double p_hi, double* __restrict__ out) {
+    extern __shared__ double s_x[];                  // [Mp]
+    __shared__ int s_cnt;
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const int nh = reinterpret_cast<const int*>(rec + off[i])[O];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int l = 0; l < L; ++l) {
+        double* o4 = out + (size_t)i * 4 * L + l;
+        if (l >= nh) {
+            if (tid < 4) o4[(size_t)tid * L] = nan;
+            continue;
+        }
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        int local = 0;
+        for (int m = tid; m < Mp; m += blockDim.x) {
+            double v = (m < M) ? S[((size_t)i * M + m) * L + l] : INFINITY;
+            if (m < M && isnan(v)) v = INFINITY; else if (m < M) local++;
+            s_x[m] = v;
+        }
+        atomicAdd(&s_cnt, local);
+        __syncthreads();
+        for (int k = 2; k <= Mp; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < Mp; t += blockDim.x) {
+                    const int ixj = t ^ j;
+                    if (ixj > t) {
+                        const double x = s_x[t], y = s_x[ixj];
+                        const bool up = ((t & k) == 0);
+                        if ((x > y) == up) { s_x[t] = y; s_x[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (tid == 0) {
+            const int cnt = s_cnt;                   // +inf paddings sort last; genuine +inf values are counted
+            if (cnt == 0) { o4[0] = nan; o4[L] = nan; o4[2 * (size_t)L] = nan; o4[3 * (size_t)L] = nan; }
+            else {
+                double sum = 0.0;                    // rowMeans(na.rm = TRUE) in draw order
+                for (int m = 0; m < M; ++m) { const double v = S[((size_t)i * M + m) * L + l]; if (!isnan(v)) sum += v; }
+                o4[0] = sum / cnt;
+                const int half = (cnt + 1) / 2;
+                o4[L] = (cnt % 2 == 1) ? s_x[half - 1] : (s_x[half - 1] + s_x[half]) / 2.0;
+                const double pr[2] = {p_lo, p_hi};
+                for (int k = 0; k < 2; ++k) {
+                    const double index = 1.0 + (cnt - 1) * pr[k];
+                    const double lo = floor(index), hi = ceil(index);
+                    double qs = s_x[(int)lo - 1];
+                    const double xh = s_x[(int)hi - 1];
+                    if (index > lo && xh != qs) { const double h = index - lo; qs = (1.0 - h) * qs + h * xh; }
+                    o4[(size_t)(2 + k) * L] = qs;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace jmb
