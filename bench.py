@@ -34,7 +34,13 @@ WORKLOADS = {
     "config4_shard": ("config4", 125000),   # 1M-subject config 4 split over 8 GPUs: 125k per GPU
     "config3": ("config3", 100000),
     "config2": ("config2", 100000),
+    # survfitJM dynamic predictions (BASELINE config 5): M = 200 draws x L = 10 horizons per subject; one "step" =
+    # the whole per-subject loop (mode search + MH over the draws + horizon integrals + summaries) for every subject
+    "config5": ("config3", 25000),
 }
+SVFT_M, SVFT_L = 200, 10
+SVFT_METRIC = "subject-draws/sec of survfitJM dynamic predictions (M=200 draws x L=10 horizons per subject)"
+SVFT_UNIT = "subject-draws/s"
 CPU_SAMPLE_N = 20000
 
 
@@ -353,8 +359,143 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 5: survfitJM.mvJMbayes() loop (R/survfitJM.mvJMbayes.R:277-414)
+# ------------------------------------------------------------------------------------------------
+def _svft_case(n, seed):
+    from jmbayes_b200 import survfit as sv
+    from jmbayes_b200.cohorts import make_cohort
+    c = make_cohort("config3", n=n, seed=seed)
+    d = sv.newdata_designs(c, L=SVFT_L)
+    means, draws = sv.posterior_draws(c, M=SVFT_M)
+    return d, means, draws
+
+
+def _svft_cpu(n, workers):
+    """The restated R loop (oracle/jmb_oracle_svft.c) on the host cores, subjects split over worker threads."""
+    from oracle import oracle, oracle_svft
+    oracle.build()
+    d, means, draws = _svft_case(n, 4242)
+    t0 = time.perf_counter()
+    oracle_svft.survfitJM(d, means, draws, threads=workers, full=False)
+    dt = time.perf_counter() - t0
+    return n * SVFT_M / dt, dt
+
+
+def run_config5_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    workers = max(1, (os.cpu_count() or 1) - 1)
+    _, dt0 = _svft_cpu(40 * workers, workers)              # probe, then ~15 s of CPU work
+    n = int(min(40000, max(40 * workers, 40 * workers * 15.0 / max(dt0, 1e-3))))
+    val, dt = _svft_cpu(n, workers)
+    line = {"impl": "reference", "metric": SVFT_METRIC, "value": val, "unit": SVFT_UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config5", "subjects": n, "M": SVFT_M, "L": SVFT_L,
+                       "note": "restated survfitJM loop (R absent from the image): optim BFGS + MH over M draws + horizon integrals"},
+            "cpu_baseline": {"value": val, "unit": SVFT_UNIT, "cores": workers, "kind": "port",
+                             "sample": f"{n} subjects x {SVFT_M} draws x {SVFT_L} horizons, {workers} worker threads ({dt:.1f} s)"},
+            "e2e": {"value": val, "unit": SVFT_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_config5(args):
+    import torch
+    import torch.distributed as dist
+    from jmbayes_b200 import build
+    from jmbayes_b200 import survfit as sv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not os.path.exists(build.LIB):
+        raise RuntimeError("libjmb200.so missing: run __graft_entry__.build()")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the hot path has no CPU fallback")
+    n = args.n_per_gpu or WORKLOADS["config5"][1]
+    steps, warmup = min(args.steps, 20), min(args.warmup, 3)
+    d, means, draws = _svft_case(n, 5000 + rank)          # subjects shard over ranks; no collective on this path
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    h = sv.SurvFit(d, device=local, subject_offset=rank * n)
+    for _ in range(max(warmup, 1)):
+        h.survfitJM(means, draws, full=False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = h.info()["launches"]
+    dev_ms, t0 = 0.0, time.perf_counter()
+    for _ in range(steps):                                 # every step: params H2D, the kernels, summaries D2H
+        h.survfitJM(means, draws, full=False)
+        dev_ms += h.info()["last_kernel_ms"]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    info = h.info()
+    t = torch.tensor([dev_ms, wall], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall = float(t[0].item()), float(t[1].item())
+    n_total = n * world
+    value = n_total * SVFT_M * steps / (dev_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    rec_bytes = info["record_bytes_per_subject"]
+    out_bytes = 8.0 * SVFT_M * SVFT_L * 2 + 8.0 * (4 * SVFT_L + 6 * 6 + 6 * 2 + 1)   # S written + re-read by the summary kernel, results
+    achieved = (rec_bytes + out_bytes) * n / (dev_ms / steps * 1e-3) / 1e9
+    pbytes = 8.0 * (SVFT_M + 1) * 70
+    line = {
+        "metric": SVFT_METRIC, "value": value, "unit": SVFT_UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "config5", "cohort": "config3 fit, all subjects as newdata truncated at 0.5 T", "subjects_per_gpu": n,
+                   "subjects_total": n_total, "M": SVFT_M, "L": SVFT_L, "q": 6, "outcomes": 3, "K": 15,
+                   "parallelism": f"subject-shards x{world} (no collective)",
+                   "l2": "each subject's record (%.1f kB) is read once from HBM and re-used ~2900 times from L1/L2" % (rec_bytes / 1e3)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "jmb_svft_static<SvSpecThree>", "kernel_ms": dev_ms / steps,
+                     "alg_bytes_per_subject": rec_bytes + out_bytes,
+                     "note": "compulsory bytes are ~1e-3 of what the time would allow: this kernel is bound by fp64 issue "
+                             "(~2900 quadrature / visit evaluations per subject), not by HBM; see profiles/"},
+        "e2e": {"value": n_total * SVFT_M * steps / wall, "unit": SVFT_UNIT, "h2d_bytes_per_step": pbytes,
+                "d2h_bytes_per_step": 8.0 * n * (4 * SVFT_L + 6 + 36 + 6 + 1) + 12.0 * n,
+                "what": "survfitJM() through the C ABI with host buffers: parameter H2D, kernels, modes / Hessians / summaries D2H, wall clock"},
+        "gpu_launches": int(info["launches"] - l0), "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        workers = max(1, (os.cpu_count() or 1) - 1)
+        _, dt0 = _svft_cpu(40 * workers, workers)
+        nc = int(min(40000, max(40 * workers, 40 * workers * 12.0 / max(dt0, 1e-3))))
+        val, dt = _svft_cpu(nc, workers)
+        line["cpu_baseline"] = {"value": val, "unit": SVFT_UNIT, "cores": workers, "kind": "port",
+                                "sample": f"{nc} subjects x {SVFT_M} draws x {SVFT_L} horizons, restated R loop, {workers} threads ({dt:.1f} s)"}
+    h.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
+    if args.workload == "config5":
+        return run_config5_reference(args) if args.impl == "reference" else run_config5(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -54,7 +54,7 @@ struct jmb_svft_handle_s {
     float last_ms = 0.f;
     long long launches = 0;
     int kernel = 0;                                 // 0 generic, 1 three outcomes, 2 value gaussian
-    int grid = 0, smem = 0;
+    int grid[2] = {0, 0}, smem = 0;                 // launch shape of the mode-search and of the sampling kernel
 };
 
 extern "C" int jmb_svft_destroy(jmb_svft_handle h) {
@@ -193,14 +193,38 @@ extern "C" int jmb_svft_create(const jmb_svft_data* d, int device, jmb_svft_hand
         md.z_ones0[k] = (md.qk[k] >= 1 && all_ones(d->Z[k], d->N[k], false)) ? 1 : 0;
         md.x_ones0[k] = all_ones(d->X[k], d->N[k], false) ? 1 : 0;
     }
+    // XXs / ZZs columns: all ones -> not stored; identical to an earlier column over every row -> stored once
+    struct ColRef { const double* q; const double* h; };
+    std::vector<ColRef> pool;
+    auto same_col = [&](const double* a, const double* b, long long rows, bool horizon) {
+        if (a == b) return true;
+        std::atomic<int> ok{1};
+        parallel_for(rows, [&, a, b, horizon](long long lo, long long hi) {
+            for (long long r = lo; r < hi; ++r) {
+                if (horizon && !live_h(r)) continue;
+                if (a[r] != b[r]) { ok.store(0); return; }
+            }
+        });
+        return ok.load() == 1;
+    };
+    auto place = [&](const double* cq, const double* ch) -> int {
+        if (all_ones(cq, nK, false) && (!nH || all_ones(ch, nH, true))) return -1;
+        for (size_t c = 0; c < pool.size(); ++c)
+            if (same_col(cq, pool[c].q, nK, false) && (!nH || same_col(ch, pool[c].h, nH, true))) return (int)c;
+        pool.push_back({cq, ch});
+        return (int)pool.size() - 1;
+    };
     for (int t = 0; t < T; ++t) {
-        md.zz_ones0[t] = (md.rt[t] >= 1 && all_ones(d->ZZs[t], nK, false) && (!nH || all_ones(d->ZZs_h[t], nH, true))) ? 1 : 0;
-        md.xx_ones0[t] = (md.ft[t] >= 1 && all_ones(d->XXs[t], nK, false) && (!nH || all_ones(d->XXs_h[t], nH, true))) ? 1 : 0;
+        for (int f = 0; f < md.ft[t]; ++f)
+            md.xx_col[t][f] = place(d->XXs[t] + (long long)f * nK, nH ? d->XXs_h[t] + (long long)f * nH : nullptr);
+        for (int j = 0; j < md.rt[t]; ++j)
+            md.zz_col[t][j] = place(d->ZZs[t] + (long long)j * nK, nH ? d->ZZs_h[t] + (long long)j * nH : nullptr);
         bool uo = true;
         for (int u = 0; u < md.ut[t] && uo; ++u)
             uo = all_ones(d->Us[t] + (long long)u * nK, nK, false) && (!nH || all_ones(d->Us_h[t] + (long long)u * nH, nH, true));
         md.u_ones[t] = uo ? 1 : 0;
     }
+    md.NC = (int)pool.size();
     {
         std::atomic<int> ok{p > 0 ? 1 : 0};
         if (p > 0)
@@ -254,12 +278,9 @@ extern "C" int jmb_svft_create(const jmb_svft_data* d, int device, jmb_svft_hand
                     w1off[k] = off;
                     for (int j = 0; j < WB; ++j) blk[LY.b_W1v + j * kSvG + k] = W1x[src + (long long)(off + j) * rows];
                     if (!md.w2_const) for (int j = 0; j < p; ++j) blk[LY.b_W2 + j * kSvG + k] = W2x[src + (long long)j * rows];
+                    for (int c = 0; c < md.NC; ++c) blk[LY.b_col + c * kSvG + k] = (hz ? pool[c].h : pool[c].q)[src];
                     for (int t = 0; t < T; ++t) {
-                        const double* XXx = hz ? d->XXs_h[t] : d->XXs[t];
-                        const double* ZZx = hz ? d->ZZs_h[t] : d->ZZs[t];
                         const double* Ux = hz ? d->Us_h[t] : d->Us[t];
-                        for (int f2 = md.xx_ones0[t]; f2 < md.ft[t]; ++f2) blk[LY.b_XX[t] + (f2 - md.xx_ones0[t]) * kSvG + k] = XXx[src + (long long)f2 * rows];
-                        for (int j = md.zz_ones0[t]; j < md.rt[t]; ++j) blk[LY.b_ZZ[t] + (j - md.zz_ones0[t]) * kSvG + k] = ZZx[src + (long long)j * rows];
                         if (!md.u_ones[t]) for (int u = 0; u < md.ut[t]; ++u) blk[LY.b_U[t] + u * kSvG + k] = Ux[src + (long long)u * rows];
                     }
                 }
@@ -311,12 +332,16 @@ extern "C" int jmb_svft_create(const jmb_svft_data* d, int device, jmb_svft_hand
     const int gd = (sv_group_doubles(q, h->ps_len) + 1) / 2 * 2;
     h->smem = (int)sizeof(double) * groups * gd;
     if (h->smem > 220 * 1024) { jmb_svft_destroy(h); return fail("jmb_svft_create: model too large for the shared-memory state"); }
-    const void* fn = h->kernel == 1 ? (const void*)jmb_svft_static<SvSpecThree> : (h->kernel == 2 ? (const void*)jmb_svft_static<SvSpecValue> : (const void*)jmb_svft_generic);
-    CUH(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
-    int per_sm = 1;
-    CUH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, JMB_SVFT_THREADS, h->smem));
-    per_sm = std::max(per_sm, 1);
-    h->grid = std::max(1, std::min(h->num_sms * per_sm, (n + groups - 1) / groups));
+    const void* fns[2] = {
+        h->kernel == 1 ? (const void*)jmb_svft_modes_static<SvSpecThree> : (h->kernel == 2 ? (const void*)jmb_svft_modes_static<SvSpecValue> : (const void*)jmb_svft_modes_generic),
+        h->kernel == 1 ? (const void*)jmb_svft_sample_static<SvSpecThree> : (h->kernel == 2 ? (const void*)jmb_svft_sample_static<SvSpecValue> : (const void*)jmb_svft_sample_generic)};
+    for (int f = 0; f < 2; ++f) {
+        CUH(cudaFuncSetAttribute(fns[f], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+        int per_sm = 1;
+        CUH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fns[f], JMB_SVFT_THREADS, h->smem));
+        per_sm = std::max(per_sm, 1);
+        h->grid[f] = std::max(1, std::min(h->num_sms * per_sm, (n + groups - 1) / groups));
+    }
 #undef CUH
 #undef BAD
     *out = h;
@@ -407,11 +432,20 @@ static int run(jmb_svft_handle h, const jmb_svft_params* pm, const jmb_svft_para
     a.acc_rate = h->d_acc; a.b_last = h->d_blast; a.work = h->d_work;
 
     CU(cudaEventRecord(h->ev0, h->stream));
-    if (h->kernel == 1) jmb_svft_static<SvSpecThree><<<h->grid, JMB_SVFT_THREADS, h->smem, h->stream>>>(a);
-    else if (h->kernel == 2) jmb_svft_static<SvSpecValue><<<h->grid, JMB_SVFT_THREADS, h->smem, h->stream>>>(a);
-    else jmb_svft_generic<<<h->grid, JMB_SVFT_THREADS, h->smem, h->stream>>>(h->mm, a);
-    h->launches += 1;
-    CU(cudaGetLastError());
+    if (do_modes) {
+        if (h->kernel == 1) jmb_svft_modes_static<SvSpecThree><<<h->grid[0], JMB_SVFT_THREADS, h->smem, h->stream>>>(a);
+        else if (h->kernel == 2) jmb_svft_modes_static<SvSpecValue><<<h->grid[0], JMB_SVFT_THREADS, h->smem, h->stream>>>(a);
+        else jmb_svft_modes_generic<<<h->grid[0], JMB_SVFT_THREADS, h->smem, h->stream>>>(h->mm, a);
+        h->launches += 1;
+        CU(cudaGetLastError());
+    }
+    if (do_sample) {
+        if (h->kernel == 1) jmb_svft_sample_static<SvSpecThree><<<h->grid[1], JMB_SVFT_THREADS, h->smem, h->stream>>>(a);
+        else if (h->kernel == 2) jmb_svft_sample_static<SvSpecValue><<<h->grid[1], JMB_SVFT_THREADS, h->smem, h->stream>>>(a);
+        else jmb_svft_sample_generic<<<h->grid[1], JMB_SVFT_THREADS, h->smem, h->stream>>>(h->mm, a);
+        h->launches += 1;
+        CU(cudaGetLastError());
+    }
     if (do_sample && L > 0) {
         int Mp = 1;
         while (Mp < M) Mp <<= 1;

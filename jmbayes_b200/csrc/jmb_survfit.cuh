@@ -7,14 +7,19 @@
 // a .Call into src/survfitJM_mvJMbayes.cpp:140-187.  optim's BFGS (vmmin) and optimhess are R's own C code
 // (src/appl/optim.c, src/library/stats/src/optim.c), restated here from the published algorithm.
 //
-// Mapping: one 16-lane group per subject (two subjects per warp).  All 16 lanes evaluate log_post_RE_svft /
-// survPred_svft_2 together - one Gauss-Kronrod node per lane, the visit rows lane-strided - and lane 0 of
-// the group is the subject's control thread: it owns a resumable state machine (BFGS line search,
-// central-difference gradient, Hessian, MH loop) that consumes the value of the previous evaluation and
-// posts the next request.  Both groups of a warp therefore always meet in the same evaluation code, no
-// matter where each subject is in its own algorithm; groups fetch new subjects from an atomic counter.
-// The subject's design record is read from HBM once and stays L1/L2-resident for its ~3000 evaluations:
-// the kernel is bound by fp64 issue, not by HBM.
+// Mapping: one 16-lane group per subject (two subjects per warp); all 16 lanes evaluate log_post_RE_svft /
+// survPred_svft_2 together - one Gauss-Kronrod node per lane, the visit rows lane-strided.
+//   jmb_svft_modes_*  : mode search.  Lane 0 of the group is the subject's control thread: a resumable vmmin state
+//                       machine that posts coarse requests (one function value, or a whole central-difference
+//                       gradient = 2q values), so both groups of a warp always meet in the same evaluation loop no
+//                       matter where each subject is in its own line search; groups pull subjects from an atomic
+//                       counter.
+//   jmb_svft_sample_* : the M Metropolis-Hastings steps and the horizon integrals as straight-line code; the
+//                       vector work (proposal, quadratic forms, state copies) is spread over the lanes and the two
+//                       subjects of a warp stay in lock-step (every step costs 2 + n_horizons evaluations).
+//   jmb_svft_summary  : per subject and interval, sort of the M values and R's type-7 summaries.
+// A subject's design record is read from HBM once per kernel and stays L1/L2-resident for its ~3000 evaluations:
+// the path is bound by fp64 issue, not by HBM.
 #pragma once
 #include "../../include/jmb200_survfit.h"
 #include "jmb_device.cuh"
@@ -28,19 +33,24 @@ constexpr uint32_t kSvKey = 0x53564654u;     // second half of the Philox key of
 // model shape of a survfit handle; constexpr-constructible so that precompiled shapes fold away
 struct SvDesc {
     int O, q, T, A, p, K, WB, w2_const, NB;  // NB = sum of p_k
+    int NC;                                  // distinct non-constant XXs / ZZs columns stored per quadrature row
     int fam[kMaxO], link[kMaxO], qk[kMaxO], z_ones0[kMaxO], pk[kMaxO], x_ones0[kMaxO], boff[kMaxO];
     int re_inds[kMaxO][kSvQ];
-    int rt[kMaxT], ut[kMaxT], tf[kMaxT], zz_ones0[kMaxT], u_ones[kMaxT], ft[kMaxT], xx_ones0[kMaxT], outc[kMaxT];
+    int rt[kMaxT], ut[kMaxT], tf[kMaxT], u_ones[kMaxT], ft[kMaxT], outc[kMaxT];
     int re2[kMaxT][kMaxRT], col[kMaxT][kMaxUT], indf[kMaxT][kSvFT];
+    // where column f of XXs[[t]] / column j of ZZs[[t]] lives: -1 = all ones (not stored), else pooled column
+    int xx_col[kMaxT][kSvFT], zz_col[kMaxT][kMaxRT];
 };
 
 // Record of one subject (doubles): int32 visit counts [O] + number of prediction intervals | W2 row (when the
 // W2s rows repeat) | nh + 1 quadrature blocks (block 0: (0, last.time], block l + 1: interval l), each field
 // stored [column][16 lanes] | longitudinal rows per outcome: y[v] | stored X columns | stored Z columns.
-// All-ones first columns of X / Z / XXs / ZZs and all-ones Us are not stored (decided from the data).
+// All-ones columns of XXs / ZZs / Us and all-ones first columns of X / Z are not stored, and XXs / ZZs columns
+// that are identical over all rows (e.g. the time variable of every value term) are stored once (decided from
+// the data by jmb_svft_create, so it never changes results).
 struct SvLayout {
     int o_V, o_W2c, o_blk0, blk;
-    int b_Pw, b_W1off, b_W1v, b_W2, b_XX[kMaxT], b_ZZ[kMaxT], b_U[kMaxT];
+    int b_Pw, b_W1off, b_W1v, b_W2, b_col, b_U[kMaxT];
     int long_cols[kMaxO];
     int ps_betas, ps_isig, ps_gam, ps_alp, ps_invD, ps_Bs;   // parameter set: ... | invD q x q | Bs_gammas [B]
 };
@@ -58,11 +68,8 @@ JMB_HD constexpr SvLayout sv_make_layout(const SvDesc& d) {
     L.b_W1v = b; b += d.WB * kSvG;
     L.b_W2 = b;
     if (!d.w2_const) b += d.p * kSvG;
-    for (int t = 0; t < d.T; ++t) {
-        L.b_XX[t] = b; b += (d.ft[t] - d.xx_ones0[t]) * kSvG;
-        L.b_ZZ[t] = b; b += (d.rt[t] - d.zz_ones0[t]) * kSvG;
-        L.b_U[t] = b; b += (d.u_ones[t] ? 0 : d.ut[t]) * kSvG;
-    }
+    L.b_col = b; b += d.NC * kSvG;
+    for (int t = 0; t < d.T; ++t) { L.b_U[t] = b; b += (d.u_ones[t] ? 0 : d.ut[t]) * kSvG; }
     L.blk = b;
     for (int k = 0; k < d.O; ++k) L.long_cols[k] = 1 + (d.pk[k] - d.x_ones0[k]) + (d.qk[k] - d.z_ones0[k]);
     int s = 0;
@@ -77,18 +84,18 @@ JMB_HD constexpr SvLayout sv_make_layout(const SvDesc& d) {
 
 JMB_HD constexpr bool sv_same_desc(const SvDesc& a, const SvDesc& b) {
     if (a.O != b.O || a.q != b.q || a.T != b.T || a.A != b.A || a.p != b.p || a.K != b.K || a.WB != b.WB ||
-        a.w2_const != b.w2_const || a.NB != b.NB) return false;
+        a.w2_const != b.w2_const || a.NB != b.NB || a.NC != b.NC) return false;
     for (int k = 0; k < a.O; ++k) {
         if (a.fam[k] != b.fam[k] || a.link[k] != b.link[k] || a.qk[k] != b.qk[k] || a.z_ones0[k] != b.z_ones0[k] ||
             a.pk[k] != b.pk[k] || a.x_ones0[k] != b.x_ones0[k] || a.boff[k] != b.boff[k]) return false;
         for (int j = 0; j < a.qk[k]; ++j) if (a.re_inds[k][j] != b.re_inds[k][j]) return false;
     }
     for (int t = 0; t < a.T; ++t) {
-        if (a.rt[t] != b.rt[t] || a.ut[t] != b.ut[t] || a.tf[t] != b.tf[t] || a.zz_ones0[t] != b.zz_ones0[t] ||
-            a.u_ones[t] != b.u_ones[t] || a.ft[t] != b.ft[t] || a.xx_ones0[t] != b.xx_ones0[t] || a.outc[t] != b.outc[t]) return false;
-        for (int j = 0; j < a.rt[t]; ++j) if (a.re2[t][j] != b.re2[t][j]) return false;
+        if (a.rt[t] != b.rt[t] || a.ut[t] != b.ut[t] || a.tf[t] != b.tf[t] || a.u_ones[t] != b.u_ones[t] ||
+            a.ft[t] != b.ft[t] || a.outc[t] != b.outc[t]) return false;
+        for (int j = 0; j < a.rt[t]; ++j) if (a.re2[t][j] != b.re2[t][j] || a.zz_col[t][j] != b.zz_col[t][j]) return false;
         for (int u = 0; u < a.ut[t]; ++u) if (a.col[t][u] != b.col[t][u]) return false;
-        for (int f = 0; f < a.ft[t]; ++f) if (a.indf[t][f] != b.indf[t][f]) return false;
+        for (int f = 0; f < a.ft[t]; ++f) if (a.indf[t][f] != b.indf[t][f] || a.xx_col[t][f] != b.xx_col[t][f]) return false;
     }
     return true;
 }
@@ -98,6 +105,7 @@ JMB_HD constexpr bool sv_same_desc(const SvDesc& a, const SvDesc& b) {
 JMB_HD constexpr SvDesc sv_desc_three_outcomes() {
     SvDesc d{};
     d.O = 3; d.q = 6; d.T = 6; d.A = 6; d.p = 2; d.K = 15; d.WB = 4; d.w2_const = 1; d.NB = 6;
+    d.NC = 1;                                 // the time variable, shared by the three value terms
     d.fam[0] = JMB_FAM_GAUSSIAN; d.link[0] = JMB_LINK_IDENTITY;
     d.fam[1] = JMB_FAM_BINOMIAL; d.link[1] = JMB_LINK_LOGIT;
     d.fam[2] = JMB_FAM_POISSON; d.link[2] = JMB_LINK_LOG;
@@ -105,11 +113,12 @@ JMB_HD constexpr SvDesc sv_desc_three_outcomes() {
         d.qk[k] = 2; d.z_ones0[k] = 1; d.pk[k] = 2; d.x_ones0[k] = 1; d.boff[k] = 2 * k;
         d.re_inds[k][0] = 2 * k; d.re_inds[k][1] = 2 * k + 1;
         const int tv = 2 * k, ts = 2 * k + 1;
-        d.rt[tv] = 2; d.ut[tv] = 1; d.tf[tv] = JMB_TF_IDENTITY; d.zz_ones0[tv] = 1; d.u_ones[tv] = 1;
-        d.ft[tv] = 2; d.xx_ones0[tv] = 1; d.outc[tv] = k; d.indf[tv][0] = 0; d.indf[tv][1] = 1;
+        d.rt[tv] = 2; d.ut[tv] = 1; d.tf[tv] = JMB_TF_IDENTITY; d.u_ones[tv] = 1;
+        d.ft[tv] = 2; d.outc[tv] = k; d.indf[tv][0] = 0; d.indf[tv][1] = 1;
+        d.xx_col[tv][0] = -1; d.xx_col[tv][1] = 0; d.zz_col[tv][0] = -1; d.zz_col[tv][1] = 0;
         d.re2[tv][0] = 2 * k; d.re2[tv][1] = 2 * k + 1; d.col[tv][0] = tv;
-        d.rt[ts] = 1; d.ut[ts] = 1; d.tf[ts] = JMB_TF_IDENTITY; d.zz_ones0[ts] = 1; d.u_ones[ts] = 1;
-        d.ft[ts] = 1; d.xx_ones0[ts] = 1; d.outc[ts] = k; d.indf[ts][0] = 1;
+        d.rt[ts] = 1; d.ut[ts] = 1; d.tf[ts] = JMB_TF_IDENTITY; d.u_ones[ts] = 1;
+        d.ft[ts] = 1; d.outc[ts] = k; d.indf[ts][0] = 1; d.xx_col[ts][0] = -1; d.zz_col[ts][0] = -1;
         d.re2[ts][0] = 2 * k + 1; d.col[ts][0] = ts;
     }
     return d;
@@ -118,10 +127,11 @@ JMB_HD constexpr SvDesc sv_desc_three_outcomes() {
 // one gaussian outcome, random intercept + slope, current-value association (configs 1 / 2)
 JMB_HD constexpr SvDesc sv_desc_value_gaussian() {
     SvDesc d{};
-    d.O = 1; d.q = 2; d.T = 1; d.A = 1; d.p = 2; d.K = 15; d.WB = 4; d.w2_const = 1; d.NB = 2;
+    d.O = 1; d.q = 2; d.T = 1; d.A = 1; d.p = 2; d.K = 15; d.WB = 4; d.w2_const = 1; d.NB = 2; d.NC = 1;
     d.fam[0] = JMB_FAM_GAUSSIAN; d.link[0] = JMB_LINK_IDENTITY; d.qk[0] = 2; d.z_ones0[0] = 1; d.pk[0] = 2; d.x_ones0[0] = 1;
     d.re_inds[0][0] = 0; d.re_inds[0][1] = 1;
-    d.rt[0] = 2; d.ut[0] = 1; d.tf[0] = JMB_TF_IDENTITY; d.zz_ones0[0] = 1; d.u_ones[0] = 1; d.ft[0] = 2; d.xx_ones0[0] = 1;
+    d.rt[0] = 2; d.ut[0] = 1; d.tf[0] = JMB_TF_IDENTITY; d.u_ones[0] = 1; d.ft[0] = 2;
+    d.xx_col[0][0] = -1; d.xx_col[0][1] = 0; d.zz_col[0][0] = -1; d.zz_col[0][1] = 0;
     d.indf[0][0] = 0; d.indf[0][1] = 1; d.re2[0][0] = 0; d.re2[0][1] = 1; d.col[0][0] = 0;
     return d;
 }
@@ -151,13 +161,10 @@ struct SvArgs {
 };
 
 // ---- per-group shared state --------------------------------------------------------------------------
-enum { SC_FMIN = 0, SC_F, SC_GP, SC_STEP, SC_F1, SC_X1, SC_W, SC_U, SC_DMVT_P, SC_DMVT_O, SC_LP_P, SC_CUM, SC_EPS_H, SC_N };
-enum { IC_SUBJ = 0, IC_STATE, IC_ACT, IC_FULL, IC_BLK, IC_GI, IC_RET, IC_COUNT, IC_FUN, IC_GRC, IC_ILAST, IC_ITER,
-       IC_HI, IC_M, IC_L, IC_NACC, IC_NH, IC_CONV, IC_O, IC_N };
-enum { ACT_EVAL = 0, ACT_RNG = 1, ACT_DONE = 2 };
-enum { ST_FETCH = 0, ST_F0, ST_GRAD_P, ST_GRAD_M, ST_LS, ST_MH_RNG, ST_MH_P, ST_MH_O, ST_HZ,
-       PC_LOOP_TOP, PC_LS_TRY, PC_LS_DONE, PC_LOOP_END, PC_VM_DONE, PC_GRAD_DONE, PC_MODE_DONE, PC_SAMPLE_INIT,
-       PC_MH_NEXT, PC_SUBJ_DONE };
+enum { SC_FMIN = 0, SC_F, SC_GP, SC_STEP, SC_F1, SC_X1, SC_W, SC_U, SC_EPS_H, SC_N };
+enum { IC_SUBJ = 0, IC_STATE, IC_NEV, IC_RET, IC_COUNT, IC_FUN, IC_GRC, IC_ILAST, IC_ITER, IC_HI, IC_CONV, IC_BAD, IC_N };
+// states of the mode-search control thread: ST_* consume the result of the posted request, PC_* are internal
+enum { ST_FETCH = 0, ST_F0, ST_GRAD, ST_LS, PC_LOOP_TOP, PC_LS_TRY, PC_LS_DONE, PC_LOOP_END, PC_VM_DONE, PC_MODE_DONE };
 enum { RET_INIT = 0, RET_LS, RET_H1, RET_H2 };
 
 struct SvG {                // views into one group's shared memory
@@ -228,12 +235,16 @@ __device__ __forceinline__ double sv_eval_generic(const SvDesc& d, const SvLayou
     double s3 = 0.0;
     for (int t = 0; t < d.T; ++t) {
         const int bo = d.boff[d.outc[t]];
-        double xb = d.xx_ones0[t] ? sp[L.ps_betas + bo + d.indf[t][0]] : 0.0;
-        for (int f = d.xx_ones0[t]; f < d.ft[t]; ++f)
-            xb += blk[L.b_XX[t] + (f - d.xx_ones0[t]) * kSvG + lane] * sp[L.ps_betas + bo + d.indf[t][f]];
-        double zb = d.zz_ones0[t] ? sb[d.re2[t][0]] : 0.0;
-        for (int j = d.zz_ones0[t]; j < d.rt[t]; ++j)
-            zb += blk[L.b_ZZ[t] + (j - d.zz_ones0[t]) * kSvG + lane] * sb[d.re2[t][j]];
+        double xb = 0.0;
+        for (int f = 0; f < d.ft[t]; ++f) {
+            const int c = d.xx_col[t][f];
+            xb += (c < 0 ? 1.0 : blk[L.b_col + c * kSvG + lane]) * sp[L.ps_betas + bo + d.indf[t][f]];
+        }
+        double zb = 0.0;
+        for (int j = 0; j < d.rt[t]; ++j) {
+            const int c = d.zz_col[t][j];
+            zb += (c < 0 ? 1.0 : blk[L.b_col + c * kSvG + lane]) * sb[d.re2[t][j]];
+        }
         const double v = trans_fun(d.tf[t], xb + zb);
         for (int u = 0; u < d.ut[t]; ++u) {
             const double w = d.u_ones[t] ? v : blk[L.b_U[t] + u * kSvG + lane] * v;
@@ -293,24 +304,25 @@ __device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec,
     double s2 = 0.0;
     sfor<p>([&](auto j) { s2 += (W2C ? rec[oW2c + j] : blk[bW2 + j * kSvG + lane]) * sp[psG + j]; });
     double s3 = 0.0;
+    constexpr int bCol = Spec::L.b_col;
+    double colv[Spec::d.NC > 0 ? Spec::d.NC : 1];
+    sfor<Spec::d.NC>([&](auto c) { colv[c] = blk[bCol + c * kSvG + lane]; });
     sfor<T>([&](auto tc) {
         constexpr int t = tc;
-        constexpr int bo = Spec::d.boff[Spec::d.outc[t]], x0 = Spec::d.xx_ones0[t], z0 = Spec::d.zz_ones0[t];
+        constexpr int bo = Spec::d.boff[Spec::d.outc[t]], bU = Spec::L.b_U[t], tf = Spec::d.tf[t];
         double xb = 0.0;
-        constexpr int bXX = Spec::L.b_XX[t], bZZ = Spec::L.b_ZZ[t], bU = Spec::L.b_U[t], tf = Spec::d.tf[t];
-        constexpr int if0 = Spec::d.indf[t][0], r20 = Spec::d.re2[t][0];
-        if constexpr (x0 == 1) xb = sp[psB + bo + if0];
-        sfor<Spec::d.ft[t] - x0>([&](auto fc) {
-            constexpr int f = fc + x0;
-            constexpr int idx = Spec::d.indf[t][f];
-            xb += blk[bXX + (f - x0) * kSvG + lane] * sp[psB + bo + idx];
+        sfor<Spec::d.ft[t]>([&](auto fc) {
+            constexpr int f = fc;
+            constexpr int idx = Spec::d.indf[t][f], c = Spec::d.xx_col[t][f];
+            if constexpr (c < 0) xb += sp[psB + bo + idx];               // 1 * beta is exact
+            else xb += colv[c] * sp[psB + bo + idx];
         });
         double zb = 0.0;
-        if constexpr (z0 == 1) zb = b[r20];
-        sfor<Spec::d.rt[t] - z0>([&](auto jc) {
-            constexpr int j = jc + z0;
-            constexpr int idx = Spec::d.re2[t][j];
-            zb += blk[bZZ + (j - z0) * kSvG + lane] * b[idx];
+        sfor<Spec::d.rt[t]>([&](auto jc) {
+            constexpr int j = jc;
+            constexpr int idx = Spec::d.re2[t][j], c = Spec::d.zz_col[t][j];
+            if constexpr (c < 0) zb += b[idx];
+            else zb += colv[c] * b[idx];
         });
         double v = xb + zb;
         if constexpr (tf != JMB_TF_IDENTITY) v = trans_fun(tf, v);
@@ -419,49 +431,30 @@ __device__ inline void sv_eigen_sym(double* a, int n, double* val, double* vec) 
     }
 }
 
-// ---- the subject's control thread: consume `val`, run until the next request is posted -------------------------
-// vmmin (R src/appl/optim.c), fminfn / fmingr / optimhess (R src/library/stats/src/optim.c), cd (R/cd.R) and the
-// MH loop of R/survfitJM.mvJMbayes.R:338-398 as one resumable state machine.
-__device__ __noinline__ void sv_advance(const SvArgs& a, const int q, SvG& G, const double val) {
+// ---- mode search: the subject's control thread -----------------------------------------------------------------
+// vmmin (R src/appl/optim.c), fminfn / fmingr / optimhess (R src/library/stats/src/optim.c) as one resumable state
+// machine.  A request is IC_NEV evaluations of -log_post_RE_svft: 1 = the point btry, 2q = the central-difference
+// gradient cd(x, ff, eps) of R/cd.R at x (filled into grad[], already multiplied by parscale as fmingr does).
+__device__ __noinline__ void sv_advance_modes(const SvArgs& a, const int q, SvG& G, const double val) {
     const double ps = a.c.parscale, stepredn = 0.2, acctol = 0.0001, reltest = 10.0;
     const int n = q;
     int* ic = G.ic;
     double* sc = G.sc;
     int st = ic[IC_STATE];
-    auto post_full = [&](int state) { ic[IC_ACT] = ACT_EVAL; ic[IC_FULL] = 1; ic[IC_BLK] = 0; ic[IC_STATE] = state; };
-    // cd(): request f(x + ex e_i)
-    auto grad_plus = [&]() {
-        const int i = ic[IC_GI];
-        const double ex = a.c.cd_eps * (fabs(G.x[i]) + a.c.cd_eps);
-        for (int j = 0; j < n; ++j) G.btry[j] = G.x[j];
-        G.btry[i] = G.x[i] + ex;
-        sc[SC_X1] = G.btry[i];
-        post_full(ST_GRAD_P);
-    };
-    // fmingr at the optimiser point z: x = z * parscale, then cd()
-    auto start_grad = [&](const double* z, int ret) {
+    auto post_value = [&](int state) { ic[IC_NEV] = 1; ic[IC_STATE] = state; };
+    auto post_grad = [&](const double* z, int ret) {     // fmingr at the optimiser point z: x = z * parscale
         for (int j = 0; j < n; ++j) G.x[j] = z[j] * ps;
-        ic[IC_GI] = 0; ic[IC_RET] = ret;
-        grad_plus();
+        ic[IC_RET] = ret; ic[IC_NEV] = 2 * n; ic[IC_STATE] = ST_GRAD;
     };
     for (;;) {
         switch (st) {
         case ST_FETCH: {
             const int s = atomicAdd(a.work, 1);
-            if (s >= a.n) { ic[IC_SUBJ] = -1; ic[IC_ACT] = ACT_DONE; ic[IC_STATE] = ST_FETCH; return; }
-            ic[IC_SUBJ] = s;
-            ic[IC_NH] = reinterpret_cast<const int*>(a.rec + a.off[s])[ic[IC_O]];      // header: visit counts [O], then nh
-            ic[IC_CONV] = 0; ic[IC_NACC] = 0;
-            for (int j = 0; j < a.ps_len; ++j) G.par[j] = a.par_mean ? a.par_mean[j] : 0.0;
-            if (a.do_modes) {
-                for (int j = 0; j < n; ++j) { G.bz[j] = 0.0 / ps; G.btry[j] = G.bz[j] * ps; }   // start = rep(0, q)
-                post_full(ST_F0);
-                return;
-            }
-            for (int j = 0; j < n; ++j) G.mode[j] = a.modes[(long long)s * n + j];
-            for (int j = 0; j < n * n; ++j) G.hess[j] = a.hess[(long long)s * n * n + j];
-            st = PC_SAMPLE_INIT;
-            break;
+            if (s >= a.n) { ic[IC_SUBJ] = -1; ic[IC_NEV] = 0; ic[IC_STATE] = ST_FETCH; return; }
+            ic[IC_SUBJ] = s; ic[IC_CONV] = 0;
+            for (int j = 0; j < n; ++j) { G.bz[j] = 0.0 / ps; G.btry[j] = G.bz[j] * ps; }   // start = rep(0, q)
+            post_value(ST_F0);
+            return;
         }
         case ST_F0: {
             const double f = 0.0 - val;
@@ -475,28 +468,10 @@ __device__ __noinline__ void sv_advance(const SvArgs& a, const int q, SvG& G, co
             }
             sc[SC_FMIN] = f; sc[SC_F] = f;
             ic[IC_FUN] = 1; ic[IC_GRC] = 1; ic[IC_ITER] = 0; ic[IC_COUNT] = 0;
-            start_grad(G.bz, RET_INIT);
+            post_grad(G.bz, RET_INIT);
             return;
         }
-        case ST_GRAD_P: {
-            const int i = ic[IC_GI];
-            sc[SC_F1] = 0.0 - val;                   // ff(x1)
-            const double ex = a.c.cd_eps * (fabs(G.x[i]) + a.c.cd_eps);
-            G.btry[i] = G.x[i] - ex;
-            post_full(ST_GRAD_M);
-            return;
-        }
-        case ST_GRAD_M: {
-            const int i = ic[IC_GI];
-            const double diff_f = sc[SC_F1] - (0.0 - val);
-            const double diff_x = sc[SC_X1] - G.btry[i];
-            G.grad[i] = (diff_f / diff_x) * ps;      // fmingr: gr(x) * parscale
-            ic[IC_GI] = i + 1;
-            if (i + 1 < n) { grad_plus(); return; }
-            st = PC_GRAD_DONE;
-            break;
-        }
-        case PC_GRAD_DONE: {
+        case ST_GRAD: {
             const int ret = ic[IC_RET];
             if (ret == RET_INIT) {
                 for (int j = 0; j < n; ++j) G.g[j] = G.grad[j];
@@ -533,7 +508,7 @@ __device__ __noinline__ void sv_advance(const SvArgs& a, const int q, SvG& G, co
                 const int hi = ic[IC_HI];
                 for (int j = 0; j < n; ++j) G.df1[j] = G.grad[j];
                 G.dpar[hi] = G.dpar[hi] - 2 * sc[SC_EPS_H];
-                start_grad(G.dpar, RET_H2);
+                post_grad(G.dpar, RET_H2);
                 return;
             } else {                                 // RET_H2: df2 at dpar - eps e_i
                 const int hi = ic[IC_HI];
@@ -543,7 +518,7 @@ __device__ __noinline__ void sv_advance(const SvArgs& a, const int q, SvG& G, co
                 if (hi + 1 < n) {
                     ic[IC_HI] = hi + 1;
                     G.dpar[hi + 1] = G.dpar[hi + 1] + eps;
-                    start_grad(G.dpar, RET_H1);
+                    post_grad(G.dpar, RET_H1);
                     return;
                 }
                 for (int i = 0; i < n; ++i)
@@ -588,7 +563,7 @@ __device__ __noinline__ void sv_advance(const SvArgs& a, const int q, SvG& G, co
             ic[IC_COUNT] = count;
             if (count < n) {
                 for (int j = 0; j < n; ++j) G.btry[j] = G.bz[j] * ps;
-                post_full(ST_LS);
+                post_value(ST_LS);
                 return;
             }
             st = PC_LS_DONE;
@@ -609,7 +584,7 @@ __device__ __noinline__ void sv_advance(const SvArgs& a, const int q, SvG& G, co
             if (!enough) { ic[IC_COUNT] = n; sc[SC_FMIN] = f; }
             if (ic[IC_COUNT] < n) {                  // making progress
                 sc[SC_FMIN] = f;
-                start_grad(G.bz, RET_LS);
+                post_grad(G.bz, RET_LS);
                 return;
             }
             if (ic[IC_ILAST] < ic[IC_GRC]) { ic[IC_COUNT] = 0; ic[IC_ILAST] = ic[IC_GRC]; }   // no progress
@@ -630,7 +605,7 @@ __device__ __noinline__ void sv_advance(const SvArgs& a, const int q, SvG& G, co
             for (int j = 0; j < n; ++j) G.dpar[j] = G.mode[j] / ps;
             ic[IC_HI] = 0;
             G.dpar[0] = G.dpar[0] + eps;
-            start_grad(G.dpar, RET_H1);
+            post_grad(G.dpar, RET_H1);
             return;
         }
         case PC_MODE_DONE: {
@@ -639,123 +614,11 @@ __device__ __noinline__ void sv_advance(const SvArgs& a, const int q, SvG& G, co
             for (int j = 0; j < n * n; ++j) a.hess[s * n * n + j] = G.hess[j];
             a.conv[s] = ic[IC_CONV];
             a.counts[2 * s] = ic[IC_FUN]; a.counts[2 * s + 1] = ic[IC_GRC];
-            st = a.do_sample ? PC_SAMPLE_INIT : ST_FETCH;
-            break;
-        }
-        case PC_SAMPLE_INIT: {                       // invVars.b, Vars.b (:304-305), eigen for rmvt / dmvt
-            bool bad = false;
-            for (int j = 0; j < n; ++j) if (!isfinite(G.mode[j])) bad = true;
-            for (int j = 0; j < n * n; ++j) {
-                if (!isfinite(G.hess[j])) bad = true;
-                G.invV[j] = G.hess[j] / a.c.scale;
-                G.Wa[j] = G.hess[j];
-            }
-            if (!bad && sv_inverse(G.Wa, n, G.Wb)) bad = true;
-            if (!bad) {
-                for (int i = 0; i < n; ++i)
-                    for (int j = 0; j < n; ++j) G.Wa[i + j * n] = 0.5 * (G.Wb[i + j * n] * a.c.scale + G.Wb[j + i * n] * a.c.scale);
-                sv_eigen_sym(G.Wa, n, G.X, G.Wb);    // values -> X, vectors -> Wb
-                if (!(G.X[n - 1] >= -1e-06 * fabs(G.X[0]))) bad = true;
-                for (int j = 0; j < n; ++j) if (!(G.X[j] > 0.0)) bad = true;
-            }
-            if (bad) {
-                const long long s = ic[IC_SUBJ];
-                const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                for (long long k = 0; k < (long long)a.M * a.L; ++k) a.S[s * a.M * a.L + k] = nan;
-                a.acc_rate[s] = nan;
-                for (int j = 0; j < n; ++j) a.b_last[s * n + j] = nan;
-                a.conv[s] = 20;
-                st = ST_FETCH;
-                break;
-            }
-            for (int r = 0; r < n; ++r)
-                for (int c = 0; c < n; ++c) {
-                    G.Af[r + c * n] = G.Wb[r + c * n] * sqrt(G.X[c] > 0.0 ? G.X[c] : 0.0);
-                    double s = 0.0;
-                    for (int k = 0; k < n; ++k) s += G.Wb[r + k * n] * (G.Wb[c + k * n] / G.X[k]);
-                    G.invS[r + c * n] = s;
-                }
-            for (int j = 0; j < n; ++j) { G.b_old[j] = G.mode[j]; G.b_new[j] = G.mode[j]; }
-            ic[IC_M] = 0; ic[IC_NACC] = 0;
-            st = PC_MH_NEXT;
-            break;
-        }
-        case PC_MH_NEXT: {
-            if (ic[IC_M] >= a.M) { st = PC_SUBJ_DONE; break; }
-            ic[IC_ACT] = ACT_RNG; ic[IC_STATE] = ST_MH_RNG;      // all lanes: draws of step m + parameter set m
-            return;
-        }
-        case ST_MH_RNG: {                            // proposal m of rmvt() and its dmvt (:330-337,354-355)
-            const double den = sqrt(sc[SC_W] / a.c.df);
-            for (int r = 0; r < n; ++r) {
-                double s = 0.0;
-                for (int c = 0; c < n; ++c) s += G.Af[r + c * n] * G.z[c];
-                G.pb[r] = G.mode[r] + s / den;
-            }
-            double quad_p = 0.0, quad_o = 0.0;
-            for (int c = 0; c < n; ++c) {
-                double tp = 0.0, to = 0.0;
-                for (int r = 0; r < n; ++r) {
-                    tp += (G.pb[r] - G.mode[r]) * G.invS[r + c * n];
-                    to += (G.b_old[r] - G.mode[r]) * G.invV[r + c * n];
-                }
-                quad_p += tp * (G.pb[c] - G.mode[c]); quad_o += to * (G.b_old[c] - G.mode[c]);
-            }
-            sc[SC_DMVT_P] = -0.5 * (a.c.df + n) * log(1.0 + quad_p / a.c.df);
-            sc[SC_DMVT_O] = -0.5 * (a.c.df + n) * log(1.0 + quad_o / a.c.df);
-            for (int j = 0; j < n; ++j) G.btry[j] = G.pb[j];
-            post_full(ST_MH_P);
-            return;
-        }
-        case ST_MH_P: {
-            sc[SC_LP_P] = val;
-            for (int j = 0; j < n; ++j) G.btry[j] = G.b_old[j];
-            post_full(ST_MH_O);
-            return;
-        }
-        case ST_MH_O: {                              // :372-377
-            const double ea = exp(sc[SC_LP_P] + sc[SC_DMVT_O] - val - sc[SC_DMVT_P]);
-            if (!isnan(ea)) {
-                const double acc = ea < 1.0 ? ea : 1.0;
-                if (sc[SC_U] <= acc) { for (int j = 0; j < n; ++j) G.b_new[j] = G.pb[j]; ic[IC_NACC] += 1; }
-            }
-            sc[SC_CUM] = 0.0; ic[IC_L] = 0;
-            if (ic[IC_NH] > 0) {
-                for (int j = 0; j < n; ++j) G.btry[j] = G.b_new[j];
-                ic[IC_ACT] = ACT_EVAL; ic[IC_FULL] = 0; ic[IC_BLK] = 1; ic[IC_STATE] = ST_HZ;
-                return;
-            }
-            for (int l = 0; l < a.L; ++l) a.S[((long long)ic[IC_SUBJ] * a.M + ic[IC_M]) * a.L + l] = __longlong_as_double(0x7ff8000000000000LL);
-            for (int j = 0; j < n; ++j) G.b_old[j] = G.b_new[j];
-            ic[IC_M] += 1;
-            st = PC_MH_NEXT;
-            break;
-        }
-        case ST_HZ: {                                // :378-395
-            const int l = ic[IC_L];
-            sc[SC_CUM] += val;
-            a.S[((long long)ic[IC_SUBJ] * a.M + ic[IC_M]) * a.L + l] = a.c.log ? val : exp(sc[SC_CUM]);
-            if (l + 1 < ic[IC_NH]) {
-                ic[IC_L] = l + 1; ic[IC_BLK] = l + 2;
-                ic[IC_ACT] = ACT_EVAL; ic[IC_STATE] = ST_HZ;
-                return;
-            }
-            for (int l2 = l + 1; l2 < a.L; ++l2)        // intervals this subject does not have
-                a.S[((long long)ic[IC_SUBJ] * a.M + ic[IC_M]) * a.L + l2] = __longlong_as_double(0x7ff8000000000000LL);
-            for (int j = 0; j < n; ++j) G.b_old[j] = G.b_new[j];
-            ic[IC_M] += 1;
-            st = PC_MH_NEXT;
-            break;
-        }
-        case PC_SUBJ_DONE: {
-            const long long s = ic[IC_SUBJ];
-            a.acc_rate[s] = (double)ic[IC_NACC] / (a.M > 0 ? a.M : 1);
-            for (int j = 0; j < n; ++j) a.b_last[s * n + j] = G.b_new[j];
             st = ST_FETCH;
             break;
         }
         default:
-            ic[IC_ACT] = ACT_DONE; ic[IC_SUBJ] = -1;
+            ic[IC_NEV] = 0; ic[IC_SUBJ] = -1;
             return;
         }
     }
@@ -783,65 +646,218 @@ struct SvEvalStatic {
     }
 };
 
+// mode search of all subjects (R/survfitJM.mvJMbayes.R:277-305)
 template <class Eval>
-__device__ __forceinline__ void sv_run(const int q, const int O, const SvArgs& a, const Eval& eval) {
+__device__ __forceinline__ void sv_modes_run(const int q, const SvArgs& a, const Eval& eval) {
     extern __shared__ double sv_smem[];
     const int tid = threadIdx.x, lane = tid & (kSvG - 1), grp = tid / kSvG;
     const unsigned gmask = 0xFFFFu << (16 * ((tid & 31) >> 4));
-    const int gd = (sv_group_doubles(q, a.ps_len) + 1) / 2 * 2;
+    const int gdn = sv_group_doubles(q, a.ps_len), gd = (gdn + 1) / 2 * 2;
     // views derived from the shared-memory window itself, so that the hot loads compile to LDS
     double* gbase = sv_smem + (size_t)grp * gd;
-    const double* sp = gbase;                        // parameter set in use
-    const double* sb = gbase + a.ps_len;             // point of the posted request
+    const double* sp = gbase;                        // parameter set (posterior means)
+    double* sbtry = gbase + a.ps_len;                // point of the evaluation
+    const double* sx = sbtry + q;                    // point of the posted gradient
+    double* sgrad = sbtry + 2 * q;
+    double* ssc = gbase + (gdn - (IC_N + 1) / 2 - SC_N);
+    volatile int* ic = reinterpret_cast<int*>(gbase + (gdn - (IC_N + 1) / 2));
     SvG G;
     sv_bind(G, gbase, q, a.ps_len);
-    volatile int* ic = reinterpret_cast<int*>(gbase + (sv_group_doubles(q, a.ps_len) - (IC_N + 1) / 2));
+    for (int j = lane; j < a.ps_len; j += kSvG) gbase[j] = a.par_mean[j];
     if (lane == 0) {
         for (int j = 0; j < IC_N; ++j) G.ic[j] = 0;
-        G.ic[IC_O] = O;
         G.ic[IC_STATE] = ST_FETCH; G.ic[IC_SUBJ] = -1;
-        sv_advance(a, q, G, 0.0);
+        sv_advance_modes(a, q, G, 0.0);
     }
     __syncwarp();
+    const double ps = a.c.parscale, eps = a.c.cd_eps;
     for (;;) {
-        const int act = ic[IC_ACT];
-        const bool done = (act == ACT_DONE);
-        if (__all_sync(0xFFFFFFFFu, done)) break;
+        const int nev = ic[IC_NEV];
+        const int nmax = max(nev, __shfl_xor_sync(0xFFFFFFFFu, nev, 16));
+        if (nmax == 0) break;
+        const double* rec = a.rec + a.off[max(ic[IC_SUBJ], 0)];
         double val = 0.0;
-        if (act == ACT_EVAL) {
-            const int s = ic[IC_SUBJ];
-            val = eval(a.rec + a.off[s], ic[IC_BLK], ic[IC_FULL] != 0, sb, sp, lane, gmask);
-        } else if (act == ACT_RNG) {
-            // draws of MH step m (streams of DESIGN.md section 4, key (seed, 'SVFT')) and parameter set m
-            const uint32_t gid = (uint32_t)(a.subject_offset + ic[IC_SUBJ]), m = (uint32_t)ic[IC_M];
-            if (lane < (q + 1) / 2) {
-                double z0, z1;
-                rnorm_pair(a.c.seed, kSvKey, gid, m, (uint32_t)lane, 0u, z0, z1);
-                G.z[2 * lane] = z0; G.z[2 * lane + 1] = z1;
-            } else if (lane == 8) {
-                G.sc[SC_W] = rgamma_dev(a.c.seed, kSvKey, gid, m, 0.5 * a.c.df, 2.0);    // rchisq(df)
-            } else if (lane == 9) {
-                uint32_t r[4];
-                philox4x32(a.c.seed, kSvKey, gid, m, 0u, 1u, r);
-                G.sc[SC_U] = u01(r[0], r[1]);
+        for (int e = 0; e < nmax; ++e) {
+            const bool act = e < nev;
+            const int i = e >> 1;
+            if (act && nev > 1 && lane < q) {         // cd(): x1 = x + ex e_i, then x2 = x - ex e_i (R/cd.R:5-10)
+                double xv = sx[lane];
+                if (lane == i) { const double ex = eps * (fabs(xv) + eps); xv = (e & 1) ? xv - ex : xv + ex; }
+                sbtry[lane] = xv;
             }
-            const double* src = a.par_draws + (size_t)m * a.ps_len;
-            for (int j = lane; j < a.ps_len; j += kSvG) gbase[j] = src[j];
+            __syncwarp();
+            if (act) val = eval(rec, 0, true, sbtry, sp, lane, gmask);
+            if (act && nev > 1 && lane == 0) {
+                if (!(e & 1)) { ssc[SC_F1] = 0.0 - val; ssc[SC_X1] = sbtry[i]; }
+                else sgrad[i] = ((ssc[SC_F1] - (0.0 - val)) / (ssc[SC_X1] - sbtry[i])) * ps;   // diff.f / diff.x, fmingr scaling
+            }
+            __syncwarp();
         }
+        if (lane == 0 && nev > 0) sv_advance_modes(a, q, G, val);
         __syncwarp();
-        if (lane == 0 && !done) sv_advance(a, q, G, val);
+    }
+}
+
+// per-subject set-up of the sampler by the control lane: invVars.b = hessian / scale, Vars.b = scale * solve(hessian)
+// (:304-305), eigen(Vars.b) for rmvt (R/rmvt.R) and dmvt (R/dmvt.R).  Returns 1 when the Hessian is unusable.
+__device__ __noinline__ int sv_sample_setup(const SvArgs& a, const int n, SvG& G, const long long s) {
+    for (int j = 0; j < n; ++j) G.mode[j] = a.modes[s * n + j];
+    for (int j = 0; j < n * n; ++j) G.hess[j] = a.hess[s * n * n + j];
+    bool bad = false;
+    for (int j = 0; j < n; ++j) if (!isfinite(G.mode[j])) bad = true;
+    for (int j = 0; j < n * n; ++j) {
+        if (!isfinite(G.hess[j])) bad = true;
+        G.invV[j] = G.hess[j] / a.c.scale;
+        G.Wa[j] = G.hess[j];
+    }
+    if (!bad && sv_inverse(G.Wa, n, G.Wb)) bad = true;
+    if (!bad) {
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) G.Wa[i + j * n] = 0.5 * (G.Wb[i + j * n] * a.c.scale + G.Wb[j + i * n] * a.c.scale);
+        sv_eigen_sym(G.Wa, n, G.X, G.Wb);            // values -> X, vectors -> Wb
+        if (!(G.X[n - 1] >= -1e-06 * fabs(G.X[0]))) bad = true;     // dmvt: "'Sigma' is not positive definite"
+        for (int j = 0; j < n; ++j) if (!(G.X[j] > 0.0)) bad = true;
+    }
+    if (bad) return 1;
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) {
+            G.Af[r + c * n] = G.Wb[r + c * n] * sqrt(G.X[c] > 0.0 ? G.X[c] : 0.0);   // evec * rep(sqrt(pmax(ev, 0)), each = p)
+            double t = 0.0;
+            for (int k = 0; k < n; ++k) t += G.Wb[r + k * n] * (G.Wb[c + k * n] / G.X[k]);   // evec %*% (t(evec) / ev)
+            G.invS[r + c * n] = t;
+        }
+    for (int j = 0; j < n; ++j) { G.b_old[j] = G.mode[j]; G.b_new[j] = G.mode[j]; }
+    return 0;
+}
+
+// the M Metropolis-Hastings steps and the horizon integrals of all subjects (R/survfitJM.mvJMbayes.R:330-398)
+template <class Eval>
+__device__ __forceinline__ void sv_sample_run(const int q, const int O, const SvArgs& a, const Eval& eval) {
+    extern __shared__ double sv_smem[];
+    const int tid = threadIdx.x, lane = tid & (kSvG - 1), grp = tid / kSvG;
+    const unsigned gmask = 0xFFFFu << (16 * ((tid & 31) >> 4));
+    const int gdn = sv_group_doubles(q, a.ps_len), gd = (gdn + 1) / 2 * 2;
+    double* gbase = sv_smem + (size_t)grp * gd;
+    const int zq = (q + 2) / 2 * 2, qq = q * q;
+    // the same carving as sv_bind, from the shared-memory window (LDS / STS)
+    const double* sp = gbase;
+    double* v0 = gbase + a.ps_len;
+    const double* smode = v0 + 10 * q;
+    double* sb_old = v0 + 11 * q;
+    double* sb_new = v0 + 12 * q;
+    double* spb = v0 + 13 * q;
+    double* sz = v0 + 14 * q;
+    const double* sAf = sz + zq + 2 * qq;
+    const double* sinvS = sAf + qq;
+    const double* sinvV = sinvS + qq;
+    double* ssc = gbase + (gdn - (IC_N + 1) / 2 - SC_N);
+    volatile int* ic = reinterpret_cast<int*>(gbase + (gdn - (IC_N + 1) / 2));
+    SvG G;
+    sv_bind(G, gbase, q, a.ps_len);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const int groups = blockDim.x / kSvG;
+    const long long stride = (long long)gridDim.x * groups;
+    for (long long s = (long long)blockIdx.x * groups + grp;; s += stride) {
+        const bool have = s < a.n;
+        if (!__any_sync(0xFFFFFFFFu, have)) break;
+        const double* rec = a.rec + a.off[have ? s : 0];
+        const int nh = have ? reinterpret_cast<const int*>(rec)[O] : 0;
+        if (have && lane == 0) G.ic[IC_BAD] = sv_sample_setup(a, q, G, s);
+        __syncwarp();
+        const bool live = have && ic[IC_BAD] == 0;
+        if (have && !live) {                         // unusable Hessian: reported, not propagated
+            for (long long k = lane; k < (long long)a.M * a.L; k += kSvG) a.S[s * a.M * a.L + k] = nan;
+            if (lane < q) a.b_last[s * q + lane] = nan;
+            if (lane == 0) { a.acc_rate[s] = nan; a.conv[s] = 20; }
+        }
+        const int nhl = live ? nh : 0;
+        const int nh_max = max(nhl, __shfl_xor_sync(0xFFFFFFFFu, nhl, 16));
+        const uint32_t gid = (uint32_t)(a.subject_offset + s);
+        int n_acc = 0;
+        for (int m = 0; m < a.M; ++m) {
+            if (live) {
+                // draws of step m (streams of DESIGN.md section 4, key (seed, 'SVFT')) and parameter set m
+                if (lane < (q + 1) / 2) {
+                    double z0, z1;
+                    rnorm_pair(a.c.seed, kSvKey, gid, (uint32_t)m, (uint32_t)lane, 0u, z0, z1);
+                    sz[2 * lane] = z0; sz[2 * lane + 1] = z1;
+                } else if (lane == 8) {
+                    ssc[SC_W] = rgamma_dev(a.c.seed, kSvKey, gid, (uint32_t)m, 0.5 * a.c.df, 2.0);    // rchisq(df)
+                } else if (lane == 9) {
+                    uint32_t r[4];
+                    philox4x32(a.c.seed, kSvKey, gid, (uint32_t)m, 0u, 1u, r);
+                    ssc[SC_U] = u01(r[0], r[1]);
+                }
+                const double* src = a.par_draws + (size_t)m * a.ps_len;
+                for (int j = lane; j < a.ps_len; j += kSvG) gbase[j] = src[j];
+            }
+            __syncwarp();
+            if (live && lane < q) {                  // proposal m of rmvt(M, mode, Vars.b, df) (:330-331)
+                const double den = sqrt(ssc[SC_W] / a.c.df);
+                double t = 0.0;
+                for (int c = 0; c < q; ++c) t += sAf[lane + c * q] * sz[c];
+                spb[lane] = smode[lane] + t / den;
+            }
+            __syncwarp();
+            bool accept = false;
+            if (live) {
+                double tp = 0.0, to = 0.0;           // dmvt(prop = TRUE) of the proposal and of b.old (:334-337,354)
+                if (lane < q) {
+                    for (int r = 0; r < q; ++r) {
+                        tp += (spb[r] - smode[r]) * sinvS[r + lane * q];
+                        to += (sb_old[r] - smode[r]) * sinvV[r + lane * q];
+                    }
+                    tp *= (spb[lane] - smode[lane]); to *= (sb_old[lane] - smode[lane]);
+                }
+                const double quad_p = group_sum<kSvG>(tp, gmask), quad_o = group_sum<kSvG>(to, gmask);
+                const double dmvt_p = -0.5 * (a.c.df + q) * log(1.0 + quad_p / a.c.df);
+                const double dmvt_o = -0.5 * (a.c.df + q) * log(1.0 + quad_o / a.c.df);
+                const double lp_p = eval(rec, 0, true, spb, sp, lane, gmask);
+                const double lp_o = eval(rec, 0, true, sb_old, sp, lane, gmask);
+                const double ea = exp(lp_p + dmvt_o - lp_o - dmvt_p);               // :372-377
+                accept = !isnan(ea) && ssc[SC_U] <= (ea < 1.0 ? ea : 1.0);
+                if (accept && lane < q) sb_new[lane] = spb[lane];
+                n_acc += accept ? 1 : 0;
+            }
+            __syncwarp();
+            double cum = 0.0;                        // survival on each prediction interval (:378-395)
+            double* Srow = a.S + ((size_t)(have ? s : 0) * a.M + m) * a.L;
+            for (int l = 0; l < nh_max; ++l) {
+                if (live && l < nh) {
+                    const double v = eval(rec, l + 1, false, sb_new, sp, lane, gmask);
+                    cum += v;
+                    if (lane == 0) Srow[l] = a.c.log ? v : exp(cum);
+                }
+            }
+            if (live) {
+                for (int l = nh + lane; l < a.L; l += kSvG) Srow[l] = nan;        // intervals this subject does not have
+                if (lane < q) sb_old[lane] = sb_new[lane];
+            }
+            __syncwarp();
+        }
+        if (live) {
+            if (lane == 0) a.acc_rate[s] = (double)n_acc / (a.M > 0 ? a.M : 1);
+            if (lane < q) a.b_last[s * q + lane] = sb_new[lane];
+        }
         __syncwarp();
     }
 }
 
 template <class Spec>
-__global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS) jmb_svft_static(const __grid_constant__ SvArgs a) {
-    sv_run(Spec::d.q, Spec::d.O, a, SvEvalStatic<Spec>{});
+__global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS) jmb_svft_modes_static(const __grid_constant__ SvArgs a) {
+    sv_modes_run(Spec::d.q, a, SvEvalStatic<Spec>{});
 }
-
 __global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS)
-jmb_svft_generic(const __grid_constant__ SvMeta mm, const __grid_constant__ SvArgs a) {
-    sv_run(mm.d.q, mm.d.O, a, SvEvalGeneric{mm.d, mm.L});
+jmb_svft_modes_generic(const __grid_constant__ SvMeta mm, const __grid_constant__ SvArgs a) {
+    sv_modes_run(mm.d.q, a, SvEvalGeneric{mm.d, mm.L});
+}
+template <class Spec>
+__global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS) jmb_svft_sample_static(const __grid_constant__ SvArgs a) {
+    sv_sample_run(Spec::d.q, Spec::d.O, a, SvEvalStatic<Spec>{});
+}
+__global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS)
+jmb_svft_sample_generic(const __grid_constant__ SvMeta mm, const __grid_constant__ SvArgs a) {
+    sv_sample_run(mm.d.q, mm.d.O, a, SvEvalGeneric{mm.d, mm.L});
 }
 
 // ---- Mean / Median / Lower / Upper over the M draws (R/survfitJM.mvJMbayes.R:400-414) ----------------------------
