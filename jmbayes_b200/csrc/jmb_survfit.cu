@@ -450,8 +450,16 @@ static int run(jmb_svft_handle h, const jmb_svft_params* pm, const jmb_svft_para
         int Mp = 1;
         while (Mp < M) Mp <<= 1;
         if (Mp > 4096) return fail("jmb_svft: M too large for the summary kernel (max 4096)");
-        jmb_svft_summary<<<n, 128, sizeof(double) * Mp, h->stream>>>(h->d_S, h->d_off, h->d_rec, md.O, n, M, L, Mp,
-                                                                     ct->CI_levels[0], ct->CI_levels[1], h->d_sum);
+        const long long warps = (long long)n * L;
+        const unsigned wg = (unsigned)((warps * 32 + 127) / 128);
+#define SUMMARY_WARP(E) jmb_svft_summary_warp<E><<<wg, 128, 0, h->stream>>>(h->d_S, h->d_off, h->d_rec, md.O, n, M, L, ct->CI_levels[0], ct->CI_levels[1], h->d_sum)
+        if (Mp <= 32) SUMMARY_WARP(1);
+        else if (Mp <= 64) SUMMARY_WARP(2);
+        else if (Mp <= 128) SUMMARY_WARP(4);
+        else if (Mp <= 256) SUMMARY_WARP(8);
+        else jmb_svft_summary<<<n, 128, sizeof(double) * Mp, h->stream>>>(h->d_S, h->d_off, h->d_rec, md.O, n, M, L, Mp,
+                                                                          ct->CI_levels[0], ct->CI_levels[1], h->d_sum);
+#undef SUMMARY_WARP
         h->launches += 1;
         CU(cudaGetLastError());
     }

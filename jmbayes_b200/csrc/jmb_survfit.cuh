@@ -220,6 +220,33 @@ __device__ __forceinline__ double sv_logdens(int fam, int link, double y, double
     }
 }
 
+// sv_logdens with E = exp(eta) supplied by the caller (the same call, hoisted out of the family branches)
+__device__ __forceinline__ double sv_logdens_e(int fam, int link, double y, double eta, double E, double inv_sigma) {
+    if (fam == JMB_FAM_GAUSSIAN) {
+        const double t = (y - eta) * inv_sigma;
+        return -0.5 * (t * t);
+    } else if (fam == JMB_FAM_BINOMIAL) {
+        double pr;
+        if (link == JMB_LINK_LOGIT) pr = E / (1.0 + E);
+        else if (link == JMB_LINK_PROBIT) pr = 0.5 * erfc(-eta * 0.70710678118654752440);
+        else pr = -exp(-E) + 1.0;
+        const bool one = (y == 1.0), zero = (y == 0.0);
+        if (one || zero) {
+            const double ld = log(one ? pr : 1.0 - pr);
+            const bool dead_inf = one ? (pr == 1.0) : (pr == 0.0);
+            return dead_inf ? __longlong_as_double(0x7ff8000000000000LL) : ld;
+        }
+        return y * log(pr) + (1.0 - y) * log(1.0 - pr);
+    } else {
+        if (link == JMB_LINK_LOG) {
+            double ld = y * eta - E;
+            if (E == 0.0) ld = (y == 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : (y > 0.0 ? -INFINITY : INFINITY);
+            return ld;
+        }
+        return row_logdens(fam, link, y, eta, inv_sigma);
+    }
+}
+
 // value of the posted request: full -> log_post_RE_svft(btry) on block 0 (src/survfitJM_mvJMbayes.cpp:140-166),
 // else survPred_svft_2(btry) = -H on block `blk_index` (:168-187).  Generic flavour: runtime descriptor.
 __device__ __forceinline__ double sv_eval_generic(const SvDesc& d, const SvLayout& L, const double* __restrict__ rec,
@@ -338,26 +365,42 @@ __device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec,
     const double H = group_sum<kSvG>(e, gmask);
     if (!full) return 0.0 - H;
 
+    // visit rows of all outcomes as one lane-strided list (a subject has ~n_i rows per outcome, far fewer than 16):
+    // each lane finds the outcome of its row, the exponential is shared by the logit / cloglog / log tails
     const int* hdr = reinterpret_cast<const int*>(rec + oV);
     const int nh = hdr[O];
     const double* __restrict__ lrec = rec + oBlk0 + (long long)(nh + 1) * BLK;
+    int vk[O], total = 0;
+    sfor<O>([&](auto k) { vk[k] = hdr[k]; total += vk[k]; });
     double acc = 0.0;
-    sfor<O>([&](auto kc) {
-        constexpr int k = kc;
-        constexpr int x0 = Spec::d.x_ones0[k], z0 = Spec::d.z_ones0[k], pk = Spec::d.pk[k], qk = Spec::d.qk[k], xc = pk - x0;
-        constexpr int bo = Spec::d.boff[k], ri0 = Spec::d.re_inds[k][0], fam = Spec::d.fam[k], link = Spec::d.link[k], lcols = Spec::L.long_cols[k];
-        const int v = hdr[k];
-        for (int r = lane; r < v; r += kSvG) {
-            double xb = 0.0;
-            if constexpr (x0 == 1) xb = sp[psB + bo];
-            sfor<pk - x0>([&](auto cc) { constexpr int c = cc + x0; xb += lrec[(1 + c - x0) * v + r] * sp[psB + bo + c]; });
-            double zb = 0.0;
-            if constexpr (z0 == 1) zb = b[ri0];
-            sfor<qk - z0>([&](auto jc) { constexpr int j = jc + z0; constexpr int idx = Spec::d.re_inds[k][j]; zb += lrec[(1 + xc + j - z0) * v + r] * b[idx]; });
-            acc += sv_logdens(fam, link, lrec[r], xb + zb, sp[psS + k]);
-        }
-        lrec += lcols * v;
-    });
+    for (int r = lane; r < total; r += kSvG) {
+        double eta = 0.0, y = 0.0, isg = 1.0;
+        int mine = -1, c0 = 0, o0 = 0;
+        sfor<O>([&](auto kc) {
+            constexpr int k = kc;
+            constexpr int x0 = Spec::d.x_ones0[k], z0 = Spec::d.z_ones0[k], pk = Spec::d.pk[k], qk = Spec::d.qk[k], xc = pk - x0;
+            constexpr int bo = Spec::d.boff[k], ri0 = Spec::d.re_inds[k][0], lcols = Spec::L.long_cols[k];
+            const int v = vk[k];
+            if (r >= c0 && r < c0 + v) {
+                const double* __restrict__ lr = lrec + o0;
+                const int rr = r - c0;
+                double xb = 0.0;
+                if constexpr (x0 == 1) xb = sp[psB + bo];
+                sfor<pk - x0>([&](auto cc) { constexpr int c = cc + x0; xb += lr[(1 + c - x0) * v + rr] * sp[psB + bo + c]; });
+                double zb = 0.0;
+                if constexpr (z0 == 1) zb = b[ri0];
+                sfor<qk - z0>([&](auto jc) { constexpr int j = jc + z0; constexpr int idx = Spec::d.re_inds[k][j]; zb += lr[(1 + xc + j - z0) * v + rr] * b[idx]; });
+                eta = xb + zb; y = lr[rr]; isg = sp[psS + k]; mine = k;
+            }
+            c0 += v; o0 += lcols * v;
+        });
+        const double E = exp(eta);
+        sfor<O>([&](auto kc) {
+            constexpr int k = kc;
+            constexpr int fam = Spec::d.fam[k], link = Spec::d.link[k];
+            if (mine == k) acc += sv_logdens_e(fam, link, y, eta, E, isg);
+        });
+    }
     double qf = 0.0;
     if (lane < q) {
         double t = 0.0;
@@ -628,7 +671,7 @@ __device__ __noinline__ void sv_advance_modes(const SvArgs& a, const int q, SvG&
 #define JMB_SVFT_THREADS 256
 #endif
 #ifndef JMB_SVFT_MIN_CTAS
-#define JMB_SVFT_MIN_CTAS 2
+#define JMB_SVFT_MIN_CTAS 3     // 80 registers, no spills; A/B on B200: 2 -> 40.8 ms, 3 -> 36.1 ms, 4 -> 37.4 ms per 25k subjects
 #endif
 
 struct SvEvalGeneric {
@@ -776,17 +819,43 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
         int n_acc = 0;
         for (int m = 0; m < a.M; ++m) {
             if (live) {
-                // draws of step m (streams of DESIGN.md section 4, key (seed, 'SVFT')) and parameter set m
-                if (lane < (q + 1) / 2) {
-                    double z0, z1;
-                    rnorm_pair(a.c.seed, kSvKey, gid, (uint32_t)m, (uint32_t)lane, 0u, z0, z1);
-                    sz[2 * lane] = z0; sz[2 * lane + 1] = z1;
-                } else if (lane == 8) {
-                    ssc[SC_W] = rgamma_dev(a.c.seed, kSvKey, gid, (uint32_t)m, 0.5 * a.c.df, 2.0);    // rchisq(df)
-                } else if (lane == 9) {
+                // draws of step m (streams of DESIGN.md section 4, key (seed, 'SVFT')) and parameter set m.  Every lane
+                // runs the same Philox block + Box-Muller on its own counter: lanes 0-3 the proposal normals (slot =
+                // lane), lanes 4-7 / 8-11 the normal / log-uniform of attempts 0-3 of the Marsaglia-Tsang gamma
+                // (rchisq(df) = rgamma(df / 2, scale 2); same streams and attempt order as rgamma_dev), lane 12 the
+                // acceptance uniform.
+                {
+                    const uint32_t c2 = (lane < 4) ? (uint32_t)lane : ((lane < 12) ? (uint32_t)(lane & 3) : 0u);
+                    const uint32_t c3 = (lane < 4) ? 0u : ((lane < 8) ? (uint32_t)ST_GIBBS_N : ((lane < 12) ? (uint32_t)ST_GIBBS_U : 1u));
                     uint32_t r[4];
-                    philox4x32(a.c.seed, kSvKey, gid, (uint32_t)m, 0u, 1u, r);
-                    ssc[SC_U] = u01(r[0], r[1]);
+                    philox4x32(a.c.seed, kSvKey, gid, (uint32_t)m, c2, c3, r);
+                    const double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+                    const double lg = log(u1);
+                    const double rad = sqrt(-2.0 * lg);
+                    double sn, cs;
+                    sincospi(2.0 * u2, &sn, &cs);
+                    const double z0 = rad * cs, z1 = rad * sn;
+                    if (lane < (q + 1) / 2) { sz[2 * lane] = z0; sz[2 * lane + 1] = z1; }
+                    if (lane == 12) ssc[SC_U] = u1;
+                    const double shape = 0.5 * a.c.df;
+                    const double lu = __shfl_sync(gmask, lg, (lane & 3) + 8, kSvG);     // attempt's log-uniform
+                    bool ok = false;
+                    double xg = 0.0;
+                    if (shape >= 1.0 && lane >= 4 && lane < 8) {
+                        const double dd = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+                        const double t = 1.0 + cc * z0;
+                        if (t > 0.0) {
+                            const double v = t * t * t;
+                            if (lu < 0.5 * z0 * z0 + dd - dd * v + dd * log(v)) { ok = true; xg = dd * v; }
+                        }
+                    }
+                    const unsigned hit = (__ballot_sync(gmask, ok) >> (16 * ((tid & 31) >> 4))) & 0xF0u;
+                    if (hit) {
+                        const int first = __ffs(hit) - 1;
+                        if (lane == first) ssc[SC_W] = xg * 2.0;
+                    } else if (lane == 4) {
+                        ssc[SC_W] = rgamma_dev(a.c.seed, kSvKey, gid, (uint32_t)m, shape, 2.0);   // shape < 1 or four rejections
+                    }
                 }
                 const double* src = a.par_draws + (size_t)m * a.ps_len;
                 for (int j = lane; j < a.ps_len; j += kSvG) gbase[j] = src[j];
@@ -820,13 +889,17 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
                 n_acc += accept ? 1 : 0;
             }
             __syncwarp();
-            double cum = 0.0;                        // survival on each prediction interval (:378-395)
+            double cum = 0.0, mine = 0.0;            // survival on each prediction interval (:378-395)
             double* Srow = a.S + ((size_t)(have ? s : 0) * a.M + m) * a.L;
             for (int l = 0; l < nh_max; ++l) {
                 if (live && l < nh) {
                     const double v = eval(rec, l + 1, false, sb_new, sp, lane, gmask);
                     cum += v;
-                    if (lane == 0) Srow[l] = a.c.log ? v : exp(cum);
+                    if (lane == (l & (kSvG - 1))) mine = a.c.log ? v : cum;
+                }
+                if ((l & (kSvG - 1)) == kSvG - 1 || l == nh_max - 1) {       // 16 intervals: exp(cumsum(logS)) by lane
+                    const int ll = (l & ~(kSvG - 1)) + lane;
+                    if (live && ll < nh) Srow[ll] = a.c.log ? mine : exp(mine);
                 }
             }
             if (live) {
@@ -858,6 +931,102 @@ __global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS) jmb_svft_
 __global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS)
 jmb_svft_sample_generic(const __grid_constant__ SvMeta mm, const __grid_constant__ SvArgs a) {
     sv_sample_run(mm.d.q, mm.d.O, a, SvEvalGeneric{mm.d, mm.L});
+}
+
+// ---- Mean / Median / Lower / Upper, M <= 32 * EPL: one warp per (subject, interval) -------------------------------------
+// The M values live in registers (element e = lane * EPL + i), sorted by a bitonic network whose partner distances below
+// EPL are register swaps and the others lane shuffles; NaN is removed (na.rm = TRUE) by sorting it last as +inf.
+template <int EPL>
+__global__ void __launch_bounds__(128) jmb_svft_summary_warp(const double* __restrict__ S, const long long* __restrict__ off,
+                                                             const double* __restrict__ rec, const int O, const int n,
+                                                             const int M, const int L, const double p_lo, const double p_hi,
+                                                             double* __restrict__ out) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (long long)n * L) return;
+    const long long i = w / L;
+    const int l = (int)(w % L);
+    const int nh = reinterpret_cast<const int*>(rec + off[i])[O];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double* o4 = out + (size_t)i * 4 * L + l;
+    if (l >= nh) {
+        if (lane < 4) o4[(size_t)lane * L] = nan;
+        return;
+    }
+    double x[EPL];
+    int cnt = 0;
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const int m = lane * EPL + k;
+        double v = (m < M) ? S[((size_t)i * M + m) * L + l] : INFINITY;
+        if (m < M && !isnan(v)) { cnt++; sum += v; } else v = INFINITY;
+        x[k] = v;
+    }
+    // rowMeans(na.rm = TRUE): per-lane partial sums in draw order, then lanes in order (fixed, data-independent order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o); }
+    double tot = 0.0;
+    for (int src = 0; src < 32; ++src) tot += __shfl_sync(0xFFFFFFFFu, sum, src);
+#pragma unroll
+    for (int k = 2; k <= 32 * EPL; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= EPL) {                          // partner in another lane
+                const int lj = j / EPL;
+#pragma unroll
+                for (int t = 0; t < EPL; ++t) {
+                    const int e = lane * EPL + t;
+                    const double y = __shfl_xor_sync(0xFFFFFFFFu, x[t], lj);
+                    const bool up = ((e & k) == 0), lower = ((lane & lj) == 0);
+                    const double mn = fmin(x[t], y), mx = fmax(x[t], y);
+                    x[t] = (up == lower) ? mn : mx;
+                }
+            } else {                                 // partner in this lane's registers
+#pragma unroll
+                for (int t = 0; t < EPL; ++t) {
+                    const int u = t ^ j;
+                    if (u > t) {
+                        const int e = lane * EPL + t;
+                        const bool up = ((e & k) == 0);
+                        const double a = x[t], b = x[u];
+                        const double mn = fmin(a, b), mx = fmax(a, b);
+                        x[t] = up ? mn : mx; x[u] = up ? mx : mn;
+                    }
+                }
+            }
+        }
+    }
+    // sorted ascending: element e in lane e / EPL, register e % EPL
+    auto at = [&](int e) -> double {
+        double v = 0.0;
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) if ((e % EPL) == t) v = x[t];
+        return __shfl_sync(0xFFFFFFFFu, v, e / EPL);
+    };
+    if (cnt == 0) {
+        if (lane < 4) o4[(size_t)lane * L] = nan;
+        return;
+    }
+    const int half = (cnt + 1) / 2;
+    const double m0 = at(half - 1), m1 = at(min(half, 32 * EPL - 1));
+    const double pr[2] = {p_lo, p_hi};
+    double qv[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double index = 1.0 + (cnt - 1) * pr[k];
+        const double lo = floor(index), hi = ceil(index);
+        double qs = at((int)lo - 1);
+        const double xh = at((int)hi - 1);
+        if (index > lo && xh != qs) { const double h = index - lo; qs = (1.0 - h) * qs + h * xh; }
+        qv[k] = qs;
+    }
+    if (lane == 0) {
+        o4[0] = tot / cnt;
+        o4[L] = (cnt % 2 == 1) ? m0 : (m0 + m1) / 2.0;
+        o4[2 * (size_t)L] = qv[0];
+        o4[3 * (size_t)L] = qv[1];
+    }
 }
 
 // ---- Mean / Median / Lower / Upper over the M draws (R/survfitJM.mvJMbayes.R:400-414) ----------------------------
