@@ -313,9 +313,41 @@ __device__ __forceinline__ double sv_eval_generic(const SvDesc& d, const SvLayou
 
 // Static flavour: the model shape is the constexpr descriptor Spec::d, every loop over outcomes / terms /
 // columns is unrolled at compile time and b stays in registers.  Same arithmetic, same order.
+// b-independent part of the lane's block-0 hazard row under fixed parameters (the mode search evaluates it ~500 times)
 template <class Spec>
+struct SvHazCache { double s12; double xb[Spec::d.T]; };
+
+template <class Spec>
+__device__ __forceinline__ void sv_haz_prepare(const double* __restrict__ rec, const double* sp, const int lane, SvHazCache<Spec>& hc) {
+    constexpr int T = Spec::d.T, p = Spec::d.p, WB = Spec::d.WB;
+    constexpr bool W2C = Spec::d.w2_const != 0;
+    constexpr int oBlk0 = Spec::L.o_blk0, psB = Spec::L.ps_betas, psG = Spec::L.ps_gam, psBs = Spec::L.ps_Bs;
+    constexpr int bW1off = Spec::L.b_W1off, bW1v = Spec::L.b_W1v, oW2c = Spec::L.o_W2c, bW2 = Spec::L.b_W2, bCol = Spec::L.b_col;
+    const double* __restrict__ blk = rec + oBlk0;
+    const int off = reinterpret_cast<const int*>(blk + bW1off)[lane];
+    double s1 = 0.0;
+    sfor<WB>([&](auto j) { s1 += blk[bW1v + j * kSvG + lane] * sp[psBs + off + j]; });
+    double s2 = 0.0;
+    sfor<p>([&](auto j) { s2 += (W2C ? rec[oW2c + j] : blk[bW2 + j * kSvG + lane]) * sp[psG + j]; });
+    hc.s12 = s1 + s2;
+    sfor<T>([&](auto tc) {
+        constexpr int t = tc;
+        constexpr int bo = Spec::d.boff[Spec::d.outc[t]];
+        double xb = 0.0;
+        sfor<Spec::d.ft[t]>([&](auto fc) {
+            constexpr int f = fc;
+            constexpr int idx = Spec::d.indf[t][f], c = Spec::d.xx_col[t][f];
+            if constexpr (c < 0) xb += sp[psB + bo + idx];
+            else xb += blk[bCol + c * kSvG + lane] * sp[psB + bo + idx];
+        });
+        hc.xb[t] = xb;
+    });
+}
+
+template <class Spec, bool CACHED>
 __device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec, const int blk_index, const bool full,
-                                                 const double* sb, const double* sp, const int lane, const unsigned gmask) {
+                                                 const double* sb, const double* sp, const int lane, const unsigned gmask,
+                                                 const SvHazCache<Spec>& hc) {
     constexpr int q = Spec::d.q, O = Spec::d.O, T = Spec::d.T, p = Spec::d.p, K = Spec::d.K, WB = Spec::d.WB;
     constexpr bool W2C = Spec::d.w2_const != 0;
     constexpr int oBlk0 = Spec::L.o_blk0, BLK = Spec::L.blk, psB = Spec::L.ps_betas, psG = Spec::L.ps_gam, psA = Spec::L.ps_alp;
@@ -325,20 +357,27 @@ __device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec,
 
     const double* __restrict__ blk = rec + oBlk0 + (long long)blk_index * BLK;
     constexpr int bW1off = Spec::L.b_W1off, bW1v = Spec::L.b_W1v, oW2c = Spec::L.o_W2c, bW2 = Spec::L.b_W2, bPw = Spec::L.b_Pw, oV = Spec::L.o_V;
-    const int off = reinterpret_cast<const int*>(blk + bW1off)[lane];
-    double s1 = 0.0;
-    sfor<WB>([&](auto j) { s1 += blk[bW1v + j * kSvG + lane] * sp[psBs + off + j]; });
-    double s2 = 0.0;
-    sfor<p>([&](auto j) { s2 += (W2C ? rec[oW2c + j] : blk[bW2 + j * kSvG + lane]) * sp[psG + j]; });
+    double s12;
+    if constexpr (CACHED) s12 = hc.s12;
+    else {
+        const int off = reinterpret_cast<const int*>(blk + bW1off)[lane];
+        double s1 = 0.0;
+        sfor<WB>([&](auto j) { s1 += blk[bW1v + j * kSvG + lane] * sp[psBs + off + j]; });
+        double s2 = 0.0;
+        sfor<p>([&](auto j) { s2 += (W2C ? rec[oW2c + j] : blk[bW2 + j * kSvG + lane]) * sp[psG + j]; });
+        s12 = s1 + s2;
+    }
     double s3 = 0.0;
     constexpr int bCol = Spec::L.b_col;
     double colv[Spec::d.NC > 0 ? Spec::d.NC : 1];
     sfor<Spec::d.NC>([&](auto c) { colv[c] = blk[bCol + c * kSvG + lane]; });
     sfor<T>([&](auto tc) {
         constexpr int t = tc;
-        constexpr int bo = Spec::d.boff[Spec::d.outc[t]], bU = Spec::L.b_U[t], tf = Spec::d.tf[t];
+        [[maybe_unused]] constexpr int bo = Spec::d.boff[Spec::d.outc[t]];
+        constexpr int bU = Spec::L.b_U[t], tf = Spec::d.tf[t];
         double xb = 0.0;
-        sfor<Spec::d.ft[t]>([&](auto fc) {
+        if constexpr (CACHED) xb = hc.xb[t];
+        else sfor<Spec::d.ft[t]>([&](auto fc) {
             constexpr int f = fc;
             constexpr int idx = Spec::d.indf[t][f], c = Spec::d.xx_col[t][f];
             if constexpr (c < 0) xb += sp[psB + bo + idx];               // 1 * beta is exact
@@ -361,7 +400,7 @@ __device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec,
             s3 += w * sp[psA + cidx];
         });
     });
-    const double e = (lane < K) ? blk[bPw + lane] * exp((s1 + s2) + s3) : 0.0;
+    const double e = (lane < K) ? blk[bPw + lane] * exp(s12 + s3) : 0.0;
     const double H = group_sum<kSvG>(e, gmask);
     if (!full) return 0.0 - H;
 
@@ -474,199 +513,6 @@ __device__ inline void sv_eigen_sym(double* a, int n, double* val, double* vec) 
     }
 }
 
-// ---- mode search: the subject's control thread -----------------------------------------------------------------
-// vmmin (R src/appl/optim.c), fminfn / fmingr / optimhess (R src/library/stats/src/optim.c) as one resumable state
-// machine.  A request is IC_NEV evaluations of -log_post_RE_svft: 1 = the point btry, 2q = the central-difference
-// gradient cd(x, ff, eps) of R/cd.R at x (filled into grad[], already multiplied by parscale as fmingr does).
-__device__ __noinline__ void sv_advance_modes(const SvArgs& a, const int q, SvG& G, const double val) {
-    const double ps = a.c.parscale, stepredn = 0.2, acctol = 0.0001, reltest = 10.0;
-    const int n = q;
-    int* ic = G.ic;
-    double* sc = G.sc;
-    int st = ic[IC_STATE];
-    auto post_value = [&](int state) { ic[IC_NEV] = 1; ic[IC_STATE] = state; };
-    auto post_grad = [&](const double* z, int ret) {     // fmingr at the optimiser point z: x = z * parscale
-        for (int j = 0; j < n; ++j) G.x[j] = z[j] * ps;
-        ic[IC_RET] = ret; ic[IC_NEV] = 2 * n; ic[IC_STATE] = ST_GRAD;
-    };
-    for (;;) {
-        switch (st) {
-        case ST_FETCH: {
-            const int s = atomicAdd(a.work, 1);
-            if (s >= a.n) { ic[IC_SUBJ] = -1; ic[IC_NEV] = 0; ic[IC_STATE] = ST_FETCH; return; }
-            ic[IC_SUBJ] = s; ic[IC_CONV] = 0;
-            for (int j = 0; j < n; ++j) { G.bz[j] = 0.0 / ps; G.btry[j] = G.bz[j] * ps; }   // start = rep(0, q)
-            post_value(ST_F0);
-            return;
-        }
-        case ST_F0: {
-            const double f = 0.0 - val;
-            if (!isfinite(f)) {                      // error("initial value in 'vmmin' is not finite")
-                ic[IC_CONV] = 10; ic[IC_FUN] = 1; ic[IC_GRC] = 0;
-                const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                for (int j = 0; j < n; ++j) G.mode[j] = nan;
-                for (int j = 0; j < n * n; ++j) G.hess[j] = nan;
-                st = PC_MODE_DONE;
-                break;
-            }
-            sc[SC_FMIN] = f; sc[SC_F] = f;
-            ic[IC_FUN] = 1; ic[IC_GRC] = 1; ic[IC_ITER] = 0; ic[IC_COUNT] = 0;
-            post_grad(G.bz, RET_INIT);
-            return;
-        }
-        case ST_GRAD: {
-            const int ret = ic[IC_RET];
-            if (ret == RET_INIT) {
-                for (int j = 0; j < n; ++j) G.g[j] = G.grad[j];
-                ic[IC_ITER] = 1; ic[IC_ILAST] = ic[IC_GRC];
-                st = PC_LOOP_TOP;
-            } else if (ret == RET_LS) {
-                ic[IC_GRC] += 1; ic[IC_ITER] += 1;
-                const double step = sc[SC_STEP];
-                double D1 = 0.0;
-                for (int i = 0; i < n; ++i) {
-                    G.t[i] = step * G.t[i];
-                    G.c[i] = G.grad[i] - G.c[i];
-                    G.g[i] = G.grad[i];
-                    D1 += G.t[i] * G.c[i];
-                }
-                if (D1 > 0) {
-                    double D2 = 0.0;
-                    for (int i = 0; i < n; ++i) {
-                        double s = 0.0;
-                        for (int j = 0; j <= i; ++j) s += G.Bm[i * n + j] * G.c[j];
-                        for (int j = i + 1; j < n; ++j) s += G.Bm[j * n + i] * G.c[j];
-                        G.X[i] = s;
-                        D2 += s * G.c[i];
-                    }
-                    D2 = 1.0 + D2 / D1;
-                    for (int i = 0; i < n; ++i)
-                        for (int j = 0; j <= i; ++j)
-                            G.Bm[i * n + j] += (D2 * G.t[i] * G.t[j] - G.X[i] * G.t[j] - G.t[i] * G.X[j]) / D1;
-                } else {
-                    ic[IC_ILAST] = ic[IC_GRC];
-                }
-                st = PC_LOOP_END;
-            } else if (ret == RET_H1) {              // optimhess: df1 at dpar + eps e_i
-                const int hi = ic[IC_HI];
-                for (int j = 0; j < n; ++j) G.df1[j] = G.grad[j];
-                G.dpar[hi] = G.dpar[hi] - 2 * sc[SC_EPS_H];
-                post_grad(G.dpar, RET_H2);
-                return;
-            } else {                                 // RET_H2: df2 at dpar - eps e_i
-                const int hi = ic[IC_HI];
-                const double eps = sc[SC_EPS_H];
-                for (int j = 0; j < n; ++j) G.hess[hi * n + j] = (G.df1[j] - G.grad[j]) / (2 * eps * ps * ps);
-                G.dpar[hi] = G.dpar[hi] + eps;
-                if (hi + 1 < n) {
-                    ic[IC_HI] = hi + 1;
-                    G.dpar[hi + 1] = G.dpar[hi + 1] + eps;
-                    post_grad(G.dpar, RET_H1);
-                    return;
-                }
-                for (int i = 0; i < n; ++i)
-                    for (int j = 0; j < i; ++j) {
-                        const double tmp = 0.5 * (G.hess[i * n + j] + G.hess[j * n + i]);
-                        G.hess[i * n + j] = tmp; G.hess[j * n + i] = tmp;
-                    }
-                st = PC_MODE_DONE;
-            }
-            break;
-        }
-        case PC_LOOP_TOP: {
-            if (ic[IC_ILAST] == ic[IC_GRC])
-                for (int i = 0; i < n; ++i) { for (int j = 0; j < i; ++j) G.Bm[i * n + j] = 0.0; G.Bm[i * n + i] = 1.0; }
-            for (int i = 0; i < n; ++i) { G.X[i] = G.bz[i]; G.c[i] = G.g[i]; }
-            double gradproj = 0.0;
-            for (int i = 0; i < n; ++i) {
-                double s = 0.0;
-                for (int j = 0; j <= i; ++j) s -= G.Bm[i * n + j] * G.c[j];
-                for (int j = i + 1; j < n; ++j) s -= G.Bm[j * n + i] * G.c[j];
-                G.t[i] = s;
-                gradproj += s * G.c[i];
-            }
-            sc[SC_GP] = gradproj;
-            if (gradproj < 0.0) {                    // search direction is downhill
-                sc[SC_STEP] = 1.0;
-                st = PC_LS_TRY;
-            } else {                                 // uphill search
-                ic[IC_COUNT] = 0;
-                if (ic[IC_ILAST] == ic[IC_GRC]) ic[IC_COUNT] = n; else ic[IC_ILAST] = ic[IC_GRC];
-                st = PC_LOOP_END;
-            }
-            break;
-        }
-        case PC_LS_TRY: {
-            const double step = sc[SC_STEP];
-            int count = 0;
-            for (int i = 0; i < n; ++i) {
-                G.bz[i] = G.X[i] + step * G.t[i];
-                if (reltest + G.X[i] == reltest + G.bz[i]) count++;
-            }
-            ic[IC_COUNT] = count;
-            if (count < n) {
-                for (int j = 0; j < n; ++j) G.btry[j] = G.bz[j] * ps;
-                post_value(ST_LS);
-                return;
-            }
-            st = PC_LS_DONE;
-            break;
-        }
-        case ST_LS: {
-            const double f = 0.0 - val;
-            sc[SC_F] = f;
-            ic[IC_FUN] += 1;
-            const bool accpoint = isfinite(f) && (f <= sc[SC_FMIN] + sc[SC_GP] * sc[SC_STEP] * acctol);
-            if (!accpoint) { sc[SC_STEP] *= stepredn; st = PC_LS_TRY; }
-            else st = PC_LS_DONE;
-            break;
-        }
-        case PC_LS_DONE: {
-            const double f = sc[SC_F], Fmin = sc[SC_FMIN];
-            const bool enough = fabs(f - Fmin) > a.c.reltol * (fabs(Fmin) + a.c.reltol);   // abstol = -Inf
-            if (!enough) { ic[IC_COUNT] = n; sc[SC_FMIN] = f; }
-            if (ic[IC_COUNT] < n) {                  // making progress
-                sc[SC_FMIN] = f;
-                post_grad(G.bz, RET_LS);
-                return;
-            }
-            if (ic[IC_ILAST] < ic[IC_GRC]) { ic[IC_COUNT] = 0; ic[IC_ILAST] = ic[IC_GRC]; }   // no progress
-            st = PC_LOOP_END;
-            break;
-        }
-        case PC_LOOP_END: {
-            if (ic[IC_ITER] >= a.c.maxit) { st = PC_VM_DONE; break; }
-            if (ic[IC_GRC] - ic[IC_ILAST] > 2 * n) ic[IC_ILAST] = ic[IC_GRC];      // periodic restart
-            st = (ic[IC_COUNT] != n || ic[IC_ILAST] != ic[IC_GRC]) ? PC_LOOP_TOP : PC_VM_DONE;
-            break;
-        }
-        case PC_VM_DONE: {
-            ic[IC_CONV] = (ic[IC_ITER] < a.c.maxit) ? 0 : 1;
-            for (int j = 0; j < n; ++j) G.mode[j] = G.bz[j] * ps;                  // opt$par
-            const double eps = a.c.ndeps / ps;                                    // optimhess
-            sc[SC_EPS_H] = eps;
-            for (int j = 0; j < n; ++j) G.dpar[j] = G.mode[j] / ps;
-            ic[IC_HI] = 0;
-            G.dpar[0] = G.dpar[0] + eps;
-            post_grad(G.dpar, RET_H1);
-            return;
-        }
-        case PC_MODE_DONE: {
-            const long long s = ic[IC_SUBJ];
-            for (int j = 0; j < n; ++j) a.modes[s * n + j] = G.mode[j];
-            for (int j = 0; j < n * n; ++j) a.hess[s * n * n + j] = G.hess[j];
-            a.conv[s] = ic[IC_CONV];
-            a.counts[2 * s] = ic[IC_FUN]; a.counts[2 * s + 1] = ic[IC_GRC];
-            st = ST_FETCH;
-            break;
-        }
-        default:
-            ic[IC_NEV] = 0; ic[IC_SUBJ] = -1;
-            return;
-        }
-    }
-}
-
 #ifndef JMB_SVFT_THREADS
 #define JMB_SVFT_THREADS 256
 #endif
@@ -680,64 +526,268 @@ struct SvEvalGeneric {
                                                  int lane, unsigned gmask) const {
         return sv_eval_generic(d, L, rec, blk, full, sb, sp, lane, gmask);
     }
+    // the mode search evaluates block 0 under fixed parameters; the generic flavour keeps no per-lane cache
+    __device__ __forceinline__ void prepare(const double*, const double*, int) {}
+    __device__ __forceinline__ double full0(const double* rec, const double* sb, const double* sp, int lane, unsigned gmask) const {
+        return sv_eval_generic(d, L, rec, 0, true, sb, sp, lane, gmask);
+    }
 };
 template <class Spec>
 struct SvEvalStatic {
+    SvHazCache<Spec> hc;
     __device__ __forceinline__ double operator()(const double* rec, int blk, bool full, const double* sb, const double* sp,
                                                  int lane, unsigned gmask) const {
-        return sv_eval_static<Spec>(rec, blk, full, sb, sp, lane, gmask);
+        return sv_eval_static<Spec, false>(rec, blk, full, sb, sp, lane, gmask, hc);
+    }
+    __device__ __forceinline__ void prepare(const double* rec, const double* sp, int lane) { sv_haz_prepare<Spec>(rec, sp, lane, hc); }
+    __device__ __forceinline__ double full0(const double* rec, const double* sb, const double* sp, int lane, unsigned gmask) const {
+        return sv_eval_static<Spec, true>(rec, 0, true, sb, sp, lane, gmask, hc);
     }
 };
 
-// mode search of all subjects (R/survfitJM.mvJMbayes.R:277-305)
+// Mode search of all subjects (R/survfitJM.mvJMbayes.R:277-305): vmmin (R src/appl/optim.c), fminfn / fmingr /
+// optimhess (R src/library/stats/src/optim.c) and cd (R/cd.R) as a resumable state machine that all 16 lanes of the
+// group execute together.  Scalars are replicated in registers and computed by every lane with vmmin's own sequential
+// arithmetic; vectors live in shared memory, lane i owning element / row i.  A request is `nev` evaluations of
+// -log_post_RE_svft: 1 = the point btry, 2q = the central-difference gradient at x (written to grad[], already
+// multiplied by parscale as fmingr does).  Both groups of a warp always meet in the evaluation loop.
 template <class Eval>
-__device__ __forceinline__ void sv_modes_run(const int q, const SvArgs& a, const Eval& eval) {
+__device__ __forceinline__ void sv_modes_run(const int q, const SvArgs& a, Eval& eval) {
     extern __shared__ double sv_smem[];
     const int tid = threadIdx.x, lane = tid & (kSvG - 1), grp = tid / kSvG;
     const unsigned gmask = 0xFFFFu << (16 * ((tid & 31) >> 4));
     const int gdn = sv_group_doubles(q, a.ps_len), gd = (gdn + 1) / 2 * 2;
-    // views derived from the shared-memory window itself, so that the hot loads compile to LDS
+    // views carved from the shared-memory window itself (same order as sv_bind), so that loads compile to LDS
     double* gbase = sv_smem + (size_t)grp * gd;
     const double* sp = gbase;                        // parameter set (posterior means)
-    double* sbtry = gbase + a.ps_len;                // point of the evaluation
-    const double* sx = sbtry + q;                    // point of the posted gradient
-    double* sgrad = sbtry + 2 * q;
-    double* ssc = gbase + (gdn - (IC_N + 1) / 2 - SC_N);
-    volatile int* ic = reinterpret_cast<int*>(gbase + (gdn - (IC_N + 1) / 2));
-    SvG G;
-    sv_bind(G, gbase, q, a.ps_len);
+    double* v0 = gbase + a.ps_len;
+    double *btry = v0, *x = v0 + q, *grad = v0 + 2 * q, *bz = v0 + 3 * q, *X = v0 + 4 * q, *c = v0 + 5 * q, *t = v0 + 6 * q,
+           *g = v0 + 7 * q, *dpar = v0 + 8 * q, *df1 = v0 + 9 * q, *mode = v0 + 10 * q;
+    const int zq = (q + 2) / 2 * 2;
+    double* Bm = v0 + 14 * q + zq;
+    double* hess = Bm + q * q;
+    const int n = q;
+    const bool own = lane < n;                       // this lane owns element / row `lane`
+    const double ps = a.c.parscale, eps = a.c.cd_eps, stepredn = 0.2, acctol = 0.0001, reltest = 10.0;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (int j = lane; j < a.ps_len; j += kSvG) gbase[j] = a.par_mean[j];
-    if (lane == 0) {
-        for (int j = 0; j < IC_N; ++j) G.ic[j] = 0;
-        G.ic[IC_STATE] = ST_FETCH; G.ic[IC_SUBJ] = -1;
-        sv_advance_modes(a, q, G, 0.0);
-    }
     __syncwarp();
-    const double ps = a.c.parscale, eps = a.c.cd_eps;
+
+    // replicated control state
+    int st = ST_FETCH, subj = -1, nev = 0, ret = 0, count = 0, fun = 0, grc = 0, ilast = 0, iter = 0, hi = 0, conv = 0;
+    double Fmin = 0.0, f = 0.0, gradproj = 0.0, step = 0.0, epsH = 0.0, val = 0.0, f1 = 0.0, x1 = 0.0;
+    const double* rec = a.rec;
+    auto gsync = [&]() { __syncwarp(gmask); };
+    auto post_grad = [&](const double* z, int r) {   // fmingr at the optimiser point z: x = z * parscale
+        if (own) x[lane] = z[lane] * ps;
+        gsync();
+        ret = r; nev = 2 * n; st = ST_GRAD;
+    };
+    bool finished = false;                           // no more subjects for this group
     for (;;) {
-        const int nev = ic[IC_NEV];
+        // ---- control: consume `val` (or grad[]), run until the next request is posted ----
+        bool posted = finished;
+        while (!posted) {
+            switch (st) {
+            case ST_FETCH: {
+                int s = 0;
+                if (lane == 0) s = atomicAdd(a.work, 1);
+                s = __shfl_sync(gmask, s, 0, kSvG);
+                if (s >= a.n) { subj = -1; nev = 0; finished = true; posted = true; break; }
+                subj = s; conv = 0;
+                rec = a.rec + a.off[s];
+                eval.prepare(rec, sp, lane);
+                if (own) { bz[lane] = 0.0 / ps; btry[lane] = bz[lane] * ps; }       // start = rep(0, q)
+                gsync();
+                nev = 1; st = ST_F0; posted = true;
+                break;
+            }
+            case ST_F0: {
+                f = 0.0 - val;
+                if (!isfinite(f)) {                  // error("initial value in 'vmmin' is not finite")
+                    conv = 10; fun = 1; grc = 0;
+                    if (own) mode[lane] = nan;
+                    for (int j = lane; j < n * n; j += kSvG) hess[j] = nan;
+                    gsync();
+                    st = PC_MODE_DONE;
+                    break;
+                }
+                Fmin = f;
+                fun = 1; grc = 1; iter = 0; count = 0;
+                post_grad(bz, RET_INIT); posted = true;
+                break;
+            }
+            case ST_GRAD: {
+                if (ret == RET_INIT) {
+                    if (own) g[lane] = grad[lane];
+                    gsync();
+                    iter = 1; ilast = grc;
+                    st = PC_LOOP_TOP;
+                } else if (ret == RET_LS) {
+                    grc += 1; iter += 1;
+                    if (own) { t[lane] = step * t[lane]; c[lane] = grad[lane] - c[lane]; g[lane] = grad[lane]; }
+                    gsync();
+                    double D1 = 0.0;
+                    for (int i = 0; i < n; ++i) D1 += t[i] * c[i];
+                    if (D1 > 0) {
+                        if (own) {
+                            const int i = lane;
+                            double s = 0.0;
+                            for (int j = 0; j <= i; ++j) s += Bm[i * n + j] * c[j];
+                            for (int j = i + 1; j < n; ++j) s += Bm[j * n + i] * c[j];
+                            X[i] = s;
+                        }
+                        gsync();
+                        double D2 = 0.0;
+                        for (int i = 0; i < n; ++i) D2 += X[i] * c[i];
+                        D2 = 1.0 + D2 / D1;
+                        if (own) {
+                            const int i = lane;
+                            for (int j = 0; j <= i; ++j) Bm[i * n + j] += (D2 * t[i] * t[j] - X[i] * t[j] - t[i] * X[j]) / D1;
+                        }
+                        gsync();
+                    } else {
+                        ilast = grc;
+                    }
+                    st = PC_LOOP_END;
+                } else if (ret == RET_H1) {          // optimhess: df1 at dpar + eps e_i
+                    if (own) df1[lane] = grad[lane];
+                    if (lane == hi) dpar[hi] = dpar[hi] - 2 * epsH;
+                    gsync();
+                    post_grad(dpar, RET_H2); posted = true;
+                } else {                             // RET_H2: df2 at dpar - eps e_i
+                    if (own) hess[hi * n + lane] = (df1[lane] - grad[lane]) / (2 * epsH * ps * ps);
+                    if (lane == hi) dpar[hi] = dpar[hi] + epsH;
+                    gsync();
+                    if (hi + 1 < n) {
+                        hi += 1;
+                        if (lane == hi) dpar[hi] = dpar[hi] + epsH;
+                        gsync();
+                        post_grad(dpar, RET_H1); posted = true;
+                        break;
+                    }
+                    if (own) {
+                        const int i = lane;
+                        for (int j = 0; j < i; ++j) {
+                            const double tmp = 0.5 * (hess[i * n + j] + hess[j * n + i]);
+                            hess[i * n + j] = tmp; hess[j * n + i] = tmp;
+                        }
+                    }
+                    gsync();
+                    st = PC_MODE_DONE;
+                }
+                break;
+            }
+            case PC_LOOP_TOP: {
+                if (ilast == grc && own) {
+                    const int i = lane;
+                    for (int j = 0; j < i; ++j) Bm[i * n + j] = 0.0;
+                    Bm[i * n + i] = 1.0;
+                }
+                if (own) { X[lane] = bz[lane]; c[lane] = g[lane]; }
+                gsync();
+                if (own) {
+                    const int i = lane;
+                    double s = 0.0;
+                    for (int j = 0; j <= i; ++j) s -= Bm[i * n + j] * c[j];
+                    for (int j = i + 1; j < n; ++j) s -= Bm[j * n + i] * c[j];
+                    t[i] = s;
+                }
+                gsync();
+                gradproj = 0.0;
+                for (int i = 0; i < n; ++i) gradproj += t[i] * c[i];
+                if (gradproj < 0.0) {                // search direction is downhill
+                    step = 1.0;
+                    st = PC_LS_TRY;
+                } else {                             // uphill search
+                    count = 0;
+                    if (ilast == grc) count = n; else ilast = grc;
+                    st = PC_LOOP_END;
+                }
+                break;
+            }
+            case PC_LS_TRY: {
+                bool same = false;
+                if (own) {
+                    const double nb = X[lane] + step * t[lane];
+                    bz[lane] = nb;
+                    same = (reltest + X[lane] == reltest + nb);
+                    btry[lane] = nb * ps;
+                }
+                count = __popc(__ballot_sync(gmask, same));
+                gsync();
+                if (count < n) { nev = 1; st = ST_LS; posted = true; }
+                else st = PC_LS_DONE;
+                break;
+            }
+            case ST_LS: {
+                f = 0.0 - val;
+                fun += 1;
+                const bool accpoint = isfinite(f) && (f <= Fmin + gradproj * step * acctol);
+                if (!accpoint) { step *= stepredn; st = PC_LS_TRY; }
+                else st = PC_LS_DONE;
+                break;
+            }
+            case PC_LS_DONE: {
+                const bool enough = fabs(f - Fmin) > a.c.reltol * (fabs(Fmin) + a.c.reltol);   // abstol = -Inf
+                if (!enough) { count = n; Fmin = f; }
+                if (count < n) {                     // making progress
+                    Fmin = f;
+                    post_grad(bz, RET_LS); posted = true;
+                    break;
+                }
+                if (ilast < grc) { count = 0; ilast = grc; }                              // no progress
+                st = PC_LOOP_END;
+                break;
+            }
+            case PC_LOOP_END: {
+                if (iter >= a.c.maxit) { st = PC_VM_DONE; break; }
+                if (grc - ilast > 2 * n) ilast = grc;                                     // periodic restart
+                st = (count != n || ilast != grc) ? PC_LOOP_TOP : PC_VM_DONE;
+                break;
+            }
+            case PC_VM_DONE: {
+                conv = (iter < a.c.maxit) ? 0 : 1;
+                epsH = a.c.ndeps / ps;                                                    // optimhess
+                if (own) { mode[lane] = bz[lane] * ps; dpar[lane] = mode[lane] / ps; }    // opt$par
+                hi = 0;
+                if (lane == 0) dpar[0] = dpar[0] + epsH;
+                gsync();
+                post_grad(dpar, RET_H1); posted = true;
+                break;
+            }
+            default: {                               // PC_MODE_DONE
+                const long long s = subj;
+                if (own) a.modes[s * n + lane] = mode[lane];
+                for (int j = lane; j < n * n; j += kSvG) a.hess[s * n * n + j] = hess[j];
+                if (lane == 0) { a.conv[s] = conv; a.counts[2 * s] = fun; a.counts[2 * s + 1] = grc; }
+                st = ST_FETCH;
+                break;
+            }
+            }
+        }
+        // ---- evaluation: both groups of the warp together ----
         const int nmax = max(nev, __shfl_xor_sync(0xFFFFFFFFu, nev, 16));
         if (nmax == 0) break;
-        const double* rec = a.rec + a.off[max(ic[IC_SUBJ], 0)];
-        double val = 0.0;
         for (int e = 0; e < nmax; ++e) {
             const bool act = e < nev;
             const int i = e >> 1;
-            if (act && nev > 1 && lane < q) {         // cd(): x1 = x + ex e_i, then x2 = x - ex e_i (R/cd.R:5-10)
-                double xv = sx[lane];
+            if (act && nev > 1 && own) {              // cd(): x1 = x + ex e_i, then x2 = x - ex e_i (R/cd.R:5-10)
+                double xv = x[lane];
                 if (lane == i) { const double ex = eps * (fabs(xv) + eps); xv = (e & 1) ? xv - ex : xv + ex; }
-                sbtry[lane] = xv;
+                btry[lane] = xv;
             }
             __syncwarp();
-            if (act) val = eval(rec, 0, true, sbtry, sp, lane, gmask);
-            if (act && nev > 1 && lane == 0) {
-                if (!(e & 1)) { ssc[SC_F1] = 0.0 - val; ssc[SC_X1] = sbtry[i]; }
-                else sgrad[i] = ((ssc[SC_F1] - (0.0 - val)) / (ssc[SC_X1] - sbtry[i])) * ps;   // diff.f / diff.x, fmingr scaling
+            if (act) {
+                val = eval.full0(rec, btry, sp, lane, gmask);
+                if (nev > 1) {
+                    const double bi = btry[i];
+                    if (!(e & 1)) { f1 = 0.0 - val; x1 = bi; }
+                    else if (lane == 0) grad[i] = ((f1 - (0.0 - val)) / (x1 - bi)) * ps;   // diff.f / diff.x, fmingr scaling
+                }
             }
             __syncwarp();
         }
-        if (lane == 0 && nev > 0) sv_advance_modes(a, q, G, val);
-        __syncwarp();
     }
 }
 
@@ -916,13 +966,18 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
     }
 }
 
+#ifndef JMB_SVFT_MODES_MIN_CTAS
+#define JMB_SVFT_MODES_MIN_CTAS 2  // the mode search keeps more scalars live: 128 registers, no spills (A/B: 29.2 vs 30.0 ms)
+#endif
 template <class Spec>
-__global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS) jmb_svft_modes_static(const __grid_constant__ SvArgs a) {
-    sv_modes_run(Spec::d.q, a, SvEvalStatic<Spec>{});
+__global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MODES_MIN_CTAS) jmb_svft_modes_static(const __grid_constant__ SvArgs a) {
+    SvEvalStatic<Spec> ev{};
+    sv_modes_run(Spec::d.q, a, ev);
 }
-__global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS)
+__global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MODES_MIN_CTAS)
 jmb_svft_modes_generic(const __grid_constant__ SvMeta mm, const __grid_constant__ SvArgs a) {
-    sv_modes_run(mm.d.q, a, SvEvalGeneric{mm.d, mm.L});
+    SvEvalGeneric ev{mm.d, mm.L};
+    sv_modes_run(mm.d.q, a, ev);
 }
 template <class Spec>
 __global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS) jmb_svft_sample_static(const __grid_constant__ SvArgs a) {
