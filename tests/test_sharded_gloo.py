@@ -88,3 +88,46 @@ def test_shard_bounds_cover_and_balance():
         loads = np.add.reduceat(w, b[:-1])
         assert loads.max() / loads.mean() < 1.05
     assert list(shard_bounds(3, 3)) == [0, 1, 2, 3]
+
+
+# ---- survfitJM (config 5): subjects shard over ranks, no collective on the data path -----------------------------
+def _svft_worker(rank, world, port, n, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    from jmbayes_b200 import survfit as sv
+    from jmbayes_b200.cohorts import make_cohort
+    from jmbayes_b200.sharding import shard_bounds
+    from oracle import oracle_svft
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = make_cohort("config3", n=n)
+    means, draws = sv.posterior_draws(c, M=12)
+    b = shard_bounds(n, world)
+    sel = np.arange(int(b[rank]), int(b[rank + 1]))
+    d = sv.newdata_designs(c, L=3, subjects=sel)
+    r = oracle_svft.survfitJM(d, means, draws, subject_offset=int(b[rank]))
+    parts = [None] * world
+    dist.all_gather_object(parts, (int(b[rank]), r["summaries"], r["modes"]))      # a gather of results, nothing else
+    if rank == 0:
+        full = oracle_svft.survfitJM(sv.newdata_designs(c, L=3), means, draws)
+        parts = sorted(parts, key=lambda x: x[0])
+        S = np.concatenate([p[1] for p in parts], axis=2)
+        m = np.concatenate([p[2] for p in parts], axis=0)
+        ret.put(bool(np.array_equal(S, full["summaries"]) and np.array_equal(m, full["modes"])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_survfit_equals_single_process():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_svft_worker, args=(r, 2, port, 30, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert ret.get(timeout=5) is True
