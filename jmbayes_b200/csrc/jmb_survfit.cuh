@@ -344,65 +344,87 @@ __device__ __forceinline__ void sv_haz_prepare(const double* __restrict__ rec, c
     });
 }
 
-template <class Spec, bool CACHED>
-__device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec, const int blk_index, const bool full,
-                                                 const double* sb, const double* sp, const int lane, const unsigned gmask,
-                                                 const SvHazCache<Spec>& hc) {
-    constexpr int q = Spec::d.q, O = Spec::d.O, T = Spec::d.T, p = Spec::d.p, K = Spec::d.K, WB = Spec::d.WB;
+// NB blocks x NP points in one pass (one of them is 1): slot s evaluates block (NB == 2 ? s : 0) at point (NP == 2 ? s : 0).
+// Two slots give every lane two independent exp / log chains (the kernels are bound by fixed-latency fp64 dependencies),
+// and two points on the same block share the b-independent part of the row.  Arithmetic per slot is that of one slot.
+template <class Spec, bool CACHED, int NB, int NP>
+__device__ __forceinline__ void sv_eval_static_n(const double* __restrict__ rec, const int (&blk_index)[NB], const bool full,
+                                                 const double* const (&sb)[NP], const double* sp, const int lane,
+                                                 const unsigned gmask, const SvHazCache<Spec>& hc,
+                                                 double (&out)[(NB > NP ? NB : NP)]) {
+    constexpr int S = (NB > NP ? NB : NP);
+    static_assert(NB == 1 || NP == 1, "two blocks or two points, not both");
+    constexpr int q = Spec::d.q, O = Spec::d.O, T = Spec::d.T, p = Spec::d.p, K = Spec::d.K, WB = Spec::d.WB, NC = Spec::d.NC;
     constexpr bool W2C = Spec::d.w2_const != 0;
     constexpr int oBlk0 = Spec::L.o_blk0, BLK = Spec::L.blk, psB = Spec::L.ps_betas, psG = Spec::L.ps_gam, psA = Spec::L.ps_alp;
     constexpr int psBs = Spec::L.ps_Bs, psD = Spec::L.ps_invD, psS = Spec::L.ps_isig;
-    double b[q];
-    sfor<q>([&](auto j) { b[j] = sb[j]; });
+    constexpr int bW1off = Spec::L.b_W1off, bW1v = Spec::L.b_W1v, oW2c = Spec::L.o_W2c, bW2 = Spec::L.b_W2, bPw = Spec::L.b_Pw;
+    constexpr int oV = Spec::L.o_V, bCol = Spec::L.b_col;
+    double b[NP][q];
+    sfor<NP>([&](auto pc) { sfor<q>([&](auto j) { b[pc][j] = sb[pc][j]; }); });
 
-    const double* __restrict__ blk = rec + oBlk0 + (long long)blk_index * BLK;
-    constexpr int bW1off = Spec::L.b_W1off, bW1v = Spec::L.b_W1v, oW2c = Spec::L.o_W2c, bW2 = Spec::L.b_W2, bPw = Spec::L.b_Pw, oV = Spec::L.o_V;
-    double s12;
-    if constexpr (CACHED) s12 = hc.s12;
-    else {
-        const int off = reinterpret_cast<const int*>(blk + bW1off)[lane];
-        double s1 = 0.0;
-        sfor<WB>([&](auto j) { s1 += blk[bW1v + j * kSvG + lane] * sp[psBs + off + j]; });
-        double s2 = 0.0;
-        sfor<p>([&](auto j) { s2 += (W2C ? rec[oW2c + j] : blk[bW2 + j * kSvG + lane]) * sp[psG + j]; });
-        s12 = s1 + s2;
-    }
-    double s3 = 0.0;
-    constexpr int bCol = Spec::L.b_col;
-    double colv[Spec::d.NC > 0 ? Spec::d.NC : 1];
-    sfor<Spec::d.NC>([&](auto c) { colv[c] = blk[bCol + c * kSvG + lane]; });
-    sfor<T>([&](auto tc) {
-        constexpr int t = tc;
-        [[maybe_unused]] constexpr int bo = Spec::d.boff[Spec::d.outc[t]];
-        constexpr int bU = Spec::L.b_U[t], tf = Spec::d.tf[t];
-        double xb = 0.0;
-        if constexpr (CACHED) xb = hc.xb[t];
-        else sfor<Spec::d.ft[t]>([&](auto fc) {
-            constexpr int f = fc;
-            constexpr int idx = Spec::d.indf[t][f], c = Spec::d.xx_col[t][f];
-            if constexpr (c < 0) xb += sp[psB + bo + idx];               // 1 * beta is exact
-            else xb += colv[c] * sp[psB + bo + idx];
-        });
-        double zb = 0.0;
-        sfor<Spec::d.rt[t]>([&](auto jc) {
-            constexpr int j = jc;
-            constexpr int idx = Spec::d.re2[t][j], c = Spec::d.zz_col[t][j];
-            if constexpr (c < 0) zb += b[idx];
-            else zb += colv[c] * b[idx];
-        });
-        double v = xb + zb;
-        if constexpr (tf != JMB_TF_IDENTITY) v = trans_fun(tf, v);
-        sfor<Spec::d.ut[t]>([&](auto uc) {
-            constexpr int u = uc;
-            double w = v;
-            constexpr int cidx = Spec::d.col[t][u];
-            if constexpr (Spec::d.u_ones[t] == 0) w = blk[bU + u * kSvG + lane] * v;
-            s3 += w * sp[psA + cidx];
+    const double* __restrict__ blk[NB];
+    double s12[NB], colv[NB][NC > 0 ? NC : 1], xbv[NB][T], pw[NB];
+    sfor<NB>([&](auto bc) {
+        constexpr int ib = bc;
+        blk[ib] = rec + oBlk0 + (long long)blk_index[ib] * BLK;
+        pw[ib] = blk[ib][bPw + lane];
+        sfor<NC>([&](auto c) { colv[ib][c] = blk[ib][bCol + c * kSvG + lane]; });
+        if constexpr (CACHED) s12[ib] = hc.s12;
+        else {
+            const int off = reinterpret_cast<const int*>(blk[ib] + bW1off)[lane];
+            double s1 = 0.0;
+            sfor<WB>([&](auto j) { s1 += blk[ib][bW1v + j * kSvG + lane] * sp[psBs + off + j]; });
+            double s2 = 0.0;
+            sfor<p>([&](auto j) { s2 += (W2C ? rec[oW2c + j] : blk[ib][bW2 + j * kSvG + lane]) * sp[psG + j]; });
+            s12[ib] = s1 + s2;
+        }
+        sfor<T>([&](auto tc) {
+            constexpr int t = tc;
+            [[maybe_unused]] constexpr int bo = Spec::d.boff[Spec::d.outc[t]];
+            double xb = 0.0;
+            if constexpr (CACHED) xb = hc.xb[t];
+            else sfor<Spec::d.ft[t]>([&](auto fc) {
+                constexpr int f = fc;
+                constexpr int idx = Spec::d.indf[t][f], c = Spec::d.xx_col[t][f];
+                if constexpr (c < 0) xb += sp[psB + bo + idx];               // 1 * beta is exact
+                else xb += colv[ib][c] * sp[psB + bo + idx];
+            });
+            xbv[ib][t] = xb;
         });
     });
-    const double e = (lane < K) ? blk[bPw + lane] * exp(s12 + s3) : 0.0;
-    const double H = group_sum<kSvG>(e, gmask);
-    if (!full) return 0.0 - H;
+    double H[S];
+    sfor<S>([&](auto sc) {
+        constexpr int sl = sc;
+        constexpr int ib = (NB == 2) ? sl : 0, ip = (NP == 2) ? sl : 0;
+        double s3 = 0.0;
+        sfor<T>([&](auto tc) {
+            constexpr int t = tc;
+            constexpr int bU = Spec::L.b_U[t], tf = Spec::d.tf[t];
+            double zb = 0.0;
+            sfor<Spec::d.rt[t]>([&](auto jc) {
+                constexpr int j = jc;
+                constexpr int idx = Spec::d.re2[t][j], c = Spec::d.zz_col[t][j];
+                if constexpr (c < 0) zb += b[ip][idx];
+                else zb += colv[ib][c] * b[ip][idx];
+            });
+            double v = xbv[ib][t] + zb;
+            if constexpr (tf != JMB_TF_IDENTITY) v = trans_fun(tf, v);
+            sfor<Spec::d.ut[t]>([&](auto uc) {
+                constexpr int u = uc;
+                double w = v;
+                constexpr int cidx = Spec::d.col[t][u];
+                if constexpr (Spec::d.u_ones[t] == 0) w = blk[ib][bU + u * kSvG + lane] * v;
+                s3 += w * sp[psA + cidx];
+            });
+        });
+        H[sl] = (lane < K) ? pw[ib] * exp(s12[ib] + s3) : 0.0;
+    });
+    sfor<S>([&](auto sc) { H[sc] = group_sum<kSvG>(H[sc], gmask); });
+    if (!full) {
+        sfor<S>([&](auto sc) { out[sc] = 0.0 - H[sc]; });
+        return;
+    }
 
     // visit rows of all outcomes as one lane-strided list (a subject has ~n_i rows per outcome, far fewer than 16):
     // each lane finds the outcome of its row, the exponential is shared by the logit / cloglog / log tails
@@ -411,9 +433,11 @@ __device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec,
     const double* __restrict__ lrec = rec + oBlk0 + (long long)(nh + 1) * BLK;
     int vk[O], total = 0;
     sfor<O>([&](auto k) { vk[k] = hdr[k]; total += vk[k]; });
-    double acc = 0.0;
+    double acc[NP];
+    sfor<NP>([&](auto pc) { acc[pc] = 0.0; });
     for (int r = lane; r < total; r += kSvG) {
-        double eta = 0.0, y = 0.0, isg = 1.0;
+        double eta[NP], y = 0.0, isg = 1.0;
+        sfor<NP>([&](auto pc) { eta[pc] = 0.0; });
         int mine = -1, c0 = 0, o0 = 0;
         sfor<O>([&](auto kc) {
             constexpr int k = kc;
@@ -426,29 +450,48 @@ __device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec,
                 double xb = 0.0;
                 if constexpr (x0 == 1) xb = sp[psB + bo];
                 sfor<pk - x0>([&](auto cc) { constexpr int c = cc + x0; xb += lr[(1 + c - x0) * v + rr] * sp[psB + bo + c]; });
-                double zb = 0.0;
-                if constexpr (z0 == 1) zb = b[ri0];
-                sfor<qk - z0>([&](auto jc) { constexpr int j = jc + z0; constexpr int idx = Spec::d.re_inds[k][j]; zb += lr[(1 + xc + j - z0) * v + rr] * b[idx]; });
-                eta = xb + zb; y = lr[rr]; isg = sp[psS + k]; mine = k;
+                sfor<NP>([&](auto pc) {
+                    constexpr int ip = pc;
+                    double zb = 0.0;
+                    if constexpr (z0 == 1) zb = b[ip][ri0];
+                    sfor<qk - z0>([&](auto jc) { constexpr int j = jc + z0; constexpr int idx = Spec::d.re_inds[k][j]; zb += lr[(1 + xc + j - z0) * v + rr] * b[ip][idx]; });
+                    eta[ip] = xb + zb;
+                });
+                y = lr[rr]; isg = sp[psS + k]; mine = k;
             }
             c0 += v; o0 += lcols * v;
         });
-        const double E = exp(eta);
+        double E[NP];
+        sfor<NP>([&](auto pc) { E[pc] = exp(eta[pc]); });
         sfor<O>([&](auto kc) {
             constexpr int k = kc;
             constexpr int fam = Spec::d.fam[k], link = Spec::d.link[k];
-            if (mine == k) acc += sv_logdens_e(fam, link, y, eta, E, isg);
+            if (mine == k) sfor<NP>([&](auto pc) { acc[pc] += sv_logdens_e(fam, link, y, eta[pc], E[pc], isg); });
         });
     }
-    double qf = 0.0;
-    if (lane < q) {
-        double t = 0.0;
-        sfor<q>([&](auto l) { t += b[l] * sp[psD + l + lane * q]; });
-        qf = t * sb[lane];
-    }
-    const double log_pyb = group_sum<kSvG>(acc, gmask);
-    const double log_pb = -0.5 * group_sum<kSvG>(qf, gmask);
-    return (log_pyb + (0.0 - H)) + log_pb;
+    sfor<NP>([&](auto pc) {
+        constexpr int ip = pc;
+        double qf = 0.0;
+        if (lane < q) {
+            double t = 0.0;
+            sfor<q>([&](auto l) { t += b[ip][l] * sp[psD + l + lane * q]; });
+            qf = t * sb[ip][lane];
+        }
+        const double log_pyb = group_sum<kSvG>(acc[ip], gmask);
+        const double log_pb = -0.5 * group_sum<kSvG>(qf, gmask);
+        out[ip] = (log_pyb + (0.0 - H[ip])) + log_pb;
+    });
+}
+
+template <class Spec, bool CACHED>
+__device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec, const int blk_index, const bool full,
+                                                 const double* sb, const double* sp, const int lane, const unsigned gmask,
+                                                 const SvHazCache<Spec>& hc) {
+    const int bi[1] = {blk_index};
+    const double* const pts[1] = {sb};
+    double out[1];
+    sv_eval_static_n<Spec, CACHED, 1, 1>(rec, bi, full, pts, sp, lane, gmask, hc, out);
+    return out[0];
 }
 
 // ---- small dense helpers of the control thread (same algorithms as oracle/jmb_oracle_svft.c) ---------------
@@ -531,6 +574,17 @@ struct SvEvalGeneric {
     __device__ __forceinline__ double full0(const double* rec, const double* sb, const double* sp, int lane, unsigned gmask) const {
         return sv_eval_generic(d, L, rec, 0, true, sb, sp, lane, gmask);
     }
+    // two points on block 0 / two blocks at one point: the generic flavour simply evaluates twice
+    __device__ __forceinline__ void full2(const double* rec, const double* sbA, const double* sbB, const double* sp, int lane,
+                                          unsigned gmask, double& vA, double& vB) const {
+        vA = sv_eval_generic(d, L, rec, 0, true, sbA, sp, lane, gmask);
+        vB = sv_eval_generic(d, L, rec, 0, true, sbB, sp, lane, gmask);
+    }
+    __device__ __forceinline__ void block2(const double* rec, int blkA, int blkB, const double* sb, const double* sp, int lane,
+                                           unsigned gmask, double& vA, double& vB) const {
+        vA = sv_eval_generic(d, L, rec, blkA, false, sb, sp, lane, gmask);
+        vB = sv_eval_generic(d, L, rec, blkB, false, sb, sp, lane, gmask);
+    }
 };
 template <class Spec>
 struct SvEvalStatic {
@@ -542,6 +596,22 @@ struct SvEvalStatic {
     __device__ __forceinline__ void prepare(const double* rec, const double* sp, int lane) { sv_haz_prepare<Spec>(rec, sp, lane, hc); }
     __device__ __forceinline__ double full0(const double* rec, const double* sb, const double* sp, int lane, unsigned gmask) const {
         return sv_eval_static<Spec, true>(rec, 0, true, sb, sp, lane, gmask, hc);
+    }
+    __device__ __forceinline__ void full2(const double* rec, const double* sbA, const double* sbB, const double* sp, int lane,
+                                          unsigned gmask, double& vA, double& vB) const {
+        const int bi[1] = {0};
+        const double* const pts[2] = {sbA, sbB};
+        double out[2];
+        sv_eval_static_n<Spec, false, 1, 2>(rec, bi, true, pts, sp, lane, gmask, hc, out);
+        vA = out[0]; vB = out[1];
+    }
+    __device__ __forceinline__ void block2(const double* rec, int blkA, int blkB, const double* sb, const double* sp, int lane,
+                                           unsigned gmask, double& vA, double& vB) const {
+        const int bi[2] = {blkA, blkB};
+        const double* const pts[1] = {sb};
+        double out[2];
+        sv_eval_static_n<Spec, false, 2, 1>(rec, bi, false, pts, sp, lane, gmask, hc, out);
+        vA = out[0]; vB = out[1];
     }
 };
 
@@ -931,8 +1001,8 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
                 const double quad_p = group_sum<kSvG>(tp, gmask), quad_o = group_sum<kSvG>(to, gmask);
                 const double dmvt_p = -0.5 * (a.c.df + q) * log(1.0 + quad_p / a.c.df);
                 const double dmvt_o = -0.5 * (a.c.df + q) * log(1.0 + quad_o / a.c.df);
-                const double lp_p = eval(rec, 0, true, spb, sp, lane, gmask);
-                const double lp_o = eval(rec, 0, true, sb_old, sp, lane, gmask);
+                double lp_p, lp_o;                   // both points in one pass over block 0 and the visit rows
+                eval.full2(rec, spb, sb_old, sp, lane, gmask, lp_p, lp_o);
                 const double ea = exp(lp_p + dmvt_o - lp_o - dmvt_p);               // :372-377
                 accept = !isnan(ea) && ssc[SC_U] <= (ea < 1.0 ? ea : 1.0);
                 if (accept && lane < q) sb_new[lane] = spb[lane];
@@ -941,13 +1011,19 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
             __syncwarp();
             double cum = 0.0, mine = 0.0;            // survival on each prediction interval (:378-395)
             double* Srow = a.S + ((size_t)(have ? s : 0) * a.M + m) * a.L;
-            for (int l = 0; l < nh_max; ++l) {
+            for (int l = 0; l < nh_max; l += 2) {    // two intervals per pass
                 if (live && l < nh) {
-                    const double v = eval(rec, l + 1, false, sb_new, sp, lane, gmask);
-                    cum += v;
-                    if (lane == (l & (kSvG - 1))) mine = a.c.log ? v : cum;
+                    const bool two = l + 1 < nh;
+                    double v0, v1;
+                    eval.block2(rec, l + 1, two ? l + 2 : l + 1, sb_new, sp, lane, gmask, v0, v1);
+                    cum += v0;
+                    if (lane == (l & (kSvG - 1))) mine = a.c.log ? v0 : cum;
+                    if (two) {
+                        cum += v1;
+                        if (lane == ((l + 1) & (kSvG - 1))) mine = a.c.log ? v1 : cum;
+                    }
                 }
-                if ((l & (kSvG - 1)) == kSvG - 1 || l == nh_max - 1) {       // 16 intervals: exp(cumsum(logS)) by lane
+                if (((l + 1) & (kSvG - 1)) == kSvG - 1 || l + 2 >= nh_max) {  // 16 intervals: exp(cumsum(logS)) by lane
                     const int ll = (l & ~(kSvG - 1)) + lane;
                     if (live && ll < nh) Srow[ll] = a.c.log ? mine : exp(mine);
                 }
