@@ -111,6 +111,21 @@ typedef struct jmb_draw {
     const double* invD;                /* q x q */
 } jmb_draw;
 
+/* Fixed-effects designs of the fit (Data$X, Data$XX, Data$XXs, Data$XXs_int; R/mvJointModelBayes.R:234,407-467) for
+ * jmb_set_xdesigns / jmb_set_draw_betas: the per-draw linear predictors of Xbetas_calc
+ * (R/supportFuns_mvJointModelBayes.R:43-55, called for every draw at R/mvJointModelBayes.R:760-768) are then
+ * computed on the device from the draw's betas instead of being sent as N-vectors. */
+typedef struct jmb_xdesigns {
+    const int32_t* p_k;             /* [n_outcomes] ncol(X[[k]]) = length(betas[[k]]) */
+    const double* const* X;         /* [n_outcomes] N_k x p_k */
+    const int32_t* outcome;         /* [n_terms] outcome whose betas term t uses (0-based) */
+    const int32_t* f_t;             /* [n_terms] ncol(XX[[t]]) = length(indFixed[[t]]) */
+    const int32_t* const* indFixed; /* [n_terms][f_t] positions in betas[[outcome[t]]] (0-based) */
+    const double* const* XX;        /* [n_terms] n x f_t */
+    const double* const* XXs;       /* [n_terms] nK x f_t */
+    const double* const* XXs_int;   /* [n_terms] nK x f_t (interval_cens only) */
+} jmb_xdesigns;
+
 /* `priors` (src/fast_LAPRWM.cpp:531-569) */
 typedef struct jmb_priors {
     const double* mean_Bs_gammas; const double* Tau_Bs_gammas;  /* [B], B x B */
@@ -194,6 +209,12 @@ int jmb_destroy(jmb_handle h);
 
 /* Per-draw vectors of one chain (R/mvJointModelBayes.R:760-770). */
 int jmb_set_draw(jmb_handle h, const jmb_draw* draw);
+
+/* Upload the fixed-effects designs once per fit; afterwards jmb_set_draw_betas (betas[[k]] of the draw, sigmas,
+ * invD) is equivalent to Xbetas_calc on the host + jmb_set_draw, with a few hundred bytes of host-to-device
+ * traffic per draw instead of the N-vectors. */
+int jmb_set_xdesigns(jmb_handle h, const jmb_xdesigns* x);
+int jmb_set_draw_betas(jmb_handle h, const double* const* betas, const double* sigmas, const double* invD);
 
 /* lap_rwm_C (src/fast_LAPRWM.cpp:431-896) for the current draw. */
 int jmb_lap_rwm(jmb_handle h, const jmb_priors* priors, const jmb_control* control,

@@ -46,6 +46,11 @@ class JmbDraw(C.Structure):
                 ("XXsbetas_int", c_double_pp), ("sigmas", c_double_p), ("invD", c_double_p)]
 
 
+class JmbXDesigns(C.Structure):
+    _fields_ = [("p_k", c_int32_p), ("X", c_double_pp), ("outcome", c_int32_p), ("f_t", c_int32_p),
+                ("indFixed", c_int32_pp), ("XX", c_double_pp), ("XXs", c_double_pp), ("XXs_int", c_double_pp)]
+
+
 class JmbPriors(C.Structure):
     _fields_ = [
         ("mean_Bs_gammas", c_double_p), ("Tau_Bs_gammas", c_double_p),
@@ -194,6 +199,21 @@ def marshal_draw(Data: dict, interval_cens: bool):
     w.sigmas = k.f64(sig)
     w.invD = k.f64(Data["invD"])
     return w, k
+
+
+def marshal_xdesigns(Data: dict, interval_cens: bool):
+    """Data$X / XX / XXs / XXs_int + indFixed + outcome -> JmbXDesigns."""
+    k = Keep()
+    x = JmbXDesigns()
+    x.p_k = k.i32([np.asarray(m).shape[1] for m in Data["X"]])
+    x.X = k.f64_list(Data["X"])
+    x.outcome = k.i32(Data["outcome"])
+    x.f_t = k.i32([len(f) for f in Data["indFixed"]])
+    x.indFixed = k.i32_list(Data["indFixed"])
+    x.XX, x.XXs = k.f64_list(Data["XX"]), k.f64_list(Data["XXs"])
+    if interval_cens:
+        x.XXs_int = k.f64_list(Data["XXs_int"])
+    return x, k
 
 
 def marshal_priors(priors: dict):

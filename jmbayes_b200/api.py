@@ -45,6 +45,8 @@ def lib():
     L.jmb_create.argtypes = [C.POINTER(_abi.JmbData), C.c_int, C.POINTER(vp)]
     L.jmb_destroy.argtypes = [vp]
     L.jmb_set_draw.argtypes = [vp, C.POINTER(_abi.JmbDraw)]
+    L.jmb_set_xdesigns.argtypes = [vp, C.POINTER(_abi.JmbXDesigns)]
+    L.jmb_set_draw_betas.argtypes = [vp, _abi.c_double_pp, _abi.c_double_p, _abi.c_double_p]
     L.jmb_lap_rwm.argtypes = [vp, C.POINTER(_abi.JmbPriors), C.POINTER(_abi.JmbControl),
                               C.POINTER(_abi.JmbChainIn), C.POINTER(_abi.JmbChainOut)]
     L.jmb_chain_begin.argtypes = [vp, C.POINTER(_abi.JmbPriors), C.POINTER(_abi.JmbControl),
@@ -134,6 +136,22 @@ class Fit:
         w, keep = _abi.marshal_draw(Data, self.interval_cens)
         _check(lib().jmb_set_draw(self._h, C.byref(w)))
         del keep
+
+    def set_xdesigns(self, Data: dict):
+        """Upload Data$X / XX / XXs[_int] once per fit so that Xbetas_calc (R/supportFuns_mvJointModelBayes.R:43-55)
+        runs on the device for every draw (:meth:`set_draw_betas`)."""
+        x, keep = _abi.marshal_xdesigns(Data, self.interval_cens)
+        _check(lib().jmb_set_xdesigns(self._h, C.byref(x)))
+        del keep
+
+    def set_draw_betas(self, betas, sigmas, invD):
+        """The per-draw step of runParallel (R/mvJointModelBayes.R:760-770) from the draw's ``betas`` (list per outcome),
+        ``sigmas`` and ``invD``: a few hundred bytes host-to-device instead of the N-vectors of :meth:`set_draw`."""
+        k = _abi.Keep()
+        bl = k.f64_list([np.ascontiguousarray(b, dtype=np.float64) for b in betas])
+        sig = [1.0 if (s is None or (isinstance(s, float) and np.isnan(s))) else float(s) for s in sigmas]
+        _check(lib().jmb_set_draw_betas(self._h, bl, k.f64(sig), k.f64(invD)))
+        del k
 
     # -- lap_rwm_C --------------------------------------------------------------------------------
     def _marshal_chain(self, initials, priors, scales, Covs, control, chain_id):

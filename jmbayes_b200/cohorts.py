@@ -249,6 +249,7 @@ def make_cohort(config: str = "config3", n: int = 1000, seed: int | None = None,
 
     # ---- association terms, R/mvJointModelBayes.R:407-504 ---------------------------------
     XXbetas, XXsbetas, XXsbetas_int = [], [], []
+    XX, XXs, XXs_int, indFixed = [], [], [], []     # designs behind XXbetas = Xbetas_calc(XX, betas, indFixed, outcome)
     ZZ, ZZs, ZZs_int, U, Us, Us_int = [], [], [], [], [], []
     RE_inds = [np.array([2 * k, 2 * k + 1], dtype=np.int32) for k in range(O)]
     RE_inds2, col_inds, trans_Funs, outcome_of_term = [], [], [], []
@@ -259,10 +260,15 @@ def make_cohort(config: str = "config3", n: int = 1000, seed: int | None = None,
             f = lambda t: betas_draw[k][0] + betas_draw[k][1] * t
             z = lambda t: np.column_stack([np.ones_like(t), t])
             RE_inds2.append(RE_inds[k].copy())
+            indFixed.append(np.array([0, 1], dtype=np.int32))
         else:  # slope: fixed = ~1 with indFixed = 2, random = ~1 with indRandom = 2
             f = lambda t: np.full_like(t, betas_draw[k][1])
             z = lambda t: np.ones((t.size, 1))
             RE_inds2.append(RE_inds[k][1:].copy())
+            indFixed.append(np.array([1], dtype=np.int32))
+        XX.append(_F(z(Time))); XXs.append(_F(z(st_vec)))
+        if interval:
+            XXs_int.append(_F(z(st_int_vec)))
         XXbetas.append(f(Time)); XXsbetas.append(f(st_vec))
         ZZ.append(_F(z(Time))); ZZs.append(_F(z(st_vec)))
         U.append(_F(np.ones((n, 1)))); Us.append(_F(np.ones((n * K, 1))))
@@ -296,6 +302,7 @@ def make_cohort(config: str = "config3", n: int = 1000, seed: int | None = None,
         idTs=[np.repeat(np.arange(n, dtype=np.int32), K) for _ in range(A)],
         Pw=Pw, nRisks=1, kn_strat_first=np.array([0]), kn_strat_last=np.array([B - 1]),
         outcome=np.array(outcome_of_term, dtype=np.int32), st=st_vec, knots=knots,
+        XX=XX, XXs=XXs, XXs_int=XXs_int, indFixed=indFixed, betas=[np.asarray(bk, dtype=np.float64) for bk in betas_draw],
     )
     Data["idT2"] = Data["idT"]
     Data["idT2s"] = Data["idTs"]

@@ -126,6 +126,9 @@ struct jmb_handle_s {
     // launch configuration
     int grid = 0, subjects_per_cta = 0, smem_bytes = 0;
     long long launches = 0;
+    // fixed-effects designs for Xbetas_calc on the device (jmb_set_xdesigns)
+    double* d_xrec = nullptr; long long* d_xoff = nullptr; double* d_betas = nullptr;
+    XbDesc xd{}; int n_betas = 0; bool xdesigns_set = false;
     // step kernel chosen for this model: a precompiled static specialisation or the generic one
     void (*static_kernel)(int, ParamLayout, ChainConst, StepArgs) = nullptr;
     void (*tma_kernel)(int, ParamLayout, ChainConst, StepArgs, TmaArgs) = nullptr;
@@ -548,7 +551,7 @@ extern "C" int jmb_destroy(jmb_handle h) {
     for (ChainCtx* x : h->slots) if (x->stream) cudaStreamSynchronize(x->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->d_drec); cudaFree(h->d_doff); cudaFree(h->d_coff); cudaFree(h->d_rowptr); cudaFree(h->d_eval);
-    cudaFree(h->d_Rchol);
+    cudaFree(h->d_Rchol); cudaFree(h->d_xrec); cudaFree(h->d_xoff); cudaFree(h->d_betas);
     for (size_t r = 0; r < h->peer_ptrs.size(); ++r)
         if (h->peer_ptrs[r] && (int)r != h->rank) cudaIpcCloseMemHandle(h->peer_ptrs[r]);
     cudaFree(h->d_mbox); cudaFree(h->d_peer_mbox);
@@ -604,6 +607,100 @@ extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
     for (int k = 0; k < O; ++k) h->c->h_par[h->pl.sigmas + k] = (mm.d.fam[k] == JMB_FAM_GAUSSIAN) ? w->sigmas[k] : 1.0;
     CU(cudaMemcpyAsync(h->c->d_par + h->pl.invD, h->c->h_par + h->pl.invD, sizeof(double) * (mm.d.q * mm.d.q + O), cudaMemcpyHostToDevice, h->c->stream));
     h->c->draw_set = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Xbetas_calc on the device: fixed-effects designs once per fit, betas per draw
+// ---------------------------------------------------------------------------------------------
+extern "C" int jmb_set_xdesigns(jmb_handle h, const jmb_xdesigns* x) {
+    if (!h || !x || !x->p_k || !x->X || !x->outcome || !x->f_t || !x->indFixed || !x->XX || !x->XXs)
+        return fail("jmb_set_xdesigns: null argument");
+    const ModelMeta& mm = h->mm;
+    const int n = h->n, K = mm.d.K, RP = mm.L.RP, S = mm.d.S, T = mm.d.T, O = mm.d.O;
+    if (S == 2 && !x->XXs_int) return fail("jmb_set_xdesigns: XXs_int required with interval censoring");
+    XbDesc& xd = h->xd;
+    memset(&xd, 0, sizeof(xd));
+    xd.T = T; xd.O = O; xd.RP = RP;
+    int nb = 0;
+    for (int k = 0; k < O; ++k) {
+        if (x->p_k[k] <= 0 || x->p_k[k] > 64) return fail("jmb_set_xdesigns: p_k out of range");
+        xd.pk[k] = x->p_k[k]; xd.boff[k] = nb; nb += x->p_k[k];
+    }
+    h->n_betas = nb;
+    int tb = 0;
+    for (int t = 0; t < T; ++t) {
+        if (x->f_t[t] < 0 || x->f_t[t] > JMB_MAX_RT) return fail("jmb_set_xdesigns: f_t out of range (0..8)");
+        if (x->outcome[t] < 0 || x->outcome[t] >= O) return fail("jmb_set_xdesigns: outcome[t] out of range");
+        xd.ft[t] = x->f_t[t]; xd.tbase[t] = tb; tb += x->f_t[t]; xd.tboff[t] = xd.boff[x->outcome[t]];
+        for (int f = 0; f < xd.ft[t]; ++f) {
+            xd.indf[t][f] = x->indFixed[t][f];
+            if (xd.indf[t][f] < 0 || xd.indf[t][f] >= xd.pk[x->outcome[t]]) return fail("jmb_set_xdesigns: indFixed out of range");
+        }
+    }
+    const long long ns = (long long)n * K;
+    std::vector<long long> xoff(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        long long len = (long long)tb * RP;
+        for (int k = 0; k < O; ++k) len += (long long)(h->rowptr[k][i + 1] - h->rowptr[k][i]) * xd.pk[k];
+        xoff[i + 1] = xoff[i] + len;
+    }
+    std::vector<double> xrec((size_t)std::max<long long>(xoff[n], 1), 0.0);
+    parallel_for(n, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            double* xr = xrec.data() + xoff[i];
+            for (int t = 0; t < T; ++t)
+                for (int f = 0; f < xd.ft[t]; ++f) {
+                    double* col = xr + (size_t)(xd.tbase[t] + f) * RP;
+                    col[0] = x->XX[t][i + (long long)f * n];
+                    for (int r = 1; r <= K; ++r) col[r] = x->XXs[t][(long long)i * K + r - 1 + (long long)f * ns];
+                    if (S == 2) for (int r = 1; r <= K; ++r) col[K + r] = x->XXs_int[t][(long long)i * K + r - 1 + (long long)f * ns];
+                }
+            double* l = xr + (size_t)tb * RP;
+            for (int k = 0; k < O; ++k) {
+                const int r0 = h->rowptr[k][i], v = h->rowptr[k][i + 1] - r0;
+                const long long Nk = h->N[k];
+                for (int c = 0; c < xd.pk[k]; ++c)
+                    for (int r = 0; r < v; ++r) l[(size_t)c * v + r] = x->X[k][r0 + r + (long long)c * Nk];
+                l += (size_t)xd.pk[k] * v;
+            }
+        }
+    });
+    CU(cudaSetDevice(h->device));
+    cudaFree(h->d_xrec); cudaFree(h->d_xoff); cudaFree(h->d_betas);
+    h->d_xrec = nullptr; h->d_xoff = nullptr; h->d_betas = nullptr;
+    CU(cudaMalloc(&h->d_xrec, sizeof(double) * xrec.size()));
+    CU(cudaMalloc(&h->d_xoff, sizeof(long long) * (n + 1)));
+    CU(cudaMalloc(&h->d_betas, sizeof(double) * std::max(nb, 1) * 64));       // one slice per chain slot
+    CU(cudaMemcpy(h->d_xrec, xrec.data(), sizeof(double) * xrec.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_xoff, xoff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
+    h->xdesigns_set = true;
+    return 0;
+}
+
+extern "C" int jmb_set_draw_betas(jmb_handle h, const double* const* betas, const double* sigmas, const double* invD) {
+    if (!h || !betas || !invD) return fail("jmb_set_draw_betas: null argument");
+    if (!h->xdesigns_set) return fail("jmb_set_draw_betas: call jmb_set_xdesigns first");
+    CU(cudaSetDevice(h->device));
+    const ModelMeta& mm = h->mm;
+    const int O = mm.d.O, n = h->n;
+    ChainCtx* c = h->c;
+    CU(cudaStreamSynchronize(c->stream));           // h_par staging may still be in flight
+    double* hb = c->h_tmp;                          // pinned staging (n * (q + 1) doubles >= n_betas)
+    if (h->n_betas > (long long)n * (mm.d.q + 1)) return fail("jmb_set_draw_betas: too many fixed effects for the staging buffer");
+    for (int k = 0; k < O; ++k)
+        for (int j = 0; j < h->xd.pk[k]; ++j) hb[h->xd.boff[k] + j] = betas[k][j];
+    double* d_b = h->d_betas + (size_t)c->slot_index * std::max(h->n_betas, 1);
+    CU(cudaMemcpyAsync(d_b, hb, sizeof(double) * h->n_betas, cudaMemcpyHostToDevice, c->stream));
+    const unsigned grid = (unsigned)(((long long)n * 32 + 255) / 256);
+    jmb_xbetas_kernel<<<grid, 256, 0, c->stream>>>(h->xd, h->d_xrec, h->d_xoff, h->d_coff, h->d_rowptr, d_b, n, c->d_crec);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    for (int j = 0; j < mm.d.q * mm.d.q; ++j) c->h_par[h->pl.invD + j] = invD[j];
+    for (int k = 0; k < O; ++k) c->h_par[h->pl.sigmas + k] = (mm.d.fam[k] == JMB_FAM_GAUSSIAN) ? sigmas[k] : 1.0;
+    CU(cudaMemcpyAsync(c->d_par + h->pl.invD, c->h_par + h->pl.invD, sizeof(double) * (mm.d.q * mm.d.q + O), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));           // the staging buffers are reused by chain_begin
+    c->draw_set = true;
     return 0;
 }
 

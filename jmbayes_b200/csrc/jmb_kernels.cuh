@@ -755,6 +755,46 @@ __global__ void jmb_extract_b_kernel(const double* state, int stride, int n, int
 }
 
 // state <- initial b (n x q column-major) and scales$b
+// Xbetas_calc on the device (R/supportFuns_mvJointModelBayes.R:43-55): fills a chain's per-draw records from the
+// fixed-effects designs of the fit and the betas of the draw.  The x-record of a subject mirrors its per-draw
+// record: per term [f_t][RP] design columns, then per outcome [p_k][v] design columns.  One warp per subject.
+struct XbDesc {
+    int T, O, RP;
+    int ft[kMaxT], tbase[kMaxT], tboff[kMaxT];          // columns, first column in the x-record, offset of betas[[outcome]]
+    int indf[kMaxT][JMB_MAX_RT];
+    int pk[kMaxO], boff[kMaxO];
+};
+__global__ void jmb_xbetas_kernel(const __grid_constant__ XbDesc xd, const double* __restrict__ xrec,
+                                  const long long* __restrict__ xoff, const long long* __restrict__ coff,
+                                  const int* __restrict__ rowptr, const double* __restrict__ betas, const int n,
+                                  double* __restrict__ crec) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const int i = (int)w;
+    const double* __restrict__ xr = xrec + xoff[i];
+    double* __restrict__ cr = crec + coff[i];
+    const int RP = xd.RP, nt = xd.T * RP;
+    for (int e = lane; e < nt; e += 32) {
+        const int t = e / RP, r = e - t * RP;
+        double acc = 0.0;
+        for (int f = 0; f < xd.ft[t]; ++f) acc += xr[(xd.tbase[t] + f) * RP + r] * betas[xd.tboff[t] + xd.indf[t][f]];
+        cr[e] = acc;
+    }
+    int xo = 0, co = nt;
+    for (int t = 0; t < xd.T; ++t) xo += xd.ft[t] * RP;
+    for (int k = 0; k < xd.O; ++k) {
+        const int v = rowptr[(long long)k * (n + 1) + i + 1] - rowptr[(long long)k * (n + 1) + i];
+        for (int r = lane; r < v; r += 32) {
+            double acc = 0.0;
+            for (int c = 0; c < xd.pk[k]; ++c) acc += xr[xo + c * v + r] * betas[xd.boff[k] + c];
+            cr[co + r] = acc;
+        }
+        xo += xd.pk[k] * v;
+        co += v;
+    }
+}
+
 __global__ void jmb_load_state_kernel(double* state, int stride, int n, int q, const double* b,
                                       const double* sigma_b) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -203,3 +203,45 @@ def test_chains_in_flight_equal_sequential_chains(cuda_lib):
         assert np.array_equal(a["extras"]["trace_surv"], b["extras"]["trace_surv"])
         assert np.array_equal(a["scales"]["sigma"]["b"], b["scales"]["sigma"]["b"])
     assert not np.array_equal(par[0]["mcmc"]["alphas"], par[1]["mcmc"]["alphas"])
+
+
+# ---- Xbetas_calc on the device: set_xdesigns + set_draw_betas == host Xbetas_calc + set_draw -----------
+@pytest.mark.parametrize("cfg", ["config2", "config4"])
+def test_device_xbetas_equals_host_xbetas(cuda_lib, cfg):
+    """R/supportFuns_mvJointModelBayes.R:43-55 evaluated by jmb_xbetas_kernel from Data$X / XX / XXs[_int] and the draw's
+    betas: per-subject log-posterior pieces within 1e-12 relative of the host-Xbetas path (only the rounding of the
+    two-term dot products can differ), chains identical to 1e-9, also on a second chain slot."""
+    c = make_cohort(cfg, n=700)
+    D, ini = c["Data"], c["inits"]
+    ctl = dict(c["control"]); ctl.update(n_burnin=30, n_iter=10, n_block=10, n_thin=10)
+    with cuda_lib.Fit(D, c["Covs"]["b"], c["interval_cens"]) as fit:
+        fit.set_draw(D)
+        ref = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+        ch_ref = fit.lap_rwm_C(ini, c["priors"], c["scales"], c["Covs"], ctl)
+        fit.set_xdesigns(D)
+        fit.set_draw_betas(D["betas"], D["sigmas"], D["invD"])
+        got = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+        for k in ("log_pyb", "log_pb", "log_h", "H", "log_ptb"):
+            assert np.allclose(got[k], ref[k], rtol=1e-12, atol=1e-13), k
+        ch = fit.lap_rwm_C(ini, c["priors"], c["scales"], c["Covs"], ctl)
+        assert np.allclose(ch["extras"]["trace_surv"], ch_ref["extras"]["trace_surv"], rtol=1e-9)
+        assert np.allclose(ch["mcmc"]["b"], ch_ref["mcmc"]["b"], rtol=1e-8, atol=1e-10)
+        # another draw on another chain slot: different betas must give the host result for those betas
+        fit.chain_slots(2)
+        fit.select_chain(1)
+        b2 = [b + 0.05 for b in D["betas"]]
+        D2 = dict(D)
+        D2["Xbetas"] = [np.asarray(D["X"][k]) @ b2[k] for k in range(len(b2))]
+        for name in ("XXbetas", "XXsbetas") + (("XXsbetas_int",) if c["interval_cens"] else ()):
+            src = {"XXbetas": "XX", "XXsbetas": "XXs", "XXsbetas_int": "XXs_int"}[name]
+            D2[name] = [np.asarray(D[src][t]) @ b2[D["outcome"][t]][D["indFixed"][t]] for t in range(len(D["XX"]))]
+        fit.set_draw_betas(b2, D["sigmas"], D["invD"])
+        got2 = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+        fit.set_draw(D2)
+        ref2 = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+        for k in ("log_pyb", "log_h", "H", "log_ptb"):
+            assert np.allclose(got2[k], ref2[k], rtol=1e-12, atol=1e-13), k
+        assert not np.allclose(got2["log_pyb"], ref["log_pyb"], rtol=1e-6)
+    with cuda_lib.Fit(D, c["Covs"]["b"], c["interval_cens"]) as fit:
+        with pytest.raises(cuda_lib.JmbError):
+            fit.set_draw_betas(D["betas"], D["sigmas"], D["invD"])       # designs not uploaded
