@@ -364,11 +364,11 @@ def run_cuda(args):
 # ------------------------------------------------------------------------------------------------
 # BASELINE config 5: survfitJM.mvJMbayes() loop (R/survfitJM.mvJMbayes.R:277-414)
 # ------------------------------------------------------------------------------------------------
-def _svft_case(n, seed):
+def _svft_case(n, seed, dense_basis=True):
     from jmbayes_b200 import survfit as sv
     from jmbayes_b200.cohorts import make_cohort
     c = make_cohort("config3", n=n, seed=seed)
-    d = sv.newdata_designs(c, L=SVFT_L)
+    d = sv.newdata_designs(c, L=SVFT_L, dense_basis=dense_basis)     # the CPU restatement reads the reference's dense bases
     means, draws = sv.posterior_draws(c, M=SVFT_M)
     return d, means, draws
 
@@ -420,7 +420,9 @@ def run_config5(args):
         raise RuntimeError("no CUDA device: the hot path has no CPU fallback")
     n = args.n_per_gpu or WORKLOADS["config5"][1]
     steps, warmup = min(args.steps, 20), min(args.warmup, 3)
-    d, means, draws = _svft_case(n, 5000 + rank)          # subjects shard over ranks; no collective on this path
+    # subjects shard over ranks, no collective on this path; the B-spline rows are evaluated by the library from
+    # (knots, quadrature times), so the dense n*L*K x 17 basis never exists on the host
+    d, means, draws = _svft_case(n, 5000 + rank, dense_basis=False)
 
     def barrier():
         torch.cuda.synchronize()

@@ -1,7 +1,7 @@
 /*
  * jmb200_survfit.h - C ABI of the B200-native survfitJM.mvJMbayes() hot loop (BASELINE config 5).
  *
- * Replaces, for all new subjects at once and in ONE kernel launch, the per-subject R loops of
+ * Replaces, for all new subjects at once (three kernel launches: mode search, sampling, summaries), the per-subject R loops of
  * R/survfitJM.mvJMbayes.R (paths relative to the JMbayes source tree):
  *   :277-305  mode search  optim(start = 0, ff = -log_post_RE_svft, gg = cd(ff, eps = 1e-3), method = "BFGS",
  *             hessian = TRUE, control = list(maxit = 200, parscale = 0.1))
@@ -78,6 +78,13 @@ typedef struct jmb_svft_data {
     const int32_t* n_horizons;      /* [n] length(times.to.pred_upper[[i]]) <= L */
     const double* W1s_h; const double* W2s_h; const double* Pw_h;
     const double* const* XXs_h; const double* const* ZZs_h; const double* const* Us_h;
+    /* Alternative to the dense bases: when W1s (resp. W1s_h) is NULL, the rows
+     * splines::splineDesign(knots, x, ord, outer.ok = TRUE) (R/survfitJM.mvJMbayes.R:205,258) are evaluated by
+     * the library from the quadrature times themselves - the dense nK x n_Bs / nH x n_Bs matrices (20 GB for the
+     * horizons of 1M subjects) never exist.  n_knots = n_Bs + ord. */
+    const double* knots; int32_t n_knots; int32_t ord;
+    const double* st;               /* [nK]  c(t(GK_points_postRE)) */
+    const double* st_h;             /* [nH]  GK_points_CumHaz rows, row (i*L + l)*K + k */
 } jmb_svft_data;
 
 /* Parameters: either the posterior means (M = 1; :117-128) or the M sub-sampled posterior draws
@@ -122,7 +129,7 @@ int jmb_svft_modes(jmb_svft_handle h, const jmb_svft_params* post_means, const j
 /* :306-414 only, from given modes / Hessians (out->modes, out->hessians are INPUTS here). */
 int jmb_svft_sample(jmb_svft_handle h, const jmb_svft_params* draws, const jmb_svft_control* control,
                     jmb_svft_out* out);
-/* The whole loop (:277-414), one kernel launch for the subject work + one for the summaries. */
+/* The whole loop (:277-414): mode-search kernel, sampling kernel, summary kernel, back to back on one stream. */
 int jmb_survfitJM(jmb_svft_handle h, const jmb_svft_params* post_means, const jmb_svft_params* draws,
                   const jmb_svft_control* control, jmb_svft_out* out);
 

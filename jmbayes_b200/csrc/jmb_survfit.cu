@@ -39,6 +39,34 @@ static void parallel_for(long long n, F f) {
     for (auto& x : th) x.join();
 }
 
+// One row of splines::splineDesign(knots, x, ord, outer.ok = TRUE) in band form (R/survfitJM.mvJMbayes.R:205,258;
+// de Boor's local recursion): the `ord` values of the basis functions off .. off + ord - 1; rows outside
+// [knots[ord-1], knots[n_knots-ord]] are zero, the basis is right-closed at the last knot.
+static void spline_band_row(const double* t, int nk, int ord, double x, int& off, double* vals) {
+    const int nb = nk - ord;
+    for (int r = 0; r < ord; ++r) vals[r] = 0.0;
+    off = 0;
+    if (!(x >= t[ord - 1] && x <= t[nb])) return;
+    int j = (int)(std::upper_bound(t, t + nk, x) - t) - 1;      // t[j] <= x < t[j+1]
+    j = std::min(std::max(j, ord - 1), nb - 1);
+    double Bl[16], dl[16], dr[16];
+    Bl[0] = 1.0;
+    for (int d = 1; d < ord; ++d) {
+        dr[d - 1] = t[j + d] - x;
+        dl[d - 1] = x - t[j + 1 - d];
+        double saved = 0.0;
+        for (int r = 0; r < d; ++r) {
+            const double den = dr[r] + dl[d - 1 - r];
+            const double term = den != 0.0 ? Bl[r] / den : 0.0;
+            Bl[r] = saved + dr[r] * term;
+            saved = dl[d - 1 - r] * term;
+        }
+        Bl[d] = saved;
+    }
+    off = j - (ord - 1);
+    for (int r = 0; r < ord; ++r) vals[r] = Bl[r];
+}
+
 struct jmb_svft_handle_s {
     int device = 0, n = 0, B = 0, L = 0, ps_len = 0, num_sms = 148;
     long long subject_offset = 0;
@@ -127,6 +155,12 @@ extern "C" int jmb_svft_create(const jmb_svft_data* d, int device, jmb_svft_hand
         }
     }
     const long long nK = (long long)n * K, nH = (long long)n * L * K;
+    const bool from_knots = (d->W1s == nullptr);
+    if (from_knots) {
+        if (!d->knots || !d->st || (nH && !d->st_h)) BAD("jmb_svft_create: W1s is NULL, so knots / st / st_h are required");
+        if (d->ord < 1 || d->ord > 8 || d->n_knots != B + d->ord) BAD("jmb_svft_create: need 1 <= ord <= 8 and n_knots = n_Bs + ord");
+        for (int j = 1; j < d->n_knots; ++j) if (d->knots[j] < d->knots[j - 1]) BAD("jmb_svft_create: knots must be non-decreasing");
+    } else if (nH && !d->W1s_h) BAD("jmb_svft_create: W1s_h is required with a dense W1s");
 
     // ---- segment boundaries of the longitudinal outcomes (rows grouped by subject; empty segments allowed) ----
     std::vector<std::vector<int>> rowptr(O);
@@ -156,7 +190,8 @@ extern "C" int jmb_svft_create(const jmb_svft_data* d, int device, jmb_svft_hand
             if (W[r + (long long)j * rows] != 0.0) { if (first == B) first = j; last = j; }
     };
     int WB = 1;
-    {
+    if (from_knots) WB = std::min(d->ord, B);
+    else {
         std::atomic<int> wmax{1};
         auto scan = [&](const double* W, long long rows, bool horizon) {
             parallel_for(rows, [&, W, rows, horizon](long long lo, long long hi) {
@@ -271,12 +306,20 @@ extern "C" int jmb_svft_create(const jmb_svft_data* d, int device, jmb_svft_hand
                 for (int k = 0; k < K; ++k) {
                     const long long src = base + k;
                     blk[LY.b_Pw + k] = Pwx[src];
-                    int f, l;
-                    band_of(W1x, rows, src, f, l);
-                    int off = (l < f) ? 0 : std::min(f, B - WB);
-                    if (WB == B) off = 0;
-                    w1off[k] = off;
-                    for (int j = 0; j < WB; ++j) blk[LY.b_W1v + j * kSvG + k] = W1x[src + (long long)(off + j) * rows];
+                    if (from_knots) {
+                        int off; double bv[16];
+                        spline_band_row(d->knots, d->n_knots, d->ord, (hz ? d->st_h : d->st)[src], off, bv);
+                        // keep the window inside the basis when ord > n_Bs - off cannot happen: off <= n_Bs - ord
+                        w1off[k] = off;
+                        for (int j = 0; j < WB; ++j) blk[LY.b_W1v + j * kSvG + k] = bv[j];
+                    } else {
+                        int f, l;
+                        band_of(W1x, rows, src, f, l);
+                        int off = (l < f) ? 0 : std::min(f, B - WB);
+                        if (WB == B) off = 0;
+                        w1off[k] = off;
+                        for (int j = 0; j < WB; ++j) blk[LY.b_W1v + j * kSvG + k] = W1x[src + (long long)(off + j) * rows];
+                    }
                     if (!md.w2_const) for (int j = 0; j < p; ++j) blk[LY.b_W2 + j * kSvG + k] = W2x[src + (long long)j * rows];
                     for (int c = 0; c < md.NC; ++c) blk[LY.b_col + c * kSvG + k] = (hz ? pool[c].h : pool[c].q)[src];
                     for (int t = 0; t < T; ++t) {

@@ -33,6 +33,7 @@ class SvftData(C.Structure):
         ("XXs", c_double_pp), ("ZZs", c_double_pp), ("Us", c_double_pp),
         ("n_horizons", c_int32_p), ("W1s_h", c_double_p), ("W2s_h", c_double_p), ("Pw_h", c_double_p),
         ("XXs_h", c_double_pp), ("ZZs_h", c_double_pp), ("Us_h", c_double_pp),
+        ("knots", c_double_p), ("n_knots", C.c_int32), ("ord", C.c_int32), ("st", c_double_p), ("st_h", c_double_p),
     ]
 
 
@@ -59,7 +60,8 @@ def marshal_data(sv: dict, subject_offset: int = 0):
     d.n, d.K, d.L, d.q = int(sv["n"]), int(sv["K"]), int(sv["L"]), int(sv["q"])
     d.n_outcomes, d.n_terms = len(sv["y_long"]), len(sv["XXs"])
     d.n_alphas = int(sum(len(c) for c in sv["col_inds"]))
-    d.n_Bs = int(np.asarray(sv["W1s"]).shape[1])
+    from_knots = sv.get("W1s") is None            # bases evaluated by the library from (knots, times)
+    d.n_Bs = int(len(sv["knots"]) - sv.get("ord", 4)) if from_knots else int(np.asarray(sv["W1s"]).shape[1])
     W2s = np.asarray(sv["W2s"])
     d.n_gammas = int(W2s.shape[1]) if W2s.ndim == 2 else 0
     d.subject_offset = int(subject_offset)
@@ -79,10 +81,17 @@ def marshal_data(sv: dict, subject_offset: int = 0):
     d.outcome = k.i32(sv["outcome"])
     d.f_t = k.i32([len(f) for f in sv["indFixed"]])
     d.indFixed = k.i32_list(sv["indFixed"])
-    d.W1s, d.W2s, d.Pw = k.f64(sv["W1s"]), k.f64(sv["W2s"]), k.f64(sv["Pw"])
+    d.W2s, d.Pw = k.f64(sv["W2s"]), k.f64(sv["Pw"])
+    if from_knots:
+        d.knots, d.n_knots, d.ord = k.f64(sv["knots"]), int(len(sv["knots"])), int(sv.get("ord", 4))
+        d.st, d.st_h = k.f64(sv["st"]), k.f64(sv["st_h"])
+    else:
+        d.W1s = k.f64(sv["W1s"])
     d.XXs, d.ZZs, d.Us = k.f64_list(sv["XXs"]), k.f64_list(sv["ZZs"]), k.f64_list(sv["Us"])
     d.n_horizons = k.i32(sv["n_horizons"])
-    d.W1s_h, d.W2s_h, d.Pw_h = k.f64(sv["W1s_h"]), k.f64(sv["W2s_h"]), k.f64(sv["Pw_h"])
+    d.W2s_h, d.Pw_h = k.f64(sv["W2s_h"]), k.f64(sv["Pw_h"])
+    if not from_knots:
+        d.W1s_h = k.f64(sv["W1s_h"])
     d.XXs_h, d.ZZs_h, d.Us_h = k.f64_list(sv["XXs_h"]), k.f64_list(sv["ZZs_h"]), k.f64_list(sv["Us_h"])
     return d, k
 
@@ -246,7 +255,7 @@ def survfitJM(sv: dict, post_means: dict, draws: dict, control: dict | None = No
 # synthetic new subjects (config 5): designs as R/survfitJM.mvJMbayes.R:85-116,149-276 builds them
 # ------------------------------------------------------------------------------------------------
 def newdata_designs(cohort: dict, L: int = 10, horizon_step: float = 0.5, last_frac: float = 0.5,
-                    subjects: np.ndarray | None = None) -> dict:
+                    subjects: np.ndarray | None = None, dense_basis: bool = True) -> dict:
     """All (or ``subjects``) of a cohort as ``newdata`` truncated at ``last.time = last_frac * Time``, with
     ``L`` prediction times ``last.time + (1..L) * horizon_step`` each."""
     D, truth, K = cohort["Data"], cohort["truth"], cohort["K"]
@@ -309,9 +318,10 @@ def newdata_designs(cohort: dict, L: int = 10, horizon_step: float = 0.5, last_f
         fams=D["fams"], links=D["links"], RE_inds=D["RE_inds"], RE_inds2=RE_inds2, col_inds=D["col_inds"],
         trans_Funs=D["trans_Funs"], outcome=outcome, indFixed=indFixed,
         y_long=y_long, X_long=X_long, Z_long=Z_long, idL=[idL.copy() for _ in range(O)],
-        W1s=spline_design(knots, st), W2s=_F(np.repeat(W2, K, axis=0)), Pw=Pw, XXs=XXs, ZZs=ZZs, Us=Us,
+        W1s=spline_design(knots, st) if dense_basis else None, W2s=_F(np.repeat(W2, K, axis=0)), Pw=Pw, XXs=XXs, ZZs=ZZs, Us=Us,
         n_horizons=np.full(n, L, dtype=np.int32),
-        W1s_h=spline_design(knots, st_h), W2s_h=_F(np.repeat(W2, K * L, axis=0)), Pw_h=Pw_h,
+        W1s_h=spline_design(knots, st_h) if dense_basis else None, W2s_h=_F(np.repeat(W2, K * L, axis=0)), Pw_h=Pw_h,
+        knots=np.asarray(knots, dtype=np.float64), ord=4, st=st, st_h=st_h,
         XXs_h=XXs_h, ZZs_h=ZZs_h, Us_h=Us_h,
         last_time=last_time, times_to_pred=upper, subjects=sel)
 

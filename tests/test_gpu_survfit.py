@@ -124,3 +124,24 @@ def test_bad_hessian_and_sharded_keys(cuda_lib, osv):
     with sv.SurvFit(d2, subject_offset=25) as h2:
         part = h2.sample(draws, o["modes"][sel], o["hessians"][:, :, sel])
     assert np.array_equal(part["full_results"], whole["full_results"][:, :, sel])
+
+
+def test_basis_from_knots_equals_dense_basis(cuda_lib, osv):
+    """with W1s / W1s_h = NULL the library evaluates splineDesign(knots, x, ord = 4, outer.ok = TRUE)
+    itself (band form, de Boor) from the quadrature times; results must equal the dense-basis path, including the
+    all-zero rows left of the first boundary knot."""
+    c = make_cohort("config3", n=80)
+    dense = sv.newdata_designs(c, L=4)
+    lean = sv.newdata_designs(c, L=4, dense_basis=False)
+    assert lean["W1s"] is None and lean["W1s_h"] is None
+    assert np.any(np.asarray(dense["W1s"]).sum(axis=1) == 0.0)        # the edge case is present
+    means, draws = sv.posterior_draws(c, M=20)
+    with sv.SurvFit(dense) as h:
+        a = h.survfitJM(means, draws)
+    with sv.SurvFit(lean) as h:
+        b = h.survfitJM(means, draws)
+    assert np.allclose(a["modes"], b["modes"], rtol=0, atol=1e-12)
+    assert np.allclose(a["summaries"], b["summaries"], rtol=1e-12, atol=0)
+    bad = dict(lean); bad["knots"] = lean["knots"][::-1].copy()
+    with pytest.raises(cuda_lib.JmbError):
+        sv.SurvFit(bad)
