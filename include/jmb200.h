@@ -242,6 +242,26 @@ int jmb_gradient_logPosterior(jmb_handle h, double temp, const double* Bs_gammas
                               const double* gammas, const double* alphas, const jmb_priors* priors,
                               double tauBs, double A_tauBs, double B_tauBs, double* out);
 
+/* marglogLik2(thetas, Data, priors, temp, fixed_tau_Bs_gammas) (R/margLogLik2.R:1-140; called at
+ * R/mvJointModelBayes.R:716-725 for the initial values / proposal covariances and, with update_RE = FALSE, once per draw
+ * at :792): optim(BFGS, hessian = TRUE) on -logPosterior with the analytic score, the Laplace value, and - with
+ * fixed_tau_Bs_gammas - cd.vec + solve + nearPD for attr(, "Covs").  The BFGS driver runs natively on the host; every
+ * function value / gradient is a pass over the designs on the device (jmb_set_wlong first).  d = n_Bs + n_gammas + n_alphas
+ * (+ 1 when tau_Bs_gammas is free; then `tau_Bs_gammas` is on the log scale, :39-40).  SURVEY.md section 8(f)2. */
+typedef struct jmb_mll_out {
+    double value;            /* the Laplace approximation marglogLik2 returns (:110-111) */
+    double opt_value;        /* opt$value */
+    int32_t convergence;     /* opt$convergence */
+    int32_t counts[2];       /* opt$counts */
+    double* par;             /* [d]   opt$par (attr(, "inits") = its Bs_gammas | gammas | alphas blocks) */
+    double* hessian;         /* d x d opt$hessian */
+    double* Cov_Bs_gammas; double* Cov_gammas; double* Cov_alphas;   /* attr(, "Covs") (fixed_tau_Bs_gammas only) */
+} jmb_mll_out;
+int jmb_marglogLik2(jmb_handle h, const double* Bs_gammas, const double* gammas, const double* alphas,
+                    double tau_Bs_gammas, const jmb_priors* priors, double temp, int fixed_tau_Bs_gammas,
+                    jmb_mll_out* out);
+int jmb_param_dims(jmb_handle h, int32_t* n_Bs, int32_t* n_gammas, int32_t* n_alphas);
+
 /* lap_rwm_C_woRE / lap_rwm_C_woRE_nogammas (src/fast_LAPRWM.cpp:934-1139,1142-1297; control$update_RE =
  * FALSE): the survival block alone on the association designs of jmb_set_wlong.  `in->b`, `in->sigma_b`
  * and the b-related outputs are not used; logPost [n_out] receives the list element `logPost`. */

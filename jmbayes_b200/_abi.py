@@ -97,6 +97,11 @@ class JmbChainOut(C.Structure):
     _fields_ = [(f, c_double_p) for f in _OUT_FIELDS]
 
 
+class JmbMllOut(C.Structure):
+    _fields_ = [("value", C.c_double), ("opt_value", C.c_double), ("convergence", C.c_int32), ("counts", C.c_int32 * 2)] + \
+               [(f, c_double_p) for f in ("par", "hessian", "Cov_Bs_gammas", "Cov_gammas", "Cov_alphas")]
+
+
 class JmbEvalOut(C.Structure):
     _fields_ = [(f, c_double_p) for f in ("log_pyb", "log_pb", "log_h", "H", "HL", "log_ptb")]
 

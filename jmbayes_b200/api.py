@@ -69,6 +69,8 @@ def lib():
     L.jmb_lap_rwm_woRE.argtypes = [vp, C.POINTER(_abi.JmbPriors), C.POINTER(_abi.JmbControl), C.POINTER(_abi.JmbChainIn),
                                    C.POINTER(_abi.JmbChainOut), _abi.c_double_p]
     L.jmb_gradient_logPosterior.argtypes = post
+    L.jmb_marglogLik2.argtypes = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p, C.c_double, C.POINTER(_abi.JmbPriors),
+                                  C.c_double, C.c_int, C.POINTER(_abi.JmbMllOut)]
     L.jmb_layout_info.argtypes = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p, _abi.c_int32_p]
     L.jmb_launch_count.argtypes = [vp, _abi.c_int64_p]
     L.jmb_comm_unique_id.argtypes = [C.c_char_p]
@@ -270,6 +272,30 @@ class Fit:
         _check(lib().jmb_gradient_logPosterior(self._h, float(temp), _dptr(Bs), _dptr(g), _dptr(al), C.byref(pr),
                                                float(tauBs), float(A_tauBs), float(B_tauBs), _dptr(out)))
         return out
+
+    def marglogLik2(self, thetas: dict, priors: dict, temp: float = 1.0, fixed_tau_Bs_gammas: bool = False):
+        """marglogLik2(thetas, Data, priors, temp, fixed_tau_Bs_gammas) (R/margLogLik2.R) on the designs of this fit and
+        the association designs of :meth:`set_wlong`: the BFGS driver runs natively in the library, every evaluation on
+        the device.  Returns the value plus ``par``, ``hessian`` and - when tau is fixed - ``Covs`` / ``inits`` (the
+        attributes of the reference's result).  ``thetas['tau_Bs_gammas']`` is on the log scale when it is not fixed."""
+        Bs, g, al, pr, keep = self._post_args(thetas["Bs_gammas"], thetas.get("gammas", np.zeros(0)), thetas["alphas"], priors)
+        P = self.B + self.p + self.A
+        d = P if fixed_tau_Bs_gammas else P + 1
+        tau = float(np.asarray(thetas["tau_Bs_gammas"]).ravel()[0])
+        bufs = dict(par=np.zeros(d), hessian=np.zeros((d, d), order="F"), Cov_Bs_gammas=np.zeros((self.B, self.B), order="F"),
+                    Cov_gammas=np.zeros((max(self.p, 1), max(self.p, 1)), order="F"), Cov_alphas=np.zeros((self.A, self.A), order="F"))
+        out = _abi.JmbMllOut()
+        for name, a in bufs.items():
+            setattr(out, name, _dptr(a))
+        _check(lib().jmb_marglogLik2(self._h, _dptr(Bs), _dptr(g), _dptr(al), tau, C.byref(pr), float(temp),
+                                     int(bool(fixed_tau_Bs_gammas)), C.byref(out)))
+        res = dict(value=out.value, opt_value=out.opt_value, convergence=out.convergence, counts=(out.counts[0], out.counts[1]),
+                   par=bufs["par"], hessian=bufs["hessian"])
+        if fixed_tau_Bs_gammas:
+            res["Covs"] = dict(Bs_gammas=bufs["Cov_Bs_gammas"], gammas=bufs["Cov_gammas"][:self.p, :self.p], alphas=bufs["Cov_alphas"])
+            res["inits"] = dict(Bs_gammas=bufs["par"][:self.B], gammas=bufs["par"][self.B:self.B + self.p],
+                                alphas=bufs["par"][self.B + self.p:P], tau_Bs_gammas=tau)
+        return res
 
     def lap_rwm_C_woRE(self, initials, priors, scales, Covs, control, chain_id: int = 0):
         """lap_rwm_C_woRE[_nogammas] (src/fast_LAPRWM.cpp:934-1297) on the designs of ``set_wlong``."""

@@ -1315,6 +1315,14 @@ extern "C" int jmb_layout_info(jmb_handle h, double* shared_bytes, double* chain
     return 0;
 }
 
+extern "C" int jmb_param_dims(jmb_handle h, int32_t* n_Bs, int32_t* n_gammas, int32_t* n_alphas) {
+    if (!h) return fail("jmb_param_dims: null handle");
+    if (n_Bs) *n_Bs = h->mm.B;
+    if (n_gammas) *n_gammas = h->mm.d.p;
+    if (n_alphas) *n_alphas = h->mm.d.A;
+    return 0;
+}
+
 extern "C" int jmb_launch_count(jmb_handle h, int64_t* launches) {
     if (!h) return fail("jmb_launch_count: null handle");
     *launches = h->launches;

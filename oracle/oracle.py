@@ -32,7 +32,7 @@ def _cpu_stamp() -> str:
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(HERE, f) for f in ("jmb_oracle.c", "jmb_oracle.h", "jmb_oracle_svft.c", "jmb_oracle_svft.h")]
+    src = [os.path.join(HERE, f) for f in ("jmb_oracle.c", "jmb_oracle.h", "jmb_oracle_svft.c", "jmb_oracle_svft.h", "jmb_oracle_mll.c", "jmb_oracle_mll.h")]
     stamp_file = os.path.join(HERE, "_build", "cpu.stamp")
     stamp = _cpu_stamp()
     old = open(stamp_file).read() if os.path.exists(stamp_file) else ""
@@ -186,3 +186,61 @@ def lap_rwm_C_woRE(initials, Data, priors, scales, Covs, control, Covs_b, chain_
                                        alphas=float(bufs["sigma_surv"][2])),
                             Sigma=dict(Bs_gammas=bufs["Sigma_Bs_gammas"], gammas=bufs["Sigma_gammas"], alphas=bufs["Sigma_alphas"])),
                 extras=dict(trace_surv=bufs.get("trace_surv")))
+
+
+# ---- marglogLik2 (R/margLogLik2.R) ------------------------------------------------------------------------------------
+class _MllData(C.Structure):
+    _fields_ = [("n", C.c_int32), ("ns", C.c_int64), ("B", C.c_int32), ("p", C.c_int32), ("A", C.c_int32)] + \
+               [(f, _abi.c_double_p) for f in ("event", "W1", "W1s", "W2", "W2s", "Wlong", "Wlongs", "Pw")]
+
+
+class _MllOut(C.Structure):
+    _fields_ = [("value", C.c_double), ("opt_value", C.c_double), ("convergence", C.c_int32), ("counts", C.c_int32 * 2)] + \
+               [(f, _abi.c_double_p) for f in ("par", "hessian", "Cov_Bs_gammas", "Cov_gammas", "Cov_alphas")]
+
+
+def marglogLik2(thetas, Data, priors, temp=1.0, fixed_tau_Bs_gammas=False):
+    """marglogLik2(thetas, Data, priors, temp, fixed_tau_Bs_gammas) restated (oracle/jmb_oracle_mll.c).  ``thetas``:
+    dict(Bs_gammas, gammas, alphas, tau_Bs_gammas); tau is on the log scale when it is not fixed (:39-40)."""
+    k = _abi.Keep()
+    W1, W2 = np.asarray(Data["W1"]), np.asarray(Data["W2"])
+    d = _MllData()
+    d.n, d.ns = int(W1.shape[0]), int(np.asarray(Data["Pw"]).shape[0])
+    d.B, d.p, d.A = int(W1.shape[1]), int(W2.shape[1]) if W2.ndim == 2 else 0, int(np.asarray(Data["Wlong"]).shape[1])
+    for f in ("event", "W1", "W1s", "W2", "W2s", "Wlong", "Wlongs", "Pw"):
+        setattr(d, f, k.f64(Data[f]))
+    pr, kp = _abi.marshal_priors(priors)
+    P = d.B + d.p + d.A
+    dim = P if fixed_tau_Bs_gammas else P + 1
+    th = np.concatenate([np.asarray(thetas["Bs_gammas"], dtype=np.float64).ravel(), np.asarray(thetas.get("gammas", []), dtype=np.float64).ravel(),
+                         np.asarray(thetas["alphas"], dtype=np.float64).ravel()])
+    tau = float(np.asarray(thetas["tau_Bs_gammas"]).ravel()[0])
+    if not fixed_tau_Bs_gammas:
+        th = np.concatenate([th, [tau]])
+    bufs = dict(par=np.zeros(dim), hessian=np.zeros((dim, dim), order="F"), Cov_Bs_gammas=np.zeros((d.B, d.B), order="F"),
+                Cov_gammas=np.zeros((max(d.p, 1), max(d.p, 1)), order="F"), Cov_alphas=np.zeros((d.A, d.A), order="F"))
+    out = _MllOut()
+    for name, a in bufs.items():
+        setattr(out, name, _p(a))
+    L = lib()
+    L.orc_marglogLik2.argtypes = [C.POINTER(_MllData), C.POINTER(_abi.JmbPriors), _abi.c_double_p, C.c_double, C.c_double, C.c_int,
+                                  C.POINTER(_MllOut)]
+    rc = L.orc_marglogLik2(C.byref(d), C.byref(pr), _p(np.ascontiguousarray(th)), tau, float(temp), int(bool(fixed_tau_Bs_gammas)), C.byref(out))
+    if rc:
+        raise RuntimeError(f"orc_marglogLik2 failed with code {rc}")
+    res = dict(value=out.value, opt_value=out.opt_value, convergence=out.convergence, counts=(out.counts[0], out.counts[1]),
+               par=bufs["par"], hessian=bufs["hessian"])
+    if fixed_tau_Bs_gammas:
+        res["Covs"] = dict(Bs_gammas=bufs["Cov_Bs_gammas"], gammas=bufs["Cov_gammas"][:d.p, :d.p], alphas=bufs["Cov_alphas"])
+        res["inits"] = dict(Bs_gammas=bufs["par"][:d.B], gammas=bufs["par"][d.B:d.B + d.p], alphas=bufs["par"][d.B + d.p:P],
+                            tau_Bs_gammas=tau)
+    return res
+
+
+def nearPD(M):
+    M = np.asfortranarray(M, dtype=np.float64)
+    out = np.zeros_like(M, order="F")
+    L = lib()
+    L.orc_nearPD.argtypes = [_abi.c_double_p, C.c_int, _abi.c_double_p]
+    L.orc_nearPD(_p(M), M.shape[0], _p(out))
+    return out

@@ -218,12 +218,13 @@ def test_struct_layouts_match_the_header():
     """sizeof of the ctypes mirrors against the C compiler's view of include/jmb200.h."""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "jmb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(jmb_data), sizeof(jmb_draw), sizeof(jmb_priors), sizeof(jmb_control), sizeof(jmb_chain_in), sizeof(jmb_chain_out), sizeof(jmb_eval_out));return 0;}'
+    src = '#include <stdio.h>\n#include "jmb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(jmb_data), sizeof(jmb_draw), sizeof(jmb_priors), sizeof(jmb_control), sizeof(jmb_chain_in), sizeof(jmb_chain_out), sizeof(jmb_eval_out), sizeof(jmb_xdesigns), sizeof(jmb_mll_out));return 0;}'
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "s.c"), "w").write(src)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "s"), os.path.join(td, "s.c")], check=True)
         out = subprocess.run([os.path.join(td, "s")], capture_output=True, text=True, check=True).stdout.split()
-    got = [C.sizeof(x) for x in (_abi.JmbData, _abi.JmbDraw, _abi.JmbPriors, _abi.JmbControl, _abi.JmbChainIn, _abi.JmbChainOut, _abi.JmbEvalOut)]
+    got = [C.sizeof(x) for x in (_abi.JmbData, _abi.JmbDraw, _abi.JmbPriors, _abi.JmbControl, _abi.JmbChainIn, _abi.JmbChainOut, _abi.JmbEvalOut,
+                                 _abi.JmbXDesigns, _abi.JmbMllOut)]
     assert got == [int(x) for x in out]
 
 

@@ -92,6 +92,18 @@ def test_pbc2_on_cuda_matches_cpu(cuda_lib, oracle, pbc2_cpu):
         assert np.allclose(dev["inits"]["alphas"], pb["inits"]["alphas"], rtol=1e-5)
         assert np.allclose(dev["inits"]["Bs_gammas"], pb["inits"]["Bs_gammas"], rtol=1e-4, atol=1e-5)
         assert abs(dev["laplace_value"] - pb["laplace_value"]) < 1e-6 * abs(pb["laplace_value"])
+        # the native driver (jmb_marglogLik2: R's vmmin / optimhess / cd.vec / nearPD restated) against its CPU restatement,
+        # and against the SciPy-driven stand-in above (same optimum)
+        B = pb["B"]
+        th0 = dict(Bs_gammas=np.zeros(B), gammas=np.zeros(2), alphas=np.zeros(1), tau_Bs_gammas=200.0)
+        nat = fit.marglogLik2(th0, pr, fixed_tau_Bs_gammas=True)
+        Dm = dict(D); Dm["Wlong"] = pb["Wlong"]; Dm["Wlongs"] = pb["Wlongs"]
+        orc = oracle.marglogLik2(th0, Dm, pr, fixed_tau_Bs_gammas=True)
+        assert nat["convergence"] == orc["convergence"] == 0
+        assert np.allclose(nat["par"], orc["par"], rtol=0, atol=1e-6)
+        assert np.allclose(nat["Covs"]["alphas"], orc["Covs"]["alphas"], rtol=1e-4)
+        assert np.allclose(nat["inits"]["alphas"], pb["inits"]["alphas"], rtol=2e-3)
+        assert abs(nat["opt_value"] - pb["laplace_value"]) < 1e-5 * abs(pb["laplace_value"])
         # the chain, from the CPU-side inits so that both sides start from identical numbers
         ctl = dict(pb["control"]); ctl.update(n_burnin=100, n_iter=100, n_block=50, n_thin=20)
         fit.set_draw(D)
