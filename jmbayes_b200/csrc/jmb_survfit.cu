@@ -74,7 +74,9 @@ struct jmb_svft_handle_s {
     std::vector<long long> off;                     // host record offsets
     double* d_rec = nullptr; long long* d_off = nullptr;
     double *d_modes = nullptr, *d_hess = nullptr, *d_S = nullptr, *d_acc = nullptr, *d_blast = nullptr, *d_sum = nullptr;
-    double *d_par_mean = nullptr, *d_par_draws = nullptr;
+    double *d_par_mean = nullptr, *d_par_draws = nullptr, *d_cbuf = nullptr;
+    size_t cap_cbuf = 0;
+    bool split_horizons = false;                    // linear model with a precompiled shape: jmb_svft_horizons does the intervals
     int *d_conv = nullptr, *d_counts = nullptr, *d_work = nullptr;
     size_t cap_S = 0, cap_draws = 0;
     cudaStream_t stream = nullptr;
@@ -90,7 +92,7 @@ extern "C" int jmb_svft_destroy(jmb_svft_handle h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_rec); cudaFree(h->d_off); cudaFree(h->d_modes); cudaFree(h->d_hess); cudaFree(h->d_S);
-    cudaFree(h->d_acc); cudaFree(h->d_blast); cudaFree(h->d_sum); cudaFree(h->d_par_mean); cudaFree(h->d_par_draws);
+    cudaFree(h->d_acc); cudaFree(h->d_blast); cudaFree(h->d_sum); cudaFree(h->d_par_mean); cudaFree(h->d_par_draws); cudaFree(h->d_cbuf);
     cudaFree(h->d_conv); cudaFree(h->d_counts); cudaFree(h->d_work);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -371,6 +373,8 @@ extern "C" int jmb_svft_create(const jmb_svft_data* d, int device, jmb_svft_hand
     else if (sv_same_desc(md, SvSpecValue::d)) h->kernel = 2;
     const char* env = getenv("JMB_SVFT_KERNEL");
     if (env && !strcmp(env, "generic")) h->kernel = 0;
+    h->split_horizons = (h->kernel == 1 && sv_is_linear<SvSpecThree>()) || (h->kernel == 2 && sv_is_linear<SvSpecValue>());
+    if (env && !strcmp(env, "fused")) h->split_horizons = false;        // A/B: intervals inside the sampling kernel
     const int groups = JMB_SVFT_THREADS / kSvG;
     const int gd = (sv_group_doubles(q, h->ps_len) + 1) / 2 * 2;
     h->smem = (int)sizeof(double) * groups * gd;
@@ -445,6 +449,14 @@ static int run(jmb_svft_handle h, const jmb_svft_params* pm, const jmb_svft_para
             h->cap_draws = pdk.size();
         }
         CU(cudaMemcpyAsync(h->d_par_draws, pdk.data(), sizeof(double) * pdk.size(), cudaMemcpyHostToDevice, h->stream));
+        if (h->split_horizons && L > 0) {
+            const size_t needC = (size_t)n * M * (md.NC + 1);
+            if (needC > h->cap_cbuf) {
+                cudaFree(h->d_cbuf); h->d_cbuf = nullptr;
+                CU(cudaMalloc(&h->d_cbuf, sizeof(double) * needC));
+                h->cap_cbuf = needC;
+            }
+        }
         const size_t needS = (size_t)n * M * std::max(L, 1);
         if (needS > h->cap_S) {
             cudaFree(h->d_S); h->d_S = nullptr;
@@ -471,6 +483,7 @@ static int run(jmb_svft_handle h, const jmb_svft_params* pm, const jmb_svft_para
     a.c.scale = ct->scale; a.c.df = ct->df; a.c.ci_lo = ct->CI_levels[0]; a.c.ci_hi = ct->CI_levels[1];
     a.c.parscale = ct->parscale; a.c.reltol = ct->reltol; a.c.ndeps = ct->ndeps; a.c.cd_eps = ct->cd_eps;
     a.c.log = ct->log; a.c.maxit = ct->maxit; a.c.seed = ct->seed;
+    a.Cbuf = (do_sample && h->split_horizons && L > 0) ? h->d_cbuf : nullptr; a.ncoef = md.NC + 1;
     a.modes = h->d_modes; a.hess = h->d_hess; a.conv = h->d_conv; a.counts = h->d_counts; a.S = h->d_S;
     a.acc_rate = h->d_acc; a.b_last = h->d_blast; a.work = h->d_work;
 
@@ -486,6 +499,20 @@ static int run(jmb_svft_handle h, const jmb_svft_params* pm, const jmb_svft_para
         if (h->kernel == 1) jmb_svft_sample_static<SvSpecThree><<<h->grid[1], JMB_SVFT_THREADS, h->smem, h->stream>>>(a);
         else if (h->kernel == 2) jmb_svft_sample_static<SvSpecValue><<<h->grid[1], JMB_SVFT_THREADS, h->smem, h->stream>>>(a);
         else jmb_svft_sample_generic<<<h->grid[1], JMB_SVFT_THREADS, h->smem, h->stream>>>(h->mm, a);
+        h->launches += 1;
+        CU(cudaGetLastError());
+    }
+    if (a.Cbuf) {                                   // horizon integrals: one thread per draw
+        const int MC = 256;
+        const size_t smem = sizeof(double) * ((size_t)MC * h->B + (size_t)md.K * (2 + md.WB + md.NC));
+        const int grid = std::max(1, std::min(n, h->num_sms * 4));
+        if (h->kernel == 1) {
+            CU(cudaFuncSetAttribute((const void*)jmb_svft_horizons<SvSpecThree>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            jmb_svft_horizons<SvSpecThree><<<grid, MC, smem, h->stream>>>(a);
+        } else {
+            CU(cudaFuncSetAttribute((const void*)jmb_svft_horizons<SvSpecValue>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            jmb_svft_horizons<SvSpecValue><<<grid, MC, smem, h->stream>>>(a);
+        }
         h->launches += 1;
         CU(cudaGetLastError());
     }

@@ -150,12 +150,13 @@ struct SvConst {            // jmb_svft_control + sizes
 struct SvArgs {
     const double* rec; const long long* off;       // subject records and their offsets [n + 1]
     const double* par_mean; const double* par_draws; // [ps_len], [M][ps_len]
-    int n, M, L, B, ps_len;
+    int n, M, L, B, ps_len, ncoef;
     long long subject_offset;
     int do_modes, do_sample;
     SvConst c;
     double* modes; double* hess; int* conv; int* counts;   // [n][q], [n][q*q], [n], [n][2]
     double* S;                                     // [n][M][L]
+    double* Cbuf;                                  // [n][M][NC + 1] linear-predictor coefficients of b.new per draw, or NULL
     double* acc_rate; double* b_last;              // [n], [n][q]
     int* work;                                     // atomic subject counter
 };
@@ -483,6 +484,76 @@ __device__ __forceinline__ void sv_eval_static_n(const double* __restrict__ rec,
     });
 }
 
+// Models whose association terms are all untransformed with the default interaction design (tf = identity, Us = 1):
+// sum_t alpha_t (XXs_t beta + ZZs_t b) is then linear in the pooled design columns, sum_c col_c * C_c + C_0, with
+// coefficients that depend only on (draw, b).  The horizon integrals of one draw (same b, same parameters, nh blocks)
+// compute C once and pay NC + 1 multiply-adds per quadrature row instead of ~40; the value differs from the term-by-term
+// sum only by fp64 rounding (<= 1e-15 relative; the parity gate is 1e-9).
+template <class Spec>
+constexpr bool sv_is_linear() {
+    for (int t = 0; t < Spec::d.T; ++t)
+        if (Spec::d.tf[t] != JMB_TF_IDENTITY || Spec::d.u_ones[t] == 0 || Spec::d.ut[t] != 1) return false;
+    return Spec::d.w2_const != 0;
+}
+
+template <class Spec>
+struct SvLinCoef { double c0; double cc[Spec::d.NC > 0 ? Spec::d.NC : 1]; };
+
+// C_0 (incl. W2 gamma, constant within the subject) and C_c for the point sb under the parameter set sp
+template <class Spec>
+__device__ __forceinline__ void sv_lin_coefs(const double* __restrict__ rec, const double* sb, const double* sp, SvLinCoef<Spec>& L) {
+    constexpr int T = Spec::d.T, p = Spec::d.p, NC = Spec::d.NC, q = Spec::d.q;
+    constexpr int psB = Spec::L.ps_betas, psG = Spec::L.ps_gam, psA = Spec::L.ps_alp, oW2c = Spec::L.o_W2c;
+    double b[q];
+    sfor<q>([&](auto j) { b[j] = sb[j]; });
+    double c0 = 0.0;
+    sfor<p>([&](auto j) { c0 += rec[oW2c + j] * sp[psG + j]; });
+    sfor<NC>([&](auto c) { L.cc[c] = 0.0; });
+    sfor<T>([&](auto tc) {
+        constexpr int t = tc;
+        constexpr int bo = Spec::d.boff[Spec::d.outc[t]], cidx = Spec::d.col[t][0];
+        const double al = sp[psA + cidx];
+        double k0 = 0.0;
+        double kc[NC > 0 ? NC : 1];
+        sfor<NC>([&](auto c) { kc[c] = 0.0; });
+        sfor<Spec::d.ft[t]>([&](auto fc) {
+            constexpr int f = fc;
+            constexpr int idx = Spec::d.indf[t][f], c = Spec::d.xx_col[t][f];
+            if constexpr (c < 0) k0 += sp[psB + bo + idx]; else kc[c] += sp[psB + bo + idx];
+        });
+        sfor<Spec::d.rt[t]>([&](auto jc) {
+            constexpr int j = jc;
+            constexpr int idx = Spec::d.re2[t][j], c = Spec::d.zz_col[t][j];
+            if constexpr (c < 0) k0 += b[idx]; else kc[c] += b[idx];
+        });
+        c0 += al * k0;
+        sfor<NC>([&](auto c) { L.cc[c] += al * kc[c]; });
+    });
+    L.c0 = c0;
+}
+
+// -H of two blocks at the point / parameters behind the coefficients L
+template <class Spec>
+__device__ __forceinline__ void sv_block2_lin(const double* __restrict__ rec, const int blkA, const int blkB, const double* sp,
+                                              const SvLinCoef<Spec>& L, const int lane, const unsigned gmask, double& vA, double& vB) {
+    constexpr int K = Spec::d.K, WB = Spec::d.WB, NC = Spec::d.NC;
+    constexpr int oBlk0 = Spec::L.o_blk0, BLK = Spec::L.blk, psBs = Spec::L.ps_Bs;
+    constexpr int bW1off = Spec::L.b_W1off, bW1v = Spec::L.b_W1v, bPw = Spec::L.b_Pw, bCol = Spec::L.b_col;
+    double e[2];
+    sfor<2>([&](auto sc) {
+        constexpr int sl = sc;
+        const double* __restrict__ blk = rec + oBlk0 + (long long)(sl == 0 ? blkA : blkB) * BLK;
+        const int off = reinterpret_cast<const int*>(blk + bW1off)[lane];
+        double s1 = 0.0;
+        sfor<WB>([&](auto j) { s1 += blk[bW1v + j * kSvG + lane] * sp[psBs + off + j]; });
+        double a = L.c0;
+        sfor<NC>([&](auto c) { a += blk[bCol + c * kSvG + lane] * L.cc[c]; });
+        e[sl] = (lane < K) ? blk[bPw + lane] * exp(s1 + a) : 0.0;
+    });
+    vA = 0.0 - group_sum<kSvG>(e[0], gmask);
+    vB = 0.0 - group_sum<kSvG>(e[1], gmask);
+}
+
 template <class Spec, bool CACHED>
 __device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec, const int blk_index, const bool full,
                                                  const double* sb, const double* sp, const int lane, const unsigned gmask,
@@ -585,6 +656,13 @@ struct SvEvalGeneric {
         vA = sv_eval_generic(d, L, rec, blkA, false, sb, sp, lane, gmask);
         vB = sv_eval_generic(d, L, rec, blkB, false, sb, sp, lane, gmask);
     }
+    // horizon integrals of one draw: nothing to hoist in the generic flavour
+    __device__ __forceinline__ void begin_horizons(const double*, const double*, const double*) {}
+    __device__ __forceinline__ void store_coefs(double*) const {}
+    __device__ __forceinline__ void block2h(const double* rec, int blkA, int blkB, const double* sb, const double* sp, int lane,
+                                            unsigned gmask, double& vA, double& vB) const {
+        block2(rec, blkA, blkB, sb, sp, lane, gmask, vA, vB);
+    }
 };
 template <class Spec>
 struct SvEvalStatic {
@@ -612,6 +690,19 @@ struct SvEvalStatic {
         double out[2];
         sv_eval_static_n<Spec, false, 2, 1>(rec, bi, false, pts, sp, lane, gmask, hc, out);
         vA = out[0]; vB = out[1];
+    }
+    // horizon integrals of one draw at one point: hoist the (draw, b) part of the linear predictor when the model allows
+    SvLinCoef<Spec> lc;
+    __device__ __forceinline__ void begin_horizons(const double* rec, const double* sb, const double* sp) {
+        if constexpr (sv_is_linear<Spec>()) sv_lin_coefs<Spec>(rec, sb, sp, lc);
+    }
+    __device__ __forceinline__ void store_coefs(double* dst) const {      // [NC + 1]: c0, cc[0..NC-1]
+        if constexpr (sv_is_linear<Spec>()) { dst[0] = lc.c0; sfor<Spec::d.NC>([&](auto c) { dst[1 + c] = lc.cc[c]; }); }
+    }
+    __device__ __forceinline__ void block2h(const double* rec, int blkA, int blkB, const double* sb, const double* sp, int lane,
+                                            unsigned gmask, double& vA, double& vB) const {
+        if constexpr (sv_is_linear<Spec>()) sv_block2_lin<Spec>(rec, blkA, blkB, sp, lc, lane, gmask, vA, vB);
+        else block2(rec, blkA, blkB, sb, sp, lane, gmask, vA, vB);
     }
 };
 
@@ -895,7 +986,7 @@ __device__ __noinline__ int sv_sample_setup(const SvArgs& a, const int n, SvG& G
 
 // the M Metropolis-Hastings steps and the horizon integrals of all subjects (R/survfitJM.mvJMbayes.R:330-398)
 template <class Eval>
-__device__ __forceinline__ void sv_sample_run(const int q, const int O, const SvArgs& a, const Eval& eval) {
+__device__ __forceinline__ void sv_sample_run(const int q, const int O, const SvArgs& a, Eval& eval) {
     extern __shared__ double sv_smem[];
     const int tid = threadIdx.x, lane = tid & (kSvG - 1), grp = tid / kSvG;
     const unsigned gmask = 0xFFFFu << (16 * ((tid & 31) >> 4));
@@ -1011,11 +1102,17 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
             __syncwarp();
             double cum = 0.0, mine = 0.0;            // survival on each prediction interval (:378-395)
             double* Srow = a.S + ((size_t)(have ? s : 0) * a.M + m) * a.L;
-            for (int l = 0; l < nh_max; l += 2) {    // two intervals per pass
+            if (live) eval.begin_horizons(rec, sb_new, sp);
+            const bool split = a.Cbuf != nullptr;    // the horizon integrals run in jmb_svft_horizons from the coefficients
+            if (split && have && lane == 0) {
+                double* cdst = a.Cbuf + ((size_t)s * a.M + m) * a.ncoef;
+                if (live) eval.store_coefs(cdst); else for (int j = 0; j < a.ncoef; ++j) cdst[j] = nan;
+            }
+            for (int l = 0; l < (split ? 0 : nh_max); l += 2) {    // two intervals per pass
                 if (live && l < nh) {
                     const bool two = l + 1 < nh;
                     double v0, v1;
-                    eval.block2(rec, l + 1, two ? l + 2 : l + 1, sb_new, sp, lane, gmask, v0, v1);
+                    eval.block2h(rec, l + 1, two ? l + 2 : l + 1, sb_new, sp, lane, gmask, v0, v1);
                     cum += v0;
                     if (lane == (l & (kSvG - 1))) mine = a.c.log ? v0 : cum;
                     if (two) {
@@ -1029,7 +1126,7 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
                 }
             }
             if (live) {
-                for (int l = nh + lane; l < a.L; l += kSvG) Srow[l] = nan;        // intervals this subject does not have
+                if (!split) for (int l = nh + lane; l < a.L; l += kSvG) Srow[l] = nan;   // intervals this subject does not have
                 if (lane < q) sb_old[lane] = sb_new[lane];
             }
             __syncwarp();
@@ -1057,11 +1154,89 @@ jmb_svft_modes_generic(const __grid_constant__ SvMeta mm, const __grid_constant_
 }
 template <class Spec>
 __global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS) jmb_svft_sample_static(const __grid_constant__ SvArgs a) {
-    sv_sample_run(Spec::d.q, Spec::d.O, a, SvEvalStatic<Spec>{});
+    SvEvalStatic<Spec> ev{};
+    sv_sample_run(Spec::d.q, Spec::d.O, a, ev);
 }
 __global__ void __launch_bounds__(JMB_SVFT_THREADS, JMB_SVFT_MIN_CTAS)
 jmb_svft_sample_generic(const __grid_constant__ SvMeta mm, const __grid_constant__ SvArgs a) {
-    sv_sample_run(mm.d.q, mm.d.O, a, SvEvalGeneric{mm.d, mm.L});
+    SvEvalGeneric ev{mm.d, mm.L};
+    sv_sample_run(mm.d.q, mm.d.O, a, ev);
+}
+
+// ---- horizon integrals of linear models: one THREAD per posterior draw ---------------------------------------------------
+// For the models of sv_is_linear() the linear predictor of a quadrature row is s1(row, Bs_m) + C_0(m) + sum_c col_c(row)
+// C_c(m), where the coefficients C(m) of b.new after draw m come from jmb_svft_sample_* (a.Cbuf).  A CTA walks subjects;
+// thread m keeps C(m) in registers, the Bs_gammas of all draws sit in shared memory ([M][B], conflict-free for odd B), the K
+// rows of an interval are staged in shared memory and broadcast; every thread sums its K rows in row order (the order of the
+// reference's cumsum, src/survfitJM_mvJMbayes.cpp:7-14), accumulates cumsum(logS) over the intervals and writes
+// S = exp(cumsum) (R/survfitJM.mvJMbayes.R:378-395).  No reductions, no divergence, 32 of 32 lanes busy.
+template <class Spec>
+__global__ void __launch_bounds__(256) jmb_svft_horizons(const __grid_constant__ SvArgs a) {
+    constexpr int K = Spec::d.K, WB = Spec::d.WB, NC = Spec::d.NC, O = Spec::d.O;
+    constexpr int oBlk0 = Spec::L.o_blk0, BLK = Spec::L.blk, psBs = Spec::L.ps_Bs;
+    constexpr int bW1off = Spec::L.b_W1off, bW1v = Spec::L.b_W1v, bPw = Spec::L.b_Pw, bCol = Spec::L.b_col;
+    constexpr int RW = 2 + WB + NC;                  // staged row: Pw, band offset, band values, pooled columns
+    extern __shared__ double hz_smem[];
+    const int B = a.B, tid = threadIdx.x, MC = blockDim.x;
+    double* s_Bs = hz_smem;                          // [MC][B]
+    double* s_row = hz_smem + (size_t)MC * B;        // [K][RW]
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int m0 = 0; m0 < a.M; m0 += MC) {           // chunks of blockDim.x draws (one chunk when M <= 256)
+        const int m = m0 + tid;
+        const bool on = m < a.M;
+        __syncthreads();
+        for (int e = tid; e < MC * B; e += MC) {
+            const int mm = e / B, j = e - mm * B;
+            s_Bs[e] = (m0 + mm < a.M) ? a.par_draws[(size_t)(m0 + mm) * a.ps_len + psBs + j] : 0.0;
+        }
+        const double* myBs = s_Bs + (size_t)tid * B;
+        for (int s = blockIdx.x; s < a.n; s += gridDim.x) {
+            const double* __restrict__ rec = a.rec + a.off[s];
+            const int nh = reinterpret_cast<const int*>(rec)[O];
+            double c0 = 0.0, cc[NC > 0 ? NC : 1];
+            if (on) {
+                const double* cs = a.Cbuf + ((size_t)s * a.M + m) * a.ncoef;
+                c0 = cs[0];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) cc[c] = cs[1 + c];
+            }
+            double cum = 0.0;
+            double* Srow = a.S + ((size_t)s * a.M + (on ? m : 0)) * a.L;
+            for (int l = 0; l < nh; ++l) {
+                const double* __restrict__ blk = rec + oBlk0 + (long long)(l + 1) * BLK;
+                __syncthreads();
+                for (int e = tid; e < K * RW; e += MC) {
+                    const int k = e / RW, f = e - k * RW;
+                    double v;
+                    if (f == 0) v = blk[bPw + k];
+                    else if (f == 1) v = (double)reinterpret_cast<const int*>(blk + bW1off)[k];
+                    else if (f < 2 + WB) v = blk[bW1v + (f - 2) * kSvG + k];
+                    else v = blk[bCol + (f - 2 - WB) * kSvG + k];
+                    s_row[e] = v;
+                }
+                __syncthreads();
+                if (on) {
+                    double H = 0.0;
+#pragma unroll 5
+                    for (int k = 0; k < K; ++k) {
+                        const double* r = s_row + k * RW;
+                        const int off = (int)r[1];
+                        double s1 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < WB; ++j) s1 += r[2 + j] * myBs[off + j];
+                        double al = c0;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) al += r[2 + WB + c] * cc[c];
+                        H += r[0] * exp(s1 + al);
+                    }
+                    const double logS = 0.0 - H;
+                    cum += logS;
+                    Srow[l] = a.c.log ? logS : exp(cum);
+                }
+            }
+            if (on) for (int l = nh; l < a.L; ++l) Srow[l] = nan;
+        }
+    }
 }
 
 // ---- Mean / Median / Lower / Upper, M <= 32 * EPL: one warp per (subject, interval) -------------------------------------
