@@ -645,6 +645,8 @@ struct SvEvalGeneric {
     __device__ __forceinline__ double full0(const double* rec, const double* sb, const double* sp, int lane, unsigned gmask) const {
         return sv_eval_generic(d, L, rec, 0, true, sb, sp, lane, gmask);
     }
+    __device__ __forceinline__ void full2c(const double* rec, const double* sbA, const double* sbB, const double* sp, int lane,
+                                           unsigned gmask, double& vA, double& vB) const { full2(rec, sbA, sbB, sp, lane, gmask, vA, vB); }
     // two points on block 0 / two blocks at one point: the generic flavour simply evaluates twice
     __device__ __forceinline__ void full2(const double* rec, const double* sbA, const double* sbB, const double* sp, int lane,
                                           unsigned gmask, double& vA, double& vB) const {
@@ -681,6 +683,15 @@ struct SvEvalStatic {
         const double* const pts[2] = {sbA, sbB};
         double out[2];
         sv_eval_static_n<Spec, false, 1, 2>(rec, bi, true, pts, sp, lane, gmask, hc, out);
+        vA = out[0]; vB = out[1];
+    }
+    // the same with the cached b-independent row part (mode search: both points of a central difference in one pass)
+    __device__ __forceinline__ void full2c(const double* rec, const double* sbA, const double* sbB, const double* sp, int lane,
+                                           unsigned gmask, double& vA, double& vB) const {
+        const int bi[1] = {0};
+        const double* const pts[2] = {sbA, sbB};
+        double out[2];
+        sv_eval_static_n<Spec, true, 1, 2>(rec, bi, true, pts, sp, lane, gmask, hc, out);
         vA = out[0]; vB = out[1];
     }
     __device__ __forceinline__ void block2(const double* rec, int blkA, int blkB, const double* sb, const double* sp, int lane,
@@ -723,7 +734,7 @@ __device__ __forceinline__ void sv_modes_run(const int q, const SvArgs& a, Eval&
     const double* sp = gbase;                        // parameter set (posterior means)
     double* v0 = gbase + a.ps_len;
     double *btry = v0, *x = v0 + q, *grad = v0 + 2 * q, *bz = v0 + 3 * q, *X = v0 + 4 * q, *c = v0 + 5 * q, *t = v0 + 6 * q,
-           *g = v0 + 7 * q, *dpar = v0 + 8 * q, *df1 = v0 + 9 * q, *mode = v0 + 10 * q;
+           *g = v0 + 7 * q, *dpar = v0 + 8 * q, *df1 = v0 + 9 * q, *mode = v0 + 10 * q, *bt2 = v0 + 13 * q;
     const int zq = (q + 2) / 2 * 2;
     double* Bm = v0 + 14 * q + zq;
     double* hess = Bm + q * q;
@@ -736,7 +747,7 @@ __device__ __forceinline__ void sv_modes_run(const int q, const SvArgs& a, Eval&
 
     // replicated control state
     int st = ST_FETCH, subj = -1, nev = 0, ret = 0, count = 0, fun = 0, grc = 0, ilast = 0, iter = 0, hi = 0, conv = 0;
-    double Fmin = 0.0, f = 0.0, gradproj = 0.0, step = 0.0, epsH = 0.0, val = 0.0, f1 = 0.0, x1 = 0.0;
+    double Fmin = 0.0, f = 0.0, gradproj = 0.0, step = 0.0, epsH = 0.0, val = 0.0;
     const double* rec = a.rec;
     auto gsync = [&]() { __syncwarp(gmask); };
     auto post_grad = [&](const double* z, int r) {   // fmingr at the optimiser point z: x = z * parscale
@@ -927,24 +938,26 @@ __device__ __forceinline__ void sv_modes_run(const int q, const SvArgs& a, Eval&
             }
             }
         }
-        // ---- evaluation: both groups of the warp together ----
-        const int nmax = max(nev, __shfl_xor_sync(0xFFFFFFFFu, nev, 16));
+        // ---- evaluation: both groups of the warp together; a gradient request evaluates the two points of each
+        //      central difference x +- ex e_i (R/cd.R:5-10) in one pass ----
+        const int nit = (nev > 1) ? nev / 2 : nev;
+        const int nmax = max(nit, __shfl_xor_sync(0xFFFFFFFFu, nit, 16));
         if (nmax == 0) break;
-        for (int e = 0; e < nmax; ++e) {
-            const bool act = e < nev;
-            const int i = e >> 1;
-            if (act && nev > 1 && own) {              // cd(): x1 = x + ex e_i, then x2 = x - ex e_i (R/cd.R:5-10)
-                double xv = x[lane];
-                if (lane == i) { const double ex = eps * (fabs(xv) + eps); xv = (e & 1) ? xv - ex : xv + ex; }
-                btry[lane] = xv;
+        for (int it = 0; it < nmax; ++it) {
+            const bool act = it < nit;
+            if (act && nev > 1 && own) {
+                double xa = x[lane], xb2 = xa;
+                if (lane == it) { const double ex = eps * (fabs(xa) + eps); xb2 = xa - ex; xa = xa + ex; }
+                btry[lane] = xa; bt2[lane] = xb2;
             }
             __syncwarp();
             if (act) {
-                val = eval.full0(rec, btry, sp, lane, gmask);
                 if (nev > 1) {
-                    const double bi = btry[i];
-                    if (!(e & 1)) { f1 = 0.0 - val; x1 = bi; }
-                    else if (lane == 0) grad[i] = ((f1 - (0.0 - val)) / (x1 - bi)) * ps;   // diff.f / diff.x, fmingr scaling
+                    double vA, vB;
+                    eval.full2c(rec, btry, bt2, sp, lane, gmask, vA, vB);
+                    if (lane == 0) grad[it] = (((0.0 - vA) - (0.0 - vB)) / (btry[it] - bt2[it])) * ps;   // diff.f / diff.x, fmingr scaling
+                } else {
+                    val = eval.full0(rec, btry, sp, lane, gmask);
                 }
             }
             __syncwarp();
