@@ -81,3 +81,37 @@ def test_full_size_config4_properties(cuda_lib, oracle, monkeypatch):
     assert np.allclose(chain2["extras"]["trace_surv"], tr, rtol=1e-12)
     assert np.array_equal(chain2["mcmc"]["b"], chain["mcmc"]["b"])
     assert abs(tr[0] - (got["log_ptb"].sum())) < 0.05 * abs(tr[0])      # one b-step away from the initial state
+
+
+# ---- BASELINE config 5 at the size of one GPU's shard: 125 000 new subjects, M = 200 draws, L = 10 horizons --------------
+N_SVFT = int(os.environ.get("JMB_FULL_SVFT_N", "125000"))
+
+
+def test_survfit_full_shard_properties(cuda_lib):
+    """Size-independent properties of survfitJM on the full per-GPU shard of config 5, and agreement with the restated R
+    loop on a random sub-cohort (draws are keyed by the global subject index, so a sub-cohort reproduces its subjects)."""
+    from jmbayes_b200 import survfit as sv
+    from oracle import oracle_svft
+    c = make_cohort("config3", n=N_SVFT, seed=777)
+    means, draws = sv.posterior_draws(c, M=200)
+    d = sv.newdata_designs(c, L=10, dense_basis=False)           # bases evaluated by the library from (knots, times)
+    with sv.SurvFit(d) as h:
+        r = h.survfitJM(means, draws, full=False)
+        info = h.info()
+    S = r["summaries"]                                            # L x 4 x n: Mean, Median, Lower, Upper
+    assert S.shape == (10, 4, N_SVFT) and np.all(np.isfinite(S))
+    assert np.all(S > 0) and np.all(S <= 1.0)
+    assert np.all(S[:, 2] <= S[:, 1] + 1e-15) and np.all(S[:, 1] <= S[:, 3] + 1e-15)     # Lower <= Median <= Upper
+    assert np.all(np.diff(S[:, 0], axis=0) <= 1e-15)              # the mean survival curve decreases over the horizons
+    assert np.mean(r["convergence"] == 0) > 0.999 and np.all(np.isfinite(r["modes"]))
+    assert 0.3 < r["accept_rate"].mean() < 0.8 and r["accept_rate"].min() > 0.02
+    assert info["launches"] == 4                                  # mode search, sampling, horizons, summaries
+    # random sub-cohort against the oracle: same subjects, same global indices
+    rng = np.random.default_rng(5)
+    for start in rng.integers(0, N_SVFT - 8, size=3):
+        sel = np.arange(start, start + 8)
+        ds = sv.newdata_designs(c, L=10, subjects=sel)
+        o = oracle_svft.survfitJM(ds, means, draws, subject_offset=int(start))
+        assert np.max(np.abs(o["modes"] - r["modes"][sel])) < 1e-6
+        diff = np.max(np.abs(o["summaries"] - S[:, :, sel]), axis=(0, 1))
+        assert np.sum(diff > 1e-5) <= 1                           # an MH decision can flip only within ~1e-7 of the ratio
