@@ -36,7 +36,7 @@ WORKLOADS = {
     "config2": ("config2", 100000),
     # survfitJM dynamic predictions (BASELINE config 5): M = 200 draws x L = 10 horizons per subject; one "step" =
     # the whole per-subject loop (mode search + MH over the draws + horizon integrals + summaries) for every subject
-    "config5": ("config3", 25000),
+    "config5": ("config4", 25000),
 }
 SVFT_M, SVFT_L = 200, 10
 SVFT_METRIC = "subject-draws/sec of survfitJM dynamic predictions (M=200 draws x L=10 horizons per subject)"
@@ -367,7 +367,7 @@ def run_cuda(args):
 def _svft_case(n, seed, dense_basis=True):
     from jmbayes_b200 import survfit as sv
     from jmbayes_b200.cohorts import make_cohort
-    c = make_cohort("config3", n=n, seed=seed)
+    c = make_cohort("config4", n=n, seed=seed)                       # new subjects of the config-4 fit (BASELINE config 5)
     d = sv.newdata_designs(c, L=SVFT_L, dense_basis=dense_basis)     # the CPU restatement reads the reference's dense bases
     means, draws = sv.posterior_draws(c, M=SVFT_M)
     return d, means, draws
@@ -467,7 +467,7 @@ def run_config5(args):
         "metric": SVFT_METRIC, "value": value, "unit": SVFT_UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "config5", "cohort": "config3 fit, all subjects as newdata truncated at 0.5 T", "subjects_per_gpu": n,
+        "config": {"workload": "config5", "cohort": "config-4 fit (3 outcomes, q = 6, value + slope), all subjects as newdata truncated at 0.5 T", "subjects_per_gpu": n,
                    "subjects_total": n_total, "M": SVFT_M, "L": SVFT_L, "q": 6, "outcomes": 3, "K": 15,
                    "parallelism": f"subject-shards x{world} (no collective)",
                    "l2": "each subject's record (%.1f kB) is read once from HBM and re-used ~2900 times from L1/L2" % (rec_bytes / 1e3)},
