@@ -99,6 +99,14 @@ typedef struct jmb_data {
     const double* const* Us_int;    /* [n_terms] nK x u_t (interval_cens only) */
     /* Covs$b: q x q x n upper Cholesky factors (R/mvJointModelBayes.R:728-729) */
     const double* Covs_b;
+    /* Alternative to the dense bases: when W1 is NULL, the rows of
+     * splines::splineDesign(knots, x, ord, outer.ok = TRUE) (R/mvJointModelBayes.R:382-383,389-392) are evaluated by
+     * the library from Time / st / st_int - the dense n x n_Bs and nK x n_Bs matrices (2 x 2 GB at 1M subjects) never
+     * exist.  n_knots = n_Bs + ord.  W1s / W1s_int are then ignored. */
+    const double* knots; int32_t n_knots; int32_t ord;
+    const double* Time;             /* [n]  event times */
+    const double* st;               /* [nK] c(t(st)): quadrature times */
+    const double* st_int;           /* [nK] (interval_cens only) */
 } jmb_data;
 
 /* The per-draw part of `Data` (R/mvJointModelBayes.R:760-770). */

@@ -38,6 +38,8 @@ class JmbData(C.Structure):
         ("ZZ", c_double_pp), ("ZZs", c_double_pp), ("ZZs_int", c_double_pp),
         ("U", c_double_pp), ("Us", c_double_pp), ("Us_int", c_double_pp),
         ("Covs_b", c_double_p),
+        ("knots", c_double_p), ("n_knots", C.c_int32), ("ord", C.c_int32), ("Time", c_double_p), ("st", c_double_p),
+        ("st_int", c_double_p),
     ]
 
 
@@ -145,8 +147,9 @@ class Keep:
 
 
 def marshal_data(Data: dict, Covs_b, interval_cens: bool, multi_state: bool = False,
-                 subject_offset: int = 0, K: int | None = None):
-    """``Data`` + ``Covs$b`` -> (JmbData, Keep)."""
+                 subject_offset: int = 0, K: int | None = None, basis_from_knots: bool = False):
+    """``Data`` + ``Covs$b`` -> (JmbData, Keep).  ``basis_from_knots``: pass knots / Time / st (/ st_int) instead of the
+    dense W1 / W1s (/ W1s_int); the library evaluates splineDesign itself."""
     k = Keep()
     d = JmbData()
     n = int(np.asarray(Data["event"]).shape[0])
@@ -174,7 +177,13 @@ def marshal_data(Data: dict, Covs_b, interval_cens: bool, multi_state: bool = Fa
     d.idL = k.i32_list(Data["idL"])
     d.idL2 = k.i32_list(Data["idL2"])
     d.event = k.f64(Data["event"])
-    d.W1, d.W1s = k.f64(W1), k.f64(Data["W1s"])
+    if basis_from_knots:
+        d.knots, d.n_knots, d.ord = k.f64(Data["knots"]), int(len(Data["knots"])), int(Data.get("ordSpline", 4))
+        d.Time, d.st = k.f64(Data["Time"]), k.f64(Data["st"])
+        if interval_cens:
+            d.st_int = k.f64(Data["st_int"])
+    else:
+        d.W1, d.W1s = k.f64(W1), k.f64(Data["W1s"])
     d.W2, d.W2s = k.f64(W2), k.f64(Data["W2s"])
     d.Pw = k.f64(Data["Pw"])
     d.idGK_fast = k.i32(Data["idGK_fast"])
@@ -186,7 +195,9 @@ def marshal_data(Data: dict, Covs_b, interval_cens: bool, multi_state: bool = Fa
     d.ZZ, d.ZZs = k.f64_list(Data["ZZ"]), k.f64_list(Data["ZZs"])
     d.U, d.Us = k.f64_list(Data["U"]), k.f64_list(Data["Us"])
     if interval_cens:
-        d.W1s_int, d.W2s_int, d.Pw_int = k.f64(Data["W1s_int"]), k.f64(Data["W2s_int"]), k.f64(Data["Pw_int"])
+        if not basis_from_knots:
+            d.W1s_int = k.f64(Data["W1s_int"])
+        d.W2s_int, d.Pw_int = k.f64(Data["W2s_int"]), k.f64(Data["Pw_int"])
         d.ZZs_int, d.Us_int = k.f64_list(Data["ZZs_int"]), k.f64_list(Data["Us_int"])
     d.Covs_b = k.f64(Covs_b)
     return d, k

@@ -105,10 +105,10 @@ class Fit:
     """
 
     def __init__(self, Data: dict, Covs_b, interval_cens: bool = False, multiState: bool = False,
-                 device: int = 0, subject_offset: int = 0):
+                 device: int = 0, subject_offset: int = 0, basis_from_knots: bool = False):
         self._h = C.c_void_p()
         self.interval_cens = bool(interval_cens)
-        d, keep = _abi.marshal_data(Data, Covs_b, interval_cens, multiState, subject_offset)
+        d, keep = _abi.marshal_data(Data, Covs_b, interval_cens, multiState, subject_offset, basis_from_knots=basis_from_knots)
         self.n, self.q = d.n, d.q
         self.B, self.p, self.A = d.n_Bs, d.n_gammas, d.n_alphas
         self.O, self.T, self.K = d.n_outcomes, d.n_terms, d.K

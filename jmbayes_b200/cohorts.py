@@ -311,7 +311,7 @@ def make_cohort(config: str = "config3", n: int = 1000, seed: int | None = None,
         Data.update(
             Levent1=(ev == 1), Levent01=(ev == 1) | (ev == 0), Levent2=(ev == 2), Levent3=(ev == 3),
             W1s_int=spline_design(knots, st_int_vec), W2s_int=W2s.copy(order="F"),
-            Us_int=Us_int, XXsbetas_int=XXsbetas_int, ZZs_int=ZZs_int, Pw_int=Pw_int)
+            Us_int=Us_int, XXsbetas_int=XXsbetas_int, ZZs_int=ZZs_int, Pw_int=Pw_int, st_int=st_int_vec)
     else:
         e0 = np.zeros(0, dtype=bool)
         Data.update(Levent1=e0, Levent01=e0, Levent2=e0, Levent3=e0,

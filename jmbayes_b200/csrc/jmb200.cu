@@ -262,7 +262,13 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     const int S = d->interval_cens ? 2 : 1;
     if (d->K <= 0 || 1 + d->K * S > 32) return fail("jmb_create: 1 + K * (1 + interval_cens) must be <= 32");
     if (d->q + kStateExtra > 32) return fail("jmb_create: q + 7 must be <= 32");
-    if (S == 2 && (!d->W1s_int || !d->Pw_int || !d->ZZs_int || !d->Us_int || (d->n_gammas && !d->W2s_int)))
+    const bool from_knots = (d->W1 == nullptr);
+    if (from_knots) {
+        if (!d->knots || !d->Time || !d->st || (S == 2 && !d->st_int)) return fail("jmb_create: W1 is NULL, so knots / Time / st (/ st_int) are required");
+        if (d->ord < 1 || d->ord > 8 || d->n_knots != d->n_Bs + d->ord) return fail("jmb_create: need 1 <= ord <= 8 and n_knots = n_Bs + ord");
+        for (int j = 1; j < d->n_knots; ++j) if (d->knots[j] < d->knots[j - 1]) return fail("jmb_create: knots must be non-decreasing");
+    } else if (!d->W1s || (S == 2 && !d->W1s_int)) return fail("jmb_create: W1s (/ W1s_int) required with a dense W1");
+    if (S == 2 && (!d->Pw_int || !d->ZZs_int || !d->Us_int || (d->n_gammas && !d->W2s_int)))
         return fail("jmb_create: interval_cens needs the *_int designs");
 
     auto* h = new jmb_handle_s();
@@ -333,7 +339,8 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
             if (W[r + (long long)j * rows] != 0.0) { if (first == B) first = j; last = j; }
     };
     int WB = 1;
-    {
+    if (from_knots) WB = std::min(d->ord, B);
+    else {
         std::atomic<int> wmax{1};
         auto scan = [&](const double* W, long long rows) {
             parallel_for((int)std::min<long long>(rows, 2147483647LL), [&, W, rows](int lo, int hi) {
@@ -420,12 +427,20 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
                 const double* W2x = cls == 0 ? d->W2 : (cls == 1 ? d->W2s : d->W2s_int);
                 if (cls == 1) rec[L.o_Pw + r] = d->Pw[src];
                 if (cls == 2) rec[L.o_Pw + r] = d->Pw_int[src];
-                int f, l;
-                band_of(W1x, rows, src, f, l);
-                int off = (l < f) ? 0 : std::min(f, B - WB);
-                if (WB == B) off = 0;
-                w1off[r] = off;
-                for (int j = 0; j < WB; ++j) rec[L.o_W1v + j * RP + r] = W1x[src + (long long)(off + j) * rows];
+                if (from_knots) {
+                    const double tx = cls == 0 ? d->Time[src] : (cls == 1 ? d->st[src] : d->st_int[src]);
+                    int off; double bv[16];
+                    spline_band_row(d->knots, d->n_knots, d->ord, tx, off, bv);
+                    w1off[r] = off;
+                    for (int j = 0; j < WB; ++j) rec[L.o_W1v + j * RP + r] = bv[j];
+                } else {
+                    int f, l;
+                    band_of(W1x, rows, src, f, l);
+                    int off = (l < f) ? 0 : std::min(f, B - WB);
+                    if (WB == B) off = 0;
+                    w1off[r] = off;
+                    for (int j = 0; j < WB; ++j) rec[L.o_W1v + j * RP + r] = W1x[src + (long long)(off + j) * rows];
+                }
                 if (!md.w2_const) for (int j = 0; j < p; ++j) rec[L.o_W2 + j * RP + r] = W2x[src + (long long)j * rows];
                 for (int t = 0; t < T; ++t) {
                     const double* ZZx = cls == 0 ? d->ZZ[t] : (cls == 1 ? d->ZZs[t] : d->ZZs_int[t]);
@@ -463,6 +478,13 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     // event_colSums of W1 and W2 (R/mvJointModelBayes.R:677-679) for gradient_logPosterior
     h->h_event.assign(d->event, d->event + n);
     h->ecs.assign(B + p + d->n_alphas, 0.0);
+    if (from_knots) {      // event_colSumsW1 from the band rows, subjects in order (the dense sum's order per column)
+        for (int i = 0; i < n; ++i) {
+            int off; double bv[16];
+            spline_band_row(d->knots, d->n_knots, d->ord, d->Time[i], off, bv);
+            for (int j = 0; j < std::min(d->ord, B); ++j) h->ecs[off + j] += d->event[i] * bv[j];
+        }
+    } else
     for (int j = 0; j < B; ++j) { double t = 0.0; for (int i = 0; i < n; ++i) t += d->event[i] * d->W1[i + (long long)j * n]; h->ecs[j] = t; }
     for (int j = 0; j < p; ++j) { double t = 0.0; for (int i = 0; i < n; ++i) t += d->event[i] * d->W2[i + (long long)j * n]; h->ecs[B + j] = t; }
 

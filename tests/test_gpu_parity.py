@@ -245,3 +245,29 @@ def test_device_xbetas_equals_host_xbetas(cuda_lib, cfg):
     with cuda_lib.Fit(D, c["Covs"]["b"], c["interval_cens"]) as fit:
         with pytest.raises(cuda_lib.JmbError):
             fit.set_draw_betas(D["betas"], D["sigmas"], D["invD"])       # designs not uploaded
+
+
+@pytest.mark.parametrize("cfg", ["config3", "config4"])
+def test_basis_from_knots_equals_dense_basis(cuda_lib, oracle, cfg):
+    """jmb_create with W1 = NULL evaluates splineDesign(knots, x, ord = 4, outer.ok = TRUE) itself from
+    Time / st / st_int; everything downstream must equal the dense-basis handle (band values are the same numbers)."""
+    c = make_cohort(cfg, n=500)
+    D, ini, pr = c["Data"], c["inits"], c["priors"]
+    Wl = oracle.wlong(D, c["Covs"]["b"], c["interval_cens"], ini["b"], 0)
+    Wls = oracle.wlong(D, c["Covs"]["b"], c["interval_cens"], ini["b"], 1)
+    res = []
+    for lean in (False, True):
+        with cuda_lib.Fit(D, c["Covs"]["b"], c["interval_cens"], basis_from_knots=lean) as fit:
+            fit.set_draw(D)
+            ev = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+            fit.set_wlong(Wl, Wls)
+            gr = fit.gradient_logPosterior(1.0, ini["Bs_gammas"], ini["gammas"], ini["alphas"], pr, 200.0, 1.0, 0.01)
+            res.append((ev, gr, fit.layout_info()["w1_band"]))
+    (e0, g0, w0), (e1, g1, w1) = res
+    assert w0 == w1 == 4
+    for k in ("log_h", "H", "log_ptb"):
+        assert np.allclose(e0[k], e1[k], rtol=1e-14, atol=0), k
+    assert np.allclose(g0, g1, rtol=1e-12, atol=1e-12)
+    bad = dict(D); bad["knots"] = np.asarray(D["knots"])[:-1]
+    with pytest.raises(cuda_lib.JmbError):
+        cuda_lib.Fit(bad, c["Covs"]["b"], c["interval_cens"], basis_from_knots=True)
