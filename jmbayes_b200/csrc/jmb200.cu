@@ -729,14 +729,39 @@ extern "C" int jmb_set_draw_betas(jmb_handle h, const double* const* betas, cons
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch of the two per-iteration kernels (JMB_PDL=0 disables it for A/B runs): launch latency and
+// CTA set-up of the step kernel overlap the previous finalize kernel, and the finalize kernel preloads its parameter block
+// under the tail of the step kernel.  (Prefetching the first record stages before the wait as well costs the step kernel
+// 180 B of extra spills and 35 % of its speed: profiles/r1_experiments.md.)
+static bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("JMB_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 static int launch_step(jmb_handle h, int mode) {
     StepArgs a{};
     a.drec = h->d_drec; a.doff = h->d_doff; a.crec = h->c->d_crec; a.coff = h->d_coff; a.rowptr = h->d_rowptr;
     a.state = h->c->d_state; a.par = h->c->d_par; a.ctl = h->c->d_ctl; a.partials = h->c->d_partials; a.eval_out = h->d_eval;
     a.n = h->n; a.subject_offset = h->subject_offset; a.mode = mode; a.subjects_per_cta = h->subjects_per_cta;
     a.rng = h->c->d_rng; a.rng_chunk = h->c->rng_chunk; a.rng_stride = h->rng_stride;
-    if (mode == MODE_STEP && h->kernel_mode == 2)
-        h->tma_kernel<<<h->tma_grid, kTmaThreads, h->tma_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a, h->ta);
+    if (mode == MODE_STEP && h->kernel_mode == 2) {
+        if (pdl_enabled()) {
+            CU(launch_pdl(h->tma_kernel, dim3(h->tma_grid), dim3(kTmaThreads), (size_t)h->tma_smem, h->c->stream, h->mm.B, h->pl, h->c->cc, a, h->ta));
+        } else {
+            h->tma_kernel<<<h->tma_grid, kTmaThreads, h->tma_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a, h->ta);
+        }
+    }
     else if (mode == MODE_STEP && h->kernel_mode == 1)
         h->static_kernel<<<h->grid, 256, h->static_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a);
     else if (h->mm.d.G == 16)
@@ -772,7 +797,8 @@ static int launch_finalize(jmb_handle h, int phase) {
         CU(cudaFuncSetAttribute((const void*)jmb_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
         h->c->fin_attr_set = true;
     }
-    jmb_finalize_kernel<<<1, 128, a.use_smem ? fin_smem : 0, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
+    if (pdl_enabled()) CU(launch_pdl(jmb_finalize_kernel, dim3(1), dim3(128), a.use_smem ? fin_smem : 0, h->c->stream, h->mm, h->pl, h->c->cc, a));
+    else jmb_finalize_kernel<<<1, 128, a.use_smem ? fin_smem : 0, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
     h->launches += 1;
     CU(cudaGetLastError());
     return 0;

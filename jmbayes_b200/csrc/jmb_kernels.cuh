@@ -38,6 +38,12 @@ struct StepArgs {
     int rng_stride;          // q + 1 rounded up to even
 };
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor has completed and flushed,
+// pdl_trigger() lets the successor start.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // -------------------------------------------------------------------------------------------
 // generic step kernel: runtime model descriptor, G lanes per subject.  Fallback for model shapes
 // without a precompiled specialisation (jmb_step_static.cuh); same results.
@@ -345,10 +351,12 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     // the scalar logic below makes dozens of dependent accesses, each a 600-cycle trip in global memory
     extern __shared__ double s_par[];
     double* par = a.use_smem ? s_par : gpar;
-    if (a.use_smem) {
+    if (a.use_smem) {          // the parameter block is written by finalize kernels only: safe before pdl_wait()
         for (int j = tid; j < pl.block_par; j += blockDim.x) s_par[j] = gpar[j];
         __syncthreads();
     }
+    pdl_wait();                // the step kernel (partials, state) has completed
+    pdl_trigger();             // the next step kernel may start its prologue (records, state and draws are final)
 
     if (a.phase == 1) {
         if (tid == 0) {

@@ -379,9 +379,14 @@ jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_c
     double* s_stage = smem + head;                 // [WARPS][2][stage_doubles]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
+    // Programmatic dependent launch: this kernel may be scheduled while the previous finalize kernel still runs (launch
+    // latency and CTA set-up overlap it); pdl_wait() returns once the parameter block and the loop control are final.
+    if (tid < WARPS * 2) mbar_init(&s_bar[tid], 1);
+    pdl_wait();
+    pdl_trigger();             // only now (the previous finalize kernel is complete) may the next finalize kernel be
+                               // scheduled: it preloads the parameter block before its own wait
     for (int j = tid; j < P; j += THREADS) { s_cur[j] = a.par[pl.cur + j]; s_prop[j] = a.par[pl.prop + j]; }
     for (int j = tid; j < q * q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
-    if (tid < WARPS * 2) mbar_init(&s_bar[tid], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const int i_blk = a.ctl->i;
     const bool last_acc = a.ctl->last_accept != 0;
