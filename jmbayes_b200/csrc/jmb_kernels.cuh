@@ -316,14 +316,17 @@ struct FinalizeArgs {
 };
 
 // survival proposal for iteration `iter`: cur + sqrt(sigma) * z' chol(Sigma)  (:659-661,732-734)
-__device__ inline void make_proposal(const ModelMeta& mm, const ParamLayout& pl, const ChainConst& cc,
-                                     double* par, int iter, int tid, int nthreads, double* s_z) {
-    const int B = mm.B, p = mm.d.p, A = mm.d.A;
+__device__ inline void proposal_normals(const ModelMeta& mm, const ChainConst& cc, int iter, int tid, int nthreads, double* s_z) {
     for (int s = tid; s < (mm.P + 1) / 2; s += nthreads) {
         double z0, z1;
         rnorm_pair(cc.seed, cc.chain_id, 0u, (uint32_t)iter, (uint32_t)s, ST_SURV, z0, z1);
         s_z[2 * s] = z0; s_z[2 * s + 1] = z1;
     }
+}
+__device__ inline void make_proposal(const ModelMeta& mm, const ParamLayout& pl, const ChainConst& cc,
+                                     double* par, int iter, int tid, int nthreads, double* s_z, bool have_z = false) {
+    const int B = mm.B, p = mm.d.p, A = mm.d.A;
+    if (!have_z) proposal_normals(mm, cc, iter, tid, nthreads, s_z);
     __syncthreads();
     for (int j = tid; j < mm.P; j += nthreads) {
         int base, m, jj, Ho, sg;
@@ -354,6 +357,29 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     if (a.use_smem) {          // the parameter block is written by finalize kernels only: safe before pdl_wait()
         for (int j = tid; j < pl.block_par; j += blockDim.x) s_par[j] = gpar[j];
         __syncthreads();
+    }
+    // Everything random in this kernel depends only on (seed, chain, iteration), and the loop control is written by
+    // finalize kernels only: draw it now, under the tail of the step kernel.  Gamma draws are taken at unit scale (the
+    // data-dependent scale multiplies the same number afterwards: bitwise the value rgamma_dev would return).
+    __shared__ double s_lu, s_gam[4 + JMB_MAX_TERMS + JMB_MAX_GAMMAS + 2 * JMB_MAX_ALPHAS];
+    const int iter_pre = a.ctl->iter;
+    if (a.phase == 0) {
+        int nd = 1 + cc.n_td;
+        const int d_g = nd; if (cc.shrink_gammas) nd += p + 1;
+        const int d_a = nd; if (cc.shrink_alphas) nd += A + 1 + (cc.double_gamma_alphas ? A + 1 : 0);
+        for (int dd = tid; dd < nd; dd += blockDim.x) {
+            double shape;
+            if (dd == 0) shape = cc.Apost_tau_Bs;
+            else if (dd < d_g) shape = cc.Apost_tau_td;
+            else if (dd < d_a) shape = (dd - d_g < p) ? cc.Apost_phi_g : cc.Apost_tau_g;
+            else {
+                const int k = dd - d_a;
+                shape = (k < A) ? cc.Apost_phi_a : (k == A ? cc.Apost_tau_a : (k < 2 * A + 1 ? cc.Apost_nu_a : cc.Apost_xi_a));
+            }
+            s_gam[dd] = rgamma_dev(cc.seed, cc.chain_id, (uint32_t)dd, (uint32_t)iter_pre, shape, 1.0);
+        }
+        if (tid == blockDim.x - 1) s_lu = log_unif(cc.seed, cc.chain_id, 0u, (uint32_t)iter_pre, 0xFFFFFFFFu, ST_SURV);
+        proposal_normals(mm, cc, iter_pre + 1, tid, blockDim.x, s_z);
     }
     pdl_wait();                // the step kernel (partials, state) has completed
     pdl_trigger();             // the next step kernel may start its prologue (records, state and draws are final)
@@ -474,7 +500,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         const double cur_lp = a.wore ? par[pl.cur_lp] : s_tot[0] - 0.5 * qc[0] - 0.5 * tau_g * qc[1] - 0.5 * tau_a * qc[2];
         const double new_lp = s_tot[1] - 0.5 * tBs * qp[0] - 0.5 * tau_g * qp[1] - 0.5 * tau_a * qp[2];
         if (a.wore && a.trace) { a.trace[2LL * iter] = cur_lp; a.trace[2LL * iter + 1] = new_lp; }
-        const double lu = log_unif(cc.seed, cc.chain_id, 0u, (uint32_t)iter, 0xFFFFFFFFu, ST_SURV);
+        const double lu = s_lu;
         ctl->last_accept = 0;
         double raw_Bs = rawc;
         if (lu < new_lp - cur_lp) {
@@ -489,7 +515,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         uint32_t draw = 0;
         {
             const double Bpost = cc.B_tau_Bs + 0.5 * raw_Bs;           // B_tau + 0.5 Bs' Tau Bs (:778-779)
-            par[pl.tau_Bs] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_tau_Bs, 1.0 / Bpost)));
+            par[pl.tau_Bs] = fmin(cc.eps3, fmax(cc.eps2, (s_gam[draw++] * (1.0 / Bpost))));
         }
         double* alp = cur + B + p;
         double* gam = cur + B;
@@ -498,32 +524,32 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
             double s = 0.0;
             for (int a1 = 0; a1 < L; ++a1) for (int a2 = 0; a2 < L; ++a2)
                 s += alp[cc.td_cols[kk][a1]] * par[pl.Tau_a_pen + cc.td_cols[kk][a1] + cc.td_cols[kk][a2] * A] * alp[cc.td_cols[kk][a2]];
-            const double tv = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_tau_td, 1.0 / (cc.B_tau_td + 0.5 * s))));
+            const double tv = fmin(cc.eps3, fmax(cc.eps2, (s_gam[draw++] * (1.0 / (cc.B_tau_td + 0.5 * s)))));
             par[pl.tau_td + kk] = tv;
             for (int a1 = 0; a1 < L; ++a1) for (int a2 = 0; a2 < L; ++a2)
                 par[pl.Tau_a + cc.td_cols[kk][a1] + cc.td_cols[kk][a2] * A] = tv * par[pl.Tau_a_pen + cc.td_cols[kk][a1] + cc.td_cols[kk][a2] * A];
         }
         if (cc.shrink_gammas) {
             for (int k1 = 0; k1 < p; ++k1) {
-                const double v = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_phi_g, 1.0 / (cc.B_phi_g + 0.5 * par[pl.tau_g] * gam[k1] * gam[k1]))));
+                const double v = fmin(cc.eps3, fmax(cc.eps2, (s_gam[draw++] * (1.0 / (cc.B_phi_g + 0.5 * par[pl.tau_g] * gam[k1] * gam[k1])))));
                 par[pl.phi_g + k1] = v; par[pl.Tau_g + k1 + k1 * p] = v;
             }
             const double s = quad_form_dev(gam, nullptr, par + pl.Tau_g, p);
-            par[pl.tau_g] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_tau_g, 1.0 / (cc.B_tau_g + 0.5 * s))));
+            par[pl.tau_g] = fmin(cc.eps3, fmax(cc.eps2, (s_gam[draw++] * (1.0 / (cc.B_tau_g + 0.5 * s)))));
         }
         if (cc.shrink_alphas) {
             for (int k2 = 0; k2 < A; ++k2) {
                 const double Bp = (cc.double_gamma_alphas ? par[pl.nu_a + k2] : cc.B_phi_a) + 0.5 * par[pl.tau_a] * alp[k2] * alp[k2];
-                const double v = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_phi_a, 1.0 / Bp)));
+                const double v = fmin(cc.eps3, fmax(cc.eps2, (s_gam[draw++] * (1.0 / Bp))));
                 par[pl.phi_a + k2] = v; par[pl.Tau_a + k2 + k2 * A] = v;
             }
             const double s = quad_form_dev(alp, nullptr, par + pl.Tau_a, A);
             const double Bp = (cc.double_gamma_alphas ? par[pl.xi_a] : cc.B_tau_a) + 0.5 * s;
-            par[pl.tau_a] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_tau_a, 1.0 / Bp)));
+            par[pl.tau_a] = fmin(cc.eps3, fmax(cc.eps2, (s_gam[draw++] * (1.0 / Bp))));
             if (cc.double_gamma_alphas) {
                 for (int k2 = 0; k2 < A; ++k2)
-                    par[pl.nu_a + k2] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_nu_a, 1.0 / (cc.B_nu_a + par[pl.phi_a + k2]))));
-                par[pl.xi_a] = fmin(cc.eps3, fmax(cc.eps2, rgamma_dev(cc.seed, cc.chain_id, draw++, iter, cc.Apost_xi_a, 1.0 / (cc.B_xi_a + par[pl.tau_a]))));
+                    par[pl.nu_a + k2] = fmin(cc.eps3, fmax(cc.eps2, (s_gam[draw++] * (1.0 / (cc.B_nu_a + par[pl.phi_a + k2])))));
+                par[pl.xi_a] = fmin(cc.eps3, fmax(cc.eps2, (s_gam[draw++] * (1.0 / (cc.B_xi_a + par[pl.tau_a])))));
             }
         }
         // ---- kept iterations (:836-851; 0-based iter against the 1-based keep sequence) ----
@@ -564,7 +590,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         s_next_iter = iter + 1;
     }
     __syncthreads();
-    make_proposal(mm, pl, cc, par, s_next_iter, tid, blockDim.x, s_z);
+    make_proposal(mm, pl, cc, par, s_next_iter, tid, blockDim.x, s_z, /*have_z=*/true);   // normals of iter + 1 drawn above
     if (a.use_smem) {
         __syncthreads();
         for (int j = tid; j < pl.block_par; j += blockDim.x) gpar[j] = s_par[j];
