@@ -111,7 +111,7 @@ typedef struct jmb_svft_control {
 
 typedef struct jmb_svft_out {
     double* modes;       /* n x q      modes.b (:303) */
-    double* hessians;    /* q x q x n  opt$hessian (:304-305) */
+    double* hessians;    /* q x q x n  opt$hessian (:304-305); may be NULL in jmb_survfitJM (only Vars.b / invVars.b use it) */
     int32_t* convergence;/* [n] optim()$convergence: 0, 1 (maxit reached); 10 + x: could not be started / not PD */
     int32_t* counts;     /* 2 x n      optim()$counts (function, gradient) */
     double* summaries;   /* L x 4 x n  Mean, Median, Lower, Upper (:406-412); NaN beyond n_horizons[i] */

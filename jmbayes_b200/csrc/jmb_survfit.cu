@@ -399,7 +399,8 @@ static int run(jmb_svft_handle h, const jmb_svft_params* pm, const jmb_svft_para
     if (!h || !ct || !out) return fail("jmb_svft: null argument");
     if (do_modes && (!pm || pm->M < 1)) return fail("jmb_svft: posterior means required");
     if (do_sample && !pd) return fail("jmb_svft: posterior draws required");
-    if (!out->modes || !out->hessians) return fail("jmb_svft: out->modes and out->hessians are required");
+    if (!out->modes || (!out->hessians && !(do_modes && do_sample)))
+        return fail("jmb_svft: out->modes is required; out->hessians may be NULL only for jmb_survfitJM (it is internal there)");
     if (do_sample && !out->summaries) return fail("jmb_svft: out->summaries is required");
     if (!(ct->parscale > 0.0) || !(ct->scale > 0.0) || !(ct->df > 0.0) || ct->maxit <= 0 || !(ct->cd_eps > 0.0) || !(ct->ndeps > 0.0))
         return fail("jmb_svft: bad control");
@@ -514,7 +515,7 @@ static int run(jmb_svft_handle h, const jmb_svft_params* pm, const jmb_svft_para
         tmp.resize((size_t)n * q);
         CU(cudaMemcpy(tmp.data(), h->d_modes, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
         for (int i = 0; i < n; ++i) for (int j = 0; j < q; ++j) out->modes[i + (size_t)j * n] = tmp[(size_t)i * q + j];
-        CU(cudaMemcpy(out->hessians, h->d_hess, sizeof(double) * (size_t)n * q * q, cudaMemcpyDeviceToHost));
+        if (out->hessians) CU(cudaMemcpy(out->hessians, h->d_hess, sizeof(double) * (size_t)n * q * q, cudaMemcpyDeviceToHost));
         if (out->counts) CU(cudaMemcpy(out->counts, h->d_counts, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
     }
     if (out->convergence) {

@@ -137,7 +137,7 @@ def marshal_control(control: dict | None = None):
     return s
 
 
-def alloc_out(n, q, L, M, full=True, modes=None, hessians=None):
+def alloc_out(n, q, L, M, full=True, modes=None, hessians=None, want_hessians=True):
     bufs = dict(
         modes=np.zeros((n, q), order="F") if modes is None else np.asfortranarray(np.array(modes, dtype=np.float64)),
         hessians=np.zeros((q, q, n), order="F") if hessians is None else np.asfortranarray(np.array(hessians, dtype=np.float64)),
@@ -147,6 +147,8 @@ def alloc_out(n, q, L, M, full=True, modes=None, hessians=None):
         bufs["full"] = np.full((L, M, n), np.nan, order="F")
     o = SvftOut()
     for name, a in bufs.items():
+        if name == "hessians" and not want_hessians:
+            continue
         setattr(o, name, a.ctypes.data_as(c_int32_p if a.dtype == np.int32 else c_double_p))
     return o, bufs
 
@@ -229,11 +231,12 @@ class SurvFit:
         del k
         return self._result(bufs)
 
-    def survfitJM(self, post_means: dict, draws: dict, control: dict | None = None, full: bool = True):
-        """The whole per-subject loop of survfitJM.mvJMbayes (:277-414)."""
+    def survfitJM(self, post_means: dict, draws: dict, control: dict | None = None, full: bool = True, hessians: bool = True):
+        """The whole per-subject loop of survfitJM.mvJMbayes (:277-414).  ``hessians=False``: opt$hessian stays on the
+        device (survfitJM itself only uses it for Vars.b / invVars.b)."""
         pm, k1 = marshal_params(post_means)
         pd, k2 = marshal_params(draws)
-        out, bufs = alloc_out(self.n, self.q, self.L, pd.M, full=full)
+        out, bufs = alloc_out(self.n, self.q, self.L, pd.M, full=full, want_hessians=hessians)
         ct = marshal_control(control)
         _check(_lib().jmb_survfitJM(self._h, C.byref(pm), C.byref(pd), C.byref(ct), C.byref(out)))
         del k1, k2
