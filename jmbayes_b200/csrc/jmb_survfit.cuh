@@ -646,7 +646,10 @@ struct SvEvalGeneric {
         return sv_eval_generic(d, L, rec, 0, true, sb, sp, lane, gmask);
     }
     __device__ __forceinline__ void full2c(const double* rec, const double* sbA, const double* sbB, const double* sp, int lane,
-                                           unsigned gmask, double& vA, double& vB) const { full2(rec, sbA, sbB, sp, lane, gmask, vA, vB); }
+                                           unsigned gmask, double& vA, double& vB) const {
+        if (sbA == sbB) { vA = sv_eval_generic(d, L, rec, 0, true, sbA, sp, lane, gmask); vB = vA; }
+        else full2(rec, sbA, sbB, sp, lane, gmask, vA, vB);
+    }
     // two points on block 0 / two blocks at one point: the generic flavour simply evaluates twice
     __device__ __forceinline__ void full2(const double* rec, const double* sbA, const double* sbB, const double* sp, int lane,
                                           unsigned gmask, double& vA, double& vB) const {
@@ -756,9 +759,11 @@ __device__ __forceinline__ void sv_modes_run(const int q, const SvArgs& a, Eval&
         ret = r; nev = 2 * n; st = ST_GRAD;
     };
     bool finished = false;                           // no more subjects for this group
+    int it = 0, nit = 0;                             // pass of the posted request / passes it needs
     for (;;) {
-        // ---- control: consume `val` (or grad[]), run until the next request is posted ----
-        bool posted = finished;
+        // ---- control: when this group's request is complete, consume `val` (or grad[]) and post the next one; the other
+        //      group of the warp is not waited for (requests are 1 or q passes long and rarely aligned) ----
+        bool posted = finished || it < nit;
         while (!posted) {
             switch (st) {
             case ST_FETCH: {
@@ -938,29 +943,28 @@ __device__ __forceinline__ void sv_modes_run(const int q, const SvArgs& a, Eval&
             }
             }
         }
-        // ---- evaluation: both groups of the warp together; a gradient request evaluates the two points of each
-        //      central difference x +- ex e_i (R/cd.R:5-10) in one pass ----
-        const int nit = (nev > 1) ? nev / 2 : nev;
-        const int nmax = max(nit, __shfl_xor_sync(0xFFFFFFFFu, nit, 16));
-        if (nmax == 0) break;
-        for (int it = 0; it < nmax; ++it) {
-            const bool act = it < nit;
-            if (act && nev > 1 && own) {
+        if (it >= nit) { nit = (nev > 1) ? nev / 2 : nev; it = 0; }
+        if (__all_sync(0xFFFFFFFFu, finished)) break;
+        // ---- one evaluation pass.  A gradient request evaluates the two points x +- ex e_i of a central difference
+        //      (R/cd.R:5-10) in one pass; a single value goes through the same two-slot code (both slots on the point), so
+        //      that the two groups of the warp stay converged whatever each of them is asking for ----
+        if (!finished) {
+            const bool grad_req = nev > 1;
+            if (grad_req && own) {
                 double xa = x[lane], xb2 = xa;
                 if (lane == it) { const double ex = eps * (fabs(xa) + eps); xb2 = xa - ex; xa = xa + ex; }
                 btry[lane] = xa; bt2[lane] = xb2;
             }
-            __syncwarp();
-            if (act) {
-                if (nev > 1) {
-                    double vA, vB;
-                    eval.full2c(rec, btry, bt2, sp, lane, gmask, vA, vB);
-                    if (lane == 0) grad[it] = (((0.0 - vA) - (0.0 - vB)) / (btry[it] - bt2[it])) * ps;   // diff.f / diff.x, fmingr scaling
-                } else {
-                    val = eval.full0(rec, btry, sp, lane, gmask);
-                }
+            __syncwarp(gmask);
+            double vA, vB;
+            eval.full2c(rec, btry, grad_req ? bt2 : btry, sp, lane, gmask, vA, vB);
+            if (grad_req) {
+                if (lane == 0) grad[it] = (((0.0 - vA) - (0.0 - vB)) / (btry[it] - bt2[it])) * ps;   // diff.f / diff.x, fmingr scaling
+            } else {
+                val = vA;
             }
-            __syncwarp();
+            __syncwarp(gmask);
+            it += 1;
         }
     }
 }
