@@ -969,35 +969,79 @@ __device__ __forceinline__ void sv_modes_run(const int q, const SvArgs& a, Eval&
     }
 }
 
-// per-subject set-up of the sampler by the control lane: invVars.b = hessian / scale, Vars.b = scale * solve(hessian)
-// (:304-305), eigen(Vars.b) for rmvt (R/rmvt.R) and dmvt (R/dmvt.R).  Returns 1 when the Hessian is unusable.
-__device__ __noinline__ int sv_sample_setup(const SvArgs& a, const int n, SvG& G, const long long s) {
-    for (int j = 0; j < n; ++j) G.mode[j] = a.modes[s * n + j];
-    for (int j = 0; j < n * n; ++j) G.hess[j] = a.hess[s * n * n + j];
-    bool bad = false;
-    for (int j = 0; j < n; ++j) if (!isfinite(G.mode[j])) bad = true;
-    for (int j = 0; j < n * n; ++j) {
-        if (!isfinite(G.hess[j])) bad = true;
-        G.invV[j] = G.hess[j] / a.c.scale;
-        G.Wa[j] = G.hess[j];
+// per-subject set-up of the sampler: invVars.b = hessian / scale, Vars.b = scale * solve(hessian) (:304-305) and
+// eigen(Vars.b) for rmvt (R/rmvt.R) and dmvt (R/dmvt.R).  The inverse is taken by the control lane; the Jacobi rotations and
+// the two factor matrices are spread over the lanes of the group (lane k owns row / column element k of each update, so
+// every element sees the arithmetic of the serial algorithm in oracle/jmb_oracle_svft.c).  Returns 1 when the Hessian is
+// unusable (uniform over the group).
+__device__ __noinline__ int sv_sample_setup(const SvArgs& a, const int n, SvG& G, const long long s, const int lane,
+                                            const unsigned gmask) {
+    if (lane == 0) {
+        for (int j = 0; j < n; ++j) G.mode[j] = a.modes[s * n + j];
+        for (int j = 0; j < n * n; ++j) G.hess[j] = a.hess[s * n * n + j];
+        bool bad = false;
+        for (int j = 0; j < n; ++j) if (!isfinite(G.mode[j])) bad = true;
+        for (int j = 0; j < n * n; ++j) {
+            if (!isfinite(G.hess[j])) bad = true;
+            G.invV[j] = G.hess[j] / a.c.scale;
+            G.Wa[j] = G.hess[j];
+        }
+        if (!bad && sv_inverse(G.Wa, n, G.Wb)) bad = true;
+        if (!bad)
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) G.Wa[i + j * n] = 0.5 * (G.Wb[i + j * n] * a.c.scale + G.Wb[j + i * n] * a.c.scale);
+        G.ic[IC_BAD] = bad ? 1 : 0;
     }
-    if (!bad && sv_inverse(G.Wa, n, G.Wb)) bad = true;
-    if (!bad) {
-        for (int i = 0; i < n; ++i)
-            for (int j = 0; j < n; ++j) G.Wa[i + j * n] = 0.5 * (G.Wb[i + j * n] * a.c.scale + G.Wb[j + i * n] * a.c.scale);
-        sv_eigen_sym(G.Wa, n, G.X, G.Wb);            // values -> X, vectors -> Wb
-        if (!(G.X[n - 1] >= -1e-06 * fabs(G.X[0]))) bad = true;     // dmvt: "'Sigma' is not positive definite"
-        for (int j = 0; j < n; ++j) if (!(G.X[j] > 0.0)) bad = true;
+    __syncwarp(gmask);
+    if (G.ic[IC_BAD]) return 1;
+    // eigen(S, symmetric = TRUE): cyclic Jacobi, 12 sweeps (sv_eigen_sym), rotations applied by lane k to element k
+    double* am = G.Wa; double* vec = G.Wb; double* val = G.X;
+    const bool own = lane < n;
+    if (own) for (int j = 0; j < n; ++j) vec[lane + j * n] = (lane == j) ? 1.0 : 0.0;
+    __syncwarp(gmask);
+    for (int sweep = 0; sweep < 12; ++sweep)
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = am[p + q * n], app = am[p + p * n], aqq = am[q + q * n];
+                if (fabs(apq) <= 1e-20 * (fabs(app) + fabs(aqq))) continue;
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                __syncwarp(gmask);                   // everybody has read the pivot entries
+                if (own) { const double x = am[lane + p * n], y = am[lane + q * n]; am[lane + p * n] = c * x - sn * y; am[lane + q * n] = sn * x + c * y; }
+                __syncwarp(gmask);
+                if (own) { const double x = am[p + lane * n], y = am[q + lane * n]; am[p + lane * n] = c * x - sn * y; am[q + lane * n] = sn * x + c * y; }
+                if (own) { const double x = vec[lane + p * n], y = vec[lane + q * n]; vec[lane + p * n] = c * x - sn * y; vec[lane + q * n] = sn * x + c * y; }
+                __syncwarp(gmask);
+            }
+    if (lane == 0) {
+        for (int j = 0; j < n; ++j) val[j] = am[j + j * n];
+        for (int j = 0; j < n - 1; ++j) {
+            int best = j;
+            for (int l = j + 1; l < n; ++l) if (val[l] > val[best]) best = l;
+            if (best != j) {
+                double t = val[j]; val[j] = val[best]; val[best] = t;
+                for (int k = 0; k < n; ++k) { t = vec[k + j * n]; vec[k + j * n] = vec[k + best * n]; vec[k + best * n] = t; }
+            }
+        }
+        bool bad = false;
+        if (!(val[n - 1] >= -1e-06 * fabs(val[0]))) bad = true;      // dmvt: "'Sigma' is not positive definite"
+        for (int j = 0; j < n; ++j) if (!(val[j] > 0.0)) bad = true;
+        G.ic[IC_BAD] = bad ? 1 : 0;
     }
-    if (bad) return 1;
-    for (int r = 0; r < n; ++r)
+    __syncwarp(gmask);
+    if (G.ic[IC_BAD]) return 1;
+    if (own) {
+        const int r = lane;
         for (int c = 0; c < n; ++c) {
-            G.Af[r + c * n] = G.Wb[r + c * n] * sqrt(G.X[c] > 0.0 ? G.X[c] : 0.0);   // evec * rep(sqrt(pmax(ev, 0)), each = p)
+            G.Af[r + c * n] = vec[r + c * n] * sqrt(val[c] > 0.0 ? val[c] : 0.0);    // evec * rep(sqrt(pmax(ev, 0)), each = p)
             double t = 0.0;
-            for (int k = 0; k < n; ++k) t += G.Wb[r + k * n] * (G.Wb[c + k * n] / G.X[k]);   // evec %*% (t(evec) / ev)
+            for (int k = 0; k < n; ++k) t += vec[r + k * n] * (vec[c + k * n] / val[k]);   // evec %*% (t(evec) / ev)
             G.invS[r + c * n] = t;
         }
-    for (int j = 0; j < n; ++j) { G.b_old[j] = G.mode[j]; G.b_new[j] = G.mode[j]; }
+        G.b_old[r] = G.mode[r]; G.b_new[r] = G.mode[r];
+    }
+    __syncwarp(gmask);
     return 0;
 }
 
@@ -1022,7 +1066,6 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
     const double* sinvS = sAf + qq;
     const double* sinvV = sinvS + qq;
     double* ssc = gbase + (gdn - (IC_N + 1) / 2 - SC_N);
-    volatile int* ic = reinterpret_cast<int*>(gbase + (gdn - (IC_N + 1) / 2));
     SvG G;
     sv_bind(G, gbase, q, a.ps_len);
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -1033,9 +1076,10 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
         if (!__any_sync(0xFFFFFFFFu, have)) break;
         const double* rec = a.rec + a.off[have ? s : 0];
         const int nh = have ? reinterpret_cast<const int*>(rec)[O] : 0;
-        if (have && lane == 0) G.ic[IC_BAD] = sv_sample_setup(a, q, G, s);
+        int bad_subject = 1;
+        if (have) bad_subject = sv_sample_setup(a, q, G, s, lane, gmask);
         __syncwarp();
-        const bool live = have && ic[IC_BAD] == 0;
+        const bool live = have && bad_subject == 0;
         if (have && !live) {                         // unusable Hessian: reported, not propagated
             for (long long k = lane; k < (long long)a.M * a.L; k += kSvG) a.S[s * a.M * a.L + k] = nan;
             if (lane < q) a.b_last[s * q + lane] = nan;
