@@ -346,7 +346,6 @@ extern "C" int jmb_svft_create(const jmb_svft_data* d, int device, jmb_svft_hand
     const char* env = getenv("JMB_SVFT_KERNEL");
     if (env && !strcmp(env, "generic")) h->kernel = 0;
     h->split_horizons = (h->kernel == 1 && sv_is_linear<SvSpecThree>()) || (h->kernel == 2 && sv_is_linear<SvSpecValue>());
-    if (env && !strcmp(env, "fused")) h->split_horizons = false;        // A/B: intervals inside the sampling kernel
     const int groups = JMB_SVFT_THREADS / kSvG;
     const int gd = (sv_group_doubles(q, h->ps_len) + 1) / 2 * 2;
     h->smem = (int)sizeof(double) * groups * gd;

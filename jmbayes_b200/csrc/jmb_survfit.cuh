@@ -221,6 +221,10 @@ __device__ __forceinline__ double sv_logdens(int fam, int link, double y, double
     }
 }
 
+// responses of a binomial outcome that are neither 0 nor 1 (not produced by the reference's factor2numeric, R/extractFrames.R:27-29):
+// kept out of line so that its two logarithms do not sit in the hot instruction stream
+__device__ __noinline__ double sv_binom_general(double y, double pr) { return y * log(pr) + (1.0 - y) * log(1.0 - pr); }
+
 // sv_logdens with E = exp(eta) supplied by the caller (the same call, hoisted out of the family branches)
 __device__ __forceinline__ double sv_logdens_e(int fam, int link, double y, double eta, double E, double inv_sigma) {
     if (fam == JMB_FAM_GAUSSIAN) {
@@ -237,7 +241,7 @@ __device__ __forceinline__ double sv_logdens_e(int fam, int link, double y, doub
             const bool dead_inf = one ? (pr == 1.0) : (pr == 0.0);
             return dead_inf ? __longlong_as_double(0x7ff8000000000000LL) : ld;
         }
-        return y * log(pr) + (1.0 - y) * log(1.0 - pr);
+        return sv_binom_general(y, pr);
     } else {
         if (link == JMB_LINK_LOG) {
             double ld = y * eta - E;
@@ -565,6 +569,11 @@ __device__ __forceinline__ double sv_eval_static(const double* __restrict__ rec,
     return out[0];
 }
 
+// rare path of the chi-square draw (shape < 1, or four Marsaglia-Tsang rejections in a row): out of the hot instruction stream
+__device__ __noinline__ double sv_rgamma_slow(uint32_t seed, uint32_t key, uint32_t gid, uint32_t m, double shape, double scale) {
+    return rgamma_dev(seed, key, gid, m, shape, scale);
+}
+
 // ---- small dense helpers of the control thread (same algorithms as oracle/jmb_oracle_svft.c) ---------------
 // solve(A): Gauss-Jordan with partial pivoting; a is destroyed; returns 1 when singular
 __device__ inline int sv_inverse(double* a, int n, double* inv) {
@@ -635,6 +644,7 @@ __device__ inline void sv_eigen_sym(double* a, int n, double* val, double* vec) 
 #endif
 
 struct SvEvalGeneric {
+    static constexpr bool kSplit = false;            // the horizon integrals stay inside the sampling kernel
     const SvDesc& d; const SvLayout& L;
     __device__ __forceinline__ double operator()(const double* rec, int blk, bool full, const double* sb, const double* sp,
                                                  int lane, unsigned gmask) const {
@@ -671,6 +681,7 @@ struct SvEvalGeneric {
 };
 template <class Spec>
 struct SvEvalStatic {
+    static constexpr bool kSplit = sv_is_linear<Spec>();   // the horizon integrals run in jmb_svft_horizons<Spec>
     SvHazCache<Spec> hc;
     __device__ __forceinline__ double operator()(const double* rec, int blk, bool full, const double* sb, const double* sp,
                                                  int lane, unsigned gmask) const {
@@ -1126,7 +1137,7 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
                         const int first = __ffs(hit) - 1;
                         if (lane == first) ssc[SC_W] = xg * 2.0;
                     } else if (lane == 4) {
-                        ssc[SC_W] = rgamma_dev(a.c.seed, kSvKey, gid, (uint32_t)m, shape, 2.0);   // shape < 1 or four rejections
+                        ssc[SC_W] = sv_rgamma_slow(a.c.seed, kSvKey, gid, (uint32_t)m, shape, 2.0);   // shape < 1 or four rejections
                     }
                 }
                 const double* src = a.par_draws + (size_t)m * a.ps_len;
@@ -1163,27 +1174,32 @@ __device__ __forceinline__ void sv_sample_run(const int q, const int O, const Sv
             __syncwarp();
             double cum = 0.0, mine = 0.0;            // survival on each prediction interval (:378-395)
             double* Srow = a.S + ((size_t)(have ? s : 0) * a.M + m) * a.L;
-            if (live) eval.begin_horizons(rec, sb_new, sp);
-            const bool split = a.Cbuf != nullptr;    // the horizon integrals run in jmb_svft_horizons from the coefficients
-            if (split && have && lane == 0) {
-                double* cdst = a.Cbuf + ((size_t)s * a.M + m) * a.ncoef;
-                if (live) eval.store_coefs(cdst); else for (int j = 0; j < a.ncoef; ++j) cdst[j] = nan;
-            }
-            for (int l = 0; l < (split ? 0 : nh_max); l += 2) {    // two intervals per pass
-                if (live && l < nh) {
-                    const bool two = l + 1 < nh;
-                    double v0, v1;
-                    eval.block2h(rec, l + 1, two ? l + 2 : l + 1, sb_new, sp, lane, gmask, v0, v1);
-                    cum += v0;
-                    if (lane == (l & (kSvG - 1))) mine = a.c.log ? v0 : cum;
-                    if (two) {
-                        cum += v1;
-                        if (lane == ((l + 1) & (kSvG - 1))) mine = a.c.log ? v1 : cum;
+            constexpr bool split = Eval::kSplit;      // the horizon integrals run in jmb_svft_horizons from the coefficients
+            if constexpr (split) {
+                if (have && a.Cbuf != nullptr) {
+                    if (live) eval.begin_horizons(rec, sb_new, sp);
+                    if (lane == 0) {
+                        double* cdst = a.Cbuf + ((size_t)s * a.M + m) * a.ncoef;
+                        if (live) eval.store_coefs(cdst); else for (int j = 0; j < a.ncoef; ++j) cdst[j] = nan;
                     }
                 }
-                if (((l + 1) & (kSvG - 1)) == kSvG - 1 || l + 2 >= nh_max) {  // 16 intervals: exp(cumsum(logS)) by lane
-                    const int ll = (l & ~(kSvG - 1)) + lane;
-                    if (live && ll < nh) Srow[ll] = a.c.log ? mine : exp(mine);
+            } else {
+                for (int l = 0; l < nh_max; l += 2) {    // two intervals per pass
+                    if (live && l < nh) {
+                        const bool two = l + 1 < nh;
+                        double v0, v1;
+                        eval.block2(rec, l + 1, two ? l + 2 : l + 1, sb_new, sp, lane, gmask, v0, v1);
+                        cum += v0;
+                        if (lane == (l & (kSvG - 1))) mine = a.c.log ? v0 : cum;
+                        if (two) {
+                            cum += v1;
+                            if (lane == ((l + 1) & (kSvG - 1))) mine = a.c.log ? v1 : cum;
+                        }
+                    }
+                    if (((l + 1) & (kSvG - 1)) == kSvG - 1 || l + 2 >= nh_max) {  // 16 intervals: exp(cumsum(logS)) by lane
+                        const int ll = (l & ~(kSvG - 1)) + lane;
+                        if (live && ll < nh) Srow[ll] = a.c.log ? mine : exp(mine);
+                    }
                 }
             }
             if (live) {
