@@ -37,7 +37,13 @@ WORKLOADS = {
     # survfitJM dynamic predictions (BASELINE config 5): M = 200 draws x L = 10 horizons per subject; one "step" =
     # the whole per-subject loop (mode search + MH over the draws + horizon integrals + summaries) for every subject
     "config5": ("config4", 25000),
+    # posterior summaries of the random effects of the config-4 shard: 125 000 subjects x q = 6 series of
+    # M = 500 kept draws, the ten statistics of mvJointModelBayes()$statistics per series; one "step" = all series
+    "summaries": ("config4", 125000),
 }
+STATS_M, STATS_Q = 500, 6
+STATS_METRIC = "series/sec of mvJointModelBayes posterior summaries (ten statistics per series of M=500 kept draws)"
+STATS_UNIT = "series/s"
 SVFT_M, SVFT_L = 200, 10
 SVFT_METRIC = "subject-draws/sec of survfitJM dynamic predictions (M=200 draws x L=10 horizons per subject)"
 SVFT_UNIT = "subject-draws/s"
@@ -496,8 +502,145 @@ def run_config5(args):
         dist.destroy_process_group()
 
 
+def _stats_cpu(S, seed=99):
+    """R's summary_fun is a serial apply(): the restated R code (oracle/oracle_stats.py, NumPy) on one core."""
+    import numpy as np
+    from oracle import oracle_stats
+    rng = np.random.default_rng(seed)
+    X = np.cumsum(rng.normal(size=(S, STATS_M)), axis=1) * 0.05 + rng.normal(size=(S, STATS_M))
+    w = oracle_stats.stand(rng.normal(size=STATS_M))
+    t0 = time.perf_counter()
+    oracle_stats.statistics(X, w)
+    dt = time.perf_counter() - t0
+    return S / dt, dt
+
+
+def run_summaries_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    _, dt0 = _stats_cpu(200)
+    S = int(min(20000, max(200, 200 * 15.0 / max(dt0, 1e-3))))
+    val, dt = _stats_cpu(S)
+    line = {"impl": "reference", "metric": STATS_METRIC, "value": val, "unit": STATS_UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "summaries", "series": S, "M": STATS_M,
+                       "note": "restated summary_fun sweeps (R absent from the image), serial as R's apply()"},
+            "cpu_baseline": {"value": val, "unit": STATS_UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{S} series x {STATS_M} draws, ten statistics, NumPy restatement ({dt:.1f} s)"},
+            "e2e": {"value": val, "unit": STATS_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_summaries(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from jmbayes_b200 import build, summaries
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not os.path.exists(build.LIB):
+        raise RuntimeError("libjmb200.so missing: run __graft_entry__.build()")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the hot path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    n = args.n_per_gpu or WORKLOADS["summaries"][1]
+    S, M = n * STATS_Q, STATS_M
+    steps, warmup = min(args.steps, 10), max(min(args.warmup, 3), 3)
+    # synthetic kept draws of b (n x q x M, series contiguous): autocorrelated chains around subject-specific centres;
+    # 3 GB per GPU, larger than L2, so no flush is needed between steps
+    g = torch.Generator(device=dev).manual_seed(7000 + rank)
+    x = torch.empty((M, S), dtype=torch.float64, device=dev)
+    centre = torch.randn(S, dtype=torch.float64, device=dev, generator=g)
+    rho = torch.rand(S, dtype=torch.float64, device=dev, generator=g) * 0.8
+    cur = torch.randn(S, dtype=torch.float64, device=dev, generator=g)
+    for m in range(M):
+        cur = rho * cur + torch.randn(S, dtype=torch.float64, device=dev, generator=g)
+        x[m] = centre + 0.5 * cur
+    w = summaries.stand(np.random.default_rng(7).normal(size=M))
+    outs = {name: torch.empty(S * (2 if name in ("CIs", "wCIs") else 1), dtype=torch.float64, device=dev) for name in summaries.NAMES}
+    ptrs = {k: v.data_ptr() for k, v in outs.items()}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        summaries.device_statistics(x.data_ptr(), S, M, 1, S, w, ptrs, device=local)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_ms = 0.0
+    for _ in range(steps):
+        dev_ms += summaries.device_statistics(x.data_ptr(), S, M, 1, S, w, ptrs, device=local)   # CUDA events on the launch stream
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e: the same series from pinned host memory through the public call, chunked copies overlapped with the kernel
+    xh = torch.empty((M, S), dtype=torch.float64).pin_memory()
+    xh.copy_(x)
+    torch.cuda.synchronize()
+    xn = xh.numpy()
+    summaries.series_statistics(xn, S, M, 1, S, w, device=local)
+    e2e_steps = max(1, min(steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        summaries.series_statistics(xn, S, M, 1, S, w, device=local)
+    wall = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([dev_ms, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall = float(t[0].item()), float(t[1].item())
+    S_total = S * world
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = 8.0 * (M + 12)
+    achieved = alg * S / (dev_ms / steps * 1e-3) / 1e9
+    line = {
+        "metric": STATS_METRIC, "value": S_total * steps / (dev_ms * 1e-3), "unit": STATS_UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "summaries", "what": "mcmc$b of the config-4 shard: n x q x M kept draws, series contiguous",
+                   "subjects_per_gpu": n, "q": STATS_Q, "series_per_gpu": S, "series_total": S_total, "M": M,
+                   "parallelism": f"series-shards x{world} (no collective)", "l2": "inputs (3 GB per GPU) larger than L2"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "jmb_stats_kernel", "kernel_ms": dev_ms / steps, "alg_bytes_per_series": alg,
+                     "note": "each series is read once (M doubles) and 12 doubles are written; the time goes to the warp-level sort "
+                             "and the binned kernel density of modes() (fp64 issue from shared memory), not to HBM; see profiles/"},
+        "e2e": {"value": S_total / wall, "unit": STATS_UNIT, "h2d_bytes_per_step": 8.0 * M * S, "d2h_bytes_per_step": 96.0 * S,
+                "what": "jmb_mcmc_statistics() through the C ABI on pinned host draws: chunked H2D overlapped with the kernel, "
+                        "all ten statistics D2H, wall clock"},
+        "gpu_launches": steps, "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, dt0 = _stats_cpu(200)
+        Sc = int(min(20000, max(200, 200 * 12.0 / max(dt0, 1e-3))))
+        val, dt = _stats_cpu(Sc)
+        line["cpu_baseline"] = {"value": val, "unit": STATS_UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{Sc} series x {M} draws, ten statistics, NumPy restatement of the serial R sweeps ({dt:.1f} s)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
+    if args.workload == "summaries":
+        return run_summaries_reference(args) if args.impl == "reference" else run_summaries(args)
     if args.workload == "config5":
         return run_config5_reference(args) if args.impl == "reference" else run_config5(args)
     if args.impl == "reference":

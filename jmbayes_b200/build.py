@@ -15,8 +15,9 @@ UNITS = {
     "jmb200.cu": ["jmb_kernels.cuh", "jmb_device.cuh", "jmb_model.h", "jmb_step_static.cuh", "jmb_host.h"],
     "jmb_survfit.cu": ["jmb_survfit.cuh", "jmb_device.cuh", "jmb_model.h", "jmb_host.h"],
     "jmb_laplace.cu": ["jmb_host.h"],
+    "jmb_summaries.cu": ["jmb_host.h"],
 }
-HEADERS = [os.path.join(ROOT, "include", f) for f in ("jmb200.h", "jmb200_survfit.h")]
+HEADERS = [os.path.join(ROOT, "include", f) for f in ("jmb200.h", "jmb200_survfit.h", "jmb200_summaries.h")]
 SOURCES = [os.path.join(CSRC, f) for f in UNITS]
 
 

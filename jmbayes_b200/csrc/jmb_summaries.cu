@@ -1,0 +1,419 @@
+// jmb_summaries.cu - posterior summaries of the kept draws (include/jmb200_summaries.h).
+//
+// One warp owns one series (the M kept draws of one scalar of the mcmc list) in shared memory and computes the ten entries
+// of `statistics` (R/mvJointModelBayes.R:959-971) for it: moments, weighted moments, the Yule-Walker spectrum at zero
+// (R/effectiveSize.R), the sort, type-7 and Hmisc "i/(n+1)" quantiles, and the binned kernel density of R/modes.R whose
+// FFT convolution is evaluated here as the direct sum over the occupied cells (the same numbers: the kernel's wrap-around
+// terms fall on empty cells).  A CTA loads the series of its warps together so that global reads are coalesced for both
+// layouts (draws contiguous, or series contiguous as in the n x q x M array of random effects).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/jmb200_summaries.h"
+#include "jmb_host.h"
+
+namespace jmb {
+
+constexpr int kStN = 1024;          // density.default: n = 1000 -> 2^ceiling(log2(n)) cells between lo and up
+constexpr int kStUser = 1000;       // modes(): density(..., n = 1000)
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct StArgs {
+    const double* x; long long S; int M, P, warps; long long sstride, dstride;
+    const double* w;                // weights [M]
+    double sumw, sumwt2, p_lo, p_hi, m_pow; int om;
+    double *mean, *wmean, *mode, *ess, *sd, *wsd, *se, *ci, *wci, *pval;
+};
+
+__device__ __forceinline__ double st_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// quantile(x, p, type = 7) on the sorted keys (stats:::quantile.default)
+__device__ __forceinline__ double st_q7(const double* k, int M, double p) {
+    const double index = (double)(M - 1) * p;
+    const int lo = (int)floor(index), hi = (int)ceil(index);
+    const double h = index - (double)lo;
+    double qs = k[lo];
+    if (index > (double)lo && k[hi] != qs) qs = (1.0 - h) * qs + h * k[hi];
+    return qs;
+}
+
+// doubles of shared memory per warp: [A | Bk] (>= 1024, reused for the density values) | Y | Kn | idx (uint16)
+__host__ __device__ inline int st_warp_doubles(int P) { return (2 * P > 1024 ? 2 * P : 1024) + 2 * 1024 + (P + 3) / 4; }
+
+__global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
+    extern __shared__ double st_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int M = a.M, P = a.P, W = a.warps;
+    double* sw = st_smem;                                       // weights [M] (padded to even)
+    const int wd = st_warp_doubles(P);
+    double* base = st_smem + (M + 1) / 2 * 2 + (size_t)wid * wd;
+    double* A = base;                                           // the series in draw order; later cumulative weights
+    double* Bk = base + P;                                      // sorted keys
+    double* Rb = base;                                          // density on the cells jlo..jhi (overlays A | Bk)
+    double* Y = base + max(2 * P, kStN);                        // BinDist cells
+    double* Kn = Y + kStN;                                      // dnorm(m dk, sd = bw)
+    unsigned short* idx = reinterpret_cast<unsigned short*>(Kn + kStN);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+    for (int j = tid; j < M; j += blockDim.x) sw[j] = a.w[j];
+
+    for (long long tile = blockIdx.x; tile * W < a.S; tile += gridDim.x) {
+        const long long s0 = tile * W;
+        __syncthreads();                                         // the previous tile's series are no longer read
+        if (a.dstride == 1) {                                    // draws contiguous: lanes run over the draws of one series
+            for (int e = tid; e < W * M; e += blockDim.x) {
+                const int sl = e / M, m = e - sl * M;
+                if (s0 + sl < a.S) st_smem[(M + 1) / 2 * 2 + (size_t)sl * wd + m] = a.x[(s0 + sl) * a.sstride + m];
+            }
+        } else {                                                 // series contiguous: W neighbours of one draw per read
+            for (int e = tid; e < W * M; e += blockDim.x) {
+                const int m = e / W, sl = e - m * W;
+                if (s0 + sl < a.S) st_smem[(M + 1) / 2 * 2 + (size_t)sl * wd + m] = a.x[(s0 + sl) * a.sstride + (long long)m * a.dstride];
+            }
+        }
+        __syncthreads();
+        const long long s = s0 + wid;
+        if (wid >= W || s >= a.S) continue;
+
+        // ---- moments: mean (two passes, as R's mean), var, weighted mean / variance (cov.wt), computeP -------------------
+        double t0 = 0.0;
+        for (int m = lane; m < M; m += 32) t0 += A[m];
+        double mean = st_sum(t0) / (double)M;
+        t0 = 0.0;
+        for (int m = lane; m < M; m += 32) t0 += A[m] - mean;
+        mean += st_sum(t0) / (double)M;
+        double ss = 0.0, swx = 0.0, cnt = 0.0, sty = 0.0;
+        const double tb = 0.5 * (double)(M + 1);
+        for (int m = lane; m < M; m += 32) {
+            const double v = A[m], d = v - mean;
+            ss += d * d; swx += v * sw[m]; cnt += (v >= 0.0) ? 1.0 : 0.0; sty += ((double)(m + 1) - tb) * d;
+        }
+        const double var = st_sum(ss) / (double)(M - 1);
+        const double wmean = st_sum(swx);
+        cnt = st_sum(cnt);
+        const double center = wmean / a.sumw;
+        double sw2 = 0.0;
+        for (int m = lane; m < M; m += 32) { const double d = A[m] - center; sw2 += sw[m] * d * d; }
+        const double wvar = st_sum(sw2) / a.sumw / (1.0 - a.sumwt2);
+        const double above = cnt / (double)M, below = ((double)M - cnt) / (double)M;
+
+        // ---- effectiveSize: residuals of the linear trend, autocovariances, Levinson recursion, AIC order ----------------
+        const double beta = st_sum(sty) / ((double)M * ((double)M * (double)M - 1.0) / 12.0);
+        double rs = 0.0;
+        for (int m = lane; m < M; m += 32) { const double r = (A[m] - mean) - beta * ((double)(m + 1) - tb); rs += r * r; }
+        const double sd_res = sqrt(st_sum(rs) / (double)(M - 1));
+        double spec = 0.0;
+        if (sd_res > 1.5e-8) {                                   // identical(all.equal(sd(res), 0), TRUE) is FALSE
+            double r = 0.0;                                      // lane l: autocovariance at lag l (divisor n)
+            if (lane <= a.om) {
+                for (int m = 0; m + lane < M; ++m) r += (A[m] - mean) * (A[m + lane] - mean);
+                r /= (double)M;
+            }
+            double phi = 0.0;                                    // lane j: coefficient j of the current order
+            double v = __shfl_sync(kFull, r, 0);
+            double best = (double)M * log(v) + 2.0, vbest = v, sumphi = 0.0;
+            int order = 0;
+            for (int l = 1; l <= a.om; ++l) {
+                const bool in = lane >= 1 && lane < l;
+                const double rj = __shfl_sync(kFull, r, (l - lane) & 31);
+                const double acc = __shfl_sync(kFull, r, l) - st_sum(in ? phi * rj : 0.0);
+                const double k = acc / v;
+                const double prev = __shfl_sync(kFull, phi, (l - lane) & 31);
+                phi = in ? phi - k * prev : (lane == l ? k : phi);
+                v *= 1.0 - k * k;
+                const double aic = (double)M * log(v) + 2.0 * (double)l + 2.0;
+                const double sp = st_sum((lane >= 1 && lane <= l) ? phi : 0.0);
+                if (aic < best) { best = aic; order = l; vbest = v; sumphi = sp; }
+            }
+            const double var_pred = vbest * (double)M / (double)(M - (order + 1));
+            spec = var_pred / ((1.0 - sumphi) * (1.0 - sumphi));
+        }
+        const double ess = (spec == 0.0) ? 0.0 : (double)M * var / spec;
+
+        // ---- sort (bitonic, keys with their draw index) ------------------------------------------------------------------
+        for (int k = lane; k < P; k += 32) { Bk[k] = k < M ? A[k] : inf; idx[k] = (unsigned short)k; }
+        __syncwarp();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < P / 2; t += 32) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+                    const bool up = (i & k) == 0;
+                    const double x0 = Bk[i], x1 = Bk[p];
+                    if ((x0 > x1) == up) {
+                        Bk[i] = x1; Bk[p] = x0;
+                        const unsigned short i0 = idx[i]; idx[i] = idx[p]; idx[p] = i0;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        const double q_lo = st_q7(Bk, M, a.p_lo), q_hi = st_q7(Bk, M, a.p_hi);
+        const double iqr = st_q7(Bk, M, 0.75) - st_q7(Bk, M, 0.25);
+
+        // ---- Hmisc::wtd.quantile(type = "i/(n+1)"): cumulative weights in sorted order, knots at the last of tied keys ----
+        const int C = P / 32;                                    // contiguous elements per lane
+        double* cum = A;
+        {
+            double part = 0.0;
+            for (int k = lane * C; k < (lane + 1) * C; ++k) if (k < M) part += sw[idx[k]];
+            double incl = part;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+            double run = incl - part;
+            for (int k = lane * C; k < (lane + 1) * C; ++k) if (k < M) { run += sw[idx[k]]; cum[k] = run; }
+        }
+        __syncwarp();
+        const double wn1 = cum[M - 1] + 1.0;                     // n + 1, n = sum of the weights
+        double wq[2];
+        {
+            int first_k = P, last_k = -1;                        // first / last knot of this lane's chunk
+            int jge[2] = {P, P}, ilt[2] = {-1, -1};
+            const double pr[2] = {a.p_lo, a.p_hi};
+            for (int k = lane * C; k < (lane + 1) * C; ++k) {
+                if (k >= M || sw[idx[k]] == 0.0) continue;       // zero-weight observations are dropped
+                int k2 = k + 1;
+                while (k2 < M && sw[idx[k2]] == 0.0) ++k2;
+                if (k2 < M && Bk[k2] == Bk[k]) continue;         // wtd.table: tied values are one point
+                first_k = min(first_k, k); last_k = k;
+                const double cdf = cum[k] / wn1;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (cdf >= pr[e]) jge[e] = min(jge[e], k); else ilt[e] = k;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                first_k = min(first_k, __shfl_xor_sync(kFull, first_k, o));
+                last_k = max(last_k, __shfl_xor_sync(kFull, last_k, o));
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    jge[e] = min(jge[e], __shfl_xor_sync(kFull, jge[e], o));
+                    ilt[e] = max(ilt[e], __shfl_xor_sync(kFull, ilt[e], o));
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (last_k < 0) wq[e] = nan;                                   // no positive weight
+                else if (jge[e] >= P) wq[e] = Bk[last_k];                      // approx(rule = 2) beyond the last point
+                else if (ilt[e] < 0) wq[e] = Bk[first_k];                      // between the prepended (0, x[1]) and x[1]
+                else {
+                    const double ci = cum[ilt[e]] / wn1, cj = cum[jge[e]] / wn1, yi = Bk[ilt[e]], yj = Bk[jge[e]];
+                    wq[e] = yi + (yj - yi) * ((pr[e] - ci) / (cj - ci));
+                }
+            }
+        }
+
+        // ---- modes(): density(y, bw = "nrd", adjust = 3, n = 1000), x of the maximum -------------------------------------
+        double mode = nan;
+        const double bw = 3.0 * (1.06 * fmin(sqrt(var), iqr / 1.34) * a.m_pow);
+        const double xmin = Bk[0], xmax = Bk[M - 1];
+        __syncwarp();
+        if (bw > 0.0 && bw < inf) {
+            const double from = xmin - 3.0 * bw, to = xmax + 3.0 * bw, lo = from - 4.0 * bw, up = to + 4.0 * bw;
+            const double xdelta = (up - lo) / (double)(kStN - 1);
+            const double wi = 1.0 / (double)M;
+            for (int k = lane; k < kStN; k += 32) Y[k] = 0.0;
+            __syncwarp();
+            for (int k = lane; k < M; k += 32) {                 // BinDist: the data lie 7 bw inside (lo, up), no edge cases
+                const double xpos = (Bk[k] - lo) / xdelta;
+                const int ix = (int)floor(xpos);
+                const double fx = xpos - (double)ix;
+                atomicAdd(&Y[ix], wi * (1.0 - fx));
+                atomicAdd(&Y[ix + 1], wi * fx);
+            }
+            const int klo = (int)floor((xmin - lo) / xdelta), khi = min(kStN - 1, (int)floor((xmax - lo) / xdelta) + 1);
+            const int jlo = max(0, (int)floor((from - lo) / xdelta) - 1), jhi = min(kStN - 1, (int)floor((to - lo) / xdelta) + 2);
+            const int mmax = max(khi - jlo, jhi - klo);
+            const double dk = 2.0 * (up - lo) / (double)(2 * kStN - 1), cn = 0.3989422804014327 / bw;
+            for (int m = lane; m <= mmax; m += 32) { const double z = (double)m * dk / bw; Kn[m] = cn * exp(-0.5 * z * z); }
+            __syncwarp();
+            for (int j0 = jlo + lane; j0 - lane <= jhi; j0 += 128) {           // four cells per lane share the loads of Y
+                double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+                for (int k = klo; k <= khi; ++k) {
+                    const double y = Y[k];
+                    r0 += y * Kn[min(abs(k - j0), kStN - 1)];
+                    r1 += y * Kn[min(abs(k - j0 - 32), kStN - 1)];
+                    r2 += y * Kn[min(abs(k - j0 - 64), kStN - 1)];
+                    r3 += y * Kn[min(abs(k - j0 - 96), kStN - 1)];
+                }
+                if (j0 <= jhi) Rb[j0 - jlo] = fmax(0.0, r0);
+                if (j0 + 32 <= jhi) Rb[j0 + 32 - jlo] = fmax(0.0, r1);
+                if (j0 + 64 <= jhi) Rb[j0 + 64 - jlo] = fmax(0.0, r2);
+                if (j0 + 96 <= jhi) Rb[j0 + 96 - jlo] = fmax(0.0, r3);
+            }
+            __syncwarp();
+            const double by = (to - from) / (double)(kStUser - 1);
+            double bv = -1.0; int bt = kStUser;
+            for (int t = lane; t < kStUser; t += 32) {            // approx(xords, kords, x) and which.max
+                const double xt = (t == kStUser - 1) ? to : from + (double)t * by;
+                int jj = min(max((int)floor((xt - lo) / xdelta), jlo), jhi - 1);
+                if (jj > jlo && lo + (double)jj * xdelta > xt) --jj;
+                else if (jj < jhi - 1 && lo + (double)(jj + 1) * xdelta <= xt) ++jj;
+                const double xa = lo + (double)jj * xdelta, xb = lo + (double)(jj + 1) * xdelta;
+                const double ya = Rb[jj - jlo], yb = Rb[jj + 1 - jlo];
+                const double val = ya + (yb - ya) * ((xt - xa) / (xb - xa));
+                if (val > bv) { bv = val; bt = t; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(kFull, bv, o);
+                const int ot = __shfl_xor_sync(kFull, bt, o);
+                if (ov > bv || (ov == bv && ot < bt)) { bv = ov; bt = ot; }
+            }
+            mode = (bt == kStUser - 1) ? to : from + (double)bt * by;
+        }
+
+        if (lane == 0) {
+            if (a.mean) a.mean[s] = mean;
+            if (a.wmean) a.wmean[s] = wmean;
+            if (a.mode) a.mode[s] = mode;
+            if (a.ess) a.ess[s] = ess;
+            if (a.sd) a.sd[s] = sqrt(var);
+            if (a.wsd) a.wsd[s] = sqrt(wvar);
+            if (a.se) a.se[s] = sqrt(var / ess);
+            if (a.ci) { a.ci[2 * s] = q_lo; a.ci[2 * s + 1] = q_hi; }
+            if (a.wci) { a.wci[2 * s] = wq[0]; a.wci[2 * s + 1] = wq[1]; }
+            if (a.pval) a.pval[s] = 2.0 * fmin(above, below);
+        }
+    }
+}
+
+}  // namespace jmb
+
+using namespace jmb;
+
+namespace {
+int fail(const std::string& m) { return jmb_set_error(m); }
+}  // namespace
+
+extern "C" int jmb_stand_weights(const double* LogLiks, int32_t M, double* weights) {
+    if (!LogLiks || !weights || M <= 0) return fail("jmb_stand_weights: NULL argument or M <= 0");
+    double mx = -INFINITY;
+    for (int m = 0; m < M; ++m) if (LogLiks[m] > mx) mx = LogLiks[m];             // max(x, na.rm = TRUE)
+    const double upp = mx + std::log((double)M);
+    double s = 0.0;
+    for (int m = 0; m < M; ++m) { weights[m] = std::exp(LogLiks[m] - upp); s += weights[m]; }
+    for (int m = 0; m < M; ++m) weights[m] /= s;
+    return 0;
+}
+
+extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32_t M, int64_t series_stride,
+                                   int64_t draw_stride, const double* weights, const double probs[2], int on_device,
+                                   jmb_stats_out* out, float* kernel_ms) {
+    if (!x || !weights || !probs || !out) return fail("jmb_mcmc_statistics: NULL argument");
+    if (S <= 0) return fail("jmb_mcmc_statistics: S <= 0");
+    if (M < 4 || M > JMB_STATS_MAX_M) return fail("jmb_mcmc_statistics: M outside 4.." + std::to_string(JMB_STATS_MAX_M));
+    if (!(series_stride == 1 && draw_stride >= S) && !(draw_stride == 1 && series_stride >= M))
+        return fail("jmb_mcmc_statistics: layout must be series-contiguous (series_stride = 1, draw_stride >= S) or "
+                    "draw-contiguous (draw_stride = 1, series_stride >= M)");
+    for (int e = 0; e < 2; ++e) if (!(probs[e] >= 0.0 && probs[e] <= 1.0)) return fail("jmb_mcmc_statistics: probs outside [0, 1]");
+    double sumw = 0.0, sumwt2 = 0.0;
+    for (int m = 0; m < M; ++m) {
+        if (!(weights[m] >= 0.0)) return fail("jmb_mcmc_statistics: weights must be non-negative and not NA");
+        sumw += weights[m];
+    }
+    if (!(sumw > 0.0)) return fail("jmb_mcmc_statistics: weights sum to zero");
+    for (int m = 0; m < M; ++m) { const double t = weights[m] / sumw; sumwt2 += t * t; }
+
+    cudaError_t e;
+    std::vector<void*> owned;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> evs;
+    auto cleanup = [&]() {
+        for (void* p : owned) cudaFree(p);
+        for (auto ev : evs) cudaEventDestroy(ev);
+        for (auto s : st) if (s) cudaStreamDestroy(s);
+    };
+#define CUS(call) do { e = (call); if (e != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e); cleanup(); return fail(m_); } } while (0)
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail("jmb_mcmc_statistics: no CUDA device (there is no CPU fallback)");
+    CUS(cudaSetDevice(device));
+    int num_sms = 0;
+    CUS(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+    for (auto& s : st) CUS(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+
+    StArgs a{};
+    a.M = M; a.P = 4; while (a.P < M) a.P <<= 1;
+    a.P = std::max(a.P, 32);
+    a.warps = a.P <= 512 ? 8 : 6;
+    a.sumw = sumw; a.sumwt2 = sumwt2; a.p_lo = probs[0]; a.p_hi = probs[1];
+    a.m_pow = std::pow((double)M, -0.2);
+    a.om = (int)std::min<double>(M - 1, std::floor(10.0 * std::log10((double)M)));
+    const size_t smem = sizeof(double) * ((size_t)(M + 1) / 2 * 2 + (size_t)a.warps * st_warp_doubles(a.P));
+    CUS(cudaFuncSetAttribute(jmb_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    double* d_w = nullptr;
+    CUS(cudaMalloc(&d_w, sizeof(double) * M)); owned.push_back(d_w);
+    CUS(cudaMemcpy(d_w, weights, sizeof(double) * M, cudaMemcpyHostToDevice));
+    a.w = d_w;
+
+    double* host_out[10] = {out->postMeans, out->postwMeans, out->postModes, out->EffectiveSize, out->StDev, out->wStDev,
+                            out->StErr, out->CIs, out->wCIs, out->Pvalues};
+    const int width[10] = {1, 1, 1, 1, 1, 1, 1, 2, 2, 1};
+    double* dev_out[10] = {nullptr};
+    for (int k = 0; k < 10; ++k) {
+        if (!host_out[k]) continue;
+        if (on_device) dev_out[k] = host_out[k];
+        else { CUS(cudaMalloc(&dev_out[k], sizeof(double) * width[k] * S)); owned.push_back(dev_out[k]); }
+    }
+    auto launch = [&](const double* xd, long long s0, long long count, long long sstride, long long dstride, cudaStream_t stream) {
+        StArgs b = a;
+        b.x = xd; b.S = count; b.sstride = sstride; b.dstride = dstride;
+        b.mean = dev_out[0] ? dev_out[0] + s0 : nullptr; b.wmean = dev_out[1] ? dev_out[1] + s0 : nullptr;
+        b.mode = dev_out[2] ? dev_out[2] + s0 : nullptr; b.ess = dev_out[3] ? dev_out[3] + s0 : nullptr;
+        b.sd = dev_out[4] ? dev_out[4] + s0 : nullptr; b.wsd = dev_out[5] ? dev_out[5] + s0 : nullptr;
+        b.se = dev_out[6] ? dev_out[6] + s0 : nullptr; b.ci = dev_out[7] ? dev_out[7] + 2 * s0 : nullptr;
+        b.wci = dev_out[8] ? dev_out[8] + 2 * s0 : nullptr; b.pval = dev_out[9] ? dev_out[9] + s0 : nullptr;
+        const long long tiles = (count + a.warps - 1) / a.warps;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, num_sms));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); evs.push_back(e0); evs.push_back(e1);
+        cudaEventRecord(e0, stream);
+        jmb_stats_kernel<<<grid, 32 * 8, smem, stream>>>(b);
+        cudaEventRecord(e1, stream);
+    };
+
+    if (on_device) {
+        launch(x, 0, S, series_stride, draw_stride, st[0]);
+        CUS(cudaGetLastError());
+    } else {
+        // stream the series through two device buffers: copy of chunk c + 1 overlaps the kernel of chunk c
+        const long long chunk = std::max<long long>(a.warps, std::min<long long>(S, (256LL << 20) / (8LL * M)) / a.warps * a.warps);
+        double* d_x[2] = {nullptr, nullptr};
+        for (auto& p : d_x) { CUS(cudaMalloc(&p, sizeof(double) * chunk * M)); owned.push_back(p); }
+        int c = 0;
+        for (long long s0 = 0; s0 < S; s0 += chunk, c ^= 1) {
+            const long long cnt = std::min<long long>(chunk, S - s0);
+            if (series_stride == 1) {                            // rows = draws, cnt series wide
+                CUS(cudaMemcpy2DAsync(d_x[c], sizeof(double) * cnt, x + s0, sizeof(double) * draw_stride, sizeof(double) * cnt, M,
+                                      cudaMemcpyHostToDevice, st[c]));
+                launch(d_x[c], s0, cnt, 1, cnt, st[c]);
+            } else {                                             // rows = series, M draws wide
+                CUS(cudaMemcpy2DAsync(d_x[c], sizeof(double) * M, x + s0 * series_stride, sizeof(double) * series_stride,
+                                      sizeof(double) * M, cnt, cudaMemcpyHostToDevice, st[c]));
+                launch(d_x[c], s0, cnt, M, 1, st[c]);
+            }
+            CUS(cudaGetLastError());
+        }
+    }
+    for (auto s : st) CUS(cudaStreamSynchronize(s));
+    if (kernel_ms) {
+        *kernel_ms = 0.f;
+        for (size_t k = 0; k + 1 < evs.size(); k += 2) { float ms = 0.f; CUS(cudaEventElapsedTime(&ms, evs[k], evs[k + 1])); *kernel_ms += ms; }
+    }
+    if (!on_device)
+        for (int k = 0; k < 10; ++k)
+            if (host_out[k]) CUS(cudaMemcpy(host_out[k], dev_out[k], sizeof(double) * width[k] * S, cudaMemcpyDeviceToHost));
+#undef CUS
+    cleanup();
+    return 0;
+}
