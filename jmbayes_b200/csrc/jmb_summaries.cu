@@ -41,13 +41,64 @@ __device__ __forceinline__ double st_q7(const double* k, int M, double p) {
     const double index = (double)(M - 1) * p;
     const int lo = (int)floor(index), hi = (int)ceil(index);
     const double h = index - (double)lo;
-    double qs = k[lo];
-    if (index > (double)lo && k[hi] != qs) qs = (1.0 - h) * qs + h * k[hi];
+    double qs = k[lo + (lo >> 5)];
+    if (index > (double)lo && k[hi + (hi >> 5)] != qs) qs = (1.0 - h) * qs + h * k[hi + (hi >> 5)];
     return qs;
 }
 
-// doubles of shared memory per warp: [A | Bk] (>= 1024, reused for the density values) | Y | Kn | idx (uint16)
-__host__ __device__ inline int st_warp_doubles(int P) { return (2 * P > 1024 ? 2 * P : 1024) + 2 * 1024 + (P + 3) / 4; }
+// doubles of shared memory per warp: [A | Bk] (>= 1024, reused for the density values) | Y | Kn | idx (uint16).
+// Sorted keys and cumulative weights are stored skewed, element e at e + e / 32, so that both access patterns - lane l
+// touching e = l * (P / 32) + r (the sort's registers, the per-lane chunks) and e = l + 32 i - are at most 2-way conflicted.
+__host__ __device__ inline int st_half(int P) { return P + P / 32; }
+__host__ __device__ inline int st_work(int P) { return 2 * st_half(P) > 1024 ? 2 * st_half(P) : 1024; }
+__host__ __device__ inline int st_warp_doubles(int P) { return st_work(P) + 2 * 1024 + (P + 3) / 4; }
+#define SKEW(e) ((e) + ((e) >> 5))
+
+// Bitonic sort of the P = 32 EPL keys of a warp in registers: lane l holds positions l EPL .. l EPL + EPL - 1, so the
+// exchanges at distance < EPL stay inside a lane and the others are one shuffle per element.  Writes the sorted keys
+// (skewed) and the draw index of each to shared memory.
+template <int EPL>
+__device__ __forceinline__ void st_sort(const double* A, double* Bk, unsigned short* idx, int M, int lane) {
+    constexpr int P = 32 * EPL;
+    double key[EPL];
+    int id[EPL];
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) {                     // any initial placement will do: read without bank conflicts
+        const int src = r * 32 + lane;
+        key[r] = src < M ? A[src] : __longlong_as_double(0x7ff0000000000000LL);
+        id[r] = src;
+    }
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j >= EPL; j >>= 1) {
+            const int lm = j / EPL;
+            const bool lower = (lane & lm) == 0;
+#pragma unroll
+            for (int r = 0; r < EPL; ++r) {
+                const double ok = __shfl_xor_sync(kFull, key[r], lm);
+                const int oi = __shfl_xor_sync(kFull, id[r], lm);
+                const bool up = ((lane * EPL + r) & k) == 0;
+                const bool take = (up == lower) ? (ok < key[r]) : (ok > key[r]);
+                if (take) { key[r] = ok; id[r] = oi; }
+            }
+        }
+#pragma unroll
+        for (int jj = EPL >> 1; jj > 0; jj >>= 1) {
+            if (jj <= (k >> 1)) {
+#pragma unroll
+                for (int r = 0; r < EPL; ++r) {
+                    if ((r & jj) == 0) {
+                        const int p = r | jj;
+                        const bool up = ((lane * EPL + r) & k) == 0;
+                        const double x0 = key[r], x1 = key[p];
+                        if ((x0 > x1) == up) { key[r] = x1; key[p] = x0; const int t = id[r]; id[r] = id[p]; id[p] = t; }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) { const int e = lane * EPL + r; Bk[SKEW(e)] = key[r]; idx[e] = (unsigned short)id[r]; }
+}
 
 __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
     extern __shared__ double st_smem[];
@@ -57,9 +108,9 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
     const int wd = st_warp_doubles(P);
     double* base = st_smem + (M + 1) / 2 * 2 + (size_t)wid * wd;
     double* A = base;                                           // the series in draw order; later cumulative weights
-    double* Bk = base + P;                                      // sorted keys
+    double* Bk = base + st_half(P);                             // sorted keys (skewed)
     double* Rb = base;                                          // density on the cells jlo..jhi (overlays A | Bk)
-    double* Y = base + max(2 * P, kStN);                        // BinDist cells
+    double* Y = base + st_work(P);                              // BinDist cells
     double* Kn = Y + kStN;                                      // dnorm(m dk, sd = bw)
     unsigned short* idx = reinterpret_cast<unsigned short*>(Kn + kStN);
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -141,22 +192,14 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
         const double ess = (spec == 0.0) ? 0.0 : (double)M * var / spec;
 
         // ---- sort (bitonic, keys with their draw index) ------------------------------------------------------------------
-        for (int k = lane; k < P; k += 32) { Bk[k] = k < M ? A[k] : inf; idx[k] = (unsigned short)k; }
         __syncwarp();
-        for (int k = 2; k <= P; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = lane; t < P / 2; t += 32) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
-                    const bool up = (i & k) == 0;
-                    const double x0 = Bk[i], x1 = Bk[p];
-                    if ((x0 > x1) == up) {
-                        Bk[i] = x1; Bk[p] = x0;
-                        const unsigned short i0 = idx[i]; idx[i] = idx[p]; idx[p] = i0;
-                    }
-                }
-                __syncwarp();
-            }
+        switch (P) {
+            case 128: st_sort<4>(A, Bk, idx, M, lane); break;
+            case 256: st_sort<8>(A, Bk, idx, M, lane); break;
+            case 512: st_sort<16>(A, Bk, idx, M, lane); break;
+            default: st_sort<32>(A, Bk, idx, M, lane); break;
         }
+        __syncwarp();
         const double q_lo = st_q7(Bk, M, a.p_lo), q_hi = st_q7(Bk, M, a.p_hi);
         const double iqr = st_q7(Bk, M, 0.75) - st_q7(Bk, M, 0.25);
 
@@ -170,10 +213,10 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
             double run = incl - part;
-            for (int k = lane * C; k < (lane + 1) * C; ++k) if (k < M) { run += sw[idx[k]]; cum[k] = run; }
+            for (int k = lane * C; k < (lane + 1) * C; ++k) if (k < M) { run += sw[idx[k]]; cum[SKEW(k)] = run; }
         }
         __syncwarp();
-        const double wn1 = cum[M - 1] + 1.0;                     // n + 1, n = sum of the weights
+        const double wn1 = cum[SKEW(M - 1)] + 1.0;                     // n + 1, n = sum of the weights
         double wq[2];
         {
             int first_k = P, last_k = -1;                        // first / last knot of this lane's chunk
@@ -183,9 +226,9 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
                 if (k >= M || sw[idx[k]] == 0.0) continue;       // zero-weight observations are dropped
                 int k2 = k + 1;
                 while (k2 < M && sw[idx[k2]] == 0.0) ++k2;
-                if (k2 < M && Bk[k2] == Bk[k]) continue;         // wtd.table: tied values are one point
+                if (k2 < M && Bk[SKEW(k2)] == Bk[SKEW(k)]) continue;         // wtd.table: tied values are one point
                 first_k = min(first_k, k); last_k = k;
-                const double cdf = cum[k] / wn1;
+                const double cdf = cum[SKEW(k)] / wn1;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     if (cdf >= pr[e]) jge[e] = min(jge[e], k); else ilt[e] = k;
@@ -204,10 +247,10 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 if (last_k < 0) wq[e] = nan;                                   // no positive weight
-                else if (jge[e] >= P) wq[e] = Bk[last_k];                      // approx(rule = 2) beyond the last point
-                else if (ilt[e] < 0) wq[e] = Bk[first_k];                      // between the prepended (0, x[1]) and x[1]
+                else if (jge[e] >= P) wq[e] = Bk[SKEW(last_k)];                      // approx(rule = 2) beyond the last point
+                else if (ilt[e] < 0) wq[e] = Bk[SKEW(first_k)];                      // between the prepended (0, x[1]) and x[1]
                 else {
-                    const double ci = cum[ilt[e]] / wn1, cj = cum[jge[e]] / wn1, yi = Bk[ilt[e]], yj = Bk[jge[e]];
+                    const double ci = cum[SKEW(ilt[e])] / wn1, cj = cum[SKEW(jge[e])] / wn1, yi = Bk[SKEW(ilt[e])], yj = Bk[SKEW(jge[e])];
                     wq[e] = yi + (yj - yi) * ((pr[e] - ci) / (cj - ci));
                 }
             }
@@ -216,7 +259,7 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
         // ---- modes(): density(y, bw = "nrd", adjust = 3, n = 1000), x of the maximum -------------------------------------
         double mode = nan;
         const double bw = 3.0 * (1.06 * fmin(sqrt(var), iqr / 1.34) * a.m_pow);
-        const double xmin = Bk[0], xmax = Bk[M - 1];
+        const double xmin = Bk[0], xmax = Bk[SKEW(M - 1)];
         __syncwarp();
         if (bw > 0.0 && bw < inf) {
             const double from = xmin - 3.0 * bw, to = xmax + 3.0 * bw, lo = from - 4.0 * bw, up = to + 4.0 * bw;
@@ -225,36 +268,53 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
             for (int k = lane; k < kStN; k += 32) Y[k] = 0.0;
             __syncwarp();
             for (int k = lane; k < M; k += 32) {                 // BinDist: the data lie 7 bw inside (lo, up), no edge cases
-                const double xpos = (Bk[k] - lo) / xdelta;
+                const double xpos = (Bk[SKEW(k)] - lo) / xdelta;
                 const int ix = (int)floor(xpos);
                 const double fx = xpos - (double)ix;
                 atomicAdd(&Y[ix], wi * (1.0 - fx));
                 atomicAdd(&Y[ix + 1], wi * fx);
             }
+            const double by = (to - from) / (double)(kStUser - 1);
             const int klo = (int)floor((xmin - lo) / xdelta), khi = min(kStN - 1, (int)floor((xmax - lo) / xdelta) + 1);
-            const int jlo = max(0, (int)floor((from - lo) / xdelta) - 1), jhi = min(kStN - 1, (int)floor((to - lo) / xdelta) + 2);
-            const int mmax = max(khi - jlo, jhi - klo);
+            // Left of the first and right of the last occupied cell the estimate is monotone (every kernel term is), so the
+            // maximum over density()'s 1000-point grid is taken between the draws: only those grid points (and a margin of
+            // four, a cell being at most 2.3 grid steps wide) and the cells under them are evaluated.
+            const int t_lo = max(0, (int)floor((xmin - from) / by) - 4), t_hi = min(kStUser - 1, (int)ceil((xmax - from) / by) + 4);
+            const double xt_hi = (t_hi == kStUser - 1) ? to : from + (double)t_hi * by;
+            const int jlo = max(0, (int)floor((from + (double)t_lo * by - lo) / xdelta) - 1);
+            const int jhi = min(kStN - 1, (int)floor((xt_hi - lo) / xdelta) + 2);
+            const int span = max(khi - jlo, jhi - klo);
             const double dk = 2.0 * (up - lo) / (double)(2 * kStN - 1), cn = 0.3989422804014327 / bw;
-            for (int m = lane; m <= mmax; m += 32) { const double z = (double)m * dk / bw; Kn[m] = cn * exp(-0.5 * z * z); }
-            __syncwarp();
-            for (int j0 = jlo + lane; j0 - lane <= jhi; j0 += 128) {           // four cells per lane share the loads of Y
-                double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
-                for (int k = klo; k <= khi; ++k) {
-                    const double y = Y[k];
-                    r0 += y * Kn[min(abs(k - j0), kStN - 1)];
-                    r1 += y * Kn[min(abs(k - j0 - 32), kStN - 1)];
-                    r2 += y * Kn[min(abs(k - j0 - 64), kStN - 1)];
-                    r3 += y * Kn[min(abs(k - j0 - 96), kStN - 1)];
+            if (2 * span + 1 <= kStN) {
+                // two-sided table Kn[d + span] = dnorm(|d| dk, sd = bw): the inner loop is loads and fused multiply-adds only
+                for (int m = lane; m <= 2 * span; m += 32) { const double z = (double)abs(m - span) * dk / bw; Kn[m] = cn * exp(-0.5 * z * z); }
+                __syncwarp();
+                for (int jb = jlo; jb <= jhi; jb += 128) {                     // four cells per lane share the loads of Y
+                    const int j0 = jb + lane;
+                    const double* kp = Kn + span - j0;                         // kp[k - 32 i] = kernel between cells k and j0 + 32 i
+                    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+#pragma unroll 4
+                    for (int k = klo; k <= khi; ++k) {
+                        const double y = Y[k];
+                        r0 += y * kp[k]; r1 += y * kp[k - 32]; r2 += y * kp[k - 64]; r3 += y * kp[k - 96];
+                    }
+                    if (j0 <= jhi) Rb[j0 - jlo] = fmax(0.0, r0);
+                    if (j0 + 32 <= jhi) Rb[j0 + 32 - jlo] = fmax(0.0, r1);
+                    if (j0 + 64 <= jhi) Rb[j0 + 64 - jlo] = fmax(0.0, r2);
+                    if (j0 + 96 <= jhi) Rb[j0 + 96 - jlo] = fmax(0.0, r3);
                 }
-                if (j0 <= jhi) Rb[j0 - jlo] = fmax(0.0, r0);
-                if (j0 + 32 <= jhi) Rb[j0 + 32 - jlo] = fmax(0.0, r1);
-                if (j0 + 64 <= jhi) Rb[j0 + 64 - jlo] = fmax(0.0, r2);
-                if (j0 + 96 <= jhi) Rb[j0 + 96 - jlo] = fmax(0.0, r3);
+            } else {                                                           // very long tails: one-sided table, |k - j| per term
+                for (int m = lane; m <= span; m += 32) { const double z = (double)m * dk / bw; Kn[m] = cn * exp(-0.5 * z * z); }
+                __syncwarp();
+                for (int j0 = jlo + lane; j0 <= jhi; j0 += 32) {
+                    double r0 = 0.0;
+                    for (int k = klo; k <= khi; ++k) r0 += Y[k] * Kn[abs(k - j0)];
+                    Rb[j0 - jlo] = fmax(0.0, r0);
+                }
             }
             __syncwarp();
-            const double by = (to - from) / (double)(kStUser - 1);
             double bv = -1.0; int bt = kStUser;
-            for (int t = lane; t < kStUser; t += 32) {            // approx(xords, kords, x) and which.max
+            for (int t = t_lo + lane; t <= t_hi; t += 32) {       // approx(xords, kords, x) and which.max
                 const double xt = (t == kStUser - 1) ? to : from + (double)t * by;
                 int jj = min(max((int)floor((xt - lo) / xdelta), jlo), jhi - 1);
                 if (jj > jlo && lo + (double)jj * xdelta > xt) --jj;
@@ -344,7 +404,7 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
 
     StArgs a{};
     a.M = M; a.P = 4; while (a.P < M) a.P <<= 1;
-    a.P = std::max(a.P, 32);
+    a.P = std::max(a.P, 128);
     a.warps = a.P <= 512 ? 8 : 6;
     a.sumw = sumw; a.sumwt2 = sumwt2; a.p_lo = probs[0]; a.p_hi = probs[1];
     a.m_pow = std::pow((double)M, -0.2);
