@@ -591,10 +591,12 @@ def run_summaries(args):
     summaries.series_statistics(xn, S, M, 1, S, w, device=local)
     e2e_steps = max(1, min(steps, 3))
     barrier()
-    t0 = time.perf_counter()
+    walls = []
     for _ in range(e2e_steps):
+        t0 = time.perf_counter()
         summaries.series_statistics(xn, S, M, 1, S, w, device=local)
-    wall = (time.perf_counter() - t0) / e2e_steps
+        walls.append(time.perf_counter() - t0)
+    wall = sum(walls) / e2e_steps
     t = torch.tensor([dev_ms, wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -621,7 +623,7 @@ def run_summaries(args):
                              "and the binned kernel density of modes() (fp64 issue from shared memory), not to HBM; see profiles/"},
         "e2e": {"value": S_total / wall, "unit": STATS_UNIT, "h2d_bytes_per_step": 8.0 * M * S, "d2h_bytes_per_step": 96.0 * S,
                 "what": "jmb_mcmc_statistics() through the C ABI on pinned host draws: chunked H2D overlapped with the kernel, "
-                        "all ten statistics D2H, wall clock"},
+                        "all ten statistics D2H, wall clock", "wall_ms_per_call": [round(1e3 * t, 1) for t in walls]},
         "gpu_launches": steps, "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -28,6 +28,7 @@ struct StArgs {
     const double* w;                // weights [M]
     double sumw, sumwt2, p_lo, p_hi, m_pow; int om;
     double *mean, *wmean, *mode, *ess, *sd, *wsd, *se, *ci, *wci, *pval;
+    double* scratch;                // kStScratch doubles per resident warp
 };
 
 __device__ __forceinline__ double st_sum(double v) {
@@ -46,12 +47,15 @@ __device__ __forceinline__ double st_q7(const double* k, int M, double p) {
     return qs;
 }
 
-// doubles of shared memory per warp: [A | Bk] (>= 1024, reused for the density values) | Y | Kn | idx (uint16).
+// Shared memory per warp (doubles): R1 [max(P + P / 32, 528)]: the series in draw order, then the sorted keys, then the density on the
+// evaluated cells | R2 [512 + 1024]: cumulative weights, then the occupied BinDist cells and the kernel table | idx (uint16).
 // Sorted keys and cumulative weights are stored skewed, element e at e + e / 32, so that both access patterns - lane l
 // touching e = l * (P / 32) + r (the sort's registers, the per-lane chunks) and e = l + 32 i - are at most 2-way conflicted.
+constexpr int kStYFast = 512, kStKFast = 1024;      // cells / kernel ordinates the shared-memory density path holds
+constexpr int kStScratch = 4096;                    // doubles of global scratch per warp for series with longer tails
 __host__ __device__ inline int st_half(int P) { return P + P / 32; }
-__host__ __device__ inline int st_work(int P) { return 2 * st_half(P) > 1024 ? 2 * st_half(P) : 1024; }
-__host__ __device__ inline int st_warp_doubles(int P) { return st_work(P) + 2 * 1024 + (P + 3) / 4; }
+__host__ __device__ inline int st_r1(int P) { return st_half(P) > 528 ? st_half(P) : 528; }
+__host__ __device__ inline int st_warp_doubles(int P) { return st_r1(P) + 512 + 1024 + (P + 3) / 4; }
 #define SKEW(e) ((e) + ((e) >> 5))
 
 // Bitonic sort of the P = 32 EPL keys of a warp in registers: lane l holds positions l EPL .. l EPL + EPL - 1, so the
@@ -78,7 +82,8 @@ __device__ __forceinline__ void st_sort(const double* A, double* Bk, unsigned sh
                 const int oi = __shfl_xor_sync(kFull, id[r], lm);
                 const bool up = ((lane * EPL + r) & k) == 0;
                 const bool take = (up == lower) ? (ok < key[r]) : (ok > key[r]);
-                if (take) { key[r] = ok; id[r] = oi; }
+                key[r] = take ? ok : key[r];
+                id[r] = take ? oi : id[r];
             }
         }
 #pragma unroll
@@ -100,19 +105,77 @@ __device__ __forceinline__ void st_sort(const double* A, double* Bk, unsigned sh
     for (int r = 0; r < EPL; ++r) { const int e = lane * EPL + r; Bk[SKEW(e)] = key[r]; idx[e] = (unsigned short)id[r]; }
 }
 
-__global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
+// The binned Gaussian kernel estimate of density.default on the cells jlo..jhi (into Ro) from the sorted keys, and the argmax
+// over the grid points t_lo..t_hi of density()'s 1000-point grid.  Yb holds the occupied cells klo..khi, Kb the two-sided
+// table Kb[d + span] = dnorm(|d| dk, sd = bw); the three buffers are shared memory or, for long-tailed series, global scratch.
+struct StGrid { double from, to, lo, xdelta, by, dk, bw; int klo, khi, jlo, jhi, span, t_lo, t_hi; };
+
+__device__ __forceinline__ int st_density_argmax(const StGrid& g, const double* Bk, int M, int C, double* Yb, double* Kb, double* Ro, int lane) {
+    const int ncell = g.khi - g.klo + 1;
+    for (int k = lane; k < ncell; k += 32) Yb[k] = 0.0;
+    const double cn = 0.3989422804014327 / g.bw;
+    for (int m = lane; m <= 2 * g.span; m += 32) { const double z = (double)abs(m - g.span) * g.dk / g.bw; Kb[m] = cn * exp(-0.5 * z * z); }
+    __syncwarp();
+    const double wi = 1.0 / (double)M;
+    for (int r = 0; r < C; ++r) {                            // BinDist: the data lie 7 bw inside (lo, up), no edge cases;
+        const int k = lane * C + r;                          // a lane's chunk of the sorted keys is far from its neighbours'
+        if (k >= M) break;
+        const double xpos = (Bk[SKEW(k)] - g.lo) / g.xdelta;
+        const int ix = (int)floor(xpos);
+        const double fx = xpos - (double)ix;
+        atomicAdd(&Yb[ix - g.klo], wi * (1.0 - fx));
+        atomicAdd(&Yb[ix + 1 - g.klo], wi * fx);
+    }
+    __syncwarp();                                            // the sorted keys are no longer read: Ro may overlay them
+    for (int jb = g.jlo; jb <= g.jhi; jb += 128) {           // four cells per lane share the loads of Yb
+        const int j0 = jb + lane;
+        const double* kp = Kb + g.span - j0 + g.klo;         // kp[c - 32 i] = kernel between cells klo + c and j0 + 32 i
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+#pragma unroll 4
+        for (int c = 0; c < ncell; ++c) {
+            const double y = Yb[c];
+            r0 += y * kp[c]; r1 += y * kp[c - 32]; r2 += y * kp[c - 64]; r3 += y * kp[c - 96];
+        }
+        if (j0 <= g.jhi) Ro[j0 - g.jlo] = fmax(0.0, r0);
+        if (j0 + 32 <= g.jhi) Ro[j0 + 32 - g.jlo] = fmax(0.0, r1);
+        if (j0 + 64 <= g.jhi) Ro[j0 + 64 - g.jlo] = fmax(0.0, r2);
+        if (j0 + 96 <= g.jhi) Ro[j0 + 96 - g.jlo] = fmax(0.0, r3);
+    }
+    __syncwarp();
+    double bv = -1.0; int bt = kStUser;
+    for (int t = g.t_lo + lane; t <= g.t_hi; t += 32) {      // approx(xords, kords, x) and which.max
+        const double xt = (t == kStUser - 1) ? g.to : g.from + (double)t * g.by;
+        int jj = min(max((int)floor((xt - g.lo) / g.xdelta), g.jlo), g.jhi - 1);
+        if (jj > g.jlo && g.lo + (double)jj * g.xdelta > xt) --jj;
+        else if (jj < g.jhi - 1 && g.lo + (double)(jj + 1) * g.xdelta <= xt) ++jj;
+        const double xa = g.lo + (double)jj * g.xdelta, xb = g.lo + (double)(jj + 1) * g.xdelta;
+        const double ya = Ro[jj - g.jlo], yb = Ro[jj + 1 - g.jlo];
+        const double val = ya + (yb - ya) * ((xt - xa) / (xb - xa));
+        if (val > bv) { bv = val; bt = t; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(kFull, bv, o);
+        const int ot = __shfl_xor_sync(kFull, bt, o);
+        if (ov > bv || (ov == bv && ot < bt)) { bv = ov; bt = ot; }
+    }
+    return bt;
+}
+
+__global__ void __launch_bounds__(192, 2) jmb_stats_kernel(const StArgs a) {
     extern __shared__ double st_smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int M = a.M, P = a.P, W = a.warps;
     double* sw = st_smem;                                       // weights [M] (padded to even)
     const int wd = st_warp_doubles(P);
     double* base = st_smem + (M + 1) / 2 * 2 + (size_t)wid * wd;
-    double* A = base;                                           // the series in draw order; later cumulative weights
-    double* Bk = base + st_half(P);                             // sorted keys (skewed)
-    double* Rb = base;                                          // density on the cells jlo..jhi (overlays A | Bk)
-    double* Y = base + st_work(P);                              // BinDist cells
-    double* Kn = Y + kStN;                                      // dnorm(m dk, sd = bw)
-    unsigned short* idx = reinterpret_cast<unsigned short*>(Kn + kStN);
+    double* A = base;                                           // R1: the series in draw order ...
+    double* Bk = base;                                          // ... the sorted keys (skewed) ...
+    double* Rb = base;                                          // ... the density on the cells jlo..jhi
+    double* cum = base + st_r1(P);                              // R2: cumulative weights in sorted order (skewed) ...
+    double* Y = base + st_r1(P);                                // ... the occupied BinDist cells ...
+    double* Kn = Y + kStYFast;                                  // ... and the kernel table
+    unsigned short* idx = reinterpret_cast<unsigned short*>(Kn + kStKFast);
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
@@ -134,7 +197,7 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
         }
         __syncthreads();
         const long long s = s0 + wid;
-        if (wid >= W || s >= a.S) continue;
+        if (s >= a.S) continue;
 
         // ---- moments: mean (two passes, as R's mean), var, weighted mean / variance (cov.wt), computeP -------------------
         double t0 = 0.0;
@@ -172,8 +235,7 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
             }
             double phi = 0.0;                                    // lane j: coefficient j of the current order
             double v = __shfl_sync(kFull, r, 0);
-            double best = (double)M * log(v) + 2.0, vbest = v, sumphi = 0.0;
-            int order = 0;
+            double v_own = v, sp_own = 0.0;                      // lane l keeps var.pred and sum(ar) of order l
             for (int l = 1; l <= a.om; ++l) {
                 const bool in = lane >= 1 && lane < l;
                 const double rj = __shfl_sync(kFull, r, (l - lane) & 31);
@@ -182,16 +244,26 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
                 const double prev = __shfl_sync(kFull, phi, (l - lane) & 31);
                 phi = in ? phi - k * prev : (lane == l ? k : phi);
                 v *= 1.0 - k * k;
-                const double aic = (double)M * log(v) + 2.0 * (double)l + 2.0;
                 const double sp = st_sum((lane >= 1 && lane <= l) ? phi : 0.0);
-                if (aic < best) { best = aic; order = l; vbest = v; sumphi = sp; }
+                if (lane == l) { v_own = v; sp_own = sp; }
             }
+            // xaic = n.used * log(var.pred) + 2 * order + 2; the first minimum over the orders 0..order.max
+            double aic = (lane <= a.om) ? (double)M * log(v_own) + 2.0 * (double)lane + 2.0 : inf;
+            if (!(aic == aic)) aic = inf;
+            int order = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oa = __shfl_xor_sync(kFull, aic, o);
+                const int oo = __shfl_xor_sync(kFull, order, o);
+                if (oa < aic || (oa == aic && oo < order)) { aic = oa; order = oo; }
+            }
+            const double vbest = __shfl_sync(kFull, v_own, order), sumphi = __shfl_sync(kFull, sp_own, order);
             const double var_pred = vbest * (double)M / (double)(M - (order + 1));
             spec = var_pred / ((1.0 - sumphi) * (1.0 - sumphi));
         }
         const double ess = (spec == 0.0) ? 0.0 : (double)M * var / spec;
 
-        // ---- sort (bitonic, keys with their draw index) ------------------------------------------------------------------
+        // ---- sort (bitonic in registers, keys with their draw index); the sorted keys replace the series ------------------
         __syncwarp();
         switch (P) {
             case 128: st_sort<4>(A, Bk, idx, M, lane); break;
@@ -205,7 +277,6 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
 
         // ---- Hmisc::wtd.quantile(type = "i/(n+1)"): cumulative weights in sorted order, knots at the last of tied keys ----
         const int C = P / 32;                                    // contiguous elements per lane
-        double* cum = A;
         {
             double part = 0.0;
             for (int k = lane * C; k < (lane + 1) * C; ++k) if (k < M) part += sw[idx[k]];
@@ -216,7 +287,7 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
             for (int k = lane * C; k < (lane + 1) * C; ++k) if (k < M) { run += sw[idx[k]]; cum[SKEW(k)] = run; }
         }
         __syncwarp();
-        const double wn1 = cum[SKEW(M - 1)] + 1.0;                     // n + 1, n = sum of the weights
+        const double wn1 = cum[SKEW(M - 1)] + 1.0;               // n + 1, n = sum of the weights
         double wq[2];
         {
             int first_k = P, last_k = -1;                        // first / last knot of this lane's chunk
@@ -247,8 +318,8 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 if (last_k < 0) wq[e] = nan;                                   // no positive weight
-                else if (jge[e] >= P) wq[e] = Bk[SKEW(last_k)];                      // approx(rule = 2) beyond the last point
-                else if (ilt[e] < 0) wq[e] = Bk[SKEW(first_k)];                      // between the prepended (0, x[1]) and x[1]
+                else if (jge[e] >= P) wq[e] = Bk[SKEW(last_k)];                // approx(rule = 2) beyond the last point
+                else if (ilt[e] < 0) wq[e] = Bk[SKEW(first_k)];                // between the prepended (0, x[1]) and x[1]
                 else {
                     const double ci = cum[SKEW(ilt[e])] / wn1, cj = cum[SKEW(jge[e])] / wn1, yi = Bk[SKEW(ilt[e])], yj = Bk[SKEW(jge[e])];
                     wq[e] = yi + (yj - yi) * ((pr[e] - ci) / (cj - ci));
@@ -260,77 +331,32 @@ __global__ void __launch_bounds__(256, 1) jmb_stats_kernel(const StArgs a) {
         double mode = nan;
         const double bw = 3.0 * (1.06 * fmin(sqrt(var), iqr / 1.34) * a.m_pow);
         const double xmin = Bk[0], xmax = Bk[SKEW(M - 1)];
-        __syncwarp();
+        __syncwarp();                                            // the cumulative weights are no longer read
         if (bw > 0.0 && bw < inf) {
-            const double from = xmin - 3.0 * bw, to = xmax + 3.0 * bw, lo = from - 4.0 * bw, up = to + 4.0 * bw;
-            const double xdelta = (up - lo) / (double)(kStN - 1);
-            const double wi = 1.0 / (double)M;
-            for (int k = lane; k < kStN; k += 32) Y[k] = 0.0;
-            __syncwarp();
-            for (int k = lane; k < M; k += 32) {                 // BinDist: the data lie 7 bw inside (lo, up), no edge cases
-                const double xpos = (Bk[SKEW(k)] - lo) / xdelta;
-                const int ix = (int)floor(xpos);
-                const double fx = xpos - (double)ix;
-                atomicAdd(&Y[ix], wi * (1.0 - fx));
-                atomicAdd(&Y[ix + 1], wi * fx);
-            }
-            const double by = (to - from) / (double)(kStUser - 1);
-            const int klo = (int)floor((xmin - lo) / xdelta), khi = min(kStN - 1, (int)floor((xmax - lo) / xdelta) + 1);
+            StGrid g;
+            g.bw = bw;
+            g.from = xmin - 3.0 * bw; g.to = xmax + 3.0 * bw; g.lo = g.from - 4.0 * bw;
+            const double up = g.to + 4.0 * bw;
+            g.xdelta = (up - g.lo) / (double)(kStN - 1);
+            g.by = (g.to - g.from) / (double)(kStUser - 1);
+            g.dk = 2.0 * (up - g.lo) / (double)(2 * kStN - 1);
+            g.klo = (int)floor((xmin - g.lo) / g.xdelta); g.khi = min(kStN - 1, (int)floor((xmax - g.lo) / g.xdelta) + 1);
             // Left of the first and right of the last occupied cell the estimate is monotone (every kernel term is), so the
             // maximum over density()'s 1000-point grid is taken between the draws: only those grid points (and a margin of
             // four, a cell being at most 2.3 grid steps wide) and the cells under them are evaluated.
-            const int t_lo = max(0, (int)floor((xmin - from) / by) - 4), t_hi = min(kStUser - 1, (int)ceil((xmax - from) / by) + 4);
-            const double xt_hi = (t_hi == kStUser - 1) ? to : from + (double)t_hi * by;
-            const int jlo = max(0, (int)floor((from + (double)t_lo * by - lo) / xdelta) - 1);
-            const int jhi = min(kStN - 1, (int)floor((xt_hi - lo) / xdelta) + 2);
-            const int span = max(khi - jlo, jhi - klo);
-            const double dk = 2.0 * (up - lo) / (double)(2 * kStN - 1), cn = 0.3989422804014327 / bw;
-            if (2 * span + 1 <= kStN) {
-                // two-sided table Kn[d + span] = dnorm(|d| dk, sd = bw): the inner loop is loads and fused multiply-adds only
-                for (int m = lane; m <= 2 * span; m += 32) { const double z = (double)abs(m - span) * dk / bw; Kn[m] = cn * exp(-0.5 * z * z); }
-                __syncwarp();
-                for (int jb = jlo; jb <= jhi; jb += 128) {                     // four cells per lane share the loads of Y
-                    const int j0 = jb + lane;
-                    const double* kp = Kn + span - j0;                         // kp[k - 32 i] = kernel between cells k and j0 + 32 i
-                    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
-#pragma unroll 4
-                    for (int k = klo; k <= khi; ++k) {
-                        const double y = Y[k];
-                        r0 += y * kp[k]; r1 += y * kp[k - 32]; r2 += y * kp[k - 64]; r3 += y * kp[k - 96];
-                    }
-                    if (j0 <= jhi) Rb[j0 - jlo] = fmax(0.0, r0);
-                    if (j0 + 32 <= jhi) Rb[j0 + 32 - jlo] = fmax(0.0, r1);
-                    if (j0 + 64 <= jhi) Rb[j0 + 64 - jlo] = fmax(0.0, r2);
-                    if (j0 + 96 <= jhi) Rb[j0 + 96 - jlo] = fmax(0.0, r3);
-                }
-            } else {                                                           // very long tails: one-sided table, |k - j| per term
-                for (int m = lane; m <= span; m += 32) { const double z = (double)m * dk / bw; Kn[m] = cn * exp(-0.5 * z * z); }
-                __syncwarp();
-                for (int j0 = jlo + lane; j0 <= jhi; j0 += 32) {
-                    double r0 = 0.0;
-                    for (int k = klo; k <= khi; ++k) r0 += Y[k] * Kn[abs(k - j0)];
-                    Rb[j0 - jlo] = fmax(0.0, r0);
-                }
+            g.t_lo = max(0, (int)floor((xmin - g.from) / g.by) - 4); g.t_hi = min(kStUser - 1, (int)ceil((xmax - g.from) / g.by) + 4);
+            const double xt_hi = (g.t_hi == kStUser - 1) ? g.to : g.from + (double)g.t_hi * g.by;
+            g.jlo = max(0, (int)floor((g.from + (double)g.t_lo * g.by - g.lo) / g.xdelta) - 1);
+            g.jhi = min(kStN - 1, (int)floor((xt_hi - g.lo) / g.xdelta) + 2);
+            g.span = max(g.khi - g.jlo, g.jhi - g.klo);
+            int bt;
+            if (g.khi - g.klo + 1 <= kStYFast && 2 * g.span + 1 <= kStKFast && g.jhi - g.jlo + 1 <= st_r1(P)) {
+                bt = st_density_argmax(g, Bk, M, C, Y, Kn, Rb, lane);
+            } else {                                             // long tails: the same arithmetic on global scratch
+                double* sc = a.scratch + ((size_t)blockIdx.x * W + wid) * kStScratch;
+                bt = st_density_argmax(g, Bk, M, C, sc, sc + kStN, sc + 3 * kStN, lane);
             }
-            __syncwarp();
-            double bv = -1.0; int bt = kStUser;
-            for (int t = t_lo + lane; t <= t_hi; t += 32) {       // approx(xords, kords, x) and which.max
-                const double xt = (t == kStUser - 1) ? to : from + (double)t * by;
-                int jj = min(max((int)floor((xt - lo) / xdelta), jlo), jhi - 1);
-                if (jj > jlo && lo + (double)jj * xdelta > xt) --jj;
-                else if (jj < jhi - 1 && lo + (double)(jj + 1) * xdelta <= xt) ++jj;
-                const double xa = lo + (double)jj * xdelta, xb = lo + (double)(jj + 1) * xdelta;
-                const double ya = Rb[jj - jlo], yb = Rb[jj + 1 - jlo];
-                const double val = ya + (yb - ya) * ((xt - xa) / (xb - xa));
-                if (val > bv) { bv = val; bt = t; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(kFull, bv, o);
-                const int ot = __shfl_xor_sync(kFull, bt, o);
-                if (ov > bv || (ov == bv && ot < bt)) { bv = ov; bt = ot; }
-            }
-            mode = (bt == kStUser - 1) ? to : from + (double)bt * by;
+            mode = (bt == kStUser - 1) ? g.to : g.from + (double)bt * g.by;
         }
 
         if (lane == 0) {
@@ -405,7 +431,7 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
     StArgs a{};
     a.M = M; a.P = 4; while (a.P < M) a.P <<= 1;
     a.P = std::max(a.P, 128);
-    a.warps = a.P <= 512 ? 8 : 6;
+    a.warps = a.P <= 512 ? 6 : 4;                 // two CTAs per SM
     a.sumw = sumw; a.sumwt2 = sumwt2; a.p_lo = probs[0]; a.p_hi = probs[1];
     a.m_pow = std::pow((double)M, -0.2);
     a.om = (int)std::min<double>(M - 1, std::floor(10.0 * std::log10((double)M)));
@@ -413,6 +439,11 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
     CUS(cudaFuncSetAttribute(jmb_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     double* d_w = nullptr;
     CUS(cudaMalloc(&d_w, sizeof(double) * M)); owned.push_back(d_w);
+    const int max_grid = 2 * num_sms;
+    double* d_scratch = nullptr;
+    const size_t scratch_doubles = (size_t)kStScratch * max_grid * a.warps;       // one set per stream
+    CUS(cudaMalloc(&d_scratch, sizeof(double) * 2 * scratch_doubles)); owned.push_back(d_scratch);
+    a.scratch = d_scratch;
     CUS(cudaMemcpy(d_w, weights, sizeof(double) * M, cudaMemcpyHostToDevice));
     a.w = d_w;
 
@@ -427,6 +458,7 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
     }
     auto launch = [&](const double* xd, long long s0, long long count, long long sstride, long long dstride, cudaStream_t stream) {
         StArgs b = a;
+        b.scratch = d_scratch + (stream == st[1] ? scratch_doubles : 0);
         b.x = xd; b.S = count; b.sstride = sstride; b.dstride = dstride;
         b.mean = dev_out[0] ? dev_out[0] + s0 : nullptr; b.wmean = dev_out[1] ? dev_out[1] + s0 : nullptr;
         b.mode = dev_out[2] ? dev_out[2] + s0 : nullptr; b.ess = dev_out[3] ? dev_out[3] + s0 : nullptr;
@@ -434,11 +466,11 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
         b.se = dev_out[6] ? dev_out[6] + s0 : nullptr; b.ci = dev_out[7] ? dev_out[7] + 2 * s0 : nullptr;
         b.wci = dev_out[8] ? dev_out[8] + 2 * s0 : nullptr; b.pval = dev_out[9] ? dev_out[9] + s0 : nullptr;
         const long long tiles = (count + a.warps - 1) / a.warps;
-        const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, num_sms));
+        const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, max_grid));
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1); evs.push_back(e0); evs.push_back(e1);
         cudaEventRecord(e0, stream);
-        jmb_stats_kernel<<<grid, 32 * 8, smem, stream>>>(b);
+        jmb_stats_kernel<<<grid, 32 * a.warps, smem, stream>>>(b);
         cudaEventRecord(e1, stream);
     };
 
