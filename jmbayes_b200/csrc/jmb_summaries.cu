@@ -95,7 +95,10 @@ __device__ __forceinline__ void st_sort(const double* A, double* Bk, unsigned sh
                         const int p = r | jj;
                         const bool up = ((lane * EPL + r) & k) == 0;
                         const double x0 = key[r], x1 = key[p];
-                        if ((x0 > x1) == up) { key[r] = x1; key[p] = x0; const int t = id[r]; id[r] = id[p]; id[p] = t; }
+                        const bool ex = (x0 > x1) == up;          // selects, not branches: the warp must stay converged
+                        const int i0 = id[r], i1 = id[p];
+                        key[r] = ex ? x1 : x0; key[p] = ex ? x0 : x1;
+                        id[r] = ex ? i1 : i0; id[p] = ex ? i0 : i1;
                     }
                 }
             }
@@ -119,12 +122,13 @@ __device__ __forceinline__ int st_density_argmax(const StGrid& g, const double* 
     const double wi = 1.0 / (double)M;
     for (int r = 0; r < C; ++r) {                            // BinDist: the data lie 7 bw inside (lo, up), no edge cases;
         const int k = lane * C + r;                          // a lane's chunk of the sorted keys is far from its neighbours'
-        if (k >= M) break;
-        const double xpos = (Bk[SKEW(k)] - g.lo) / g.xdelta;
-        const int ix = (int)floor(xpos);
-        const double fx = xpos - (double)ix;
-        atomicAdd(&Yb[ix - g.klo], wi * (1.0 - fx));
-        atomicAdd(&Yb[ix + 1 - g.klo], wi * fx);
+        if (k < M) {
+            const double xpos = (Bk[SKEW(k)] - g.lo) / g.xdelta;
+            const int ix = (int)floor(xpos);
+            const double fx = xpos - (double)ix;
+            atomicAdd(&Yb[ix - g.klo], wi * (1.0 - fx));
+            atomicAdd(&Yb[ix + 1 - g.klo], wi * fx);
+        }
     }
     __syncwarp();                                            // the sorted keys are no longer read: Ro may overlay them
     for (int jb = g.jlo; jb <= g.jhi; jb += 128) {           // four cells per lane share the loads of Yb
