@@ -117,7 +117,7 @@ __device__ __forceinline__ int st_density_argmax(const StGrid& g, const double* 
     const int ncell = g.khi - g.klo + 1;
     for (int k = lane; k < ncell; k += 32) Yb[k] = 0.0;
     const double cn = 0.3989422804014327 / g.bw;
-    for (int m = lane; m <= 2 * g.span; m += 32) { const double z = (double)abs(m - g.span) * g.dk / g.bw; Kb[m] = cn * exp(-0.5 * z * z); }
+    for (int d = lane; d <= g.span; d += 32) { const double z = (double)d * g.dk / g.bw, kv = cn * exp(-0.5 * z * z); Kb[g.span + d] = kv; Kb[g.span - d] = kv; }
     __syncwarp();
     const double wi = 1.0 / (double)M;
     for (int r = 0; r < C; ++r) {                            // BinDist: the data lie 7 bw inside (lo, up), no edge cases;
@@ -232,11 +232,13 @@ __global__ void __launch_bounds__(192, 2) jmb_stats_kernel(const StArgs a) {
         const double sd_res = sqrt(st_sum(rs) / (double)(M - 1));
         double spec = 0.0;
         if (sd_res > 1.5e-8) {                                   // identical(all.equal(sd(res), 0), TRUE) is FALSE
+            double* xc = cum;                                    // the centred series (R2 is free until the sort is done)
+            for (int m = lane; m < M + 32; m += 32) xc[m] = m < M ? A[m] - mean : 0.0;
+            __syncwarp();
             double r = 0.0;                                      // lane l: autocovariance at lag l (divisor n)
-            if (lane <= a.om) {
-                for (int m = 0; m + lane < M; ++m) r += (A[m] - mean) * (A[m + lane] - mean);
-                r /= (double)M;
-            }
+#pragma unroll 4
+            for (int m = 0; m < M; ++m) r += xc[m] * xc[m + lane];       // the zero padding ends every lag's sum at M - l
+            r /= (double)M;
             double phi = 0.0;                                    // lane j: coefficient j of the current order
             double v = __shfl_sync(kFull, r, 0);
             double v_own = v, sp_own = 0.0;                      // lane l keeps var.pred and sum(ar) of order l
