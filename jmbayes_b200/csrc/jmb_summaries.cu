@@ -52,7 +52,7 @@ __device__ __forceinline__ double st_q7(const double* k, int M, double p) {
 // Sorted keys and cumulative weights are stored skewed, element e at e + e / 32, so that both access patterns - lane l
 // touching e = l * (P / 32) + r (the sort's registers, the per-lane chunks) and e = l + 32 i - are at most 2-way conflicted.
 constexpr int kStYFast = 512, kStKFast = 1024;      // cells / kernel ordinates the shared-memory density path holds
-constexpr int kStScratch = 4096;                    // doubles of global scratch per warp for series with longer tails
+constexpr int kStScratch = 4608;                    // doubles of global scratch per warp for series with longer tails
 __host__ __device__ inline int st_half(int P) { return P + P / 32; }
 __host__ __device__ inline int st_r1(int P) { return st_half(P) > 528 ? st_half(P) : 528; }
 __host__ __device__ inline int st_warp_doubles(int P) { return st_r1(P) + 512 + 1024 + (P + 3) / 4; }
@@ -110,14 +110,29 @@ __device__ __forceinline__ void st_sort(const double* A, double* Bk, unsigned sh
 
 // The binned Gaussian kernel estimate of density.default on the cells jlo..jhi (into Ro) from the sorted keys, and the argmax
 // over the grid points t_lo..t_hi of density()'s 1000-point grid.  Yb holds the occupied cells klo..khi, Kb the two-sided
-// table Kb[d + span] = dnorm(|d| dk, sd = bw); the three buffers are shared memory or, for long-tailed series, global scratch.
+// table of dnorm(|d| dk, sd = bw) over the cell distances d; the three buffers are shared memory or, for long-tailed
+// series, global scratch.
 struct StGrid { double from, to, lo, xdelta, by, dk, bw; int klo, khi, jlo, jhi, span, t_lo, t_hi; };
+
+// Padding of the two tables: four zero cells in front of and eight behind the occupied cells (the sum runs over whole
+// groups of four cells), and the kernel table reaches kStKPad ordinates further than the widest cell distance on both sides
+// (the last block of 128 output cells may hang over jhi; those sums are discarded, their reads stay inside the table).
+constexpr int kStYPad = 12, kStKPad = 136;
+__host__ __device__ inline int st_ktable_quarter(int span) { return (2 * span + 2 * kStKPad + 1 + 3) / 4; }
 
 __device__ __forceinline__ int st_density_argmax(const StGrid& g, const double* Bk, int M, int C, double* Yb, double* Kb, double* Ro, int lane) {
     const int ncell = g.khi - g.klo + 1;
-    for (int k = lane; k < ncell; k += 32) Yb[k] = 0.0;
+    double* Yz = Yb + 4;                                     // Yz[c] = cell klo + c
+    for (int k = lane; k < ncell + kStYPad; k += 32) Yb[k] = 0.0;
+    // Kernel table, entry e = d + off for the cell distance d, stored permuted - entry e at (e & 3) Q + (e >> 2) - so that
+    // lanes whose entries are four apart read neighbouring words.
+    const int off = g.span + kStKPad, Q = st_ktable_quarter(g.span);
     const double cn = 0.3989422804014327 / g.bw;
-    for (int d = lane; d <= g.span; d += 32) { const double z = (double)d * g.dk / g.bw, kv = cn * exp(-0.5 * z * z); Kb[g.span + d] = kv; Kb[g.span - d] = kv; }
+    for (int e = lane; e < 4 * Q; e += 32) {
+        const int d = abs(e - off);
+        const double z = (double)d * g.dk / g.bw;
+        Kb[(e & 3) * Q + (e >> 2)] = d <= g.span ? cn * exp(-0.5 * z * z) : 0.0;
+    }
     __syncwarp();
     const double wi = 1.0 / (double)M;
     for (int r = 0; r < C; ++r) {                            // BinDist: the data lie 7 bw inside (lo, up), no edge cases;
@@ -126,24 +141,37 @@ __device__ __forceinline__ int st_density_argmax(const StGrid& g, const double* 
             const double xpos = (Bk[SKEW(k)] - g.lo) / g.xdelta;
             const int ix = (int)floor(xpos);
             const double fx = xpos - (double)ix;
-            atomicAdd(&Yb[ix - g.klo], wi * (1.0 - fx));
-            atomicAdd(&Yb[ix + 1 - g.klo], wi * fx);
+            atomicAdd(&Yz[ix - g.klo], wi * (1.0 - fx));
+            atomicAdd(&Yz[ix + 1 - g.klo], wi * fx);
         }
     }
     __syncwarp();                                            // the sorted keys are no longer read: Ro may overlay them
-    for (int jb = g.jlo; jb <= g.jhi; jb += 128) {           // four cells per lane share the loads of Yb
-        const int j0 = jb + lane;
-        const double* kp = Kb + g.span - j0 + g.klo;         // kp[c - 32 i] = kernel between cells klo + c and j0 + 32 i
+    // Lane l sums the four neighbouring cells jb + 4 l + i: stepping to the next occupied cell k shifts the four kernel
+    // ordinates by one, so each step costs one new ordinate and one (broadcast) cell: 2 LDS per 4 DFMA.
+    for (int jb = g.jlo; jb <= g.jhi; jb += 128) {
+        const int kstart = g.klo - ((g.klo - jb + off) & 3);             // (kstart - jb + off) is a multiple of four
+        const int c0 = ((kstart - jb + off) >> 2) - lane;                // entry of (kstart + 4 t + u, i = 0) is 4 (c0 + t) + u
+        const double* y = Yz + (kstart - g.klo);
+        const double *p0 = Kb + c0, *p1 = Kb + Q + c0, *p2 = Kb + 2 * Q + c0, *p3 = Kb + 3 * Q + c0;
+        // ordinates of i = 1, 2, 3 at kstart: entries 4 c0 - 1, - 2, - 3
+        double w1 = p3[-1], w2 = p2[-1], w3 = p1[-1];
         double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
-#pragma unroll 4
-        for (int c = 0; c < ncell; ++c) {
-            const double y = Yb[c];
-            r0 += y * kp[c]; r1 += y * kp[c - 32]; r2 += y * kp[c - 64]; r3 += y * kp[c - 96];
+        const int nt = (g.khi - kstart + 4) >> 2;
+#pragma unroll 2
+        for (int t = 0; t < nt; ++t) {
+            const double y0 = y[4 * t], y1 = y[4 * t + 1], y2 = y[4 * t + 2], y3 = y[4 * t + 3];
+            const double a0 = p0[t], a1 = p1[t], a2 = p2[t], a3 = p3[t];
+            r0 += y0 * a0; r1 += y0 * w1; r2 += y0 * w2; r3 += y0 * w3;
+            r0 += y1 * a1; r1 += y1 * a0; r2 += y1 * w1; r3 += y1 * w2;
+            r0 += y2 * a2; r1 += y2 * a1; r2 += y2 * a0; r3 += y2 * w1;
+            r0 += y3 * a3; r1 += y3 * a2; r2 += y3 * a1; r3 += y3 * a0;
+            w1 = a3; w2 = a2; w3 = a1;
         }
-        if (j0 <= g.jhi) Ro[j0 - g.jlo] = fmax(0.0, r0);
-        if (j0 + 32 <= g.jhi) Ro[j0 + 32 - g.jlo] = fmax(0.0, r1);
-        if (j0 + 64 <= g.jhi) Ro[j0 + 64 - g.jlo] = fmax(0.0, r2);
-        if (j0 + 96 <= g.jhi) Ro[j0 + 96 - g.jlo] = fmax(0.0, r3);
+        const int j = jb + 4 * lane;
+        if (j <= g.jhi) Ro[j - g.jlo] = fmax(0.0, r0);
+        if (j + 1 <= g.jhi) Ro[j + 1 - g.jlo] = fmax(0.0, r1);
+        if (j + 2 <= g.jhi) Ro[j + 2 - g.jlo] = fmax(0.0, r2);
+        if (j + 3 <= g.jhi) Ro[j + 3 - g.jlo] = fmax(0.0, r3);
     }
     __syncwarp();
     double bv = -1.0; int bt = kStUser;
@@ -356,11 +384,11 @@ __global__ void __launch_bounds__(192, 2) jmb_stats_kernel(const StArgs a) {
             g.jhi = min(kStN - 1, (int)floor((xt_hi - g.lo) / g.xdelta) + 2);
             g.span = max(g.khi - g.jlo, g.jhi - g.klo);
             int bt;
-            if (g.khi - g.klo + 1 <= kStYFast && 2 * g.span + 1 <= kStKFast && g.jhi - g.jlo + 1 <= st_r1(P)) {
+            if (g.khi - g.klo + 1 + kStYPad <= kStYFast && 4 * st_ktable_quarter(g.span) <= kStKFast && g.jhi - g.jlo + 1 <= st_r1(P)) {
                 bt = st_density_argmax(g, Bk, M, C, Y, Kn, Rb, lane);
             } else {                                             // long tails: the same arithmetic on global scratch
                 double* sc = a.scratch + ((size_t)blockIdx.x * W + wid) * kStScratch;
-                bt = st_density_argmax(g, Bk, M, C, sc, sc + kStN, sc + 3 * kStN, lane);
+                bt = st_density_argmax(g, Bk, M, C, sc, sc + 1056, sc + 3456, lane);   // cells | kernel table (<= 2320) | density
             }
             mode = (bt == kStUser - 1) ? g.to : g.from + (double)bt * g.by;
         }
