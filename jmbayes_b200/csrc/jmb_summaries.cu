@@ -74,16 +74,22 @@ __device__ __forceinline__ void st_sort(const double* A, double* Bk, unsigned sh
     }
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j >= EPL; j >>= 1) {
+            // The partner of every key of this lane lives in lane ^ lm; the lane keeps the smaller key where it holds the
+            // lower position of an ascending pair (or the upper of a descending one), else the larger: compared with the
+            // sign bits flipped in the second case.  Bit masks, not branches - the compiler turns selects of three
+            // registers into divergent branches.
             const int lm = j / EPL;
-            const bool lower = (lane & lm) == 0;
+            const bool keep_min = (((lane * EPL) & k) == 0) == ((lane & lm) == 0);
+            const int flip = keep_min ? 0 : (int)0x80000000u;
 #pragma unroll
             for (int r = 0; r < EPL; ++r) {
-                const double ok = __shfl_xor_sync(kFull, key[r], lm);
+                int mh = __double2hiint(key[r]), ml = __double2loint(key[r]);
+                const int oh = __shfl_xor_sync(kFull, mh, lm), ol = __shfl_xor_sync(kFull, ml, lm);
                 const int oi = __shfl_xor_sync(kFull, id[r], lm);
-                const bool up = ((lane * EPL + r) & k) == 0;
-                const bool take = (up == lower) ? (ok < key[r]) : (ok > key[r]);
-                key[r] = take ? ok : key[r];
-                id[r] = take ? oi : id[r];
+                const int tk = (__hiloint2double(oh ^ flip, ol) < __hiloint2double(mh ^ flip, ml)) ? -1 : 0;
+                mh = (oh & tk) | (mh & ~tk); ml = (ol & tk) | (ml & ~tk);
+                id[r] = (oi & tk) | (id[r] & ~tk);
+                key[r] = __hiloint2double(mh, ml);
             }
         }
 #pragma unroll
