@@ -114,6 +114,24 @@ __device__ __forceinline__ void st_sort(const double* A, double* Bk, unsigned sh
     for (int r = 0; r < EPL; ++r) { const int e = lane * EPL + r; Bk[SKEW(e)] = key[r]; idx[e] = (unsigned short)id[r]; }
 }
 
+// Autocovariance sums of the lags 0..om of the centred, zero-padded series xc (P + 32 entries): every lane keeps its P / 32
+// elements in registers, one pass per lag; lane l returns the sum of lag l.
+template <int EPL>
+__device__ __forceinline__ double st_acf(const double* xc, int om, int lane) {
+    double xr[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) xr[i] = xc[lane + 32 * i];
+    double mine = 0.0;
+    for (int l = 0; l <= om; ++l) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) s += xr[i] * xc[lane + 32 * i + l];       // the zero padding ends the sum at M - l
+        s = st_sum(s);
+        mine = (lane == l) ? s : mine;
+    }
+    return mine;
+}
+
 // The binned Gaussian kernel estimate of density.default on the cells jlo..jhi (into Ro) from the sorted keys, and the argmax
 // over the grid points t_lo..t_hi of density()'s 1000-point grid.  Yb holds the occupied cells klo..khi, Kb the two-sided
 // table of dnorm(|d| dk, sd = bw) over the cell distances d; the three buffers are shared memory or, for long-tailed
@@ -134,10 +152,12 @@ __device__ __forceinline__ int st_density_argmax(const StGrid& g, const double* 
     // lanes whose entries are four apart read neighbouring words.
     const int off = g.span + kStKPad, Q = st_ktable_quarter(g.span);
     const double cn = 0.3989422804014327 / g.bw;
-    for (int e = lane; e < 4 * Q; e += 32) {
-        const int d = abs(e - off);
+    for (int d = lane; off + d < 4 * Q; d += 32) {           // one exp per distance, stored on both sides
         const double z = (double)d * g.dk / g.bw;
-        Kb[(e & 3) * Q + (e >> 2)] = d <= g.span ? cn * exp(-0.5 * z * z) : 0.0;
+        const double kv = d <= g.span ? cn * exp(-0.5 * z * z) : 0.0;
+        const int e1 = off + d, e0 = off - d;
+        Kb[(e1 & 3) * Q + (e1 >> 2)] = kv;
+        if (e0 >= 0) Kb[(e0 & 3) * Q + (e0 >> 2)] = kv;
     }
     __syncwarp();
     const double wi = 1.0 / (double)M;
@@ -267,11 +287,15 @@ __global__ void __launch_bounds__(192, 2) jmb_stats_kernel(const StArgs a) {
         double spec = 0.0;
         if (sd_res > 1.5e-8) {                                   // identical(all.equal(sd(res), 0), TRUE) is FALSE
             double* xc = cum;                                    // the centred series (R2 is free until the sort is done)
-            for (int m = lane; m < M + 32; m += 32) xc[m] = m < M ? A[m] - mean : 0.0;
+            for (int m = lane; m < P + 32; m += 32) xc[m] = m < M ? A[m] - mean : 0.0;
             __syncwarp();
-            double r = 0.0;                                      // lane l: autocovariance at lag l (divisor n)
-#pragma unroll 4
-            for (int m = 0; m < M; ++m) r += xc[m] * xc[m + lane];       // the zero padding ends every lag's sum at M - l
+            double r;                                            // lane l: autocovariance at lag l (divisor n)
+            switch (P) {
+                case 128: r = st_acf<4>(xc, a.om, lane); break;
+                case 256: r = st_acf<8>(xc, a.om, lane); break;
+                case 512: r = st_acf<16>(xc, a.om, lane); break;
+                default: r = st_acf<32>(xc, a.om, lane); break;
+            }
             r /= (double)M;
             double phi = 0.0;                                    // lane j: coefficient j of the current order
             double v = __shfl_sync(kFull, r, 0);
