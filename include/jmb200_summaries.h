@@ -62,6 +62,10 @@ int jmb_stand_weights(const double* LogLiks, int32_t M, double* weights);
 int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32_t M, int64_t series_stride, int64_t draw_stride,
                         const double* weights, const double probs[2], int on_device, jmb_stats_out* out, float* kernel_ms);
 
+/* jmb_mcmc_statistics keeps its device buffers (staging, scratch, outputs) and streams per device between calls; this frees
+ * them (additive: the reference has no such state). */
+int jmb_stats_release(void);
+
 #ifdef __cplusplus
 }
 #endif

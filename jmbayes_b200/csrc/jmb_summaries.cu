@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -444,7 +445,41 @@ using namespace jmb;
 
 namespace {
 int fail(const std::string& m) { return jmb_set_error(m); }
+
+// Device buffers and streams of jmb_mcmc_statistics, kept per device between calls (grow-only; jmb_stats_release frees
+// them): allocating and freeing ~0.7 GB per call costs more than the kernel at small S.
+struct StWorkspace {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // weights, scratch, staging 0, staging 1, outputs
+    size_t cap[5] = {0, 0, 0, 0, 0};
+};
+constexpr int kStMaxDevices = 64;
+std::mutex g_st_mu;
+StWorkspace g_st_ws[kStMaxDevices];
+
+cudaError_t st_reserve(StWorkspace& w, int slot, size_t bytes) {
+    if (w.cap[slot] >= bytes) return cudaSuccess;
+    if (w.buf[slot]) cudaFree(w.buf[slot]);
+    w.buf[slot] = nullptr; w.cap[slot] = 0;
+    const cudaError_t e = cudaMalloc(&w.buf[slot], bytes);
+    if (e == cudaSuccess) w.cap[slot] = bytes;
+    return e;
+}
 }  // namespace
+
+extern "C" int jmb_stats_release(void) {
+    std::lock_guard<std::mutex> lock(g_st_mu);
+    for (int d = 0; d < kStMaxDevices; ++d) {
+        StWorkspace& w = g_st_ws[d];
+        bool used = w.st[0] || w.st[1];
+        for (int k = 0; k < 5; ++k) used = used || w.buf[k];
+        if (!used) continue;
+        if (cudaSetDevice(d) != cudaSuccess) continue;
+        for (int k = 0; k < 5; ++k) { if (w.buf[k]) cudaFree(w.buf[k]); w.buf[k] = nullptr; w.cap[k] = 0; }
+        for (auto& s : w.st) { if (s) cudaStreamDestroy(s); s = nullptr; }
+    }
+    return 0;
+}
 
 extern "C" int jmb_stand_weights(const double* LogLiks, int32_t M, double* weights) {
     if (!LogLiks || !weights || M <= 0) return fail("jmb_stand_weights: NULL argument or M <= 0");
@@ -475,22 +510,20 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
     if (!(sumw > 0.0)) return fail("jmb_mcmc_statistics: weights sum to zero");
     for (int m = 0; m < M; ++m) { const double t = weights[m] / sumw; sumwt2 += t * t; }
 
+    if (device < 0 || device >= kStMaxDevices) return fail("jmb_mcmc_statistics: device out of range");
+    std::lock_guard<std::mutex> lock(g_st_mu);
+    StWorkspace& ws = g_st_ws[device];
     cudaError_t e;
-    std::vector<void*> owned;
-    cudaStream_t st[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> evs;
-    auto cleanup = [&]() {
-        for (void* p : owned) cudaFree(p);
-        for (auto ev : evs) cudaEventDestroy(ev);
-        for (auto s : st) if (s) cudaStreamDestroy(s);
-    };
+    auto cleanup = [&]() { for (auto ev : evs) cudaEventDestroy(ev); };
 #define CUS(call) do { e = (call); if (e != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e); cleanup(); return fail(m_); } } while (0)
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail("jmb_mcmc_statistics: no CUDA device (there is no CPU fallback)");
     CUS(cudaSetDevice(device));
     int num_sms = 0;
     CUS(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
-    for (auto& s : st) CUS(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& sx : ws.st) if (!sx) CUS(cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking));
+    cudaStream_t* st = ws.st;
 
     StArgs a{};
     a.M = M; a.P = 4; while (a.P < M) a.P <<= 1;
@@ -501,12 +534,12 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
     a.om = (int)std::min<double>(M - 1, std::floor(10.0 * std::log10((double)M)));
     const size_t smem = sizeof(double) * ((size_t)(M + 1) / 2 * 2 + (size_t)a.warps * st_warp_doubles(a.P));
     CUS(cudaFuncSetAttribute(jmb_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    double* d_w = nullptr;
-    CUS(cudaMalloc(&d_w, sizeof(double) * M)); owned.push_back(d_w);
+    CUS(st_reserve(ws, 0, sizeof(double) * JMB_STATS_MAX_M));
+    double* d_w = static_cast<double*>(ws.buf[0]);
     const int max_grid = 2 * num_sms;
-    double* d_scratch = nullptr;
     const size_t scratch_doubles = (size_t)kStScratch * max_grid * a.warps;       // one set per stream
-    CUS(cudaMalloc(&d_scratch, sizeof(double) * 2 * scratch_doubles)); owned.push_back(d_scratch);
+    CUS(st_reserve(ws, 1, sizeof(double) * 2 * scratch_doubles));
+    double* d_scratch = static_cast<double*>(ws.buf[1]);
     a.scratch = d_scratch;
     CUS(cudaMemcpy(d_w, weights, sizeof(double) * M, cudaMemcpyHostToDevice));
     a.w = d_w;
@@ -515,10 +548,10 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
                             out->StErr, out->CIs, out->wCIs, out->Pvalues};
     const int width[10] = {1, 1, 1, 1, 1, 1, 1, 2, 2, 1};
     double* dev_out[10] = {nullptr};
-    for (int k = 0; k < 10; ++k) {
+    if (!on_device) CUS(st_reserve(ws, 4, sizeof(double) * 12 * (size_t)S));
+    for (int k = 0, col = 0; k < 10; col += width[k], ++k) {
         if (!host_out[k]) continue;
-        if (on_device) dev_out[k] = host_out[k];
-        else { CUS(cudaMalloc(&dev_out[k], sizeof(double) * width[k] * S)); owned.push_back(dev_out[k]); }
+        dev_out[k] = on_device ? host_out[k] : static_cast<double*>(ws.buf[4]) + (size_t)col * S;
     }
     auto launch = [&](const double* xd, long long s0, long long count, long long sstride, long long dstride, cudaStream_t stream) {
         StArgs b = a;
@@ -545,7 +578,7 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
         // stream the series through two device buffers: copy of chunk c + 1 overlaps the kernel of chunk c
         const long long chunk = std::max<long long>(a.warps, std::min<long long>(S, (256LL << 20) / (8LL * M)) / a.warps * a.warps);
         double* d_x[2] = {nullptr, nullptr};
-        for (auto& p : d_x) { CUS(cudaMalloc(&p, sizeof(double) * chunk * M)); owned.push_back(p); }
+        for (int c2 = 0; c2 < 2; ++c2) { CUS(st_reserve(ws, 2 + c2, sizeof(double) * chunk * M)); d_x[c2] = static_cast<double*>(ws.buf[2 + c2]); }
         int c = 0;
         for (long long s0 = 0; s0 < S; s0 += chunk, c ^= 1) {
             const long long cnt = std::min<long long>(chunk, S - s0);
@@ -561,7 +594,7 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
             CUS(cudaGetLastError());
         }
     }
-    for (auto s : st) CUS(cudaStreamSynchronize(s));
+    for (int c2 = 0; c2 < 2; ++c2) CUS(cudaStreamSynchronize(st[c2]));
     if (kernel_ms) {
         *kernel_ms = 0.f;
         for (size_t k = 0; k + 1 < evs.size(); k += 2) { float ms = 0.f; CUS(cudaEventElapsedTime(&ms, evs[k], evs[k + 1])); *kernel_ms += ms; }

@@ -38,6 +38,11 @@ def _check(rc):
         raise api.JmbError(_lib().jmb_last_error().decode())
 
 
+def release():
+    """Free the device buffers ``jmb_mcmc_statistics`` keeps between calls."""
+    _check(_lib().jmb_stats_release())
+
+
 def stand(LogLiks):
     """``stand()`` (``R/mvJointModelBayes.R:940-945``)."""
     x = np.ascontiguousarray(LogLiks, dtype=np.float64)
