@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -528,7 +529,8 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
     StArgs a{};
     a.M = M; a.P = 4; while (a.P < M) a.P <<= 1;
     a.P = std::max(a.P, 128);
-    a.warps = a.P <= 512 ? 6 : 4;                 // two CTAs per SM
+    a.warps = 4;                                  // three CTAs per SM at M <= 512 (74 kB each), two at M <= 1024
+    if (const char* ev = getenv("JMB_STATS_WARPS")) { const int wv = atoi(ev); if (wv >= 1 && wv <= 6) a.warps = wv; }   // experiments
     a.sumw = sumw; a.sumwt2 = sumwt2; a.p_lo = probs[0]; a.p_hi = probs[1];
     a.m_pow = std::pow((double)M, -0.2);
     a.om = (int)std::min<double>(M - 1, std::floor(10.0 * std::log10((double)M)));
@@ -536,7 +538,9 @@ extern "C" int jmb_mcmc_statistics(int device, const double* x, int64_t S, int32
     CUS(cudaFuncSetAttribute(jmb_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUS(st_reserve(ws, 0, sizeof(double) * JMB_STATS_MAX_M));
     double* d_w = static_cast<double*>(ws.buf[0]);
-    const int max_grid = 2 * num_sms;
+    int per_sm = 1;
+    CUS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jmb_stats_kernel, 32 * a.warps, smem));
+    const int max_grid = std::max(per_sm, 1) * num_sms;
     const size_t scratch_doubles = (size_t)kStScratch * max_grid * a.warps;       // one set per stream
     CUS(st_reserve(ws, 1, sizeof(double) * 2 * scratch_doubles));
     double* d_scratch = static_cast<double*>(ws.buf[1]);
