@@ -503,14 +503,16 @@ def run_config5(args):
 
 
 def _stats_cpu(S, seed=99):
-    """R's summary_fun is a serial apply(): the restated R code (oracle/oracle_stats.py, NumPy) on one core."""
+    """R's summary_fun is a serial apply(): the restated R code in plain C (oracle/jmb_oracle_stats.c) on one core."""
     import numpy as np
-    from oracle import oracle_stats
+    from oracle import oracle, oracle_stats
+    oracle.build()
     rng = np.random.default_rng(seed)
     X = np.cumsum(rng.normal(size=(S, STATS_M)), axis=1) * 0.05 + rng.normal(size=(S, STATS_M))
     w = oracle_stats.stand(rng.normal(size=STATS_M))
+    oracle_stats.statistics_c(X[:8], w)
     t0 = time.perf_counter()
-    oracle_stats.statistics(X, w)
+    oracle_stats.statistics_c(X, w)
     dt = time.perf_counter() - t0
     return S / dt, dt
 
@@ -518,16 +520,16 @@ def _stats_cpu(S, seed=99):
 def run_summaries_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    _, dt0 = _stats_cpu(200)
-    S = int(min(20000, max(200, 200 * 15.0 / max(dt0, 1e-3))))
+    _, dt0 = _stats_cpu(500)
+    S = int(min(100000, max(500, 500 * 15.0 / max(dt0, 1e-3))))
     val, dt = _stats_cpu(S)
     line = {"impl": "reference", "metric": STATS_METRIC, "value": val, "unit": STATS_UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "summaries", "series": S, "M": STATS_M,
-                       "note": "restated summary_fun sweeps (R absent from the image), serial as R's apply()"},
+                       "note": "restated summary_fun sweeps in plain C (R absent from the image), serial as R's apply()"},
             "cpu_baseline": {"value": val, "unit": STATS_UNIT, "cores": 1, "kind": "port",
-                             "sample": f"{S} series x {STATS_M} draws, ten statistics, NumPy restatement ({dt:.1f} s)"},
+                             "sample": f"{S} series x {STATS_M} draws, ten statistics, plain-C restatement, one thread as R's apply() ({dt:.1f} s)"},
             "e2e": {"value": val, "unit": STATS_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -627,11 +629,11 @@ def run_summaries(args):
         "gpu_launches": steps, "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, dt0 = _stats_cpu(200)
-        Sc = int(min(20000, max(200, 200 * 12.0 / max(dt0, 1e-3))))
+        _, dt0 = _stats_cpu(500)
+        Sc = int(min(100000, max(500, 500 * 12.0 / max(dt0, 1e-3))))
         val, dt = _stats_cpu(Sc)
         line["cpu_baseline"] = {"value": val, "unit": STATS_UNIT, "cores": 1, "kind": "port",
-                                "sample": f"{Sc} series x {M} draws, ten statistics, NumPy restatement of the serial R sweeps ({dt:.1f} s)"}
+                                "sample": f"{Sc} series x {M} draws, ten statistics, plain-C restatement of the serial R sweeps, one thread ({dt:.1f} s)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -32,7 +32,7 @@ def _cpu_stamp() -> str:
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(HERE, f) for f in ("jmb_oracle.c", "jmb_oracle.h", "jmb_oracle_svft.c", "jmb_oracle_svft.h", "jmb_oracle_mll.c", "jmb_oracle_mll.h")]
+    src = [os.path.join(HERE, f) for f in ("jmb_oracle.c", "jmb_oracle.h", "jmb_oracle_svft.c", "jmb_oracle_svft.h", "jmb_oracle_mll.c", "jmb_oracle_mll.h", "jmb_oracle_stats.c")]
     stamp_file = os.path.join(HERE, "_build", "cpu.stamp")
     stamp = _cpu_stamp()
     old = open(stamp_file).read() if os.path.exists(stamp_file) else ""

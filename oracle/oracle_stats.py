@@ -262,3 +262,28 @@ def statistics(X, weights, probs=(0.025, 0.975)):
         "EffectiveSize": effective_size(X), "StDev": st_dev(X), "wStDev": w_st_dev(X, weights), "StErr": std_err(X),
         "CIs": cis(X, probs), "wCIs": w_cis(X, weights, probs), "Pvalues": p_values(X),
     }
+
+
+C_ROWS = ("postMeans", "postwMeans", "postModes", "EffectiveSize", "StDev", "wStDev", "StErr", "CIs0", "CIs1", "wCIs0", "wCIs1", "Pvalues")
+
+
+def statistics_c(X, weights, probs=(0.025, 0.975)):
+    """The same ten entries from the independently written plain-C restatement (oracle/jmb_oracle_stats.c)."""
+    import ctypes as C
+
+    from . import oracle
+    L = oracle.lib()
+    dp = C.POINTER(C.c_double)
+    L.orc_stats.argtypes = [dp, C.c_long, C.c_int, dp, dp, dp]
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    pr = np.ascontiguousarray(probs, dtype=np.float64)
+    S, M = X.shape
+    out = np.empty((12, S))
+    rc = L.orc_stats(X.ctypes.data_as(dp), S, M, w.ctypes.data_as(dp), pr.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    if rc:
+        raise RuntimeError(f"orc_stats failed with code {rc}")
+    res = {name: out[k] for k, name in enumerate(C_ROWS) if not name[-1].isdigit()}
+    res["CIs"] = np.stack([out[7], out[8]], axis=1)
+    res["wCIs"] = np.stack([out[9], out[10]], axis=1)
+    return res
