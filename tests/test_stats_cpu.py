@@ -173,3 +173,32 @@ def test_stand_weights_host_function_and_loud_failure_without_a_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(api.JmbError, match="no CUDA device"):
             summaries.series_statistics(X, 3, 64, 64, 1, np.ones(64))
+
+
+def test_statistics_margins_and_layouts_with_a_stand_in_backend(monkeypatch):
+    """Host logic of summaries.statistics(): apply margins, strides and output shapes, checked on CPU by serving
+    series_statistics from the restatement (the GPU test of the same name runs the real kernel)."""
+    from jmbayes_b200 import summaries
+
+    def fake(x, S, M, ss, ds, weights, probs=(0.025, 0.975), device=0, want=summaries.NAMES):
+        flat = np.asarray(x).reshape(-1)
+        X = np.stack([flat[s * ss : s * ss + (M - 1) * ds + 1 : ds] for s in range(S)])
+        r = st.statistics_c(X, weights, probs)
+        return {k: r[k] for k in want}, 0.0
+
+    monkeypatch.setattr(summaries, "series_statistics", fake)
+    monkeypatch.setattr(summaries, "stand", st.stand)
+    rng = np.random.default_rng(12)
+    M, n, q = 60, 7, 3
+    mcmc = {"alphas": rng.normal(size=(M, 2)), "D": rng.normal(size=(M, q, q)), "b": rng.normal(size=(n, q, M)),
+            "tau": rng.gamma(2.0, size=M), "none": None}
+    res = summaries.statistics(mcmc, LogLiks=rng.normal(size=M))["statistics"]
+    assert "none" not in res["postMeans"]
+    assert np.allclose(res["postMeans"]["alphas"], mcmc["alphas"].mean(0))
+    assert np.allclose(res["postMeans"]["D"], mcmc["D"].mean(0))
+    assert np.allclose(res["postMeans"]["b"], mcmc["b"].mean(2))
+    assert np.isclose(res["postMeans"]["tau"], mcmc["tau"].mean())
+    assert res["CIs"]["b"].shape == (2, n, q) and res["CIs"]["D"].shape == (2, q, q) and res["CIs"]["tau"].shape == (2,)
+    assert np.allclose(res["CIs"]["b"][0], np.quantile(mcmc["b"], 0.025, axis=2))
+    assert np.allclose(res["CIs"]["D"][1], np.quantile(mcmc["D"], 0.975, axis=0))
+    assert np.allclose(res["StDev"]["alphas"], mcmc["alphas"].std(0, ddof=1))
