@@ -16,6 +16,9 @@
  *   CIs            quantile(x, probs = c(0.025, 0.975), na.rm = TRUE) (type 7)                       :967
  *   wCIs           Hmisc::wtd.quantile(x, weights, probs, type = "i/(n+1)", na.rm = TRUE)            :968-970
  *   Pvalues        computeP (R/computeP.R:1-6): 2 min(mean(x >= 0), mean(x < 0))                     :971
+ * density() is the algorithm of R <= 4.3, the releases the reference was written against (from R 4.4.0 on:
+ * density(old.coords = TRUE); the new default grid changes the estimate by a factor of about 0.999 and can move a mode by
+ * one cell of the 1000-point grid).
  * and jmb_stand_weights is stand() (:940-945).  Draws are assumed free of NA (the chains never produce one); a series that
  * holds a NaN yields NaN statistics.  Conventions as in jmb200.h: plain pointers and sizes, caller-allocated outputs, 0 on
  * success / jmb_last_error() otherwise, no CPU fallback.

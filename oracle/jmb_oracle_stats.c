@@ -8,6 +8,7 @@
  * functions follow the published algorithms of base R's stats package (mean, var, quantile type 7, cov.wt, bw.nrd,
  * density.default = BinDist + FFT convolution + approx, ar.yw.default = acf + eureka + AIC) and of Hmisc's
  * wtd.quantile(type = "i/(n+1)") / wtd.Ecdf / wtd.table.
+ * density.default is the algorithm of R <= 4.3 (= density(old.coords = TRUE) from R 4.4.0 on), see oracle_stats.py.
  *
  * Series are the rows of X (S x M, row-major).  Output: out[k * S + s], k = 0 postMeans, 1 postwMeans, 2 postModes,
  * 3 EffectiveSize, 4 StDev, 5 wStDev, 6 StErr, 7 / 8 CIs lower / upper, 9 / 10 wCIs lower / upper, 11 Pvalues.

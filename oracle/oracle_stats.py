@@ -7,6 +7,9 @@ restates the R code it cites; where the arithmetic lives outside /root/reference
   * base R `stats` (R >= 3.x; DESCRIPTION pins no version): mean, var / sd, quantile (type 7), cov.wt, bw.nrd,
     density.default (linear binning BinDist + FFT convolution + approx), ar.yw.default (acf with divisor n, Levinson
     recursion `eureka`, AIC order selection), all.equal.numeric;
+  * density.default is restated as it stood up to R 4.3 (the releases JMbayes 0.8 was developed against): the kernel
+    ordinates are spaced 2 (up - lo) / (2n - 1) apart while the cells are (up - lo) / (n - 1) wide.  R 4.4.0 changed the
+    grid ("old.coords = FALSE", densities differ by a factor of about 0.999); density(old.coords = TRUE) is this algorithm.
   * Hmisc (Imports of DESCRIPTION:13, no version pinned): wtd.quantile(type = "i/(n+1)") through wtd.Ecdf / wtd.table.
 Checked in tests/test_stats_cpu.py against numpy.quantile, numpy.cov(aweights), scipy.linalg.solve_toeplitz and
 analytic cases.
