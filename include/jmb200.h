@@ -61,7 +61,8 @@ typedef struct jmb_data {
     int32_t n_gammas;       /* ncol(W2) (0 -> the *_nogammas flavour) */
     int32_t K;              /* quadrature points per subject (15 or 7) */
     int32_t interval_cens;  /* lap_rwm_C argument `interval_cens` */
-    int32_t multi_state;    /* lap_rwm_C argument `multiState`; must be 0 (out of scope) */
+    int32_t multi_state;    /* lap_rwm_C argument `multiState`: the survival part has nT transition rows, several
+                               per subject (see the multi-state fields at the end of this struct) */
     int64_t subject_offset; /* global index of local subject 0: keys the counter RNG so that a
                                sharded run reproduces the single-GPU chain */
     /* longitudinal part, per outcome k */
@@ -107,6 +108,17 @@ typedef struct jmb_data {
     const double* Time;             /* [n]  event times */
     const double* st;               /* [nK] c(t(st)): quadrature times */
     const double* st_int;           /* [nK] (interval_cens only) */
+    /* Multi-state fits (multi_state != 0; src/fast_LAPRWM.cpp:519-529, R/mvJointModelBayes.R:76-101,559-570,651-670):
+     * every array documented above with n (or nK) survival rows - event, W1, W2, ZZ[[t]], U[[t]], XXbetas[[t]] and
+     * W1s, W2s, Pw, ZZs[[t]], Us[[t]], XXsbetas[[t]], idGK_fast - then has nT (or nT * K) rows, one per transition a
+     * subject is at risk for, grouped by subject in subject order; n stays the number of subjects (rows of b).
+     * Ignored when multi_state == 0.  interval_cens and the knots alternative cannot be combined with it. */
+    int32_t nT;                     /* length(Data$event) */
+    int32_t nRisks;                 /* Data$nRisks: strata of the baseline hazard */
+    const int32_t* idT;             /* [nT] subject of each transition row = Data$idT2[[t]] - 1 (the same for every t);
+                                       rows_wlong / rows_wlongs / idT2s / idT_rsum follow from it */
+    const int32_t* kn_strat_first;  /* [nRisks] first / last column of W1 owned by each stratum (0-based, as R builds */
+    const int32_t* kn_strat_last;   /*          them, R/mvJointModelBayes.R:668-669) */
 } jmb_data;
 
 /* The per-draw part of `Data` (R/mvJointModelBayes.R:760-770). */
@@ -164,7 +176,7 @@ typedef struct jmb_control {
 typedef struct jmb_chain_in {
     const double* b;              /* n x q */
     const double* Bs_gammas; const double* gammas; const double* alphas;
-    const double* tau_Bs_gammas;  /* [1] */
+    const double* tau_Bs_gammas;  /* [1]; [nRisks] for a multi-state fit (R/mvJointModelBayes.R:723-724) */
     double tau_gammas, tau_alphas;
     const double* phi_gammas;     /* [p] */
     const double* phi_alphas;     /* [A] */
@@ -182,7 +194,7 @@ typedef struct jmb_chain_out {
     double* alphas;          /* A x n_out */
     double* phi_gammas;      /* p x n_out */
     double* phi_alphas;      /* A x n_out */
-    double* tau_Bs_gammas;   /* 1 x n_out */
+    double* tau_Bs_gammas;   /* 1 x n_out; nRisks x n_out for a multi-state fit (src/fast_LAPRWM.cpp:607) */
     double* tau_gammas;      /* [n_out] */
     double* tau_alphas;      /* [n_out] */
     double* tau_td_alphas;   /* n_td x n_out */
@@ -201,10 +213,10 @@ typedef struct jmb_chain_out {
 typedef struct jmb_eval_out {
     double* log_pyb;  /* [n] */
     double* log_pb;   /* [n] */
-    double* log_h;    /* [n] */
-    double* H;        /* [n] */
-    double* HL;       /* [n] (interval_cens only; may be NULL) */
-    double* log_ptb;  /* [n] */
+    double* log_h;    /* [n]; [nT] for a multi-state fit (one value per transition row) */
+    double* H;        /* [n]; [nT] */
+    double* HL;       /* [n] (interval_cens only; may be NULL); [nT] */
+    double* log_ptb;  /* [n]; [nT] - the b-step uses rowsum(log_ptb, idT_rsum), src/fast_LAPRWM.cpp:669 */
 } jmb_eval_out;
 
 const char* jmb_last_error(void);

@@ -40,6 +40,8 @@ class JmbData(C.Structure):
         ("Covs_b", c_double_p),
         ("knots", c_double_p), ("n_knots", C.c_int32), ("ord", C.c_int32), ("Time", c_double_p), ("st", c_double_p),
         ("st_int", c_double_p),
+        ("nT", C.c_int32), ("nRisks", C.c_int32), ("idT", c_int32_p), ("kn_strat_first", c_int32_p),
+        ("kn_strat_last", c_int32_p),
     ]
 
 
@@ -152,7 +154,7 @@ def marshal_data(Data: dict, Covs_b, interval_cens: bool, multi_state: bool = Fa
     dense W1 / W1s (/ W1s_int); the library evaluates splineDesign itself."""
     k = Keep()
     d = JmbData()
-    n = int(np.asarray(Data["event"]).shape[0])
+    n = int(np.asarray(Covs_b).shape[2]) if multi_state else int(np.asarray(Data["event"]).shape[0])
     O = len(Data["y"])
     T = len(Data["XXbetas"])
     ns = int(np.asarray(Data["Pw"]).shape[0])
@@ -163,7 +165,12 @@ def marshal_data(Data: dict, Covs_b, interval_cens: bool, multi_state: bool = Fa
     d.n_Bs = int(W1.shape[1])
     d.n_gammas = int(W2.shape[1]) if W2.ndim == 2 else 0
     d.n_alphas = int(sum(len(c) for c in Data["col_inds"]))
-    d.K = int(K if K is not None else ns // n)
+    nT = int(np.asarray(Data["event"]).shape[0])
+    d.K = int(K if K is not None else ns // nT)
+    if multi_state:     # Data$idT2 (subject of each transition row), nRisks, kn_strat_* (R/mvJointModelBayes.R:651-670)
+        d.nT, d.nRisks = nT, int(Data["nRisks"])
+        d.idT = k.i32(np.asarray(Data["idT2"][0]))
+        d.kn_strat_first, d.kn_strat_last = k.i32(Data["kn_strat_first"]), k.i32(Data["kn_strat_last"])
     d.interval_cens = int(bool(interval_cens))
     d.multi_state = int(bool(multi_state))
     d.subject_offset = int(subject_offset)
@@ -281,14 +288,14 @@ def marshal_chain_in(inits: dict, scales: dict, Covs: dict):
     return s, k
 
 
-def alloc_chain_out(n, q, B, p, A, n_td, n_out, total_iters, extras=True):
+def alloc_chain_out(n, q, B, p, A, n_td, n_out, total_iters, extras=True, n_risks=1):
     """Caller-allocated outputs shaped like the list lap_rwm_C returns."""
     no = max(n_out, 0)
     bufs = dict(
         b=np.zeros((n, q, no), order="F"), Bs_gammas=np.zeros((B, no), order="F"),
         gammas=np.zeros((p, no), order="F"), alphas=np.zeros((A, no), order="F"),
         phi_gammas=np.zeros((p, no), order="F"), phi_alphas=np.zeros((A, no), order="F"),
-        tau_Bs_gammas=np.zeros((1, no), order="F"), tau_gammas=np.zeros(no), tau_alphas=np.zeros(no),
+        tau_Bs_gammas=np.zeros((n_risks, no), order="F"), tau_gammas=np.zeros(no), tau_alphas=np.zeros(no),
         tau_td_alphas=np.zeros((n_td, no), order="F"), logWeights=np.zeros(no),
         sigma_b=np.zeros(n), sigma_surv=np.zeros(3), Sigma_Bs_gammas=np.zeros((B, B), order="F"),
         Sigma_gammas=np.zeros((p, p), order="F"), Sigma_alphas=np.zeros((A, A), order="F"))

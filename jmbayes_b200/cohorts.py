@@ -382,6 +382,180 @@ def make_cohort(config: str = "config3", n: int = 1000, seed: int | None = None,
                             g0=g0, a0=a0, n_ev=n_ev))
 
 
+def make_multistate_cohort(n: int = 300, seed: int = 20253, K: int = 15, mean_visits: float = 6.0,
+                           draw_jitter: float = 0.02) -> dict:
+    """Illness-death cohort in the reference's multi-state ``Data`` contract (``multiState = TRUE``,
+    R/mvJointModelBayes.R:76-101,139-150,351-378,559-570,588-600,651-670; src/fast_LAPRWM.cpp:519-529).
+
+    Every subject is at risk for transitions 1 (healthy -> ill) and 2 (healthy -> dead) on ``(0, stop]``; subjects who
+    fall ill add a row for transition 3 (ill -> dead) on ``(T_ill, stop]``.  The survival part therefore has
+    ``nT = sum(2 or 3)`` rows grouped by subject (``idT2``), the baseline hazard is stratified by transition
+    (``nRisks = 3``; block-structured ``W1`` / ``Tau_Bs_gammas``; ``kn_strat_first/last``), ``W2`` holds
+    transition-specific covariate effects, term 0 (value of the gaussian outcome) interacts with the transition
+    (``U`` = stratum indicators, 3 columns of ``Wlong``) and term 1 (value of the binary outcome's linear predictor,
+    ``expit``-transformed) has the default ``U`` of ones.
+    """
+    rng = np.random.default_rng(seed)
+    sk, wk = gauss_kronrod(K)
+    fams, links = ["gaussian", "binomial"], ["identity", "logit"]
+    betas = [np.array([1.0, 0.3]), np.array([-0.5, 0.25])]
+    sd = np.array([0.77, 0.32, 0.6, 0.2])
+    Rho = np.full((4, 4), 0.2); np.fill_diagonal(Rho, 1.0)
+    D = Rho * np.outer(sd, sd)
+    O, q, nR = 2, 4, 3
+    sigma_true = 0.4
+    gammas_true = np.array([-0.3, 0.2, 0.1])                  # effect of x on each transition
+    alphas_true = np.array([0.3, 0.2, 0.4, 0.5])              # value1 x transition (3), expit(value2)
+    base = np.log(np.array([0.04, 0.02, 0.08]) * 1.3)
+    b = rng.multivariate_normal(np.zeros(q), D, size=n)
+    x = rng.normal(size=n)
+    t_max = 10.0
+
+    def log_haz(h, t, rows):
+        v1 = betas[0][0] + b[rows, 0][:, None] + (betas[0][1] + b[rows, 1][:, None]) * t
+        v2 = betas[1][0] + b[rows, 2][:, None] + (betas[1][1] + b[rows, 3][:, None]) * t
+        return (base[h] + 0.3 * np.log(t) + gammas_true[h] * x[rows][:, None] + alphas_true[h] * v1
+                + alphas_true[3] / (1.0 + np.exp(-v2)))
+
+    grid = np.linspace(0.0, t_max, 401)[1:]
+    dg = grid[1] - grid[0]
+    mid = grid - 0.5 * dg
+    rows_all = np.arange(n)
+
+    def draw_time(h, start):
+        haz = np.exp(np.clip(log_haz(h, mid[None, :], rows_all), -50, 50)) * dg
+        haz = np.where(mid[None, :] > start[:, None], haz, 0.0)
+        cum = np.cumsum(haz, axis=1)
+        E = rng.exponential(size=n)
+        idx = (cum < E[:, None]).sum(axis=1)
+        t = np.where(idx >= grid.size, np.inf, grid[np.minimum(idx, grid.size - 1)])
+        return t * (1.0 + 1e-3 * rng.uniform(-1, 1, n))
+
+    T01, T02 = draw_time(0, np.zeros(n)), draw_time(1, np.zeros(n))
+    stop1 = np.maximum(np.minimum(np.minimum(T01, T02), t_max), 1e-4)
+    ill = (T01 < T02) & (T01 < t_max)
+    dead_direct = (T02 <= T01) & (T02 < t_max)
+    T12 = draw_time(2, np.where(ill, stop1, t_max))
+    stop2 = np.minimum(np.maximum(T12, stop1 + 1e-3), t_max)
+    # transition rows, grouped by subject
+    idT, trans, TimeL, TimeR, event = [], [], [], [], []
+    for i in range(n):
+        idT += [i, i]; trans += [0, 1]; TimeL += [0.0, 0.0]; TimeR += [stop1[i], stop1[i]]
+        event += [float(ill[i]), float(dead_direct[i])]
+        if ill[i]:
+            idT.append(i); trans.append(2); TimeL.append(stop1[i]); TimeR.append(stop2[i]); event.append(float(T12[i] < t_max))
+    idT = np.array(idT, dtype=np.int32); trans = np.array(trans); TimeL = np.array(TimeL); TimeR = np.array(TimeR)
+    event = np.array(event)
+    nT = idT.size
+    last_time = np.where(ill, stop2, stop1)
+
+    # ---- visits ---------------------------------------------------------------------------------
+    v = 1 + rng.poisson(mean_visits, n)
+    N = int(v.sum())
+    row_ptr = np.concatenate([[0], np.cumsum(v)])
+    idL = np.repeat(np.arange(n), v)
+    tt = rng.uniform(size=N) * last_time[idL]
+    tt[row_ptr[:-1]] = 0.0
+    tt = tt[np.lexsort((tt, idL))]
+    idL2 = (row_ptr[1:] - 1).astype(np.int32)
+    y, X, Z = [], [], []
+    for k in range(O):
+        Xk = np.column_stack([np.ones(N), tt])
+        eta = Xk @ betas[k] + b[idL, 2 * k] + b[idL, 2 * k + 1] * tt
+        y.append(eta + sigma_true * rng.normal(size=N) if k == 0 else rng.binomial(1, 1.0 / (1.0 + np.exp(-eta))).astype(float))
+        X.append(_F(Xk)); Z.append(_F(Xk.copy()))
+    betas_draw = [bk + draw_jitter * rng.normal(size=2) for bk in betas]
+    sigma_draw = sigma_true * np.exp(draw_jitter * rng.normal())
+    invD = np.linalg.inv(D); invD = 0.5 * (invD + invD.T)
+
+    # ---- quadrature grid (R/mvJointModelBayes.R:121-135) -------------------------------------------
+    P = (TimeR - TimeL) / 2.0
+    st_vec = (np.outer(P, sk) + ((TimeR + TimeL) / 2.0)[:, None]).reshape(-1)
+    Pw = np.repeat(P, K) * np.tile(wk, nT)
+    trans_s = np.repeat(trans, K)
+
+    # ---- stratified baseline hazard (R/mvJointModelBayes.R:154-208,351-373) -----------------------
+    W1_blocks, W1s_blocks, knots_strat, Tau_blocks = [], [], [], []
+    for h in range(nR):
+        th, sh = TimeR[trans == h], st_vec[trans_s == h]
+        pp = np.quantile(th, [0.05, 0.95])
+        kn = np.linspace(pp[0], pp[1], 5)[1:-1]                 # lng.in.kn.multiState = 5
+        rr = np.array([min(th.min(), sh.min()), max(th.max(), sh.max())])
+        knots = np.sort(np.concatenate([np.repeat(rr, 4), kn]))
+        w1 = np.zeros((nT, len(knots) - 4), order="F"); w1[trans == h] = spline_design(knots, th)
+        w1s = np.zeros((nT * K, len(knots) - 4), order="F"); w1s[trans_s == h] = spline_design(knots, sh)
+        W1_blocks.append(w1); W1s_blocks.append(w1s); knots_strat.append(w1.shape[1])
+        DD = np.diff(np.eye(w1.shape[1]), n=2, axis=0)
+        Tau_blocks.append(DD.T @ DD + 1e-6 * np.eye(w1.shape[1]))
+    W1, W1s = _F(np.hstack(W1_blocks)), _F(np.hstack(W1s_blocks))
+    knots_strat = np.array(knots_strat)
+    B = int(knots_strat.sum())
+    kn_last = (np.cumsum(knots_strat) - 1).astype(np.int32)
+    kn_first = (np.cumsum(knots_strat) - knots_strat).astype(np.int32)
+    Tau_Bs = np.zeros((B, B))
+    for h in range(nR):
+        Tau_Bs[kn_first[h]:kn_last[h] + 1, kn_first[h]:kn_last[h] + 1] = Tau_blocks[h]
+    W2 = np.zeros((nT, nR)); W2[np.arange(nT), trans] = x[idT]
+    W2s = _F(np.repeat(W2, K, axis=0))
+
+    # ---- association terms ---------------------------------------------------------------------------
+    ind = np.zeros((nT, nR)); ind[np.arange(nT), trans] = 1.0
+    zfun = lambda t: np.column_stack([np.ones_like(t), t])
+    XXbetas = [zfun(TimeR) @ betas_draw[k] for k in range(O)]
+    XXsbetas = [zfun(st_vec) @ betas_draw[k] for k in range(O)]
+    ZZ = [_F(zfun(TimeR)) for _ in range(O)]; ZZs = [_F(zfun(st_vec)) for _ in range(O)]
+    U = [_F(ind), _F(np.ones((nT, 1)))]
+    Us = [_F(np.repeat(ind, K, axis=0)), _F(np.ones((nT * K, 1)))]
+    RE_inds = [np.array([0, 1], dtype=np.int32), np.array([2, 3], dtype=np.int32)]
+    col_inds = [np.array([0, 1, 2], dtype=np.int32), np.array([3], dtype=np.int32)]
+    A = 4
+    idTs = np.repeat(idT, K)
+    last_row = np.flatnonzero(np.r_[idT[1:] != idT[:-1], True]).astype(np.int32)
+    e0 = np.zeros(0, dtype=bool)
+    Data = dict(
+        y=y, Xbetas=[X[k] @ betas_draw[k] for k in range(O)], X=X, Z=Z, RE_inds=RE_inds, RE_inds2=[r.copy() for r in RE_inds],
+        idL=[idL.astype(np.int32) for _ in range(O)], idL2=[idL2 for _ in range(O)],
+        sigmas=[sigma_draw, float("nan")], invD=_F(invD), fams=fams, links=links, trans_Funs=["identity", "expit"],
+        Time=TimeR, event=event, idGK_fast=(np.arange(1, nT + 1) * K - 1).astype(np.int32), idT_rsum=last_row,
+        W1=W1, W1s=W1s, W2=_F(W2), W2s=W2s, U=U, Us=Us, col_inds=col_inds,
+        row_inds_U=np.arange(nT, dtype=np.int32), row_inds_Us=np.arange(nT * K, dtype=np.int32),
+        XXbetas=XXbetas, XXsbetas=XXsbetas, ZZ=ZZ, ZZs=ZZs,
+        idT=[idT for _ in range(O)], idTs=[idTs for _ in range(O)], idT2=[idT for _ in range(O)], idT2s=[idTs for _ in range(O)],
+        Pw=Pw, nRisks=nR, kn_strat_first=kn_first, kn_strat_last=kn_last, outcome=np.array([0, 1], dtype=np.int32), st=st_vec,
+        strata=trans.astype(np.int32), TimeL=TimeL,
+        Levent1=e0, Levent01=e0, Levent2=e0, Levent3=e0, W1s_int=np.zeros((0, 0), order="F"), W2s_int=np.zeros((0, 0), order="F"),
+        Us_int=[np.zeros((0, 0), order="F")], XXsbetas_int=[np.zeros(0)], ZZs_int=[np.zeros((0, 0), order="F")], Pw_int=np.zeros(0))
+    priors = dict(
+        mean_Bs_gammas=np.zeros(B), Tau_Bs_gammas=_F(Tau_Bs), mean_gammas=np.zeros(nR), Tau_gammas=_F(0.01 * np.eye(nR)),
+        mean_alphas=np.zeros(A), Tau_alphas=_F(0.01 * np.eye(A)), td_cols=[], rank_Tau_td_alphas=0,
+        A_tau_Bs_gammas=1.0, B_tau_Bs_gammas=0.01, rank_Tau_Bs_gammas=float(np.linalg.matrix_rank(Tau_Bs)),
+        shrink_gammas=False, A_tau_gammas=0.1, B_tau_gammas=0.1, rank_Tau_gammas=float(nR), A_phi_gammas=0.5, B_phi_gammas=0.01,
+        shrink_alphas=False, double_gamma_alphas=False, A_tau_alphas=0.5, B_tau_alphas=0.1, rank_Tau_alphas=float(A),
+        A_phi_alphas=0.5, B_phi_alphas=0.01, A_nu_alphas=0.5, B_nu_alphas=1.0, A_xi_alphas=0.5, B_xi_alphas=1.0)
+    tgt = base[trans_s] + 0.3 * np.log(st_vec)
+    Ws = np.asarray(W1s)
+    Bs0 = np.linalg.solve(Ws.T @ Ws + 1e-3 * Tau_Bs + 1e-8 * np.eye(B), Ws.T @ tgt)
+    n_ev = max(1.0, float(event.sum()))
+    inits = dict(
+        b=_F(b + 0.05 * rng.normal(size=b.shape)), Bs_gammas=Bs0, gammas=gammas_true + 0.01 * rng.normal(size=nR),
+        alphas=alphas_true + 0.01 * rng.normal(size=A), tau_Bs_gammas=np.full(nR, 200.0),     # rep(., nRisks), :723-724
+        tau_gammas=1.0, tau_alphas=1.0, phi_gammas=np.ones(nR), phi_alphas=np.ones(A), tau_td_alphas=np.zeros(0))
+    Prec = np.broadcast_to(invD, (n, q, q)).copy()
+    for k in range(O):
+        eta = X[k] @ betas[k] + b[idL, 2 * k] + b[idL, 2 * k + 1] * tt
+        pr = 1.0 / (1.0 + np.exp(-eta))
+        w = np.full(N, 1.0 / sigma_true ** 2) if k == 0 else pr * (1 - pr)
+        s0 = np.add.reduceat(w, row_ptr[:-1]); s1 = np.add.reduceat(w * tt, row_ptr[:-1]); s2 = np.add.reduceat(w * tt * tt, row_ptr[:-1])
+        Prec[:, 2 * k, 2 * k] += s0; Prec[:, 2 * k, 2 * k + 1] += s1; Prec[:, 2 * k + 1, 2 * k] += s1; Prec[:, 2 * k + 1, 2 * k + 1] += s2
+    Rb = np.transpose(np.linalg.cholesky(np.linalg.inv(Prec)), (0, 2, 1))
+    Covs = dict(b=np.asfortranarray(np.transpose(Rb, (1, 2, 0))), Bs_gammas=_F(np.eye(B) * (4.0 / n_ev)),
+                gammas=_F(np.eye(nR) * (2.0 / n_ev)), alphas=_F(np.eye(A) * (2.0 / n_ev)))
+    scales = dict(b=np.full(n, 5.76 / q), Bs_gammas=5.76 / B, gammas=5.76 / nR, alphas=5.76 / A)
+    truth = dict(b=b, betas=betas, D=D, sigma=sigma_true, gammas=gammas_true, alphas=alphas_true, row_ptr=row_ptr, times=tt)
+    return dict(Data=Data, priors=priors, inits=inits, scales=scales, Covs=Covs, control=dict(CONTROL_DEFAULTS), truth=truth,
+                interval_cens=False, multiState=True, config="multistate", n=n, K=K)
+
+
 def shared_model(config: str, n_total: int, pilot_n: int = 20000, K: int = 15) -> dict:
     """Fit-wide quantities every shard of a multi-GPU run must agree on, derived from a small
     seeded pilot cohort: spline knots (boundary knots widened to the whole possible time range),

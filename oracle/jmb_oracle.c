@@ -210,10 +210,24 @@ static double trans_fun(int tf, double x) {
     }
 }
 
+/* rows of the survival part: n, or the transition rows of a multi-state fit (src/fast_LAPRWM.cpp:519-529) */
+static int32_t surv_rows(const orc_data* d) { return d->multi_state ? d->nT : d->n; }
+
+/* idT_rsum (R/mvJointModelBayes.R:567-568): 0-based last transition row of each subject */
+static int32_t* make_idT_rsum(const orc_data* d) {
+    int32_t* last = (int32_t*)malloc(sizeof(int32_t) * d->n);
+    if (!d->multi_state) { for (int32_t i = 0; i < d->n; ++i) last[i] = i; return last; }
+    int32_t m = 0;
+    for (int32_t r = 0; r < d->nT; ++r)
+        if (r == d->nT - 1 || d->idT[r] != d->idT[r + 1]) { if (m < d->n) last[m] = r; ++m; }
+    for (; m < d->n; ++m) last[m] = d->nT - 1;
+    return last;
+}
+
 /* lin_pred_matF: src/fast_LAPRWM.cpp:80-109 */
 int orc_wlong(const orc_data* d, const orc_draw* w, const double* b, int which, double* out) {
-    int32_t n = d->n, K = d->K;
-    int64_t rows = which == 0 ? n : (int64_t)n * K;
+    int32_t n = d->n, K = d->K, nT = surv_rows(d);
+    int64_t rows = which == 0 ? nT : (int64_t)nT * K;
     memset(out, 0, sizeof(double) * rows * d->n_alphas);
     for (int32_t t = 0; t < d->n_terms; ++t) {
         const double* xb = which == 0 ? w->XXbetas[t] : which == 1 ? w->XXsbetas[t] : w->XXsbetas_int[t];
@@ -222,6 +236,7 @@ int orc_wlong(const orc_data* d, const orc_draw* w, const double* b, int which, 
         int32_t rt = d->r_t[t], ut = d->u_t[t];
         for (int64_t r = 0; r < rows; ++r) {
             int64_t id = which == 0 ? r : r / K;   /* idT2 / idT2s: :622-630 */
+            if (d->multi_state) id = d->idT[id];   /* idT.list / idTs.list, R/mvJointModelBayes.R:560-564 */
             double zb = 0.0;
             for (int32_t j = 0; j < rt; ++j) zb += ZZ[r + (int64_t)j * rows] * b[id + (int64_t)d->RE_inds2[t][j] * n];
             double v = trans_fun(d->trans_Funs[t], xb[r] + zb);
@@ -236,7 +251,7 @@ int orc_wlong(const orc_data* d, const orc_draw* w, const double* b, int which, 
 static void hazard_parts(const orc_data* d, const double* Bs, const double* gam, const double* alp,
                          const double* Wlong, const double* Wlongs, const double* Wlongs_int,
                          double* log_h, double* H, double* HL, double* tmp_ns) {
-    int32_t n = d->n, K = d->K;
+    int32_t n = surv_rows(d), K = d->K;       /* one log_h / H per transition row in a multi-state fit */
     int64_t ns = (int64_t)n * K;
     for (int32_t i = 0; i < n; ++i) log_h[i] = 0.0;
     gemv_acc(d->W1, n, d->n_Bs, Bs, log_h);
@@ -272,7 +287,7 @@ static void hazard_parts(const orc_data* d, const double* Bs, const double* gam,
 /* event / censoring term: src/fast_LAPRWM.cpp:640-650 (same at :692-702, :742-752) */
 static void log_ptb_all(const orc_data* d, const double* log_h, const double* H, const double* HL,
                         double* out) {
-    int32_t n = d->n;
+    int32_t n = surv_rows(d);
     if (d->interval_cens) {
         for (int32_t i = 0; i < n; ++i) {
             double e = d->event[i], r = 0.0;       /* Levent* flags, R/mvJointModelBayes.R:694-696 */
@@ -289,8 +304,8 @@ static void log_ptb_all(const orc_data* d, const double* log_h, const double* H,
 
 int orc_eval_logpost_re(const orc_data* d, const orc_draw* w, const double* b, const double* Bs,
                         const double* gam, const double* alp, orc_eval_out* out) {
-    int32_t n = d->n, K = d->K, A = d->n_alphas;
-    int64_t ns = (int64_t)n * K;
+    int32_t n = d->n, K = d->K, A = d->n_alphas, nT = surv_rows(d);
+    int64_t ns = (int64_t)nT * K;
     double** eta = (double**)malloc(sizeof(double*) * d->n_outcomes);
     for (int k = 0; k < d->n_outcomes; ++k) {
         eta[k] = (double*)malloc(sizeof(double) * d->N[k]);
@@ -299,11 +314,11 @@ int orc_eval_logpost_re(const orc_data* d, const orc_draw* w, const double* b, c
     double* tmp_n = (double*)malloc(sizeof(double) * n);
     log_longF(d, w, eta, out->log_pyb, tmp_n);
     log_pb_all(d, w, b, out->log_pb);
-    double* Wlong = (double*)malloc(sizeof(double) * n * A);
+    double* Wlong = (double*)malloc(sizeof(double) * nT * A);
     double* Wlongs = (double*)malloc(sizeof(double) * ns * A);
     double* Wlongs_int = d->interval_cens ? (double*)malloc(sizeof(double) * ns * A) : 0;
     double* tmp_ns = (double*)malloc(sizeof(double) * 2 * ns);
-    double* HLbuf = out->HL ? out->HL : (double*)malloc(sizeof(double) * n);
+    double* HLbuf = out->HL ? out->HL : (double*)malloc(sizeof(double) * nT);
     orc_wlong(d, w, b, 0, Wlong);
     orc_wlong(d, w, b, 1, Wlongs);
     if (d->interval_cens) orc_wlong(d, w, b, 2, Wlongs_int);
@@ -381,14 +396,26 @@ static void adapt_cov(double* Sigma, int32_t m, const double* block, int32_t nb,
 
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
+/* rowsum(log_ptb, idT_rsum) (src/fast_LAPRWM.cpp:669,703,728,754): the subject's sum over its transition rows.
+ * Without multiState idT_rsum is the identity; the restatement then takes the values themselves, as it always
+ * has (the pin against the compiled reference, tests/test_reference_golden.py, covers that choice). */
+static void subject_ptb(const orc_data* d, const double* ptb, const int32_t* last, double* out) {
+    if (!d->multi_state) { memcpy(out, ptb, sizeof(double) * d->n); return; }
+    orc_rowsum(ptb, d->nT, last, d->n, out);
+}
+
 /* ------------------------------------------------------------------------------------------
  * lap_rwm_C: src/fast_LAPRWM.cpp:431-896
  * ---------------------------------------------------------------------------------------- */
 int orc_lap_rwm(const orc_data* d, const orc_draw* w, const orc_priors* pr, const orc_control* ct,
                 const orc_chain_in* in, orc_chain_out* out, int max_iters) {
     const int32_t n = d->n, q = d->q, K = d->K, A = d->n_alphas, B = d->n_Bs, p = d->n_gammas;
-    const int64_t ns = (int64_t)n * K;
+    const int32_t nT = surv_rows(d);                 /* :519-529 */
+    const int32_t nRisks = d->multi_state ? d->nRisks : 1;
+    const int64_t ns = (int64_t)nT * K;
     const int ic = d->interval_cens;
+    if (d->multi_state && (ic || nRisks < 1 || nRisks > 16)) return 4;
+    int32_t* idT_rsum = make_idT_rsum(d);
     /* derived from control :584-588 */
     const int total_it = ct->n_iter + ct->n_burnin;
     const int its = (int)ceil((double)total_it / ct->n_block);
@@ -413,7 +440,9 @@ int orc_lap_rwm(const orc_data* d, const orc_draw* w, const orc_priors* pr, cons
     memcpy(Bs, in->Bs_gammas, sizeof(double) * B);
     if (p) memcpy(gam, in->gammas, sizeof(double) * p);
     memcpy(alp, in->alphas, sizeof(double) * A);
-    double tau_Bs = in->tau_Bs_gammas[0], tau_g = in->tau_gammas, tau_a = in->tau_alphas;
+    double tau_Bs[16];
+    for (int j = 0; j < nRisks; ++j) tau_Bs[j] = in->tau_Bs_gammas[j];
+    double tau_g = in->tau_gammas, tau_a = in->tau_alphas;
     double xi_a = in->tau_alphas;                                  /* :518 (quirk 2) */
     double* phi_g = (double*)malloc(sizeof(double) * (p + 1));
     double* phi_a = (double*)malloc(sizeof(double) * (A + 1));
@@ -460,14 +489,15 @@ int orc_lap_rwm(const orc_data* d, const orc_draw* w, const orc_priors* pr, cons
     double* new_b = (double*)malloc(sizeof(double) * n * q);
     double *c_pyb = (double*)malloc(sizeof(double) * n), *n_pyb = (double*)malloc(sizeof(double) * n);
     double *c_pb = (double*)malloc(sizeof(double) * n), *n_pb = (double*)malloc(sizeof(double) * n);
-    double *c_Wl = (double*)malloc(sizeof(double) * n * A), *n_Wl = (double*)malloc(sizeof(double) * n * A);
+    double *c_Wl = (double*)malloc(sizeof(double) * nT * A), *n_Wl = (double*)malloc(sizeof(double) * nT * A);
     double *c_Wls = (double*)malloc(sizeof(double) * ns * A), *n_Wls = (double*)malloc(sizeof(double) * ns * A);
     double *c_Wli = ic ? (double*)malloc(sizeof(double) * ns * A) : 0;
     double *n_Wli = ic ? (double*)malloc(sizeof(double) * ns * A) : 0;
-    double *c_lh = (double*)malloc(sizeof(double) * n), *n_lh = (double*)malloc(sizeof(double) * n);
-    double *c_H = (double*)malloc(sizeof(double) * n), *n_H = (double*)malloc(sizeof(double) * n);
-    double *c_HL = (double*)malloc(sizeof(double) * n), *n_HL = (double*)malloc(sizeof(double) * n);
-    double *c_ptb = (double*)malloc(sizeof(double) * n), *n_ptb = (double*)malloc(sizeof(double) * n);
+    double *c_lh = (double*)malloc(sizeof(double) * nT), *n_lh = (double*)malloc(sizeof(double) * nT);
+    double *c_H = (double*)malloc(sizeof(double) * nT), *n_H = (double*)malloc(sizeof(double) * nT);
+    double *c_HL = (double*)malloc(sizeof(double) * nT), *n_HL = (double*)malloc(sizeof(double) * nT);
+    double *c_ptb = (double*)malloc(sizeof(double) * nT), *n_ptb = (double*)malloc(sizeof(double) * nT);
+    double *c_sub = (double*)malloc(sizeof(double) * n), *n_sub = (double*)malloc(sizeof(double) * n);   /* per-subject sums */
     double* accept_b = (double*)calloc(n, sizeof(double));
     double* accept_b_tot = (double*)calloc(n, sizeof(double));
     double* block_par = (double*)malloc(sizeof(double) * (B + p + A) * ct->n_block);
@@ -515,10 +545,12 @@ int orc_lap_rwm(const orc_data* d, const orc_draw* w, const orc_priors* pr, cons
             if (ic) orc_wlong(d, w, new_b, 2, n_Wli);                                    /* :680 */
             hazard_parts(d, Bs, gam, alp, n_Wl, n_Wls, n_Wli, n_lh, n_H, n_HL, tmp_ns); /* :684-691 */
             log_ptb_all(d, n_lh, n_H, n_HL, n_ptb);                                      /* :692-702 */
+            subject_ptb(d, c_ptb, idT_rsum, c_sub);                                      /* :669 */
+            subject_ptb(d, n_ptb, idT_rsum, n_sub);                                      /* :703 */
             for (int32_t m = 0; m < n; ++m) {                                            /* :703-725 */
                 const uint32_t gid = (uint32_t)(d->subject_offset + m);
-                double cur = c_pyb[m] + c_ptb[m] + c_pb[m];
-                double nw = n_pyb[m] + n_ptb[m] + n_pb[m];
+                double cur = c_pyb[m] + c_sub[m] + c_pb[m];
+                double nw = n_pyb[m] + n_sub[m] + n_pb[m];
                 uint32_t r[4];
                 orc_philox4x32(seed, chain, gid, iter, 0u, ST_B_ACC, r);
                 double log_u = log(orc_u01(r[0], r[1]));
@@ -526,22 +558,26 @@ int orc_lap_rwm(const orc_data* d, const orc_draw* w, const orc_priors* pr, cons
                     accept_b[m] += 1.0;
                     for (int32_t j = 0; j < q; ++j) b[m + (int64_t)j * n] = new_b[m + (int64_t)j * n];
                     c_pyb[m] = n_pyb[m]; c_pb[m] = n_pb[m];
-                    for (int32_t a = 0; a < A; ++a) {
-                        c_Wl[m + (int64_t)a * n] = n_Wl[m + (int64_t)a * n];
-                        for (int32_t k = 0; k < K; ++k) {
-                            int64_t r2 = (int64_t)m * K + k + (int64_t)a * ns;
-                            c_Wls[r2] = n_Wls[r2];
-                            if (ic) c_Wli[r2] = n_Wli[r2];
+                    /* rows_wlong[[m]] / rows_wlongs[[m]]: the subject's transition rows (:711-722) */
+                    for (int32_t tr = (m == 0 ? 0 : idT_rsum[m - 1] + 1); tr <= idT_rsum[m]; ++tr) {
+                        for (int32_t a = 0; a < A; ++a) {
+                            c_Wl[tr + (int64_t)a * nT] = n_Wl[tr + (int64_t)a * nT];
+                            for (int32_t k = 0; k < K; ++k) {
+                                int64_t r2 = (int64_t)tr * K + k + (int64_t)a * ns;
+                                c_Wls[r2] = n_Wls[r2];
+                                if (ic) c_Wli[r2] = n_Wli[r2];
+                            }
                         }
+                        c_lh[tr] = n_lh[tr]; c_H[tr] = n_H[tr];
+                        if (ic) c_HL[tr] = n_HL[tr];
+                        c_ptb[tr] = n_ptb[tr];
                     }
-                    c_lh[m] = n_lh[m]; c_H[m] = n_H[m];
-                    if (ic) c_HL[m] = n_HL[m];
-                    c_ptb[m] = n_ptb[m];
                 }
             }
             /* ---- survival block :727-770 ---- */
             double sums[3] = {0.0, 0.0, 0.0};
-            for (int32_t m = 0; m < n; ++m) sums[0] += c_ptb[m];
+            subject_ptb(d, c_ptb, idT_rsum, c_sub);                                          /* :728 */
+            for (int32_t m = 0; m < n; ++m) sums[0] += c_sub[m];
             {
                 int P = B + p + A;
                 double zz[2 * ((JMB_ORC_PMAX + 1) / 2)];
@@ -552,7 +588,8 @@ int orc_lap_rwm(const orc_data* d, const orc_draw* w, const orc_priors* pr, cons
             }
             hazard_parts(d, nBs, ngam, nalp, c_Wl, c_Wls, c_Wli, n_lh, n_H, n_HL, tmp_ns);   /* :735-741 */
             log_ptb_all(d, n_lh, n_H, n_HL, n_ptb);                                         /* :742-752 */
-            for (int32_t m = 0; m < n; ++m) sums[1] += n_ptb[m];
+            subject_ptb(d, n_ptb, idT_rsum, n_sub);                                          /* :754 */
+            for (int32_t m = 0; m < n; ++m) sums[1] += n_sub[m];
             for (int32_t m = 0; m < n; ++m) sums[2] += c_pyb[m] + c_pb[m];                   /* log_weightsREF :359-369 */
             if (g_allreduce) g_allreduce(sums, 3, g_allreduce_ctx);
             if (out->trace_surv) { out->trace_surv[2 * (int64_t)iter] = sums[0]; out->trace_surv[2 * (int64_t)iter + 1] = sums[1]; }
@@ -580,9 +617,20 @@ int orc_lap_rwm(const orc_data* d, const orc_draw* w, const orc_priors* pr, cons
             for (int j = 0; j < A; ++j) block_par[B + p + j + i * (B + p + A)] = alp[j];
             /* ---- Gibbs precisions :776-834 ---- */
             uint32_t draw = 0;
-            {   /* B_tau + 0.5 Bs' Tau Bs (no mean subtracted) :778-779 */
+            if (!d->multi_state) {   /* B_tau + 0.5 Bs' Tau Bs (no mean subtracted) :778-779 */
                 double Bpost = pr->B_tau_Bs_gammas + 0.5 * quad_form(Bs, pr->Tau_Bs_gammas, B);
-                tau_Bs = clampd(orc_rgamma(seed, chain, draw++, iter, Apost_tau_Bs, 1.0 / Bpost), ct->eps2, ct->eps3);
+                tau_Bs[0] = clampd(orc_rgamma(seed, chain, draw++, iter, Apost_tau_Bs, 1.0 / Bpost), ct->eps2, ct->eps3);
+            } else {                 /* one draw per stratum on its diagonal block of Tau_Bs_gammas :777-782 */
+                for (int ij = 0; ij < nRisks; ++ij) {
+                    const int f = d->kn_strat_first[ij], l = d->kn_strat_last[ij];
+                    double sq = 0.0;
+                    for (int a2 = f; a2 <= l; ++a2) {
+                        double t = 0.0;
+                        for (int a1 = f; a1 <= l; ++a1) t += Bs[a1] * pr->Tau_Bs_gammas[a1 + a2 * B];
+                        sq += t * Bs[a2];
+                    }
+                    tau_Bs[ij] = clampd(orc_rgamma(seed, chain, draw++, iter, Apost_tau_Bs, 1.0 / (pr->B_tau_Bs_gammas + 0.5 * sq)), ct->eps2, ct->eps3);
+                }
             }
             for (int kk = 0; kk < n_td; ++kk) {                                            /* :783-794 */
                 int L = pr->td_len[kk];
@@ -628,7 +676,7 @@ int orc_lap_rwm(const orc_data* d, const orc_draw* w, const orc_priors* pr, cons
                 memcpy(out->alphas + ko * A, alp, sizeof(double) * A);
                 if (p) memcpy(out->phi_gammas + ko * p, phi_g, sizeof(double) * p);
                 memcpy(out->phi_alphas + ko * A, phi_a, sizeof(double) * A);
-                out->tau_Bs_gammas[ko] = tau_Bs;
+                for (int j = 0; j < nRisks; ++j) out->tau_Bs_gammas[j + ko * nRisks] = tau_Bs[j];
                 out->tau_gammas[ko] = tau_g;
                 out->tau_alphas[ko] = tau_a;
                 for (int j = 0; j < n_td; ++j) out->tau_td_alphas[j + ko * n_td] = tau_td[j];
@@ -679,7 +727,7 @@ int orc_lap_rwm(const orc_data* d, const orc_draw* w, const orc_priors* pr, cons
     free(eta); free(tmp_n); free(tmp_ns); free(new_b); free(c_pyb); free(n_pyb); free(c_pb); free(n_pb);
     free(c_Wl); free(n_Wl); free(c_Wls); free(n_Wls); free(c_Wli); free(n_Wli); free(c_lh); free(n_lh);
     free(c_H); free(n_H); free(c_HL); free(n_HL); free(c_ptb); free(n_ptb); free(accept_b);
-    free(accept_b_tot); free(block_par);
+    free(accept_b_tot); free(block_par); free(c_sub); free(n_sub); free(idT_rsum);
     return rc;
 }
 

@@ -42,6 +42,10 @@ typedef struct orc_data {
     const double* const* ZZ; const double* const* ZZs; const double* const* ZZs_int;
     const double* const* U; const double* const* Us; const double* const* Us_int;
     const double* Covs_b;
+    /* fields of jmb_data the oracle does not use (kept so that the two structs stay layout-compatible) */
+    const double* knots; int32_t n_knots; int32_t ord; const double* Time; const double* st; const double* st_int;
+    /* multi-state fits (multi_state != 0): nT transition rows in the survival part, src/fast_LAPRWM.cpp:519-529 */
+    int32_t nT, nRisks; const int32_t* idT; const int32_t* kn_strat_first; const int32_t* kn_strat_last;
 } orc_data;
 
 typedef struct orc_draw {

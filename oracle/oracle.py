@@ -90,11 +90,12 @@ def rowsum(x, last):
     return out
 
 
-def eval_logpost_re(Data, Covs_b, interval_cens, b, Bs_gammas, gammas, alphas):
-    d, k1 = _abi.marshal_data(Data, Covs_b, interval_cens)
+def eval_logpost_re(Data, Covs_b, interval_cens, b, Bs_gammas, gammas, alphas, multiState=False):
+    d, k1 = _abi.marshal_data(Data, Covs_b, interval_cens, multiState)
     w, k2 = _abi.marshal_draw(Data, interval_cens)
     n = d.n
-    res = {k: np.zeros(n) for k in ("log_pyb", "log_pb", "log_h", "H", "HL", "log_ptb")}
+    nT = d.nT if multiState else n        # log_h / H / log_ptb: one value per transition row
+    res = {k: np.zeros(n if k in ("log_pyb", "log_pb") else nT) for k in ("log_pyb", "log_pb", "log_h", "H", "HL", "log_ptb")}
     out = _abi.JmbEvalOut()
     for k, a in res.items():
         setattr(out, k, _p(a))
@@ -109,10 +110,11 @@ def eval_logpost_re(Data, Covs_b, interval_cens, b, Bs_gammas, gammas, alphas):
     return res
 
 
-def wlong(Data, Covs_b, interval_cens, b, which):
-    d, k1 = _abi.marshal_data(Data, Covs_b, interval_cens)
+def wlong(Data, Covs_b, interval_cens, b, which, multiState=False):
+    d, k1 = _abi.marshal_data(Data, Covs_b, interval_cens, multiState)
     w, k2 = _abi.marshal_draw(Data, interval_cens)
-    rows = d.n if which == 0 else d.n * d.K
+    nT = d.nT if multiState else d.n
+    rows = nT if which == 0 else nT * d.K
     out = np.zeros((rows, d.n_alphas), order="F")
     b = np.asfortranarray(np.asarray(b, dtype=np.float64))
     lib().orc_wlong(C.byref(d), C.byref(w), _p(b), which, _p(out))
@@ -130,7 +132,8 @@ def lap_rwm_C(initials, Data, priors, scales, Covs, control, interval_cens=False
     ct = _abi.marshal_control(control, chain_id)
     ci, k4 = _abi.marshal_chain_in(initials, scales, Covs)
     total, n_out = _abi.chain_dims(control)
-    out, bufs = _abi.alloc_chain_out(d.n, d.q, d.n_Bs, d.n_gammas, d.n_alphas, pr.n_td, n_out, total)
+    out, bufs = _abi.alloc_chain_out(d.n, d.q, d.n_Bs, d.n_gammas, d.n_alphas, pr.n_td, n_out, total,
+                                      n_risks=d.nRisks if multiState else 1)
     L = lib()
     cb = None
     if allreduce is not None:

@@ -63,7 +63,8 @@ def lap_rwm_C(initials, Data, priors, scales, Covs, control, interval_cens=False
     ct = _abi.marshal_control(control, chain_id)
     ci, k4 = _abi.marshal_chain_in(initials, scales, Covs)
     total, n_out = _abi.chain_dims(control)
-    out, bufs = _abi.alloc_chain_out(d.n, d.q, d.n_Bs, d.n_gammas, d.n_alphas, pr.n_td, n_out, total, extras=False)
+    out, bufs = _abi.alloc_chain_out(d.n, d.q, d.n_Bs, d.n_gammas, d.n_alphas, pr.n_td, n_out, total, extras=False,
+                                      n_risks=d.nRisks if multiState else 1)
     rc = lib().jmbref_lap_rwm(C.byref(d), C.byref(w), C.byref(pr), C.byref(ct), C.byref(ci), C.byref(out))
     if rc != 0:
         raise RuntimeError("reference lap_rwm_C: " + lib().jmbref_last_error().decode())

@@ -120,7 +120,15 @@ const char* TF[] = {"identity", "expit", "exp", "log", "log2", "log10", "sqrt"};
 
 List build_data(const orc_data* d, const orc_draw* w) {
     const int n = d->n, O = d->n_outcomes, T = d->n_terms, K = d->K, B = d->n_Bs, p = d->n_gammas;
-    const arma::uword ns = (arma::uword)n * K;
+    const bool ms = d->multi_state != 0;
+    const int nT = ms ? d->nT : n;            // rows of the survival part (R/mvJointModelBayes.R:76-101)
+    const arma::uword ns = (arma::uword)nT * K;
+    // Data$idT2 / idT2s (1-based subject of each transition / quadrature row, R/mvJointModelBayes.R:559-565)
+    auto idT_vec = [&](int each) {
+        auto v = std::make_shared<Value>(); v->kind = Value::INT;
+        for (int r = 0; r < nT; ++r) for (int e = 0; e < each; ++e) v->ints.push_back((long long)(ms ? d->idT[r] : r) + 1);
+        return v;
+    };
     List D;
     std::vector<ValuePtr> y, Xb, Z, REi, idL, idL2, sig;
     std::vector<std::string> fams, links, tfs;
@@ -137,32 +145,48 @@ List build_data(const orc_data* d, const orc_draw* w) {
     std::vector<ValuePtr> RE2, cols, XXb, XXsb, XXsbi, ZZ, ZZs, ZZsi, U, Us, Usi, idT, idTs, rowsw, rowsws;
     for (int t = 0; t < T; ++t) {
         RE2.push_back(int_vec(d->RE_inds2[t], d->r_t[t], 1)); cols.push_back(int_vec(d->col_inds[t], d->u_t[t], 1));
-        XXb.push_back(num_vec(w->XXbetas[t], n)); XXsb.push_back(num_vec(w->XXsbetas[t], ns));
-        ZZ.push_back(num_mat(d->ZZ[t], n, d->r_t[t])); ZZs.push_back(num_mat(d->ZZs[t], ns, d->r_t[t]));
-        U.push_back(num_mat(d->U[t], n, d->u_t[t])); Us.push_back(num_mat(d->Us[t], ns, d->u_t[t]));
-        idT.push_back(seq_vec(1, n)); idTs.push_back(seq_vec(1, n, K));
+        XXb.push_back(num_vec(w->XXbetas[t], nT)); XXsb.push_back(num_vec(w->XXsbetas[t], ns));
+        ZZ.push_back(num_mat(d->ZZ[t], nT, d->r_t[t])); ZZs.push_back(num_mat(d->ZZs[t], ns, d->r_t[t]));
+        U.push_back(num_mat(d->U[t], nT, d->u_t[t])); Us.push_back(num_mat(d->Us[t], ns, d->u_t[t]));
+        idT.push_back(idT_vec(1)); idTs.push_back(idT_vec(K));
         tfs.push_back(TF[d->trans_Funs[t]]);
         if (d->interval_cens) {
             XXsbi.push_back(num_vec(w->XXsbetas_int[t], ns)); ZZsi.push_back(num_mat(d->ZZs_int[t], ns, d->r_t[t]));
             Usi.push_back(num_mat(d->Us_int[t], ns, d->u_t[t]));
         }
     }
-    for (int i = 0; i < n; ++i) { rowsw.push_back(seq_vec(i + 1, 1)); rowsws.push_back(seq_vec((long long)i * K + 1, K)); }
+    // rows_wlong / rows_wlongs = tapply(seq_along(idT), idT, c) (:569-570,580-581); idT_rsum = last row of each subject
+    std::vector<long long> rsum;
+    for (int r = 0, i = 0; r < nT; ++i) {
+        int r1 = r;
+        while (r1 + 1 < nT && (ms ? d->idT[r1 + 1] == d->idT[r] : false)) ++r1;
+        rowsw.push_back(seq_vec(r + 1, r1 - r + 1)); rowsws.push_back(seq_vec((long long)r * K + 1, (long long)(r1 - r + 1) * K));
+        rsum.push_back(r1);
+        r = r1 + 1;
+    }
+    auto rsum_v = std::make_shared<Value>(); rsum_v->kind = Value::INT; rsum_v->ints = rsum;
     D.push("y", list_of(y)); D.push("Xbetas", list_of(Xb)); D.push("Z", list_of(Z)); D.push("RE_inds", list_of(REi));
     D.push("RE_inds2", list_of(RE2)); D.push("sigmas", list_of(sig)); D.push("invD", num_mat(w->invD, d->q, d->q));
     D.push("idL", list_of(idL)); D.push("idL2", list_of(idL2)); D.push("fams", str_vec(fams)); D.push("links", str_vec(links));
-    D.push("trans_Funs", str_vec(tfs)); D.push("event", num_vec(d->event, n));
-    D.push("idGK_fast", int_vec(d->idGK_fast, n, 0)); D.push("idT_rsum", seq_vec(0, n));
-    D.push("W1", num_mat(d->W1, n, B)); D.push("W1s", num_mat(d->W1s, ns, B));
-    D.push("W2", num_mat(d->W2, n, p)); D.push("W2s", num_mat(d->W2s, ns, p));
-    D.push("U", list_of(U)); D.push("Us", list_of(Us)); D.push("row_inds_U", seq_vec(1, n)); D.push("row_inds_Us", seq_vec(1, (long long)ns));
+    D.push("trans_Funs", str_vec(tfs)); D.push("event", num_vec(d->event, nT));
+    D.push("idGK_fast", int_vec(d->idGK_fast, nT, 0)); D.push("idT_rsum", rsum_v);
+    D.push("W1", num_mat(d->W1, nT, B)); D.push("W1s", num_mat(d->W1s, ns, B));
+    D.push("W2", num_mat(d->W2, nT, p)); D.push("W2s", num_mat(d->W2s, ns, p));
+    D.push("U", list_of(U)); D.push("Us", list_of(Us)); D.push("row_inds_U", seq_vec(1, nT)); D.push("row_inds_Us", seq_vec(1, (long long)ns));
     D.push("col_inds", list_of(cols)); D.push("XXbetas", list_of(XXb)); D.push("XXsbetas", list_of(XXsb));
     D.push("ZZ", list_of(ZZ)); D.push("ZZs", list_of(ZZs)); D.push("idT", list_of(idT)); D.push("idTs", list_of(idTs));
     D.push("idT2", list_of(idT)); D.push("idT2s", list_of(idTs)); D.push("Pw", num_vec(d->Pw, ns));
     D.push("rows_wlong", list_of(rowsw)); D.push("rows_wlongs", list_of(rowsws));
-    D.push("nRisks", scalar(1.0));
-    double kl = B - 1, kf = 0;
-    D.push("kn_strat_last", num_vec(&kl, 1)); D.push("kn_strat_first", num_vec(&kf, 1));
+    if (ms) {                              // R/mvJointModelBayes.R:667-669
+        std::vector<double> kf(d->nRisks), kl(d->nRisks);
+        for (int j = 0; j < d->nRisks; ++j) { kf[j] = d->kn_strat_first[j]; kl[j] = d->kn_strat_last[j]; }
+        D.push("nRisks", scalar((double)d->nRisks));
+        D.push("kn_strat_last", num_vec(kl.data(), kl.size())); D.push("kn_strat_first", num_vec(kf.data(), kf.size()));
+    } else {
+        D.push("nRisks", scalar(1.0));
+        double kl = B - 1, kf = 0;
+        D.push("kn_strat_last", num_vec(&kl, 1)); D.push("kn_strat_first", num_vec(&kf, 1));
+    }
     if (d->interval_cens) {
         std::vector<int> l1(n), l01(n), l2(n), l3(n);
         for (int i = 0; i < n; ++i) {      // R/mvJointModelBayes.R:694-696
@@ -197,7 +221,7 @@ extern "C" int jmbref_lap_rwm(const orc_data* d, const orc_draw* w, const orc_pr
         initials.push("b", num_mat(in->b, n, q)); initials.push("Bs_gammas", num_vec(in->Bs_gammas, B));
         initials.push("gammas", num_vec(in->gammas, p)); initials.push("alphas", num_vec(in->alphas, A));
         initials.push("phi_gammas", num_vec(in->phi_gammas, p)); initials.push("phi_alphas", num_vec(in->phi_alphas, A));
-        initials.push("tau_td_alphas", num_vec(in->tau_td_alphas, pr->n_td)); initials.push("tau_Bs_gammas", num_vec(in->tau_Bs_gammas, 1));
+        initials.push("tau_td_alphas", num_vec(in->tau_td_alphas, pr->n_td)); initials.push("tau_Bs_gammas", num_vec(in->tau_Bs_gammas, d->multi_state ? d->nRisks : 1));
         initials.push("tau_gammas", scalar(in->tau_gammas)); initials.push("tau_alphas", scalar(in->tau_alphas));
         priors.push("mean_Bs_gammas", num_vec(pr->mean_Bs_gammas, B)); priors.push("Tau_Bs_gammas", num_mat(pr->Tau_Bs_gammas, B, B));
         priors.push("mean_gammas", num_vec(pr->mean_gammas, p)); priors.push("Tau_gammas", num_mat(pr->Tau_gammas, p, p));
@@ -221,7 +245,7 @@ extern "C" int jmbref_lap_rwm(const orc_data* d, const orc_draw* w, const orc_pr
         g = Provider();
         g.seed = ct->seed; g.chain = ct->chain_id; g.offset = d->subject_offset;
         g.n = n; g.q = q; g.B = B; g.p = p; g.A = A; g.n_block = ct->n_block;
-        g.draws_per_iter = 1 + pr->n_td + (pr->shrink_gammas ? p + 1 : 0) +
+        g.draws_per_iter = (d->multi_state ? d->nRisks : 1) + pr->n_td + (pr->shrink_gammas ? p + 1 : 0) +
                            (pr->shrink_alphas ? A + 1 + (pr->double_gamma_alphas ? A + 1 : 0) : 0);
         jmbref_fill = provider_fill; jmbref_rgamma = provider_rgamma;
         List res = lap_rwm_C(initials, Data, priors, scales, Covs, control, d->interval_cens != 0, d->multi_state != 0);
