@@ -41,6 +41,7 @@ enum { JMB_TF_IDENTITY = 0, JMB_TF_EXPIT = 1, JMB_TF_EXP = 2, JMB_TF_LOG = 3, JM
 #define JMB_MAX_BS 64
 #define JMB_MAX_GAMMAS 32
 #define JMB_MAX_ALPHAS 32
+#define JMB_MAX_RISKS 16  /* strata of the baseline hazard (multi-state fits) */
 
 typedef struct jmb_handle_s* jmb_handle;
 
@@ -305,6 +306,16 @@ int jmb_survPred_svft_2(jmb_handle h, const double* b, const double* Bs_gammas, 
 int jmb_get_row_ptr(jmb_handle h, int outcome, int64_t* row_ptr /* [n+1] */);
 int jmb_layout_info(jmb_handle h, double* shared_bytes_per_subject,
                     double* chain_bytes_per_subject, int32_t* w1_band, int32_t* group_lanes);
+
+/* Layout inspection without a device, for the CPU tests of the record packer (never part of a compute path; a handle
+ * made by jmb_debug_pack_host holds no device state and must only be passed to these functions and jmb_destroy).  jmb_debug_layout: ints[0..15] = RP,
+ * o_V, o_W2c, o_Pw, o_W1off, o_W1v, o_W2, o_long, c_long, HB, state_stride, WB, G, w2_const, MS, S; ints[16+t] = o_ZZ[t];
+ * ints[32+t] = o_U[t]; ints[48+t] bit 0 = first ZZ column not stored (all ones), bit 1 = U not stored (all ones), and for
+ * outcome o < 8, ints[56+o] bit 8 = first Z column not stored, bits 16.. = stored doubles per longitudinal row
+ * (jmbayes_b200/csrc/jmb_model.h describes the records). */
+int jmb_debug_pack_host(const jmb_data* data, jmb_handle* out);
+int jmb_debug_layout(jmb_handle h, int32_t* ints /* [64] */, int64_t* doff /* [n+1] */, int64_t* coff /* [n+1] */);
+int jmb_debug_records(jmb_handle h, const jmb_draw* draw, double* drec, double* crec);
 
 /* Multi-GPU: one process per GPU, contiguous subject shards, one all-reduce of the
  * survival-block partial sums per iteration.  The 128-byte NCCL unique id

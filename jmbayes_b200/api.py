@@ -112,6 +112,10 @@ class Fit:
         self.n, self.q = d.n, d.q
         self.B, self.p, self.A = d.n_Bs, d.n_gammas, d.n_alphas
         self.O, self.T, self.K = d.n_outcomes, d.n_terms, d.K
+        # multi-state fits: nT transition rows in the survival part, nRisks strata (src/fast_LAPRWM.cpp:519-529,607)
+        self.multiState = bool(multiState)
+        self.nT = d.nT if multiState else d.n
+        self.nRisks = d.nRisks if multiState else 1
         _check(lib().jmb_create(C.byref(d), device, C.byref(self._h)))
         del keep
 
@@ -179,7 +183,7 @@ class Fit:
         (src/fast_LAPRWM.cpp:870-895) plus ``extras`` (acceptance rates, per-iteration sums)."""
         pr, ct, ci, keep = self._marshal_chain(initials, priors, scales, Covs, control, chain_id)
         total, n_out = _abi.chain_dims(control)
-        out, bufs = _abi.alloc_chain_out(self.n, self.q, self.B, self.p, self.A, pr.n_td, n_out, total)
+        out, bufs = _abi.alloc_chain_out(self.n, self.q, self.B, self.p, self.A, pr.n_td, n_out, total, n_risks=self.nRisks)
         _check(lib().jmb_lap_rwm(self._h, C.byref(pr), C.byref(ct), C.byref(ci), C.byref(out)))
         del keep
         return self._result(bufs, n_out)
@@ -217,17 +221,17 @@ class Fit:
             _check(lib().jmb_chain_end(self._h, None))
             return None
         n_td, total, n_out = self._chain_meta
-        out, bufs = _abi.alloc_chain_out(self.n, self.q, self.B, self.p, self.A, n_td, n_out, total)
+        out, bufs = _abi.alloc_chain_out(self.n, self.q, self.B, self.p, self.A, n_td, n_out, total, n_risks=self.nRisks)
         _check(lib().jmb_chain_end(self._h, C.byref(out)))
         return self._result(bufs, n_out)
 
     # -- parity probes -------------------------------------------------------------------------------
     def eval_logpost_re(self, b, Bs_gammas, gammas, alphas):
         """Per-subject log p(y|b), log p(b), log h, H, HL, log p(T|b) at (b, params)
-        (src/fast_LAPRWM.cpp:619-650)."""
+        (src/fast_LAPRWM.cpp:619-650); for a multi-state fit the last four have one value per transition row."""
         n = self.n
         b = np.asfortranarray(np.asarray(b, dtype=np.float64))
-        res = {k: np.zeros(n) for k in ("log_pyb", "log_pb", "log_h", "H", "HL", "log_ptb")}
+        res = {k: np.zeros(n if k in ("log_pyb", "log_pb") else self.nT) for k in ("log_pyb", "log_pb", "log_h", "H", "HL", "log_ptb")}
         out = _abi.JmbEvalOut()
         for k, a in res.items():
             setattr(out, k, _dptr(a))

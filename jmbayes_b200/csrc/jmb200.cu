@@ -102,11 +102,17 @@ struct jmb_handle_s {
     ModelMeta mm{};
     ParamLayout pl{};
     int n = 0;
+    // multi-state fits: nT transition rows in the survival part, trow[i] = first row of subject i
+    bool ms = false; int nT = 0, nRisks = 1;
+    std::vector<int> trow, kn_first, kn_last;
+    int* d_trow = nullptr;
     long long subject_offset = 0;
     int n_block_cap = 1024;
     std::vector<long long> N;                       // rows per outcome
     std::vector<std::vector<int>> rowptr;           // host CSR per outcome
     std::vector<long long> doff, coff;              // host offsets
+    std::vector<double> h_drec;                     // host copy of the design records (jmb_debug_pack_host handles only)
+    bool host_only = false;
     // device data shared by all chains
     double* d_drec = nullptr; long long* d_doff = nullptr; long long* d_coff = nullptr;
     int* d_rowptr = nullptr;
@@ -230,7 +236,7 @@ static void build_param_layout(const ModelMeta& mm, int n_td, int n_block_cap, P
     auto take = [&](int len) { int r = o; o += std::max(len, 1); return r; };
     pl.cur = take(mm.P); pl.prop = take(mm.P);
     pl.invD = take(mm.d.q * mm.d.q); pl.sigmas = take(mm.d.O);
-    pl.tau_Bs = take(1); pl.tau_g = take(1); pl.tau_a = take(1); pl.xi_a = take(1);
+    pl.tau_Bs = take(JMB_MAX_RISKS); pl.tau_g = take(1); pl.tau_a = take(1); pl.xi_a = take(1);
     pl.phi_g = take(mm.d.p); pl.phi_a = take(mm.d.A); pl.nu_a = take(mm.d.A); pl.tau_td = take(n_td);
     pl.Tau_g = take(mm.d.p * mm.d.p); pl.Tau_a = take(mm.d.A * mm.d.A); pl.Tau_a_pen = take(mm.d.A * mm.d.A);
     pl.sig = take(3);
@@ -246,14 +252,26 @@ static void build_param_layout(const ModelMeta& mm, int n_td, int n_block_cap, P
 // ---------------------------------------------------------------------------------------------
 // jmb_create: validate, compact and repack the static designs into per-subject records
 // ---------------------------------------------------------------------------------------------
-extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
+static int create_impl(const jmb_data* d, int device, jmb_handle* out, bool host_only) {
     if (!d || !out) return fail("jmb_create: null argument");
     *out = nullptr;
-    int ndev = 0;
-    if (jmb_device_count(&ndev) || ndev == 0)
-        return fail("jmb_create: no CUDA device available (this library has no CPU fallback): " + g_err);
-    if (device < 0 || device >= ndev) return fail("jmb_create: bad device ordinal");
-    if (d->multi_state) return fail("jmb_create: multiState = TRUE is not supported by the CUDA path");
+    if (!host_only) {
+        int ndev = 0;
+        if (jmb_device_count(&ndev) || ndev == 0)
+            return fail("jmb_create: no CUDA device available (this library has no CPU fallback): " + g_err);
+        if (device < 0 || device >= ndev) return fail("jmb_create: bad device ordinal");
+    }
+    const bool ms = d->multi_state != 0;
+    if (ms) {
+        if (d->interval_cens) return fail("jmb_create: multiState cannot be combined with interval censoring (the reference's state copy "
+                                          "assumes K rows per subject there, src/fast_LAPRWM.cpp:712-717)");
+        if (!d->W1) return fail("jmb_create: multiState needs the dense (stratified) W1 / W1s; the knots alternative is single-stratum");
+        if (d->nT < d->n || !d->idT) return fail("jmb_create: multiState needs nT >= n and idT");
+        if (d->nRisks < 1 || d->nRisks > JMB_MAX_RISKS || !d->kn_strat_first || !d->kn_strat_last) return fail("jmb_create: nRisks out of range (1..16) or kn_strat_* missing");
+        for (int k = 0; k < d->nRisks; ++k)
+            if (d->kn_strat_first[k] < 0 || d->kn_strat_last[k] < d->kn_strat_first[k] || d->kn_strat_last[k] >= d->n_Bs)
+                return fail("jmb_create: kn_strat_first / kn_strat_last out of range");
+    }
     if (d->n <= 0 || d->n_outcomes <= 0 || d->n_outcomes > JMB_MAX_OUTCOMES) return fail("jmb_create: bad n / n_outcomes");
     if (d->q <= 0 || d->q > JMB_MAX_Q) return fail("jmb_create: q out of range");
     if (d->n_terms <= 0 || d->n_terms > JMB_MAX_TERMS) return fail("jmb_create: n_terms out of range");
@@ -276,11 +294,33 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     h->n = d->n;
     h->subject_offset = d->subject_offset;
     const int n = d->n, O = d->n_outcomes, q = d->q, T = d->n_terms, B = d->n_Bs, p = d->n_gammas, K = d->K;
-    const long long ns = (long long)n * K;
+    // rows of the survival part: one per subject, or one per transition a subject is at risk for (multi-state,
+    // src/fast_LAPRWM.cpp:519-529); trow[i] .. trow[i+1]-1 are subject i's rows (rows_wlong[[i]], idT_rsum)
+    const int nT = ms ? d->nT : n;
+    h->ms = ms; h->nT = nT; h->nRisks = ms ? d->nRisks : 1;
+    h->trow.assign(n + 1, 0);
+    if (ms) {
+        int prev = 0;
+        for (int r = 0; r < nT; ++r) {
+            const int sbj = d->idT[r];
+            if (sbj < 0 || sbj >= n || sbj < prev) { delete h; return fail("jmb_create: idT must be 0-based and grouped by subject in subject order"); }
+            prev = sbj;
+            h->trow[sbj + 1] += 1;
+        }
+        for (int i = 0; i < n; ++i) {
+            if (h->trow[i + 1] == 0) { delete h; return fail("jmb_create: every subject needs at least one transition row"); }
+            h->trow[i + 1] += h->trow[i];
+        }
+        h->kn_first.assign(d->kn_strat_first, d->kn_strat_first + d->nRisks);
+        h->kn_last.assign(d->kn_strat_last, d->kn_strat_last + d->nRisks);
+    } else {
+        for (int i = 0; i <= n; ++i) h->trow[i] = i;
+    }
+    const long long ns = (long long)nT * K;
     ModelMeta& mm = h->mm;
     ModelDesc& md = mm.d;
     memset(&mm, 0, sizeof(mm));
-    md.O = O; md.q = q; md.T = T; md.A = d->n_alphas; md.p = p; md.K = K; md.S = S;
+    md.O = O; md.q = q; md.T = T; md.A = d->n_alphas; md.p = p; md.K = K; md.S = S; md.MS = ms ? 1 : 0;
     mm.B = B;
     mm.P = B + p + d->n_alphas;
     md.G = (1 + K * S <= 16) ? 16 : 32;
@@ -329,7 +369,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
             if (d->idL2[k][i] != rp[i + 1] - 1) { delete h; return fail("jmb_create: idL2 is not the last row of each subject"); }
     }
     if (d->idGK_fast)
-        for (int i = 0; i < n; ++i)
+        for (int i = 0; i < nT; ++i)
             if (d->idGK_fast[i] != (i + 1) * K - 1) { delete h; return fail("jmb_create: idGK_fast must be (i+1)K-1"); }
 
     // ---- band of the B-spline basis rows (splineDesign rows have `ord` contiguous non-zeros) ----
@@ -350,7 +390,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
                 while (m > cur && !wmax.compare_exchange_weak(cur, m)) {}
             });
         };
-        scan(d->W1, n); scan(d->W1s, ns);
+        scan(d->W1, nT); scan(d->W1s, ns);
         if (S == 2) scan(d->W1s_int, ns);
         WB = wmax.load();
         if (WB > 8) WB = B;                 // not banded: keep the dense rows
@@ -368,15 +408,15 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     };
     for (int k = 0; k < O; ++k) md.z_ones0[k] = (md.qk[k] >= 1 && all_ones(d->Z[k], d->N[k])) ? 1 : 0;
     for (int t = 0; t < T; ++t) {
-        bool zo = md.rt[t] >= 1 && all_ones(d->ZZ[t], n) && all_ones(d->ZZs[t], ns) && (S == 1 || all_ones(d->ZZs_int[t], ns));
+        bool zo = md.rt[t] >= 1 && all_ones(d->ZZ[t], nT) && all_ones(d->ZZs[t], ns) && (S == 1 || all_ones(d->ZZs_int[t], ns));
         md.zz_ones0[t] = zo ? 1 : 0;
-        bool uo = all_ones(d->U[t], (long long)n * md.ut[t]) && all_ones(d->Us[t], ns * md.ut[t]) &&
+        bool uo = all_ones(d->U[t], (long long)nT * md.ut[t]) && all_ones(d->Us[t], ns * md.ut[t]) &&
                   (S == 1 || all_ones(d->Us_int[t], ns * md.ut[t]));
         md.u_ones[t] = uo ? 1 : 0;
     }
     {
-        std::atomic<int> ok{p > 0 ? 1 : 0};
-        if (p > 0)
+        std::atomic<int> ok{(p > 0 && !ms) ? 1 : 0};   // multi-state: W2 rows differ between a subject's transitions
+        if (p > 0 && !ms)
             parallel_for(n, [&](int lo, int hi) {
                 for (int i = lo; i < hi; ++i)
                     for (int j = 0; j < p; ++j) {
@@ -398,7 +438,8 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     h->doff.assign(n + 1, 0);
     h->coff.assign(n + 1, 0);
     for (int i = 0; i < n; ++i) {
-        long long dl = L.o_long, cl = L.c_long;
+        const int ntr = h->trow[i + 1] - h->trow[i];
+        long long dl = L.o_long + (long long)(ntr - 1) * L.HB, cl = (long long)L.c_long * ntr;
         for (int k = 0; k < O; ++k) {
             int v = h->rowptr[k][i + 1] - h->rowptr[k][i];
             dl += (long long)v * L.long_cols[k];
@@ -412,17 +453,22 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     std::vector<double> drec((size_t)h->doff[n], 0.0);
     parallel_for(n, [&](int lo, int hi) {
         for (int i = lo; i < hi; ++i) {
-            double* rec = drec.data() + h->doff[i];
-            rec[0] = d->event[i];
-            for (int k = 0; k < O; ++k) reinterpret_cast<int*>(rec + L.o_V)[k] = h->rowptr[k][i + 1] - h->rowptr[k][i];
-            if (md.w2_const) for (int j = 0; j < p; ++j) rec[L.o_W2c + j] = d->W2[i + (long long)j * n];
+            double* rec0 = drec.data() + h->doff[i];
+            const int ntr = h->trow[i + 1] - h->trow[i];
+            rec0[0] = ms ? (double)ntr : d->event[i];
+            for (int k = 0; k < O; ++k) reinterpret_cast<int*>(rec0 + L.o_V)[k] = h->rowptr[k][i + 1] - h->rowptr[k][i];
+            if (md.w2_const) for (int j = 0; j < p; ++j) rec0[L.o_W2c + j] = d->W2[i + (long long)j * n];
+            for (int tb = 0; tb < ntr; ++tb) {
+            double* rec = rec0 + (size_t)tb * L.HB;           // hazard-row block of transition row ti
+            const long long ti = h->trow[i] + tb;
+            if (ms) rec[L.o_Pw] = d->event[ti];               // lane 0's Pw slot: event indicator of the transition
             int* w1off = reinterpret_cast<int*>(rec + L.o_W1off);
             for (int r = 0; r < RP; ++r) {
                 int cls = (r == 0) ? 0 : (r <= K ? 1 : ((S == 2 && r <= 2 * K) ? 2 : 3));
                 w1off[r] = 0;
                 if (cls == 3) continue;
-                const long long rows = cls == 0 ? n : ns;
-                const long long src = cls == 0 ? i : (cls == 1 ? (long long)i * K + (r - 1) : (long long)i * K + (r - 1 - K));
+                const long long rows = cls == 0 ? nT : ns;
+                const long long src = cls == 0 ? ti : (cls == 1 ? ti * K + (r - 1) : ti * K + (r - 1 - K));
                 const double* W1x = cls == 0 ? d->W1 : (cls == 1 ? d->W1s : d->W1s_int);
                 const double* W2x = cls == 0 ? d->W2 : (cls == 1 ? d->W2s : d->W2s_int);
                 if (cls == 1) rec[L.o_Pw + r] = d->Pw[src];
@@ -450,7 +496,8 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
                     if (!md.u_ones[t]) for (int u = 0; u < md.ut[t]; ++u) rec[L.o_U[t] + u * RP + r] = Ux[src + (long long)u * rows];
                 }
             }
-            double* lrec = rec + L.o_long;
+            }
+            double* lrec = rec0 + L.o_long + (size_t)(ntr - 1) * L.HB;
             for (int k = 0; k < O; ++k) {
                 const int r0 = h->rowptr[k][i], v = h->rowptr[k][i + 1] - r0;
                 const long long Nk = d->N[k];
@@ -476,7 +523,7 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     h->rng_stride = (q + 2) / 2 * 2;
 
     // event_colSums of W1 and W2 (R/mvJointModelBayes.R:677-679) for gradient_logPosterior
-    h->h_event.assign(d->event, d->event + n);
+    h->h_event.assign(d->event, d->event + nT);
     h->ecs.assign(B + p + d->n_alphas, 0.0);
     if (from_knots) {      // event_colSumsW1 from the band rows, subjects in order (the dense sum's order per column)
         for (int i = 0; i < n; ++i) {
@@ -485,8 +532,16 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
             for (int j = 0; j < std::min(d->ord, B); ++j) h->ecs[off + j] += d->event[i] * bv[j];
         }
     } else
-    for (int j = 0; j < B; ++j) { double t = 0.0; for (int i = 0; i < n; ++i) t += d->event[i] * d->W1[i + (long long)j * n]; h->ecs[j] = t; }
-    for (int j = 0; j < p; ++j) { double t = 0.0; for (int i = 0; i < n; ++i) t += d->event[i] * d->W2[i + (long long)j * n]; h->ecs[B + j] = t; }
+    for (int j = 0; j < B; ++j) { double t = 0.0; for (int i = 0; i < nT; ++i) t += d->event[i] * d->W1[i + (long long)j * nT]; h->ecs[j] = t; }
+    for (int j = 0; j < p; ++j) { double t = 0.0; for (int i = 0; i < nT; ++i) t += d->event[i] * d->W2[i + (long long)j * nT]; h->ecs[B + j] = t; }
+
+    if (host_only) {       // layout inspection only (jmb_debug_pack_host): no device, no compute
+        h->host_only = true;
+        h->h_drec = std::move(drec);
+        build_param_layout(mm, JMB_MAX_TERMS, h->n_block_cap, h->pl);
+        *out = h;
+        return 0;
+    }
 
     // ---- device allocations ----
     cudaError_t e;
@@ -496,7 +551,9 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     CUH(cudaMalloc(&h->d_doff, sizeof(long long) * (n + 1)));
     CUH(cudaMalloc(&h->d_coff, sizeof(long long) * (n + 1)));
     CUH(cudaMalloc(&h->d_rowptr, sizeof(int) * (size_t)O * (n + 1)));
-    CUH(cudaMalloc(&h->d_eval, sizeof(double) * (size_t)n * 6));
+    CUH(cudaMalloc(&h->d_eval, sizeof(double) * (size_t)std::max(n, nT) * 6));
+    CUH(cudaMalloc(&h->d_trow, sizeof(int) * (n + 1)));
+    CUH(cudaMemcpy(h->d_trow, h->trow.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
     CUH(cudaMemcpy(h->d_drec, drec.data(), sizeof(double) * drec.size(), cudaMemcpyHostToDevice));
     CUH(cudaMalloc(&h->d_Rchol, sizeof(double) * rchol.size()));
     CUH(cudaMemcpy(h->d_Rchol, rchol.data(), sizeof(double) * rchol.size(), cudaMemcpyHostToDevice));
@@ -525,6 +582,8 @@ extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) {
     *out = h;
     return 0;
 }
+
+extern "C" int jmb_create(const jmb_data* d, int device, jmb_handle* out) { return create_impl(d, device, out, false); }
 
 // one more chain slot (own stream, per-draw records, state, parameter block, staging)
 int jmb_handle_s::add_slot() {
@@ -569,10 +628,12 @@ extern "C" int jmb_select_chain(jmb_handle h, int slot) {
 
 extern "C" int jmb_destroy(jmb_handle h) {
     if (!h) return 0;
+    if (h->host_only) { delete h; return 0; }
     cudaSetDevice(h->device);
     for (ChainCtx* x : h->slots) if (x->stream) cudaStreamSynchronize(x->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->d_drec); cudaFree(h->d_doff); cudaFree(h->d_coff); cudaFree(h->d_rowptr); cudaFree(h->d_eval);
+    cudaFree(h->d_trow);
     cudaFree(h->d_Rchol); cudaFree(h->d_xrec); cudaFree(h->d_xoff); cudaFree(h->d_betas);
     for (size_t r = 0; r < h->peer_ptrs.size(); ++r)
         if (h->peer_ptrs[r] && (int)r != h->rank) cudaIpcCloseMemHandle(h->peer_ptrs[r]);
@@ -598,25 +659,25 @@ extern "C" int jmb_destroy(jmb_handle h) {
 // ---------------------------------------------------------------------------------------------
 // per-draw vectors
 // ---------------------------------------------------------------------------------------------
-extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
-    if (!h || !w) return fail("jmb_set_draw: null argument");
-    CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->c->stream));        // the staging buffer may still be in flight
+// per-draw records of all subjects into `base` (coff[n] doubles)
+static void pack_draw(jmb_handle h, const jmb_draw* w, double* base) {
     const ModelMeta& mm = h->mm;
     const int n = h->n, K = mm.d.K, RP = mm.L.RP, S = mm.d.S, T = mm.d.T, O = mm.d.O;
-    if (S == 2 && !w->XXsbetas_int) return fail("jmb_set_draw: XXsbetas_int required with interval censoring");
-    double* base = h->c->h_crec;
     parallel_for(n, [&](int lo, int hi) {
         for (int i = lo; i < hi; ++i) {
             double* rec = base + h->coff[i];
-            for (int t = 0; t < T; ++t) {
-                double* x = rec + t * RP;
-                x[0] = w->XXbetas[t][i];
-                for (int r = 1; r <= K; ++r) x[r] = w->XXsbetas[t][(long long)i * K + r - 1];
-                if (S == 2) for (int r = 1; r <= K; ++r) x[K + r] = w->XXsbetas_int[t][(long long)i * K + r - 1];
-                for (int r = 1 + K * S; r < RP; ++r) x[r] = 0.0;
+            const int ntr = h->trow[i + 1] - h->trow[i];
+            for (int tb = 0; tb < ntr; ++tb) {              // one [T][RP] block per transition row (one unless multi-state)
+                const long long ti = h->trow[i] + tb;
+                for (int t = 0; t < T; ++t) {
+                    double* x = rec + (size_t)tb * mm.L.c_long + t * RP;
+                    x[0] = w->XXbetas[t][ti];
+                    for (int r = 1; r <= K; ++r) x[r] = w->XXsbetas[t][ti * K + r - 1];
+                    if (S == 2) for (int r = 1; r <= K; ++r) x[K + r] = w->XXsbetas_int[t][ti * K + r - 1];
+                    for (int r = 1 + K * S; r < RP; ++r) x[r] = 0.0;
+                }
             }
-            double* l = rec + mm.L.c_long;
+            double* l = rec + (size_t)mm.L.c_long * ntr;
             for (int k = 0; k < O; ++k) {
                 const int r0 = h->rowptr[k][i], v = h->rowptr[k][i + 1] - r0;
                 memcpy(l, w->Xbetas[k] + r0, sizeof(double) * v);
@@ -624,6 +685,17 @@ extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
             }
         }
     });
+}
+
+extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
+    if (!h || !w) return fail("jmb_set_draw: null argument");
+    if (h->host_only) return fail("jmb_set_draw: this handle was made by jmb_debug_pack_host (no device)");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->c->stream));        // the staging buffer may still be in flight
+    const ModelMeta& mm = h->mm;
+    const int n = h->n, O = mm.d.O;
+    if (mm.d.S == 2 && !w->XXsbetas_int) return fail("jmb_set_draw: XXsbetas_int required with interval censoring");
+    pack_draw(h, w, h->c->h_crec);
     CU(cudaMemcpyAsync(h->c->d_crec, h->c->h_crec, sizeof(double) * h->coff[n], cudaMemcpyHostToDevice, h->c->stream));
     for (int j = 0; j < mm.d.q * mm.d.q; ++j) h->c->h_par[h->pl.invD + j] = w->invD[j];
     for (int k = 0; k < O; ++k) h->c->h_par[h->pl.sigmas + k] = (mm.d.fam[k] == JMB_FAM_GAUSSIAN) ? w->sigmas[k] : 1.0;
@@ -638,6 +710,7 @@ extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
 extern "C" int jmb_set_xdesigns(jmb_handle h, const jmb_xdesigns* x) {
     if (!h || !x || !x->p_k || !x->X || !x->outcome || !x->f_t || !x->indFixed || !x->XX || !x->XXs)
         return fail("jmb_set_xdesigns: null argument");
+    if (h->ms) return fail("jmb_set_xdesigns: not available for multi-state fits yet (pass the per-draw vectors with jmb_set_draw)");
     const ModelMeta& mm = h->mm;
     const int n = h->n, K = mm.d.K, RP = mm.L.RP, S = mm.d.S, T = mm.d.T, O = mm.d.O;
     if (S == 2 && !x->XXs_int) return fail("jmb_set_xdesigns: XXs_int required with interval censoring");
@@ -755,6 +828,7 @@ static int launch_step(jmb_handle h, int mode) {
     a.state = h->c->d_state; a.par = h->c->d_par; a.ctl = h->c->d_ctl; a.partials = h->c->d_partials; a.eval_out = h->d_eval;
     a.n = h->n; a.subject_offset = h->subject_offset; a.mode = mode; a.subjects_per_cta = h->subjects_per_cta;
     a.rng = h->c->d_rng; a.rng_chunk = h->c->rng_chunk; a.rng_stride = h->rng_stride;
+    a.trow = h->d_trow; a.eval_stride = std::max(h->n, h->nT);
     if (mode == MODE_STEP && h->kernel_mode == 2) {
         if (pdl_enabled()) {
             CU(launch_pdl(h->tma_kernel, dim3(h->tma_grid), dim3(kTmaThreads), (size_t)h->tma_smem, h->c->stream, h->mm.B, h->pl, h->c->cc, a, h->ta));
@@ -764,10 +838,14 @@ static int launch_step(jmb_handle h, int mode) {
     }
     else if (mode == MODE_STEP && h->kernel_mode == 1)
         h->static_kernel<<<h->grid, 256, h->static_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a);
+    else if (h->ms && h->mm.d.G == 16)
+        jmb_step_kernel<16, true><<<h->grid, 256, h->smem_bytes, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
+    else if (h->ms)
+        jmb_step_kernel<32, true><<<h->grid, 256, h->smem_bytes, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
     else if (h->mm.d.G == 16)
-        jmb_step_kernel<16><<<h->grid, 256, h->smem_bytes, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
+        jmb_step_kernel<16, false><<<h->grid, 256, h->smem_bytes, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
     else
-        jmb_step_kernel<32><<<h->grid, 256, h->smem_bytes, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
+        jmb_step_kernel<32, false><<<h->grid, 256, h->smem_bytes, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
     h->launches += 1;
     CU(cudaGetLastError());
     return 0;
@@ -829,6 +907,11 @@ static int chain_setup(jmb_handle h, const jmb_priors* pr, const jmb_control* ct
     cc.target_acc = ct->target_acc; cc.eps1 = ct->eps1; cc.eps2 = ct->eps2; cc.eps3 = ct->eps3;
     cc.c0 = ct->c0; cc.mc1 = -ct->c1; cc.seed = ct->seed; cc.chain_id = ct->chain_id;
     cc.B_tau_Bs = pr->B_tau_Bs_gammas; cc.Apost_tau_Bs = pr->A_tau_Bs_gammas + 0.5 * pr->rank_Tau_Bs_gammas;
+    if (h->ms) {
+        if (wore) return fail("lap_rwm_C_woRE is not defined for multi-state fits (the reference reads a scalar tau_Bs_gammas there)");
+        cc.nRisks = h->nRisks;
+        for (int k = 0; k < h->nRisks; ++k) { cc.kn_first[k] = h->kn_first[k]; cc.kn_last[k] = h->kn_last[k]; }
+    }
     cc.shrink_gammas = pr->shrink_gammas; cc.B_tau_g = pr->B_tau_gammas;
     cc.Apost_tau_g = pr->A_tau_gammas + 0.5 * pr->rank_Tau_gammas;
     cc.B_phi_g = pr->B_phi_gammas; cc.Apost_phi_g = pr->A_phi_gammas + 0.5;
@@ -863,7 +946,8 @@ static int chain_setup(jmb_handle h, const jmb_priors* pr, const jmb_control* ct
     if (p) memcpy(hp + pl.cur + B, in->gammas, sizeof(double) * p);
     memcpy(hp + pl.cur + B + p, in->alphas, sizeof(double) * A);
     memcpy(hp + pl.prop, hp + pl.cur, sizeof(double) * mm.P);
-    hp[pl.tau_Bs] = in->tau_Bs_gammas[0]; hp[pl.tau_g] = in->tau_gammas; hp[pl.tau_a] = in->tau_alphas;
+    for (int k = 0; k < h->nRisks; ++k) hp[pl.tau_Bs + k] = in->tau_Bs_gammas[k];     // rep(., nRisks), R/mvJointModelBayes.R:723-724
+    hp[pl.tau_g] = in->tau_gammas; hp[pl.tau_a] = in->tau_alphas;
     hp[pl.xi_a] = in->tau_alphas;                                        // src/fast_LAPRWM.cpp:518
     for (int j = 0; j < p; ++j) hp[pl.phi_g + j] = in->phi_gammas[j];
     for (int j = 0; j < A; ++j) { hp[pl.phi_a + j] = in->phi_alphas[j]; hp[pl.nu_a + j] = in->phi_alphas[j]; }   // :513
@@ -885,7 +969,7 @@ static int chain_setup(jmb_handle h, const jmb_priors* pr, const jmb_control* ct
     // outputs on the device (buffers are kept across chains of the same shape: cudaMalloc / cudaFree
     // synchronise the device and are slow once peer mappings exist)
     const int no = std::max(cc.n_out, 1);
-    const size_t par_out = (size_t)no * (B + 2 * p + 2 * A + 4 + JMB_MAX_TERMS);
+    const size_t par_out = (size_t)no * (B + 2 * p + 2 * A + 3 + JMB_MAX_RISKS + JMB_MAX_TERMS);
     const size_t need_b = wore ? 1 : (size_t)n * q * no, need_tr = 2 * (size_t)std::max(h->c->total_iters, 1);
     if (need_b > h->c->cap_ob) { cudaFree(h->c->o_b); h->c->o_b = nullptr; CU(cudaMalloc(&h->c->o_b, sizeof(double) * need_b)); h->c->cap_ob = need_b; }
     if (par_out > h->c->cap_opar) { cudaFree(h->c->o_par); h->c->o_par = nullptr; CU(cudaMalloc(&h->c->o_par, sizeof(double) * par_out)); h->c->cap_opar = par_out; }
@@ -901,7 +985,7 @@ static int chain_setup(jmb_handle h, const jmb_priors* pr, const jmb_control* ct
     fa.o_a = o; o += (size_t)no * A;
     fa.o_phi_g = o; o += (size_t)no * p;
     fa.o_phi_a = o; o += (size_t)no * A;
-    fa.o_tau_Bs = o; o += no; fa.o_tau_g = o; o += no; fa.o_tau_a = o; o += no;
+    fa.o_tau_Bs = o; o += (size_t)no * JMB_MAX_RISKS; fa.o_tau_g = o; o += no; fa.o_tau_a = o; o += no;
     fa.o_tau_td = o; o += (size_t)no * JMB_MAX_TERMS;
     fa.o_lw = o;
     fa.trace = h->c->o_trace;
@@ -1070,7 +1154,7 @@ extern "C" int jmb_chain_end(jmb_handle h, jmb_chain_out* out) {
     CU(d2h(out->alphas, fa.o_a, (size_t)A * no));
     CU(d2h(out->phi_gammas, fa.o_phi_g, (size_t)p * no));
     CU(d2h(out->phi_alphas, fa.o_phi_a, (size_t)A * no));
-    CU(d2h(out->tau_Bs_gammas, fa.o_tau_Bs, no));
+    CU(d2h(out->tau_Bs_gammas, fa.o_tau_Bs, (size_t)h->nRisks * no));
     CU(d2h(out->tau_gammas, fa.o_tau_g, no));
     CU(d2h(out->tau_alphas, fa.o_tau_a, no));
     CU(d2h(out->tau_td_alphas, fa.o_tau_td, (size_t)h->c->n_td * no));
@@ -1139,8 +1223,9 @@ extern "C" int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* 
     if (launch_step(h, MODE_EVAL)) return 1;
     CU(cudaStreamSynchronize(h->c->stream));
     double* dst[6] = {out->log_pyb, out->log_pb, out->log_h, out->H, out->HL, out->log_ptb};
+    const size_t es = (size_t)std::max(n, h->nT);       // log_h / H / HL / log_ptb: one value per transition row
     for (int k = 0; k < 6; ++k)
-        if (dst[k]) CU(cudaMemcpy(dst[k], h->d_eval + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        if (dst[k]) CU(cudaMemcpy(dst[k], h->d_eval + (size_t)k * es, sizeof(double) * (k < 2 ? n : h->nT), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -1149,6 +1234,7 @@ extern "C" int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* 
 // ---------------------------------------------------------------------------------------------
 extern "C" int jmb_set_wlong(jmb_handle h, const double* Wlong, const double* Wlongs) {
     if (!h || !Wlong || !Wlongs) return fail("jmb_set_wlong: null argument");
+    if (h->ms) return fail("jmb_set_wlong: the Laplace step (logPosterior / gradient_logPosterior / marglogLik2) is not available for multi-state fits yet");
     CU(cudaSetDevice(h->device));
     const int n = h->n, A = h->mm.d.A, K = h->mm.d.K, B = h->mm.B, p = h->mm.d.p;
     const size_t ns = (size_t)n * K;
@@ -1322,6 +1408,7 @@ extern "C" int jmb_lap_rwm_woRE(jmb_handle h, const jmb_priors* pr, const jmb_co
 static int svft_eval(jmb_handle h, const double* b, const double* Bs, const double* gam, const double* alp,
                      double* log_post, double* surv_pred) {
     const int n = h->n;
+    if (h->ms) return fail("survfitJM evaluators are not available on a multi-state handle");
     std::vector<double> pyb(n), pb(n), H(n);
     jmb_eval_out eo{};
     eo.log_pyb = pyb.data(); eo.log_pb = pb.data(); eo.H = H.data();
@@ -1341,6 +1428,33 @@ extern "C" int jmb_log_post_RE_svft(jmb_handle h, const double* b, const double*
 extern "C" int jmb_survPred_svft_2(jmb_handle h, const double* b, const double* Bs, const double* gam, const double* alp, double* out) {
     if (!h || !b || !out) return fail("jmb_survPred_svft_2: null argument");
     return svft_eval(h, b, Bs, gam, alp, nullptr, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout inspection without a device (CPU tests of the packer; never part of a compute path)
+// ---------------------------------------------------------------------------------------------
+extern "C" int jmb_debug_pack_host(const jmb_data* d, jmb_handle* out) { return create_impl(d, 0, out, true); }
+
+extern "C" int jmb_debug_layout(jmb_handle h, int32_t* ints /* [64] */, int64_t* doff /* [n+1] */, int64_t* coff /* [n+1] */) {
+    if (!h || !ints) return fail("jmb_debug_layout: null argument");
+    const RecordLayout& L = h->mm.L; const ModelDesc& md = h->mm.d;
+    int k = 0;
+    ints[k++] = L.RP; ints[k++] = L.o_V; ints[k++] = L.o_W2c; ints[k++] = L.o_Pw; ints[k++] = L.o_W1off; ints[k++] = L.o_W1v;
+    ints[k++] = L.o_W2; ints[k++] = L.o_long; ints[k++] = L.c_long; ints[k++] = L.HB; ints[k++] = L.state_stride;
+    ints[k++] = md.WB; ints[k++] = md.G; ints[k++] = md.w2_const; ints[k++] = md.MS; ints[k++] = md.S;       // k == 16
+    for (int t = 0; t < kMaxT; ++t) { ints[16 + t] = L.o_ZZ[t]; ints[32 + t] = L.o_U[t]; }
+    for (int t = 0; t < kMaxT; ++t) ints[48 + t] = (t < md.T) ? (md.zz_ones0[t] | (md.u_ones[t] << 1)) : 0;
+    for (int o = 0; o < md.O && o < 8; ++o) ints[48 + 8 + o] |= (md.z_ones0[o] << 8) | (L.long_cols[o] << 16);
+    if (doff) for (int i = 0; i <= h->n; ++i) doff[i] = h->doff[i];
+    if (coff) for (int i = 0; i <= h->n; ++i) coff[i] = h->coff[i];
+    return 0;
+}
+
+extern "C" int jmb_debug_records(jmb_handle h, const jmb_draw* w, double* drec /* [doff[n]] */, double* crec /* [coff[n]] */) {
+    if (!h || !h->host_only) return fail("jmb_debug_records: needs a handle made by jmb_debug_pack_host");
+    if (drec) memcpy(drec, h->h_drec.data(), sizeof(double) * h->h_drec.size());
+    if (crec && w) pack_draw(h, w, crec);
+    return 0;
 }
 
 extern "C" int jmb_get_row_ptr(jmb_handle h, int outcome, int64_t* row_ptr) {

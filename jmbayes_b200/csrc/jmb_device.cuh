@@ -34,7 +34,7 @@ struct ModelMeta {
 struct ParamLayout {
     int cur, prop;                  // [P] each: Bs_gammas | gammas | alphas
     int invD, sigmas;               // [q*q], [O]
-    int tau_Bs, tau_g, tau_a, xi_a; // scalars
+    int tau_Bs, tau_g, tau_a, xi_a; // scalars (tau_Bs: [JMB_MAX_RISKS], one per stratum of a multi-state fit)
     int phi_g, phi_a, nu_a, tau_td; // [p], [A], [A], [n_td]
     int Tau_g, Tau_a, Tau_a_pen;    // [p*p], [A*A], [A*A]
     int sig;                        // [3] sigma_Bs, sigma_gammas, sigma_alphas
@@ -63,6 +63,8 @@ struct ChainConst {                 // scalar constants of one chain (kernel par
     double B_tau_a, Apost_tau_a, B_phi_a, Apost_phi_a, B_xi_a, Apost_xi_a, B_nu_a, Apost_nu_a;
     int n_td; double B_tau_td, Apost_tau_td;
     int td_len[JMB_MAX_TERMS]; int td_cols[JMB_MAX_TERMS][JMB_MAX_UT];
+    // strata of the baseline hazard (multi-state fits, src/fast_LAPRWM.cpp:489-491,777-782); nRisks = 0: unstratified
+    int nRisks; int kn_first[JMB_MAX_RISKS]; int kn_last[JMB_MAX_RISKS];
 };
 
 enum { ST_B_PROP = 0, ST_B_ACC = 1, ST_SURV = 2, ST_GIBBS_N = 3, ST_GIBBS_U = 4, ST_GIBBS_B = 5 };

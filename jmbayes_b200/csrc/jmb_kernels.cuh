@@ -36,6 +36,10 @@ struct StepArgs {
     const double* rng;       // [rng_chunk][n][rng_stride]: proposal increments b_new - b (q) and log u
     int rng_chunk;           // iterations covered by the buffer (the block position i indexes it)
     int rng_stride;          // q + 1 rounded up to even
+    // multi-state fits: first transition row of each subject (global row index, for MODE_EVAL) and the
+    // distance between the six MODE_EVAL output vectors (max(n, nT); n otherwise)
+    const int* trow;         // [n+1]
+    long long eval_stride;
 };
 
 // Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
@@ -48,7 +52,11 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // generic step kernel: runtime model descriptor, G lanes per subject.  Fallback for model shapes
 // without a precompiled specialisation (jmb_step_static.cuh); same results.
 // -------------------------------------------------------------------------------------------
-template <int G>
+// MS = true (multi-state fits, src/fast_LAPRWM.cpp:519-529,669,703): the hazard-row block is repeated once per
+// transition row of the subject (jmb_model.h); log p(T|b) is the sum of the blocks' terms, i.e.
+// rowsum(log_ptb, idT_rsum).  The survival-step sums are then taken for both the old and the proposed b inside
+// the block loop (two more exp per quadrature row) so that nothing per block has to outlive the accept decision.
+template <int G, bool MS>
 __global__ void __launch_bounds__(256)
 jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ ParamLayout pl,
                 const __grid_constant__ ChainConst cc, const __grid_constant__ StepArgs a) {
@@ -86,6 +94,7 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         const double* rec = a.drec + a.doff[s];
         const double* crec = a.crec + a.coff[s];
         double* st = a.state + (long long)s * L.state_stride;
+        const int ntr = MS ? (int)rec[0] : 1;               // transition rows of this subject
         // ---- state + proposal (mvrnorm_cube / extract_b, src/fast_LAPRWM.cpp:123-146,670) ----
         // the draws of this iteration were produced by jmb_block_prep_kernel
         const double* rg = a.rng + ((long long)(i_blk % a.rng_chunk) * a.n + s) * a.rng_stride;
@@ -106,8 +115,8 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         // ---- GLMM log-density over the visit segment (lin_predF + log_longF, :67-78,168-202) ----
         double v_pyb = 0.0;
         {
-            const double* lrec = rec + L.o_long;
-            const double* lcrec = crec + L.c_long;
+            const double* lrec = rec + L.o_long + (ntr - 1) * L.HB;
+            const double* lcrec = crec + L.c_long * ntr;
             for (int k = 0; k < md.O; ++k) {
                 const int* rp = a.rowptr + (long long)k * (a.n + 1);
                 const int v = rp[s + 1] - rp[s];
@@ -128,18 +137,23 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         // One row per lane (RP == G is enforced at jmb_create).
         const int r = lane;
         const int cls = (r == 0) ? 0 : (r <= K ? 1 : ((S == 2 && r <= 2 * K) ? 2 : 3));
+        const int src0 = (tid & 31) - lane;                 // lane 0 of this group inside the warp
         double l_co, l_cn, l_po, l_pn;                       // current/proposed params x old/new b
-        {
-            const int off = reinterpret_cast<const int*>(rec + L.o_W1off)[r];
+        double pw = 0.0, H_co = 0.0, H_cn = 0.0, HL_co = 0.0, HL_cn = 0.0, h_co, h_cn, h_po, h_pn;
+        double ms_co = 0.0, ms_cn = 0.0, ms_po = 0.0, ms_pn = 0.0;   // MS: sums over the subject's transitions
+        for (int tb = 0; tb < ntr; ++tb) {
+            const double* hrec = rec + tb * L.HB;            // this transition's hazard rows (tb == 0 unless MS)
+            const double* hcrec = crec + tb * L.c_long;
+            const int off = reinterpret_cast<const int*>(hrec + L.o_W1off)[r];
             double s1c = 0.0, s1p = 0.0;
             for (int j = 0; j < md.WB; ++j) {
-                const double wv = rec[L.o_W1v + j * RP + r];
+                const double wv = hrec[L.o_W1v + j * RP + r];
                 s1c += wv * s_cur[off + j];
                 s1p += wv * s_prop[off + j];
             }
             double s2c = 0.0, s2p = 0.0;
             for (int j = 0; j < md.p; ++j) {
-                const double wv = md.w2_const ? rec[L.o_W2c + j] : rec[L.o_W2 + j * RP + r];
+                const double wv = md.w2_const ? rec[L.o_W2c + j] : hrec[L.o_W2 + j * RP + r];
                 s2c += wv * s_cur[mm.B + j];
                 s2p += wv * s_prop[mm.B + j];
             }
@@ -147,17 +161,17 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
             const double* alc = s_cur + mm.B + md.p;
             const double* alp = s_prop + mm.B + md.p;
             for (int t = 0; t < md.T; ++t) {
-                const double xxb = crec[t * RP + r];
+                const double xxb = hcrec[t * RP + r];
                 const int ones0 = md.zz_ones0[t];
                 double zo = ones0 ? bo[md.re2[t][0]] : 0.0, zn = ones0 ? bn[md.re2[t][0]] : 0.0;
                 for (int j = ones0; j < md.rt[t]; ++j) {
-                    const double zz = rec[L.o_ZZ[t] + (j - ones0) * RP + r];
+                    const double zz = hrec[L.o_ZZ[t] + (j - ones0) * RP + r];
                     zo += zz * bo[md.re2[t][j]];
                     zn += zz * bn[md.re2[t][j]];
                 }
                 const double vo = trans_fun(md.tf[t], xxb + zo), vn = trans_fun(md.tf[t], xxb + zn);
                 for (int u = 0; u < md.ut[t]; ++u) {
-                    const double uu = md.u_ones[t] ? 1.0 : rec[L.o_U[t] + u * RP + r];
+                    const double uu = md.u_ones[t] ? 1.0 : hrec[L.o_U[t] + u * RP + r];
                     const int c = md.col[t][u];
                     const double wo = uu * vo, wn = uu * vn;
                     a_co += wo * alc[c]; a_cn += wn * alc[c];
@@ -166,27 +180,42 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
             }
             l_co = (s1c + s2c) + a_co; l_cn = (s1c + s2c) + a_cn;
             l_po = (s1p + s2p) + a_po; l_pn = (s1p + s2p) + a_pn;
+            pw = (cls == 1 || cls == 2) ? hrec[L.o_Pw + r] : 0.0;
+            H_co = 0.0; H_cn = 0.0; HL_co = 0.0; HL_cn = 0.0;
+            if (cls == 1) { H_co = pw * exp(l_co); H_cn = pw * exp(l_cn); }
+            else if (cls == 2) { HL_co = pw * exp(l_co); HL_cn = pw * exp(l_cn); }
+            h_co = l_co; h_cn = l_cn; h_po = l_po; h_pn = l_pn;          // meaningful on lane 0 only
+            H_co = group_sum<G>(H_co, gmask);
+            H_cn = group_sum<G>(H_cn, gmask);
+            if (S == 2) { HL_co = group_sum<G>(HL_co, gmask); HL_cn = group_sum<G>(HL_cn, gmask); }
+            h_co = __shfl_sync(gmask, h_co, src0); h_cn = __shfl_sync(gmask, h_cn, src0);
+            h_po = __shfl_sync(gmask, h_po, src0); h_pn = __shfl_sync(gmask, h_pn, src0);
+            if (MS) {
+                // event indicator of this transition: the Pw slot of the event-time row (lane 0 of the block)
+                const double ev_tb = hrec[L.o_Pw];
+                const double Hp_o = group_sum<G>((cls == 1) ? pw * exp(l_po) : 0.0, gmask);
+                const double Hp_n = group_sum<G>((cls == 1) ? pw * exp(l_pn) : 0.0, gmask);
+                const double t_cn = log_ptb_term(1, ev_tb, h_cn, H_cn, 0.0);
+                ms_co += log_ptb_term(1, ev_tb, h_co, H_co, 0.0);
+                ms_cn += t_cn;
+                ms_po += log_ptb_term(1, ev_tb, h_po, Hp_o, 0.0);
+                ms_pn += log_ptb_term(1, ev_tb, h_pn, Hp_n, 0.0);
+                if (a.mode == MODE_EVAL && lane == 0) {      // one value per transition row
+                    const long long tr = (long long)a.trow[s] + tb;
+                    a.eval_out[2LL * a.eval_stride + tr] = h_cn; a.eval_out[3LL * a.eval_stride + tr] = H_cn;
+                    a.eval_out[4LL * a.eval_stride + tr] = H_cn; a.eval_out[5LL * a.eval_stride + tr] = t_cn;
+                }
+            }
         }
-        const double pw = (cls == 1 || cls == 2) ? rec[L.o_Pw + r] : 0.0;
-        double H_co = 0.0, H_cn = 0.0, HL_co = 0.0, HL_cn = 0.0;
-        if (cls == 1) { H_co = pw * exp(l_co); H_cn = pw * exp(l_cn); }
-        else if (cls == 2) { HL_co = pw * exp(l_co); HL_cn = pw * exp(l_cn); }
-        double h_co = l_co, h_cn = l_cn, h_po = l_po, h_pn = l_pn;   // meaningful on lane 0 only
         v_pyb = group_sum<G>(v_pyb, gmask);
         v_pb = -0.5 * group_sum<G>(v_pb, gmask);
-        H_co = group_sum<G>(H_co, gmask);
-        H_cn = group_sum<G>(H_cn, gmask);
-        if (S == 2) { HL_co = group_sum<G>(HL_co, gmask); HL_cn = group_sum<G>(HL_cn, gmask); }
-        const int src0 = (tid & 31) - lane;                 // lane 0 of this group inside the warp
-        h_co = __shfl_sync(gmask, h_co, src0); h_cn = __shfl_sync(gmask, h_cn, src0);
-        h_po = __shfl_sync(gmask, h_po, src0); h_pn = __shfl_sync(gmask, h_pn, src0);
 
-        const double event = rec[0];
+        const double event = MS ? 0.0 : rec[0];
         // log p(T|b_old) under the current parameters is carried in the state: slot q+5 when the
         // last survival proposal was rejected, slot q+6 (evaluated at that proposal) when accepted
         const double ptb_co = (a.mode == MODE_STEP) ? (last_acc ? bo[q + 6] : bo[q + 5])
-                                                    : log_ptb_term(S, event, h_co, H_co, HL_co);
-        const double ptb_cn = log_ptb_term(S, event, h_cn, H_cn, HL_cn);
+                                                    : (MS ? ms_co : log_ptb_term(S, event, h_co, H_co, HL_co));
+        const double ptb_cn = MS ? ms_cn : log_ptb_term(S, event, h_cn, H_cn, HL_cn);
 
         bool accept;
         double pyb_new = v_pyb, pb_new = v_pb;
@@ -199,13 +228,18 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
             accept = true;
         }
         // ---- proposed survival parameters at the accepted b (:735-752) ----
-        double Hp = 0.0, HLp = 0.0;
-        if (cls == 1) Hp = pw * exp(accept ? l_pn : l_po);
-        else if (cls == 2) HLp = pw * exp(accept ? l_pn : l_po);
-        Hp = group_sum<G>(Hp, gmask);
-        if (S == 2) HLp = group_sum<G>(HLp, gmask);
+        double ptb_p;
+        if (MS) {
+            ptb_p = accept ? ms_pn : ms_po;
+        } else {
+            double Hp = 0.0, HLp = 0.0;
+            if (cls == 1) Hp = pw * exp(accept ? l_pn : l_po);
+            else if (cls == 2) HLp = pw * exp(accept ? l_pn : l_po);
+            Hp = group_sum<G>(Hp, gmask);
+            if (S == 2) HLp = group_sum<G>(HLp, gmask);
+            ptb_p = log_ptb_term(S, event, accept ? h_pn : h_po, Hp, HLp);
+        }
         const double ptb_c = accept ? ptb_cn : ptb_co;
-        const double ptb_p = log_ptb_term(S, event, accept ? h_pn : h_po, Hp, HLp);
         const double pyb_acc = accept ? pyb_new : pyb_old;
         const double pb_acc = accept ? pb_new : pb_old;
         acc_cur += ptb_c; acc_prop += ptb_p; acc_lw += pyb_acc + pb_acc;
@@ -213,10 +247,12 @@ jmb_step_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ Pa
         // ---- write back (:707-724) + per-subject scale adaptation at block ends (:853-859) ----
         if (a.mode == MODE_EVAL) {
             if (lane == 0) {
-                a.eval_out[s] = pyb_new; a.eval_out[a.n + s] = pb_new;
-                a.eval_out[2LL * a.n + s] = h_cn; a.eval_out[3LL * a.n + s] = H_cn;
-                a.eval_out[4LL * a.n + s] = (S == 2) ? HL_cn : H_cn;
-                a.eval_out[5LL * a.n + s] = ptb_cn;
+                a.eval_out[s] = pyb_new; a.eval_out[a.eval_stride + s] = pb_new;
+                if (!MS) {
+                    a.eval_out[2LL * a.eval_stride + s] = h_cn; a.eval_out[3LL * a.eval_stride + s] = H_cn;
+                    a.eval_out[4LL * a.eval_stride + s] = (S == 2) ? HL_cn : H_cn;
+                    a.eval_out[5LL * a.eval_stride + s] = ptb_cn;
+                }
             }
         } else {
             double accb = bo[q + 3] + ((a.mode == MODE_STEP && accept) ? 1.0 : 0.0);
@@ -361,15 +397,16 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     // Everything random in this kernel depends only on (seed, chain, iteration), and the loop control is written by
     // finalize kernels only: draw it now, under the tail of the step kernel.  Gamma draws are taken at unit scale (the
     // data-dependent scale multiplies the same number afterwards: bitwise the value rgamma_dev would return).
-    __shared__ double s_lu, s_gam[4 + JMB_MAX_TERMS + JMB_MAX_GAMMAS + 2 * JMB_MAX_ALPHAS];
+    __shared__ double s_lu, s_gam[4 + JMB_MAX_RISKS + JMB_MAX_TERMS + JMB_MAX_GAMMAS + 2 * JMB_MAX_ALPHAS];
+    const int nR = cc.nRisks > 0 ? cc.nRisks : 1;       // Gibbs draws of tau_Bs_gammas: one per stratum (:777-782)
     const int iter_pre = a.ctl->iter;
     if (a.phase == 0) {
-        int nd = 1 + cc.n_td;
+        int nd = nR + cc.n_td;
         const int d_g = nd; if (cc.shrink_gammas) nd += p + 1;
         const int d_a = nd; if (cc.shrink_alphas) nd += A + 1 + (cc.double_gamma_alphas ? A + 1 : 0);
         for (int dd = tid; dd < nd; dd += blockDim.x) {
             double shape;
-            if (dd == 0) shape = cc.Apost_tau_Bs;
+            if (dd < nR) shape = cc.Apost_tau_Bs;
             else if (dd < d_g) shape = cc.Apost_tau_td;
             else if (dd < d_a) shape = (dd - d_g < p) ? cc.Apost_phi_g : cc.Apost_tau_g;
             else {
@@ -468,12 +505,16 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
             else if (tid < B + p) { base = B; m = p; To = pl.Tau_g; Mo = pl.mean_g; }
             else { base = B + p; m = A; To = pl.Tau_a; Mo = pl.mean_a; }
             const int jj = tid - base;
+            // stratified baseline hazard: the tau_Bs_gammas draw of a stratum uses its diagonal block of Tau_Bs_gammas only
+            int sf = 0, sl = m - 1;
+            if (cc.nRisks > 0 && tid < B)
+                for (int k = 0; k < cc.nRisks; ++k) if (jj >= cc.kn_first[k] && jj <= cc.kn_last[k]) { sf = cc.kn_first[k]; sl = cc.kn_last[k]; }
             double tc = 0.0, tp = 0.0, rc = 0.0, rp = 0.0;
             for (int l = 0; l < m; ++l) {
                 const double tau = par[To + l + jj * m], mu = par[Mo + l];
                 const double xc = cur[base + l], xp = prop[base + l];
                 tc += (xc - mu) * tau; tp += (xp - mu) * tau;
-                rc += xc * tau; rp += xp * tau;
+                if (l >= sf && l <= sl) { rc += xc * tau; rp += xp * tau; }
             }
             const double mu = par[Mo + jj];
             s_q[0][tid] = tc * (cur[tid] - mu); s_q[1][tid] = tp * (prop[tid] - mu);
@@ -503,19 +544,26 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         const double lu = s_lu;
         ctl->last_accept = 0;
         double raw_Bs = rawc;
+        int raw_row = 2;                                   // s_q row holding (x' Tau_Bs)_j x_j of the state kept
         if (lu < new_lp - cur_lp) {
             for (int j = 0; j < mm.P; ++j) cur[j] = prop[j];
             ctl->accept_s_block += 1; ctl->accept_s_total += 1;
             ctl->last_accept = 1;
-            raw_Bs = rawp;
+            raw_Bs = rawp; raw_row = 3;
             if (a.wore) par[pl.cur_lp] = new_lp;
         }
         if (cc.adaptCov) for (int j = 0; j < mm.P; ++j) gpar[pl.block_par + j + ctl->i * mm.P] = cur[j];
         // ---- Gibbs draws of the precisions (:776-834) ----
         uint32_t draw = 0;
-        {
+        if (cc.nRisks == 0) {
             const double Bpost = cc.B_tau_Bs + 0.5 * raw_Bs;           // B_tau + 0.5 Bs' Tau Bs (:778-779)
             par[pl.tau_Bs] = fmin(cc.eps3, fmax(cc.eps2, (s_gam[draw++] * (1.0 / Bpost))));
+        } else {
+            for (int k = 0; k < cc.nRisks; ++k) {                      // one draw per stratum (:777-782)
+                double sq = 0.0;
+                for (int j = cc.kn_first[k]; j <= cc.kn_last[k]; ++j) sq += s_q[raw_row][j];
+                par[pl.tau_Bs + k] = fmin(cc.eps3, fmax(cc.eps2, (s_gam[draw++] * (1.0 / (cc.B_tau_Bs + 0.5 * sq)))));
+            }
         }
         double* alp = cur + B + p;
         double* gam = cur + B;
@@ -559,7 +607,8 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
             for (int j = 0; j < B; ++j) a.o_Bs[j + ko * B] = cur[j];
             for (int j = 0; j < p; ++j) { a.o_g[j + ko * p] = gam[j]; a.o_phi_g[j + ko * p] = par[pl.phi_g + j]; }
             for (int j = 0; j < A; ++j) { a.o_a[j + ko * A] = alp[j]; a.o_phi_a[j + ko * A] = par[pl.phi_a + j]; }
-            a.o_tau_Bs[ko] = par[pl.tau_Bs]; a.o_tau_g[ko] = par[pl.tau_g]; a.o_tau_a[ko] = par[pl.tau_a];
+            for (int k = 0; k < nR; ++k) a.o_tau_Bs[k + ko * nR] = par[pl.tau_Bs + k];
+            a.o_tau_g[ko] = par[pl.tau_g]; a.o_tau_a[ko] = par[pl.tau_a];
             for (int j = 0; j < cc.n_td; ++j) a.o_tau_td[j + ko * cc.n_td] = par[pl.tau_td + j];
             a.o_lw[ko] = a.wore ? par[pl.cur_lp] : -s_tot[2];        // log_weightsREF :359-369,847 / out_logPost :1107
             ctl->keep_iterator += 1; ctl->check_iterator += 1;

@@ -16,6 +16,12 @@
 // The upper Cholesky factors of Covs$b (packed by column, q(q+1)/2 doubles per subject) live in
 // their own array: only the once-per-block proposal kernel reads them.
 //
+// Multi-state fits (ModelDesc::MS; src/fast_LAPRWM.cpp:519-529): a subject has ntr >= 1 transition rows, each with its
+// own event-time row and K quadrature rows.  The hazard-row part of the design record ([o_Pw, o_long), HB doubles) is
+// then repeated ntr times, followed by the longitudinal rows; rec[0] holds ntr instead of the event indicator, and the
+// event indicator of a transition sits in its block's Pw slot of lane 0 (the event-time row has no quadrature weight).
+// The per-draw record repeats its [T][RP] part ntr times in the same way.  w2_const is never set for these fits.
+//
 // "Stored" columns: an all-ones first column of Z / ZZ (random intercept) and an all-ones U
 // (default interaction design ~1) are not stored; the flags below say so.  jmb_create() decides
 // the flags by scanning the data, so they never change results.
@@ -41,6 +47,7 @@ struct ModelDesc {
     int WB;                         // stored band of the B-spline basis rows (n_Bs when dense)
     int G;                          // lanes per subject (16 or 32); RP == G
     int w2_const;                   // W2s rows equal the W2 row within each subject
+    int MS;                         // multi-state fit: variable number of hazard-row blocks per subject
     int fam[kMaxO], link[kMaxO], qk[kMaxO], z_ones0[kMaxO];
     int re_inds[kMaxO][kMaxQ];
     int rt[kMaxT], ut[kMaxT], tf[kMaxT], zz_ones0[kMaxT], u_ones[kMaxT];
@@ -52,6 +59,7 @@ struct RecordLayout {
     int RP, o_V, o_W2c, o_Pw, o_W1off, o_W1v, o_W2, o_ZZ[kMaxT], o_U[kMaxT], o_long, c_long;
     int long_cols[kMaxO];           // stored doubles per longitudinal row of outcome k (y + Z cols)
     int state_stride;               // q + kStateExtra, padded to even
+    int HB;                         // doubles of one hazard-row block = o_long - o_Pw (stride between transition blocks)
 };
 
 JMB_HD constexpr RecordLayout make_layout(const ModelDesc& d) {
@@ -72,6 +80,7 @@ JMB_HD constexpr RecordLayout make_layout(const ModelDesc& d) {
         L.o_U[t] = o; o += (d.u_ones[t] ? 0 : d.ut[t]) * L.RP;
     }
     L.o_long = o;
+    L.HB = L.o_long - L.o_Pw;
     L.c_long = d.T * L.RP;
     for (int k = 0; k < d.O; ++k) L.long_cols[k] = 1 + d.qk[k] - d.z_ones0[k];
     L.state_stride = (d.q + kStateExtra + 1) / 2 * 2;
@@ -80,7 +89,7 @@ JMB_HD constexpr RecordLayout make_layout(const ModelDesc& d) {
 
 JMB_HD constexpr bool same_desc(const ModelDesc& a, const ModelDesc& b) {
     if (a.O != b.O || a.q != b.q || a.T != b.T || a.A != b.A || a.p != b.p || a.K != b.K || a.S != b.S ||
-        a.WB != b.WB || a.G != b.G || a.w2_const != b.w2_const) return false;
+        a.WB != b.WB || a.G != b.G || a.w2_const != b.w2_const || a.MS != b.MS) return false;
     for (int k = 0; k < a.O; ++k) {
         if (a.fam[k] != b.fam[k] || a.link[k] != b.link[k] || a.qk[k] != b.qk[k] || a.z_ones0[k] != b.z_ones0[k]) return false;
         for (int j = 0; j < a.qk[k]; ++j) if (a.re_inds[k][j] != b.re_inds[k][j]) return false;

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from jmbayes_b200 import _abi  # noqa: E402
-from jmbayes_b200.cohorts import make_cohort  # noqa: E402
+from jmbayes_b200.cohorts import make_cohort, make_multistate_cohort  # noqa: E402
 from oracle import np_twin, ref  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -37,6 +37,34 @@ def run_case(name):
     ctl = dict(c["control"]); ctl.update(ctl_over)
     pr = dict(c["priors"]); pr.update(pr_over)
     r = ref.lap_rwm_C(c["inits"], c["Data"], pr, c["scales"], c["Covs"], ctl, c["interval_cens"], chain_id=chain)
+    out = {f"mcmc_{k}": v for k, v in r["mcmc"].items()}
+    out["logWeights"] = r["logWeights"]
+    out["sigma_b"] = r["scales"]["sigma"]["b"]
+    out["sigma_surv"] = np.array([r["scales"]["sigma"][k] for k in ("Bs_gammas", "gammas", "alphas")])
+    for k in ("Bs_gammas", "gammas", "alphas"):
+        out[f"Sigma_{k}"] = r["scales"]["Sigma"][k]
+    return out
+
+
+MS_CASES = {
+    # multi-state fits (multiState = TRUE): name -> (n, control overrides, prior overrides, chain id)
+    "chain_multistate": (90, dict(n_burnin=40, n_iter=20, n_block=10, n_thin=5), {}, 6),
+    "chain_multistate_shrink_adapt": (70, dict(n_burnin=30, n_iter=30, n_block=10, n_thin=6, adaptCov=True),
+                                      dict(shrink_gammas=True, shrink_alphas=True, double_gamma_alphas=True), 7),
+}
+
+
+def ms_inputs(name):
+    n, ctl_over, pr_over, chain = MS_CASES[name]
+    c = make_multistate_cohort(n=n)
+    ctl = dict(c["control"]); ctl.update(ctl_over)
+    pr = dict(c["priors"]); pr.update(pr_over)
+    return c, ctl, pr, chain
+
+
+def run_ms_case(name):
+    c, ctl, pr, chain = ms_inputs(name)
+    r = ref.lap_rwm_C(c["inits"], c["Data"], pr, c["scales"], c["Covs"], ctl, False, True, chain_id=chain)
     out = {f"mcmc_{k}": v for k, v in r["mcmc"].items()}
     out["logWeights"] = r["logWeights"]
     out["sigma_b"] = r["scales"]["sigma"]["b"]
@@ -135,6 +163,9 @@ if __name__ == "__main__":
     ref.build(force=True)
     for name in CASES:
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_case(name))
+        print("wrote", name)
+    for name in MS_CASES:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_ms_case(name))
         print("wrote", name)
     for name in WORE_CASES:
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_wore_case(name))

@@ -169,8 +169,9 @@ def test_errors_are_loud(cuda_lib):
     with cuda_lib.Fit(c["Data"], c["Covs"]["b"], False) as fit:
         with pytest.raises(cuda_lib.JmbError):   # no draw set yet
             fit.eval_logpost_re(c["inits"]["b"], c["inits"]["Bs_gammas"], c["inits"]["gammas"], c["inits"]["alphas"])
-    with pytest.raises(cuda_lib.JmbError):
-        cuda_lib.Fit(c["Data"], c["Covs"]["b"], False, multiState=True)
+    with pytest.raises(cuda_lib.JmbError):       # multiState without the transition-row fields
+        D2 = dict(c["Data"]); D2["nRisks"] = 0
+        cuda_lib.Fit(D2, c["Covs"]["b"], False, multiState=True)
     # a control for which the reference indexes past its output arrays (src/fast_LAPRWM.cpp:836-850)
     ctl = dict(c["control"]); ctl.update(n_burnin=40, n_iter=40, n_block=10, n_thin=7)
     with pytest.raises(cuda_lib.JmbError):

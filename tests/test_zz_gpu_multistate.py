@@ -1,0 +1,110 @@
+"""Multi-state fits (``multiState = TRUE``) on the CUDA path, through the C ABI, against the CPU oracle, the reference's
+golden vectors and a size-independent property.  Tolerances as in test_gpu_parity.py (1e-10 relative on the pieces of
+the b-step target against the exact-rowsum oracle).
+
+STATUS: this path (jmb_step_kernel<G, true>, the per-stratum tau_Bs_gammas draws of the finalize kernel, the packer for
+several transition rows per subject) was written after round 1's GPU minutes were spent: it is compiled for sm_100a and
+checked on the CPU side (tests/test_multistate_cpu.py), but had not been run on a B200 when it was committed.  The
+tests are therefore marked xfail(strict=False): they report XPASS when the path is right and cannot hide a regression
+of anything else (this file sorts last).  Remove the marker after the first green run.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from jmbayes_b200.cohorts import make_cohort, make_multistate_cohort
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="multi-state CUDA path not yet run on a B200 (round-1 GPU budget spent)")]
+RTOL = 1e-10
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+make_golden = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(make_golden)
+
+
+def _rel(a, b, floor=1e-12):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def test_one_transition_per_subject_is_the_ordinary_fit(cuda_lib, monkeypatch):
+    """One transition row per subject, one stratum: the multi-state kernel must walk the chain of the generic kernel."""
+    monkeypatch.setenv("JMB_KERNEL", "generic")
+    c = make_cohort("config3", n=300)
+    ctl = dict(c["control"]); ctl.update(n_burnin=30, n_iter=20, n_block=10, n_thin=10)
+    ini = c["inits"]
+    res = []
+    for ms in (False, True):
+        with cuda_lib.Fit(c["Data"], c["Covs"]["b"], False, multiState=ms) as fit:
+            assert fit.layout_info()["kernel"] == "generic"
+            fit.set_draw(c["Data"])
+            ev = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+            res.append((ev, fit.lap_rwm_C(ini, c["priors"], c["scales"], c["Covs"], ctl)))
+    (e0, r0), (e1, r1) = res
+    for k in ("log_pyb", "log_pb", "log_h", "H", "log_ptb"):
+        assert _rel(e1[k], e0[k]) <= 1e-13, k
+    assert _rel(r1["extras"]["trace_surv"], r0["extras"]["trace_surv"]) <= 1e-12
+    assert np.allclose(r1["mcmc"]["b"], r0["mcmc"]["b"], rtol=1e-10, atol=1e-12)
+    for k in ("Bs_gammas", "gammas", "alphas", "tau_Bs_gammas"):
+        assert np.allclose(r1["mcmc"][k], r0["mcmc"][k], rtol=1e-10), k
+
+
+@pytest.mark.parametrize("n", [400, 23])
+def test_logpost_pieces_match_oracle_multistate(cuda_lib, oracle, n):
+    c = make_multistate_cohort(n=n)
+    D, ini = c["Data"], c["inits"]
+    oracle.set_rowsum_mode(1)
+    ref = oracle.eval_logpost_re(D, c["Covs"]["b"], False, ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"], multiState=True)
+    with cuda_lib.Fit(D, c["Covs"]["b"], False, multiState=True) as fit:
+        assert fit.nT == D["event"].size and fit.nRisks == 3
+        fit.set_draw(D)
+        got = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+    for key in ("log_pyb", "log_pb", "log_h", "H", "log_ptb"):
+        assert got[key].shape == ref[key].shape, key
+        assert np.isfinite(got[key]).all(), key
+        assert _rel(got[key], ref[key]) <= RTOL, (key, _rel(got[key], ref[key]))
+    # the b-step target: log p(y|b) + rowsum(log_ptb, idT_rsum) + log p(b)  (src/fast_LAPRWM.cpp:669)
+    idT = np.asarray(D["idT2"][0])
+    tot = got["log_pyb"] + np.bincount(idT, weights=got["log_ptb"]) + got["log_pb"]
+    tot_ref = ref["log_pyb"] + np.bincount(idT, weights=ref["log_ptb"]) + ref["log_pb"]
+    assert _rel(tot, tot_ref) <= RTOL
+
+
+def test_chain_matches_oracle_multistate(cuda_lib, oracle):
+    c = make_multistate_cohort(n=300)
+    ctl = dict(c["control"]); ctl.update(n_burnin=60, n_iter=40, n_block=10, n_thin=10)
+    oracle.set_rowsum_mode(1)
+    ref = oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, False, True, chain_id=3)
+    got = cuda_lib.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, False, True, chain_id=3)
+    assert _rel(got["extras"]["trace_surv"], ref["extras"]["trace_surv"]) <= 1e-9
+    assert np.allclose(got["mcmc"]["b"], ref["mcmc"]["b"], rtol=1e-8, atol=1e-11)
+    assert got["mcmc"]["tau_Bs_gammas"].shape == (3, 4)                       # nRisks x n_out
+    for key in ("Bs_gammas", "gammas", "alphas", "tau_Bs_gammas"):
+        assert np.allclose(got["mcmc"][key], ref["mcmc"][key], rtol=1e-8, atol=1e-12), key
+    assert np.allclose(got["logWeights"], ref["logWeights"], rtol=1e-10)
+    assert np.allclose(got["scales"]["sigma"]["b"], ref["scales"]["sigma"]["b"], rtol=1e-9)
+    assert np.allclose(got["extras"]["accept_b"], ref["extras"]["accept_b"])
+    assert 0.05 < got["extras"]["accept_b"].mean() < 0.8
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.MS_CASES))
+def test_cuda_reproduces_reference_multistate_golden(cuda_lib, name):
+    from test_multistate_cpu import check_chain
+    c, ctl, pr, chain = make_golden.ms_inputs(name)
+    r = cuda_lib.lap_rwm_C(c["inits"], c["Data"], pr, c["scales"], c["Covs"], ctl, False, True, chain_id=chain)
+    check_chain(r, dict(np.load(os.path.join(HERE, "golden", name + ".npz"))), rtol=1e-7, atol=1e-10)
+
+
+def test_multistate_limits_are_loud(cuda_lib):
+    c = make_multistate_cohort(n=40)
+    with pytest.raises(cuda_lib.JmbError):            # not combinable with interval censoring
+        cuda_lib.Fit(c["Data"], c["Covs"]["b"], True, multiState=True)
+    D = dict(c["Data"]); D["idT2"] = [np.asarray(D["idT2"][0])[::-1].copy()]
+    with pytest.raises(cuda_lib.JmbError):            # transition rows must be grouped by subject
+        cuda_lib.Fit(D, c["Covs"]["b"], False, multiState=True)
+    with cuda_lib.Fit(c["Data"], c["Covs"]["b"], False, multiState=True) as fit:
+        with pytest.raises(cuda_lib.JmbError):        # Laplace step not available for multi-state fits yet
+            fit.set_wlong(np.zeros((fit.n, fit.A)), np.zeros((fit.n * fit.K, fit.A)))
