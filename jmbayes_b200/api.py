@@ -248,8 +248,8 @@ class Fit:
         """Data$Wlong (n x A) and Data$Wlongs (nK x A) for logPosterior / gradient_logPosterior."""
         a = np.asfortranarray(np.asarray(Wlong, dtype=np.float64))
         b = np.asfortranarray(np.asarray(Wlongs, dtype=np.float64))
-        if a.shape != (self.n, self.A) or b.shape != (self.n * self.K, self.A):
-            raise JmbError("set_wlong: Wlong must be n x n_alphas and Wlongs nK x n_alphas")
+        if a.shape != (self.nT, self.A) or b.shape != (self.nT * self.K, self.A):
+            raise JmbError("set_wlong: Wlong must be n x n_alphas and Wlongs nK x n_alphas (nT rows for a multi-state fit)")
         _check(lib().jmb_set_wlong(self._h, _dptr(a), _dptr(b)))
 
     def _post_args(self, Bs_gammas, gammas, alphas, priors):

@@ -1234,9 +1234,9 @@ extern "C" int jmb_eval_logpost_re(jmb_handle h, const double* b, const double* 
 // ---------------------------------------------------------------------------------------------
 extern "C" int jmb_set_wlong(jmb_handle h, const double* Wlong, const double* Wlongs) {
     if (!h || !Wlong || !Wlongs) return fail("jmb_set_wlong: null argument");
-    if (h->ms) return fail("jmb_set_wlong: the Laplace step (logPosterior / gradient_logPosterior / marglogLik2) is not available for multi-state fits yet");
     CU(cudaSetDevice(h->device));
-    const int n = h->n, A = h->mm.d.A, K = h->mm.d.K, B = h->mm.B, p = h->mm.d.p;
+    // rows of Wlong: one per subject, or one per transition row of a multi-state fit (R/mvJointModelBayes.R:559-565)
+    const int n = h->ms ? h->nT : h->n, A = h->mm.d.A, K = h->mm.d.K, B = h->mm.B, p = h->mm.d.p;
     const size_t ns = (size_t)n * K;
     if (!h->d_Wlong) {
         CU(cudaMalloc(&h->d_Wlong, sizeof(double) * (size_t)n * A));
@@ -1265,6 +1265,7 @@ static int launch_surv_post(jmb_handle h, const double* d_theta, int value_only)
     SurvPostArgs a{};
     a.drec = h->d_drec; a.doff = h->d_doff; a.Wlong = h->d_Wlong; a.Wlongs = h->d_Wlongs; a.theta = d_theta;
     a.partials = h->d_sp_partials; a.n = h->n; a.subjects_per_cta = h->subjects_per_cta; a.value_only = value_only;
+    a.trow = h->d_trow; a.nT = h->nT; a.ms = h->ms ? 1 : 0;
     const int groups = 256 / mm.d.G;
     const int smem = (int)sizeof(double) * (mm.P + groups * NA);
     if (mm.d.G == 16) jmb_surv_post_kernel<16><<<h->grid, 256, smem, h->c->stream>>>(mm, a);

@@ -721,6 +721,8 @@ struct SurvPostArgs {
     double* partials;        // [gridDim.x][P + 2]
     int n, subjects_per_cta;
     int value_only;          // skip the score sums (woRE chain: only the log-posterior is needed)
+    // multi-state fits: Wlong has nT rows, Wlongs nT * K; trow[s] = first transition row of subject s
+    const int* trow; int nT; int ms;
 };
 
 template <int G>
@@ -739,10 +741,15 @@ jmb_surv_post_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant
     for (int j = tid; j < GROUPS * NA; j += THREADS) s_acc[j] = 0.0;
     __syncthreads();
     double* acc = s_acc + grp * NA;
-    const long long ns = (long long)a.n * K;
+    const long long nT = a.ms ? a.nT : a.n;           // rows of Wlong
+    const long long ns = nT * K;
     const int s_begin = blockIdx.x * a.subjects_per_cta, s_end = min(a.n, s_begin + a.subjects_per_cta);
     for (int s = s_begin + grp; s < s_end; s += GROUPS) {
-        const double* rec = a.drec + a.doff[s];
+      const double* rec0 = a.drec + a.doff[s];
+      const int ntr = a.ms ? (int)rec0[0] : 1;       // one hazard-row block per transition row (jmb_model.h)
+      for (int tb = 0; tb < ntr; ++tb) {
+        const double* rec = rec0 + tb * L.HB;
+        const long long tr = a.ms ? (long long)a.trow[s] + tb : s;
         const int r = lane;
         const int cls = (r == 0) ? 0 : (r <= K ? 1 : 3);
         const int off = reinterpret_cast<const int*>(rec + L.o_W1off)[r];
@@ -751,15 +758,15 @@ jmb_surv_post_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant
             for (int j = 0; j < md.WB && md.WB <= 8; ++j) { w1[j] = rec[L.o_W1v + j * RP + r]; lin += w1[j] * s_theta[off + j]; }
             if (md.WB > 8) for (int j = 0; j < md.WB; ++j) lin += rec[L.o_W1v + j * RP + r] * s_theta[off + j];
             double l2 = 0.0;
-            for (int j = 0; j < p; ++j) l2 += (md.w2_const ? rec[L.o_W2c + j] : rec[L.o_W2 + j * RP + r]) * s_theta[B + j];
+            for (int j = 0; j < p; ++j) l2 += (md.w2_const ? rec0[L.o_W2c + j] : rec[L.o_W2 + j * RP + r]) * s_theta[B + j];
             double l3 = 0.0;
             for (int c = 0; c < A; ++c) {
-                wl[c] = (cls == 0) ? a.Wlong[s + (long long)c * a.n] : a.Wlongs[(long long)s * K + (r - 1) + (long long)c * ns];
+                wl[c] = (cls == 0) ? a.Wlong[tr + (long long)c * nT] : a.Wlongs[tr * K + (r - 1) + (long long)c * ns];
                 l3 += wl[c] * s_theta[B + p + c];
             }
             lin = (lin + l2) + l3;
         }
-        const double event = rec[0];
+        const double event = a.ms ? rec[L.o_Pw] : rec0[0];
         const double pw = (cls == 1) ? rec[L.o_Pw + r] : 0.0;
         const double Int = (cls == 1) ? pw * exp(lin) : 0.0;
         // value terms
@@ -783,7 +790,7 @@ jmb_surv_post_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant
             }
         }
         for (int j = 0; j < p; ++j) {
-            const double wv = md.w2_const ? rec[L.o_W2c + j] : rec[L.o_W2 + j * RP + r];
+            const double wv = md.w2_const ? rec0[L.o_W2c + j] : rec[L.o_W2 + j * RP + r];
             const double v = group_sum<G>(wv * Int, gmask);
             if (lane == 0) acc[2 + B + j] += v;
         }
@@ -791,6 +798,7 @@ jmb_surv_post_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant
             const double v = group_sum<G>((cls == 1) ? wl[c] * Int : 0.0, gmask);
             if (lane == 0) acc[2 + B + p + c] += v;
         }
+      }
     }
     __syncthreads();
     for (int j = tid; j < NA; j += THREADS) {

@@ -106,5 +106,36 @@ def test_multistate_limits_are_loud(cuda_lib):
     with pytest.raises(cuda_lib.JmbError):            # transition rows must be grouped by subject
         cuda_lib.Fit(D, c["Covs"]["b"], False, multiState=True)
     with cuda_lib.Fit(c["Data"], c["Covs"]["b"], False, multiState=True) as fit:
-        with pytest.raises(cuda_lib.JmbError):        # Laplace step not available for multi-state fits yet
+        with pytest.raises(cuda_lib.JmbError):        # Wlong has one row per transition
             fit.set_wlong(np.zeros((fit.n, fit.A)), np.zeros((fit.n * fit.K, fit.A)))
+        with pytest.raises(cuda_lib.JmbError):        # Xbetas_calc on the device: not for multi-state fits yet
+            fit.set_xdesigns(c["Data"])
+
+
+def test_laplace_step_multistate(cuda_lib, oracle):
+    """logPosterior / gradient_logPosterior (src/fast_logPost.cpp:8-26, src/fast_score.cpp:8-50) on the nT transition
+    rows of a multi-state fit, as marglogLik2 calls them (R/margLogLik2.R:42-65), against NumPy."""
+    from oracle import np_twin
+    c = make_multistate_cohort(n=300)
+    D, ini, pr = c["Data"], c["inits"], c["priors"]
+    b = np.asarray(ini["b"])
+    Wl = oracle.wlong(D, c["Covs"]["b"], False, b, 0, multiState=True)
+    Wls = oracle.wlong(D, c["Covs"]["b"], False, b, 1, multiState=True)
+    Bs, g, a = (np.asarray(ini[k], dtype=float) for k in ("Bs_gammas", "gammas", "alphas"))
+    tau, temp = 3.5, 0.7
+    want = np_twin.logPosterior(temp, D, Wl, Wls, Bs, g, a, pr, tau)
+    ev = np.asarray(D["event"])
+    W = np.hstack([np.asarray(D["W1s"]), np.asarray(D["W2s"]), Wls])
+    Int = np.asarray(D["Pw"]) * np.exp(W @ np.concatenate([Bs, g, a]))
+    ecs = ev @ np.hstack([np.asarray(D["W1"]), np.asarray(D["W2"]), Wl])
+    pen = np.concatenate([tau * (pr["Tau_Bs_gammas"] @ (Bs - pr["mean_Bs_gammas"])), pr["Tau_gammas"] @ (g - pr["mean_gammas"]),
+                          pr["Tau_alphas"] @ (a - pr["mean_alphas"])])
+    score = temp * (ecs - W.T @ Int) - pen
+    zb = Bs - pr["mean_Bs_gammas"]
+    last = tau * (-0.5 * zb @ pr["Tau_Bs_gammas"] @ zb + (pr["A_tau_Bs_gammas"] - 1.0) / tau - pr["B_tau_Bs_gammas"])
+    with cuda_lib.Fit(D, c["Covs"]["b"], False, multiState=True) as fit:
+        fit.set_wlong(Wl, Wls)
+        lp = fit.logPosterior(temp, Bs, g, a, pr, tau, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"])
+        gr = fit.gradient_logPosterior(temp, Bs, g, a, pr, tau, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"])
+    assert abs(lp - want) <= 1e-10 * abs(want)
+    assert np.allclose(gr[:-1], score, rtol=1e-9, atol=1e-9) and np.isclose(gr[-1], last, rtol=1e-10)
