@@ -32,16 +32,23 @@ def shard_bounds(n: int, world: int, rows_per_subject=None):
 def shard_cohort(c: dict, rank: int, world: int) -> dict:
     """Slice a cohort dict (``cohorts.make_cohort``) to the subjects of ``rank``."""
     D = c["Data"]
-    n = int(np.asarray(D["event"]).shape[0])
-    K = int(np.asarray(D["Pw"]).shape[0]) // n
+    ms = bool(c.get("multiState", False))
+    # rows of the survival part: one per subject, or the transition rows of a multi-state fit (grouped by subject,
+    # Data$idT2); a shard takes all the transition rows of its subjects
+    idT = np.asarray(D["idT2"][0]) if ms else None
+    n = int(np.asarray(c["inits"]["b"]).shape[0]) if ms else int(np.asarray(D["event"]).shape[0])
+    nT = int(np.asarray(D["event"]).shape[0])
+    K = int(np.asarray(D["Pw"]).shape[0]) // nT
     O = len(D["y"])
     counts = np.zeros(n)
     for k in range(O):
         counts += np.bincount(np.asarray(D["idL"][k]), minlength=n)
-    b = shard_bounds(n, world, counts + K)
+    ntr = np.bincount(idT, minlength=n) if ms else np.ones(n, dtype=np.int64)
+    b = shard_bounds(n, world, counts + K * ntr)
     lo, hi = int(b[rank]), int(b[rank + 1])
     m = hi - lo
-    qs = slice(lo * K, hi * K)
+    t0, t1 = (int(np.searchsorted(idT, lo, "left")), int(np.searchsorted(idT, hi, "left"))) if ms else (lo, hi)
+    qs = slice(t0 * K, t1 * K)
 
     def rows(a, sl):
         a = np.asarray(a)
@@ -58,8 +65,8 @@ def shard_cohort(c: dict, rank: int, world: int) -> dict:
         idLs.append((idL[r0:r1] - lo).astype(np.int32))
         idL2s.append((np.asarray(D["idL2"][k])[lo:hi] - r0).astype(np.int32))
     out.update(y=ys, Xbetas=Xb, Z=Zs, idL=idLs, idL2=idL2s)
-    sub = slice(lo, hi)
-    for key in ("event", "W1", "W2", "Time"):
+    sub = slice(t0, t1)
+    for key in ("event", "W1", "W2", "Time", "strata", "TimeL"):
         if key in D:
             out[key] = rows(D[key], sub)
     for key in ("W1s", "W2s", "Pw"):
@@ -73,8 +80,14 @@ def shard_cohort(c: dict, rank: int, world: int) -> dict:
             out[key] = rows(D[key], qs)
         for key in ("XXsbetas_int", "ZZs_int", "Us_int"):
             out[key] = [rows(x, qs) for x in D[key]]
-    out["idGK_fast"] = (np.arange(1, m + 1) * K - 1).astype(np.int32)
+    out["idGK_fast"] = (np.arange(1, (t1 - t0) + 1) * K - 1).astype(np.int32)
     out["idT_rsum"] = np.arange(m, dtype=np.int32)
+    if ms:
+        loc = (idT[t0:t1] - lo).astype(np.int32)
+        T = len(D["XXbetas"])
+        out["idT"] = out["idT2"] = [loc for _ in range(T)]
+        out["idTs"] = out["idT2s"] = [np.repeat(loc, K) for _ in range(T)]
+        out["idT_rsum"] = np.flatnonzero(np.r_[loc[1:] != loc[:-1], True]).astype(np.int32)
     inits = dict(c["inits"]); inits["b"] = np.asfortranarray(np.asarray(c["inits"]["b"])[lo:hi])
     scales = dict(c["scales"]); scales["b"] = np.asarray(c["scales"]["b"])[lo:hi].copy()
     Covs = dict(c["Covs"]); Covs["b"] = np.asfortranarray(np.asarray(c["Covs"]["b"])[:, :, lo:hi])

@@ -28,11 +28,12 @@ def _worker(rank, world, port, cfg, n, ret):
     os.environ["MASTER_PORT"] = str(port)
     import torch
     import torch.distributed as dist
-    from jmbayes_b200.cohorts import make_cohort
+    from jmbayes_b200.cohorts import make_cohort, make_multistate_cohort
     from jmbayes_b200.sharding import shard_cohort
     from oracle import oracle
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    c = make_cohort(cfg, n=n)
+    c = make_multistate_cohort(n=n) if cfg == "multistate" else make_cohort(cfg, n=n)
+    ms = bool(c["multiState"])
     ctl = dict(c["control"]); ctl.update(n_burnin=15, n_iter=10, n_block=5, n_thin=5)
     sh = shard_cohort(c, rank, world)
 
@@ -42,19 +43,20 @@ def _worker(rank, world, port, cfg, n, ret):
         buf[:] = t.numpy()
 
     oracle.set_rowsum_mode(1)
-    r = oracle.lap_rwm_C(sh["inits"], sh["Data"], sh["priors"], sh["scales"], sh["Covs"], ctl, c["interval_cens"],
+    r = oracle.lap_rwm_C(sh["inits"], sh["Data"], sh["priors"], sh["scales"], sh["Covs"], ctl, c["interval_cens"], ms,
                          subject_offset=sh["subject_offset"], allreduce=allreduce)
     # gather the shards' b draws on rank 0
     parts = [None] * world
     dist.all_gather_object(parts, (sh["subject_offset"], r["mcmc"]["b"], r["scales"]["sigma"]["b"]))
     if rank == 0:
-        full = oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"])
+        full = oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"], ms)
         b = np.concatenate([p[1] for p in sorted(parts, key=lambda x: x[0])], axis=0)
         sg = np.concatenate([p[2] for p in sorted(parts, key=lambda x: x[0])])
         ok = (np.allclose(b, full["mcmc"]["b"], rtol=1e-9, atol=1e-12)
               and np.allclose(sg, full["scales"]["sigma"]["b"], rtol=1e-10)
               and np.allclose(r["mcmc"]["alphas"], full["mcmc"]["alphas"], rtol=1e-9)
               and np.allclose(r["mcmc"]["Bs_gammas"], full["mcmc"]["Bs_gammas"], rtol=1e-9, atol=1e-12)
+              and np.allclose(r["mcmc"]["tau_Bs_gammas"], full["mcmc"]["tau_Bs_gammas"], rtol=1e-9)
               and np.allclose(r["logWeights"], full["logWeights"], rtol=1e-11)
               and np.allclose(r["extras"]["trace_surv"], full["extras"]["trace_surv"], rtol=1e-11))
         ret.put(bool(ok))
@@ -62,7 +64,7 @@ def _worker(rank, world, port, cfg, n, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cfg", ["config3", "config4"])
+@pytest.mark.parametrize("cfg", ["config3", "config4", "multistate"])
 def test_two_rank_sharded_chain_equals_single_process(cfg):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
