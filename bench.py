@@ -4,7 +4,7 @@
 One "step" = one MCMC iteration over the whole cohort (every subject's b_i update, the
 survival-block step, the Gibbs draws and the adaptation): n subject-iterations.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config4_shard|config3|config2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config4_shard|config3|config2|config5|summaries|multistate]
   python bench.py --impl reference ...      # restated reference CPU path on the host cores
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
@@ -40,6 +40,8 @@ WORKLOADS = {
     # posterior summaries of the random effects of the config-4 shard: 125 000 subjects x q = 6 series of
     # M = 500 kept draws, the ten statistics of mvJointModelBayes()$statistics per series; one "step" = all series
     "summaries": ("config4", 125000),
+    # multi-state fit (multiState = TRUE): illness-death cohort, 2-3 transition rows per subject, 3 strata
+    "multistate": ("multistate", 50000),
 }
 STATS_M, STATS_Q = 500, 6
 STATS_METRIC = "series/sec of mvJointModelBayes posterior summaries (ten statistics per series of M=500 kept draws)"
@@ -117,8 +119,9 @@ def _ref_kind():
 
 def _cpu_worker(args):
     cfg, n, iters, chain_id, kind = args
-    from jmbayes_b200.cohorts import make_cohort
-    c = make_cohort(cfg, n=n)
+    from jmbayes_b200.cohorts import make_cohort, make_multistate_cohort
+    c = make_multistate_cohort(n=n) if cfg == "multistate" else make_cohort(cfg, n=n)
+    ms = bool(c.get("multiState", False))
     ctl = dict(c["control"])
     if kind == "reference":
         from oracle import ref
@@ -127,12 +130,12 @@ def _cpu_worker(args):
         ctl.update(n_burnin=iters - nb, n_iter=nb, n_thin=nb)
         ref.lib()
         t0 = time.perf_counter()
-        ref.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"], chain_id=chain_id)
+        ref.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"], ms, chain_id=chain_id)
         return time.perf_counter() - t0, iters
     from oracle import oracle
     oracle.set_rowsum_mode(0)        # the reference's own cumsum-difference rowsum
     t0 = time.perf_counter()
-    oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"],
+    oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"], ms,
                      chain_id=chain_id, max_iters=iters)
     return time.perf_counter() - t0, iters
 
@@ -359,6 +362,132 @@ def run_cuda(args):
                                 "sample": f"{iters} iterations x {CPU_SAMPLE_N} subjects of {cfg}, single thread ({dt:.1f} s); "
                                           + ("the reference's own lap_rwm_C source compiled against the stand-in Armadillo/Rcpp header"
                                              if kind == "reference" else "restated lap_rwm_C (C port)")}
+    fit.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-state fits (multiState = TRUE): same metric, generic step kernel with one hazard-row block per
+# transition row.  Every rank generates its own illness-death cohort (weak scaling; the per-iteration sums are still
+# all-reduced).  The algorithmic bytes are the record layout's (jmb_layout_info): SURVEY 8(d) gives no figure for this shape.
+# ------------------------------------------------------------------------------------------------
+def run_multistate(args):
+    import torch
+    import torch.distributed as dist
+    from jmbayes_b200 import api, build
+    from jmbayes_b200.cohorts import make_multistate_cohort
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not os.path.exists(build.LIB):
+        raise RuntimeError("libjmb200.so missing: run __graft_entry__.build()")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the hot path has no CPU fallback")
+    n = args.n_per_gpu or WORKLOADS["multistate"][1]
+    n_total = n * world
+    c = make_multistate_cohort(n=n, seed=3000 + rank)
+    Data = c["Data"]
+    fit = api.Fit(Data, c["Covs"]["b"], False, multiState=True, device=local, subject_offset=rank * n)
+    if world > 1:
+        api.connect_ranks(fit, world, rank, dist)
+    info = fit.layout_info()
+    ctl = dict(c["control"])
+    ctl.update(n_burnin=max((args.warmup + args.steps) * 2, 100), n_iter=50, n_thin=50)
+    fit.set_draw(Data)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    fit.chain_iterate(args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = fit.launch_count()
+    ms, _ = fit.chain_iterate(args.steps)
+    l1 = fit.launch_count()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    fit.chain_end(fetch=False)
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = n_total * args.steps / (ms_max * 1e-3)
+
+    fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    fit.chain_iterate(args.warmup)
+    ksteps = min(args.steps, 100)
+    _, kms = fit.chain_iterate(ksteps, time_kernels=True)
+    fit.chain_end(fetch=False)
+    k_ms = kms / ksteps
+
+    # end to end with host buffers: per-draw vectors (jmb_set_draw), chain_begin, K iterations, chain_end
+    ctl_e = dict(c["control"])
+    ctl_e.update(n_burnin=max(args.steps - 50, 0), n_iter=min(50, args.steps), n_thin=min(50, args.steps), n_block=min(50, max(1, args.steps)))
+    e2e_total = -(-(ctl_e["n_burnin"] + ctl_e["n_iter"]) // ctl_e["n_block"]) * ctl_e["n_block"]
+    barrier()
+    t0 = time.perf_counter()
+    fit.set_draw(Data)
+    fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl_e)
+    fit.chain_iterate(e2e_total)
+    res = fit.chain_end()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * e2e_total / float(te.item())
+    h2d = (sum(np.asarray(x).nbytes for key in ("Xbetas", "XXbetas", "XXsbetas") for x in Data[key])
+           + 8 * (fit.q * fit.q + fit.O) + 8 * n * (fit.q + 1))
+    d2h = sum(v.nbytes for v in res["mcmc"].values()) + res["scales"]["sigma"]["b"].nbytes + 8 * n + 16 * e2e_total
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"]
+    achieved = alg * n / (k_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "multistate", "cohort": "illness-death, 2 outcomes (gaussian + binomial), q = 4, 3 strata x 7 B-spline coefficients",
+                   "subjects_per_gpu": n, "subjects_total": n_total, "transition_rows_per_gpu": int(fit.nT), "outcomes": fit.O, "q": fit.q,
+                   "terms": fit.T, "K": fit.K, "multiState": True, "parallelism": f"subject-shards x{world}", "chains_per_launch": 1,
+                   "l2": "per-iteration working set %.2f GB per GPU (inputs larger than the 126 MB L2)" % (alg * n / 1e9)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": info["kernel"] + ":multistate", "kernel_ms": k_ms, "alg_bytes_per_subject_iteration": alg,
+                     "alg_source": "record layout (jmb_layout_info): design + per-draw records, state read/write, b-step draws",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_total, "d2h_bytes_per_step": d2h / e2e_total,
+                "what": f"jmb_set_draw + lap_rwm_C({e2e_total} iterations, multiState = TRUE) through the C ABI with host buffers, wall clock"},
+        "gpu_launches": int(l1 - l0),
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        kind = _ref_kind()
+        t_probe, it_probe = _cpu_worker(("multistate", CPU_SAMPLE_N, 50, 0, kind))
+        iters = max(50, int(12.0 / max(t_probe / it_probe, 1e-4)))
+        val, dt, iters = cpu_reference("multistate", CPU_SAMPLE_N, iters, 1, kind)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
+                                "sample": f"{iters} iterations x {CPU_SAMPLE_N} subjects of the multi-state cohort, single thread ({dt:.1f} s)"}
     fit.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -649,6 +778,8 @@ def main():
         return run_config5_reference(args) if args.impl == "reference" else run_config5(args)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "multistate":
+        run_multistate(args)
     else:
         run_cuda(args)
 
