@@ -16,8 +16,9 @@ UNITS = {
     "jmb_survfit.cu": ["jmb_survfit.cuh", "jmb_device.cuh", "jmb_model.h", "jmb_host.h"],
     "jmb_laplace.cu": ["jmb_host.h"],
     "jmb_summaries.cu": ["jmb_host.h"],
+    "jmb_accuracy.cu": ["jmb_host.h"],
 }
-HEADERS = [os.path.join(ROOT, "include", f) for f in ("jmb200.h", "jmb200_survfit.h", "jmb200_summaries.h")]
+HEADERS = [os.path.join(ROOT, "include", f) for f in ("jmb200.h", "jmb200_survfit.h", "jmb200_summaries.h", "jmb200_accuracy.h")]
 SOURCES = [os.path.join(CSRC, f) for f in UNITS]
 
 

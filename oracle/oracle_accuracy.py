@@ -1,0 +1,44 @@
+"""NumPy restatement of the pair loop of aucJM.mvJMbayes and of the sum of prederrJM.mvJMbayes.  TEST INFRASTRUCTURE ONLY
+(see oracle/jmb_oracle.h): only tests/ may import it.
+
+PARITY: unpinned - R is absent from the image and the reference ships no fixtures for these functions; the restatement
+follows R/aucJM.mvJMbayes.R:66-141 and R/prederrJM.mvJMbayes.R:104-108 line by line (combn pairs, the four indicator
+vectors, the in-place weighting, sum(, na.rm = TRUE)) and is cross-checked against an independent O(n) / sort-based
+evaluation of the same sums (tests/test_accuracy_cpu.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def aucJM_pairs(Time, event, Thoriz, pi_u_t, pi2, pi3):
+    """R/aucJM.mvJMbayes.R:66-141 on per-subject vectors (subjects in newdata2 order).  pi2[i] = 1 - S_i(Thoriz | T_i) (:98,
+    :138), pi3[j] = S_j(Thoriz | T_j) (:114,:139); returns (auc, numerator, denominator)."""
+    Time, event, pi, pi2, pi3 = (np.asarray(x, dtype=np.float64) for x in (Time, event, pi_u_t, pi2, pi3))
+    n = Time.size
+    if n < 2:
+        return float("nan"), 0.0, 0.0                              # :142-144
+    i, j = np.triu_indices(n, k=1)                                 # combn(ids, 2): first member before second (:67)
+    Ti, Tj, di, dj = Time[i], Time[j], event[i], event[j]
+    ev_i, ce_i, ce_j = (di == 1) | (di == 3), (di == 0) | (di == 2), (dj == 0) | (dj == 2)
+    ind1 = (Ti <= Thoriz) & ev_i & (Tj > Thoriz)                   # :74
+    ind2 = (Ti <= Thoriz) & ce_i & (Tj > Thoriz)                   # :75
+    ind3 = (Ti <= Thoriz) & ev_i & (Tj <= Thoriz) & ce_j           # :76
+    ind4 = (Ti <= Thoriz) & ce_i & (Tj <= Thoriz) & ce_j           # :77
+    ind = (ind1 | ind2 | ind3 | ind4).astype(np.float64)           # :79
+    ind[ind2] = ind[ind2] * pi2[i[ind2]]                           # :98-99
+    ind[ind3] = ind[ind3] * pi3[j[ind3]]                           # :114-115
+    ind[ind4] = ind[ind4] * pi2[i[ind4]] * pi3[j[ind4]]            # :138-140
+    with np.errstate(invalid="ignore"):
+        less = np.where(np.isnan(pi[i]) | np.isnan(pi[j]), np.nan, (pi[i] < pi[j]).astype(np.float64))
+        num = np.nansum(less * ind)                                # :141, sum(, na.rm = TRUE)
+    den = np.nansum(ind)
+    return (num / den if den != 0 else float("nan")), float(num), float(den)
+
+
+def prederrJM_sum(S_alive, S_dead, S_cens, w_cens, nr, lossFun="square"):
+    """R/prederrJM.mvJMbayes.R:12-16,104-108."""
+    L = np.abs if lossFun == "absolute" else np.square
+    a, d, c, w = (np.asarray(x, dtype=np.float64).ravel() for x in (S_alive, S_dead, S_cens, w_cens))
+    terms = np.concatenate([L(1 - a), L(0 - d), w * L(1 - c) + (1 - w) * L(0 - c)])
+    return float(np.nansum(terms) / nr)
