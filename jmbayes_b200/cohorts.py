@@ -523,6 +523,9 @@ def make_multistate_cohort(n: int = 300, seed: int = 20253, K: int = 15, mean_vi
         idT=[idT for _ in range(O)], idTs=[idTs for _ in range(O)], idT2=[idT for _ in range(O)], idT2s=[idTs for _ in range(O)],
         Pw=Pw, nRisks=nR, kn_strat_first=kn_first, kn_strat_last=kn_last, outcome=np.array([0, 1], dtype=np.int32), st=st_vec,
         strata=trans.astype(np.int32), TimeL=TimeL,
+        # designs behind XXbetas / XXsbetas = Xbetas_calc(XX, betas, indFixed, outcome) (R/supportFuns_mvJointModelBayes.R:43-55)
+        XX=[_F(zfun(TimeR)) for _ in range(O)], XXs=[_F(zfun(st_vec)) for _ in range(O)], XXs_int=[],
+        indFixed=[np.array([0, 1], dtype=np.int32) for _ in range(O)], betas=[np.asarray(bk, dtype=np.float64) for bk in betas_draw],
         Levent1=e0, Levent01=e0, Levent2=e0, Levent3=e0, W1s_int=np.zeros((0, 0), order="F"), W2s_int=np.zeros((0, 0), order="F"),
         Us_int=[np.zeros((0, 0), order="F")], XXsbetas_int=[np.zeros(0)], ZZs_int=[np.zeros((0, 0), order="F")], Pw_int=np.zeros(0))
     priors = dict(

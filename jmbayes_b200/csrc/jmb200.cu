@@ -710,7 +710,6 @@ extern "C" int jmb_set_draw(jmb_handle h, const jmb_draw* w) {
 extern "C" int jmb_set_xdesigns(jmb_handle h, const jmb_xdesigns* x) {
     if (!h || !x || !x->p_k || !x->X || !x->outcome || !x->f_t || !x->indFixed || !x->XX || !x->XXs)
         return fail("jmb_set_xdesigns: null argument");
-    if (h->ms) return fail("jmb_set_xdesigns: not available for multi-state fits yet (pass the per-draw vectors with jmb_set_draw)");
     const ModelMeta& mm = h->mm;
     const int n = h->n, K = mm.d.K, RP = mm.L.RP, S = mm.d.S, T = mm.d.T, O = mm.d.O;
     if (S == 2 && !x->XXs_int) return fail("jmb_set_xdesigns: XXs_int required with interval censoring");
@@ -733,10 +732,10 @@ extern "C" int jmb_set_xdesigns(jmb_handle h, const jmb_xdesigns* x) {
             if (xd.indf[t][f] < 0 || xd.indf[t][f] >= xd.pk[x->outcome[t]]) return fail("jmb_set_xdesigns: indFixed out of range");
         }
     }
-    const long long ns = (long long)n * K;
+    const long long nT = h->ms ? h->nT : n, ns = nT * K;     // rows of XX / XXs (transition rows of a multi-state fit)
     std::vector<long long> xoff(n + 1, 0);
     for (int i = 0; i < n; ++i) {
-        long long len = (long long)tb * RP;
+        long long len = (long long)tb * RP * (h->trow[i + 1] - h->trow[i]);
         for (int k = 0; k < O; ++k) len += (long long)(h->rowptr[k][i + 1] - h->rowptr[k][i]) * xd.pk[k];
         xoff[i + 1] = xoff[i] + len;
     }
@@ -744,14 +743,18 @@ extern "C" int jmb_set_xdesigns(jmb_handle h, const jmb_xdesigns* x) {
     parallel_for(n, [&](int lo, int hi) {
         for (int i = lo; i < hi; ++i) {
             double* xr = xrec.data() + xoff[i];
-            for (int t = 0; t < T; ++t)
-                for (int f = 0; f < xd.ft[t]; ++f) {
-                    double* col = xr + (size_t)(xd.tbase[t] + f) * RP;
-                    col[0] = x->XX[t][i + (long long)f * n];
-                    for (int r = 1; r <= K; ++r) col[r] = x->XXs[t][(long long)i * K + r - 1 + (long long)f * ns];
-                    if (S == 2) for (int r = 1; r <= K; ++r) col[K + r] = x->XXs_int[t][(long long)i * K + r - 1 + (long long)f * ns];
-                }
-            double* l = xr + (size_t)tb * RP;
+            const int ntr = h->trow[i + 1] - h->trow[i];
+            for (int blk = 0; blk < ntr; ++blk) {           // one block of term columns per transition row
+                const long long ti = h->trow[i] + blk;
+                for (int t = 0; t < T; ++t)
+                    for (int f = 0; f < xd.ft[t]; ++f) {
+                        double* col = xr + ((size_t)blk * tb + xd.tbase[t] + f) * RP;
+                        col[0] = x->XX[t][ti + (long long)f * nT];
+                        for (int r = 1; r <= K; ++r) col[r] = x->XXs[t][ti * K + r - 1 + (long long)f * ns];
+                        if (S == 2) for (int r = 1; r <= K; ++r) col[K + r] = x->XXs_int[t][ti * K + r - 1 + (long long)f * ns];
+                    }
+            }
+            double* l = xr + (size_t)tb * RP * ntr;
             for (int k = 0; k < O; ++k) {
                 const int r0 = h->rowptr[k][i], v = h->rowptr[k][i + 1] - r0;
                 const long long Nk = h->N[k];
@@ -788,7 +791,8 @@ extern "C" int jmb_set_draw_betas(jmb_handle h, const double* const* betas, cons
     double* d_b = h->d_betas + (size_t)c->slot_index * std::max(h->n_betas, 1);
     CU(cudaMemcpyAsync(d_b, hb, sizeof(double) * h->n_betas, cudaMemcpyHostToDevice, c->stream));
     const unsigned grid = (unsigned)(((long long)n * 32 + 255) / 256);
-    jmb_xbetas_kernel<<<grid, 256, 0, c->stream>>>(h->xd, h->d_xrec, h->d_xoff, h->d_coff, h->d_rowptr, d_b, n, c->d_crec);
+    jmb_xbetas_kernel<<<grid, 256, 0, c->stream>>>(h->xd, h->d_xrec, h->d_xoff, h->d_coff, h->d_rowptr, d_b, n, c->d_crec,
+                                                   h->ms ? h->d_trow : nullptr);
     h->launches += 1;
     CU(cudaGetLastError());
     for (int j = 0; j < mm.d.q * mm.d.q; ++j) c->h_par[h->pl.invD + j] = invD[j];

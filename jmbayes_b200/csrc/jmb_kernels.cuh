@@ -855,10 +855,11 @@ struct XbDesc {
     int indf[kMaxT][JMB_MAX_RT];
     int pk[kMaxO], boff[kMaxO];
 };
+// trow != nullptr (multi-state fits): the term part of both records is repeated once per transition row of the subject.
 __global__ void jmb_xbetas_kernel(const __grid_constant__ XbDesc xd, const double* __restrict__ xrec,
                                   const long long* __restrict__ xoff, const long long* __restrict__ coff,
                                   const int* __restrict__ rowptr, const double* __restrict__ betas, const int n,
-                                  double* __restrict__ crec) {
+                                  double* __restrict__ crec, const int* __restrict__ trow) {
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= n) return;
@@ -866,14 +867,18 @@ __global__ void jmb_xbetas_kernel(const __grid_constant__ XbDesc xd, const doubl
     const double* __restrict__ xr = xrec + xoff[i];
     double* __restrict__ cr = crec + coff[i];
     const int RP = xd.RP, nt = xd.T * RP;
-    for (int e = lane; e < nt; e += 32) {
-        const int t = e / RP, r = e - t * RP;
+    const int ntr = trow ? trow[i + 1] - trow[i] : 1;
+    int xcols = 0;
+    for (int t = 0; t < xd.T; ++t) xcols += xd.ft[t];
+    for (int e = lane; e < nt * ntr; e += 32) {
+        const int tb = e / nt, et = e - tb * nt;
+        const int t = et / RP, r = et - t * RP;
+        const double* __restrict__ xb = xr + (long long)tb * xcols * RP;
         double acc = 0.0;
-        for (int f = 0; f < xd.ft[t]; ++f) acc += xr[(xd.tbase[t] + f) * RP + r] * betas[xd.tboff[t] + xd.indf[t][f]];
+        for (int f = 0; f < xd.ft[t]; ++f) acc += xb[(xd.tbase[t] + f) * RP + r] * betas[xd.tboff[t] + xd.indf[t][f]];
         cr[e] = acc;
     }
-    int xo = 0, co = nt;
-    for (int t = 0; t < xd.T; ++t) xo += xd.ft[t] * RP;
+    int xo = xcols * RP * ntr, co = nt * ntr;
     for (int k = 0; k < xd.O; ++k) {
         const int v = rowptr[(long long)k * (n + 1) + i + 1] - rowptr[(long long)k * (n + 1) + i];
         for (int r = lane; r < v; r += 32) {

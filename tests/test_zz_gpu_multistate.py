@@ -108,8 +108,26 @@ def test_multistate_limits_are_loud(cuda_lib):
     with cuda_lib.Fit(c["Data"], c["Covs"]["b"], False, multiState=True) as fit:
         with pytest.raises(cuda_lib.JmbError):        # Wlong has one row per transition
             fit.set_wlong(np.zeros((fit.n, fit.A)), np.zeros((fit.n * fit.K, fit.A)))
-        with pytest.raises(cuda_lib.JmbError):        # Xbetas_calc on the device: not for multi-state fits yet
-            fit.set_xdesigns(c["Data"])
+
+
+def test_device_xbetas_calc_multistate(cuda_lib):
+    """jmb_set_xdesigns + jmb_set_draw_betas (Xbetas_calc on the device, R/supportFuns_mvJointModelBayes.R:43-55) fill the
+    same per-draw records as the host vectors of jmb_set_draw, one block of term rows per transition row."""
+    c = make_multistate_cohort(n=300)
+    D, ini = c["Data"], c["inits"]
+    ctl = dict(c["control"]); ctl.update(n_burnin=20, n_iter=20, n_block=10, n_thin=10)
+    with cuda_lib.Fit(D, c["Covs"]["b"], False, multiState=True) as fit:
+        fit.set_draw(D)
+        e0 = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+        r0 = fit.lap_rwm_C(ini, c["priors"], c["scales"], c["Covs"], ctl)
+    with cuda_lib.Fit(D, c["Covs"]["b"], False, multiState=True) as fit:
+        fit.set_xdesigns(D)
+        fit.set_draw_betas(D["betas"], D["sigmas"], D["invD"])
+        e1 = fit.eval_logpost_re(ini["b"], ini["Bs_gammas"], ini["gammas"], ini["alphas"])
+        r1 = fit.lap_rwm_C(ini, c["priors"], c["scales"], c["Covs"], ctl)
+    for k in ("log_pyb", "log_h", "H", "log_ptb"):
+        assert _rel(e1[k], e0[k]) <= 1e-12, k
+    assert _rel(r1["extras"]["trace_surv"], r0["extras"]["trace_surv"]) <= 1e-9
 
 
 def test_laplace_step_multistate(cuda_lib, oracle):
