@@ -1,0 +1,154 @@
+// cuda_runtime.h - stand-in for the CUDA runtime that executes the library's own kernels on CPU threads.
+//
+// TEST INFRASTRUCTURE ONLY (oracle/emu): libjmb200_emu.so is the product's jmb200.cu / jmb_kernels.cuh / jmb_device.cuh,
+// passed through the textual substitutions of make_emu.py (kernel<<<...>>>(...) launches, __shared__ -> static, the two PDL
+// asm statements) and compiled by g++ against this header, in the same way oracle/_ref compiles the reference's sources
+// against a stand-in Armadillo/Rcpp header.  It lets the CPU test suite run the generic step kernel, the finalize
+// kernel, the survival-posterior kernel and the Xbetas kernel - the code a B200 runs - on small cohorts when no GPU is
+// available.  Nothing in the product loads it; it is not a fallback and is never timed.
+//
+// Execution model: a launch runs its CTAs one after the other; the threads of a CTA are OS threads that really run
+// concurrently, __syncthreads() / __syncwarp(mask) / __shfl_*_sync(mask, ...) are barriers over exactly the threads they
+// name, so divergence between the half-warp groups of the step kernel behaves as on the device.  Streams are synchronous.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __grid_constant__
+#define __launch_bounds__(...)
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorEmu = 1 };
+struct emuStream { int dummy; };
+struct emuEvent { std::chrono::steady_clock::time_point t; };
+typedef emuStream* cudaStream_t;
+typedef emuEvent* cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1, cudaIpcMemLazyEnablePeerAccess = 1 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+struct cudaDeviceProp { int multiProcessorCount; };
+enum cudaLaunchAttributeID { cudaLaunchAttributeProgrammaticStreamSerialization = 6 };
+struct cudaLaunchAttribute { cudaLaunchAttributeID id; struct { int programmaticStreamSerializationAllowed; } val; };
+struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes = 0; cudaStream_t stream = nullptr; cudaLaunchAttribute* attrs = nullptr; unsigned numAttrs = 0; };
+
+namespace emu {
+struct Barrier {
+    std::mutex m; std::condition_variable cv; int count = 0; unsigned long long gen = 0;
+    void wait(int n) {
+        std::unique_lock<std::mutex> l(m);
+        const unsigned long long g = gen;
+        if (++count == n) { count = 0; ++gen; cv.notify_all(); }
+        else cv.wait(l, [&] { return g != gen; });
+    }
+};
+struct Cta {
+    Barrier all;
+    Barrier warp[32][3];                 // [warp][full, low half, high half]
+    unsigned long long slot[32][32];     // shuffle exchange
+};
+extern Cta g_cta;
+extern thread_local unsigned t_tid;
+inline int mask_class(unsigned mask) {
+    if (mask == 0xFFFFFFFFu) return 0;
+    if (mask == 0x0000FFFFu) return 1;
+    if (mask == 0xFFFF0000u) return 2;
+    std::fprintf(stderr, "emu: unsupported warp mask %08x\n", mask); std::abort();
+}
+inline void warp_barrier(unsigned mask) { g_cta.warp[t_tid >> 5][mask_class(mask)].wait(__builtin_popcount(mask)); }
+template <class T> inline T shfl(unsigned mask, T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle of more than 8 bytes");
+    const unsigned w = t_tid >> 5, lane = t_tid & 31;
+    unsigned long long raw = 0; std::memcpy(&raw, &v, sizeof(T));
+    g_cta.slot[w][lane] = raw;
+    warp_barrier(mask);
+    const unsigned long long got = g_cta.slot[w][src_lane & 31];
+    warp_barrier(mask);
+    T r; std::memcpy(&r, &got, sizeof(T));
+    return r;
+}
+void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, const std::function<void()>& fn);
+}  // namespace emu
+
+extern thread_local uint3 threadIdx;
+extern uint3 blockIdx;
+extern dim3 blockDim, gridDim;
+
+inline void __syncthreads() { emu::g_cta.all.wait((int)(blockDim.x * blockDim.y * blockDim.z)); }
+inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { emu::warp_barrier(mask); }
+inline void __threadfence_system() {}
+template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int off, int width = 32) { (void)width; return emu::shfl(mask, v, (int)(emu::t_tid & 31) ^ off); }
+template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+    const int lane = (int)(emu::t_tid & 31);
+    return emu::shfl(mask, v, (lane & ~(width - 1)) | (src & (width - 1)));
+}
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+inline void sincospi(double x, double* s, double* c) {      // exact reduction to a multiple of 1/2, then sin / cos of pi r
+    const double q = std::rint(2.0 * x), r = x - 0.5 * q;
+    const double sr = std::sin(M_PI * r), cr = std::cos(M_PI * r);
+    switch (((long long)q) & 3) {
+        case 0: *s = sr; *c = cr; break;
+        case 1: *s = cr; *c = -sr; break;
+        case 2: *s = -sr; *c = -cr; break;
+        default: *s = -cr; *c = sr; break;
+    }
+}
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+
+// ---- runtime -----------------------------------------------------------------------------------------------------------
+inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA runtime: unsupported call"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* c) { *c = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 4; return cudaSuccess; }
+inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = (size_t)1 << 30; *t = (size_t)2 << 30; return cudaSuccess; }
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes) { *p = (T*)std::malloc(bytes ? bytes : 8); return *p ? cudaSuccess : cudaErrorEmu; }
+template <class T> inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned) { *p = (T*)std::malloc(bytes ? bytes : 8); return *p ? cudaSuccess : cudaErrorEmu; }
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new emuStream(); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent(); return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
+inline cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorEmu; }
+inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorEmu; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorEmu; }
+template <typename... KA, typename... A>
+inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* c, void (*k)(KA...), A... a) {
+    emu::launch(c->gridDim, c->blockDim, c->dynamicSmemBytes, c->stream, [&] { k(a...); });
+    return cudaSuccess;
+}
