@@ -2,7 +2,8 @@
 size-independent properties at full size.  Sums of doubles in a different (fixed) order: 1e-11 relative.
 
 STATUS: written after round 1's GPU minutes were spent; compiled for sm_100a but not yet run on a B200, hence
-xfail(strict=False) (XPASS when right).  Remove the marker after the first green run."""
+xfail(strict=False) (XPASS when right).  The same kernels pass on CPU threads
+(tests/test_emulated_kernels_cpu.py).  Remove the marker after the first green run."""
 import numpy as np
 import pytest
 

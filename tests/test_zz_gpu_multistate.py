@@ -6,7 +6,8 @@ STATUS: this path (jmb_step_kernel<G, true>, the per-stratum tau_Bs_gammas draws
 several transition rows per subject) was written after round 1's GPU minutes were spent: it is compiled for sm_100a and
 checked on the CPU side (tests/test_multistate_cpu.py), but had not been run on a B200 when it was committed.  The
 tests are therefore marked xfail(strict=False): they report XPASS when the path is right and cannot hide a regression
-of anything else (this file sorts last).  Remove the marker after the first green run.
+of anything else (this file sorts last).  The same kernels pass on CPU threads
+(tests/test_emulated_kernels_cpu.py).  Remove the marker after the first green run.
 """
 import importlib.util
 import os
