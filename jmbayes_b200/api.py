@@ -35,7 +35,12 @@ def lib():
     if not os.path.exists(path):
         raise JmbError(f"{path} is missing: build it with __graft_entry__.build() "
                        "(nvcc, sm_100a); there is no CPU fallback")
-    L = C.CDLL(path)
+    _lib_cache = _bind(C.CDLL(path))
+    return _lib_cache
+
+
+def _bind(L):
+    """Declare the argument types of the C ABI on a loaded library."""
     L.jmb_last_error.restype = C.c_char_p
     L.jmb_stream.restype = C.c_void_p
     L.jmb_kernel_name.restype = C.c_char_p
@@ -78,7 +83,6 @@ def lib():
     L.jmb_p2p_export.argtypes = [vp, C.c_int, C.c_char_p]
     L.jmb_p2p_attach.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.jmb_device_count.argtypes = [C.POINTER(C.c_int)]
-    _lib_cache = L
     return L
 
 

@@ -28,17 +28,16 @@ def emu(oracle):
     make_emu = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(make_emu)
     lib = make_emu.build()
-    saved = (api._lib_cache, os.environ.get("JMB_LIB"), os.environ.get("JMB_KERNEL"))
-    os.environ["JMB_LIB"], os.environ["JMB_KERNEL"] = lib, "generic"
-    api._lib_cache = None
-    api.lib()
+    import ctypes as C
+    saved = (api._lib_cache, os.environ.get("JMB_KERNEL"))
+    os.environ["JMB_KERNEL"] = "generic"               # the specialised / TMA kernels are sm_100a code: not emulated
+    api._lib_cache = api._bind(C.CDLL(lib))            # test-only injection: the product never loads this library
     yield api
     api._lib_cache = saved[0]
-    for key, val in (("JMB_LIB", saved[1]), ("JMB_KERNEL", saved[2])):
-        if val is None:
-            os.environ.pop(key, None)
-        else:
-            os.environ[key] = val
+    if saved[1] is None:
+        os.environ.pop("JMB_KERNEL", None)
+    else:
+        os.environ["JMB_KERNEL"] = saved[1]
 
 
 def _rel(a, b, floor=1e-12):
