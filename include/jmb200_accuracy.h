@@ -39,6 +39,15 @@ int jmb_aucJM_pairs(int device, int32_t n, const double* Time, const double* eve
 int jmb_prederrJM_sum(int device, int32_t loss, int32_t nr, int32_t n_alive, const double* S_alive, int32_t n_dead,
                       const double* S_dead, int32_t n_cens, const double* S_cens, const double* w_cens, double* out);
 
+/* rocJM.mvJMbayes (R/rocJM.mvJMbayes.R:68-95): ind_i = 1 for subjects who died before Thoriz (T_i < Thoriz, d_i in {1, 3}),
+ * pi2_i = 1 - S_i(Thoriz | T_i) for those censored before it (d_i in {0, 2}), 0 otherwise; then for every threshold
+ *     nTP[k] = sum_i (pi_i < thrs[k]) ind_i,  nFP[k] = sum_i (pi_i < thrs[k]) (1 - ind_i),  Q[k] = mean_i (pi_i < thrs[k])
+ * - the column sums of the n x 101 matrix outer(pi.u.t, thrs, "<") (:89,92,95) - and sum_ind = sum(ind) (:90-91).  No
+ * na.rm in the reference: NaN inputs propagate.  Everything after these sums (:90-105) is arithmetic on 101 numbers and
+ * stays with the caller.  nTP, nFP, Q: [n_thr]; sum_ind: [1]. */
+int jmb_rocJM_sums(int device, int32_t n, const double* Time, const double* event, double Thoriz, const double* pi_u_t,
+                   const double* pi2, int32_t n_thr, const double* thrs, double* nTP, double* nFP, double* Q, double* sum_ind);
+
 #ifdef __cplusplus
 }
 #endif

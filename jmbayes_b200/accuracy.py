@@ -21,6 +21,8 @@ def _lib():
                                       c_double_p, C.POINTER(C.c_float)]
         L.jmb_prederrJM_sum.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_int32, c_double_p, C.c_int32, c_double_p, C.c_int32,
                                         c_double_p, c_double_p, c_double_p]
+        L.jmb_rocJM_sums.argtypes = [C.c_int, C.c_int32, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p, C.c_int32,
+                                     c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]
         L._acc_bound = True
     return L
 
@@ -61,3 +63,39 @@ def prederrJM_sum(S_alive, S_dead, S_cens, w_cens, nr: int, lossFun: str = "squa
     P = lambda v: v.ctypes.data_as(c_double_p) if v.size else None  # noqa: E731
     _check(_lib().jmb_prederrJM_sum(int(device), loss, int(nr), a.size, P(a), dd.size, P(dd), cc.size, P(cc), P(w), P(out)))
     return float(out[0])
+
+
+def rocJM(Time, event, Thoriz, pi_u_t, pi2, thrs=None, device: int = 0) -> dict:
+    """The list ``rocJM.mvJMbayes`` returns (``R/rocJM.mvJMbayes.R:88-108``) from the per-subject vectors: the sums over the
+    subjects (``nTP``, ``nFP``, ``Q``, ``sum(ind)``) on the device, the arithmetic on the 101 thresholds here."""
+    T, d, p, p2 = (_vec(x) for x in (Time, event, pi_u_t, pi2))
+    thrs = np.linspace(0.0, 1.0, 101) if thrs is None else _vec(thrs)
+    n, m = T.size, thrs.size
+    nTP, nFP, Q, s = np.zeros(m), np.zeros(m), np.zeros(m), np.zeros(1)
+    P = lambda a: a.ctypes.data_as(c_double_p)  # noqa: E731
+    _check(_lib().jmb_rocJM_sums(int(device), n, P(T), P(d), float(Thoriz), P(p), P(p2), m, P(thrs), P(nTP), P(nFP), P(Q), P(s)))
+    return _roc_tail(nTP, nFP, Q, float(s[0]), n, thrs)
+
+
+def _roc_tail(nTP, nFP, Q, sum_ind, n, thrs):
+    """R/rocJM.mvJMbayes.R:90-105."""
+    with np.errstate(all="ignore"):
+        nFN = sum_ind - nTP
+        TP = nTP / sum_ind
+        nTN = (n - sum_ind) - nFP
+        FP = nFP / (n - sum_ind)
+        Qd = 1 - Q
+        k10 = (TP - Q) / Qd
+        k00 = (1 - FP - Qd) / Q
+        Pm = sum_ind / n
+        k05 = (Pm * Qd * k10 + (1 - Pm) * Q * k00) / (Pm * Qd + (1 - Pm) * Q)
+        f1 = 2 * nTP / (2 * nTP + nFN + nFP)
+        youden = TP - FP
+    return dict(TP=TP, FP=FP, nTP=nTP, nFN=nFN, nFP=nFP, nTN=nTN, qSN=k10, qSP=k00, qOverall=k05, thrs=thrs,
+                F1score=_median_at_max(thrs, f1), Youden=_median_at_max(thrs, youden))
+
+
+def _median_at_max(thrs, x):
+    """median(thrs[x == max(x)]) (R/rocJM.mvJMbayes.R:103,105); max() without na.rm is NA as soon as one element is."""
+    m = np.max(x) if not np.any(np.isnan(x)) else float("nan")
+    return float("nan") if np.isnan(m) else float(np.median(thrs[x == m]))

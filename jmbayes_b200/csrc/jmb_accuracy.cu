@@ -108,6 +108,38 @@ __global__ void prederr_terms_kernel(int loss, int n_alive, const double* __rest
     terms[i] = (t != t) ? 0.0 : t;
 }
 
+// rocJM: thread k of a CTA owns threshold k and walks the CTA's chunk of subjects (staged in shared memory) in order;
+// partials [CTA][n_thr][3] (+ the chunk's sum(ind) in slot [CTA][n_thr][0]) are combined in CTA order by colsum_kernel
+constexpr int kRocThreads = 128, kRocChunk = 1024;
+__global__ void __launch_bounds__(kRocThreads)
+roc_sums_kernel(int n, const double* __restrict__ Time, const double* __restrict__ event, double Thoriz, const double* __restrict__ pi,
+                const double* __restrict__ pi2, int n_thr, const double* __restrict__ thrs, double* __restrict__ partials) {
+    __shared__ double s_pi[kRocChunk], s_ind[kRocChunk];
+    const int base = blockIdx.x * kRocChunk, cnt = min(kRocChunk, n - base);
+    for (int e = threadIdx.x; e < cnt; e += kRocThreads) {
+        const int i = base + e;
+        const double T = Time[i], d = event[i];
+        const bool before = T < Thoriz;                                             // strict, R/rocJM.mvJMbayes.R:69,71
+        s_ind[e] = (before && (d == 1.0 || d == 3.0)) ? 1.0 : ((before && (d == 0.0 || d == 2.0)) ? pi2[i] : 0.0);
+        s_pi[e] = pi[i];
+    }
+    __syncthreads();
+    const size_t row = (size_t)blockIdx.x * (n_thr + 1) * 3;
+    for (int k = threadIdx.x; k <= n_thr; k += kRocThreads) {
+        double tp = 0.0, fp = 0.0, q = 0.0;
+        if (k < n_thr) {
+            const double th = thrs[k];
+            for (int e = 0; e < cnt; ++e) {
+                const double lt = (s_pi[e] != s_pi[e]) ? s_pi[e] : ((s_pi[e] < th) ? 1.0 : 0.0);   // NA < x is NA
+                tp += lt * s_ind[e]; fp += lt * (1.0 - s_ind[e]); q += lt;
+            }
+        } else {
+            for (int e = 0; e < cnt; ++e) tp += s_ind[e];                                        // sum(ind) of the chunk
+        }
+        partials[row + (size_t)k * 3] = tp; partials[row + (size_t)k * 3 + 1] = fp; partials[row + (size_t)k * 3 + 2] = q;
+    }
+}
+
 struct DevBuf {
     double* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -183,5 +215,28 @@ extern "C" int jmb_prederrJM_sum(int device, int32_t loss, int32_t nr, int32_t n
     double h = 0.0;
     CUA(cudaMemcpy(&h, res.p, sizeof(h), cudaMemcpyDeviceToHost));
     *out = (1.0 / nr) * h;
+    return 0;
+}
+
+extern "C" int jmb_rocJM_sums(int device, int32_t n, const double* Time, const double* event, double Thoriz, const double* pi_u_t,
+                              const double* pi2, int32_t n_thr, const double* thrs, double* nTP, double* nFP, double* Q, double* sum_ind) {
+    if (!Time || !event || !pi_u_t || !pi2 || !thrs || !nTP || !nFP || !Q || !sum_ind) return jmb_set_error("jmb_rocJM_sums: null argument");
+    if (n <= 0 || n_thr <= 0 || n_thr > 4096) return jmb_set_error("jmb_rocJM_sums: bad n / n_thr");
+    if (pick_device(device)) return 1;
+    const int ctas = (n + kRocChunk - 1) / kRocChunk, cols = (n_thr + 1) * 3;
+    DevBuf in, part, res;
+    CUA(cudaMalloc(&in.p, sizeof(double) * (4 * (size_t)n + n_thr)));
+    CUA(cudaMalloc(&part.p, sizeof(double) * (size_t)ctas * cols));
+    CUA(cudaMalloc(&res.p, sizeof(double) * cols));
+    const double* src[4] = {Time, event, pi_u_t, pi2};
+    for (int k = 0; k < 4; ++k) CUA(cudaMemcpy(in.p + (size_t)k * n, src[k], sizeof(double) * n, cudaMemcpyHostToDevice));
+    CUA(cudaMemcpy(in.p + 4 * (size_t)n, thrs, sizeof(double) * n_thr, cudaMemcpyHostToDevice));
+    roc_sums_kernel<<<ctas, kRocThreads>>>(n, in.p, in.p + n, Thoriz, in.p + 2 * (size_t)n, in.p + 3 * (size_t)n, n_thr, in.p + 4 * (size_t)n, part.p);
+    colsum_kernel<<<cols, 256>>>(part.p, ctas, cols, res.p);
+    CUA(cudaGetLastError());
+    std::vector<double> h(cols);
+    CUA(cudaMemcpy(h.data(), res.p, sizeof(double) * cols, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n_thr; ++k) { nTP[k] = h[(size_t)k * 3]; nFP[k] = h[(size_t)k * 3 + 1]; Q[k] = h[(size_t)k * 3 + 2] / n; }
+    *sum_ind = h[(size_t)n_thr * 3];
     return 0;
 }

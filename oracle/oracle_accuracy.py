@@ -42,3 +42,37 @@ def prederrJM_sum(S_alive, S_dead, S_cens, w_cens, nr, lossFun="square"):
     a, d, c, w = (np.asarray(x, dtype=np.float64).ravel() for x in (S_alive, S_dead, S_cens, w_cens))
     terms = np.concatenate([L(1 - a), L(0 - d), w * L(1 - c) + (1 - w) * L(0 - c)])
     return float(np.nansum(terms) / nr)
+
+
+def rocJM(Time, event, Thoriz, pi_u_t, pi2):
+    """R/rocJM.mvJMbayes.R:68-105 on per-subject vectors, with the n x 101 outer() matrix as there."""
+    Time, event, pi, pi2 = (np.asarray(x, dtype=np.float64) for x in (Time, event, pi_u_t, pi2))
+    ind1 = (Time < Thoriz) & ((event == 1) | (event == 3))            # :69
+    ind2 = (Time < Thoriz) & ((event == 0) | (event == 2))            # :71
+    ind = (ind1 | ind2).astype(np.float64)                            # :72
+    ind[ind2] = ind[ind2] * pi2[ind2]                                 # :84-85
+    thrs = np.linspace(0.0, 1.0, 101)                                 # :88
+    with np.errstate(all="ignore"):
+        lt = np.where(np.isnan(pi)[:, None], np.nan, (pi[:, None] < thrs[None, :]).astype(np.float64))   # outer(pi.u.t, thrs, "<")
+        nTP = np.sum(lt * ind[:, None], axis=0)                       # :89
+        nFN = np.sum(ind) - nTP
+        TP = nTP / np.sum(ind)
+        nFP = np.sum(lt * (1 - ind)[:, None], axis=0)                 # :92
+        nTN = np.sum(1 - ind) - nFP
+        FP = nFP / np.sum(1 - ind)
+        Q = np.mean(lt, axis=0)                                       # :95
+        Qd = 1 - Q
+        k10 = (TP - Q) / Qd
+        k00 = (1 - FP - Qd) / Q
+        P = np.mean(ind)
+        k05 = (P * Qd * k10 + (1 - P) * Q * k00) / (P * Qd + (1 - P) * Q)
+        f1 = 2 * nTP / (2 * nTP + nFN + nFP)
+        youden = TP - FP
+    return dict(TP=TP, FP=FP, nTP=nTP, nFN=nFN, nFP=nFP, nTN=nTN, qSN=k10, qSP=k00, qOverall=k05, thrs=thrs,
+                F1score=_median_at_max(thrs, f1), Youden=_median_at_max(thrs, youden))
+
+
+def _median_at_max(thrs, x):
+    """median(thrs[x == max(x)]) (R/rocJM.mvJMbayes.R:103,105); max() without na.rm is NA as soon as one element is."""
+    m = np.max(x) if not np.any(np.isnan(x)) else float("nan")
+    return float("nan") if np.isnan(m) else float(np.median(thrs[x == m]))

@@ -82,7 +82,16 @@ def test_cabi_library_exports_the_accuracy_symbols():
     lib = build.build_cuda()
     hdr = open(os.path.join(ROOT, "include", "jmb200_accuracy.h")).read()
     names = sorted(set(re.findall(r"\b(jmb_[A-Za-z_0-9]+)\s*\(", hdr)))
-    assert names == ["jmb_aucJM_pairs", "jmb_prederrJM_sum"]
+    assert names == ["jmb_aucJM_pairs", "jmb_prederrJM_sum", "jmb_rocJM_sums"]
     L = C.CDLL(lib)
     for nm in names:
         assert hasattr(L, nm), nm
+
+
+def test_roc_restatement_on_a_case_worked_by_hand():
+    # three subjects: one dead before the horizon (pi .2), one censored before it (pi .6, weight .5), one alive after it (pi .9)
+    r = oa.rocJM([1.0, 2.0, 9.0], [1.0, 0.0, 0.0], 5.0, [0.2, 0.6, 0.9], [0.0, 0.5, 0.0])
+    k = 50                                                         # threshold 0.5: only the first subject is below it
+    assert np.isclose(r["nTP"][k], 1.0) and np.isclose(r["nFP"][k], 0.0) and np.isclose(r["nFN"][k], 0.5)
+    assert np.isclose(r["TP"][k], 1.0 / 1.5) and np.isclose(r["nTN"][k], 1.5)
+    assert np.isclose(r["nTP"][100], 1.5) and np.isclose(r["nFP"][100], 1.5)      # threshold 1: everybody below

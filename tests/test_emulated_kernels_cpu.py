@@ -151,3 +151,22 @@ def test_emulated_accuracy_sums_match_restated_loops(emu, n, seed, na):
     cc[3] = np.nan
     for loss in ("square", "absolute"):
         assert np.isclose(accuracy.prederrJM_sum(a, d, cc, w, 700, loss), oa.prederrJM_sum(a, d, cc, w, 700, loss), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,seed,na", [(1, 1, 0.0), (700, 2, 0.0), (2500, 3, 0.0), (300, 4, 0.05)])
+def test_emulated_roc_sums_match_restated_outer_product(emu, n, seed, na):
+    from jmbayes_b200 import accuracy
+    from oracle import oracle_accuracy as oa
+    from test_accuracy_cpu import make_case
+    Time, event, Th, pi, pi2, _ = make_case(n, seed, na)
+    want = oa.rocJM(Time, event, Th, pi, pi2)
+    got = accuracy.rocJM(Time, event, Th, pi, pi2)
+    for k in ("nTP", "nFP", "nFN", "nTN", "TP", "FP"):
+        assert np.allclose(got[k], want[k], rtol=1e-11, atol=1e-11, equal_nan=True), k
+    # the kappa-type measures are 0/0-like where every (or no) probability is below the threshold: compare inside
+    below = np.sum(np.asarray(pi)[:, None] < want["thrs"][None, :], axis=0)
+    inside = (below > 0) & (below < np.sum(~np.isnan(pi)))
+    for k in ("qSN", "qSP", "qOverall"):
+        assert np.allclose(got[k][inside], want[k][inside], rtol=1e-9, atol=1e-9, equal_nan=True), k
+    if not na:
+        assert np.isclose(got["F1score"], want["F1score"], equal_nan=True) and np.isclose(got["Youden"], want["Youden"], equal_nan=True)

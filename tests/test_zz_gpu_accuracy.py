@@ -62,3 +62,20 @@ def test_prederr_sum_matches_restatement(acc):
     for loss in ("square", "absolute"):
         assert np.isclose(acc.prederrJM_sum(a, d, c, w, 7000, loss), oa.prederrJM_sum(a, d, c, w, 7000, loss), rtol=1e-12)
     assert np.isclose(acc.prederrJM_sum(a, d, [], [], 5000), oa.prederrJM_sum(a, d, [], [], 5000), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,seed,na", [(1, 1, 0.0), (700, 2, 0.0), (50_000, 3, 0.0), (300, 4, 0.05)])
+def test_roc_sums_match_restated_outer_product(acc, n, seed, na):
+    from test_accuracy_cpu import make_case
+    Time, event, Th, pi, pi2, _ = make_case(n, seed, na)
+    want = oa.rocJM(Time, event, Th, pi, pi2)
+    got = acc.rocJM(Time, event, Th, pi, pi2)
+    for k in ("nTP", "nFP", "nFN", "nTN", "TP", "FP"):
+        assert np.allclose(got[k], want[k], rtol=1e-11, atol=1e-11, equal_nan=True), k
+    # the kappa-type measures are 0/0-like where every (or no) probability is below the threshold: compare inside
+    below = np.sum(np.asarray(pi)[:, None] < want["thrs"][None, :], axis=0)
+    inside = (below > 0) & (below < np.sum(~np.isnan(pi)))
+    for k in ("qSN", "qSP", "qOverall"):
+        assert np.allclose(got[k][inside], want[k][inside], rtol=1e-9, atol=1e-9, equal_nan=True), k
+    if not na:
+        assert np.isclose(got["F1score"], want["F1score"], equal_nan=True) and np.isclose(got["Youden"], want["Youden"], equal_nan=True)
