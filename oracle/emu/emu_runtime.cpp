@@ -7,24 +7,62 @@ dim3 blockDim, gridDim;
 namespace emu {
 Cta g_cta;
 thread_local unsigned t_tid;
+double* dyn_smem() { alignas(128) static double buf[1 << 16]; return buf; }    // 512 KB >= any CTA's dynamic shared memory
+
+namespace {
+// One OS thread per CUDA thread of the running CTA, kept between launches (a chain is thousands of small launches).
+struct Pool {
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    std::vector<std::thread> th;
+    unsigned long long gen = 0;
+    unsigned active = 0, remaining = 0;
+    const std::function<void()>* fn = nullptr;
+    dim3 block;
+
+    void worker(unsigned id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> l(m);
+            cv_job.wait(l, [&] { return gen != seen; });
+            seen = gen;
+            if (id >= active) continue;
+            const std::function<void()>* f = fn;
+            const dim3 b = block;
+            l.unlock();
+            t_tid = id;
+            ::threadIdx = uint3{id % b.x, (id / b.x) % b.y, id / (b.x * b.y)};
+            (*f)();
+            l.lock();
+            if (--remaining == 0) cv_done.notify_one();
+        }
+    }
+    void run_cta(unsigned n, dim3 b, const std::function<void()>& f) {
+        while (th.size() < n) {
+            const unsigned id = (unsigned)th.size();
+            th.emplace_back([this, id] { worker(id); });
+            th.back().detach();
+        }
+        std::unique_lock<std::mutex> l(m);
+        active = n; remaining = n; fn = &f; block = b; ++gen;
+        cv_job.notify_all();
+        cv_done.wait(l, [&] { return remaining == 0; });
+    }
+};
+Pool& pool() { static Pool* p = new Pool(); return *p; }      // never destroyed: its threads are detached
+std::mutex g_launch;                                            // one launch at a time (host threads of the library's packers do not launch)
+}  // namespace
 
 void launch(dim3 grid, dim3 block, size_t, cudaStream_t, const std::function<void()>& fn) {
     const unsigned nthreads = block.x * block.y * block.z;
-    if (nthreads > 1024) { std::fprintf(stderr, "emu: block too large\n"); std::abort(); }
+    if (nthreads == 0 || nthreads > 1024) { std::fprintf(stderr, "emu: bad block size\n"); std::abort(); }
+    std::lock_guard<std::mutex> g(g_launch);
     ::gridDim = grid; ::blockDim = block;
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 ::blockIdx = uint3{bx, by, bz};
-                std::vector<std::thread> th;
-                th.reserve(nthreads);
-                for (unsigned t = 0; t < nthreads; ++t)
-                    th.emplace_back([&, t] {
-                        t_tid = t;
-                        ::threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-                        fn();
-                    });
-                for (auto& x : th) x.join();
+                pool().run_cta(nthreads, block, fn);
             }
 }
 }  // namespace emu

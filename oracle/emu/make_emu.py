@@ -3,8 +3,9 @@ CUDA runtime of oracle/emu/shim (kernels run on CPU threads).  TEST INFRASTRUCTU
 
 The sources are used where they lie; three textual substitutions make them C++:
   1. `kernel<<<grid, block, smem, stream>>>(args)`  ->  `emu::launch(grid, block, smem, stream, [&] { kernel(args); })`
-  2. `extern __shared__` -> `extern`, `__shared__` -> `static`   (one CTA runs at a time)
-  3. the two `asm volatile("griddepcontrol...")` statements of the PDL helpers -> empty statements
+  2. `extern __shared__ T name[];` -> `T* name = (T*)emu::dyn_smem();`, `__shared__` -> `static`   (one CTA runs at a time)
+  3. the two `asm volatile("griddepcontrol...")` statements of the PDL helpers -> empty statements;
+     `__noinline__` -> `__attribute__((noinline))`
 """
 from __future__ import annotations
 
@@ -17,7 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "jmbayes_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libjmb200_emu.so")
-SOURCES = ["jmb200.cu", "jmb_kernels.cuh", "jmb_device.cuh", "jmb_model.h", "jmb_host.h", "jmb_laplace.cu", "jmb_accuracy.cu"]
+SOURCES = ["jmb200.cu", "jmb_kernels.cuh", "jmb_device.cuh", "jmb_model.h", "jmb_host.h", "jmb_laplace.cu", "jmb_accuracy.cu",
+           "jmb_survfit.cu", "jmb_survfit.cuh", "jmb_summaries.cu"]
 CALLEE = re.compile(r"[A-Za-z_][A-Za-z_0-9]*(?:->[A-Za-z_][A-Za-z_0-9]*)*(?:<[^<>;(){}]*>)?$")
 
 
@@ -69,7 +71,8 @@ def rewrite_launches(text: str) -> str:
 
 def transform(text: str) -> str:
     text = rewrite_launches(text)
-    text = text.replace("extern __shared__", "extern").replace("__shared__", "static")
+    text = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu::dyn_smem();", text)
+    text = text.replace("__shared__", "static").replace("__noinline__", "__attribute__((noinline))")
     text = re.sub(r'asm volatile\("griddepcontrol[^;]*;"[^;]*;', ";", text)
     text = text.replace('"../../include/', '"' + os.path.join(ROOT, "include") + "/")
     return text
@@ -79,7 +82,8 @@ def build(force: bool = False) -> str:
     os.makedirs(OUT, exist_ok=True)
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, "shim", f) for f in os.listdir(os.path.join(HERE, "shim"))] + \
            [os.path.join(HERE, "emu_runtime.cpp"), os.path.abspath(__file__), os.path.join(ROOT, "include", "jmb200.h"),
-            os.path.join(ROOT, "include", "jmb200_accuracy.h")]
+            os.path.join(ROOT, "include", "jmb200_accuracy.h"),
+            os.path.join(ROOT, "include", "jmb200_survfit.h"), os.path.join(ROOT, "include", "jmb200_summaries.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     for s in SOURCES:
@@ -90,8 +94,9 @@ def build(force: bool = False) -> str:
             f.write(txt)
     with open(os.path.join(HERE, "shim", "jmb_step_static.cuh")) as f, open(os.path.join(OUT, "jmb_step_static.cuh"), "w") as g:
         g.write(f.read())
-    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-I", os.path.join(HERE, "shim"), "-I", OUT,
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-fpermissive", "-fmax-errors=15", "-I", os.path.join(HERE, "shim"), "-I", OUT,
            "-o", LIB, os.path.join(OUT, "jmb200_emu.cpp"), os.path.join(OUT, "jmb_laplace_emu.cpp"), os.path.join(OUT, "jmb_accuracy_emu.cpp"),
+           os.path.join(OUT, "jmb_survfit_emu.cpp"), os.path.join(OUT, "jmb_summaries_emu.cpp"),
            os.path.join(HERE, "emu_runtime.cpp"), "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

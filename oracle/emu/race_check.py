@@ -5,7 +5,7 @@ In the emulation every CUDA thread is an OS thread and __syncthreads / __syncwar
 variable barriers, so ThreadSanitizer sees exactly the happens-before edges the CUDA programming model guarantees: a missing
 barrier between a shared-memory write of one lane and a read of another (which a B200 may tolerate by accident of warp
 lock-step) is reported as a data race.  `python oracle/emu/race_check.py` prints the number of reports for a short chain of
-every kernel family; `--drop-syncwarp` is the negative control (one __syncwarp of the step kernel removed in a scratch copy
+every kernel family (MCMC step / finalize / Laplace, accuracy, posterior summaries, survfitJM); `--drop-syncwarp` is the negative control (one __syncwarp of the step kernel removed in a scratch copy
 of the generated sources: the check must then report races).
 """
 from __future__ import annotations
@@ -47,6 +47,17 @@ rng = np.random.default_rng(1)
 n = 300
 T = np.sort(rng.uniform(2, 9, n)); d = rng.choice([0.0, 1.0, 2.0, 3.0], size=n); p = rng.uniform(size=n)
 accuracy.aucJM_pairs(T, d, 5.0, p, p, p); accuracy.rocJM(T, d, 5.0, p, p); accuracy.prederrJM_sum(p, p, p, p, 3 * n)
+if %(extra)r:
+    from jmbayes_b200 import survfit as sv, summaries
+    from oracle import oracle_svft, oracle_stats
+    X = np.cumsum(rng.normal(size=(40, 120)), axis=1) * 0.1 + rng.normal(size=(40, 120))
+    summaries.series_statistics(np.ascontiguousarray(X), 40, 120, 120, 1, oracle_stats.stand(rng.normal(size=120)))
+    c5 = make_cohort("config3", n=16)
+    d5 = sv.newdata_designs(c5, L=3)
+    means, draws = sv.posterior_draws(c5, M=6)
+    with sv.SurvFit(d5) as h:
+        g5 = h.modes(means)
+        h.sample(draws, g5["modes"], g5["hessians"])
 print("race-check driver done")
 '''
 
@@ -57,7 +68,7 @@ def libtsan():
     return p if r.returncode == 0 and os.path.isabs(p) and os.path.exists(p) else None
 
 
-def run(drop_syncwarp: bool = False, names=("config2", "config4", "multistate")):
+def run(drop_syncwarp: bool = False, names=("config2", "config4", "multistate"), extra: bool = True):
     """Returns (number of ThreadSanitizer reports, report text)."""
     make_emu.build()
     work = tempfile.mkdtemp(prefix="jmb_tsan_")
@@ -71,14 +82,15 @@ def run(drop_syncwarp: bool = False, names=("config2", "config4", "multistate"))
             assert s.count(a) == 1
             open(p, "w").write(s.replace(a, "        for (int j = lane; j < QS; j += G) bo[j] = st[j];"))
         lib = os.path.join(work, "libjmb200_emu_tsan.so")
-        cmd = ["g++", "-O1", "-g", "-fsanitize=thread", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-I", os.path.join(HERE, "shim"),
-               "-I", src, "-o", lib] + [os.path.join(src, f) for f in ("jmb200_emu.cpp", "jmb_laplace_emu.cpp", "jmb_accuracy_emu.cpp")] + \
+        cmd = ["g++", "-O1", "-g", "-fsanitize=thread", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-fpermissive", "-I", os.path.join(HERE, "shim"),
+               "-I", src, "-o", lib] + [os.path.join(src, f) for f in ("jmb200_emu.cpp", "jmb_laplace_emu.cpp", "jmb_accuracy_emu.cpp", "jmb_survfit_emu.cpp",
+                                                                           "jmb_summaries_emu.cpp")] + \
               [os.path.join(HERE, "emu_runtime.cpp"), "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("TSan build failed:\n" + r.stderr[-4000:])
         env = dict(os.environ, LD_PRELOAD=libtsan(), TSAN_OPTIONS="report_signal_unsafe=0 halt_on_error=0 exitcode=0 history_size=2")
-        r = subprocess.run([sys.executable, "-c", DRIVER % dict(root=ROOT, lib=lib, names=tuple(names))], capture_output=True, text=True, env=env, cwd=work,
+        r = subprocess.run([sys.executable, "-c", DRIVER % dict(root=ROOT, lib=lib, names=tuple(names), extra=bool(extra))], capture_output=True, text=True, env=env, cwd=work,
                            timeout=1500)
         if "race-check driver done" not in r.stdout:
             raise RuntimeError("race-check driver failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -31,6 +32,9 @@
 #define __restrict__
 #define __grid_constant__
 #define __launch_bounds__(...)
+using std::isfinite;
+using std::isnan;
+using std::isinf;
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
@@ -65,18 +69,19 @@ struct Barrier {
 };
 struct Cta {
     Barrier all;
-    Barrier warp[32][3];                 // [warp][full, low half, high half]
-    unsigned long long slot[32][32];     // shuffle exchange
+    std::mutex wm[32];
+    std::map<unsigned, Barrier> warp[32];   // [warp]: one barrier per participation mask
+    unsigned long long slot[32][32];        // shuffle / vote exchange
 };
 extern Cta g_cta;
 extern thread_local unsigned t_tid;
-inline int mask_class(unsigned mask) {
-    if (mask == 0xFFFFFFFFu) return 0;
-    if (mask == 0x0000FFFFu) return 1;
-    if (mask == 0xFFFF0000u) return 2;
-    std::fprintf(stderr, "emu: unsupported warp mask %08x\n", mask); std::abort();
+double* dyn_smem();                         // the CTA's dynamic shared memory (every `extern __shared__` array aliases it)
+inline void warp_barrier(unsigned mask) {
+    const unsigned w = t_tid >> 5;
+    Barrier* b;
+    { std::lock_guard<std::mutex> l(g_cta.wm[w]); b = &g_cta.warp[w][mask]; }
+    b->wait(__builtin_popcount(mask));
 }
-inline void warp_barrier(unsigned mask) { g_cta.warp[t_tid >> 5][mask_class(mask)].wait(__builtin_popcount(mask)); }
 template <class T> inline T shfl(unsigned mask, T v, int src_lane) {
     static_assert(sizeof(T) <= 8, "shuffle of more than 8 bytes");
     const unsigned w = t_tid >> 5, lane = t_tid & 31;
@@ -102,6 +107,44 @@ template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int off, int wid
 template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
     const int lane = (int)(emu::t_tid & 31);
     return emu::shfl(mask, v, (lane & ~(width - 1)) | (src & (width - 1)));
+}
+template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+    const int lane = (int)(emu::t_tid & 31), src = lane - (int)delta;
+    const T got = emu::shfl(mask, v, src < (lane & ~(width - 1)) ? lane : src);
+    return got;
+}
+template <class T> inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+    const int lane = (int)(emu::t_tid & 31), src = lane + (int)delta;
+    return emu::shfl(mask, v, src > (lane | (width - 1)) ? lane : src);
+}
+inline unsigned __ballot_sync(unsigned mask, int pred) {
+    const unsigned w = emu::t_tid >> 5, lane = emu::t_tid & 31;
+    emu::g_cta.slot[w][lane] = pred ? 1ull : 0ull;
+    emu::warp_barrier(mask);
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; ++l) if ((mask >> l) & 1u) r |= (unsigned)(emu::g_cta.slot[w][l] & 1ull) << l;
+    emu::warp_barrier(mask);
+    return r;
+}
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, 8); return d; }
+inline long long __double_as_longlong(double d) { long long x; std::memcpy(&x, &d, 8); return x; }
+inline double __hiloint2double(int hi, int lo) { const unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double d; std::memcpy(&d, &u, 8); return d; }
+inline int __double2loint(double d) { unsigned long long u; std::memcpy(&u, &d, 8); return (int)(unsigned)(u & 0xFFFFFFFFull); }
+inline int __double2hiint(double d) { unsigned long long u; std::memcpy(&u, &d, 8); return (int)(unsigned)(u >> 32); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline double atomicAdd(double* p, double v) {
+    unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
+    unsigned long long old = __atomic_load_n(q, __ATOMIC_RELAXED), neu;
+    double d;
+    do { std::memcpy(&d, &old, 8); d += v; std::memcpy(&neu, &d, 8); } while (!__atomic_compare_exchange_n(q, &old, neu, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    std::memcpy(&d, &old, 8);
+    return d;
 }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 inline void sincospi(double x, double* s, double* c) {      // exact reduction to a multiple of 1/2, then sin / cos of pi r
@@ -144,6 +187,14 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
 inline cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F*, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return cudaSuccess; }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr) {
+    for (size_t r = 0; r < h; ++r) std::memcpy((char*)d + r * dp, (const char*)s + r * sp, w);
+    return cudaSuccess;
+}
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorEmu; }
 inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorEmu; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorEmu; }

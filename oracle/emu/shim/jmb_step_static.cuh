@@ -4,8 +4,6 @@
 #pragma once
 #include "jmb_kernels.cuh"
 namespace jmb {
-inline double smem[1 << 16];      // the kernels' `extern __shared__ double smem[]` / `s_par[]` (one CTA runs at a time)
-inline double s_par[1 << 16];
 constexpr int kTmaThreads = 256, kTmaCtas = 1, kTmaWarps = kTmaThreads / 32;
 struct TmaArgs { int cap_d, cap_c, subjects_per_cta; };
 template <class Spec> void jmb_step_static(int, ParamLayout, ChainConst, StepArgs) { std::abort(); }

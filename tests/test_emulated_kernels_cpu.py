@@ -1,7 +1,7 @@
 """The library's OWN kernels, run on CPU threads.
 
-oracle/emu compiles jmbayes_b200/csrc/jmb200.cu (+ jmb_kernels.cuh, jmb_device.cuh, jmb_laplace.cu, jmb_accuracy.cu) - the
-sources a B200 runs, not a restatement - with g++ against a stand-in CUDA runtime in which a kernel launch executes its CTAs
+oracle/emu compiles jmbayes_b200/csrc/jmb200.cu (+ jmb_kernels.cuh, jmb_device.cuh, jmb_laplace.cu, jmb_accuracy.cu,
+jmb_survfit.cu/.cuh, jmb_summaries.cu) - the sources a B200 runs, not a restatement - with g++ against a stand-in CUDA runtime in which a kernel launch executes its CTAs
 with one OS thread per CUDA thread and __syncthreads / __syncwarp / __shfl_*_sync are barriers over exactly the threads they
 name (oracle/emu/shim/cuda_runtime.h).  That is test infrastructure in the sense of oracle/: nothing in the product loads
 it, it is never timed and it is no fallback.  It lets this CPU suite check, on small cohorts, the kernel arithmetic, the
@@ -170,3 +170,26 @@ def test_emulated_roc_sums_match_restated_outer_product(emu, n, seed, na):
         assert np.allclose(got[k][inside], want[k][inside], rtol=1e-9, atol=1e-9, equal_nan=True), k
     if not na:
         assert np.isclose(got["F1score"], want["F1score"], equal_nan=True) and np.isclose(got["Youden"], want["Youden"], equal_nan=True)
+
+
+def test_emulated_summaries_and_survfit_kernels_match_their_oracles(emu):
+    """The checks of __graft_entry__.smoke() for the posterior summaries and survfitJM, on the emulated kernels."""
+    from jmbayes_b200 import summaries, survfit as sv
+    from oracle import oracle_stats, oracle_svft
+    rng = np.random.default_rng(3)
+    X = np.cumsum(rng.normal(size=(48, 160)), axis=1) * 0.1 + rng.normal(size=(48, 160))
+    w = oracle_stats.stand(rng.normal(size=160))
+    gs, _ = summaries.series_statistics(np.ascontiguousarray(X), 48, 160, 160, 1, w)
+    rs = oracle_stats.statistics(X, w)
+    for name in ("postMeans", "postwMeans", "StDev", "wStDev", "CIs", "wCIs", "EffectiveSize", "StErr", "Pvalues"):
+        assert np.allclose(gs[name], rs[name], rtol=1e-9, atol=1e-12), name
+    c5 = make_cohort("config3", n=24)
+    d5 = sv.newdata_designs(c5, L=3)
+    means, draws = sv.posterior_draws(c5, M=6)
+    o5 = oracle_svft.modes(d5, means)
+    with sv.SurvFit(d5) as h:
+        g5 = h.modes(means)
+        s5 = h.sample(draws, o5["modes"], o5["hessians"])
+    r5 = oracle_svft.sample(d5, draws, o5["modes"], o5["hessians"])
+    assert np.max(np.abs(g5["modes"] - o5["modes"])) < 1e-6
+    assert np.allclose(s5["summaries"], r5["summaries"], rtol=1e-9)
