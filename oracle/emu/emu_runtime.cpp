@@ -10,6 +10,29 @@ thread_local unsigned t_tid;
 double* dyn_smem() { alignas(128) static double buf[1 << 16]; return buf; }    // 512 KB >= any CTA's dynamic shared memory
 
 namespace {
+struct Mbar { int count = 0, pending = 0; long long tx = 0; unsigned phase = 0; };
+std::mutex g_mb_m;
+std::condition_variable g_mb_cv;
+std::map<const void*, Mbar> g_mb;
+void mbar_maybe_complete(Mbar& b) {
+    if (b.pending == 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.count; g_mb_cv.notify_all(); }
+}
+}  // namespace
+void mbar_init(const void* bar, int count) { std::lock_guard<std::mutex> l(g_mb_m); g_mb[bar] = Mbar{count, count, 0, 0}; }
+void mbar_arrive_expect_tx(const void* bar, unsigned bytes) {
+    std::lock_guard<std::mutex> l(g_mb_m);
+    Mbar& b = g_mb[bar]; b.tx += bytes; b.pending -= 1; mbar_maybe_complete(b);
+}
+void mbar_complete_tx(const void* bar, unsigned bytes) {
+    std::lock_guard<std::mutex> l(g_mb_m);
+    Mbar& b = g_mb[bar]; b.tx -= bytes; mbar_maybe_complete(b);
+}
+void mbar_wait(const void* bar, unsigned parity) {
+    std::unique_lock<std::mutex> l(g_mb_m);
+    g_mb_cv.wait(l, [&] { return (g_mb[bar].phase & 1u) != (parity & 1u); });
+}
+
+namespace {
 // One OS thread per CUDA thread of the running CTA, kept between launches (a chain is thousands of small launches).
 struct Pool {
     std::mutex m;

@@ -4,7 +4,8 @@ CUDA runtime of oracle/emu/shim (kernels run on CPU threads).  TEST INFRASTRUCTU
 The sources are used where they lie; three textual substitutions make them C++:
   1. `kernel<<<grid, block, smem, stream>>>(args)`  ->  `emu::launch(grid, block, smem, stream, [&] { kernel(args); })`
   2. `extern __shared__ T name[];` -> `T* name = (T*)emu::dyn_smem();`, `__shared__` -> `static`   (one CTA runs at a time)
-  3. the two `asm volatile("griddepcontrol...")` statements of the PDL helpers -> empty statements;
+  3. the `asm volatile("griddepcontrol...")` / `fence.mbarrier_init` statements -> empty statements; the four PTX helpers of
+     the TMA-staged kernel (mbarrier.init / arrive.expect_tx / try_wait, cp.async.bulk) -> shim/emu_mbarrier.h;
      `__noinline__` -> `__attribute__((noinline))`
 """
 from __future__ import annotations
@@ -19,7 +20,7 @@ CSRC = os.path.join(ROOT, "jmbayes_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libjmb200_emu.so")
 SOURCES = ["jmb200.cu", "jmb_kernels.cuh", "jmb_device.cuh", "jmb_model.h", "jmb_host.h", "jmb_laplace.cu", "jmb_accuracy.cu",
-           "jmb_survfit.cu", "jmb_survfit.cuh", "jmb_summaries.cu"]
+           "jmb_survfit.cu", "jmb_survfit.cuh", "jmb_summaries.cu", "jmb_step_static.cuh"]
 CALLEE = re.compile(r"[A-Za-z_][A-Za-z_0-9]*(?:->[A-Za-z_][A-Za-z_0-9]*)*(?:<[^<>;(){}]*>)?$")
 
 
@@ -73,7 +74,12 @@ def transform(text: str) -> str:
     text = rewrite_launches(text)
     text = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu::dyn_smem();", text)
     text = text.replace("__shared__", "static").replace("__noinline__", "__attribute__((noinline))")
-    text = re.sub(r'asm volatile\("griddepcontrol[^;]*;"[^;]*;', ";", text)
+    text = re.sub(r'asm volatile\("(?:griddepcontrol|fence\.mbarrier_init)[^;]*;"[^;]*;', ";", text)
+    # the PTX helpers of the TMA-staged kernel (mbarrier + cp.async.bulk) -> their emulation (shim/emu_mbarrier.h)
+    i = text.find("__device__ __forceinline__ uint32_t smem_u32")
+    if i >= 0:
+        j = text.index("struct TmaArgs {", i)
+        text = text[:i] + '#include "emu_mbarrier.h"\n\n' + text[j:]
     text = text.replace('"../../include/', '"' + os.path.join(ROOT, "include") + "/")
     return text
 
@@ -92,8 +98,6 @@ def build(force: bool = False) -> str:
             txt = transform(f.read())
         with open(dst, "w") as f:
             f.write(txt)
-    with open(os.path.join(HERE, "shim", "jmb_step_static.cuh")) as f, open(os.path.join(OUT, "jmb_step_static.cuh"), "w") as g:
-        g.write(f.read())
     cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-fpermissive", "-fmax-errors=15", "-I", os.path.join(HERE, "shim"), "-I", OUT,
            "-o", LIB, os.path.join(OUT, "jmb200_emu.cpp"), os.path.join(OUT, "jmb_laplace_emu.cpp"), os.path.join(OUT, "jmb_accuracy_emu.cpp"),
            os.path.join(OUT, "jmb_survfit_emu.cpp"), os.path.join(OUT, "jmb_summaries_emu.cpp"),

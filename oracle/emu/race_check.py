@@ -5,8 +5,9 @@ In the emulation every CUDA thread is an OS thread and __syncthreads / __syncwar
 variable barriers, so ThreadSanitizer sees exactly the happens-before edges the CUDA programming model guarantees: a missing
 barrier between a shared-memory write of one lane and a read of another (which a B200 may tolerate by accident of warp
 lock-step) is reported as a data race.  `python oracle/emu/race_check.py` prints the number of reports for a short chain of
-every kernel family (MCMC step / finalize / Laplace, accuracy, posterior summaries, survfitJM); `--drop-syncwarp` is the negative control (one __syncwarp of the step kernel removed in a scratch copy
-of the generated sources: the check must then report races).
+every kernel family (MCMC step / finalize / Laplace, accuracy, posterior summaries, survfitJM); `--drop-syncwarp` is the negative control (one __syncwarp of the generic step kernel removed in a scratch copy of the
+generated sources: the check must then report races).  (Removing the __syncwarp that guards the re-use of a stage of the
+TMA-staged kernel is not a usable control: the emulated warp then deadlocks on the mbarrier phase, as the device would.)
 """
 from __future__ import annotations
 
@@ -32,6 +33,18 @@ from jmbayes_b200.cohorts import make_cohort, make_multistate_cohort
 from oracle import oracle
 for name in %(names)r:
     ms = name == "multistate"
+    if not ms and %(extra)r:
+        # the compile-time specialised kernel and the TMA-staged kernel (two-stage cp.async.bulk + mbarrier pipeline per warp)
+        c = make_cohort(name, n=128)     # 2 CTAs x 8 warps x 8 subjects: 4 (16 lanes) or 8 (32 lanes) pipeline steps per warp
+        ctl = dict(c["control"]); ctl.update(n_burnin=4, n_iter=2, n_block=2, n_thin=2)
+        for mode in ("direct", None):
+            if mode: os.environ["JMB_KERNEL"] = mode
+            else: os.environ.pop("JMB_KERNEL", None)
+            with api.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
+                assert fit.layout_info()["kernel"].startswith("static:" if mode else "static-tma:"), fit.layout_info()["kernel"]
+                fit.set_draw(c["Data"])
+                fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+        os.environ["JMB_KERNEL"] = "generic"
     c = make_multistate_cohort(n=24) if ms else make_cohort(name, n=24)
     ctl = dict(c["control"]); ctl.update(n_burnin=6, n_iter=4, n_block=2, n_thin=2, adaptCov=True)
     pr = dict(c["priors"]); pr.update(shrink_gammas=True, shrink_alphas=True)
@@ -91,7 +104,7 @@ def run(drop_syncwarp: bool = False, names=("config2", "config4", "multistate"),
             raise RuntimeError("TSan build failed:\n" + r.stderr[-4000:])
         env = dict(os.environ, LD_PRELOAD=libtsan(), TSAN_OPTIONS="report_signal_unsafe=0 halt_on_error=0 exitcode=0 history_size=2")
         r = subprocess.run([sys.executable, "-c", DRIVER % dict(root=ROOT, lib=lib, names=tuple(names), extra=bool(extra))], capture_output=True, text=True, env=env, cwd=work,
-                           timeout=1500)
+                           timeout=900)
         if "race-check driver done" not in r.stdout:
             raise RuntimeError("race-check driver failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
         return r.stderr.count("WARNING: ThreadSanitizer"), r.stderr

@@ -75,6 +75,10 @@ struct Cta {
 };
 extern Cta g_cta;
 extern thread_local unsigned t_tid;
+void mbar_init(const void* bar, int count);       // emulated mbarrier objects, keyed by their shared-memory address
+void mbar_arrive_expect_tx(const void* bar, unsigned bytes);
+void mbar_complete_tx(const void* bar, unsigned bytes);
+void mbar_wait(const void* bar, unsigned parity);
 double* dyn_smem();                         // the CTA's dynamic shared memory (every `extern __shared__` array aliases it)
 inline void warp_barrier(unsigned mask) {
     const unsigned w = t_tid >> 5;
@@ -167,7 +171,8 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* c) { *c = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 4; return cudaSuccess; }
+// one SM: few, large CTAs, so that every warp of the TMA-staged kernel runs several steps of its pipeline
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 1; return cudaSuccess; }
 inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = (size_t)1 << 30; *t = (size_t)2 << 30; return cudaSuccess; }
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes) { *p = (T*)std::malloc(bytes ? bytes : 8); return *p ? cudaSuccess : cudaErrorEmu; }
 template <class T> inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned) { *p = (T*)std::malloc(bytes ? bytes : 8); return *p ? cudaSuccess : cudaErrorEmu; }
@@ -190,7 +195,7 @@ inline cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { r
 template <class F> inline cudaError_t cudaFuncSetAttribute(F*, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 1; return cudaSuccess; }
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
-inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 1; return cudaSuccess; }
 inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr) {
     for (size_t r = 0; r < h; ++r) std::memcpy((char*)d + r * dp, (const char*)s + r * sp, w);
     return cudaSuccess;

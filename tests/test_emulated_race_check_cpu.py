@@ -16,7 +16,8 @@ pytestmark = pytest.mark.skipif(race_check.libtsan() is None, reason="libtsan.so
 
 
 def test_kernels_are_race_free_under_thread_sanitizer(oracle):
-    """Generic step kernel (16 / 32 lanes, multi-state blocks), block-prep, finalize (Gibbs draws, adaptCov), scale
+    """Generic, compile-time specialised and TMA-staged step kernels (16 / 32 lanes, multi-state blocks, the bulk-copy +
+    mbarrier pipeline), block-prep, finalize (Gibbs draws, adaptCov), scale
     adaptation, Xbetas, survival-posterior, the accuracy kernels, the posterior-summaries kernel and the survfitJM kernels
     (mode search, sampler, horizon integrals): no report."""
     n, text = race_check.run()
