@@ -42,9 +42,10 @@ int jmb_prederrJM_sum(int device, int32_t loss, int32_t nr, int32_t n_alive, con
 /* rocJM.mvJMbayes (R/rocJM.mvJMbayes.R:68-95): ind_i = 1 for subjects who died before Thoriz (T_i < Thoriz, d_i in {1, 3}),
  * pi2_i = 1 - S_i(Thoriz | T_i) for those censored before it (d_i in {0, 2}), 0 otherwise; then for every threshold
  *     nTP[k] = sum_i (pi_i < thrs[k]) ind_i,  nFP[k] = sum_i (pi_i < thrs[k]) (1 - ind_i),  Q[k] = mean_i (pi_i < thrs[k])
- * - the column sums of the n x 101 matrix outer(pi.u.t, thrs, "<") (:89,92,95) - and sum_ind = sum(ind) (:90-91).  No
+ * - the column sums of the n x 101 matrix outer(pi.u.t, thrs, "<") (:89,92,95) - and sum_ind = { sum(ind), sum(1 - ind) } (:90-93), each
+ * accumulated in the order of nTP / nFP so that nFN and nTN cancel exactly as they do in R.  No
  * na.rm in the reference: NaN inputs propagate.  Everything after these sums (:90-105) is arithmetic on 101 numbers and
- * stays with the caller.  nTP, nFP, Q: [n_thr]; sum_ind: [1]. */
+ * stays with the caller.  nTP, nFP, Q: [n_thr]; sum_ind: [2]. */
 int jmb_rocJM_sums(int device, int32_t n, const double* Time, const double* event, double Thoriz, const double* pi_u_t,
                    const double* pi2, int32_t n_thr, const double* thrs, double* nTP, double* nFP, double* Q, double* sum_ind);
 

@@ -71,19 +71,19 @@ def rocJM(Time, event, Thoriz, pi_u_t, pi2, thrs=None, device: int = 0) -> dict:
     T, d, p, p2 = (_vec(x) for x in (Time, event, pi_u_t, pi2))
     thrs = np.linspace(0.0, 1.0, 101) if thrs is None else _vec(thrs)
     n, m = T.size, thrs.size
-    nTP, nFP, Q, s = np.zeros(m), np.zeros(m), np.zeros(m), np.zeros(1)
+    nTP, nFP, Q, s = np.zeros(m), np.zeros(m), np.zeros(m), np.zeros(2)
     P = lambda a: a.ctypes.data_as(c_double_p)  # noqa: E731
     _check(_lib().jmb_rocJM_sums(int(device), n, P(T), P(d), float(Thoriz), P(p), P(p2), m, P(thrs), P(nTP), P(nFP), P(Q), P(s)))
-    return _roc_tail(nTP, nFP, Q, float(s[0]), n, thrs)
+    return _roc_tail(nTP, nFP, Q, float(s[0]), float(s[1]), n, thrs)
 
 
-def _roc_tail(nTP, nFP, Q, sum_ind, n, thrs):
+def _roc_tail(nTP, nFP, Q, sum_ind, sum_not_ind, n, thrs):
     """R/rocJM.mvJMbayes.R:90-105."""
     with np.errstate(all="ignore"):
         nFN = sum_ind - nTP
         TP = nTP / sum_ind
-        nTN = (n - sum_ind) - nFP
-        FP = nFP / (n - sum_ind)
+        nTN = sum_not_ind - nFP                 # sum(1 - ind) - nFP, :93
+        FP = nFP / sum_not_ind
         Qd = 1 - Q
         k10 = (TP - Q) / Qd
         k00 = (1 - FP - Qd) / Q

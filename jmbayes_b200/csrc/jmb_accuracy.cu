@@ -109,7 +109,7 @@ __global__ void prederr_terms_kernel(int loss, int n_alive, const double* __rest
 }
 
 // rocJM: thread k of a CTA owns threshold k and walks the CTA's chunk of subjects (staged in shared memory) in order;
-// partials [CTA][n_thr][3] (+ the chunk's sum(ind) in slot [CTA][n_thr][0]) are combined in CTA order by colsum_kernel
+// partials [CTA][n_thr][3] (+ the chunk's sum(ind), sum(1 - ind) in slots [CTA][n_thr][0..1]) are combined in CTA order by colsum_kernel
 constexpr int kRocThreads = 128, kRocChunk = 1024;
 __global__ void __launch_bounds__(kRocThreads)
 roc_sums_kernel(int n, const double* __restrict__ Time, const double* __restrict__ event, double Thoriz, const double* __restrict__ pi,
@@ -134,7 +134,9 @@ roc_sums_kernel(int n, const double* __restrict__ Time, const double* __restrict
                 tp += lt * s_ind[e]; fp += lt * (1.0 - s_ind[e]); q += lt;
             }
         } else {
-            for (int e = 0; e < cnt; ++e) tp += s_ind[e];                                        // sum(ind) of the chunk
+            // sum(ind) and sum(1 - ind) of the chunk, summed in the order of nTP / nFP so that nFN = sum(ind) - nTP and
+            // nTN = sum(1 - ind) - nFP (R/rocJM.mvJMbayes.R:90,93) cancel exactly where every probability is below the threshold
+            for (int e = 0; e < cnt; ++e) { tp += s_ind[e]; fp += 1.0 - s_ind[e]; }
         }
         partials[row + (size_t)k * 3] = tp; partials[row + (size_t)k * 3 + 1] = fp; partials[row + (size_t)k * 3 + 2] = q;
     }
@@ -237,6 +239,6 @@ extern "C" int jmb_rocJM_sums(int device, int32_t n, const double* Time, const d
     std::vector<double> h(cols);
     CUA(cudaMemcpy(h.data(), res.p, sizeof(double) * cols, cudaMemcpyDeviceToHost));
     for (int k = 0; k < n_thr; ++k) { nTP[k] = h[(size_t)k * 3]; nFP[k] = h[(size_t)k * 3 + 1]; Q[k] = h[(size_t)k * 3 + 2] / n; }
-    *sum_ind = h[(size_t)n_thr * 3];
+    sum_ind[0] = h[(size_t)n_thr * 3]; sum_ind[1] = h[(size_t)n_thr * 3 + 1];
     return 0;
 }

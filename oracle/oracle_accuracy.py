@@ -44,6 +44,18 @@ def prederrJM_sum(S_alive, S_dead, S_cens, w_cens, nr, lossFun="square"):
     return float(np.nansum(terms) / nr)
 
 
+def _r_sum(x, axis=None):
+    """R's sum() / colSums() / mean(): one sequential pass in subject order with an extended-precision (long double)
+    accumulator, rounded to double at the end (R src/main/summary.c rsum(), src/main/array.c do_colsum(); R's own code,
+    not under /root/reference).  NumPy's pairwise np.sum() differs from it in the last bits, which matters where the
+    reference subtracts two sums of the same terms (nFN, nTN are exactly 0 in R where every probability is below the
+    threshold)."""
+    x = np.asarray(x, dtype=np.float64)
+    if axis is None:
+        return np.float64(np.cumsum(x.ravel(), dtype=np.longdouble)[-1]) if x.size else np.float64(0.0)
+    return np.cumsum(x, axis=axis, dtype=np.longdouble).take(-1, axis=axis).astype(np.float64)
+
+
 def rocJM(Time, event, Thoriz, pi_u_t, pi2):
     """R/rocJM.mvJMbayes.R:68-105 on per-subject vectors, with the n x 101 outer() matrix as there."""
     Time, event, pi, pi2 = (np.asarray(x, dtype=np.float64) for x in (Time, event, pi_u_t, pi2))
@@ -54,17 +66,17 @@ def rocJM(Time, event, Thoriz, pi_u_t, pi2):
     thrs = np.linspace(0.0, 1.0, 101)                                 # :88
     with np.errstate(all="ignore"):
         lt = np.where(np.isnan(pi)[:, None], np.nan, (pi[:, None] < thrs[None, :]).astype(np.float64))   # outer(pi.u.t, thrs, "<")
-        nTP = np.sum(lt * ind[:, None], axis=0)                       # :89
-        nFN = np.sum(ind) - nTP
-        TP = nTP / np.sum(ind)
-        nFP = np.sum(lt * (1 - ind)[:, None], axis=0)                 # :92
-        nTN = np.sum(1 - ind) - nFP
-        FP = nFP / np.sum(1 - ind)
-        Q = np.mean(lt, axis=0)                                       # :95
+        nTP = _r_sum(lt * ind[:, None], axis=0)                       # :89
+        nFN = _r_sum(ind) - nTP
+        TP = nTP / _r_sum(ind)
+        nFP = _r_sum(lt * (1 - ind)[:, None], axis=0)                 # :92
+        nTN = _r_sum(1 - ind) - nFP
+        FP = nFP / _r_sum(1 - ind)
+        Q = _r_sum(lt, axis=0) / lt.shape[0]                          # :95
         Qd = 1 - Q
         k10 = (TP - Q) / Qd
         k00 = (1 - FP - Qd) / Q
-        P = np.mean(ind)
+        P = _r_sum(ind) / ind.size
         k05 = (P * Qd * k10 + (1 - P) * Q * k00) / (P * Qd + (1 - P) * Q)
         f1 = 2 * nTP / (2 * nTP + nFN + nFP)
         youden = TP - FP

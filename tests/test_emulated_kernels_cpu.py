@@ -155,7 +155,7 @@ def test_emulated_accuracy_sums_match_restated_loops(emu, n, seed, na):
         assert np.isclose(accuracy.prederrJM_sum(a, d, cc, w, 700, loss), oa.prederrJM_sum(a, d, cc, w, 700, loss), rtol=1e-12)
 
 
-@pytest.mark.parametrize("n,seed,na", [(1, 1, 0.0), (700, 2, 0.0), (2500, 3, 0.0), (300, 4, 0.05)])
+@pytest.mark.parametrize("n,seed,na", [(1, 1, 0.0), (700, 2, 0.0), (2500, 3, 0.0), (300, 4, 0.05), (50_000, 3, 0.0)])
 def test_emulated_roc_sums_match_restated_outer_product(emu, n, seed, na):
     from jmbayes_b200 import accuracy
     from oracle import oracle_accuracy as oa

@@ -1,16 +1,12 @@
 """aucJM / prederrJM sums on the device (include/jmb200_accuracy.h) against the line-by-line restatement and through
 size-independent properties at full size.  Sums of doubles in a different (fixed) order: 1e-11 relative.
-
-STATUS: written after round 1's GPU minutes were spent; compiled for sm_100a but not yet run on a B200, hence
-xfail(strict=False) (XPASS when right).  The same kernels pass on CPU threads
-(tests/test_emulated_kernels_cpu.py).  Remove the marker after the first green run."""
+"""
 import numpy as np
 import pytest
 
 from oracle import oracle_accuracy as oa
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="accuracy kernels not yet run on a B200 (round-1 GPU budget spent)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")

@@ -2,12 +2,6 @@
 golden vectors and a size-independent property.  Tolerances as in test_gpu_parity.py (1e-10 relative on the pieces of
 the b-step target against the exact-rowsum oracle).
 
-STATUS: this path (jmb_step_kernel<G, true>, the per-stratum tau_Bs_gammas draws of the finalize kernel, the packer for
-several transition rows per subject) was written after round 1's GPU minutes were spent: it is compiled for sm_100a and
-checked on the CPU side (tests/test_multistate_cpu.py), but had not been run on a B200 when it was committed.  The
-tests are therefore marked xfail(strict=False): they report XPASS when the path is right and cannot hide a regression
-of anything else (this file sorts last).  The same kernels pass on CPU threads
-(tests/test_emulated_kernels_cpu.py).  Remove the marker after the first green run.
 """
 import importlib.util
 import os
@@ -17,8 +11,7 @@ import pytest
 
 from jmbayes_b200.cohorts import make_cohort, make_multistate_cohort
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="multi-state CUDA path not yet run on a B200 (round-1 GPU budget spent)")]
+pytestmark = [pytest.mark.gpu]
 RTOL = 1e-10
 
 HERE = os.path.dirname(os.path.abspath(__file__))
