@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--workload", default="config4_shard", choices=sorted(WORKLOADS))
     ap.add_argument("--n-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded-chain parity check that precedes the timing")
     ap.add_argument("--chains", type=int, default=4, help="chains in flight for the extra multi_chain measurement (0: skip)")
     return ap.parse_args()
 
@@ -197,6 +198,49 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
+def _sharded_parity(api, dist, world, rank, local, n=2000, iters=40):
+    """Correctness of the N-rank path, checked on the device before anything is timed: a 2 000-subject config-4 cohort
+    sharded over the ranks must walk the chain a single rank walks (same accept decisions on every rank) and the
+    restated reference (oracle, used as the checker only)."""
+    from jmbayes_b200.cohorts import make_cohort
+    from jmbayes_b200.sharding import shard_cohort
+    c = make_cohort("config4", n=n, seed=77)
+    ctl = dict(c["control"]); ctl.update(n_burnin=iters - 10, n_iter=10, n_block=10, n_thin=5)
+    sh = shard_cohort(c, rank, world) if world > 1 else dict(c, subject_offset=0)
+    with api.Fit(sh["Data"], sh["Covs"]["b"], c["interval_cens"], device=local, subject_offset=sh["subject_offset"]) as f:
+        if world > 1:
+            api.connect_ranks(f, world, rank, dist)
+        f.set_draw(sh["Data"])
+        r = f.lap_rwm_C(sh["inits"], sh["priors"], sh["scales"], sh["Covs"], ctl)
+    mine = (int(sh["subject_offset"]), r["mcmc"]["b"], r["extras"]["accept_b"], r["extras"]["trace_surv"], r["mcmc"]["alphas"])
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    out = None
+    if rank == 0:
+        parts.sort(key=lambda x: x[0])
+        b = np.concatenate([x[1] for x in parts], axis=0)
+        acc = np.concatenate([x[2] for x in parts])
+        same_decisions = all(np.array_equal(x[3], parts[0][3]) and np.array_equal(x[4], parts[0][4]) for x in parts)
+        rel = lambda u, v: float(np.max(np.abs(u - v) / np.maximum(np.abs(v), 1e-12)))  # noqa: E731
+        if world > 1:
+            one = api.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"], device=local)
+        else:
+            one = r
+        from oracle import oracle
+        oracle.build(); oracle.set_rowsum_mode(1)
+        orc = oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"])
+        out = {"ranks": world, "subjects": n, "iterations": iters,
+               "max_rel_vs_single_rank": max(rel(b, one["mcmc"]["b"]), rel(parts[0][3], one["extras"]["trace_surv"])),
+               "max_rel_vs_oracle": max(rel(b, orc["mcmc"]["b"]), rel(parts[0][3], orc["extras"]["trace_surv"])),
+               "identical_accepts": bool(np.array_equal(acc, one["extras"]["accept_b"]) and np.array_equal(acc, orc["extras"]["accept_b"])
+                                         and same_decisions)}
+        if not (out["identical_accepts"] and out["max_rel_vs_single_rank"] <= 1e-9 and out["max_rel_vs_oracle"] <= 1e-9):
+            raise RuntimeError(f"sharded chain differs from the single-rank chain / the oracle: {out}")
+    return out
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -214,6 +258,8 @@ def run_cuda(args):
     if not torch.cuda.is_available():
         raise RuntimeError("no CUDA device: the hot path has no CPU fallback")
 
+    parity = None if args.no_parity else _sharded_parity(api, dist, world, rank, local)
+
     cfg, n_default = WORKLOADS[args.workload]
     n = args.n_per_gpu or n_default
     n_total = n * world
@@ -225,7 +271,11 @@ def run_cuda(args):
         api.connect_ranks(fit, world, rank, dist)
     info = fit.layout_info()
     ctl = dict(c["control"])
-    total_needed = args.warmup + args.steps
+    n_block = int(ctl["n_block"])
+    # the timed window must hold its share of the per-block work (scale adaptation at the block end, the draw kernels):
+    # with fewer steps than a block the window is centred on a block end
+    preroll = max(0, n_block - args.warmup - args.steps // 2) if args.steps < n_block else 0
+    total_needed = preroll + args.warmup + args.steps
     ctl.update(n_burnin=max(total_needed * 2, 100), n_iter=50, n_thin=50)   # never reaches a kept iteration
     fit.set_draw(Data)
 
@@ -235,18 +285,24 @@ def run_cuda(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident timing: K iterations, inputs in HBM, CUDA events on the library's stream ----
-    fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
-    fit.chain_iterate(args.warmup)
-    barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local)          # runs from before the warm-up to the end of the last timed region (e2e)
     if rank == 0:
         sampler.start()
-    l0 = fit.launch_count()
-    ms, _ = fit.chain_iterate(args.steps)
-    l1 = fit.launch_count()
+
+    # ---- device-resident timing: K iterations, inputs in HBM, CUDA events on the library's stream ----
+    # The last LEAD warm-up iterations are enqueued in the same call as the K timed ones: on N > 1 ranks the start event then
+    # follows their all-reduce on the device, so the ranks' clocks start together (a host barrier leaves them hundreds of
+    # microseconds apart, which a 20-step window would count as iteration time).  barrier + synchronize on both sides stay.
+    lead = min(2, args.warmup)
+    fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    if preroll:
+        fit.chain_iterate(preroll)
+    if args.warmup - lead > 0:
+        fit.chain_iterate(args.warmup - lead)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    ms, _ = fit.chain_iterate(args.steps, lead=lead)
+    launches = fit.launch_count_timed()
+    barrier()
     fit.chain_end(fetch=False)
     t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
@@ -257,7 +313,7 @@ def run_cuda(args):
     # ---- per-launch duration of the step kernel (events around every launch) ----
     fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
     fit.chain_iterate(args.warmup)
-    ksteps = min(args.steps, 100)
+    ksteps = min(max(args.steps, 20), 100)
     _, kms = fit.chain_iterate(ksteps, time_kernels=True)
     fit.chain_end(fetch=False)
     k_ms = kms / ksteps
@@ -285,50 +341,85 @@ def run_cuda(args):
                  "ms_per_step_all_chains": float(tm.item()) / args.steps,
                  "what": "independent chains (draws) of the same fit advanced together on their own streams"}
 
-    # ---- end to end through the public API with host buffers: per-draw step (betas -> device Xbetas_calc),
-    #      chain_begin (H2D of b / scales / params), K iterations, chain_end (D2H of outputs).  The fixed-effects
-    #      designs are uploaded once per fit (like jmb_create), outside the timed region. ----
+    # ---- end to end through the public API with host buffers: one chain of the reference's own length
+    #      (n_burnin = 1000, n_iter = 300, n_block = 50: R/mvJointModelBayes.R:8-12) per call = the per-draw step
+    #      (betas -> device Xbetas_calc), chain_begin (H2D of b / scales / parameters from host memory), 1 300
+    #      iterations, chain_end (D2H of the kept b, parameters, scales).  The fixed-effects designs are uploaded once
+    #      per fit (like jmb_create), outside the timed region.  One untimed warm call, then best of three; the chain
+    #      length does not depend on --steps. ----
     ctl_e = dict(c["control"])
-    ctl_e.update(n_burnin=max(args.steps - 50, 0), n_iter=min(50, args.steps), n_thin=min(50, args.steps), n_block=min(50, max(1, args.steps)))
     e2e_total = -(-(ctl_e["n_burnin"] + ctl_e["n_iter"]) // ctl_e["n_block"]) * ctl_e["n_block"]
     fit.set_xdesigns(Data)
-    barrier()
-    t0 = time.perf_counter()
-    fit.set_draw_betas(Data["betas"], Data["sigmas"], Data["invD"])
-    ta_ = time.perf_counter()
-    fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl_e)
-    tb_ = time.perf_counter()
-    fit.chain_iterate(e2e_total)
-    tc_ = time.perf_counter()
-    res = fit.chain_end()
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    print(f"[rank {rank}] e2e phases: set_draw_betas {ta_ - t0:.3f}s chain_begin {tb_ - ta_:.3f}s iterate {tc_ - tb_:.3f}s chain_end {t1 - tc_:.3f}s",
-          file=sys.stderr, flush=True)
-    te = torch.tensor([t1 - t0], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n_total * e2e_total / float(te.item())
+
+    def e2e_call():
+        barrier()
+        t0 = time.perf_counter()
+        fit.set_draw_betas(Data["betas"], Data["sigmas"], Data["invD"])
+        ta_ = time.perf_counter()
+        fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl_e)
+        tb_ = time.perf_counter()
+        fit.chain_iterate(e2e_total)
+        tc_ = time.perf_counter()
+        res_ = fit.chain_end()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        te = torch.tensor([t1 - t0], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item()), (ta_ - t0, tb_ - ta_, tc_ - tb_, t1 - tc_), res_
+
+    ctl_w = dict(ctl_e); ctl_w.update(n_burnin=ctl_e["n_block"], n_iter=ctl_e["n_block"], n_thin=ctl_e["n_block"])
+    fit.set_draw_betas(Data["betas"], Data["sigmas"], Data["invD"])          # warm call: allocations, first-touch of the staging buffers
+    fit.chain_begin(c["inits"], c["priors"], c["scales"], c["Covs"], ctl_w)
+    fit.chain_iterate(2 * ctl_e["n_block"])
+    fit.chain_end()
+    e2e_runs, res = [], None
+    for _ in range(3):
+        dt_, ph_, res = e2e_call()
+        e2e_runs.append(dt_)
+        print(f"[rank {rank}] e2e phases: set_draw_betas {ph_[0] * 1e3:.2f} ms chain_begin {ph_[1] * 1e3:.2f} ms iterate {ph_[2] * 1e3:.1f} ms "
+              f"chain_end {ph_[3] * 1e3:.2f} ms", file=sys.stderr, flush=True)
+    e2e_value = n_total * e2e_total / min(e2e_runs)
+    clocks = sampler.stop() if rank == 0 else None
     h2d = 8 * sum(len(b) for b in Data["betas"]) + 8 * (fit.q * fit.q + fit.O) + 8 * n * (fit.q + 1)
     d2h = sum(v.nbytes for v in res["mcmc"].values()) + res["scales"]["sigma"]["b"].nbytes + 8 * n + 16 * e2e_total
 
-    traffic, traffic_src = None, None
-    try:   # DRAM bytes of the step kernel from the committed ncu --set full capture (per launch)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        if tj and info["kernel"].startswith("static-tma"):
-            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * (n / tj["subjects"])
-            traffic_src = tj["source"]
+    # ---- roofline of the step kernel: bytes that really cross HBM (the record layout's compulsory bytes, cross-checked
+    #      against ncu's dram__bytes of the same kernel) over the CUDA-event launch duration ----
+    prof, traffic, traffic_src = None, None, None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(info["kernel"])
+        if prof:
+            traffic = (prof["dram_bytes_read"] + prof["dram_bytes_write"]) * (n / prof["subjects"])
+            traffic_src = prof["source"]
     except Exception:
         pass
-    alg = ALG_BYTES[cfg]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg * n / (k_ms * 1e-3) / 1e9
-    moved = (info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"]) * n / (k_ms * 1e-3) / 1e9
+    layout_bytes = info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"]
+    achieved = layout_bytes * n / (k_ms * 1e-3) / 1e9
+    alg8d = ALG_BYTES[cfg]
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": info["kernel"], "kernel_ms": k_ms,
+            "alg_bytes_per_subject_iteration": layout_bytes,
+            "alg_source": "bytes of the fused design (DESIGN.md section 2): design record + per-draw record read once, state read + "
+                          "written, b-step draws written once per chunk and read once; Wlong(s) and the cached bases never exist",
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+            "whole_step_gbs": layout_bytes * n / (ms_max / args.steps * 1e-3) / 1e9,
+            "survey_8d": {"alg_bytes_per_subject_iteration": alg8d, "gbs": alg8d * n / (k_ms * 1e-3) / 1e9,
+                          "note": "SURVEY.md 8(d) compact layout that materialises Wlong(s) and the cached bases; the fused kernel does not "
+                                  "move these bytes, so this is NOT a fraction of the roofline (it can exceed the peak)"}}
+    if prof and "inst_per_subject" in prof:
+        sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+        sms = 148
+        roof["floors_us"] = {"dram": layout_bytes * n / (peak * 1e9) * 1e6,
+                             "issue": prof["inst_per_subject"] * n / (4 * sms * sm_hz) * 1e6,
+                             "fp64": 2.0 * prof.get("fp64_inst_per_subject", 0.0) * n / (4 * sms * sm_hz) * 1e6,
+                             "source": traffic_src}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -337,18 +428,19 @@ def run_cuda(args):
         "config": {"workload": args.workload, "cohort": cfg, "subjects_per_gpu": n, "subjects_total": n_total,
                    "outcomes": fit.O, "q": fit.q, "terms": fit.T, "K": fit.K, "interval_cens": bool(c["interval_cens"]),
                    "parallelism": f"subject-shards x{world}", "chains_per_launch": 1,
-                   "l2": "per-iteration working set %.2f GB per GPU >> 126 MB L2 (inputs larger than L2)" % ((info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"]) * n / 1e9)},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": traffic_src, "kernel": info["kernel"], "kernel_ms": k_ms,
-                     "alg_bytes_per_subject_iteration": alg, "alg_source": "SURVEY.md 8(d)",
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                     "layout_bytes_per_subject_iteration": info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"],
-                     "achieved_layout_gbs": moved, "frac_layout": moved / peak},
+                   "window": f"iterations {preroll + args.warmup}..{preroll + args.warmup + args.steps - 1} of a chain with n_block = {n_block}"
+                             + (" (centred on a block end: holds the scale adaptation and its share of the draw kernels)" if preroll else ""),
+                   "l2": "per-iteration working set %.2f GB per GPU >> 126 MB L2 (inputs larger than L2)" % (layout_bytes * n / 1e9)},
+        "roofline": roof,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_total, "d2h_bytes_per_step": d2h / e2e_total,
-                "what": f"set_draw_betas (device Xbetas_calc) + lap_rwm_C({e2e_total} iterations) through the C ABI with host buffers, wall clock"},
-        "gpu_launches": int(l1 - l0),
+                "runs_s": e2e_runs, "iterations_per_call": e2e_total,
+                "what": f"set_draw_betas (device Xbetas_calc) + lap_rwm_C({e2e_total} iterations: the reference's n_burnin = 1000, n_iter = 300, "
+                        "n_block = 50) through the C ABI with host buffers, wall clock, max over ranks; one warm call, best of 3"},
+        "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if parity is not None:
+        line["sharded_parity"] = parity
     if multi:
         line["multi_chain"] = multi
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -336,8 +336,12 @@ int jmb_p2p_attach(jmb_handle h, int nranks, int rank, const char* handles);
 int jmb_chain_begin(jmb_handle h, const jmb_priors* priors, const jmb_control* control,
                     const jmb_chain_in* in);
 int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, float* step_kernel_ms);
+/* Same, with `lead` untimed iterations enqueued right before the timed ones: on several ranks the timed window then
+ * starts after the all-reduce of the last lead iteration (a device-side rendezvous), not after a host barrier. */
+int jmb_chain_iterate_after(jmb_handle h, int lead, int iters, float* elapsed_ms);
 int jmb_chain_end(jmb_handle h, jmb_chain_out* out);
 int jmb_launch_count(jmb_handle h, int64_t* launches);
+int jmb_launch_count_timed(jmb_handle h, int64_t* launches);   /* kernels launched between the two events of the last jmb_chain_iterate[_after] */
 
 /* Several chains (mvglmer draws) of one fit in flight on one device - the reference's chain
  * parallelism (foreach over blocks of draws, R/mvJointModelBayes.R:860-905).  jmb_chain_slots makes

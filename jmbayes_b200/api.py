@@ -57,6 +57,7 @@ def _bind(L):
     L.jmb_chain_begin.argtypes = [vp, C.POINTER(_abi.JmbPriors), C.POINTER(_abi.JmbControl),
                                   C.POINTER(_abi.JmbChainIn)]
     L.jmb_chain_iterate.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.jmb_chain_iterate_after.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.jmb_chain_end.argtypes = [vp, C.POINTER(_abi.JmbChainOut)]
     L.jmb_eval_logpost_re.argtypes = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_double_p,
                                       _abi.c_double_p, C.POINTER(_abi.JmbEvalOut)]
@@ -78,6 +79,7 @@ def _bind(L):
                                   C.c_double, C.c_int, C.POINTER(_abi.JmbMllOut)]
     L.jmb_layout_info.argtypes = [vp, _abi.c_double_p, _abi.c_double_p, _abi.c_int32_p, _abi.c_int32_p]
     L.jmb_launch_count.argtypes = [vp, _abi.c_int64_p]
+    L.jmb_launch_count_timed.argtypes = [vp, _abi.c_int64_p]
     L.jmb_comm_unique_id.argtypes = [C.c_char_p]
     L.jmb_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.jmb_p2p_export.argtypes = [vp, C.c_int, C.c_char_p]
@@ -199,9 +201,13 @@ class Fit:
         _check(lib().jmb_chain_begin(self._h, C.byref(pr), C.byref(ct), C.byref(ci)))
         del keep
 
-    def chain_iterate(self, iters: int, time_kernels: bool = False):
-        """Run ``iters`` iterations on the device; returns (loop ms, step-kernel ms or None)."""
+    def chain_iterate(self, iters: int, time_kernels: bool = False, lead: int = 0):
+        """Run ``iters`` iterations on the device; returns (loop ms, step-kernel ms or None).  ``lead`` untimed iterations are
+        enqueued in the same call right before the timed ones (multi-rank runs: the clock starts after their exchange)."""
         ms, kms = C.c_float(0), C.c_float(0)
+        if lead:
+            _check(lib().jmb_chain_iterate_after(self._h, int(lead), int(iters), C.byref(ms)))
+            return ms.value, None
         _check(lib().jmb_chain_iterate(self._h, int(iters), C.byref(ms),
                                        C.byref(kms) if time_kernels else None))
         return ms.value, (kms.value if time_kernels else None)
@@ -356,6 +362,11 @@ class Fit:
         return dict(shared_bytes_per_subject=sb.value, chain_bytes_per_subject=cb.value,
                     w1_band=wb.value, group_lanes=g.value,
                     kernel=lib().jmb_kernel_name(self._h).decode())
+
+    def launch_count_timed(self) -> int:
+        c = C.c_int64(0)
+        _check(lib().jmb_launch_count_timed(self._h, C.byref(c)))
+        return c.value
 
     def launch_count(self) -> int:
         c = C.c_int64(0)

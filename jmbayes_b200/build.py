@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 # translation units and what each one includes
 UNITS = {
-    "jmb200.cu": ["jmb_kernels.cuh", "jmb_device.cuh", "jmb_model.h", "jmb_step_static.cuh", "jmb_host.h"],
+    "jmb200.cu": ["jmb_kernels.cuh", "jmb_device.cuh", "jmb_model.h", "jmb_step_static.cuh", "jmb_step_rows.cuh", "jmb_host.h"],
     "jmb_survfit.cu": ["jmb_survfit.cuh", "jmb_device.cuh", "jmb_model.h", "jmb_host.h"],
     "jmb_laplace.cu": ["jmb_host.h"],
     "jmb_summaries.cu": ["jmb_host.h"],

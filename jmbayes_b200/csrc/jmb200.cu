@@ -17,6 +17,7 @@
 
 #include "jmb_host.h"
 #include "jmb_step_static.cuh"
+#include "jmb_step_rows.cuh"
 
 using namespace jmb;
 
@@ -131,18 +132,21 @@ struct jmb_handle_s {
     bool wlong_set = false;
     // launch configuration
     int grid = 0, subjects_per_cta = 0, smem_bytes = 0;
-    long long launches = 0;
+    long long launches = 0, launches_at_ev0 = 0, launches_timed = 0;
     // fixed-effects designs for Xbetas_calc on the device (jmb_set_xdesigns)
     double* d_xrec = nullptr; long long* d_xoff = nullptr; double* d_betas = nullptr;
     XbDesc xd{}; int n_betas = 0; bool xdesigns_set = false;
     // step kernel chosen for this model: a precompiled static specialisation or the generic one
     void (*static_kernel)(int, ParamLayout, ChainConst, StepArgs) = nullptr;
     void (*tma_kernel)(int, ParamLayout, ChainConst, StepArgs, TmaArgs) = nullptr;
+    void (*rows_kernel)(int, ParamLayout, ChainConst, StepArgs, RowsArgs) = nullptr;
     const char* kernel_name = "generic";
     std::string kernel_label;
     int static_smem = 0, tma_smem = 0, tma_grid = 0, num_sms = 148;
+    int rows_smem = 0, rows_grid = 0, rows_G = 0; bool rows_early = false;
     TmaArgs ta{};
-    int kernel_mode = 0;            // 0 generic, 1 static direct, 2 static TMA-staged
+    RowsArgs ra{};
+    int kernel_mode = 0;            // 0 generic, 1 static direct, 2 static TMA-staged, 3 static row-strided groups (default)
     int select_kernel();
     int add_slot();
     // multi-GPU
@@ -155,8 +159,25 @@ struct jmb_handle_s {
     bool p2p = false;
 };
 
+template <class Spec, bool EARLY>
+static void (*rows_kernel_of(int G))(int, ParamLayout, ChainConst, StepArgs, RowsArgs) {
+    switch (G) {
+        case 2: return jmb_step_rows<Spec, 2, EARLY>;
+        case 4: return jmb_step_rows<Spec, 4, EARLY>;
+        case 8: return jmb_step_rows<Spec, 8, EARLY>;
+        case 16: return jmb_step_rows<Spec, 16, EARLY>;
+    }
+    return nullptr;
+}
+static void (*pick_rows_kernel(const ModelDesc& md, int G, bool early))(int, ParamLayout, ChainConst, StepArgs, RowsArgs) {
+    if (same_desc(md, SpecValueGaussian::d)) return early ? rows_kernel_of<SpecValueGaussian, true>(G) : rows_kernel_of<SpecValueGaussian, false>(G);
+    if (same_desc(md, SpecThreeOutcomes::d)) return early ? rows_kernel_of<SpecThreeOutcomes, true>(G) : rows_kernel_of<SpecThreeOutcomes, false>(G);
+    if (same_desc(md, SpecThreeOutcomesIC::d)) return early ? rows_kernel_of<SpecThreeOutcomesIC, true>(G) : rows_kernel_of<SpecThreeOutcomesIC, false>(G);
+    return nullptr;
+}
+
 int jmb_handle_s::select_kernel() {
-    static_kernel = nullptr; tma_kernel = nullptr; kernel_name = "generic"; kernel_mode = 0;
+    static_kernel = nullptr; tma_kernel = nullptr; rows_kernel = nullptr; kernel_name = "generic"; kernel_mode = 0;
     const ModelDesc& md = mm.d;
     if (same_desc(md, SpecValueGaussian::d)) {
         static_kernel = jmb_step_static<SpecValueGaussian>; tma_kernel = jmb_step_tma<SpecValueGaussian>; kernel_name = "value_gaussian";
@@ -206,13 +227,75 @@ int jmb_handle_s::select_kernel() {
             kernel_mode = 2;
         }
     }
-    const char* env = getenv("JMB_KERNEL");   // generic | direct | tma : force a slower variant (tests, A/B runs)
+    // row-strided groups (jmb_step_rows.cuh): G lanes per subject, 32 / G subjects per warp step; the default
+    if (static_kernel) {
+        // group width and early-stage staging per model shape, from the sweeps in profiles/r2_rows_kernel.md
+        int G = (md.S == 2) ? 8 : (md.O > 1 ? 16 : 4);
+        bool early = (md.S == 1 && md.O > 1);
+        if (const char* g = getenv("JMB_ROWS_G")) G = atoi(g);
+        if (G != 2 && G != 4 && G != 8 && G != 16) G = 8;
+        if (const char* e = getenv("JMB_ROWS_EARLY")) early = atoi(e) != 0;
+        rows_kernel = pick_rows_kernel(md, G, early);
+        rows_early = early;
+        if (rows_kernel) {
+            rows_G = G;
+            const int spw = 32 / G;
+            // shared memory: parameter pairs | invD | per-group partial sums | early-stage barriers | hazard-row ring | early stages
+            int nv = 2 + md.WB + (md.w2_const ? 0 : md.p);
+            for (int t = 0; t < md.T; ++t) nv += 1 + (md.rt[t] - md.zz_ones0[t]) + (md.u_ones[t] ? 0 : md.ut[t]);
+            const long long fixed_b = 8LL * (2 * mm.P + (md.q * md.q + 1) / 2 * 2 + (kRowsWarps * spw * 3 + 1) / 2 * 2) + 8LL * kRowsWarps +
+                                      8LL * kRowsWarps * JMB_ROWS_RING * nv * 32;
+            ra.cap_dl = 0; ra.cap_cl = 0;
+            if (early) {
+                // early stage of a subject: head | state | draws | visit rows of the design and of the per-draw record; the
+                // capacity covers the longest visit segment unless that would not leave room for kRowsCtas CTAs per SM
+                // (subjects beyond the capacity read their visit rows in place)
+                long long max_dl = 0, max_cl = 0;
+                for (int i = 0; i < n; ++i) {
+                    max_dl = std::max(max_dl, doff[i + 1] - doff[i] - mm.L.o_long);
+                    max_cl = std::max(max_cl, coff[i + 1] - coff[i] - mm.L.c_long);
+                }
+                const int RSs = (md.q + 2) / 2 * 2;
+                const long long budget = ((222LL * 1024) / kRowsCtas - fixed_b) / 8 / ((long long)kRowsWarps * spw) - (kRowsHdr + mm.L.state_stride + RSs);
+                long long cd = (max_dl + 1) / 2 * 2, cc_ = (max_cl + 1) / 2 * 2;
+                if (cd + cc_ > budget) {
+                    const double f = (double)std::max<long long>(budget, 0) / (double)(cd + cc_);
+                    cd = (long long)(cd * f) / 2 * 2; cc_ = (long long)(cc_ * f) / 2 * 2;
+                }
+                ra.cap_dl = (int)std::max<long long>(cd, 0); ra.cap_cl = (int)std::max<long long>(cc_, 0);
+                const int RSd = kRowsHdr + mm.L.state_stride + RSs + ra.cap_dl + ra.cap_cl;
+                rows_smem = (int)(fixed_b + 8LL * kRowsWarps * spw * RSd);
+            } else {
+                rows_smem = (int)fixed_b;
+            }
+            if (rows_smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute((const void*)rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem);
+                if (e != cudaSuccess) { g_err = std::string("cudaFuncSetAttribute(rows): ") + cudaGetErrorString(e); return 1; }
+            }
+            const long long total_steps = ((long long)n + spw - 1) / spw;
+            int waves = 1;                                   // persistent: one resident wave of CTAs
+            if (const char* w = getenv("JMB_ROWS_WAVES")) waves = std::max(1, atoi(w));
+            const long long ctas = std::max<long long>(1, std::min<long long>((total_steps + kRowsWarps - 1) / kRowsWarps, (long long)kRowsCtas * num_sms * waves));
+            ra.steps_per_cta = (int)((total_steps + ctas - 1) / ctas);
+            rows_grid = (int)((total_steps + ra.steps_per_cta - 1) / ra.steps_per_cta);
+            ra.prefetch = 1;
+            if (const char* pf = getenv("JMB_ROWS_PREFETCH")) ra.prefetch = atoi(pf) ? 1 : 0;
+            kernel_mode = 3;
+        }
+    }
+    const char* env = getenv("JMB_KERNEL");   // generic | direct | tma | rows : force a variant (tests, A/B runs)
     if (env) {
         if (!strcmp(env, "generic")) kernel_mode = 0;
         else if (!strcmp(env, "direct") && static_kernel) kernel_mode = 1;
+        else if (!strcmp(env, "tma") && tma_kernel && tma_smem > 0) kernel_mode = 2;
     }
     if (getenv("JMB_FORCE_GENERIC") && getenv("JMB_FORCE_GENERIC")[0] == '1') kernel_mode = 0;
-    kernel_label = kernel_mode == 0 ? std::string("generic") : (kernel_mode == 1 ? std::string("static:") : std::string("static-tma:")) + (kernel_mode ? kernel_name : "");
+    switch (kernel_mode) {
+        case 0: kernel_label = "generic"; break;
+        case 1: kernel_label = std::string("static:") + kernel_name; break;
+        case 2: kernel_label = std::string("static-tma:") + kernel_name; break;
+        default: kernel_label = std::string("static-rows") + std::to_string(rows_G) + (rows_early ? "e:" : ":") + kernel_name; break;
+    }
     return 0;
 }
 
@@ -445,8 +528,8 @@ static int create_impl(const jmb_data* d, int device, jmb_handle* out, bool host
             dl += (long long)v * L.long_cols[k];
             cl += v;
         }
-        h->doff[i + 1] = h->doff[i] + ((dl + 1) / 2) * 2;
-        h->coff[i + 1] = h->coff[i] + ((cl + 1) / 2) * 2;
+        h->doff[i + 1] = h->doff[i] + ((dl + 3) / 4) * 4;       // records start on 32-byte sectors
+        h->coff[i + 1] = h->coff[i] + ((cl + 3) / 4) * 4;
     }
 
     // ---- pack the design records ----
@@ -576,7 +659,7 @@ static int create_impl(const jmb_data* d, int device, jmb_handle* out, bool host
         h->num_sms = prop.multiProcessorCount;
         if (h->select_kernel()) { std::string m_ = g_err; jmb_destroy(h); return fail(m_); }
     }
-    h->grid_cap = std::max(h->grid, h->tma_grid);
+    h->grid_cap = std::max(std::max(h->grid, h->tma_grid), h->rows_grid);
     if (h->add_slot()) { std::string m_ = g_err; jmb_destroy(h); return fail(m_); }   // chain slot 0
 #undef CUH
     *out = h;
@@ -833,7 +916,14 @@ static int launch_step(jmb_handle h, int mode) {
     a.n = h->n; a.subject_offset = h->subject_offset; a.mode = mode; a.subjects_per_cta = h->subjects_per_cta;
     a.rng = h->c->d_rng; a.rng_chunk = h->c->rng_chunk; a.rng_stride = h->rng_stride;
     a.trow = h->d_trow; a.eval_stride = std::max(h->n, h->nT);
-    if (mode == MODE_STEP && h->kernel_mode == 2) {
+    if (mode == MODE_STEP && h->kernel_mode == 3) {
+        if (pdl_enabled()) {
+            CU(launch_pdl(h->rows_kernel, dim3(h->rows_grid), dim3(kRowsThreads), (size_t)h->rows_smem, h->c->stream, h->mm.B, h->pl, h->c->cc, a, h->ra));
+        } else {
+            h->rows_kernel<<<h->rows_grid, kRowsThreads, h->rows_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a, h->ra);
+        }
+    }
+    else if (mode == MODE_STEP && h->kernel_mode == 2) {
         if (pdl_enabled()) {
             CU(launch_pdl(h->tma_kernel, dim3(h->tma_grid), dim3(kTmaThreads), (size_t)h->tma_smem, h->c->stream, h->mm.B, h->pl, h->c->cc, a, h->ta));
         } else {
@@ -859,7 +949,7 @@ static int launch_finalize(jmb_handle h, int phase) {
     FinalizeArgs a = h->c->fa;
     a.par = h->c->d_par; a.ctl = h->c->d_ctl; a.partials = h->c->d_partials; a.n_partials = h->grid;
     a.use_reduced = (h->nranks > 1) ? (h->p2p ? 2 : 1) : 0; a.phase = phase;
-    a.n_partials = (h->kernel_mode == 2) ? h->tma_grid : h->grid;
+    a.n_partials = (h->kernel_mode == 3) ? h->rows_grid : ((h->kernel_mode == 2) ? h->tma_grid : h->grid);
     a.wore = h->c->wore ? 1 : 0; a.sp_out = h->d_sp_out;
     if (a.wore) a.use_reduced = 3;                  // the data sums come from the survival-block kernels
     if (!a.wore && phase == 0 && h->nranks > 1 && h->p2p) {
@@ -1013,19 +1103,28 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
         h->launches += 1;
         CU(cudaGetLastError());
     }
-    {   // draws of the b-step: one buffer per chunk of iterations that divides n_block
-        size_t free_b = 0, total_b = 0;
-        CU(cudaMemGetInfo(&free_b, &total_b));
+    {   // draws of the b-step: one buffer per chunk of iterations that divides n_block.  Short chunks (<= 10 iterations by
+        // default, JMB_RNG_CHUNK overrides) keep the buffer small (80 MB per 125 000 subjects at q = 6) and spread the
+        // once-per-chunk kernel evenly over the iterations; the draws are keyed by (iteration, subject), so the chunk
+        // length never changes them.
         const size_t per_iter = (size_t)n * h->rng_stride * sizeof(double);
-        const size_t budget = std::max<size_t>(per_iter, std::min<size_t>(free_b / 4 + h->c->rng_capacity, (size_t)8 << 30));
-        int chunk = ct->n_block;
-        while (chunk > 1 && ((size_t)chunk * per_iter > budget || ct->n_block % chunk != 0)) --chunk;
-        h->c->rng_chunk = chunk;
+        int want = 10;
+        if (const char* e = getenv("JMB_RNG_CHUNK")) want = std::max(1, atoi(e));
+        int chunk = std::min(ct->n_block, want);
+        while (chunk > 1 && ct->n_block % chunk != 0) --chunk;
         if ((size_t)chunk * per_iter > h->c->rng_capacity) {
-            cudaFree(h->c->d_rng); h->c->d_rng = nullptr;
-            CU(cudaMalloc(&h->c->d_rng, (size_t)chunk * per_iter));
-            h->c->rng_capacity = (size_t)chunk * per_iter;
+            // growing the buffer is the only place the chain start touches the allocator (a warm chain start does not)
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            const size_t budget = std::max<size_t>(per_iter, std::min<size_t>(free_b / 4 + h->c->rng_capacity, (size_t)8 << 30));
+            while (chunk > 1 && ((size_t)chunk * per_iter > budget || ct->n_block % chunk != 0)) --chunk;
+            if ((size_t)chunk * per_iter > h->c->rng_capacity) {
+                cudaFree(h->c->d_rng); h->c->d_rng = nullptr;
+                CU(cudaMalloc(&h->c->d_rng, (size_t)chunk * per_iter));
+                h->c->rng_capacity = (size_t)chunk * per_iter;
+            }
         }
+        h->c->rng_chunk = chunk;
     }
     if (launch_finalize(h, 1)) return 1;            // Cholesky factors + proposal of iteration 0
     if (launch_step(h, MODE_INIT)) return 1;        // log_pyb / log_pb at the initial b (:619-621)
@@ -1083,13 +1182,29 @@ static int enqueue_iteration(jmb_handle h, float* kernel_ms) {
     return 0;
 }
 
+static int chain_iterate_impl(jmb_handle h, int lead, int iters, float* elapsed_ms, float* step_kernel_ms);
 extern "C" int jmb_chain_iterate(jmb_handle h, int iters, float* elapsed_ms, float* step_kernel_ms) {
+    return chain_iterate_impl(h, 0, iters, elapsed_ms, step_kernel_ms);
+}
+// `lead` untimed iterations enqueued in the same call right before the timed ones: with several ranks the start event then
+// follows the all-reduce of the last lead iteration on the device, so every rank's clock starts within the latency of that
+// exchange of the others' - a host-side barrier leaves the ranks hundreds of microseconds apart, which a short timed window
+// would otherwise count as iteration time.
+extern "C" int jmb_chain_iterate_after(jmb_handle h, int lead, int iters, float* elapsed_ms) {
+    return chain_iterate_impl(h, lead, iters, elapsed_ms, nullptr);
+}
+static int chain_iterate_impl(jmb_handle h, int lead, int iters, float* elapsed_ms, float* step_kernel_ms) {
     if (!h || !h->c->chain_open) return fail("jmb_chain_iterate: no open chain");
+    if (lead < 0 || iters < 0) return fail("jmb_chain_iterate: negative iteration count");
     CU(cudaSetDevice(h->device));
     float kms = 0.f;
+    for (int k = 0; k < lead; ++k)
+        if (enqueue_iteration(h, nullptr)) return 1;
     CU(cudaEventRecord(h->c->ev0, h->c->stream));
+    h->launches_at_ev0 = h->launches;
     for (int k = 0; k < iters; ++k)
         if (enqueue_iteration(h, step_kernel_ms ? &kms : nullptr)) return 1;
+    h->launches_timed = h->launches - h->launches_at_ev0;
     CU(cudaEventRecord(h->c->ev1, h->c->stream));
     CU(cudaEventSynchronize(h->c->ev1));
     if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, h->c->ev0, h->c->ev1));
@@ -1487,6 +1602,12 @@ extern "C" int jmb_param_dims(jmb_handle h, int32_t* n_Bs, int32_t* n_gammas, in
     if (n_Bs) *n_Bs = h->mm.B;
     if (n_gammas) *n_gammas = h->mm.d.p;
     if (n_alphas) *n_alphas = h->mm.d.A;
+    return 0;
+}
+
+extern "C" int jmb_launch_count_timed(jmb_handle h, int64_t* launches) {
+    if (!h || !launches) return fail("jmb_launch_count_timed: null argument");
+    *launches = h->launches_timed;
     return 0;
 }
 

@@ -69,7 +69,7 @@ JMB_HD constexpr RecordLayout make_layout(const ModelDesc& d) {
     int o = 1 + (d.O + 1) / 2;
     L.o_W2c = o;
     if (d.w2_const) o += d.p;
-    o = (o + 1) / 2 * 2;
+    o = (o + 3) / 4 * 4;            // hazard rows start on a 32-byte sector (records are 32-byte aligned too)
     L.o_Pw = o; o += L.RP;
     L.o_W1off = o; o += L.RP / 2;
     L.o_W1v = o; o += d.WB * L.RP;

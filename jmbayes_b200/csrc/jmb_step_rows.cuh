@@ -1,0 +1,504 @@
+// jmb_step_rows.cuh - row-strided step kernel (sm_100a), round 2.
+//
+// Same per-subject work as jmb_step_static / jmb_step_tma (one b-step + the subject's share of the survival
+// step, src/fast_LAPRWM.cpp:666-757) on the same records, but a subject is served by a group of G = 2..16
+// lanes (32 / G subjects per warp step) instead of one lane per hazard row:
+//   * lane l of a group walks the hazard rows l, l + G, l + 2G, ... (row 0 = event time, 1..K quadrature,
+//     K+1..2K lower-interval quadrature) and the visit rows l, l + G, ... of every outcome, keeps its own
+//     partial sums, and the group combines them with log2(G) xor-shuffles;
+//   * everything that is per subject and not per row (state, proposal, log p(b), censoring terms, accept,
+//     write-back) is executed once per warp for 32 / G subjects instead of once per subject.
+// With one lane per row (round 1) 1 100 warp instructions were issued per subject-iteration of config 4, most of
+// them replicated per-subject work and visit loops with 10 of 32 lanes active; here 480 (G = 4) .. 590 (G = 8)
+// (profiles/r2_rows_kernel.md).
+//
+// Memory pipeline (a warp step covers 32 / G whole records, 18 - 37 KB: too much to double-buffer per warp):
+//   * hazard rows (80 % of the bytes): a lane-private ring of JMB_ROWS_RING stages in shared memory, filled with
+//     cp.async (LDGSTS) RING - 1 row-loop trips ahead of their use.  Every lane copies and reads only its own
+//     slots, so no barrier is involved and nothing waits in the L2 for long;
+//   * "early" data of a step - record header, state, draws of the iteration, visit rows of every outcome and
+//     their per-draw linear predictors, about 1 kB per subject: one shared-memory stage per warp, filled for the
+//     warp's NEXT step by cp.async.bulk copies + an mbarrier (template parameter EARLY) as soon as the visit loops of the
+//     current step are done, i.e. a whole hazard loop ahead of its use.
+// An L2 prefetch of whole records one step ahead (cp.async.bulk.prefetch.L2) was measured first and evicts itself
+// (16 warps x 148 SMs x 37 KB = 87 MB in flight; DRAM reads 1.9x the compulsory bytes).
+//
+// The sums over quadrature rows need the proposed-parameter hazard at the accepted b, which is only known after
+// all rows have been visited: the row loop therefore accumulates it for both the old and the proposed b (three
+// exponentials per row instead of two) and selects after the accept decision.
+#pragma once
+#include "jmb_step_static.cuh"
+
+namespace jmb {
+
+struct RowsArgs {
+    int steps_per_cta;       // warp steps (of 32 / G subjects) owned by one CTA
+    int prefetch;            // EARLY = false only: 1 = L2 bulk prefetch of the next step's early data
+    int cap_dl, cap_cl;      // early stage: capacity (doubles) of the visit rows of the design / per-draw record of one subject
+};
+
+#ifndef JMB_ROWS_THREADS
+#define JMB_ROWS_THREADS 256
+#endif
+#ifndef JMB_ROWS_CTAS
+#define JMB_ROWS_CTAS 2
+#endif
+#ifndef JMB_ROWS_RING
+#define JMB_ROWS_RING 2
+#endif
+#ifndef JMB_EXP3
+#define JMB_EXP3 1
+#endif
+constexpr int kRowsThreads = JMB_ROWS_THREADS, kRowsCtas = JMB_ROWS_CTAS, kRowsWarps = JMB_ROWS_THREADS / 32;
+constexpr int kRowsHdr = 8;  // doubles of a record head that hold event, visit counts and the constant W2 row
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+#if !defined(JMB_EMU)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
+#if defined(JMB_EMU)
+    *dst = *src;
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async4(int* dst, const int* src) {
+#if defined(JMB_EMU)
+    *dst = *src;
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#if !defined(JMB_EMU)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#if !defined(JMB_EMU)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+// generic-proxy reads of a shared-memory stage must be ordered before the async-proxy (bulk copy) writes that re-fill it
+__device__ __forceinline__ void fence_proxy_async() {
+#if !defined(JMB_EMU)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
+// slots of one hazard row in the ring: band offset | WB band values | Pw | W2 columns | per term: XXbeta, stored ZZ, stored U
+template <class Spec>
+struct RowSlots {
+    static constexpr int nzz(int t) { return Spec::d.rt[t] - Spec::d.zz_ones0[t]; }
+    static constexpr int nu(int t) { return Spec::d.u_ones[t] ? 0 : Spec::d.ut[t]; }
+    static constexpr int term_base(int t) {
+        int b = 2 + Spec::d.WB + (Spec::d.w2_const ? 0 : Spec::d.p);
+        for (int k = 0; k < t; ++k) b += 1 + nzz(k) + nu(k);
+        return b;
+    }
+    static constexpr int NV = term_base(Spec::d.T);
+};
+
+// Three exponentials at once (the three hazard values of a quadrature row).  For |x| < 700 - every value a chain ever sees -
+// exp(x) = 2^n exp(r), n = rint(x log2 e), r = x - n ln 2 (two-term Cody-Waite reduction, |r| <= 0.347), exp(r) by the degree-13
+// Taylor polynomial (truncation 4e-18), 2^n added to the exponent field: 0.62 ulp worst case over [-700, 700] against the
+// correctly rounded value (measured on the host with the same arithmetic).  The three Horner chains are independent and share
+// their coefficients, which come from the constant bank (libm's exp materialises its 64-bit coefficients with two moves each,
+// per call).  Anything else (overflow, gradual underflow, NaN) goes through libm for all three.
+__constant__ double kExpTaylor[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                                      1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+__device__ __forceinline__ void exp3(const double x0, const double x1, const double x2, double& e0, double& e1, double& e2) {
+#if JMB_EXP3
+    if ((fabs(x0) < 700.0) && (fabs(x1) < 700.0) && (fabs(x2) < 700.0)) {
+        const double L2E = 1.44269504088896338700e+00, SH = 6755399441055744.0;
+        const double LN2H = 6.93147180559945286227e-01, LN2L = 2.31904681384629955842e-17;
+        const double t0 = fma(x0, L2E, SH), t1 = fma(x1, L2E, SH), t2 = fma(x2, L2E, SH);
+        const double n0 = t0 - SH, n1 = t1 - SH, n2 = t2 - SH;
+        double r0 = fma(n0, -LN2H, x0), r1 = fma(n1, -LN2H, x1), r2 = fma(n2, -LN2H, x2);
+        r0 = fma(n0, -LN2L, r0); r1 = fma(n1, -LN2L, r1); r2 = fma(n2, -LN2L, r2);
+        double p0 = kExpTaylor[0], p1 = kExpTaylor[0], p2 = kExpTaylor[0];
+#pragma unroll
+        for (int k = 1; k < 12; ++k) { const double c = kExpTaylor[k]; p0 = fma(p0, r0, c); p1 = fma(p1, r1, c); p2 = fma(p2, r2, c); }
+        p0 = fma(p0, r0, 1.0); p1 = fma(p1, r1, 1.0); p2 = fma(p2, r2, 1.0);
+        p0 = fma(p0, r0, 1.0); p1 = fma(p1, r1, 1.0); p2 = fma(p2, r2, 1.0);
+        e0 = __hiloint2double(__double2hiint(p0) + (__double2loint(t0) << 20), __double2loint(p0));
+        e1 = __hiloint2double(__double2hiint(p1) + (__double2loint(t1) << 20), __double2loint(p1));
+        e2 = __hiloint2double(__double2hiint(p2) + (__double2loint(t2) << 20), __double2loint(p2));
+    } else
+#endif
+    { e0 = exp(x0); e1 = exp(x1); e2 = exp(x2); }
+}
+
+// branch-free censoring term for a warp whose groups hold subjects of different event types
+// (src/fast_LAPRWM.cpp:640-650; same arithmetic per event type as log_ptb_static)
+template <int S>
+__device__ __forceinline__ double log_ptb_rows(double event, double lh, double H, double HL) {
+    if constexpr (S == 2) {
+        const double eH = exp(-H), eHL = exp(-HL);
+        const double arg = (event == 2.0) ? (1.0 - eH) : ((event == 3.0) ? (eHL - eH) : 1.0);
+        const double lg = log(arg);
+        double r = 0.0;
+        if (event == 1.0) r = lh - H;
+        if (event == 0.0) r = 0.0 - H;
+        if (event == 2.0 || event == 3.0) r = lg;
+        return r;
+    } else {
+        return event * lh - H;
+    }
+}
+
+// GLMM log-density of this lane's visit rows (lin_predF + log_longF, src/fast_LAPRWM.cpp:67-78,168-202); lrec / lcrec point
+// at the visit rows of the design / per-draw record, in global memory or in the warp's early stage (the call sites keep
+// the two apart so that the loads compile to LDS / LDG rather than generic loads)
+template <class Spec, int G>
+__device__ __forceinline__ double visit_rows(const double* __restrict__ lrec, const double* __restrict__ lcrec, const int* vcount,
+                                             const double (&bn)[Spec::d.q], const double (&isig)[Spec::d.O], const int l) {
+    constexpr int O = Spec::d.O;
+    double v_pyb = 0.0;
+    sfor<O>([&](auto kc) {
+        constexpr int k = kc;
+        constexpr int ones0 = Spec::d.z_ones0[k], qk = Spec::d.qk[k];
+        const int v = vcount[k];
+        for (int r = l; r < v; r += G) {
+            double eta = lcrec[r];
+            if constexpr (ones0 == 1) { constexpr int cz = Spec::d.re_inds[k][0]; eta += bn[cz]; }
+            sfor<qk - ones0>([&](auto jc) {
+                constexpr int j = jc;
+                constexpr int cj = Spec::d.re_inds[k][j + ones0];
+                eta += lrec[(1 + j) * v + r] * bn[cj];
+            });
+            v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta, isig[k]);
+        }
+        constexpr int lcols = Spec::L.long_cols[k];
+        lrec += lcols * v;
+        lcrec += v;
+    });
+    return v_pyb;
+}
+
+template <class Spec, int G, bool EARLY>
+__global__ void __launch_bounds__(JMB_ROWS_THREADS, JMB_ROWS_CTAS)
+jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_constant__ ChainConst cc,
+              const __grid_constant__ StepArgs a, const RowsArgs ra) {
+    constexpr int q = Spec::d.q, p = Spec::d.p, A = Spec::d.A, O = Spec::d.O, T = Spec::d.T, K = Spec::d.K, S = Spec::d.S;
+    constexpr int WB = Spec::d.WB, RP = Spec::L.RP, SS = Spec::L.state_stride;
+    constexpr int oV = Spec::L.o_V, oLong = Spec::L.o_long, cLong = Spec::L.c_long, oW1off = Spec::L.o_W1off;
+    constexpr int oW1v = Spec::L.o_W1v, oW2c = Spec::L.o_W2c, oW2 = Spec::L.o_W2, oPw = Spec::L.o_Pw;
+    constexpr bool W2C = Spec::d.w2_const != 0;
+    constexpr int THREADS = kRowsThreads, WARPS = THREADS / 32, SPW = 32 / G;
+    constexpr int NR = 1 + K * S;                       // hazard rows of a subject
+    constexpr int NJ = (NR + G - 1) / G;                // row-loop trips
+    constexpr int NJ_H = (1 + K + G - 1) / G;           // trips that hold the event-time row and the K rows of H
+    constexpr int RS = (q + 2) / 2 * 2;                 // rng stride: q increments + log u, padded to even
+    constexpr int NV = RowSlots<Spec>::NV, RING = JMB_ROWS_RING, LEAD = RING > 0 ? RING - 1 : 0;
+    static_assert(32 % G == 0 && G >= 2 && G <= 16, "G lanes per subject");
+    static_assert(LEAD <= NJ_H, "the trips copied ahead of the record head must be trips every subject needs");
+    static_assert(SS % 2 == 0 && RS % 2 == 0 && oLong % 2 == 0 && cLong % 2 == 0, "16-byte pieces");
+    static_assert(oPw <= kRowsHdr && oW2c + (W2C ? p : 0) <= kRowsHdr && oV * 2 + O <= 2 * kRowsHdr, "record head fits the staged header");
+    const int P = B + p + A;
+    extern __shared__ double smem[];
+    // [P] (current, proposed) pairs of Bs_gammas | gammas | alphas: one 16-byte load serves both parameter sets
+    double2* s_cp = reinterpret_cast<double2*>(smem);
+    double* s_invD = smem + 2 * P;                       // [q*q]
+    double* s_red = s_invD + (q * q + 1) / 2 * 2;        // [WARPS * SPW][3]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + (WARPS * SPW * 3 + 1) / 2 * 2);      // [WARPS] early-stage barriers
+    double* const s_ring0 = reinterpret_cast<double*>(s_bar + WARPS);                        // [WARPS][RING][NV][32]
+    // early stage of a subject: head | state | draws | visit rows (design) | visit rows (per-draw)
+    const int ES = kRowsHdr + SS + RS + ra.cap_dl + ra.cap_cl;
+    double* const s_early0 = s_ring0 + (size_t)WARPS * RING * NV * 32;                       // [WARPS][SPW][ES]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
+    const int grp = lane32 / G, l = lane32 % G;
+    double* const s_ring = s_ring0 + (size_t)warp * RING * NV * 32 + lane32;
+    double* const my_early = s_early0 + ((size_t)warp * SPW + grp) * ES;
+    uint64_t* const bar = s_bar + warp;
+    // this warp's steps: CTA-contiguous chunk, warps interleaved
+    const long long n = a.n;
+    const long long step0 = (long long)blockIdx.x * ra.steps_per_cta;
+    const long long total_steps = (n + SPW - 1) / SPW;
+    const long long step_end = min(total_steps, step0 + ra.steps_per_cta);
+    auto subject_of = [&](long long step) { return min(n - 1, step * SPW + grp); };
+
+    // offsets of this group's subject in the first step; loaded before the dependency wait (the offset tables never change)
+    long long t_step = step0 + warp;
+    long long d0 = 0, d1 = 0, c0 = 0, c1 = 0;
+    if (t_step < step_end) {
+        const long long s = subject_of(t_step);
+        d0 = a.doff[s]; d1 = a.doff[s + 1]; c0 = a.coff[s]; c1 = a.coff[s + 1];
+    }
+    if constexpr (EARLY) { if (lane32 == 0) mbar_init(bar, SPW); }
+    pdl_wait();
+    pdl_trigger();
+    for (int j = tid; j < P; j += THREADS) s_cp[j] = make_double2(a.par[pl.cur + j], a.par[pl.prop + j]);
+    for (int j = tid; j < q * q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
+#if !defined(JMB_EMU)
+    if constexpr (EARLY) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    const int i_blk = a.ctl->i;
+    const bool last_acc = a.ctl->last_accept != 0;
+    __syncthreads();
+    double isig[O];
+    sfor<O>([&](auto kc) { isig[kc] = 1.0 / a.par[pl.sigmas + kc]; });
+    const double2* s_g = s_cp + B;
+    const double2* s_al = s_cp + B + p;
+    const double* rng_it = a.rng + (long long)(i_blk % a.rng_chunk) * n * RS;
+
+    // bulk copies of one subject's early data into this group's stage slot (lane 0 of the group); `fits` = its visit rows
+    // are within the stage capacity (else they are read in place)
+    auto fits_early = [&](long long e0, long long e1, long long f0, long long f1) {
+        return (e1 - e0 - oLong) <= ra.cap_dl && (f1 - f0 - cLong) <= ra.cap_cl;
+    };
+    auto issue_early = [&](long long sn, long long e0, long long e1, long long f0, long long f1) {
+        const bool fit = fits_early(e0, e1, f0, f1);
+        const uint32_t dl = fit ? (uint32_t)(e1 - e0 - oLong) * 8u : 0u, cl = fit ? (uint32_t)(f1 - f0 - cLong) * 8u : 0u;
+        mbar_expect_tx(bar, (uint32_t)(kRowsHdr + SS + RS) * 8u + dl + cl);
+        bulk_g2s(my_early, a.drec + e0, kRowsHdr * 8u, bar);
+        bulk_g2s(my_early + kRowsHdr, a.state + sn * SS, SS * 8u, bar);
+        bulk_g2s(my_early + kRowsHdr + SS, rng_it + sn * RS, RS * 8u, bar);
+        if (dl) bulk_g2s(my_early + kRowsHdr + SS + RS, a.drec + e0 + oLong, dl, bar);
+        if (cl) bulk_g2s(my_early + kRowsHdr + SS + RS + ra.cap_dl, a.crec + f0 + cLong, cl, bar);
+    };
+    uint32_t phase = 0;
+    if constexpr (EARLY) { if (t_step < step_end && l == 0) issue_early(subject_of(t_step), d0, d1, c0, c1); }
+
+    double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;
+    for (; t_step < step_end; t_step += WARPS) {
+        const bool valid = t_step * SPW + grp < n;
+        const long long s = subject_of(t_step);
+        const double* __restrict__ rec = a.drec + d0;
+        const double* __restrict__ crec = a.crec + c0;
+        const bool staged = EARLY && fits_early(d0, d1, c0, c1);
+        // ---- next step of this warp: offsets now (used after the visit loops) ----
+        const long long t_next = t_step + WARPS;
+        const bool has_next = t_next < step_end;
+        long long nd0 = 0, nd1 = 0, nc0 = 0, nc1 = 0;
+        if (has_next) {
+            const long long sn = subject_of(t_next);
+            nd0 = a.doff[sn]; nd1 = a.doff[sn + 1]; nc0 = a.coff[sn]; nc1 = a.coff[sn + 1];
+        }
+
+        // copies of hazard-row trip jr (rows l + jr G of this lane's subject) into ring stage st
+        auto issue_row = [&](const int jr, const int st) {
+            const int rq = min(l + jr * G, RP - 1);
+            double* const dst = s_ring + (size_t)st * NV * 32;
+            cp_async4(reinterpret_cast<int*>(dst), reinterpret_cast<const int*>(rec + oW1off) + rq);
+            sfor<WB>([&](auto j) { constexpr int jv = j; cp_async8(dst + (1 + jv) * 32, rec + oW1v + jv * RP + rq); });
+            cp_async8(dst + (1 + WB) * 32, rec + oPw + rq);
+            if constexpr (!W2C) sfor<p>([&](auto j) { constexpr int jv = j; cp_async8(dst + (2 + WB + jv) * 32, rec + oW2 + jv * RP + rq); });
+            sfor<T>([&](auto tc) {
+                constexpr int t = tc;
+                constexpr int tb = RowSlots<Spec>::term_base(t), nz = RowSlots<Spec>::nzz(t), nuu = RowSlots<Spec>::nu(t);
+                constexpr int oZZq = Spec::L.o_ZZ[t], oUq = Spec::L.o_U[t];
+                cp_async8(dst + tb * 32, crec + t * RP + rq);
+                sfor<nz>([&](auto jc) { constexpr int j = jc; cp_async8(dst + (tb + 1 + j) * 32, rec + oZZq + j * RP + rq); });
+                sfor<nuu>([&](auto uc) { constexpr int u = uc; cp_async8(dst + (tb + 1 + nz + u) * 32, rec + oUq + u * RP + rq); });
+            });
+        };
+        if constexpr (RING > 0) {
+#pragma unroll
+            for (int d = 0; d < LEAD; ++d) { if (d < NJ_H) issue_row(d, d); cp_async_commit(); }
+        }
+
+        // ---- head of the record, current state and this iteration's draws (uniform within the group, 16-byte loads) ----
+        double stv[SS], rgv[RS], hdr[kRowsHdr];
+        if constexpr (EARLY) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            const double2* e2 = reinterpret_cast<const double2*>(smem + (my_early - smem));      // shared-memory provenance: LDS
+            sfor<kRowsHdr / 2>([&](auto j) { const double2 v = e2[j]; hdr[2 * j] = v.x; hdr[2 * j + 1] = v.y; });
+            sfor<SS / 2>([&](auto j) { const double2 v = e2[kRowsHdr / 2 + j]; stv[2 * j] = v.x; stv[2 * j + 1] = v.y; });
+            sfor<RS / 2>([&](auto j) { const double2 v = e2[(kRowsHdr + SS) / 2 + j]; rgv[2 * j] = v.x; rgv[2 * j + 1] = v.y; });
+        } else {
+            const double2* h2 = reinterpret_cast<const double2*>(rec);
+            sfor<kRowsHdr / 2>([&](auto j) { const double2 v = __ldg(h2 + j); hdr[2 * j] = v.x; hdr[2 * j + 1] = v.y; });
+            const double2* st2 = reinterpret_cast<const double2*>(a.state + s * SS);
+            sfor<SS / 2>([&](auto j) { const double2 v = st2[j]; stv[2 * j] = v.x; stv[2 * j + 1] = v.y; });
+            const double2* rg2 = reinterpret_cast<const double2*>(rng_it + s * RS);
+            sfor<RS / 2>([&](auto j) { const double2 v = __ldg(rg2 + j); rgv[2 * j] = v.x; rgv[2 * j + 1] = v.y; });
+        }
+        const double event = hdr[0];
+        int vcount[O];
+        sfor<O>([&](auto kc) {
+            constexpr int k = kc;
+            const double w = hdr[oV + k / 2];
+            vcount[k] = (k % 2 == 0) ? __double2loint(w) : __double2hiint(w);
+        });
+        double bo[q], bn[q];
+        sfor<q>([&](auto j) { bo[j] = stv[j]; bn[j] = stv[j] + rgv[j]; });     // :670
+        const double log_u = rgv[q];
+        const double pyb_old = stv[q + 1], pb_old = stv[q + 2];
+        // log p(T | b_old) under the current survival parameters, carried from the previous iteration
+        const double ptb_co = last_acc ? stv[q + 6] : stv[q + 5];
+
+        // ---- log p(b) at the proposal (:673) ----
+        double pb_new = 0.0;
+        sfor<q>([&](auto jc) {
+            constexpr int j = jc;
+            double t = 0.0;
+            sfor<q>([&](auto lc) { t += bn[lc] * s_invD[lc + j * q]; });
+            pb_new += t * bn[j];
+        });
+        pb_new *= -0.5;
+
+        // ---- GLMM log-density over the visit segment ----
+        double v_pyb;
+        if (staged) {
+            const double* lr = smem + (my_early - smem) + kRowsHdr + SS + RS;
+            v_pyb = visit_rows<Spec, G>(lr, lr + ra.cap_dl, vcount, bn, isig, l);
+        } else {
+            v_pyb = visit_rows<Spec, G>(rec + oLong, crec + cLong, vcount, bn, isig, l);
+        }
+
+        // ---- the early data of the warp's next step start to travel now; they are used a whole row loop later ----
+        if constexpr (EARLY) {
+            __syncwarp();                        // every lane has finished reading the stage
+            if (has_next && l == 0) { fence_proxy_async(); issue_early(subject_of(t_next), nd0, nd1, nc0, nc1); }
+        } else if (ra.prefetch && has_next && l == 0) {
+            const long long sn = subject_of(t_next);
+            l2_prefetch_bulk(a.drec + nd0, 64u);
+            const uint32_t dl = (uint32_t)(nd1 - nd0 - oLong) * 8u, cl = (uint32_t)(nc1 - nc0 - cLong) * 8u;
+            if (dl) l2_prefetch_bulk(a.drec + nd0 + oLong, dl);
+            if (cl) l2_prefetch_bulk(a.crec + nc0 + cLong, cl);
+            l2_prefetch_bulk(a.state + sn * SS, (uint32_t)SS * 8u);
+            l2_prefetch_bulk(rng_it + sn * RS, (uint32_t)RS * 8u);
+        }
+
+        // ---- hazard rows l, l + G, ...: lin_pred_matF :80-109, log_h :684, H / HL :685-691, survival step :735-741 ----
+        double s2c = 0.0, s2p = 0.0;
+        if constexpr (W2C) sfor<p>([&](auto j) { constexpr int jv = j; const double wv = hdr[oW2c + jv]; const double2 g = s_g[jv]; s2c += wv * g.x; s2p += wv * g.y; });
+        double H_cn = 0.0, HL_cn = 0.0, H_po = 0.0, HL_po = 0.0, H_pn = 0.0, HL_pn = 0.0;
+        double lh_cn = 0.0, lh_po = 0.0, lh_pn = 0.0;
+        // The lower-interval rows K+1..2K feed HL, which enters log p(T|b) of interval-censored subjects only (event == 3,
+        // src/fast_LAPRWM.cpp:699): a warp none of whose subjects is interval-censored neither copies nor evaluates the
+        // trips that hold only those rows (the reference evaluates them for everybody and discards the result).
+        const int nj = (S == 2 && NJ > NJ_H) ? (__any_sync(0xFFFFFFFFu, event == 3.0) ? NJ : NJ_H) : NJ;
+#pragma unroll 1
+        for (int jj = 0; jj < nj; ++jj) {
+            const int r = l + jj * G;
+            const int rr = min(r, RP - 1);                                   // padded rows exist up to RP - 1
+            // ring: start the copies of trip jj + LEAD into the stage consumed in the previous trip, then wait for trip jj
+            const double* const rs = s_ring + (size_t)(RING > 0 ? jj % (RING > 0 ? RING : 1) : 0) * NV * 32;
+            if constexpr (RING > 0) {
+                if (jj + LEAD < nj) issue_row(jj + LEAD, (jj + LEAD) % RING);
+                cp_async_commit();
+                cp_async_wait<LEAD>();
+            }
+            // value v of this row: from the ring, or straight from the record
+            auto rowld = [&](const int v, const double* g) { if constexpr (RING > 0) return rs[v * 32]; else return __ldg(g); };
+            const int off = (RING > 0) ? *reinterpret_cast<const int*>(rs) : __ldg(reinterpret_cast<const int*>(rec + oW1off) + rr);
+            double s1c = 0.0, s1p = 0.0;
+            sfor<WB>([&](auto j) {
+                constexpr int jv = j;
+                const double wv = rowld(1 + jv, rec + oW1v + jv * RP + rr);
+                const double2 cp = s_cp[off + jv];
+                s1c += wv * cp.x;
+                s1p += wv * cp.y;
+            });
+            double w2c_ = s2c, w2p_ = s2p;
+            if constexpr (!W2C) sfor<p>([&](auto j) { constexpr int jv = j; const double wv = rowld(2 + WB + jv, rec + oW2 + jv * RP + rr); const double2 g = s_g[jv]; w2c_ += wv * g.x; w2p_ += wv * g.y; });
+            double a_cn = 0.0, a_po = 0.0, a_pn = 0.0;
+            sfor<T>([&](auto tc) {
+                constexpr int t = tc;
+                constexpr int ones0 = Spec::d.zz_ones0[t], rt = Spec::d.rt[t];
+                constexpr int tb = RowSlots<Spec>::term_base(t), nz = RowSlots<Spec>::nzz(t);
+                const double xxb = rowld(tb, crec + t * RP + rr);
+                double zo = 0.0, zn = 0.0;
+                if constexpr (ones0 == 1) { constexpr int cz = Spec::d.re2[t][0]; zo = bo[cz]; zn = bn[cz]; }
+                constexpr int oZZ = Spec::L.o_ZZ[t], oU = Spec::L.o_U[t];
+                sfor<rt - ones0>([&](auto jc) {
+                    constexpr int j = jc;
+                    constexpr int cj = Spec::d.re2[t][j + ones0];
+                    const double zz = rowld(tb + 1 + j, rec + oZZ + j * RP + rr);
+                    zo += zz * bo[cj];
+                    zn += zz * bn[cj];
+                });
+                const double vo = trans_static<Spec::d.tf[t]>(xxb + zo), vn = trans_static<Spec::d.tf[t]>(xxb + zn);
+                sfor<Spec::d.ut[t]>([&](auto uc) {
+                    constexpr int u = uc;
+                    constexpr int c = Spec::d.col[t][u];
+                    double wo = vo, wn = vn;
+                    if constexpr (Spec::d.u_ones[t] == 0) {
+                        const double uu = rowld(tb + 1 + nz + u, rec + oU + u * RP + rr);
+                        wo *= uu; wn *= uu;
+                    }
+                    const double2 al = s_al[c];
+                    a_cn += wn * al.x;
+                    a_po += wo * al.y; a_pn += wn * al.y;
+                });
+            });
+            const double l_cn = (s1c + w2c_) + a_cn;
+            const double l_po = (s1p + w2p_) + a_po, l_pn = (s1p + w2p_) + a_pn;
+            const bool isH = (r >= 1 && r <= K), isHL = (S == 2 && r > K && r <= 2 * K);
+            const double pw = (isH || isHL) ? rowld(1 + WB, rec + oPw + rr) : 0.0;
+            double e_cn, e_po, e_pn;
+            exp3(l_cn, l_po, l_pn, e_cn, e_po, e_pn);
+            e_cn *= pw; e_po *= pw; e_pn *= pw;
+            if (r == 0) { lh_cn = l_cn; lh_po = l_po; lh_pn = l_pn; }
+            if (isH) { H_cn += e_cn; H_po += e_po; H_pn += e_pn; }
+            if constexpr (S == 2) { if (isHL) { HL_cn += e_cn; HL_po += e_po; HL_pn += e_pn; } }
+        }
+
+        // ---- group sums (xor butterflies inside the G lanes of a subject) ----
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            v_pyb += __shfl_xor_sync(0xFFFFFFFFu, v_pyb, o, G);
+            H_cn += __shfl_xor_sync(0xFFFFFFFFu, H_cn, o, G);
+            H_po += __shfl_xor_sync(0xFFFFFFFFu, H_po, o, G);
+            H_pn += __shfl_xor_sync(0xFFFFFFFFu, H_pn, o, G);
+            if constexpr (S == 2) {
+                HL_cn += __shfl_xor_sync(0xFFFFFFFFu, HL_cn, o, G);
+                HL_po += __shfl_xor_sync(0xFFFFFFFFu, HL_po, o, G);
+                HL_pn += __shfl_xor_sync(0xFFFFFFFFu, HL_pn, o, G);
+            }
+        }
+        lh_cn = __shfl_sync(0xFFFFFFFFu, lh_cn, 0, G);
+        lh_po = __shfl_sync(0xFFFFFFFFu, lh_po, 0, G);
+        lh_pn = __shfl_sync(0xFFFFFFFFu, lh_pn, 0, G);
+        const double pyb_new = v_pyb;
+
+        const double ptb_cn = log_ptb_rows<S>(event, lh_cn, H_cn, HL_cn);
+        const double cur_lp = pyb_old + ptb_co + pb_old;                 // :669
+        const double new_lp = pyb_new + ptb_cn + pb_new;                 // :703
+        const bool accept = log_u < (new_lp - cur_lp);                   // :706 (NaN rejects)
+
+        // ---- proposed survival parameters at the accepted b (:735-752) ----
+        const double ptb_p = log_ptb_rows<S>(event, accept ? lh_pn : lh_po, accept ? H_pn : H_po, accept ? HL_pn : HL_po);
+        const double ptb_c = accept ? ptb_cn : ptb_co;
+        const double pyb_acc = accept ? pyb_new : pyb_old;
+        const double pb_acc = accept ? pb_new : pb_old;
+        if (valid) { acc_cur += ptb_c; acc_prop += ptb_p; acc_lw += pyb_acc + pb_acc; }
+
+        // ---- state write-back by lane 0 of the group (:707-724); sigma_b (slot q) keeps the value read above ----
+        if (valid && l == 0) {
+            double outv[SS];
+            sfor<SS>([&](auto j) { outv[j] = stv[j]; });
+            sfor<q>([&](auto j) { outv[j] = accept ? bn[j] : bo[j]; });
+            outv[q + 1] = pyb_acc; outv[q + 2] = pb_acc;
+            outv[q + 3] = stv[q + 3] + (accept ? 1.0 : 0.0);
+            outv[q + 4] = stv[q + 4] + (accept ? 1.0 : 0.0);
+            outv[q + 5] = ptb_c; outv[q + 6] = ptb_p;
+            double2* st2 = reinterpret_cast<double2*>(a.state + s * SS);
+            sfor<SS / 2>([&](auto j) {
+                constexpr int j0 = 2 * j;
+                // pairs that hold only b are written when the proposal was accepted
+                if (j0 + 1 < q) { if (accept) st2[j] = make_double2(outv[j0], outv[j0 + 1]); }
+                else st2[j] = make_double2(outv[j0], outv[j0 + 1]);
+            });
+        }
+        d0 = nd0; d1 = nd1; c0 = nc0; c1 = nc1;
+    }
+    // ---- deterministic per-CTA partial sums: one slot per (warp, group), summed in slot order ----
+    if (l == 0) { const int slot = warp * SPW + grp; s_red[slot * 3] = acc_cur; s_red[slot * 3 + 1] = acc_prop; s_red[slot * 3 + 2] = acc_lw; }
+    __syncthreads();
+    if (tid < 3) {
+        double t = 0.0;
+        for (int g = 0; g < WARPS * SPW; ++g) t += s_red[g * 3 + tid];
+        a.partials[blockIdx.x * 3 + tid] = t;
+    }
+    (void)cc;
+}
+
+}  // namespace jmb

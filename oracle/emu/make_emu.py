@@ -20,7 +20,7 @@ CSRC = os.path.join(ROOT, "jmbayes_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libjmb200_emu.so")
 SOURCES = ["jmb200.cu", "jmb_kernels.cuh", "jmb_device.cuh", "jmb_model.h", "jmb_host.h", "jmb_laplace.cu", "jmb_accuracy.cu",
-           "jmb_survfit.cu", "jmb_survfit.cuh", "jmb_summaries.cu", "jmb_step_static.cuh"]
+           "jmb_survfit.cu", "jmb_survfit.cuh", "jmb_summaries.cu", "jmb_step_static.cuh", "jmb_step_rows.cuh"]
 CALLEE = re.compile(r"[A-Za-z_][A-Za-z_0-9]*(?:->[A-Za-z_][A-Za-z_0-9]*)*(?:<[^<>;(){}]*>)?$")
 
 
@@ -74,7 +74,7 @@ def transform(text: str) -> str:
     text = rewrite_launches(text)
     text = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu::dyn_smem();", text)
     text = text.replace("__shared__", "static").replace("__noinline__", "__attribute__((noinline))")
-    text = re.sub(r'asm volatile\("(?:griddepcontrol|fence\.mbarrier_init)[^;]*;"[^;]*;', ";", text)
+    text = re.sub(r'asm volatile\("(?:griddepcontrol|fence\.mbarrier_init|cp\.async\.bulk\.prefetch)[^;]*;"[^;]*;', ";", text)
     # the PTX helpers of the TMA-staged kernel (mbarrier + cp.async.bulk) -> their emulation (shim/emu_mbarrier.h)
     i = text.find("__device__ __forceinline__ uint32_t smem_u32")
     if i >= 0:
@@ -98,7 +98,8 @@ def build(force: bool = False) -> str:
             txt = transform(f.read())
         with open(dst, "w") as f:
             f.write(txt)
-    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-fpermissive", "-fmax-errors=15", "-I", os.path.join(HERE, "shim"), "-I", OUT,
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-fpermissive", "-fmax-errors=15", "-DJMB_EMU"] + os.environ.get("JMB_EMU_DEFS", "").split() + \
+          ["-I", os.path.join(HERE, "shim"), "-I", OUT,
            "-o", LIB, os.path.join(OUT, "jmb200_emu.cpp"), os.path.join(OUT, "jmb_laplace_emu.cpp"), os.path.join(OUT, "jmb_accuracy_emu.cpp"),
            os.path.join(OUT, "jmb_survfit_emu.cpp"), os.path.join(OUT, "jmb_summaries_emu.cpp"),
            os.path.join(HERE, "emu_runtime.cpp"), "-ldl"]

@@ -95,7 +95,7 @@ def run(drop_syncwarp: bool = False, names=("config2", "config4", "multistate"),
             assert s.count(a) == 1
             open(p, "w").write(s.replace(a, "        for (int j = lane; j < QS; j += G) bo[j] = st[j];"))
         lib = os.path.join(work, "libjmb200_emu_tsan.so")
-        cmd = ["g++", "-O1", "-g", "-fsanitize=thread", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-fpermissive", "-I", os.path.join(HERE, "shim"),
+        cmd = ["g++", "-O1", "-g", "-fsanitize=thread", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-fpermissive", "-DJMB_EMU"] + os.environ.get("JMB_EMU_DEFS", "").split() + ["-I", os.path.join(HERE, "shim"),
                "-I", src, "-o", lib] + [os.path.join(src, f) for f in ("jmb200_emu.cpp", "jmb_laplace_emu.cpp", "jmb_accuracy_emu.cpp", "jmb_survfit_emu.cpp",
                                                                            "jmb_summaries_emu.cpp")] + \
               [os.path.join(HERE, "emu_runtime.cpp"), "-ldl"]

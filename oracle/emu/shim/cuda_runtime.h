@@ -29,6 +29,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __constant__ static const
 #define __restrict__
 #define __grid_constant__
 #define __launch_bounds__(...)
@@ -161,6 +162,9 @@ inline void sincospi(double x, double* s, double* c) {      // exact reduction t
         default: *s = -cr; *c = sr; break;
     }
 }
+template <class T> inline T __ldg(const T* p) { return *p; }
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline long long min(long long a, long long b) { return a < b ? a : b; }

@@ -37,8 +37,53 @@ def build(force: bool = False) -> str | None:
     return LIB
 
 
+SHIM = os.path.join(HERE, "_ref", "libjmb_shim.so")
+_shim = None
+_use_shim = False
+
+
+def build_shim(force: bool = False) -> str:
+    """oracle/_ref/libjmb_shim.so: the SAME driver (ref_driver.cpp: R lists in, flat results out) linked with the Rcpp glue of
+    integration/fast_LAPRWM_cuda.cpp instead of the reference's sources - the exported functions with their bodies replaced
+    by calls into libjmb200.so.  Needs the CUDA library (and a GPU to run)."""
+    from jmbayes_b200 import build as jb
+    jb.build_cuda()
+    subprocess.run(["make", "-C", HERE, "-s", "shim"] + (["-B"] if force else []), check=True)
+    return SHIM
+
+
+class use_shim:
+    """Context manager: the calls of this module go to the Rcpp glue + CUDA library instead of the reference's own bodies."""
+
+    def __enter__(self):
+        global _use_shim
+        build_shim()
+        _use_shim = True
+        return self
+
+    def __exit__(self, *exc):
+        global _use_shim
+        _use_shim = False
+
+
+def _bind(path):
+    L = C.CDLL(path)
+    L.jmbref_last_error.restype = C.c_char_p
+    L.jmbref_lap_rwm.argtypes = [C.POINTER(_abi.JmbData), C.POINTER(_abi.JmbDraw), C.POINTER(_abi.JmbPriors),
+                                 C.POINTER(_abi.JmbControl), C.POINTER(_abi.JmbChainIn), C.POINTER(_abi.JmbChainOut)]
+    L.jmbref_logPosterior.restype = C.c_double
+    L.jmbref_logPosterior.argtypes = [C.c_double, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [_abi.c_double_p] * 17 + [C.c_double] * 3
+    L.jmbref_gradient_logPosterior.restype = None
+    L.jmbref_gradient_logPosterior.argtypes = [C.c_double, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [_abi.c_double_p] * 16 + [C.c_double] * 3 + [_abi.c_double_p]
+    return L
+
+
 def lib():
-    global _lib
+    global _lib, _shim
+    if _use_shim:
+        if _shim is None:
+            _shim = _bind(build_shim())
+        return _shim
     if _lib is None:
         if build() is None:
             raise RuntimeError("oracle/_ref is not available (no reference tree and no prebuilt library)")

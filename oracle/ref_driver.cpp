@@ -241,6 +241,7 @@ extern "C" int jmbref_lap_rwm(const orc_data* d, const orc_draw* w, const orc_pr
         Covs.push("gammas", num_mat(in->Sigma_gammas, p, p)); Covs.push("alphas", num_mat(in->Sigma_alphas, A, A));
 #define CT(name) control.push(#name, scalar((double)ct->name))
         CT(n_iter); CT(n_burnin); CT(n_block); CT(n_thin); CT(target_acc); CT(eps1); CT(eps2); CT(eps3); CT(c0); CT(c1); CT(adaptCov);
+        CT(seed); CT(chain_id);      // control$seed exists in R; chain_id = index of the draw (read by the CUDA glue only)
 #undef CT
         g = Provider();
         g.seed = ct->seed; g.chain = ct->chain_id; g.offset = d->subject_offset;
@@ -322,6 +323,7 @@ extern "C" int jmbref_lap_rwm_woRE(const orc_data* d, const double* Wlong, const
         Covs.push("alphas", num_mat(in->Sigma_alphas, A, A));
 #define CT(name) control.push(#name, scalar((double)ct->name))
         CT(n_iter); CT(n_burnin); CT(n_block); CT(n_thin); CT(target_acc); CT(eps1); CT(eps2); CT(eps3); CT(c0); CT(c1); CT(adaptCov);
+        CT(seed); CT(chain_id);      // control$seed exists in R; chain_id = index of the draw (read by the CUDA glue only)
 #undef CT
         g = Provider();
         g.seed = ct->seed; g.chain = ct->chain_id; g.n = 0; g.B = B; g.p = p; g.A = A; g.n_block = ct->n_block;

@@ -438,6 +438,7 @@ class List {
     Proxy operator[](const std::string& name) const { return (*this)[name.c_str()]; }
     Proxy operator[](int i) const { return Proxy{items.at((std::size_t)i).value}; }
     int size() const { return (int)items.size(); }
+    bool containsElementNamed(const char* name) const { for (const auto& it : items) if (it.name == name) return true; return false; }
     void push(const std::string& name, ValuePtr v) { items.push_back(NamedItem{name, std::move(v)}); }
     template <class... A> static List create(const A&... a) { List l; (l.items.push_back(a), ...); return l; }
 };

@@ -197,27 +197,35 @@ def test_emulated_summaries_and_survfit_kernels_match_their_oracles(emu):
     assert np.allclose(s5["summaries"], r5["summaries"], rtol=1e-9)
 
 
-@pytest.mark.parametrize("cfg,mode", [("config2", None), ("config4", None), ("config3", "direct")])
-def test_emulated_static_and_tma_staged_kernels_match_oracle(emu, oracle, cfg, mode):
-    """The hot-path kernels: jmb_step_tma (two-stage bulk-copy + mbarrier pipeline per warp; 70 subjects on the one-SM emulated
-    device give every warp three pipeline steps) and jmb_step_static, against the oracle chain."""
-    saved = os.environ.get("JMB_KERNEL")
+@pytest.mark.parametrize("cfg,mode,G,early", [("config4", None, 4, 0), ("config4", None, 8, 1), ("config4", None, 16, 1), ("config4", None, 2, 0),
+                                              ("config4", None, 8, 0), ("config3", None, 4, 1), ("config3", None, 16, 1), ("config3", None, 16, 0),
+                                              ("config2", None, 4, 1), ("config2", None, 8, 0),
+                                              ("config2", "tma", 0, 0), ("config4", "tma", 0, 0), ("config3", "direct", 0, 0)])
+def test_emulated_static_kernels_match_oracle(emu, oracle, cfg, mode, G, early):
+    """The hot-path kernels against the oracle chain: jmb_step_rows (G lanes per subject, rows strided by G; the default),
+    jmb_step_tma (two-stage bulk-copy + mbarrier pipeline per warp; 70 subjects on the one-SM emulated device give every warp
+    three pipeline steps) and jmb_step_static."""
+    saved = (os.environ.get("JMB_KERNEL"), os.environ.get("JMB_ROWS_G"), os.environ.get("JMB_ROWS_EARLY"))
     try:
+        os.environ.pop("JMB_KERNEL", None); os.environ.pop("JMB_ROWS_G", None); os.environ.pop("JMB_ROWS_EARLY", None)
         if mode:
             os.environ["JMB_KERNEL"] = mode
-        else:
-            os.environ.pop("JMB_KERNEL", None)
+        if G:
+            os.environ["JMB_ROWS_G"] = str(G)
+            os.environ["JMB_ROWS_EARLY"] = str(early)
         c = make_cohort(cfg, n=70)
         ctl = dict(c["control"]); ctl.update(n_burnin=20, n_iter=10, n_block=10, n_thin=5)
         with emu.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
-            assert fit.layout_info()["kernel"].startswith("static:" if mode else "static-tma:")
+            want = {None: "static-rows%d%s:" % (G, "e" if early else ""), "tma": "static-tma:", "direct": "static:"}[mode]
+            assert fit.layout_info()["kernel"].startswith(want)
             fit.set_draw(c["Data"])
             r1 = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
     finally:
-        if saved is None:
-            os.environ.pop("JMB_KERNEL", None)
-        else:
-            os.environ["JMB_KERNEL"] = saved
+        for key, val in zip(("JMB_KERNEL", "JMB_ROWS_G", "JMB_ROWS_EARLY"), saved):
+            if val is None:
+                os.environ.pop(key, None)
+            else:
+                os.environ[key] = val
     oracle.set_rowsum_mode(1)
     r0 = oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"])
     assert _rel(r1["extras"]["trace_surv"], r0["extras"]["trace_surv"]) <= 1e-12

@@ -92,30 +92,45 @@ def test_chain_matches_oracle_draw_for_draw(cuda_lib, oracle, cfg):
 
 @pytest.mark.parametrize("cfg", ["config2", "config3", "config4"])
 def test_static_and_generic_kernels_agree(cuda_lib, cfg, monkeypatch):
-    """The BASELINE shapes get a compile-time-specialised step kernel; the generic kernel must
-    produce the same chain."""
+    """The BASELINE shapes get compile-time-specialised step kernels (row-strided groups by default, every group width;
+    the TMA-staged and the direct one-lane-per-row kernels on request); the generic kernel must produce the same chain."""
     c = make_cohort(cfg, n=300)
     ctl = dict(c["control"]); ctl.update(n_burnin=30, n_iter=20, n_block=10, n_thin=10)
-    with cuda_lib.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
-        assert fit.layout_info()["kernel"].startswith("static-tma:")
-        fit.set_draw(c["Data"])
-        a = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+
+    def run(label):
+        with cuda_lib.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
+            assert fit.layout_info()["kernel"].startswith(label), fit.layout_info()["kernel"]
+            fit.set_draw(c["Data"])
+            return fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+
+    monkeypatch.delenv("JMB_KERNEL", raising=False)
+    monkeypatch.delenv("JMB_ROWS_G", raising=False)
+    monkeypatch.delenv("JMB_ROWS_EARLY", raising=False)
+    r = run("static-rows")
+    monkeypatch.setenv("JMB_KERNEL", "tma")
+    a = run("static-tma:")
     monkeypatch.setenv("JMB_KERNEL", "direct")
-    with cuda_lib.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
-        assert fit.layout_info()["kernel"].startswith("static:")
-        fit.set_draw(c["Data"])
-        d = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    d = run("static:")
     # same per-subject arithmetic, different partial-sum grouping only
     assert _rel(a["extras"]["trace_surv"], d["extras"]["trace_surv"]) <= 1e-12
     assert np.array_equal(a["mcmc"]["b"], d["mcmc"]["b"])
     monkeypatch.setenv("JMB_KERNEL", "generic")
-    with cuda_lib.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
-        assert fit.layout_info()["kernel"] == "generic"
-        fit.set_draw(c["Data"])
-        b = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    b = run("generic")
     assert _rel(a["extras"]["trace_surv"], b["extras"]["trace_surv"]) <= 1e-10
     assert np.allclose(a["mcmc"]["b"], b["mcmc"]["b"], rtol=1e-9, atol=1e-12)
     assert np.allclose(a["scales"]["sigma"]["b"], b["scales"]["sigma"]["b"], rtol=1e-10)
+    # the row-strided kernel sums a subject's rows in a different order (lane-strided partial sums): 1e-10
+    # (with and without the bulk-copied early stage of a step)
+    monkeypatch.delenv("JMB_KERNEL")
+    for G, early in [(None, None)] + [(g, e) for g in ("2", "4", "8", "16") for e in ("0", "1")]:
+        if G:
+            monkeypatch.setenv("JMB_ROWS_G", G)
+            monkeypatch.setenv("JMB_ROWS_EARLY", early)
+            r = run("static-rows" + G + ("e:" if early == "1" else ":"))
+        assert _rel(r["extras"]["trace_surv"], b["extras"]["trace_surv"]) <= 1e-10, (G, early)
+        assert np.allclose(r["mcmc"]["b"], b["mcmc"]["b"], rtol=1e-9, atol=1e-12), (G, early)
+        assert np.allclose(r["scales"]["sigma"]["b"], b["scales"]["sigma"]["b"], rtol=1e-10), (G, early)
+        assert np.array_equal(r["extras"]["accept_b"], b["extras"]["accept_b"]), (G, early)
 
 
 def test_uncompacted_designs_use_generic_layout(cuda_lib, oracle):

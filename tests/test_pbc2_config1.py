@@ -83,7 +83,7 @@ def test_pbc2_on_cuda_matches_cpu(cuda_lib, oracle, pbc2_cpu):
     pb = pbc2_cpu
     D, pr = pb["Data"], pb["priors"]
     with cuda_lib.Fit(D, pb["Covs_b"], False) as fit:
-        assert fit.layout_info()["kernel"] == "static-tma:value_gaussian"
+        assert fit.layout_info()["kernel"].startswith("static-rows") and fit.layout_info()["kernel"].endswith(":value_gaussian")
         # marglogLik2 driven by the device functions
         fit.set_wlong(pb["Wlong"], pb["Wlongs"])
         dev = finish_inits(make_pbc2(),
