@@ -401,22 +401,28 @@ def run_cuda(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     layout_bytes = info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"]
-    achieved = layout_bytes * n / (k_ms * 1e-3) / 1e9
+    # bytes that cross HBM per launch: ncu's dram__bytes of this very kernel when a capture is committed (the kernel skips
+    # the lower-interval rows of warps without interval-censored subjects, and over-fetches a little elsewhere), else the
+    # record layout's bytes; never more than the layout's bytes
+    real_bytes = min(traffic, layout_bytes * n) if traffic else layout_bytes * n
+    achieved = real_bytes / (k_ms * 1e-3) / 1e9
     alg8d = ALG_BYTES[cfg]
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src, "kernel": info["kernel"], "kernel_ms": k_ms,
-            "alg_bytes_per_subject_iteration": layout_bytes,
-            "alg_source": "bytes of the fused design (DESIGN.md section 2): design record + per-draw record read once, state read + "
+            "alg_bytes_per_subject_iteration": real_bytes / n,
+            "alg_source": ("ncu dram__bytes_read + dram__bytes_write of this kernel, per subject (" + str(traffic_src) + "); " if traffic else "") +
+                          "layout bytes of the fused design (DESIGN.md section 2): design record + per-draw record read once, state read + "
                           "written, b-step draws written once per chunk and read once; Wlong(s) and the cached bases never exist",
+            "layout_bytes_per_subject_iteration": layout_bytes, "frac_layout": layout_bytes * n / (k_ms * 1e-3) / 1e9 / peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-            "whole_step_gbs": layout_bytes * n / (ms_max / args.steps * 1e-3) / 1e9,
+            "whole_step_gbs": real_bytes / (ms_max / args.steps * 1e-3) / 1e9,
             "survey_8d": {"alg_bytes_per_subject_iteration": alg8d, "gbs": alg8d * n / (k_ms * 1e-3) / 1e9,
                           "note": "SURVEY.md 8(d) compact layout that materialises Wlong(s) and the cached bases; the fused kernel does not "
                                   "move these bytes, so this is NOT a fraction of the roofline (it can exceed the peak)"}}
     if prof and "inst_per_subject" in prof:
         sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
         sms = 148
-        roof["floors_us"] = {"dram": layout_bytes * n / (peak * 1e9) * 1e6,
+        roof["floors_us"] = {"dram": real_bytes / (peak * 1e9) * 1e6,
                              "issue": prof["inst_per_subject"] * n / (4 * sms * sm_hz) * 1e6,
                              "fp64": 2.0 * prof.get("fp64_inst_per_subject", 0.0) * n / (4 * sms * sm_hz) * 1e6,
                              "source": traffic_src}

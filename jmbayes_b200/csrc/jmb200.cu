@@ -81,14 +81,14 @@ struct ChainCtx {
     cudaStream_t stream = nullptr;
     ChainConst cc{};
     double* d_crec = nullptr;                       // per-draw records
-    double* d_state = nullptr; double* d_par = nullptr; Ctl* d_ctl = nullptr;
+    double* d_state = nullptr; double* d_par = nullptr; Ctl* d_ctl = nullptr; unsigned int* d_ticket = nullptr;
     double* d_partials = nullptr; double* d_tmp = nullptr;  // d_tmp: n*(q+1)
     double* d_rng = nullptr;                        // [rng_chunk][n][rng_stride] draws of the b-step
     size_t rng_capacity = 0; int rng_chunk = 1;
     double* h_crec = nullptr;                       // pinned staging for the per-draw records
     double* h_par = nullptr;                        // pinned staging for the parameter block
     double* h_tmp = nullptr;                        // pinned staging n*(q+1)
-    bool draw_set = false, chain_open = false, fin_attr_set = false, wore = false;
+    bool draw_set = false, chain_open = false, fin_attr_set = false, wore = false, step_published = false;
     int iter_host = 0, total_iters = 0, keep_host = 0, check_host = 0, n_out = 0, n_td = 0;
     double *o_b = nullptr, *o_par = nullptr, *o_trace = nullptr;   // device outputs
     size_t cap_ob = 0, cap_opar = 0, cap_otr = 0;   // capacities (doubles) of the output buffers
@@ -256,7 +256,7 @@ int jmb_handle_s::select_kernel() {
                     max_cl = std::max(max_cl, coff[i + 1] - coff[i] - mm.L.c_long);
                 }
                 const int RSs = (md.q + 2) / 2 * 2;
-                const long long budget = ((222LL * 1024) / kRowsCtas - fixed_b) / 8 / ((long long)kRowsWarps * spw) - (kRowsHdr + mm.L.state_stride + RSs);
+                const long long budget = ((222LL * 1024) / kRowsCtas - fixed_b - 6400 /* static: rows_publish_sums */) / 8 / ((long long)kRowsWarps * spw) - (kRowsHdr + mm.L.state_stride + RSs);
                 long long cd = (max_dl + 1) / 2 * 2, cc_ = (max_cl + 1) / 2 * 2;
                 if (cd + cc_ > budget) {
                     const double f = (double)std::max<long long>(budget, 0) / (double)(cd + cc_);
@@ -682,6 +682,8 @@ int jmb_handle_s::add_slot() {
     CU(cudaMalloc(&x->d_state, sizeof(double) * (size_t)n * mm.L.state_stride));
     CU(cudaMalloc(&x->d_tmp, sizeof(double) * (size_t)n * (q + 1)));
     CU(cudaMalloc(&x->d_ctl, sizeof(Ctl)));
+    CU(cudaMalloc(&x->d_ticket, sizeof(unsigned int)));
+    CU(cudaMemset(x->d_ticket, 0, sizeof(unsigned int)));
     CU(cudaMalloc(&x->d_par, sizeof(double) * pl.total));
     CU(cudaMalloc(&x->d_partials, sizeof(double) * 3 * (size_t)grid_cap));
     CU(cudaHostAlloc(&x->h_crec, sizeof(double) * crec_len, cudaHostAllocDefault));
@@ -723,7 +725,7 @@ extern "C" int jmb_destroy(jmb_handle h) {
     cudaFree(h->d_mbox); cudaFree(h->d_peer_mbox);
     cudaFree(h->d_Wlong); cudaFree(h->d_Wlongs); cudaFree(h->d_sp_partials); cudaFree(h->d_sp_out); cudaFree(h->d_theta);
     for (ChainCtx* x : h->slots) {
-        cudaFree(x->d_crec); cudaFree(x->d_state); cudaFree(x->d_par); cudaFree(x->d_ctl); cudaFree(x->d_partials);
+        cudaFree(x->d_crec); cudaFree(x->d_state); cudaFree(x->d_par); cudaFree(x->d_ctl); cudaFree(x->d_ticket); cudaFree(x->d_partials);
         cudaFree(x->d_tmp); cudaFree(x->o_b); cudaFree(x->o_par); cudaFree(x->o_trace); cudaFree(x->d_rng);
         if (x->h_crec) cudaFreeHost(x->h_crec);
         if (x->h_par) cudaFreeHost(x->h_par);
@@ -898,6 +900,11 @@ static bool pdl_enabled() {
     if (on < 0) { const char* e = getenv("JMB_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
     return on == 1;
 }
+static bool publish_enabled() {      // JMB_PUBLISH=0: the finalize kernel stores the sums itself (A/B)
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("JMB_PUBLISH"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -917,10 +924,19 @@ static int launch_step(jmb_handle h, int mode) {
     a.rng = h->c->d_rng; a.rng_chunk = h->c->rng_chunk; a.rng_stride = h->rng_stride;
     a.trow = h->d_trow; a.eval_stride = std::max(h->n, h->nT);
     if (mode == MODE_STEP && h->kernel_mode == 3) {
+        RowsArgs ra = h->ra;
+        h->c->step_published = false;
+        if (h->nranks > 1 && h->p2p && !h->c->wore && publish_enabled()) {
+            // this rank's sums travel to the mailboxes from the step kernel's last CTA (the finalize kernel of the same
+            // iteration uses the same stamp and only waits)
+            ra.peer_mbox = h->d_peer_mbox; ra.nranks = h->nranks; ra.rank = h->rank; ra.slot = h->c->slot_index;
+            ra.stamp = h->c->p2p_seq + 1; ra.ticket = h->c->d_ticket;
+            h->c->step_published = true;
+        }
         if (pdl_enabled()) {
-            CU(launch_pdl(h->rows_kernel, dim3(h->rows_grid), dim3(kRowsThreads), (size_t)h->rows_smem, h->c->stream, h->mm.B, h->pl, h->c->cc, a, h->ra));
+            CU(launch_pdl(h->rows_kernel, dim3(h->rows_grid), dim3(kRowsThreads), (size_t)h->rows_smem, h->c->stream, h->mm.B, h->pl, h->c->cc, a, ra));
         } else {
-            h->rows_kernel<<<h->rows_grid, kRowsThreads, h->rows_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a, h->ra);
+            h->rows_kernel<<<h->rows_grid, kRowsThreads, h->rows_smem, h->c->stream>>>(h->mm.B, h->pl, h->c->cc, a, ra);
         }
     }
     else if (mode == MODE_STEP && h->kernel_mode == 2) {
@@ -955,6 +971,8 @@ static int launch_finalize(jmb_handle h, int phase) {
     if (!a.wore && phase == 0 && h->nranks > 1 && h->p2p) {
         a.peer_mbox = h->d_peer_mbox; a.my_mbox = h->d_mbox; a.nranks = h->nranks; a.rank = h->rank;
         a.slot = h->c->slot_index; a.stamp = ++h->c->p2p_seq;
+        a.published = h->c->step_published ? 1 : 0;
+        h->c->step_published = false;
     }
     if (!a.wore && phase == 0 && h->nranks > 1 && !h->p2p) {
         jmb_reduce_partials_kernel<<<1, 128, 0, h->c->stream>>>(h->c->d_partials, a.n_partials, h->c->d_par + h->pl.sums);

@@ -343,6 +343,7 @@ struct FinalizeArgs {
     double* my_mbox;          // this rank's own mailbox: [slots][2][nranks][4] (3 sums + stamp)
     int nranks, rank, slot;
     unsigned long long stamp; // strictly increasing per slot; parity selects the mailbox half
+    int published;            // the step kernel's last CTA has already stored this rank's sums into the mailboxes (jmb_step_rows)
     // lap_rwm_C_woRE flavour (use_reduced == 3): sp_out[0] - sp_out[1] is the data term at the proposal
     // (phase 1: at the initial values); the current log-posterior is carried in par[pl.cur_lp]
     int wore; const double* sp_out;
@@ -449,7 +450,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         if (tid < 3) s_tot[tid] = gpar[pl.sums + tid];
     } else if (a.use_reduced == 3) {
         if (tid == 0) { s_tot[0] = 0.0; s_tot[1] = a.sp_out[0] - a.sp_out[1]; s_tot[2] = 0.0; }
-    } else {
+    } else if (!(a.use_reduced == 2 && a.published)) {
         double t0 = 0.0, t1 = 0.0, t2 = 0.0;
         for (int i = tid; i < a.n_partials; i += 128) { t0 += a.partials[i * 3]; t1 += a.partials[i * 3 + 1]; t2 += a.partials[i * 3 + 2]; }
         s_sum[tid] = t0; s_sum[128 + tid] = t1; s_sum[256 + tid] = t2;
@@ -465,7 +466,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         // ---- fused all-reduce over peer memory: compute (local sums) and collective in one kernel ----
         const int par2 = (int)(a.stamp & 1ull);
         const long long base = ((long long)(a.slot * 2 + par2) * a.nranks);
-        if (tid < a.nranks) {
+        if (tid < a.nranks && !a.published) {
             double* dst = a.peer_mbox[tid] + (base + a.rank) * 4;
             dst[0] = s_tot[0]; dst[1] = s_tot[1]; dst[2] = s_tot[2];
             __threadfence_system();

@@ -35,6 +35,10 @@ struct RowsArgs {
     int steps_per_cta;       // warp steps (of 32 / G subjects) owned by one CTA
     int prefetch;            // EARLY = false only: 1 = L2 bulk prefetch of the next step's early data
     int cap_dl, cap_cl;      // early stage: capacity (doubles) of the visit rows of the design / per-draw record of one subject
+    // several ranks (peer_mbox != NULL): the last CTA to finish reduces the per-CTA partial sums and stores the rank's three sums
+    // into every rank's mailbox itself, so that the NVLink flight overlaps the kernel boundary and the finalize kernel finds
+    // the stamps waiting (fields as in FinalizeArgs)
+    double* const* peer_mbox; int nranks, rank, slot; unsigned long long stamp; unsigned int* ticket;
 };
 
 #ifndef JMB_ROWS_THREADS
@@ -177,6 +181,28 @@ __device__ __forceinline__ double visit_rows(const double* __restrict__ lrec, co
         lcrec += v;
     });
     return v_pyb;
+}
+
+// last CTA of a multi-rank launch: fixed-order sum of the per-CTA partials, then one store per rank (values, fence, stamp)
+__device__ __noinline__ void rows_publish_sums(const double* partials, const int n_partials, const RowsArgs ra) {
+    __shared__ double s_pub[3 * JMB_ROWS_THREADS];
+    const int tid = threadIdx.x;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int i = tid; i < n_partials; i += JMB_ROWS_THREADS) { t0 += __ldcg(partials + i * 3); t1 += __ldcg(partials + i * 3 + 1); t2 += __ldcg(partials + i * 3 + 2); }
+    s_pub[tid] = t0; s_pub[JMB_ROWS_THREADS + tid] = t1; s_pub[2 * JMB_ROWS_THREADS + tid] = t2;
+    __syncthreads();
+    for (int w = JMB_ROWS_THREADS / 2; w > 0; w >>= 1) {
+        if (tid < w) { s_pub[tid] += s_pub[tid + w]; s_pub[JMB_ROWS_THREADS + tid] += s_pub[JMB_ROWS_THREADS + tid + w]; s_pub[2 * JMB_ROWS_THREADS + tid] += s_pub[2 * JMB_ROWS_THREADS + tid + w]; }
+        __syncthreads();
+    }
+    if (tid < ra.nranks) {
+        const long long base = ((long long)(ra.slot * 2 + (int)(ra.stamp & 1ull)) * ra.nranks);
+        double* dst = ra.peer_mbox[tid] + (base + ra.rank) * 4;
+        dst[0] = s_pub[0]; dst[1] = s_pub[JMB_ROWS_THREADS]; dst[2] = s_pub[2 * JMB_ROWS_THREADS];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(dst + 3) = ra.stamp;
+    }
+    if (tid == 0) *ra.ticket = 0u;                    // ready for the next launch on this chain slot
 }
 
 template <class Spec, int G, bool EARLY>
@@ -497,6 +523,14 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         double t = 0.0;
         for (int g = 0; g < WARPS * SPW; ++g) t += s_red[g * 3 + tid];
         a.partials[blockIdx.x * 3 + tid] = t;
+    }
+    if (ra.peer_mbox != nullptr) {
+        __shared__ unsigned int s_tk;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_tk = atomicAdd(ra.ticket, 1u);
+        __syncthreads();
+        if (s_tk == gridDim.x - 1) rows_publish_sums(a.partials, (int)gridDim.x, ra);
     }
     (void)cc;
 }

@@ -163,6 +163,8 @@ inline void sincospi(double x, double* s, double* c) {      // exact reduction t
     }
 }
 template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline int min(int a, int b) { return a < b ? a : b; }
