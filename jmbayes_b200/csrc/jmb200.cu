@@ -173,6 +173,7 @@ static void (*pick_rows_kernel(const ModelDesc& md, int G, bool early))(int, Par
     if (same_desc(md, SpecValueGaussian::d)) return early ? rows_kernel_of<SpecValueGaussian, true>(G) : rows_kernel_of<SpecValueGaussian, false>(G);
     if (same_desc(md, SpecThreeOutcomes::d)) return early ? rows_kernel_of<SpecThreeOutcomes, true>(G) : rows_kernel_of<SpecThreeOutcomes, false>(G);
     if (same_desc(md, SpecThreeOutcomesIC::d)) return early ? rows_kernel_of<SpecThreeOutcomesIC, true>(G) : rows_kernel_of<SpecThreeOutcomesIC, false>(G);
+    if (same_desc(md, SpecMultiState::d)) return early ? rows_kernel_of<SpecMultiState, true>(G) : rows_kernel_of<SpecMultiState, false>(G);
     return nullptr;
 }
 
@@ -228,10 +229,11 @@ int jmb_handle_s::select_kernel() {
         }
     }
     // row-strided groups (jmb_step_rows.cuh): G lanes per subject, 32 / G subjects per warp step; the default
-    if (static_kernel) {
+    if (same_desc(md, SpecMultiState::d)) kernel_name = "multistate_illness_death";
+    {
         // group width and early-stage staging per model shape, from the sweeps in profiles/r2_rows_kernel.md
-        int G = (md.S == 2) ? 8 : (md.O > 1 ? 16 : 4);
-        bool early = (md.S == 1 && md.O > 1);
+        int G = (md.S == 2 || md.MS) ? 8 : (md.O > 1 ? 16 : 4);
+        bool early = (md.S == 1 && md.O > 1 && !md.MS);
         if (const char* g = getenv("JMB_ROWS_G")) G = atoi(g);
         if (G != 2 && G != 4 && G != 8 && G != 16) G = 8;
         if (const char* e = getenv("JMB_ROWS_EARLY")) early = atoi(e) != 0;
@@ -268,7 +270,7 @@ int jmb_handle_s::select_kernel() {
             } else {
                 rows_smem = (int)fixed_b;
             }
-            if (rows_smem > 48 * 1024) {
+            {   // always: the kernel's static shared memory (6 KB) counts against the 48 KB default as well
                 cudaError_t e = cudaFuncSetAttribute((const void*)rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem);
                 if (e != cudaSuccess) { g_err = std::string("cudaFuncSetAttribute(rows): ") + cudaGetErrorString(e); return 1; }
             }
@@ -900,9 +902,12 @@ static bool pdl_enabled() {
     if (on < 0) { const char* e = getenv("JMB_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
     return on == 1;
 }
-static bool publish_enabled() {      // JMB_PUBLISH=0: the finalize kernel stores the sums itself (A/B)
+// JMB_PUBLISH=1: the step kernel's last CTA stores the rank's sums into the mailboxes instead of the finalize kernel.  Off by
+// default: measured on 2 GPUs it does not pay (0.1813 vs 0.1796 ms per iteration, profiles/r2_scaling.md) - the ticket and the
+// fences in every CTA cost what the earlier NVLink flight saves.
+static bool publish_enabled() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("JMB_PUBLISH"); on = (e && e[0] == '0') ? 0 : 1; }
+    if (on < 0) { const char* e = getenv("JMB_PUBLISH"); on = (e && e[0] == '1') ? 1 : 0; }
     return on == 1;
 }
 template <typename... KArgs, typename... Args>

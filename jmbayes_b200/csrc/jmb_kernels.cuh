@@ -472,25 +472,8 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
             __threadfence_system();
             *reinterpret_cast<volatile unsigned long long*>(dst + 3) = a.stamp;
         }
-        __syncthreads();
-        if (tid < a.nranks) {
-            const double* src = a.my_mbox + (base + tid) * 4;
-            const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(src + 3);
-            long long spins = 0;
-            while (*flag != a.stamp) {
-                if (++spins > 200000000LL) { a.ctl->error = 3; break; }     // a peer died: give up instead of hanging
-            }
-            __threadfence_system();
-            const volatile double* vs = src;
-            s_sum[tid * 3] = vs[0]; s_sum[tid * 3 + 1] = vs[1]; s_sum[tid * 3 + 2] = vs[2];
-        }
-        __syncthreads();
-        if (tid < 3) {
-            double t = 0.0;
-            for (int r = 0; r < a.nranks; ++r) t += s_sum[r * 3 + tid];     // rank order: identical on every rank
-            s_tot[tid] = t;
-        }
-        __syncthreads();
+        // the peers' sums are collected after the quadratic forms below, which do not depend on them: their arithmetic hides
+        // part of the NVLink flight
     }
 
     // ---- quadratic forms of the three Gaussian priors, one coordinate per thread ----
@@ -523,6 +506,29 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         }
     }
     __syncthreads();
+    if (a.use_reduced == 2) {
+        // ---- second half of the fused all-reduce: wait for every rank's stamp in this rank's mailbox, add in rank order ----
+        const int par2 = (int)(a.stamp & 1ull);
+        const long long base = ((long long)(a.slot * 2 + par2) * a.nranks);
+        if (tid < a.nranks) {
+            const double* src = a.my_mbox + (base + tid) * 4;
+            const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(src + 3);
+            long long spins = 0;
+            while (*flag != a.stamp) {
+                if (++spins > 200000000LL) { a.ctl->error = 3; break; }     // a peer died: give up instead of hanging
+            }
+            __threadfence_system();
+            const volatile double* vs = src;
+            s_sum[tid * 3] = vs[0]; s_sum[tid * 3 + 1] = vs[1]; s_sum[tid * 3 + 2] = vs[2];
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double t = 0.0;
+            for (int r = 0; r < a.nranks; ++r) t += s_sum[r * 3 + tid];     // rank order: identical on every rank
+            s_tot[tid] = t;
+        }
+        __syncthreads();
+    }
 
     if (tid == 0) {
         Ctl* ctl = a.ctl;

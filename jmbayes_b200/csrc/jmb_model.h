@@ -136,8 +136,26 @@ JMB_HD constexpr ModelDesc desc_three_outcomes(int S) {
     return d;
 }
 
+// multi-state illness-death shape of bench.py --workload multistate (cohorts.make_multistate_cohort): gaussian + binomial(logit),
+// q = 4, value of outcome 1 interacting with the transition (U = 3 stratum indicators) + expit(value of outcome 2),
+// transition-specific W2 (p = 3), stratified baseline hazard (3 x 7 B-spline coefficients, band of 4 inside a stratum)
+JMB_HD constexpr ModelDesc desc_multistate_illness_death() {
+    ModelDesc d{};
+    d.O = 2; d.q = 4; d.T = 2; d.A = 4; d.p = 3; d.K = 15; d.S = 1; d.WB = 4; d.G = 16; d.w2_const = 0; d.MS = 1;
+    d.fam[0] = JMB_FAM_GAUSSIAN; d.link[0] = JMB_LINK_IDENTITY;
+    d.fam[1] = JMB_FAM_BINOMIAL; d.link[1] = JMB_LINK_LOGIT;
+    for (int k = 0; k < 2; ++k) {
+        d.qk[k] = 2; d.z_ones0[k] = 1; d.re_inds[k][0] = 2 * k; d.re_inds[k][1] = 2 * k + 1;
+        d.rt[k] = 2; d.zz_ones0[k] = 1; d.re2[k][0] = 2 * k; d.re2[k][1] = 2 * k + 1;
+    }
+    d.ut[0] = 3; d.tf[0] = JMB_TF_IDENTITY; d.u_ones[0] = 0; d.col[0][0] = 0; d.col[0][1] = 1; d.col[0][2] = 2;
+    d.ut[1] = 1; d.tf[1] = JMB_TF_EXPIT; d.u_ones[1] = 1; d.col[1][0] = 3;
+    return d;
+}
+
 struct SpecValueGaussian { static constexpr ModelDesc d = desc_value_gaussian(); static constexpr RecordLayout L = make_layout(d); };
 struct SpecThreeOutcomes { static constexpr ModelDesc d = desc_three_outcomes(1); static constexpr RecordLayout L = make_layout(d); };
 struct SpecThreeOutcomesIC { static constexpr ModelDesc d = desc_three_outcomes(2); static constexpr RecordLayout L = make_layout(d); };
+struct SpecMultiState { static constexpr ModelDesc d = desc_multistate_illness_death(); static constexpr RecordLayout L = make_layout(d); };
 
 }  // namespace jmb

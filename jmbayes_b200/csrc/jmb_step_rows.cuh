@@ -214,6 +214,11 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
     constexpr int oV = Spec::L.o_V, oLong = Spec::L.o_long, cLong = Spec::L.c_long, oW1off = Spec::L.o_W1off;
     constexpr int oW1v = Spec::L.o_W1v, oW2c = Spec::L.o_W2c, oW2 = Spec::L.o_W2, oPw = Spec::L.o_Pw;
     constexpr bool W2C = Spec::d.w2_const != 0;
+    // multi-state fits (src/fast_LAPRWM.cpp:519-529,669,703): ntr >= 1 hazard-row blocks per subject (one per transition row,
+    // HB doubles apart in the design record, cLong apart in the per-draw record); log p(T|b) sums the blocks' terms
+    constexpr bool MS = Spec::d.MS != 0;
+    constexpr int HB = Spec::L.HB;
+    static_assert(!MS || (S == 1 && !W2C), "multi-state fits: no interval censoring, transition-specific W2");
     constexpr int THREADS = kRowsThreads, WARPS = THREADS / 32, SPW = 32 / G;
     constexpr int NR = 1 + K * S;                       // hazard rows of a subject
     constexpr int NJ = (NR + G - 1) / G;                // row-loop trips
@@ -251,9 +256,11 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
     // offsets of this group's subject in the first step; loaded before the dependency wait (the offset tables never change)
     long long t_step = step0 + warp;
     long long d0 = 0, d1 = 0, c0 = 0, c1 = 0;
+    int ntr = 1;                                          // transition rows of this group's subject
     if (t_step < step_end) {
         const long long s = subject_of(t_step);
         d0 = a.doff[s]; d1 = a.doff[s + 1]; c0 = a.coff[s]; c1 = a.coff[s + 1];
+        if constexpr (MS) ntr = a.trow[s + 1] - a.trow[s];
     }
     if constexpr (EARLY) { if (lane32 == 0) mbar_init(bar, SPW); }
     pdl_wait();
@@ -274,40 +281,55 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
 
     // bulk copies of one subject's early data into this group's stage slot (lane 0 of the group); `fits` = its visit rows
     // are within the stage capacity (else they are read in place)
-    auto fits_early = [&](long long e0, long long e1, long long f0, long long f1) {
-        return (e1 - e0 - oLong) <= ra.cap_dl && (f1 - f0 - cLong) <= ra.cap_cl;
+    // visit rows of a record with nb hazard-row blocks start at oLong + (nb - 1) HB (design) / nb cLong (per-draw)
+    auto fits_early = [&](long long e0, long long e1, long long f0, long long f1, int nb) {
+        return (e1 - e0 - oLong - (long long)(nb - 1) * HB) <= ra.cap_dl && (f1 - f0 - (long long)nb * cLong) <= ra.cap_cl;
     };
-    auto issue_early = [&](long long sn, long long e0, long long e1, long long f0, long long f1) {
-        const bool fit = fits_early(e0, e1, f0, f1);
-        const uint32_t dl = fit ? (uint32_t)(e1 - e0 - oLong) * 8u : 0u, cl = fit ? (uint32_t)(f1 - f0 - cLong) * 8u : 0u;
+    auto issue_early = [&](long long sn, long long e0, long long e1, long long f0, long long f1, int nb) {
+        const bool fit = fits_early(e0, e1, f0, f1, nb);
+        const long long lo = oLong + (long long)(nb - 1) * HB, lc = (long long)nb * cLong;
+        const uint32_t dl = fit ? (uint32_t)(e1 - e0 - lo) * 8u : 0u, cl = fit ? (uint32_t)(f1 - f0 - lc) * 8u : 0u;
         mbar_expect_tx(bar, (uint32_t)(kRowsHdr + SS + RS) * 8u + dl + cl);
         bulk_g2s(my_early, a.drec + e0, kRowsHdr * 8u, bar);
         bulk_g2s(my_early + kRowsHdr, a.state + sn * SS, SS * 8u, bar);
         bulk_g2s(my_early + kRowsHdr + SS, rng_it + sn * RS, RS * 8u, bar);
-        if (dl) bulk_g2s(my_early + kRowsHdr + SS + RS, a.drec + e0 + oLong, dl, bar);
-        if (cl) bulk_g2s(my_early + kRowsHdr + SS + RS + ra.cap_dl, a.crec + f0 + cLong, cl, bar);
+        if (dl) bulk_g2s(my_early + kRowsHdr + SS + RS, a.drec + e0 + lo, dl, bar);
+        if (cl) bulk_g2s(my_early + kRowsHdr + SS + RS + ra.cap_dl, a.crec + f0 + lc, cl, bar);
     };
     uint32_t phase = 0;
-    if constexpr (EARLY) { if (t_step < step_end && l == 0) issue_early(subject_of(t_step), d0, d1, c0, c1); }
+    if constexpr (EARLY) { if (t_step < step_end && l == 0) issue_early(subject_of(t_step), d0, d1, c0, c1, ntr); }
 
     double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;
     for (; t_step < step_end; t_step += WARPS) {
         const bool valid = t_step * SPW + grp < n;
         const long long s = subject_of(t_step);
-        const double* __restrict__ rec = a.drec + d0;
-        const double* __restrict__ crec = a.crec + c0;
-        const bool staged = EARLY && fits_early(d0, d1, c0, c1);
+        const double* __restrict__ rec0 = a.drec + d0;
+        const double* __restrict__ crec0 = a.crec + c0;
+        const bool staged = EARLY && fits_early(d0, d1, c0, c1, ntr);
         // ---- next step of this warp: offsets now (used after the visit loops) ----
         const long long t_next = t_step + WARPS;
         const bool has_next = t_next < step_end;
         long long nd0 = 0, nd1 = 0, nc0 = 0, nc1 = 0;
+        int n_ntr = 1;
         if (has_next) {
             const long long sn = subject_of(t_next);
             nd0 = a.doff[sn]; nd1 = a.doff[sn + 1]; nc0 = a.coff[sn]; nc1 = a.coff[sn + 1];
+            if constexpr (MS) n_ntr = a.trow[sn + 1] - a.trow[sn];
+        }
+        // every group of the warp walks the same number of blocks (the shuffles inside the loop need the whole warp); a group
+        // past its own last block re-evaluates that block and discards the result
+        int ntr_w = 1;
+        if constexpr (MS) {
+            ntr_w = ntr;
+#pragma unroll
+            for (int o = 16; o >= G; o >>= 1) ntr_w = max(ntr_w, __shfl_xor_sync(0xFFFFFFFFu, ntr_w, o));
         }
 
         // copies of hazard-row trip jr (rows l + jr G of this lane's subject) into ring stage st
-        auto issue_row = [&](const int jr, const int st) {
+        auto issue_row = [&](const int f, const int st) {
+            const int fb = MS ? min(f / NJ, ntr - 1) : 0, jr = MS ? f % NJ : f;
+            const double* const rec = rec0 + (size_t)fb * HB;
+            const double* const crec = crec0 + (size_t)fb * cLong;
             const int rq = min(l + jr * G, RP - 1);
             double* const dst = s_ring + (size_t)st * NV * 32;
             cp_async4(reinterpret_cast<int*>(dst), reinterpret_cast<const int*>(rec + oW1off) + rq);
@@ -338,7 +360,7 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
             sfor<SS / 2>([&](auto j) { const double2 v = e2[kRowsHdr / 2 + j]; stv[2 * j] = v.x; stv[2 * j + 1] = v.y; });
             sfor<RS / 2>([&](auto j) { const double2 v = e2[(kRowsHdr + SS) / 2 + j]; rgv[2 * j] = v.x; rgv[2 * j + 1] = v.y; });
         } else {
-            const double2* h2 = reinterpret_cast<const double2*>(rec);
+            const double2* h2 = reinterpret_cast<const double2*>(rec0);
             sfor<kRowsHdr / 2>([&](auto j) { const double2 v = __ldg(h2 + j); hdr[2 * j] = v.x; hdr[2 * j + 1] = v.y; });
             const double2* st2 = reinterpret_cast<const double2*>(a.state + s * SS);
             sfor<SS / 2>([&](auto j) { const double2 v = st2[j]; stv[2 * j] = v.x; stv[2 * j + 1] = v.y; });
@@ -375,19 +397,20 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
             const double* lr = smem + (my_early - smem) + kRowsHdr + SS + RS;
             v_pyb = visit_rows<Spec, G>(lr, lr + ra.cap_dl, vcount, bn, isig, l);
         } else {
-            v_pyb = visit_rows<Spec, G>(rec + oLong, crec + cLong, vcount, bn, isig, l);
+            v_pyb = visit_rows<Spec, G>(rec0 + oLong + (size_t)(ntr - 1) * HB, crec0 + (size_t)ntr * cLong, vcount, bn, isig, l);
         }
 
         // ---- the early data of the warp's next step start to travel now; they are used a whole row loop later ----
         if constexpr (EARLY) {
             __syncwarp();                        // every lane has finished reading the stage
-            if (has_next && l == 0) { fence_proxy_async(); issue_early(subject_of(t_next), nd0, nd1, nc0, nc1); }
+            if (has_next && l == 0) { fence_proxy_async(); issue_early(subject_of(t_next), nd0, nd1, nc0, nc1, n_ntr); }
         } else if (ra.prefetch && has_next && l == 0) {
             const long long sn = subject_of(t_next);
             l2_prefetch_bulk(a.drec + nd0, 64u);
-            const uint32_t dl = (uint32_t)(nd1 - nd0 - oLong) * 8u, cl = (uint32_t)(nc1 - nc0 - cLong) * 8u;
-            if (dl) l2_prefetch_bulk(a.drec + nd0 + oLong, dl);
-            if (cl) l2_prefetch_bulk(a.crec + nc0 + cLong, cl);
+            const long long lo = oLong + (long long)(n_ntr - 1) * HB, lc = (long long)n_ntr * cLong;
+            const uint32_t dl = (uint32_t)(nd1 - nd0 - lo) * 8u, cl = (uint32_t)(nc1 - nc0 - lc) * 8u;
+            if (dl) l2_prefetch_bulk(a.drec + nd0 + lo, dl);
+            if (cl) l2_prefetch_bulk(a.crec + nc0 + lc, cl);
             l2_prefetch_bulk(a.state + sn * SS, (uint32_t)SS * 8u);
             l2_prefetch_bulk(rng_it + sn * RS, (uint32_t)RS * 8u);
         }
@@ -400,10 +423,14 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         // The lower-interval rows K+1..2K feed HL, which enters log p(T|b) of interval-censored subjects only (event == 3,
         // src/fast_LAPRWM.cpp:699): a warp none of whose subjects is interval-censored neither copies nor evaluates the
         // trips that hold only those rows (the reference evaluates them for everybody and discards the result).
-        const int nj = (S == 2 && NJ > NJ_H) ? (__any_sync(0xFFFFFFFFu, event == 3.0) ? NJ : NJ_H) : NJ;
+        const int nj = MS ? ntr_w * NJ : ((S == 2 && NJ > NJ_H) ? (__any_sync(0xFFFFFFFFu, event == 3.0) ? NJ : NJ_H) : NJ);
+        double ms_cn = 0.0, ms_po = 0.0, ms_pn = 0.0, ev_tb = 0.0;           // MS: sums over the subject's transition rows
 #pragma unroll 1
         for (int jj = 0; jj < nj; ++jj) {
-            const int r = l + jj * G;
+            const int blk = MS ? jj / NJ : 0, jt = MS ? jj % NJ : jj;        // block and trip inside the block
+            const double* const rec = rec0 + (size_t)(MS ? min(blk, ntr - 1) : 0) * HB;
+            const double* const crec = crec0 + (size_t)(MS ? min(blk, ntr - 1) : 0) * cLong;
+            const int r = l + jt * G;
             const int rr = min(r, RP - 1);                                   // padded rows exist up to RP - 1
             // ring: start the copies of trip jj + LEAD into the stage consumed in the previous trip, then wait for trip jj
             const double* const rs = s_ring + (size_t)(RING > 0 ? jj % (RING > 0 ? RING : 1) : 0) * NV * 32;
@@ -458,22 +485,41 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
             const double l_cn = (s1c + w2c_) + a_cn;
             const double l_po = (s1p + w2p_) + a_po, l_pn = (s1p + w2p_) + a_pn;
             const bool isH = (r >= 1 && r <= K), isHL = (S == 2 && r > K && r <= 2 * K);
-            const double pw = (isH || isHL) ? rowld(1 + WB, rec + oPw + rr) : 0.0;
+            const double pw_raw = (MS || isH || isHL) ? rowld(1 + WB, rec + oPw + rr) : 0.0;
+            const double pw = (isH || isHL) ? pw_raw : 0.0;
+            if constexpr (MS) { if (r == 0) ev_tb = pw_raw; }                // the event-time row's Pw slot holds the transition's event indicator
             double e_cn, e_po, e_pn;
             exp3(l_cn, l_po, l_pn, e_cn, e_po, e_pn);
             e_cn *= pw; e_po *= pw; e_pn *= pw;
             if (r == 0) { lh_cn = l_cn; lh_po = l_po; lh_pn = l_pn; }
             if (isH) { H_cn += e_cn; H_po += e_po; H_pn += e_pn; }
             if constexpr (S == 2) { if (isHL) { HL_cn += e_cn; HL_po += e_po; HL_pn += e_pn; } }
+            if constexpr (MS) {
+                if (jt == NJ - 1) {          // end of a block: its term event * log h - H for the three (parameters, b) pairs
+#pragma unroll
+                    for (int o = G / 2; o > 0; o >>= 1) {
+                        H_cn += __shfl_xor_sync(0xFFFFFFFFu, H_cn, o, G);
+                        H_po += __shfl_xor_sync(0xFFFFFFFFu, H_po, o, G);
+                        H_pn += __shfl_xor_sync(0xFFFFFFFFu, H_pn, o, G);
+                    }
+                    const double ev = __shfl_sync(0xFFFFFFFFu, ev_tb, 0, G);
+                    const double h_cn = __shfl_sync(0xFFFFFFFFu, lh_cn, 0, G), h_po = __shfl_sync(0xFFFFFFFFu, lh_po, 0, G);
+                    const double h_pn = __shfl_sync(0xFFFFFFFFu, lh_pn, 0, G);
+                    if (blk < ntr) { ms_cn += ev * h_cn - H_cn; ms_po += ev * h_po - H_po; ms_pn += ev * h_pn - H_pn; }
+                    H_cn = 0.0; H_po = 0.0; H_pn = 0.0;
+                }
+            }
         }
 
         // ---- group sums (xor butterflies inside the G lanes of a subject) ----
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
             v_pyb += __shfl_xor_sync(0xFFFFFFFFu, v_pyb, o, G);
-            H_cn += __shfl_xor_sync(0xFFFFFFFFu, H_cn, o, G);
-            H_po += __shfl_xor_sync(0xFFFFFFFFu, H_po, o, G);
-            H_pn += __shfl_xor_sync(0xFFFFFFFFu, H_pn, o, G);
+            if constexpr (!MS) {
+                H_cn += __shfl_xor_sync(0xFFFFFFFFu, H_cn, o, G);
+                H_po += __shfl_xor_sync(0xFFFFFFFFu, H_po, o, G);
+                H_pn += __shfl_xor_sync(0xFFFFFFFFu, H_pn, o, G);
+            }
             if constexpr (S == 2) {
                 HL_cn += __shfl_xor_sync(0xFFFFFFFFu, HL_cn, o, G);
                 HL_po += __shfl_xor_sync(0xFFFFFFFFu, HL_po, o, G);
@@ -485,13 +531,14 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         lh_pn = __shfl_sync(0xFFFFFFFFu, lh_pn, 0, G);
         const double pyb_new = v_pyb;
 
-        const double ptb_cn = log_ptb_rows<S>(event, lh_cn, H_cn, HL_cn);
+        const double ptb_cn = MS ? ms_cn : log_ptb_rows<S>(event, lh_cn, H_cn, HL_cn);
         const double cur_lp = pyb_old + ptb_co + pb_old;                 // :669
         const double new_lp = pyb_new + ptb_cn + pb_new;                 // :703
         const bool accept = log_u < (new_lp - cur_lp);                   // :706 (NaN rejects)
 
         // ---- proposed survival parameters at the accepted b (:735-752) ----
-        const double ptb_p = log_ptb_rows<S>(event, accept ? lh_pn : lh_po, accept ? H_pn : H_po, accept ? HL_pn : HL_po);
+        const double ptb_p = MS ? (accept ? ms_pn : ms_po)
+                                : log_ptb_rows<S>(event, accept ? lh_pn : lh_po, accept ? H_pn : H_po, accept ? HL_pn : HL_po);
         const double ptb_c = accept ? ptb_cn : ptb_co;
         const double pyb_acc = accept ? pyb_new : pyb_old;
         const double pb_acc = accept ? pb_new : pb_old;
@@ -514,7 +561,7 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
                 else st2[j] = make_double2(outv[j0], outv[j0 + 1]);
             });
         }
-        d0 = nd0; d1 = nd1; c0 = nc0; c1 = nc1;
+        d0 = nd0; d1 = nd1; c0 = nc0; c1 = nc1; ntr = n_ntr;
     }
     // ---- deterministic per-CTA partial sums: one slot per (warp, group), summed in slot order ----
     if (l == 0) { const int slot = warp * SPW + grp; s_red[slot * 3] = acc_cur; s_red[slot * 3 + 1] = acc_prop; s_red[slot * 3 + 2] = acc_lw; }

@@ -84,6 +84,33 @@ def test_chain_matches_oracle_multistate(cuda_lib, oracle):
     assert 0.05 < got["extras"]["accept_b"].mean() < 0.8
 
 
+def test_multistate_specialised_and_generic_kernels_agree(cuda_lib, monkeypatch):
+    """The illness-death shape has a compile-time-specialised row-strided kernel (hazard-row blocks of the subject's
+    transition rows walked in one flattened loop); every group width, with and without the early stage, must walk the
+    chain of the runtime-descriptor kernel."""
+    c = make_multistate_cohort(n=300)
+    ctl = dict(c["control"]); ctl.update(n_burnin=30, n_iter=20, n_block=10, n_thin=10)
+
+    def run(label):
+        with cuda_lib.Fit(c["Data"], c["Covs"]["b"], False, multiState=True) as fit:
+            k = fit.layout_info()["kernel"]
+            assert k.startswith(label) and (label == "generic" or k.endswith(":multistate_illness_death")), k
+            fit.set_draw(c["Data"])
+            return fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+
+    monkeypatch.setenv("JMB_KERNEL", "generic")
+    g = run("generic")
+    monkeypatch.delenv("JMB_KERNEL")
+    for G, early in [(None, None)] + [(w, e) for w in ("4", "8", "16") for e in ("0", "1")]:
+        if G:
+            monkeypatch.setenv("JMB_ROWS_G", G); monkeypatch.setenv("JMB_ROWS_EARLY", early)
+        r = run("static-rows" + (G + ("e:" if early == "1" else ":") if G else ""))
+        assert _rel(r["extras"]["trace_surv"], g["extras"]["trace_surv"]) <= 1e-10, (G, early)
+        assert np.allclose(r["mcmc"]["b"], g["mcmc"]["b"], rtol=1e-9, atol=1e-12), (G, early)
+        assert np.array_equal(r["extras"]["accept_b"], g["extras"]["accept_b"]), (G, early)
+        assert np.allclose(r["mcmc"]["tau_Bs_gammas"], g["mcmc"]["tau_Bs_gammas"], rtol=1e-9), (G, early)
+
+
 @pytest.mark.parametrize("name", sorted(make_golden.MS_CASES))
 def test_cuda_reproduces_reference_multistate_golden(cuda_lib, name):
     from test_multistate_cpu import check_chain

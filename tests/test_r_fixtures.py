@@ -1,0 +1,79 @@
+"""R-generated fixtures for the R-level pieces restated in oracle/ (posterior summaries, marglogLik2, the survfitJM mode
+search).  R is absent from the build image: tests/golden/make_r_fixtures.R is what a reviewer with R + JMbayes runs; until
+its output exists under tests/golden/r_fixtures/ these tests SKIP with "parity unpinned" - they never pass vacuously."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIX = os.path.join(HERE, "golden", "r_fixtures")
+
+
+def _fixture(name):
+    p = os.path.join(FIX, name)
+    if not os.path.exists(p):
+        pytest.skip(f"parity unpinned: {name} not generated yet (Rscript tests/golden/make_r_fixtures.R needs R + JMbayes)")
+    return json.load(open(p))
+
+
+def _inputs():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("export_r_inputs", os.path.join(HERE, "golden", "export_r_inputs.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def _num(x):
+    return np.array([np.nan if v is None else v for v in np.ravel(x)], dtype=np.float64)
+
+
+def test_inputs_on_disk_are_the_seeded_inputs():
+    """The JSON a reviewer feeds to R is what the tests regenerate from the seeds."""
+    m = _inputs()
+    X, ll = m.stats_case()
+    d = json.load(open(os.path.join(HERE, "golden", "r_inputs", "stats.json")))
+    assert np.array_equal(np.array(d["X"]["data"]).reshape(d["X"]["dim"], order="F"), X) and np.array_equal(np.array(d["LogLiks"]), ll)
+
+
+def test_restated_summaries_match_R():
+    from oracle import oracle_stats
+    f = _fixture("stats.json")
+    X, ll = _inputs().stats_case()
+    w = oracle_stats.stand(ll)
+    assert np.allclose(w, _num(f["weights"]), rtol=1e-13)
+    r = oracle_stats.statistics(X, w)
+    for name in ("postMeans", "postwMeans", "StDev", "wStDev", "EffectiveSize", "StErr", "Pvalues", "postModes"):
+        want = np.array([_num(s[name])[0] for s in f["series"]])
+        assert np.allclose(r[name], want, rtol=1e-9 if name != "postModes" else 1e-6, atol=1e-12, equal_nan=True), name
+    for name in ("CIs", "wCIs"):
+        want = np.array([_num(s[name]) for s in f["series"]]).T
+        assert np.allclose(np.asarray(r[name]).reshape(want.shape), want, rtol=1e-9, atol=1e-12, equal_nan=True), name
+
+
+def test_restated_marglogLik2_matches_R(oracle):
+    f = _fixture("marglogLik2.json")
+    c, D, th = _inputs().mll_case()
+    for case in f:
+        fixed = bool(np.ravel(case["fixed"])[0])
+        t = dict(th)
+        if not fixed:
+            t["tau_Bs_gammas"] = np.log(200.0)
+        r = oracle.marglogLik2(t, D, c["priors"], fixed_tau_Bs_gammas=fixed)
+        assert abs(r["value"] - _num(case["value"])[0]) <= 1e-6 * abs(r["value"])
+        for k in ("Bs_gammas", "gammas", "alphas"):
+            assert np.allclose(r["inits"][k] if "inits" in r else r["par_blocks"][k], _num(case["inits"][k]), atol=1e-5), k
+
+
+def test_restated_survfit_mode_search_matches_R(oracle):
+    from jmbayes_b200 import survfit as sv
+    from oracle import oracle_svft
+    f = _fixture("survfit_modes.json")
+    c, d, means = _inputs().svft_case()
+    o = oracle_svft.modes(d, means)
+    want = np.array([_num(s["par"]) for s in f])
+    assert np.allclose(o["modes"], want, atol=1e-6)
+    H = np.array([np.array(s["hessian"], dtype=np.float64) for s in f])
+    assert np.allclose(o["hessians"], H, rtol=1e-5, atol=1e-6 * np.abs(H).max())
+    assert [int(np.ravel(s["convergence"])[0]) for s in f] == [int(x) for x in o["convergence"]]
