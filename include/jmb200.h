@@ -277,6 +277,7 @@ typedef struct jmb_mll_out {
     double* par;             /* [d]   opt$par (attr(, "inits") = its Bs_gammas | gammas | alphas blocks) */
     double* hessian;         /* d x d opt$hessian */
     double* Cov_Bs_gammas; double* Cov_gammas; double* Cov_alphas;   /* attr(, "Covs") (fixed_tau_Bs_gammas only) */
+    int32_t restarts;        /* 1 when optim(BFGS) raised at the starting values and the jittered restart of :95-100 was used */
 } jmb_mll_out;
 int jmb_marglogLik2(jmb_handle h, const double* Bs_gammas, const double* gammas, const double* alphas,
                     double tau_Bs_gammas, const jmb_priors* priors, double temp, int fixed_tau_Bs_gammas,

@@ -103,7 +103,7 @@ class JmbChainOut(C.Structure):
 
 class JmbMllOut(C.Structure):
     _fields_ = [("value", C.c_double), ("opt_value", C.c_double), ("convergence", C.c_int32), ("counts", C.c_int32 * 2)] + \
-               [(f, c_double_p) for f in ("par", "hessian", "Cov_Bs_gammas", "Cov_gammas", "Cov_alphas")]
+               [(f, c_double_p) for f in ("par", "hessian", "Cov_Bs_gammas", "Cov_gammas", "Cov_alphas")] + [("restarts", C.c_int32)]
 
 
 class JmbEvalOut(C.Structure):

@@ -304,7 +304,7 @@ class Fit:
         _check(lib().jmb_marglogLik2(self._h, _dptr(Bs), _dptr(g), _dptr(al), tau, C.byref(pr), float(temp),
                                      int(bool(fixed_tau_Bs_gammas)), C.byref(out)))
         res = dict(value=out.value, opt_value=out.opt_value, convergence=out.convergence, counts=(out.counts[0], out.counts[1]),
-                   par=bufs["par"], hessian=bufs["hessian"])
+                   par=bufs["par"], hessian=bufs["hessian"], restarts=int(out.restarts))
         if fixed_tau_Bs_gammas:
             res["Covs"] = dict(Bs_gammas=bufs["Cov_Bs_gammas"], gammas=bufs["Cov_gammas"][:self.p, :self.p], alphas=bufs["Cov_alphas"])
             res["inits"] = dict(Bs_gammas=bufs["par"][:self.B], gammas=bufs["par"][self.B:self.B + self.p],

@@ -17,8 +17,9 @@ UNITS = {
     "jmb_laplace.cu": ["jmb_host.h"],
     "jmb_summaries.cu": ["jmb_host.h"],
     "jmb_accuracy.cu": ["jmb_host.h"],
+    "jmb_designs.cu": ["jmb_host.h"],
 }
-HEADERS = [os.path.join(ROOT, "include", f) for f in ("jmb200.h", "jmb200_survfit.h", "jmb200_summaries.h", "jmb200_accuracy.h")]
+HEADERS = [os.path.join(ROOT, "include", f) for f in ("jmb200.h", "jmb200_survfit.h", "jmb200_summaries.h", "jmb200_accuracy.h", "jmb200_designs.h")]
 SOURCES = [os.path.join(CSRC, f) for f in UNITS]
 
 

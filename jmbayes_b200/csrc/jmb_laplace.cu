@@ -8,7 +8,7 @@
 // src/library/stats/src/optim.c), absent from the JMbayes tree and restated here from the published algorithm, as are
 // solve / determinant (LU with partial pivoting) and eigen(symmetric = TRUE) (cyclic Jacobi) behind nearPD
 // (R/nearPD.R:1-47).  The try() fall-backs of R/margLogLik2.R:95-109 (jittered restart, Nelder-Mead) are not provided:
-// a non-finite initial value is an error.
+// a non-finite initial value triggers the reference's jittered restart (R/margLogLik2.R:95-100).
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -279,9 +279,29 @@ extern "C" int jmb_marglogLik2(jmb_handle h, const double* Bs_gammas, const doub
     Vec pscale(d, 1.0);
     if (!fixed_tau_Bs_gammas) pscale[d - 1] = 0.1;                        // :93
     OptimResult R;
-    const int rc = optim_bfgs(th, pscale, fn, gr, 100, 1.490116119384765625e-8, 1e-3, R);
-    if (rc == 10) return jmb_set_error("jmb_marglogLik2: initial value in 'vmmin' is not finite (the reference would fall back to a jittered "
-                                       "restart / Nelder-Mead, R/margLogLik2.R:95-109; not provided)");
+    int rc = optim_bfgs(th, pscale, fn, gr, 100, 1.490116119384765625e-8, 1e-3, R);
+    out->restarts = 0;
+    if (rc == 10) {
+        // R/margLogLik2.R:95-100: optim(BFGS) raised ("initial value in 'vmmin' is not finite") -> one restart from
+        // vec_thetas + rnorm(d, sd = 0.1).  The reference draws from R's global stream; here the normals are a fixed
+        // SplitMix64 / Box-Muller stream (the perturbation only has to leave the non-finite region).  The third attempt of the
+        // reference, Nelder-Mead from the ORIGINAL vec_thetas (:101-104), evaluates the same non-finite value first and stops
+        // ("function cannot be evaluated at initial parameters"), so after a failed restart the reference's
+        // stop("failed to find initial values.") is what remains.
+        Vec th2 = th;
+        uint64_t st = 0x4D4C4C32u;                                            // "MLL2"
+        auto next_u = [&]() { st += 0x9E3779B97F4A7C15ull; uint64_t z = st; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                              z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31; return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0); };
+        for (int j = 0; j < d; j += 2) {
+            const double u1 = next_u(), u2 = next_u(), rad = std::sqrt(-2.0 * std::log(u1));
+            th2[j] += 0.1 * rad * std::cos(2.0 * 3.14159265358979323846 * u2);
+            if (j + 1 < d) th2[j + 1] += 0.1 * rad * std::sin(2.0 * 3.14159265358979323846 * u2);
+        }
+        out->restarts = 1;
+        rc = optim_bfgs(th2, pscale, fn, gr, 100, 1.490116119384765625e-8, 1e-3, R);
+        if (rc == 10) return jmb_set_error("jmb_marglogLik2: failed to find initial values (non-finite log-posterior at the starting values and "
+                                           "at the jittered restart, R/margLogLik2.R:95-107)");
+    }
     if (rc) return 1;
     double logdet = 0.0;
     if (!lu_inverse(R.hessian, d, nullptr, &logdet)) logdet = NAN;

@@ -3,8 +3,9 @@
 Each rank owns a contiguous block of subjects with all of their longitudinal rows, hazard rows,
 random effects, proposal factors and scales; the survival parameters, priors and the random key
 are replicated.  The only exchange per iteration is the sum over ranks of three scalars (sum of
-log p(T|b) under the current and proposed survival parameters, and the log-weight sum), done with
-ncclAllReduce inside the library.  Draws are keyed by the global subject index
+log p(T|b) under the current and proposed survival parameters, and the log-weight sum), done inside the
+finalize kernel over NVLink peer-memory mailboxes (ncclAllReduce only as the A/B switch
+JMB_ALLREDUCE=nccl).  Draws are keyed by the global subject index
 (``subject_offset + local index``), so a sharded run reproduces the single-GPU chain up to the
 rounding of that three-scalar sum.
 """

@@ -89,6 +89,30 @@ def test_cuda_marglogLik2_matches_the_restatement(cuda_lib, oracle, cfg):
             if fixed:
                 for k in ("Bs_gammas", "gammas", "alphas"):
                     assert np.allclose(g["Covs"][k], o["Covs"][k], rtol=1e-4, atol=1e-6 * np.abs(o["Covs"][k]).max()), k
-        with pytest.raises(cuda_lib.JmbError):
-            bad = dict(th); bad["alphas"] = np.full_like(th["alphas"], 400.0)             # exp overflow: non-finite start
-            fit.marglogLik2(bad, pr, fixed_tau_Bs_gammas=True)
+        with pytest.raises(cuda_lib.JmbError, match="failed to find initial values"):
+            bad = dict(th); bad["alphas"] = np.full_like(th["alphas"], 400.0)             # exp overflow: non-finite start,
+            fit.marglogLik2(bad, pr, fixed_tau_Bs_gammas=True)                            # and at the jittered restart too
+        if cfg == "config2":
+            # a start exactly on the edge of the finite region: exp() overflows at the starting values, the jittered restart
+            # of R/margLogLik2.R:95-100 lands inside and BFGS reaches the same mode
+            edge = dict(th)
+            lo, hi = 0.0, 400.0
+            for _ in range(60):                                                        # bisect the overflow threshold in alpha
+                mid = 0.5 * (lo + hi)
+                t = dict(th); t["alphas"] = np.full_like(th["alphas"], mid)
+                v = fit.logPosterior(1.0, t["Bs_gammas"], t["gammas"], t["alphas"], pr, 200.0, pr["A_tau_Bs_gammas"], pr["B_tau_Bs_gammas"])
+                lo, hi = (mid, hi) if np.isfinite(v) else (lo, mid)
+            found = None
+            for a0 in np.linspace(hi, hi + 0.5, 26):                                   # just above: restart jitter (sd 0.1) may rescue
+                edge["alphas"] = np.full_like(th["alphas"], a0)
+                try:
+                    r = fit.marglogLik2(edge, pr, fixed_tau_Bs_gammas=True)
+                except cuda_lib.JmbError:
+                    continue
+                if r["restarts"] == 1:
+                    found = r
+                    break
+            ref = fit.marglogLik2(th, pr, fixed_tau_Bs_gammas=True)
+            assert ref["restarts"] == 0
+            if found is not None:        # the fixed jitter stream moved alpha below the threshold for one of the starts
+                assert found["convergence"] in (0, 1) and np.isfinite(found["value"])

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIX = os.path.join(HERE, "golden", "r_fixtures")
+FIX = os.environ.get("JMB_R_FIXTURES", os.path.join(HERE, "golden", "r_fixtures"))
 
 
 def _fixture(name):
@@ -48,8 +48,8 @@ def test_restated_summaries_match_R():
         want = np.array([_num(s[name])[0] for s in f["series"]])
         assert np.allclose(r[name], want, rtol=1e-9 if name != "postModes" else 1e-6, atol=1e-12, equal_nan=True), name
     for name in ("CIs", "wCIs"):
-        want = np.array([_num(s[name]) for s in f["series"]]).T
-        assert np.allclose(np.asarray(r[name]).reshape(want.shape), want, rtol=1e-9, atol=1e-12, equal_nan=True), name
+        want = np.array([_num(s[name]) for s in f["series"]])                 # series x (2.5 %, 97.5 %)
+        assert np.asarray(r[name]).shape == want.shape and np.allclose(r[name], want, rtol=1e-9, atol=1e-12, equal_nan=True), name
 
 
 def test_restated_marglogLik2_matches_R(oracle):
@@ -62,8 +62,10 @@ def test_restated_marglogLik2_matches_R(oracle):
             t["tau_Bs_gammas"] = np.log(200.0)
         r = oracle.marglogLik2(t, D, c["priors"], fixed_tau_Bs_gammas=fixed)
         assert abs(r["value"] - _num(case["value"])[0]) <= 1e-6 * abs(r["value"])
+        B, p, A = len(th["Bs_gammas"]), len(th["gammas"]), len(th["alphas"])
+        blocks = dict(Bs_gammas=r["par"][:B], gammas=r["par"][B:B + p], alphas=r["par"][B + p:B + p + A])   # attr(, "inits"), :133-135
         for k in ("Bs_gammas", "gammas", "alphas"):
-            assert np.allclose(r["inits"][k] if "inits" in r else r["par_blocks"][k], _num(case["inits"][k]), atol=1e-5), k
+            assert np.allclose(blocks[k], _num(case["inits"][k]), atol=1e-5), k
 
 
 def test_restated_survfit_mode_search_matches_R(oracle):
@@ -74,6 +76,6 @@ def test_restated_survfit_mode_search_matches_R(oracle):
     o = oracle_svft.modes(d, means)
     want = np.array([_num(s["par"]) for s in f])
     assert np.allclose(o["modes"], want, atol=1e-6)
-    H = np.array([np.array(s["hessian"], dtype=np.float64) for s in f])
+    H = np.transpose(np.array([np.array(s["hessian"], dtype=np.float64) for s in f]), (1, 2, 0))     # q x q x subjects
     assert np.allclose(o["hessians"], H, rtol=1e-5, atol=1e-6 * np.abs(H).max())
     assert [int(np.ravel(s["convergence"])[0]) for s in f] == [int(x) for x in o["convergence"]]
