@@ -37,11 +37,11 @@ for name in %(names)r:
         # the compile-time specialised kernel and the TMA-staged kernel (two-stage cp.async.bulk + mbarrier pipeline per warp)
         c = make_cohort(name, n=128)     # 2 CTAs x 8 warps x 8 subjects: 4 (16 lanes) or 8 (32 lanes) pipeline steps per warp
         ctl = dict(c["control"]); ctl.update(n_burnin=4, n_iter=2, n_block=2, n_thin=2)
-        for mode in ("direct", None):
+        for mode, prefix in (("direct", "static:"), ("tma", "static-tma:"), (None, "static-rows")):   # None = the default: row-strided kernel
             if mode: os.environ["JMB_KERNEL"] = mode
             else: os.environ.pop("JMB_KERNEL", None)
             with api.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
-                assert fit.layout_info()["kernel"].startswith("static:" if mode else "static-tma:"), fit.layout_info()["kernel"]
+                assert fit.layout_info()["kernel"].startswith(prefix), fit.layout_info()["kernel"]
                 fit.set_draw(c["Data"])
                 fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
         os.environ["JMB_KERNEL"] = "generic"
