@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <queue>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -143,11 +145,14 @@ struct jmb_handle_s {
     const char* kernel_name = "generic";
     std::string kernel_label;
     int static_smem = 0, tma_smem = 0, tma_grid = 0, num_sms = 148;
-    int rows_smem = 0, rows_grid = 0, rows_G = 0; bool rows_early = false;
+    int rows_smem = 0, rows_grid = 0, rows_G = 0, rows_early = 0;
+    int* d_rows_order = nullptr; RowsMeta* d_rows_meta = nullptr;    // step lists of the (CTA, warp) slots; per-subject addressing
+    double rows_imbalance = 0.0;                                      // estimated cost of the slowest slot / the mean
     TmaArgs ta{};
     RowsArgs ra{};
     int kernel_mode = 0;            // 0 generic, 1 static direct, 2 static TMA-staged, 3 static row-strided groups (default)
     int select_kernel();
+    int rows_schedule(int G, int total_steps);
     int add_slot();
     // multi-GPU
     ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
@@ -159,7 +164,7 @@ struct jmb_handle_s {
     bool p2p = false;
 };
 
-template <class Spec, bool EARLY>
+template <class Spec, int EARLY>
 static void (*rows_kernel_of(int G))(int, ParamLayout, ChainConst, StepArgs, RowsArgs) {
     switch (G) {
         case 2: return jmb_step_rows<Spec, 2, EARLY>;
@@ -169,12 +174,98 @@ static void (*rows_kernel_of(int G))(int, ParamLayout, ChainConst, StepArgs, Row
     }
     return nullptr;
 }
-static void (*pick_rows_kernel(const ModelDesc& md, int G, bool early))(int, ParamLayout, ChainConst, StepArgs, RowsArgs) {
-    if (same_desc(md, SpecValueGaussian::d)) return early ? rows_kernel_of<SpecValueGaussian, true>(G) : rows_kernel_of<SpecValueGaussian, false>(G);
-    if (same_desc(md, SpecThreeOutcomes::d)) return early ? rows_kernel_of<SpecThreeOutcomes, true>(G) : rows_kernel_of<SpecThreeOutcomes, false>(G);
-    if (same_desc(md, SpecThreeOutcomesIC::d)) return early ? rows_kernel_of<SpecThreeOutcomesIC, true>(G) : rows_kernel_of<SpecThreeOutcomesIC, false>(G);
-    if (same_desc(md, SpecMultiState::d)) return early ? rows_kernel_of<SpecMultiState, true>(G) : rows_kernel_of<SpecMultiState, false>(G);
+template <class Spec>
+static void (*rows_kernel_of_early(int G, int early))(int, ParamLayout, ChainConst, StepArgs, RowsArgs) {
+    return early == 2 ? rows_kernel_of<Spec, 2>(G) : (early == 1 ? rows_kernel_of<Spec, 1>(G) : rows_kernel_of<Spec, 0>(G));
+}
+static void (*pick_rows_kernel(const ModelDesc& md, int G, int early))(int, ParamLayout, ChainConst, StepArgs, RowsArgs) {
+    if (same_desc(md, SpecValueGaussian::d)) return rows_kernel_of_early<SpecValueGaussian>(G, early);
+    if (same_desc(md, SpecThreeOutcomes::d)) return rows_kernel_of_early<SpecThreeOutcomes>(G, early);
+    if (same_desc(md, SpecThreeOutcomesIC::d)) return rows_kernel_of_early<SpecThreeOutcomesIC>(G, early);
+    if (same_desc(md, SpecMultiState::d)) return rows_kernel_of_early<SpecMultiState>(G, early);
     return nullptr;
+}
+
+// Steps of the row-strided kernel dealt to its (CTA, warp) slots.  A step's cost depends on the data - the row-loop trips (a warp
+// with an interval-censored subject walks the lower-interval rows too; a multi-state warp walks max(ntr) blocks) and the visit-row
+// trips of every outcome - so equal NUMBERS of steps per warp leave the slowest warp of the config-4 shard with 16 % more than the
+// average (13.2 steps per warp).  The steps are sorted by estimated cost and handed, longest first, to the least-loaded slot
+// (LPT); a slot walks its list in ascending step order.  The assignment is static, so the per-slot partial sums keep their fixed
+// order.  JMB_ROWS_LPT=0 restores the CTA-contiguous, warp-interleaved assignment of equal counts.
+int jmb_handle_s::rows_schedule(int G, int total_steps) {
+    const ModelDesc& md = mm.d;
+    const int spw = 32 / G, nslots = rows_grid * kRowsWarps;
+    const int NR = 1 + md.K * md.S, NJ = (NR + G - 1) / G, NJ_H = (1 + md.K + G - 1) / G;
+    double w_row = 0.135, w_vis = 0.05;              // cost of a step = 1 + w_row * row trips + w_vis * visit trips
+    if (const char* e = getenv("JMB_LPT_ROW")) w_row = atof(e);
+    if (const char* e = getenv("JMB_LPT_VIS")) w_vis = atof(e);
+    bool lpt = true;
+    if (const char* e = getenv("JMB_ROWS_LPT")) lpt = atoi(e) != 0;
+    std::vector<float> cost(total_steps);
+    for (int t = 0; t < total_steps; ++t) {
+        int ntr_w = 1, vtr = 0; bool any3 = false;
+        for (int k = 0; k < md.O; ++k) {
+            int mv = 0;
+            for (int g = 0; g < spw; ++g) { const int i = std::min(n - 1, t * spw + g); mv = std::max(mv, rowptr[k][i + 1] - rowptr[k][i]); }
+            vtr += (mv + G - 1) / G;
+        }
+        for (int g = 0; g < spw; ++g) {
+            const int i = std::min(n - 1, t * spw + g);
+            if (ms) ntr_w = std::max(ntr_w, trow[i + 1] - trow[i]);
+            else if (h_event[i] == 3.0) any3 = true;
+        }
+        const int nj = ms ? ntr_w * NJ : ((md.S == 2 && NJ > NJ_H) ? (any3 ? NJ : NJ_H) : NJ);
+        cost[t] = (float)(1.0 + w_row * nj + w_vis * vtr);
+    }
+    std::vector<std::vector<int>> lists(nslots);
+    std::vector<double> load(nslots, 0.0);
+    if (lpt) {
+        std::vector<int> idx(total_steps);
+        for (int t = 0; t < total_steps; ++t) idx[t] = t;
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+        typedef std::pair<double, int> LS;
+        std::priority_queue<LS, std::vector<LS>, std::greater<LS>> pq;
+        for (int sl = 0; sl < nslots; ++sl) pq.push(LS(0.0, sl));
+        for (int t : idx) {
+            LS top = pq.top(); pq.pop();
+            lists[top.second].push_back(t);
+            load[top.second] = top.first + cost[t];
+            pq.push(LS(load[top.second], top.second));
+        }
+        for (auto& v : lists) std::sort(v.begin(), v.end());
+    } else {
+        const int spc = (total_steps + rows_grid - 1) / rows_grid;
+        for (int c = 0; c < rows_grid; ++c)
+            for (int w = 0; w < kRowsWarps; ++w)
+                for (int t = c * spc + w; t < std::min(total_steps, (c + 1) * spc); t += kRowsWarps) { lists[c * kRowsWarps + w].push_back(t); load[c * kRowsWarps + w] += cost[t]; }
+    }
+    size_t len = 1; double tot = 0.0, mx = 0.0;
+    for (int sl = 0; sl < nslots; ++sl) { len = std::max(len, lists[sl].size()); tot += load[sl]; mx = std::max(mx, load[sl]); }
+    rows_imbalance = tot > 0.0 ? mx / (tot / nslots) : 1.0;
+    std::vector<int> order((size_t)nslots * len, -1);
+    for (int sl = 0; sl < nslots; ++sl) std::copy(lists[sl].begin(), lists[sl].end(), order.begin() + (size_t)sl * len);
+    ra.order_len = (int)len;
+    cudaFree(d_rows_order); d_rows_order = nullptr;
+    cudaError_t e = cudaMalloc(&d_rows_order, sizeof(int) * order.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d_rows_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { g_err = std::string("rows_schedule: ") + cudaGetErrorString(e); return 1; }
+    ra.order = d_rows_order;
+    ra.meta = nullptr;
+    if (rows_early == 2) {
+        std::vector<RowsMeta> meta(n);
+        for (int i = 0; i < n; ++i) {
+            RowsMeta& m = meta[i];
+            m.d0 = doff[i]; m.c0 = coff[i]; m.v[0] = m.v[1] = m.v[2] = 0;
+            for (int k = 0; k < md.O && k < 3; ++k) m.v[k] = rowptr[k][i + 1] - rowptr[k][i];
+            m.ntr = ms ? trow[i + 1] - trow[i] : 1;
+        }
+        cudaFree(d_rows_meta); d_rows_meta = nullptr;
+        e = cudaMalloc(&d_rows_meta, sizeof(RowsMeta) * (size_t)std::max(n, 1));
+        if (e == cudaSuccess) e = cudaMemcpy(d_rows_meta, meta.data(), sizeof(RowsMeta) * (size_t)n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { g_err = std::string("rows_schedule(meta): ") + cudaGetErrorString(e); return 1; }
+        ra.meta = d_rows_meta;
+    }
+    return 0;
 }
 
 int jmb_handle_s::select_kernel() {
@@ -231,12 +322,14 @@ int jmb_handle_s::select_kernel() {
     // row-strided groups (jmb_step_rows.cuh): G lanes per subject, 32 / G subjects per warp step; the default
     if (same_desc(md, SpecMultiState::d)) kernel_name = "multistate_illness_death";
     {
-        // group width and early-stage staging per model shape, from the sweeps in profiles/r2_rows_kernel.md
+        // group width and staging of a step's early data per model shape, from the sweeps in profiles/r2_rows_kernel.md:
+        // early = 0 read in place (+ L2 prefetch), 1 bulk-copied per-warp stage, 2 cp.async group slots + lane-private visit slots
         int G = (md.S == 2 || md.MS) ? 8 : (md.O > 1 ? 16 : 4);
-        bool early = (md.S == 1 && md.O > 1 && !md.MS);
+        int early = (md.S == 1 && md.O > 1 && !md.MS) ? 1 : 0;
         if (const char* g = getenv("JMB_ROWS_G")) G = atoi(g);
         if (G != 2 && G != 4 && G != 8 && G != 16) G = 8;
-        if (const char* e = getenv("JMB_ROWS_EARLY")) early = atoi(e) != 0;
+        if (const char* e = getenv("JMB_ROWS_EARLY")) early = std::max(0, std::min(2, atoi(e)));
+        if (early == 2 && md.O > 3) early = 0;
         rows_kernel = pick_rows_kernel(md, G, early);
         rows_early = early;
         if (rows_kernel) {
@@ -245,10 +338,12 @@ int jmb_handle_s::select_kernel() {
             // shared memory: parameter pairs | invD | per-group partial sums | early-stage barriers | hazard-row ring | early stages
             int nv = 2 + md.WB + (md.w2_const ? 0 : md.p);
             for (int t = 0; t < md.T; ++t) nv += 1 + (md.rt[t] - md.zz_ones0[t]) + (md.u_ones[t] ? 0 : md.ut[t]);
-            const long long fixed_b = 8LL * (2 * mm.P + (md.q * md.q + 1) / 2 * 2 + (kRowsWarps * spw * 3 + 1) / 2 * 2) + 8LL * kRowsWarps +
+            const long long fixed_b = 8LL * (2 * mm.P + (md.q * md.q + 1) / 2 * 2 + (kRowsWarps * spw * 3 + 1) / 2 * 2) + 8LL * ((kRowsWarps + 1) / 2 * 2) +
                                       8LL * kRowsWarps * JMB_ROWS_RING * nv * 32;
-            ra.cap_dl = 0; ra.cap_cl = 0;
-            if (early) {
+            const long long cta_budget = (227LL * 1024) / kRowsCtas - 1024 - 64;      // per-CTA share of an SM, minus the reserved KB and the static bytes
+            const int RSs = (md.q + 2) / 2 * 2;
+            ra.cap_dl = 0; ra.cap_cl = 0; ra.vt = 0;
+            if (early == 1) {
                 // early stage of a subject: head | state | draws | visit rows of the design and of the per-draw record; the
                 // capacity covers the longest visit segment unless that would not leave room for kRowsCtas CTAs per SM
                 // (subjects beyond the capacity read their visit rows in place)
@@ -257,8 +352,7 @@ int jmb_handle_s::select_kernel() {
                     max_dl = std::max(max_dl, doff[i + 1] - doff[i] - mm.L.o_long);
                     max_cl = std::max(max_cl, coff[i + 1] - coff[i] - mm.L.c_long);
                 }
-                const int RSs = (md.q + 2) / 2 * 2;
-                const long long budget = ((222LL * 1024) / kRowsCtas - fixed_b - 6400 /* static: rows_publish_sums */) / 8 / ((long long)kRowsWarps * spw) - (kRowsHdr + mm.L.state_stride + RSs);
+                const long long budget = (cta_budget - fixed_b) / 8 / ((long long)kRowsWarps * spw) - (kRowsHdr + mm.L.state_stride + RSs);
                 long long cd = (max_dl + 1) / 2 * 2, cc_ = (max_cl + 1) / 2 * 2;
                 if (cd + cc_ > budget) {
                     const double f = (double)std::max<long long>(budget, 0) / (double)(cd + cc_);
@@ -267,21 +361,44 @@ int jmb_handle_s::select_kernel() {
                 ra.cap_dl = (int)std::max<long long>(cd, 0); ra.cap_cl = (int)std::max<long long>(cc_, 0);
                 const int RSd = kRowsHdr + mm.L.state_stride + RSs + ra.cap_dl + ra.cap_cl;
                 rows_smem = (int)(fixed_b + 8LL * kRowsWarps * spw * RSd);
+            } else if (early == 2) {
+                // group slots (head | state | draws) + as many visit-row trips in the lane-private visit slots as the longest
+                // segment needs and the CTA's share of the SM holds
+                int vs = 0, maxv = 1;
+                for (int k = 0; k < md.O; ++k) {
+                    vs += 2 + md.qk[k] - md.z_ones0[k];
+                    for (int i = 0; i < n; ++i) maxv = std::max(maxv, rowptr[k][i + 1] - rowptr[k][i]);
+                }
+                const long long slots_b = 8LL * kRowsWarps * spw * (kRowsHdr + mm.L.state_stride + RSs) * (JMB_ROWS_REREAD ? 2 : 1);
+                const long long per_trip = 8LL * kRowsWarps * 32 * vs;
+                int vt = (maxv + G - 1) / G;
+                if (const char* v = getenv("JMB_ROWS_VT")) vt = std::max(0, atoi(v));
+                vt = (int)std::min<long long>(vt, std::max<long long>(0, (cta_budget - fixed_b - slots_b) / per_trip));
+                ra.vt = vt;
+                rows_smem = (int)(fixed_b + slots_b + per_trip * vt);
             } else {
                 rows_smem = (int)fixed_b;
             }
-            {   // always: the kernel's static shared memory (6 KB) counts against the 48 KB default as well
+            {   // always: the kernel's static shared memory counts against the 48 KB default as well
                 cudaError_t e = cudaFuncSetAttribute((const void*)rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem);
                 if (e != cudaSuccess) { g_err = std::string("cudaFuncSetAttribute(rows): ") + cudaGetErrorString(e); return 1; }
             }
+            if (const char* co = getenv("JMB_ROWS_CARVEOUT"))   // experiments: shared-memory carve-out in percent (the rest of the 256 KB is L1)
+                cudaFuncSetAttribute((const void*)rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
             const long long total_steps = ((long long)n + spw - 1) / spw;
             int waves = 1;                                   // persistent: one resident wave of CTAs
             if (const char* w = getenv("JMB_ROWS_WAVES")) waves = std::max(1, atoi(w));
             const long long ctas = std::max<long long>(1, std::min<long long>((total_steps + kRowsWarps - 1) / kRowsWarps, (long long)kRowsCtas * num_sms * waves));
-            ra.steps_per_cta = (int)((total_steps + ctas - 1) / ctas);
-            rows_grid = (int)((total_steps + ra.steps_per_cta - 1) / ra.steps_per_cta);
+            rows_grid = (int)ctas;
             ra.prefetch = 1;
             if (const char* pf = getenv("JMB_ROWS_PREFETCH")) ra.prefetch = atoi(pf) ? 1 : 0;
+            if (rows_schedule(G, (int)total_steps)) return 1;
+            if (getenv("JMB_ROWS_DEBUG")) {
+                int occ = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)rows_kernel, kRowsThreads, (size_t)rows_smem);
+                fprintf(stderr, "[jmb rows] G=%d early=%d smem=%d B vt=%d CTAs/SM=%d grid=%d steps=%lld list=%d est. slowest/mean slot=%.4f\n",
+                        G, early, rows_smem, ra.vt, occ, rows_grid, total_steps, ra.order_len, rows_imbalance);
+            }
             kernel_mode = 3;
         }
     }
@@ -296,7 +413,7 @@ int jmb_handle_s::select_kernel() {
         case 0: kernel_label = "generic"; break;
         case 1: kernel_label = std::string("static:") + kernel_name; break;
         case 2: kernel_label = std::string("static-tma:") + kernel_name; break;
-        default: kernel_label = std::string("static-rows") + std::to_string(rows_G) + (rows_early ? "e:" : ":") + kernel_name; break;
+        default: kernel_label = std::string("static-rows") + std::to_string(rows_G) + (rows_early == 2 ? "p:" : (rows_early ? "e:" : ":")) + kernel_name; break;
     }
     return 0;
 }
@@ -720,7 +837,7 @@ extern "C" int jmb_destroy(jmb_handle h) {
     for (ChainCtx* x : h->slots) if (x->stream) cudaStreamSynchronize(x->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->d_drec); cudaFree(h->d_doff); cudaFree(h->d_coff); cudaFree(h->d_rowptr); cudaFree(h->d_eval);
-    cudaFree(h->d_trow);
+    cudaFree(h->d_trow); cudaFree(h->d_rows_order); cudaFree(h->d_rows_meta);
     cudaFree(h->d_Rchol); cudaFree(h->d_xrec); cudaFree(h->d_xoff); cudaFree(h->d_betas);
     for (size_t r = 0; r < h->peer_ptrs.size(); ++r)
         if (h->peer_ptrs[r] && (int)r != h->rank) cudaIpcCloseMemHandle(h->peer_ptrs[r]);

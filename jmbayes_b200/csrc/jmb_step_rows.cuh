@@ -31,10 +31,24 @@
 
 namespace jmb {
 
+// per-subject addressing of the pipelined variant (EARLY = 2): everything the copies of a subject's early data and visit
+// rows need, in one 32-byte read (the record head, where the visit counts live, would be a dependent load)
+struct alignas(32) RowsMeta {
+    long long d0, c0;        // offsets of the design / per-draw record (doubles)
+    int v[3];                // visit counts of the outcomes (rows kernels exist for O <= 3)
+    int ntr;                 // transition rows (multi-state fits; 1 otherwise)
+};
+static_assert(sizeof(RowsMeta) == 32, "RowsMeta is read as two 16-byte words");
+
 struct RowsArgs {
-    int steps_per_cta;       // warp steps (of 32 / G subjects) owned by one CTA
-    int prefetch;            // EARLY = false only: 1 = L2 bulk prefetch of the next step's early data
-    int cap_dl, cap_cl;      // early stage: capacity (doubles) of the visit rows of the design / per-draw record of one subject
+    // warp steps (of 32 / G subjects) of every (CTA, warp) slot: order[slot * order_len + k], -1 = none.  The host deals the
+    // steps to the slots by estimated cost (longest processing time first; jmb200.cu) - with an equal NUMBER of steps per warp
+    // the slowest warp of the config-4 shard carries 16 % more row-loop trips than the average one
+    const int* order; int order_len;
+    const RowsMeta* meta;    // [n] (EARLY = 2)
+    int vt;                  // EARLY = 2: visit-row trips of an outcome held in the lane-private visit slots (later trips are read in place)
+    int prefetch;            // EARLY = 0 only: 1 = L2 bulk prefetch of the next step's early data
+    int cap_dl, cap_cl;      // EARLY = 1: capacity (doubles) of the visit rows of the design / per-draw record of one subject
     // several ranks (peer_mbox != NULL): the last CTA to finish reduces the per-CTA partial sums and stores the rank's three sums
     // into every rank's mailbox itself, so that the NVLink flight overlaps the kernel boundary and the finalize kernel finds
     // the stamps waiting (fields as in FinalizeArgs)
@@ -53,6 +67,18 @@ struct RowsArgs {
 #ifndef JMB_EXP3
 #define JMB_EXP3 1
 #endif
+// pipelined variant: two group slots per group, so that the per-subject values that are only needed after the row loop (log u,
+// the carried log-densities, counters, event) are re-read from the slot instead of being held in registers across the loop
+#ifndef JMB_ROWS_REREAD
+#define JMB_ROWS_REREAD 1
+#endif
+// ring copies by lane pairs: the lanes 2m / 2m + 1 of a warp walk neighbouring rows, so one 16-byte cp.async.cg of the even
+// (odd) lane fetches the pair's two values of an even (odd) slot.  Half the copies, and none of them passes through the L1:
+// the 8-byte copies (.ca is the only cache operator below 16 bytes) hold a 128-byte L1 line each while in flight, and 16 warps
+// keep about 120 KB of lines in flight - more than the L1 that is left once the shared memory of two CTAs exceeds 132 KB
+#ifndef JMB_ROWS_PAIR
+#define JMB_ROWS_PAIR 1
+#endif
 constexpr int kRowsThreads = JMB_ROWS_THREADS, kRowsCtas = JMB_ROWS_CTAS, kRowsWarps = JMB_ROWS_THREADS / 32;
 constexpr int kRowsHdr = 8;  // doubles of a record head that hold event, visit counts and the constant W2 row
 
@@ -66,6 +92,13 @@ __device__ __forceinline__ void cp_async8(double* dst, const double* src) {
     *dst = *src;
 #else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async16(double* dst, const double* src) {
+#if defined(JMB_EMU)
+    dst[0] = src[0]; dst[1] = src[1];
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 #endif
 }
 __device__ __forceinline__ void cp_async4(int* dst, const int* src) {
@@ -154,9 +187,41 @@ __device__ __forceinline__ double log_ptb_rows(double event, double lh, double H
     }
 }
 
+// The censoring terms of the three (survival parameters, b) pairs of a step at once - (current, new b), (proposed, old b),
+// (proposed, new b): the exponentials and logarithms are independent chains, and the term of the proposed parameters no longer
+// waits for the accept decision (which needs the first term) before it starts.
+#ifndef JMB_ROWS_PTB3
+#define JMB_ROWS_PTB3 1
+#endif
+__device__ __forceinline__ void log_ptb_rows3(const double event, const double (&lh)[3], const double (&H)[3], const double (&HL)[3], double (&out)[3]) {
+    double eH[3], eHL[3];
+    exp3(-H[0], -H[1], -H[2], eH[0], eH[1], eH[2]);
+    exp3(-HL[0], -HL[1], -HL[2], eHL[0], eHL[1], eHL[2]);
+    double lg[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double arg = (event == 2.0) ? (1.0 - eH[i]) : ((event == 3.0) ? (eHL[i] - eH[i]) : 1.0);
+        lg[i] = log(arg);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double r = 0.0;
+        if (event == 1.0) r = lh[i] - H[i];
+        if (event == 0.0) r = 0.0 - H[i];
+        if (event == 2.0 || event == 3.0) r = lg[i];
+        out[i] = r;
+    }
+}
+
 // GLMM log-density of this lane's visit rows (lin_predF + log_longF, src/fast_LAPRWM.cpp:67-78,168-202); lrec / lcrec point
 // at the visit rows of the design / per-draw record, in global memory or in the warp's early stage (the call sites keep
 // the two apart so that the loads compile to LDS / LDG rather than generic loads)
+// Two rows of an outcome per loop trip (rows r and r + G): their log-densities are independent dependency chains (exp / divide /
+// log of the logit and Poisson rows), evaluated side by side instead of one after the other; the sum keeps the row order.  A lane
+// without a second row re-evaluates its first one and drops the result.
+#ifndef JMB_ROWS_VIS2
+#define JMB_ROWS_VIS2 1
+#endif
 template <class Spec, int G>
 __device__ __forceinline__ double visit_rows(const double* __restrict__ lrec, const double* __restrict__ lcrec, const int* vcount,
                                              const double (&bn)[Spec::d.q], const double (&isig)[Spec::d.O], const int l) {
@@ -166,7 +231,7 @@ __device__ __forceinline__ double visit_rows(const double* __restrict__ lrec, co
         constexpr int k = kc;
         constexpr int ones0 = Spec::d.z_ones0[k], qk = Spec::d.qk[k];
         const int v = vcount[k];
-        for (int r = l; r < v; r += G) {
+        auto eta_of = [&](const int r) {
             double eta = lcrec[r];
             if constexpr (ones0 == 1) { constexpr int cz = Spec::d.re_inds[k][0]; eta += bn[cz]; }
             sfor<qk - ones0>([&](auto jc) {
@@ -174,8 +239,108 @@ __device__ __forceinline__ double visit_rows(const double* __restrict__ lrec, co
                 constexpr int cj = Spec::d.re_inds[k][j + ones0];
                 eta += lrec[(1 + j) * v + r] * bn[cj];
             });
-            v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta, isig[k]);
+            return eta;
+        };
+#if JMB_ROWS_VIS2
+        for (int r = l; r < v; r += 2 * G) {
+            const bool two = r + G < v;
+            const int rb = two ? r + G : r;
+            const double eta0 = eta_of(r), eta1 = eta_of(rb);
+            const double ld0 = logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta0, isig[k]);
+            const double ld1 = logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[rb], eta1, isig[k]);
+            v_pyb += ld0;
+            if (two) v_pyb += ld1;
         }
+#else
+        for (int r = l; r < v; r += G) v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta_of(r), isig[k]);
+#endif
+        constexpr int lcols = Spec::L.long_cols[k];
+        lrec += lcols * v;
+        lcrec += v;
+    });
+    return v_pyb;
+}
+
+// Pipelined variant (EARLY = 2): lane-private visit slots.  Trip t (rows l + t G) of outcome k occupies per(k) values - y, the
+// per-draw linear predictor, the stored Z columns - at [(t VS + base(k)) * 32 + lane]; they are cp.async-copied by the lane that
+// reads them, one row loop ahead of their use, so the visit loops read shared memory without bank conflicts and never wait for
+// the L2.  Trips beyond ra.vt (segments longer than vt G rows) are read in place.
+template <class Spec>
+struct VisitSlots {
+    static constexpr int per(int k) { return 2 + Spec::d.qk[k] - Spec::d.z_ones0[k]; }
+    static constexpr int base(int k) { int b = 0; for (int i = 0; i < k; ++i) b += per(i); return b; }
+    static constexpr int VS = base(Spec::d.O);
+};
+
+template <class Spec, int G>
+__device__ __forceinline__ void issue_visit_rows(double* vs, const int vt, const double* __restrict__ lrec, const double* __restrict__ lcrec,
+                                                 const int (&vcount)[Spec::d.O], const int l) {
+    constexpr int O = Spec::d.O, VS = VisitSlots<Spec>::VS;
+    sfor<O>([&](auto kc) {
+        constexpr int k = kc;
+        constexpr int ones0 = Spec::d.z_ones0[k], qk = Spec::d.qk[k], sb = VisitSlots<Spec>::base(k);
+        const int v = vcount[k];
+        int r = l;
+        for (int t = 0; t < vt && r < v; ++t, r += G) {
+            double* const dst = vs + (size_t)(t * VS + sb) * 32;
+            cp_async8(dst, lrec + r);
+            cp_async8(dst + 32, lcrec + r);
+            sfor<qk - ones0>([&](auto jc) { constexpr int j = jc; cp_async8(dst + (2 + j) * 32, lrec + (1 + j) * v + r); });
+        }
+        constexpr int lcols = Spec::L.long_cols[k];
+        lrec += lcols * v;
+        lcrec += v;
+    });
+}
+
+// same arithmetic and summation order as visit_rows; the first vt trips of every outcome come from the visit slots
+template <class Spec, int G>
+__device__ __forceinline__ double visit_rows_slots(const double* vs, const int vt, const double* __restrict__ lrec, const double* __restrict__ lcrec,
+                                                   const int* vcount, const double (&bn)[Spec::d.q], const double (&isig)[Spec::d.O], const int l) {
+    constexpr int O = Spec::d.O, VS = VisitSlots<Spec>::VS;
+    double v_pyb = 0.0;
+    sfor<O>([&](auto kc) {
+        constexpr int k = kc;
+        constexpr int ones0 = Spec::d.z_ones0[k], qk = Spec::d.qk[k], sb = VisitSlots<Spec>::base(k);
+        const int v = vcount[k];
+        auto eta_slot = [&](const double* sl) {
+            double eta = sl[32];
+            if constexpr (ones0 == 1) { constexpr int cz = Spec::d.re_inds[k][0]; eta += bn[cz]; }
+            sfor<qk - ones0>([&](auto jc) {
+                constexpr int j = jc;
+                constexpr int cj = Spec::d.re_inds[k][j + ones0];
+                eta += sl[(2 + j) * 32] * bn[cj];
+            });
+            return eta;
+        };
+        auto eta_of = [&](const int r) {
+            double eta = lcrec[r];
+            if constexpr (ones0 == 1) { constexpr int cz = Spec::d.re_inds[k][0]; eta += bn[cz]; }
+            sfor<qk - ones0>([&](auto jc) {
+                constexpr int j = jc;
+                constexpr int cj = Spec::d.re_inds[k][j + ones0];
+                eta += lrec[(1 + j) * v + r] * bn[cj];
+            });
+            return eta;
+        };
+        int r = l, t = 0;
+#if JMB_ROWS_VIS2
+        for (; t + 1 < vt && r < v; t += 2, r += 2 * G) {                 // trips t and t + 1, both in the slots
+            const bool two = r + G < v;
+            const double* const sl0 = vs + (size_t)(t * VS + sb) * 32;
+            const double* const sl1 = two ? sl0 + VS * 32 : sl0;
+            const double eta0 = eta_slot(sl0), eta1 = eta_slot(sl1);
+            const double ld0 = logdens_static<Spec::d.fam[k], Spec::d.link[k]>(sl0[0], eta0, isig[k]);
+            const double ld1 = logdens_static<Spec::d.fam[k], Spec::d.link[k]>(sl1[0], eta1, isig[k]);
+            v_pyb += ld0;
+            if (two) v_pyb += ld1;
+        }
+#endif
+        for (; t < vt && r < v; ++t, r += G) {
+            const double* const sl = vs + (size_t)(t * VS + sb) * 32;
+            v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(sl[0], eta_slot(sl), isig[k]);
+        }
+        for (; r < v; r += G) v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta_of(r), isig[k]);
         constexpr int lcols = Spec::L.long_cols[k];
         lrec += lcols * v;
         lcrec += v;
@@ -184,17 +349,18 @@ __device__ __forceinline__ double visit_rows(const double* __restrict__ lrec, co
 }
 
 // last CTA of a multi-rank launch: fixed-order sum of the per-CTA partials, then one store per rank (values, fence, stamp)
-__device__ __noinline__ void rows_publish_sums(const double* partials, const int n_partials, const RowsArgs ra) {
-    __shared__ double s_pub[3 * JMB_ROWS_THREADS];
+__device__ __noinline__ void rows_publish_sums(const double* partials, const int n_partials, const RowsArgs ra, double* s_pub /* [3 * JMB_ROWS_THREADS] */) {
     const int tid = threadIdx.x;
     double t0 = 0.0, t1 = 0.0, t2 = 0.0;
     for (int i = tid; i < n_partials; i += JMB_ROWS_THREADS) { t0 += __ldcg(partials + i * 3); t1 += __ldcg(partials + i * 3 + 1); t2 += __ldcg(partials + i * 3 + 2); }
     s_pub[tid] = t0; s_pub[JMB_ROWS_THREADS + tid] = t1; s_pub[2 * JMB_ROWS_THREADS + tid] = t2;
     __syncthreads();
-    for (int w = JMB_ROWS_THREADS / 2; w > 0; w >>= 1) {
-        if (tid < w) { s_pub[tid] += s_pub[tid + w]; s_pub[JMB_ROWS_THREADS + tid] += s_pub[JMB_ROWS_THREADS + tid + w]; s_pub[2 * JMB_ROWS_THREADS + tid] += s_pub[2 * JMB_ROWS_THREADS + tid + w]; }
-        __syncthreads();
+    if (tid < 3) {                                      // any block size: thread-order sum (this path runs once per launch, in one CTA)
+        double t = 0.0;
+        for (int i = 0; i < JMB_ROWS_THREADS; ++i) t += s_pub[tid * JMB_ROWS_THREADS + i];
+        s_pub[tid * JMB_ROWS_THREADS] = t;
     }
+    __syncthreads();
     if (tid < ra.nranks) {
         const long long base = ((long long)(ra.slot * 2 + (int)(ra.stamp & 1ull)) * ra.nranks);
         double* dst = ra.peer_mbox[tid] + (base + ra.rank) * 4;
@@ -205,7 +371,7 @@ __device__ __noinline__ void rows_publish_sums(const double* partials, const int
     if (tid == 0) *ra.ticket = 0u;                    // ready for the next launch on this chain slot
 }
 
-template <class Spec, int G, bool EARLY>
+template <class Spec, int G, int EARLY>
 __global__ void __launch_bounds__(JMB_ROWS_THREADS, JMB_ROWS_CTAS)
 jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_constant__ ChainConst cc,
               const __grid_constant__ StepArgs a, const RowsArgs ra) {
@@ -225,6 +391,14 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
     constexpr int NJ_H = (1 + K + G - 1) / G;           // trips that hold the event-time row and the K rows of H
     constexpr int RS = (q + 2) / 2 * 2;                 // rng stride: q increments + log u, padded to even
     constexpr int NV = RowSlots<Spec>::NV, RING = JMB_ROWS_RING, LEAD = RING > 0 ? RING - 1 : 0;
+    constexpr bool PAIR = JMB_ROWS_PAIR != 0 && RING > 0;
+    static_assert(!PAIR || (RP % 2 == 0 && G % 2 == 0 && oW1off % 2 == 0 && oW1v % 2 == 0 && oPw % 2 == 0 && (W2C || oW2 % 2 == 0) && HB % 2 == 0),
+                  "paired ring copies move 16-byte-aligned pairs of rows");
+    constexpr bool E1 = EARLY == 1, E2 = EARLY == 2;    // early data: 0 read in place (+ L2 prefetch), 1 bulk-copied stage, 2 cp.async slots
+    constexpr int EH = kRowsHdr + SS + RS;              // E2: head | state | draws of a subject, one slot per group
+    constexpr int VS = VisitSlots<Spec>::VS;
+    static_assert(EARLY >= 0 && EARLY <= 2, "EARLY");
+    static_assert(!E2 || (RING == 2 && O <= 3), "the pipelined variant orders its cp.async groups around a two-stage ring");
     static_assert(32 % G == 0 && G >= 2 && G <= 16, "G lanes per subject");
     static_assert(LEAD <= NJ_H, "the trips copied ahead of the record head must be trips every subject needs");
     static_assert(SS % 2 == 0 && RS % 2 == 0 && oLong % 2 == 0 && cLong % 2 == 0, "16-byte pieces");
@@ -236,39 +410,55 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
     double* s_invD = smem + 2 * P;                       // [q*q]
     double* s_red = s_invD + (q * q + 1) / 2 * 2;        // [WARPS * SPW][3]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + (WARPS * SPW * 3 + 1) / 2 * 2);      // [WARPS] early-stage barriers
-    double* const s_ring0 = reinterpret_cast<double*>(s_bar + WARPS);                        // [WARPS][RING][NV][32]
-    // early stage of a subject: head | state | draws | visit rows (design) | visit rows (per-draw)
-    const int ES = kRowsHdr + SS + RS + ra.cap_dl + ra.cap_cl;
+    double* const s_ring0 = reinterpret_cast<double*>(s_bar + (WARPS + 1) / 2 * 2);                        // [WARPS][RING][NV][32]
+    // E1: early stage of a subject: head | state | draws | visit rows (design) | visit rows (per-draw)
+    // E2: [WARPS][SPW][EH] group slots, then [WARPS][vt][VS][32] lane-private visit slots
+    constexpr int ESLOTS = (E2 && JMB_ROWS_REREAD) ? 2 : 1;
+    const int ES = E2 ? EH * ESLOTS : (kRowsHdr + SS + RS + ra.cap_dl + ra.cap_cl);
     double* const s_early0 = s_ring0 + (size_t)WARPS * RING * NV * 32;                       // [WARPS][SPW][ES]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
     const int grp = lane32 / G, l = lane32 % G;
     double* const s_ring = s_ring0 + (size_t)warp * RING * NV * 32 + lane32;
-    double* const my_early = s_early0 + ((size_t)warp * SPW + grp) * ES;
+    double* const my_early0 = s_early0 + ((size_t)warp * SPW + grp) * ES;
+    double* my_early = my_early0;                        // E2 with two slots: slot of the current step
+    double* const s_vis = s_early0 + (size_t)WARPS * SPW * ES + (size_t)warp * (E2 ? ra.vt : 0) * VS * 32 + lane32;
     uint64_t* const bar = s_bar + warp;
-    // this warp's steps: CTA-contiguous chunk, warps interleaved
+    // this warp's steps: the list the host dealt to the (CTA, warp) slot
     const long long n = a.n;
-    const long long step0 = (long long)blockIdx.x * ra.steps_per_cta;
-    const long long total_steps = (n + SPW - 1) / SPW;
-    const long long step_end = min(total_steps, step0 + ra.steps_per_cta);
-    auto subject_of = [&](long long step) { return min(n - 1, step * SPW + grp); };
+    const int* const my_order = ra.order + (size_t)(blockIdx.x * WARPS + warp) * ra.order_len;
+    auto subject_of = [&](int step) { return min(n - 1, (long long)step * SPW + grp); };
+    auto load_meta = [&](const long long sj, long long& e0, long long& f0, int (&mv)[O], int& mtr) {
+        const RowsMeta m = ra.meta[sj];                  // 32-byte aligned: two 16-byte loads
+        e0 = m.d0; f0 = m.c0;
+        sfor<O>([&](auto kc) { mv[kc] = m.v[kc]; });
+        mtr = m.ntr;
+    };
 
     // offsets of this group's subject in the first step; loaded before the dependency wait (the offset tables never change)
-    long long t_step = step0 + warp;
+    int ko = 0;                                           // position in the slot's list
+    int t_step = ra.order_len > 0 ? my_order[0] : -1;
+    int t_next = ra.order_len > 1 ? my_order[1] : -1;
+    if (t_step < 0) t_next = -1;
     long long d0 = 0, d1 = 0, c0 = 0, c1 = 0;
     int ntr = 1;                                          // transition rows of this group's subject
-    if (t_step < step_end) {
+    int mvc[O];                                           // E2: visit counts of the subject whose copies are issued next
+    sfor<O>([&](auto kc) { mvc[kc] = 0; });
+    if (t_step >= 0) {
         const long long s = subject_of(t_step);
-        d0 = a.doff[s]; d1 = a.doff[s + 1]; c0 = a.coff[s]; c1 = a.coff[s + 1];
-        if constexpr (MS) ntr = a.trow[s + 1] - a.trow[s];
+        if constexpr (E2) load_meta(s, d0, c0, mvc, ntr);
+        else {
+            d0 = a.doff[s]; d1 = a.doff[s + 1]; c0 = a.coff[s]; c1 = a.coff[s + 1];
+            if constexpr (MS) ntr = a.trow[s + 1] - a.trow[s];
+        }
     }
-    if constexpr (EARLY) { if (lane32 == 0) mbar_init(bar, SPW); }
+    if constexpr (E1) { if (lane32 == 0) mbar_init(bar, SPW); }
     pdl_wait();
     pdl_trigger();
     for (int j = tid; j < P; j += THREADS) s_cp[j] = make_double2(a.par[pl.cur + j], a.par[pl.prop + j]);
     for (int j = tid; j < q * q; j += THREADS) s_invD[j] = a.par[pl.invD + j];
 #if !defined(JMB_EMU)
-    if constexpr (EARLY) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if constexpr (E1) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
     const int i_blk = a.ctl->i;
     const bool last_acc = a.ctl->last_accept != 0;
@@ -297,24 +487,50 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         if (cl) bulk_g2s(my_early + kRowsHdr + SS + RS + ra.cap_dl, a.crec + f0 + lc, cl, bar);
     };
     uint32_t phase = 0;
-    if constexpr (EARLY) { if (t_step < step_end && l == 0) issue_early(subject_of(t_step), d0, d1, c0, c1, ntr); }
+    if constexpr (E1) { if (t_step >= 0 && l == 0) issue_early(subject_of(t_step), d0, d1, c0, c1, ntr); }
+    // E2: cp.async copies of one subject's early data (the group's lanes share the 16-byte pieces of head | state | draws into the
+    // group slot) and of this lane's visit rows (into its visit slots); one commit group
+    auto issue_ev = [&](double* const slot, const long long sj, const long long e0, const long long f0, const int (&mv)[O], const int mtr) {
+        constexpr int H2 = kRowsHdr / 2, S2 = SS / 2, R2 = RS / 2;
+#pragma unroll
+        for (int i = 0; i < (H2 + S2 + R2 + G - 1) / G; ++i) {
+            const int c = l + i * G;
+            if (c < H2 + S2 + R2) {
+                const double* src = (c < H2) ? (a.drec + e0 + 2 * c)
+                                             : ((c < H2 + S2) ? (a.state + sj * SS + 2 * (c - H2)) : (rng_it + sj * RS + 2 * (c - H2 - S2)));
+                cp_async16(slot + 2 * c, src);
+            }
+        }
+        issue_visit_rows<Spec, G>(s_vis, ra.vt, a.drec + e0 + oLong + (size_t)(mtr - 1) * HB, a.crec + f0 + (size_t)mtr * cLong, mv, l);
+        cp_async_commit();
+    };
+    if constexpr (E2) { if (t_step >= 0) issue_ev(my_early0, subject_of(t_step), d0, c0, mvc, ntr); }
 
     double acc_cur = 0.0, acc_prop = 0.0, acc_lw = 0.0;
-    for (; t_step < step_end; t_step += WARPS) {
-        const bool valid = t_step * SPW + grp < n;
+    for (; t_step >= 0; ++ko) {
+        const bool valid = (long long)t_step * SPW + grp < n;
         const long long s = subject_of(t_step);
         const double* __restrict__ rec0 = a.drec + d0;
         const double* __restrict__ crec0 = a.crec + c0;
-        const bool staged = EARLY && fits_early(d0, d1, c0, c1, ntr);
+        const bool staged = E1 && fits_early(d0, d1, c0, c1, ntr);
         // ---- next step of this warp: offsets now (used after the visit loops) ----
-        const long long t_next = t_step + WARPS;
-        const bool has_next = t_next < step_end;
+        const bool has_next = t_next >= 0;
+        const int t_next2 = (has_next && ko + 2 < ra.order_len) ? my_order[ko + 2] : -1;
         long long nd0 = 0, nd1 = 0, nc0 = 0, nc1 = 0;
         int n_ntr = 1;
         if (has_next) {
             const long long sn = subject_of(t_next);
-            nd0 = a.doff[sn]; nd1 = a.doff[sn + 1]; nc0 = a.coff[sn]; nc1 = a.coff[sn + 1];
-            if constexpr (MS) n_ntr = a.trow[sn + 1] - a.trow[sn];
+            if constexpr (E2) load_meta(sn, nd0, nc0, mvc, n_ntr);
+            else {
+                nd0 = a.doff[sn]; nd1 = a.doff[sn + 1]; nc0 = a.coff[sn]; nc1 = a.coff[sn + 1];
+                if constexpr (MS) n_ntr = a.trow[sn + 1] - a.trow[sn];
+            }
+        }
+        if constexpr (E2) {
+            // the copies of this step's early data and visit rows were issued one row loop ago; the group slot is shared
+            cp_async_wait<0>();
+            __syncwarp();
+            my_early = my_early0 + (ESLOTS == 2 ? (ko & 1) * EH : 0);
         }
         // every group of the warp walks the same number of blocks (the shuffles inside the loop need the whole warp); a group
         // past its own last block re-evaluates that block and discards the result
@@ -330,19 +546,31 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
             const int fb = MS ? min(f / NJ, ntr - 1) : 0, jr = MS ? f % NJ : f;
             const double* const rec = rec0 + (size_t)fb * HB;
             const double* const crec = crec0 + (size_t)fb * cLong;
-            const int rq = min(l + jr * G, RP - 1);
-            double* const dst = s_ring + (size_t)st * NV * 32;
-            cp_async4(reinterpret_cast<int*>(dst), reinterpret_cast<const int*>(rec + oW1off) + rq);
-            sfor<WB>([&](auto j) { constexpr int jv = j; cp_async8(dst + (1 + jv) * 32, rec + oW1v + jv * RP + rq); });
-            cp_async8(dst + (1 + WB) * 32, rec + oPw + rq);
-            if constexpr (!W2C) sfor<p>([&](auto j) { constexpr int jv = j; cp_async8(dst + (2 + WB + jv) * 32, rec + oW2 + jv * RP + rq); });
+            const int rq = PAIR ? (min(l + jr * G, RP - 1) & ~1) : min(l + jr * G, RP - 1);      // PAIR: the even row of the lane pair
+            double* const dst = (PAIR ? s_ring - (lane32 & 1) : s_ring) + (size_t)st * NV * 32;
+            [[maybe_unused]] const int par = lane32 & 1;
+            // slot v of the stage <- field starting at src (row 0); PAIR: lanes of parity v & 1 copy the pair's two values
+            auto put = [&](auto vc, const double* src) {
+                constexpr int v = vc;
+                if constexpr (PAIR) { if (par == (v & 1)) cp_async16(dst + v * 32, src + rq); }
+                else cp_async8(dst + v * 32, src + rq);
+            };
+            if constexpr (PAIR) {     // band offsets: 32 ints packed at the head of slot 0
+                if (par == 0) cp_async8(reinterpret_cast<double*>(reinterpret_cast<int*>(dst - (lane32 & ~1)) + (lane32 & ~1)),
+                                        reinterpret_cast<const double*>(reinterpret_cast<const int*>(rec + oW1off) + rq));
+            } else {
+                cp_async4(reinterpret_cast<int*>(dst), reinterpret_cast<const int*>(rec + oW1off) + rq);
+            }
+            sfor<WB>([&](auto j) { constexpr int jv = j; put(std::integral_constant<int, 1 + jv>{}, rec + oW1v + jv * RP); });
+            put(std::integral_constant<int, 1 + WB>{}, rec + oPw);
+            if constexpr (!W2C) sfor<p>([&](auto j) { constexpr int jv = j; put(std::integral_constant<int, 2 + WB + jv>{}, rec + oW2 + jv * RP); });
             sfor<T>([&](auto tc) {
                 constexpr int t = tc;
                 constexpr int tb = RowSlots<Spec>::term_base(t), nz = RowSlots<Spec>::nzz(t), nuu = RowSlots<Spec>::nu(t);
                 constexpr int oZZq = Spec::L.o_ZZ[t], oUq = Spec::L.o_U[t];
-                cp_async8(dst + tb * 32, crec + t * RP + rq);
-                sfor<nz>([&](auto jc) { constexpr int j = jc; cp_async8(dst + (tb + 1 + j) * 32, rec + oZZq + j * RP + rq); });
-                sfor<nuu>([&](auto uc) { constexpr int u = uc; cp_async8(dst + (tb + 1 + nz + u) * 32, rec + oUq + u * RP + rq); });
+                put(std::integral_constant<int, tb>{}, crec + t * RP);
+                sfor<nz>([&](auto jc) { constexpr int j = jc; put(std::integral_constant<int, tb + 1 + j>{}, rec + oZZq + j * RP); });
+                sfor<nuu>([&](auto uc) { constexpr int u = uc; put(std::integral_constant<int, tb + 1 + nz + u>{}, rec + oUq + u * RP); });
             });
         };
         if constexpr (RING > 0) {
@@ -352,8 +580,8 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
 
         // ---- head of the record, current state and this iteration's draws (uniform within the group, 16-byte loads) ----
         double stv[SS], rgv[RS], hdr[kRowsHdr];
-        if constexpr (EARLY) {
-            mbar_wait(bar, phase);
+        if constexpr (E1 || E2) {
+            if constexpr (E1) mbar_wait(bar, phase);
             phase ^= 1u;
             const double2* e2 = reinterpret_cast<const double2*>(smem + (my_early - smem));      // shared-memory provenance: LDS
             sfor<kRowsHdr / 2>([&](auto j) { const double2 v = e2[j]; hdr[2 * j] = v.x; hdr[2 * j + 1] = v.y; });
@@ -393,7 +621,9 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
 
         // ---- GLMM log-density over the visit segment ----
         double v_pyb;
-        if (staged) {
+        if constexpr (E2) {
+            v_pyb = visit_rows_slots<Spec, G>(s_vis, ra.vt, rec0 + oLong + (size_t)(ntr - 1) * HB, crec0 + (size_t)ntr * cLong, vcount, bn, isig, l);
+        } else if (staged) {
             const double* lr = smem + (my_early - smem) + kRowsHdr + SS + RS;
             v_pyb = visit_rows<Spec, G>(lr, lr + ra.cap_dl, vcount, bn, isig, l);
         } else {
@@ -401,10 +631,10 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         }
 
         // ---- the early data of the warp's next step start to travel now; they are used a whole row loop later ----
-        if constexpr (EARLY) {
+        if constexpr (E1) {
             __syncwarp();                        // every lane has finished reading the stage
             if (has_next && l == 0) { fence_proxy_async(); issue_early(subject_of(t_next), nd0, nd1, nc0, nc1, n_ntr); }
-        } else if (ra.prefetch && has_next && l == 0) {
+        } else if (!E2 && ra.prefetch && has_next && l == 0) {
             const long long sn = subject_of(t_next);
             l2_prefetch_bulk(a.drec + nd0, 64u);
             const long long lo = oLong + (long long)(n_ntr - 1) * HB, lc = (long long)n_ntr * cLong;
@@ -435,13 +665,28 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
             // ring: start the copies of trip jj + LEAD into the stage consumed in the previous trip, then wait for trip jj
             const double* const rs = s_ring + (size_t)(RING > 0 ? jj % (RING > 0 ? RING : 1) : 0) * NV * 32;
             if constexpr (RING > 0) {
+                if constexpr (PAIR) __syncwarp();        // the partner lane has read the stage that is filled next (trip jj - 1)
                 if (jj + LEAD < nj) issue_row(jj + LEAD, (jj + LEAD) % RING);
                 cp_async_commit();
-                cp_async_wait<LEAD>();
+                if constexpr (E2) {
+                    // the next step's early data and visit rows start to travel behind trip 1: the groups younger than trip jj
+                    // are then {trip 1, next step} at jj = 0, {next step, trip 2} at jj = 1 and {trip jj + 1} afterwards, so the
+                    // copies have two trips (or, in a two-trip loop, until the top of the next step) to arrive
+                    if (jj == 0) {
+                        __syncwarp();            // every lane of the group has read the group slot (top of this step)
+                        if (has_next) issue_ev(my_early0 + (ESLOTS == 2 ? ((ko + 1) & 1) * EH : 0), subject_of(t_next), nd0, nc0, mvc, n_ntr);
+                        else cp_async_commit();
+                    }
+                    if (jj < 2) cp_async_wait<2>(); else cp_async_wait<1>();
+                } else {
+                    cp_async_wait<LEAD>();
+                }
+                if constexpr (PAIR) __syncwarp();        // half of this lane's slots were copied by its partner
             }
             // value v of this row: from the ring, or straight from the record
             auto rowld = [&](const int v, const double* g) { if constexpr (RING > 0) return rs[v * 32]; else return __ldg(g); };
-            const int off = (RING > 0) ? *reinterpret_cast<const int*>(rs) : __ldg(reinterpret_cast<const int*>(rec + oW1off) + rr);
+            const int off = (RING > 0) ? (PAIR ? reinterpret_cast<const int*>(rs - lane32)[lane32] : *reinterpret_cast<const int*>(rs))
+                                       : __ldg(reinterpret_cast<const int*>(rec + oW1off) + rr);
             double s1c = 0.0, s1p = 0.0;
             sfor<WB>([&](auto j) {
                 constexpr int jv = j;
@@ -531,14 +776,39 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         lh_pn = __shfl_sync(0xFFFFFFFFu, lh_pn, 0, G);
         const double pyb_new = v_pyb;
 
-        const double ptb_cn = MS ? ms_cn : log_ptb_rows<S>(event, lh_cn, H_cn, HL_cn);
+        // per-subject values of the step head that are needed from here on: with two group slots they are read again from the
+        // slot (nothing has overwritten it) instead of having occupied registers during the row loop
+        constexpr bool REREAD = E2 && ESLOTS == 2;
+        double event_t = event, log_u_t = log_u, pyb_old_t = pyb_old, pb_old_t = pb_old, ptb_co_t = ptb_co;
+        double st_keep[SS - q];                                          // state slots q .. SS - 1 (sigma_b, counters, padding)
+        if constexpr (REREAD) {
+            const double* const es = smem + (my_early - smem);
+            event_t = es[0];
+            log_u_t = es[kRowsHdr + SS + q];
+            sfor<SS - q>([&](auto j) { st_keep[j] = es[kRowsHdr + q + j]; });
+            pyb_old_t = st_keep[1]; pb_old_t = st_keep[2];
+            ptb_co_t = last_acc ? st_keep[6] : st_keep[5];
+        } else {
+            sfor<SS - q>([&](auto j) { st_keep[j] = stv[q + j]; });
+        }
+        {
+        const double event = event_t, log_u = log_u_t, pyb_old = pyb_old_t, pb_old = pb_old_t, ptb_co = ptb_co_t;
+
+        double ptb3[3] = {0.0, 0.0, 0.0};
+        constexpr bool PTB3 = JMB_ROWS_PTB3 != 0 && S == 2 && !MS;
+        if constexpr (PTB3) {
+            const double lh3[3] = {lh_cn, lh_po, lh_pn}, H3[3] = {H_cn, H_po, H_pn}, HL3[3] = {HL_cn, HL_po, HL_pn};
+            log_ptb_rows3(event, lh3, H3, HL3, ptb3);
+        }
+        const double ptb_cn = MS ? ms_cn : (PTB3 ? ptb3[0] : log_ptb_rows<S>(event, lh_cn, H_cn, HL_cn));
         const double cur_lp = pyb_old + ptb_co + pb_old;                 // :669
         const double new_lp = pyb_new + ptb_cn + pb_new;                 // :703
         const bool accept = log_u < (new_lp - cur_lp);                   // :706 (NaN rejects)
 
         // ---- proposed survival parameters at the accepted b (:735-752) ----
         const double ptb_p = MS ? (accept ? ms_pn : ms_po)
-                                : log_ptb_rows<S>(event, accept ? lh_pn : lh_po, accept ? H_pn : H_po, accept ? HL_pn : HL_po);
+                                : (PTB3 ? (accept ? ptb3[2] : ptb3[1])
+                                        : log_ptb_rows<S>(event, accept ? lh_pn : lh_po, accept ? H_pn : H_po, accept ? HL_pn : HL_po));
         const double ptb_c = accept ? ptb_cn : ptb_co;
         const double pyb_acc = accept ? pyb_new : pyb_old;
         const double pb_acc = accept ? pb_new : pb_old;
@@ -547,11 +817,11 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         // ---- state write-back by lane 0 of the group (:707-724); sigma_b (slot q) keeps the value read above ----
         if (valid && l == 0) {
             double outv[SS];
-            sfor<SS>([&](auto j) { outv[j] = stv[j]; });
+            sfor<SS - q>([&](auto j) { outv[q + j] = st_keep[j]; });
             sfor<q>([&](auto j) { outv[j] = accept ? bn[j] : bo[j]; });
             outv[q + 1] = pyb_acc; outv[q + 2] = pb_acc;
-            outv[q + 3] = stv[q + 3] + (accept ? 1.0 : 0.0);
-            outv[q + 4] = stv[q + 4] + (accept ? 1.0 : 0.0);
+            outv[q + 3] = st_keep[3] + (accept ? 1.0 : 0.0);
+            outv[q + 4] = st_keep[4] + (accept ? 1.0 : 0.0);
             outv[q + 5] = ptb_c; outv[q + 6] = ptb_p;
             double2* st2 = reinterpret_cast<double2*>(a.state + s * SS);
             sfor<SS / 2>([&](auto j) {
@@ -561,7 +831,9 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
                 else st2[j] = make_double2(outv[j0], outv[j0 + 1]);
             });
         }
+        }
         d0 = nd0; d1 = nd1; c0 = nc0; c1 = nc1; ntr = n_ntr;
+        t_step = t_next; t_next = t_next2;
     }
     // ---- deterministic per-CTA partial sums: one slot per (warp, group), summed in slot order ----
     if (l == 0) { const int slot = warp * SPW + grp; s_red[slot * 3] = acc_cur; s_red[slot * 3 + 1] = acc_prop; s_red[slot * 3 + 2] = acc_lw; }
@@ -577,7 +849,7 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         __syncthreads();
         if (tid == 0) s_tk = atomicAdd(ra.ticket, 1u);
         __syncthreads();
-        if (s_tk == gridDim.x - 1) rows_publish_sums(a.partials, (int)gridDim.x, ra);
+        if (s_tk == gridDim.x - 1) rows_publish_sums(a.partials, (int)gridDim.x, ra, s_ring0);     // the ring is idle by now
     }
     (void)cc;
 }

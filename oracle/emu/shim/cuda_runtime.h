@@ -51,7 +51,7 @@ typedef emuStream* cudaStream_t;
 typedef emuEvent* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1, cudaIpcMemLazyEnablePeerAccess = 1 };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 struct cudaIpcMemHandle_t { char reserved[64]; };
 struct cudaDeviceProp { int multiProcessorCount; };
 enum cudaLaunchAttributeID { cudaLaunchAttributeProgrammaticStreamSerialization = 6 };
