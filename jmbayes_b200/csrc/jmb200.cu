@@ -176,7 +176,11 @@ static void (*rows_kernel_of(int G))(int, ParamLayout, ChainConst, StepArgs, Row
 }
 template <class Spec>
 static void (*rows_kernel_of_early(int G, int early))(int, ParamLayout, ChainConst, StepArgs, RowsArgs) {
-    return early == 2 ? rows_kernel_of<Spec, 2>(G) : (early == 1 ? rows_kernel_of<Spec, 1>(G) : rows_kernel_of<Spec, 0>(G));
+    if constexpr (JMB_ROWS_RING == 2) {      // the pipelined variants are written for a two-stage ring
+        if (early == 2) return rows_kernel_of<Spec, 2>(G);
+        if (early == 3) return rows_kernel_of<Spec, 3>(G);
+    }
+    return early == 1 ? rows_kernel_of<Spec, 1>(G) : rows_kernel_of<Spec, 0>(G);
 }
 static void (*pick_rows_kernel(const ModelDesc& md, int G, int early))(int, ParamLayout, ChainConst, StepArgs, RowsArgs) {
     if (same_desc(md, SpecValueGaussian::d)) return rows_kernel_of_early<SpecValueGaussian>(G, early);
@@ -251,7 +255,7 @@ int jmb_handle_s::rows_schedule(int G, int total_steps) {
     if (e != cudaSuccess) { g_err = std::string("rows_schedule: ") + cudaGetErrorString(e); return 1; }
     ra.order = d_rows_order;
     ra.meta = nullptr;
-    if (rows_early == 2) {
+    if (rows_early >= 2) {
         std::vector<RowsMeta> meta(n);
         for (int i = 0; i < n; ++i) {
             RowsMeta& m = meta[i];
@@ -322,14 +326,16 @@ int jmb_handle_s::select_kernel() {
     // row-strided groups (jmb_step_rows.cuh): G lanes per subject, 32 / G subjects per warp step; the default
     if (same_desc(md, SpecMultiState::d)) kernel_name = "multistate_illness_death";
     {
-        // group width and staging of a step's early data per model shape, from the sweeps in profiles/r2_rows_kernel.md:
-        // early = 0 read in place (+ L2 prefetch), 1 bulk-copied per-warp stage, 2 cp.async group slots + lane-private visit slots
-        int G = (md.S == 2 || md.MS) ? 8 : (md.O > 1 ? 16 : 4);
-        int early = (md.S == 1 && md.O > 1 && !md.MS) ? 1 : 0;
+        // group width and staging of a step's early data per model shape, from the sweeps in profiles/r2_rows_kernel.md and
+        // profiles/r2b_rows_kernel.md: early = 0 read in place (+ L2 prefetch), 1 bulk-copied per-group stage, 2 cp.async group
+        // slots + lane-private visit slots, 3 cp.async into the per-group stage
+        int G = md.MS ? 16 : 8;
+        int early = (md.MS || md.O == 1) ? 2 : 1;
         if (const char* g = getenv("JMB_ROWS_G")) G = atoi(g);
         if (G != 2 && G != 4 && G != 8 && G != 16) G = 8;
-        if (const char* e = getenv("JMB_ROWS_EARLY")) early = std::max(0, std::min(2, atoi(e)));
-        if (early == 2 && md.O > 3) early = 0;
+        if (const char* e = getenv("JMB_ROWS_EARLY")) early = std::max(0, std::min(3, atoi(e)));
+        if (early >= 2 && md.O > 3) early = 0;
+        if (JMB_ROWS_RING != 2 && early >= 2) early = 0;
         rows_kernel = pick_rows_kernel(md, G, early);
         rows_early = early;
         if (rows_kernel) {
@@ -343,7 +349,7 @@ int jmb_handle_s::select_kernel() {
             const long long cta_budget = (227LL * 1024) / kRowsCtas - 1024 - 64;      // per-CTA share of an SM, minus the reserved KB and the static bytes
             const int RSs = (md.q + 2) / 2 * 2;
             ra.cap_dl = 0; ra.cap_cl = 0; ra.vt = 0;
-            if (early == 1) {
+            if (early == 1 || early == 3) {
                 // early stage of a subject: head | state | draws | visit rows of the design and of the per-draw record; the
                 // capacity covers the longest visit segment unless that would not leave room for kRowsCtas CTAs per SM
                 // (subjects beyond the capacity read their visit rows in place)
@@ -352,14 +358,15 @@ int jmb_handle_s::select_kernel() {
                     max_dl = std::max(max_dl, doff[i + 1] - doff[i] - mm.L.o_long);
                     max_cl = std::max(max_cl, coff[i + 1] - coff[i] - mm.L.c_long);
                 }
-                const long long budget = (cta_budget - fixed_b) / 8 / ((long long)kRowsWarps * spw) - (kRowsHdr + mm.L.state_stride + RSs);
+                const int head = (kRowsHdr + mm.L.state_stride + RSs) * ((early == 3 && JMB_ROWS_REREAD) ? 2 : 1);
+                const long long budget = (cta_budget - fixed_b) / 8 / ((long long)kRowsWarps * spw) - head;
                 long long cd = (max_dl + 1) / 2 * 2, cc_ = (max_cl + 1) / 2 * 2;
                 if (cd + cc_ > budget) {
                     const double f = (double)std::max<long long>(budget, 0) / (double)(cd + cc_);
                     cd = (long long)(cd * f) / 2 * 2; cc_ = (long long)(cc_ * f) / 2 * 2;
                 }
                 ra.cap_dl = (int)std::max<long long>(cd, 0); ra.cap_cl = (int)std::max<long long>(cc_, 0);
-                const int RSd = kRowsHdr + mm.L.state_stride + RSs + ra.cap_dl + ra.cap_cl;
+                const int RSd = head + ra.cap_dl + ra.cap_cl;
                 rows_smem = (int)(fixed_b + 8LL * kRowsWarps * spw * RSd);
             } else if (early == 2) {
                 // group slots (head | state | draws) + as many visit-row trips in the lane-private visit slots as the longest
@@ -371,7 +378,7 @@ int jmb_handle_s::select_kernel() {
                 }
                 const long long slots_b = 8LL * kRowsWarps * spw * (kRowsHdr + mm.L.state_stride + RSs) * (JMB_ROWS_REREAD ? 2 : 1);
                 const long long per_trip = 8LL * kRowsWarps * 32 * vs;
-                int vt = (maxv + G - 1) / G;
+                int vt = std::min((maxv + G - 1) / G, md.MS ? 1 : 2);    // measured: more trips in the slots buy nothing (later trips are read in place)
                 if (const char* v = getenv("JMB_ROWS_VT")) vt = std::max(0, atoi(v));
                 vt = (int)std::min<long long>(vt, std::max<long long>(0, (cta_budget - fixed_b - slots_b) / per_trip));
                 ra.vt = vt;
@@ -413,7 +420,7 @@ int jmb_handle_s::select_kernel() {
         case 0: kernel_label = "generic"; break;
         case 1: kernel_label = std::string("static:") + kernel_name; break;
         case 2: kernel_label = std::string("static-tma:") + kernel_name; break;
-        default: kernel_label = std::string("static-rows") + std::to_string(rows_G) + (rows_early == 2 ? "p:" : (rows_early ? "e:" : ":")) + kernel_name; break;
+        default: kernel_label = std::string("static-rows") + std::to_string(rows_G) + (rows_early == 3 ? "q:" : (rows_early == 2 ? "p:" : (rows_early ? "e:" : ":"))) + kernel_name; break;
     }
     return 0;
 }

@@ -147,6 +147,8 @@ struct RowSlots {
 // per call).  Anything else (overflow, gradual underflow, NaN) goes through libm for all three.
 __constant__ double kExpTaylor[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
                                       1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+// out-of-line code takes and returns scalars only: a reference or pointer to a local would move that local to the stack everywhere
+__device__ __noinline__ double exp_libm(const double x) { return exp(x); }
 __device__ __forceinline__ void exp3(const double x0, const double x1, const double x2, double& e0, double& e1, double& e2) {
 #if JMB_EXP3
     if ((fabs(x0) < 700.0) && (fabs(x1) < 700.0) && (fabs(x2) < 700.0)) {
@@ -166,7 +168,7 @@ __device__ __forceinline__ void exp3(const double x0, const double x1, const dou
         e2 = __hiloint2double(__double2hiint(p2) + (__double2loint(t2) << 20), __double2loint(p2));
     } else
 #endif
-    { e0 = exp(x0); e1 = exp(x1); e2 = exp(x2); }
+    { e0 = exp_libm(x0); e1 = exp_libm(x1); e2 = exp_libm(x2); }
 }
 
 // branch-free censoring term for a warp whose groups hold subjects of different event types
@@ -191,7 +193,7 @@ __device__ __forceinline__ double log_ptb_rows(double event, double lh, double H
 // (proposed, new b): the exponentials and logarithms are independent chains, and the term of the proposed parameters no longer
 // waits for the accept decision (which needs the first term) before it starts.
 #ifndef JMB_ROWS_PTB3
-#define JMB_ROWS_PTB3 1
+#define JMB_ROWS_PTB3 0
 #endif
 __device__ __forceinline__ void log_ptb_rows3(const double event, const double (&lh)[3], const double (&H)[3], const double (&HL)[3], double (&out)[3]) {
     double eH[3], eHL[3];
@@ -220,7 +222,7 @@ __device__ __forceinline__ void log_ptb_rows3(const double event, const double (
 // log of the logit and Poisson rows), evaluated side by side instead of one after the other; the sum keeps the row order.  A lane
 // without a second row re-evaluates its first one and drops the result.
 #ifndef JMB_ROWS_VIS2
-#define JMB_ROWS_VIS2 1
+#define JMB_ROWS_VIS2 0
 #endif
 template <class Spec, int G>
 __device__ __forceinline__ double visit_rows(const double* __restrict__ lrec, const double* __restrict__ lcrec, const int* vcount,
@@ -293,7 +295,9 @@ __device__ __forceinline__ void issue_visit_rows(double* vs, const int vt, const
     });
 }
 
-// same arithmetic and summation order as visit_rows; the first vt trips of every outcome come from the visit slots
+// same arithmetic and summation order as visit_rows; the first vt trips of every outcome come from the visit slots, later trips
+// (segments longer than vt G rows) from the record - through ONE copy of the loop body: the addresses of a row's values are
+// selected per trip and read with generic loads
 template <class Spec, int G>
 __device__ __forceinline__ double visit_rows_slots(const double* vs, const int vt, const double* __restrict__ lrec, const double* __restrict__ lcrec,
                                                    const int* vcount, const double (&bn)[Spec::d.q], const double (&isig)[Spec::d.O], const int l) {
@@ -303,44 +307,22 @@ __device__ __forceinline__ double visit_rows_slots(const double* vs, const int v
         constexpr int k = kc;
         constexpr int ones0 = Spec::d.z_ones0[k], qk = Spec::d.qk[k], sb = VisitSlots<Spec>::base(k);
         const int v = vcount[k];
-        auto eta_slot = [&](const double* sl) {
-            double eta = sl[32];
-            if constexpr (ones0 == 1) { constexpr int cz = Spec::d.re_inds[k][0]; eta += bn[cz]; }
-            sfor<qk - ones0>([&](auto jc) {
-                constexpr int j = jc;
-                constexpr int cj = Spec::d.re_inds[k][j + ones0];
-                eta += sl[(2 + j) * 32] * bn[cj];
-            });
-            return eta;
-        };
-        auto eta_of = [&](const int r) {
-            double eta = lcrec[r];
-            if constexpr (ones0 == 1) { constexpr int cz = Spec::d.re_inds[k][0]; eta += bn[cz]; }
-            sfor<qk - ones0>([&](auto jc) {
-                constexpr int j = jc;
-                constexpr int cj = Spec::d.re_inds[k][j + ones0];
-                eta += lrec[(1 + j) * v + r] * bn[cj];
-            });
-            return eta;
-        };
-        int r = l, t = 0;
-#if JMB_ROWS_VIS2
-        for (; t + 1 < vt && r < v; t += 2, r += 2 * G) {                 // trips t and t + 1, both in the slots
-            const bool two = r + G < v;
-            const double* const sl0 = vs + (size_t)(t * VS + sb) * 32;
-            const double* const sl1 = two ? sl0 + VS * 32 : sl0;
-            const double eta0 = eta_slot(sl0), eta1 = eta_slot(sl1);
-            const double ld0 = logdens_static<Spec::d.fam[k], Spec::d.link[k]>(sl0[0], eta0, isig[k]);
-            const double ld1 = logdens_static<Spec::d.fam[k], Spec::d.link[k]>(sl1[0], eta1, isig[k]);
-            v_pyb += ld0;
-            if (two) v_pyb += ld1;
-        }
-#endif
-        for (; t < vt && r < v; ++t, r += G) {
+        int t = 0;
+        for (int r = l; r < v; r += G, ++t) {
+            const bool slot = t < vt;
             const double* const sl = vs + (size_t)(t * VS + sb) * 32;
-            v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(sl[0], eta_slot(sl), isig[k]);
+            const double* const py = slot ? sl : lrec + r;
+            const double* const pe = slot ? sl + 32 : lcrec + r;
+            double eta = *pe;
+            if constexpr (ones0 == 1) { constexpr int cz = Spec::d.re_inds[k][0]; eta += bn[cz]; }
+            sfor<qk - ones0>([&](auto jc) {
+                constexpr int j = jc;
+                constexpr int cj = Spec::d.re_inds[k][j + ones0];
+                const double* const pz = slot ? sl + (2 + j) * 32 : lrec + (1 + j) * v + r;
+                eta += *pz * bn[cj];
+            });
+            v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(*py, eta, isig[k]);
         }
-        for (; r < v; r += G) v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta_of(r), isig[k]);
         constexpr int lcols = Spec::L.long_cols[k];
         lrec += lcols * v;
         lcrec += v;
@@ -394,10 +376,14 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
     constexpr bool PAIR = JMB_ROWS_PAIR != 0 && RING > 0;
     static_assert(!PAIR || (RP % 2 == 0 && G % 2 == 0 && oW1off % 2 == 0 && oW1v % 2 == 0 && oPw % 2 == 0 && (W2C || oW2 % 2 == 0) && HB % 2 == 0),
                   "paired ring copies move 16-byte-aligned pairs of rows");
-    constexpr bool E1 = EARLY == 1, E2 = EARLY == 2;    // early data: 0 read in place (+ L2 prefetch), 1 bulk-copied stage, 2 cp.async slots
+    // early data of a step (head | state | draws, visit rows): 0 read in place (+ L2 prefetch); 1 bulk-copied per-group stage +
+    // mbarrier; 2 cp.async group slots + lane-private visit slots; 3 cp.async (16-byte, by all lanes of the group) into the per-group
+    // stage of variant 1 - a bulk copy takes its operands from uniform registers, so the four groups of a warp issue theirs one after
+    // the other (9 instructions per copy and lane: 211 of the 2 490 instructions of a warp step), the lanes' own copies do not
+    constexpr bool E1 = EARLY == 1, E3 = EARLY == 3, E2 = EARLY == 2 || E3;
     constexpr int EH = kRowsHdr + SS + RS;              // E2: head | state | draws of a subject, one slot per group
     constexpr int VS = VisitSlots<Spec>::VS;
-    static_assert(EARLY >= 0 && EARLY <= 2, "EARLY");
+    static_assert(EARLY >= 0 && EARLY <= 3, "EARLY");
     static_assert(!E2 || (RING == 2 && O <= 3), "the pipelined variant orders its cp.async groups around a two-stage ring");
     static_assert(32 % G == 0 && G >= 2 && G <= 16, "G lanes per subject");
     static_assert(LEAD <= NJ_H, "the trips copied ahead of the record head must be trips every subject needs");
@@ -414,7 +400,7 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
     // E1: early stage of a subject: head | state | draws | visit rows (design) | visit rows (per-draw)
     // E2: [WARPS][SPW][EH] group slots, then [WARPS][vt][VS][32] lane-private visit slots
     constexpr int ESLOTS = (E2 && JMB_ROWS_REREAD) ? 2 : 1;
-    const int ES = E2 ? EH * ESLOTS : (kRowsHdr + SS + RS + ra.cap_dl + ra.cap_cl);
+    const int ES = E3 ? EH * ESLOTS + ra.cap_dl + ra.cap_cl : (E2 ? EH * ESLOTS : (kRowsHdr + SS + RS + ra.cap_dl + ra.cap_cl));
     double* const s_early0 = s_ring0 + (size_t)WARPS * RING * NV * 32;                       // [WARPS][SPW][ES]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
@@ -422,7 +408,8 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
     double* const s_ring = s_ring0 + (size_t)warp * RING * NV * 32 + lane32;
     double* const my_early0 = s_early0 + ((size_t)warp * SPW + grp) * ES;
     double* my_early = my_early0;                        // E2 with two slots: slot of the current step
-    double* const s_vis = s_early0 + (size_t)WARPS * SPW * ES + (size_t)warp * (E2 ? ra.vt : 0) * VS * 32 + lane32;
+    double* const s_vis = E3 ? my_early0 + EH * ESLOTS       // E3: visit rows of the group's subject, design part then per-draw part
+                             : s_early0 + (size_t)WARPS * SPW * ES + (size_t)warp * (E2 ? ra.vt : 0) * VS * 32 + lane32;
     uint64_t* const bar = s_bar + warp;
     // this warp's steps: the list the host dealt to the (CTA, warp) slot
     const long long n = a.n;
@@ -442,7 +429,7 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
     if (t_step < 0) t_next = -1;
     long long d0 = 0, d1 = 0, c0 = 0, c1 = 0;
     int ntr = 1;                                          // transition rows of this group's subject
-    int mvc[O];                                           // E2: visit counts of the subject whose copies are issued next
+    int mvc[O];                                           // E2: visit counts of the first subject (its copies start before the loop)
     sfor<O>([&](auto kc) { mvc[kc] = 0; });
     if (t_step >= 0) {
         const long long s = subject_of(t_step);
@@ -501,7 +488,18 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
                 cp_async16(slot + 2 * c, src);
             }
         }
-        issue_visit_rows<Spec, G>(s_vis, ra.vt, a.drec + e0 + oLong + (size_t)(mtr - 1) * HB, a.crec + f0 + (size_t)mtr * cLong, mv, l);
+        if constexpr (E3) {
+            int dl = 0, cl = 0;                               // doubles of the visit rows in the design / per-draw record
+            sfor<O>([&](auto kc) { constexpr int k = kc; constexpr int lc = Spec::L.long_cols[k]; dl += lc * mv[k]; cl += mv[k]; });
+            if (dl <= ra.cap_dl && cl <= ra.cap_cl) {          // else: read in place
+                const double* const gd = a.drec + e0 + oLong + (size_t)(mtr - 1) * HB;
+                const double* const gc = a.crec + f0 + (size_t)mtr * cLong;
+                for (int c = 2 * l; c < dl; c += 2 * G) cp_async16(s_vis + c, gd + c);
+                for (int c = 2 * l; c < cl; c += 2 * G) cp_async16(s_vis + ra.cap_dl + c, gc + c);
+            }
+        } else {
+            issue_visit_rows<Spec, G>(s_vis, ra.vt, a.drec + e0 + oLong + (size_t)(mtr - 1) * HB, a.crec + f0 + (size_t)mtr * cLong, mv, l);
+        }
         cp_async_commit();
     };
     if constexpr (E2) { if (t_step >= 0) issue_ev(my_early0, subject_of(t_step), d0, c0, mvc, ntr); }
@@ -518,9 +516,11 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         const int t_next2 = (has_next && ko + 2 < ra.order_len) ? my_order[ko + 2] : -1;
         long long nd0 = 0, nd1 = 0, nc0 = 0, nc1 = 0;
         int n_ntr = 1;
+        int nvc[O];                                       // E2: visit counts of the next subject (fresh registers: the load is consumed a visit loop later)
+        sfor<O>([&](auto kc) { nvc[kc] = 0; });
         if (has_next) {
             const long long sn = subject_of(t_next);
-            if constexpr (E2) load_meta(sn, nd0, nc0, mvc, n_ntr);
+            if constexpr (E2) load_meta(sn, nd0, nc0, nvc, n_ntr);
             else {
                 nd0 = a.doff[sn]; nd1 = a.doff[sn + 1]; nc0 = a.coff[sn]; nc1 = a.coff[sn + 1];
                 if constexpr (MS) n_ntr = a.trow[sn + 1] - a.trow[sn];
@@ -621,11 +621,22 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
 
         // ---- GLMM log-density over the visit segment ----
         double v_pyb;
-        if constexpr (E2) {
+        if constexpr (E3) {
+            int dl = 0, cl = 0;
+            sfor<O>([&](auto kc) { constexpr int k = kc; constexpr int lc = Spec::L.long_cols[k]; dl += lc * vcount[k]; cl += vcount[k]; });
+            const bool st3 = dl <= ra.cap_dl && cl <= ra.cap_cl;
+            const double* const gl = rec0 + oLong + (size_t)(ntr - 1) * HB;
+            const double* const gc = crec0 + (size_t)ntr * cLong;
+            v_pyb = visit_rows<Spec, G>(st3 ? s_vis : gl, st3 ? s_vis + ra.cap_dl : gc, vcount, bn, isig, l);
+        } else if constexpr (E2) {
             v_pyb = visit_rows_slots<Spec, G>(s_vis, ra.vt, rec0 + oLong + (size_t)(ntr - 1) * HB, crec0 + (size_t)ntr * cLong, vcount, bn, isig, l);
-        } else if (staged) {
-            const double* lr = smem + (my_early - smem) + kRowsHdr + SS + RS;
-            v_pyb = visit_rows<Spec, G>(lr, lr + ra.cap_dl, vcount, bn, isig, l);
+        } else if constexpr (E1) {
+            // one copy of the visit loops serves the staged rows and the rows read in place (segments beyond the stage capacity):
+            // generic loads through a pointer that is selected here
+            const double* const lr = my_early + kRowsHdr + SS + RS;
+            const double* const gl = rec0 + oLong + (size_t)(ntr - 1) * HB;
+            const double* const gc = crec0 + (size_t)ntr * cLong;
+            v_pyb = visit_rows<Spec, G>(staged ? lr : gl, staged ? lr + ra.cap_dl : gc, vcount, bn, isig, l);
         } else {
             v_pyb = visit_rows<Spec, G>(rec0 + oLong + (size_t)(ntr - 1) * HB, crec0 + (size_t)ntr * cLong, vcount, bn, isig, l);
         }
@@ -674,7 +685,7 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
                     // copies have two trips (or, in a two-trip loop, until the top of the next step) to arrive
                     if (jj == 0) {
                         __syncwarp();            // every lane of the group has read the group slot (top of this step)
-                        if (has_next) issue_ev(my_early0 + (ESLOTS == 2 ? ((ko + 1) & 1) * EH : 0), subject_of(t_next), nd0, nc0, mvc, n_ntr);
+                        if (has_next) issue_ev(my_early0 + (ESLOTS == 2 ? ((ko + 1) & 1) * EH : 0), subject_of(t_next), nd0, nc0, nvc, n_ntr);
                         else cp_async_commit();
                     }
                     if (jj < 2) cp_async_wait<2>(); else cp_async_wait<1>();
@@ -800,15 +811,28 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
             const double lh3[3] = {lh_cn, lh_po, lh_pn}, H3[3] = {H_cn, H_po, H_pn}, HL3[3] = {HL_cn, HL_po, HL_pn};
             log_ptb_rows3(event, lh3, H3, HL3, ptb3);
         }
-        const double ptb_cn = MS ? ms_cn : (PTB3 ? ptb3[0] : log_ptb_rows<S>(event, lh_cn, H_cn, HL_cn));
+        // The censoring term is evaluated twice - current parameters at the proposal, then (after the accept decision, :706)
+        // proposed parameters at the accepted b (:735-752) - by ONE copy of its code (two exponentials and a logarithm of libm):
+        // the kernel's hot loop has to fit the instruction cache.
+        double ptb_cn = 0.0, ptb_p = 0.0;
+        bool accept = false;
         const double cur_lp = pyb_old + ptb_co + pb_old;                 // :669
-        const double new_lp = pyb_new + ptb_cn + pb_new;                 // :703
-        const bool accept = log_u < (new_lp - cur_lp);                   // :706 (NaN rejects)
-
-        // ---- proposed survival parameters at the accepted b (:735-752) ----
-        const double ptb_p = MS ? (accept ? ms_pn : ms_po)
-                                : (PTB3 ? (accept ? ptb3[2] : ptb3[1])
-                                        : log_ptb_rows<S>(event, accept ? lh_pn : lh_po, accept ? H_pn : H_po, accept ? HL_pn : HL_po));
+        if constexpr (MS || PTB3 || S != 2) {
+            ptb_cn = MS ? ms_cn : (PTB3 ? ptb3[0] : log_ptb_rows<S>(event, lh_cn, H_cn, HL_cn));
+            accept = log_u < ((pyb_new + ptb_cn + pb_new) - cur_lp);     // :703, :706 (NaN rejects)
+            ptb_p = MS ? (accept ? ms_pn : ms_po)
+                       : (PTB3 ? (accept ? ptb3[2] : ptb3[1]) : log_ptb_rows<S>(event, accept ? lh_pn : lh_po, accept ? H_pn : H_po, 0.0));
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < 2; ++it) {
+                const bool pn = accept;                                  // it == 1: which b the proposed parameters are evaluated at
+                const double lh_i = it == 0 ? lh_cn : (pn ? lh_pn : lh_po), H_i = it == 0 ? H_cn : (pn ? H_pn : H_po);
+                const double HL_i = it == 0 ? HL_cn : (pn ? HL_pn : HL_po);
+                const double r = log_ptb_rows<S>(event, lh_i, H_i, HL_i);
+                if (it == 0) { ptb_cn = r; accept = log_u < ((pyb_new + ptb_cn + pb_new) - cur_lp); }
+                else ptb_p = r;
+            }
+        }
         const double ptb_c = accept ? ptb_cn : ptb_co;
         const double pyb_acc = accept ? pyb_new : pyb_old;
         const double pb_acc = accept ? pb_new : pb_old;

@@ -24,6 +24,10 @@ __device__ __forceinline__ double trans_static(double x) {
 // branch evaluates only the live logarithm and reproduces the naive formula's NaN when the dead
 // term would be 0 * (-inf); the Poisson branch uses y*eta for y*log(exp(eta)) with the same
 // overflow / underflow outcomes.  Anything else goes through the literal formulas.
+// responses other than 0 / 1 of a binomial outcome: the literal formula, kept out of line (the specialised kernels' hot loops must
+// fit the instruction cache: two inlined logarithms per call site were 700 instructions of a kernel that never executes them)
+__device__ __noinline__ double binomial_general(double y, double pr) { return y * log(pr) + (1.0 - y) * log(1.0 - pr); }
+
 template <int FAM, int LINK>
 __device__ __forceinline__ double logdens_static(double y, double eta, double inv_sigma) {
     if constexpr (FAM == JMB_FAM_GAUSSIAN) {
@@ -40,7 +44,7 @@ __device__ __forceinline__ double logdens_static(double y, double eta, double in
             const bool dead_inf = one ? (pr == 1.0) : (pr == 0.0);      // 0 * log(0) in the naive formula
             return dead_inf ? __longlong_as_double(0x7ff8000000000000LL) : ld;
         }
-        return y * log(pr) + (1.0 - y) * log(1.0 - pr);
+        return binomial_general(y, pr);
     } else {
         if constexpr (LINK == JMB_LINK_LOG) {
             const double mu = exp(eta);

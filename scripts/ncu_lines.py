@@ -47,4 +47,4 @@ def src(ln):
     if f[0] not in src_cache: src_cache[f[0]] = open(f[0]).read().split("\n")
     return src_cache[f[0]][ln[1] - 1].strip()[:100]
 for ln, a in sorted(agg.items(), key=lambda x: -x[1]["# Samples"])[:top]:
-    print(f"{str(ln):32s} smp {a['# Samples']:5d} ({100*a['# Samples']/tot:4.1f}%) inst {a['Instructions Executed']:9d} long {a['stall_long_sb']:5d} wait {a['stall_wait']:5d} short {a['stall_short_sb']:4d} bar {a['stall_barrier']:4d} mio {a['stall_mio']:3d} math {a['stall_math']:3d} br {a['stall_branch_resolving']:3d} xs {a['L1 Wavefronts Shared Excessive']:7d} | {src(ln)}")
+    print(f"{str(ln):32s} smp {a['# Samples']:5d} ({100*a['# Samples']/tot:4.1f}%) inst {a['Instructions Executed']:9d} long {a['stall_long_sb']:5d} wait {a['stall_wait']:5d} short {a['stall_short_sb']:4d} bar {a['stall_barrier']:4d} mio {a['stall_mio']:3d} math {a['stall_math']:3d} br {a["stall_branch_resolving"]:3d} noi {a["stall_no_inst"]:4d} xs {a['L1 Wavefronts Shared Excessive']:7d} | {src(ln)}")

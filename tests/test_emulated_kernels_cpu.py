@@ -201,6 +201,7 @@ def test_emulated_summaries_and_survfit_kernels_match_their_oracles(emu):
                                               ("config4", None, 8, 0), ("config3", None, 4, 1), ("config3", None, 16, 1), ("config3", None, 16, 0),
                                               ("config2", None, 4, 1), ("config2", None, 8, 0),
                                               ("config4", None, 8, 2), ("config4", None, 4, 2), ("config3", None, 16, 2), ("config2", None, 4, 2),
+                                              ("config4", None, 8, 3), ("config4", None, 16, 3), ("config3", None, 8, 3), ("config2", None, 8, 3),
                                               ("config2", "tma", 0, 0), ("config4", "tma", 0, 0), ("config3", "direct", 0, 0)])
 def test_emulated_static_kernels_match_oracle(emu, oracle, cfg, mode, G, early):
     """The hot-path kernels against the oracle chain: jmb_step_rows (G lanes per subject, rows strided by G; the default),
@@ -217,7 +218,7 @@ def test_emulated_static_kernels_match_oracle(emu, oracle, cfg, mode, G, early):
         c = make_cohort(cfg, n=70)
         ctl = dict(c["control"]); ctl.update(n_burnin=20, n_iter=10, n_block=10, n_thin=5)
         with emu.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
-            want = {None: "static-rows%d%s:" % (G, ("", "e", "p")[early]), "tma": "static-tma:", "direct": "static:"}[mode]
+            want = {None: "static-rows%d%s:" % (G, ("", "e", "p", "q")[early]), "tma": "static-tma:", "direct": "static:"}[mode]
             assert fit.layout_info()["kernel"].startswith(want)
             fit.set_draw(c["Data"])
             r1 = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)

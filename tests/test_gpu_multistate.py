@@ -101,10 +101,10 @@ def test_multistate_specialised_and_generic_kernels_agree(cuda_lib, monkeypatch)
     monkeypatch.setenv("JMB_KERNEL", "generic")
     g = run("generic")
     monkeypatch.delenv("JMB_KERNEL")
-    for G, early in [(None, None)] + [(w, e) for w in ("4", "8", "16") for e in ("0", "1", "2")]:
+    for G, early in [(None, None)] + [(w, e) for w in ("4", "8", "16") for e in ("0", "1", "2", "3")]:
         if G:
             monkeypatch.setenv("JMB_ROWS_G", G); monkeypatch.setenv("JMB_ROWS_EARLY", early)
-        r = run("static-rows" + (G + {"0": ":", "1": "e:", "2": "p:"}[early] if G else ""))
+        r = run("static-rows" + (G + {"0": ":", "1": "e:", "2": "p:", "3": "q:"}[early] if G else ""))
         assert _rel(r["extras"]["trace_surv"], g["extras"]["trace_surv"]) <= 1e-10, (G, early)
         assert np.allclose(r["mcmc"]["b"], g["mcmc"]["b"], rtol=1e-9, atol=1e-12), (G, early)
         assert np.array_equal(r["extras"]["accept_b"], g["extras"]["accept_b"]), (G, early)

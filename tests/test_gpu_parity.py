@@ -122,11 +122,11 @@ def test_static_and_generic_kernels_agree(cuda_lib, cfg, monkeypatch):
     # the row-strided kernel sums a subject's rows in a different order (lane-strided partial sums): 1e-10
     # (with and without the bulk-copied early stage of a step)
     monkeypatch.delenv("JMB_KERNEL")
-    for G, early in [(None, None)] + [(g, e) for g in ("2", "4", "8", "16") for e in ("0", "1", "2")]:
+    for G, early in [(None, None)] + [(g, e) for g in ("2", "4", "8", "16") for e in ("0", "1", "2", "3")]:
         if G:
             monkeypatch.setenv("JMB_ROWS_G", G)
             monkeypatch.setenv("JMB_ROWS_EARLY", early)
-            r = run("static-rows" + G + {"0": ":", "1": "e:", "2": "p:"}[early])
+            r = run("static-rows" + G + {"0": ":", "1": "e:", "2": "p:", "3": "q:"}[early])
         assert _rel(r["extras"]["trace_surv"], b["extras"]["trace_surv"]) <= 1e-10, (G, early)
         assert np.allclose(r["mcmc"]["b"], b["mcmc"]["b"], rtol=1e-9, atol=1e-12), (G, early)
         assert np.allclose(r["scales"]["sigma"]["b"], b["scales"]["sigma"]["b"], rtol=1e-10), (G, early)
