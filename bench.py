@@ -424,7 +424,10 @@ def run_cuda(args):
         sms = 148
         roof["floors_us"] = {"dram": real_bytes / (peak * 1e9) * 1e6,
                              "issue": prof["inst_per_subject"] * n / (4 * sms * sm_hz) * 1e6,
-                             "fp64": 2.0 * prof.get("fp64_inst_per_subject", 0.0) * n / (4 * sms * sm_hz) * 1e6,
+                             # fp64 pipe: from the instruction count (two issue cycles per warp instruction) or from the capture's
+                             # pipe-active share of its own duration
+                             "fp64": (2.0 * prof["fp64_inst_per_subject"] * n / (4 * sms * sm_hz) * 1e6 if "fp64_inst_per_subject" in prof
+                                      else prof.get("fp64_pipe_active_pct", 0.0) / 100.0 * prof.get("ncu_time_us", 0.0) * (n / prof["subjects"])),
                              "source": traffic_src}
 
     line = {

@@ -158,7 +158,7 @@ struct jmb_handle_s {
     ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
     // peer-memory mailboxes for the fused all-reduce of the per-iteration sums
     static constexpr int kMboxSlots = 64;
-    double* d_mbox = nullptr;                       // this rank's mailbox [kMboxSlots][2][nranks][4]
+    double* d_mbox = nullptr;                       // this rank's mailbox [kMboxSlots][2][nranks][kMboxEntry]
     std::vector<void*> peer_ptrs;                   // peers' mailboxes opened through CUDA IPC
     double** d_peer_mbox = nullptr;                 // device copy of the pointer table
     bool p2p = false;
@@ -330,7 +330,7 @@ int jmb_handle_s::select_kernel() {
         // profiles/r2b_rows_kernel.md: early = 0 read in place (+ L2 prefetch), 1 bulk-copied per-group stage, 2 cp.async group
         // slots + lane-private visit slots, 3 cp.async into the per-group stage
         int G = md.MS ? 16 : 8;
-        int early = (md.MS || md.O == 1) ? 2 : 1;
+        int early = (md.MS || md.O == 1) ? 2 : 1;     // variants 1 and 3 are within 3 % of each other on configs 3 / 4; 1 was ahead on two of three boxes
         if (const char* g = getenv("JMB_ROWS_G")) G = atoi(g);
         if (G != 2 && G != 4 && G != 8 && G != 16) G = 8;
         if (const char* e = getenv("JMB_ROWS_EARLY")) early = std::max(0, std::min(3, atoi(e)));
@@ -1808,7 +1808,7 @@ extern "C" int jmb_p2p_export(jmb_handle h, int nranks, char handle[64]) {
     CU(cudaSetDevice(h->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     if (!h->d_mbox) {
-        const size_t bytes = sizeof(double) * jmb_handle_s::kMboxSlots * 2 * (size_t)nranks * 4;
+        const size_t bytes = sizeof(double) * jmb_handle_s::kMboxSlots * 2 * (size_t)nranks * kMboxEntry;
         CU(cudaMalloc(&h->d_mbox, bytes));
         CU(cudaMemset(h->d_mbox, 0, bytes));
         CU(cudaDeviceSynchronize());

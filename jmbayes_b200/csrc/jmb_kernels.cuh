@@ -376,12 +376,42 @@ __device__ inline void make_proposal(const ModelMeta& mm, const ParamLayout& pl,
     }
 }
 
+// Mailbox entry of one rank's three sums: six 8-byte words, each (stamp << 32) | one half of a double.  An 8-byte store is one
+// NVLink transaction, so a word whose upper half carries the expected stamp carries its data too: neither a system-scope fence
+// between data and flag on the sender (a round trip over NVLink) nor a separate flag is needed.
+constexpr int kMboxEntry = 8;            // doubles per (slot, parity, rank) entry: six words used
+__device__ __forceinline__ void mbox_send(double* entry, const double v0, const double v1, const double v2, const unsigned long long stamp) {
+    volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(entry);
+    const unsigned long long hi = (stamp & 0xFFFFFFFFull) << 32;
+    const double v[3] = {v0, v1, v2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v[k]);
+        w[2 * k] = hi | (b & 0xFFFFFFFFull);
+        w[2 * k + 1] = hi | (b >> 32);
+    }
+}
+// waits for the six words of an entry; false if they do not arrive (a peer died)
+__device__ __forceinline__ bool mbox_recv(const double* entry, const unsigned long long stamp, double (&v)[3]) {
+    const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(entry);
+    const unsigned long long want = stamp & 0xFFFFFFFFull;
+    unsigned long long x[6];
+    long long spins = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        while (((x[k] = w[k]) >> 32) != want) { if (++spins > 200000000LL) return false; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = __longlong_as_double((long long)((x[2 * k] & 0xFFFFFFFFull) | (x[2 * k + 1] << 32)));
+    return true;
+}
+
 __global__ void __launch_bounds__(128)
 jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ ParamLayout pl,
                     const __grid_constant__ ChainConst cc, const __grid_constant__ FinalizeArgs a) {
     __shared__ double s_sum[128 * 3];
     __shared__ double s_tot[3];
-    __shared__ int s_next_iter;
+    __shared__ int s_next_iter, s_mats_changed;
     __shared__ double s_z[JMB_MAX_BS + JMB_MAX_GAMMAS + JMB_MAX_ALPHAS + 2];
     __shared__ double s_q[4][JMB_MAX_BS + JMB_MAX_GAMMAS + JMB_MAX_ALPHAS];
     const int tid = threadIdx.x;
@@ -419,6 +449,49 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         if (tid == blockDim.x - 1) s_lu = log_unif(cc.seed, cc.chain_id, 0u, (uint32_t)iter_pre, 0xFFFFFFFFu, ST_SURV);
         proposal_normals(mm, cc, iter_pre + 1, tid, blockDim.x, s_z);
     }
+    // ---- quadratic forms of the three Gaussian priors, one coordinate per thread ----
+    // thread j < P handles coordinate j of (Bs_gammas | gammas | alphas) against its block's Tau:
+    //   s_q[0][j] = ((cur - mean)' Tau)_j (cur - mean)_j   s_q[1][j]: same at the proposal
+    //   s_q[2][j] / s_q[3][j]: (x' Tau_Bs)_j x_j without the mean, for the tau_Bs_gammas draw
+    // then the eight block sums (s_qs: current / proposed x three blocks, the two raw Bs sums), in coordinate order.
+    // They depend on the parameter block only (written by finalize kernels), so on one rank they run before the dependency wait,
+    // under the tail of the step kernel.
+    __shared__ double s_qs[8];
+    auto quad_forms = [&]() {
+        double* cur = par + pl.cur;
+        double* prop = par + pl.prop;
+        if (tid < mm.P) {
+            int base, m, To, Mo;
+            if (tid < B) { base = 0; m = B; To = pl.Tau_Bs; Mo = pl.mean_Bs; }
+            else if (tid < B + p) { base = B; m = p; To = pl.Tau_g; Mo = pl.mean_g; }
+            else { base = B + p; m = A; To = pl.Tau_a; Mo = pl.mean_a; }
+            const int jj = tid - base;
+            // stratified baseline hazard: the tau_Bs_gammas draw of a stratum uses its diagonal block of Tau_Bs_gammas only
+            int sf = 0, sl = m - 1;
+            if (cc.nRisks > 0 && tid < B)
+                for (int k = 0; k < cc.nRisks; ++k) if (jj >= cc.kn_first[k] && jj <= cc.kn_last[k]) { sf = cc.kn_first[k]; sl = cc.kn_last[k]; }
+            double tc = 0.0, tp = 0.0, rc = 0.0, rp = 0.0;
+            for (int l = 0; l < m; ++l) {
+                const double tau = par[To + l + jj * m], mu = par[Mo + l];
+                const double xc = cur[base + l], xp = prop[base + l];
+                tc += (xc - mu) * tau; tp += (xp - mu) * tau;
+                if (l >= sf && l <= sl) { rc += xc * tau; rp += xp * tau; }
+            }
+            const double mu = par[Mo + jj];
+            s_q[0][tid] = tc * (cur[tid] - mu); s_q[1][tid] = tp * (prop[tid] - mu);
+            s_q[2][tid] = rc * cur[tid]; s_q[3][tid] = rp * prop[tid];
+        }
+        __syncthreads();
+        if (tid < 8) {
+            // 0..2: current, blocks Bs | gammas | alphas; 3..5: proposed; 6 / 7: raw Bs sums (current / proposed)
+            const int blk = tid < 6 ? tid % 3 : 0, row = tid < 6 ? tid / 3 : tid - 4;
+            const int lo = blk == 0 ? 0 : (blk == 1 ? B : B + p), hi = blk == 0 ? B : (blk == 1 ? B + p : mm.P);
+            double t = 0.0;
+            for (int j = lo; j < hi; ++j) t += s_q[row][j];
+            s_qs[tid] = t;
+        }
+    };
+    if (a.phase == 0 && a.use_reduced != 2) quad_forms();
     pdl_wait();                // the step kernel (partials, state) has completed
     pdl_trigger();             // the next step kernel may start its prologue (records, state and draws are final)
 
@@ -451,75 +524,35 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     } else if (a.use_reduced == 3) {
         if (tid == 0) { s_tot[0] = 0.0; s_tot[1] = a.sp_out[0] - a.sp_out[1]; s_tot[2] = 0.0; }
     } else if (!(a.use_reduced == 2 && a.published)) {
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-        for (int i = tid; i < a.n_partials; i += 128) { t0 += a.partials[i * 3]; t1 += a.partials[i * 3 + 1]; t2 += a.partials[i * 3 + 2]; }
-        s_sum[tid] = t0; s_sum[128 + tid] = t1; s_sum[256 + tid] = t2;
-        __syncthreads();
-        for (int w = 64; w > 0; w >>= 1) {
-            if (tid < w) { s_sum[tid] += s_sum[tid + w]; s_sum[128 + tid] += s_sum[128 + tid + w]; s_sum[256 + tid] += s_sum[256 + tid + w]; }
-            __syncthreads();
+        // warp c sums component c: lane-strided partial sums (independent loads), then a butterfly - fixed order, one barrier
+        if (tid < 96) {
+            const int c = tid >> 5, ln = tid & 31;
+            double t = 0.0;
+            for (int i = ln; i < a.n_partials; i += 32) t += a.partials[i * 3 + c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+            if (ln == 0) s_tot[c] = t;
         }
-        if (tid < 3) s_tot[tid] = s_sum[tid * 128];
     }
     __syncthreads();
     if (a.use_reduced == 2) {
         // ---- fused all-reduce over peer memory: compute (local sums) and collective in one kernel ----
         const int par2 = (int)(a.stamp & 1ull);
         const long long base = ((long long)(a.slot * 2 + par2) * a.nranks);
-        if (tid < a.nranks && !a.published) {
-            double* dst = a.peer_mbox[tid] + (base + a.rank) * 4;
-            dst[0] = s_tot[0]; dst[1] = s_tot[1]; dst[2] = s_tot[2];
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned long long*>(dst + 3) = a.stamp;
-        }
+        if (tid < a.nranks && !a.published) mbox_send(a.peer_mbox[tid] + (base + a.rank) * kMboxEntry, s_tot[0], s_tot[1], s_tot[2], a.stamp);
         // the peers' sums are collected after the quadratic forms below, which do not depend on them: their arithmetic hides
         // part of the NVLink flight
     }
 
-    // ---- quadratic forms of the three Gaussian priors, one coordinate per thread ----
-    // thread j < P handles coordinate j of (Bs_gammas | gammas | alphas) against its block's Tau:
-    //   s_q[0][j] = ((cur - mean)' Tau)_j (cur - mean)_j   s_q[1][j]: same at the proposal
-    //   s_q[2][j] / s_q[3][j]: (x' Tau_Bs)_j x_j without the mean, for the tau_Bs_gammas draw
-    {
-        double* cur = par + pl.cur;
-        double* prop = par + pl.prop;
-        if (tid < mm.P) {
-            int base, m, To, Mo;
-            if (tid < B) { base = 0; m = B; To = pl.Tau_Bs; Mo = pl.mean_Bs; }
-            else if (tid < B + p) { base = B; m = p; To = pl.Tau_g; Mo = pl.mean_g; }
-            else { base = B + p; m = A; To = pl.Tau_a; Mo = pl.mean_a; }
-            const int jj = tid - base;
-            // stratified baseline hazard: the tau_Bs_gammas draw of a stratum uses its diagonal block of Tau_Bs_gammas only
-            int sf = 0, sl = m - 1;
-            if (cc.nRisks > 0 && tid < B)
-                for (int k = 0; k < cc.nRisks; ++k) if (jj >= cc.kn_first[k] && jj <= cc.kn_last[k]) { sf = cc.kn_first[k]; sl = cc.kn_last[k]; }
-            double tc = 0.0, tp = 0.0, rc = 0.0, rp = 0.0;
-            for (int l = 0; l < m; ++l) {
-                const double tau = par[To + l + jj * m], mu = par[Mo + l];
-                const double xc = cur[base + l], xp = prop[base + l];
-                tc += (xc - mu) * tau; tp += (xp - mu) * tau;
-                if (l >= sf && l <= sl) { rc += xc * tau; rp += xp * tau; }
-            }
-            const double mu = par[Mo + jj];
-            s_q[0][tid] = tc * (cur[tid] - mu); s_q[1][tid] = tp * (prop[tid] - mu);
-            s_q[2][tid] = rc * cur[tid]; s_q[3][tid] = rp * prop[tid];
-        }
-    }
-    __syncthreads();
+    if (a.use_reduced == 2) quad_forms();     // several ranks: their arithmetic hides part of the NVLink flight
     if (a.use_reduced == 2) {
         // ---- second half of the fused all-reduce: wait for every rank's stamp in this rank's mailbox, add in rank order ----
         const int par2 = (int)(a.stamp & 1ull);
         const long long base = ((long long)(a.slot * 2 + par2) * a.nranks);
         if (tid < a.nranks) {
-            const double* src = a.my_mbox + (base + tid) * 4;
-            const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(src + 3);
-            long long spins = 0;
-            while (*flag != a.stamp) {
-                if (++spins > 200000000LL) { a.ctl->error = 3; break; }     // a peer died: give up instead of hanging
-            }
-            __threadfence_system();
-            const volatile double* vs = src;
-            s_sum[tid * 3] = vs[0]; s_sum[tid * 3 + 1] = vs[1]; s_sum[tid * 3 + 2] = vs[2];
+            double v[3] = {0.0, 0.0, 0.0};
+            if (!mbox_recv(a.my_mbox + (base + tid) * kMboxEntry, a.stamp, v)) a.ctl->error = 3;     // a peer died: give up instead of hanging
+            s_sum[tid * 3] = v[0]; s_sum[tid * 3 + 1] = v[1]; s_sum[tid * 3 + 2] = v[2];
         }
         __syncthreads();
         if (tid < 3) {
@@ -531,6 +564,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     }
 
     if (tid == 0) {
+        s_mats_changed = 0;
         Ctl* ctl = a.ctl;
         const int iter = ctl->iter;
         double* cur = par + pl.cur;
@@ -538,10 +572,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         if (a.trace && !a.wore) { a.trace[2LL * iter] = s_tot[0]; a.trace[2LL * iter + 1] = s_tot[1]; }
         // ---- survival-block RWM (:727-770); tau = 1 for Bs_gammas (reference behaviour) ----
         const double tau_g = par[pl.tau_g], tau_a = par[pl.tau_a];
-        double qc[3] = {0.0, 0.0, 0.0}, qp[3] = {0.0, 0.0, 0.0}, rawc = 0.0, rawp = 0.0;
-        for (int j = 0; j < B; ++j) { qc[0] += s_q[0][j]; qp[0] += s_q[1][j]; rawc += s_q[2][j]; rawp += s_q[3][j]; }
-        for (int j = B; j < B + p; ++j) { qc[1] += s_q[0][j]; qp[1] += s_q[1][j]; }
-        for (int j = B + p; j < mm.P; ++j) { qc[2] += s_q[0][j]; qp[2] += s_q[1][j]; }
+        const double qc[3] = {s_qs[0], s_qs[1], s_qs[2]}, qp[3] = {s_qs[3], s_qs[4], s_qs[5]}, rawc = s_qs[6], rawp = s_qs[7];
         // lap_rwm_C: tau = 1 for Bs_gammas (:727,753); woRE: the sampled tau_Bs_gammas (:911) and a carried
         // current value that is only refreshed on acceptance (:1031-1053)
         const double tBs = a.wore ? par[pl.tau_Bs] : 1.0;
@@ -637,6 +668,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
                 if (p) e |= chol_upper_dev(par + pl.S_g, p, par + pl.H_g);
                 e |= chol_upper_dev(par + pl.S_a, A, par + pl.H_a);
                 if (e) ctl->error = 2;
+                s_mats_changed = 1;
             }
             ctl->accept_s_block = 0; ctl->i = 0; ctl->it += 1;
         } else {
@@ -648,8 +680,12 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     __syncthreads();
     make_proposal(mm, pl, cc, par, s_next_iter, tid, blockDim.x, s_z, /*have_z=*/true);   // normals of iter + 1 drawn above
     if (a.use_smem) {
+        // back to global memory: the part an iteration changes (parameters, precisions, scales - everything before the proposal
+        // covariances) and, after a covariance adaptation only, the matrices behind it
         __syncthreads();
-        for (int j = tid; j < pl.block_par; j += blockDim.x) gpar[j] = s_par[j];
+        const int hi = s_mats_changed ? pl.block_par : pl.S_Bs;
+        for (int j = tid; j < hi; j += blockDim.x) gpar[j] = s_par[j];
+        if (tid == 0) gpar[pl.cur_lp] = s_par[pl.cur_lp];
     }
 }
 

@@ -64,9 +64,6 @@ struct RowsArgs {
 #ifndef JMB_ROWS_RING
 #define JMB_ROWS_RING 2
 #endif
-#ifndef JMB_EXP3
-#define JMB_EXP3 1
-#endif
 // pipelined variant: two group slots per group, so that the per-subject values that are only needed after the row loop (log u,
 // the carried log-densities, counters, event) are re-read from the slot instead of being held in registers across the loop
 #ifndef JMB_ROWS_REREAD
@@ -139,38 +136,6 @@ struct RowSlots {
     static constexpr int NV = term_base(Spec::d.T);
 };
 
-// Three exponentials at once (the three hazard values of a quadrature row).  For |x| < 700 - every value a chain ever sees -
-// exp(x) = 2^n exp(r), n = rint(x log2 e), r = x - n ln 2 (two-term Cody-Waite reduction, |r| <= 0.347), exp(r) by the degree-13
-// Taylor polynomial (truncation 4e-18), 2^n added to the exponent field: 0.62 ulp worst case over [-700, 700] against the
-// correctly rounded value (measured on the host with the same arithmetic).  The three Horner chains are independent and share
-// their coefficients, which come from the constant bank (libm's exp materialises its 64-bit coefficients with two moves each,
-// per call).  Anything else (overflow, gradual underflow, NaN) goes through libm for all three.
-__constant__ double kExpTaylor[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
-                                      1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
-// out-of-line code takes and returns scalars only: a reference or pointer to a local would move that local to the stack everywhere
-__device__ __noinline__ double exp_libm(const double x) { return exp(x); }
-__device__ __forceinline__ void exp3(const double x0, const double x1, const double x2, double& e0, double& e1, double& e2) {
-#if JMB_EXP3
-    if ((fabs(x0) < 700.0) && (fabs(x1) < 700.0) && (fabs(x2) < 700.0)) {
-        const double L2E = 1.44269504088896338700e+00, SH = 6755399441055744.0;
-        const double LN2H = 6.93147180559945286227e-01, LN2L = 2.31904681384629955842e-17;
-        const double t0 = fma(x0, L2E, SH), t1 = fma(x1, L2E, SH), t2 = fma(x2, L2E, SH);
-        const double n0 = t0 - SH, n1 = t1 - SH, n2 = t2 - SH;
-        double r0 = fma(n0, -LN2H, x0), r1 = fma(n1, -LN2H, x1), r2 = fma(n2, -LN2H, x2);
-        r0 = fma(n0, -LN2L, r0); r1 = fma(n1, -LN2L, r1); r2 = fma(n2, -LN2L, r2);
-        double p0 = kExpTaylor[0], p1 = kExpTaylor[0], p2 = kExpTaylor[0];
-#pragma unroll
-        for (int k = 1; k < 12; ++k) { const double c = kExpTaylor[k]; p0 = fma(p0, r0, c); p1 = fma(p1, r1, c); p2 = fma(p2, r2, c); }
-        p0 = fma(p0, r0, 1.0); p1 = fma(p1, r1, 1.0); p2 = fma(p2, r2, 1.0);
-        p0 = fma(p0, r0, 1.0); p1 = fma(p1, r1, 1.0); p2 = fma(p2, r2, 1.0);
-        e0 = __hiloint2double(__double2hiint(p0) + (__double2loint(t0) << 20), __double2loint(p0));
-        e1 = __hiloint2double(__double2hiint(p1) + (__double2loint(t1) << 20), __double2loint(p1));
-        e2 = __hiloint2double(__double2hiint(p2) + (__double2loint(t2) << 20), __double2loint(p2));
-    } else
-#endif
-    { e0 = exp_libm(x0); e1 = exp_libm(x1); e2 = exp_libm(x2); }
-}
-
 // branch-free censoring term for a warp whose groups hold subjects of different event types
 // (src/fast_LAPRWM.cpp:640-650; same arithmetic per event type as log_ptb_static)
 template <int S>
@@ -194,6 +159,10 @@ __device__ __forceinline__ double log_ptb_rows(double event, double lh, double H
 // waits for the accept decision (which needs the first term) before it starts.
 #ifndef JMB_ROWS_PTB3
 #define JMB_ROWS_PTB3 0
+#endif
+// censoring terms evaluated lane-parallel inside the group (G >= 8)
+#ifndef JMB_ROWS_PTBL
+#define JMB_ROWS_PTBL 1
 #endif
 __device__ __forceinline__ void log_ptb_rows3(const double event, const double (&lh)[3], const double (&H)[3], const double (&HL)[3], double (&out)[3]) {
     double eH[3], eHL[3];
@@ -345,10 +314,7 @@ __device__ __noinline__ void rows_publish_sums(const double* partials, const int
     __syncthreads();
     if (tid < ra.nranks) {
         const long long base = ((long long)(ra.slot * 2 + (int)(ra.stamp & 1ull)) * ra.nranks);
-        double* dst = ra.peer_mbox[tid] + (base + ra.rank) * 4;
-        dst[0] = s_pub[0]; dst[1] = s_pub[JMB_ROWS_THREADS]; dst[2] = s_pub[2 * JMB_ROWS_THREADS];
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long*>(dst + 3) = ra.stamp;
+        mbox_send(ra.peer_mbox[tid] + (base + ra.rank) * kMboxEntry, s_pub[0], s_pub[JMB_ROWS_THREADS], s_pub[2 * JMB_ROWS_THREADS], ra.stamp);
     }
     if (tid == 0) *ra.ticket = 0u;                    // ready for the next launch on this chain slot
 }
@@ -624,6 +590,8 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         if constexpr (E3) {
             int dl = 0, cl = 0;
             sfor<O>([&](auto kc) { constexpr int k = kc; constexpr int lc = Spec::L.long_cols[k]; dl += lc * vcount[k]; cl += vcount[k]; });
+            // one copy of the visit loops for the staged rows and the rows read in place (generic loads through a selected pointer):
+            // a second, shared-memory-only copy of the loops was measured and loses more to the instruction cache than LDS gains
             const bool st3 = dl <= ra.cap_dl && cl <= ra.cap_cl;
             const double* const gl = rec0 + oLong + (size_t)(ntr - 1) * HB;
             const double* const gc = crec0 + (size_t)ntr * cLong;
@@ -817,7 +785,30 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         double ptb_cn = 0.0, ptb_p = 0.0;
         bool accept = false;
         const double cur_lp = pyb_old + ptb_co + pb_old;                 // :669
-        if constexpr (MS || PTB3 || S != 2) {
+        constexpr bool PTBL = JMB_ROWS_PTBL != 0 && S == 2 && !MS && G >= 8;
+        if constexpr (PTBL) {
+            // The six exponentials exp(-H), exp(-HL) of the three (parameters, b) pairs are evaluated by six lanes of the group at
+            // once (every lane holds all six sums after the butterflies), their three logarithms by three lanes: one exponential and
+            // one logarithm in the instruction stream of a step instead of four and two, and the term under the proposed parameters
+            // no longer waits for the accept decision.  Same values as log_ptb_rows.
+            const int role = l & 7, pr_i = min(role >> 1, 2);            // pair 0 (cur, new b) | 1 (prop, old b) | 2 (prop, new b); odd lanes: HL
+            const double Hs = pr_i == 0 ? H_cn : (pr_i == 1 ? H_po : H_pn), HLs = pr_i == 0 ? HL_cn : (pr_i == 1 ? HL_po : HL_pn);
+            const double ex = exp1(-((role & 1) ? HLs : Hs));
+            const double ex_o = __shfl_xor_sync(0xFFFFFFFFu, ex, 1);      // even lanes: exp(-HL) of their pair
+            const double arg = (event == 2.0) ? (1.0 - ex) : ((event == 3.0) ? (ex_o - ex) : 1.0);
+            const double lg = log(arg);
+            const double lg_cn = __shfl_sync(0xFFFFFFFFu, lg, 0, G), lg_po = __shfl_sync(0xFFFFFFFFu, lg, 2, G), lg_pn = __shfl_sync(0xFFFFFFFFu, lg, 4, G);
+            auto term = [&](const double lh, const double H, const double lgv) {
+                double r = 0.0;
+                if (event == 1.0) r = lh - H;
+                if (event == 0.0) r = 0.0 - H;
+                if (event == 2.0 || event == 3.0) r = lgv;
+                return r;
+            };
+            ptb_cn = term(lh_cn, H_cn, lg_cn);
+            accept = log_u < ((pyb_new + ptb_cn + pb_new) - cur_lp);     // :703, :706 (NaN rejects)
+            ptb_p = accept ? term(lh_pn, H_pn, lg_pn) : term(lh_po, H_po, lg_po);
+        } else if constexpr (MS || PTB3 || S != 2) {
             ptb_cn = MS ? ms_cn : (PTB3 ? ptb3[0] : log_ptb_rows<S>(event, lh_cn, H_cn, HL_cn));
             accept = log_u < ((pyb_new + ptb_cn + pb_new) - cur_lp);     // :703, :706 (NaN rejects)
             ptb_p = MS ? (accept ? ms_pn : ms_po)

@@ -65,9 +65,10 @@ def test_right_rows_on_device_is_bit_exact(cuda_lib, n, seed):
     idT = np.sort(np.r_[np.arange(Q.shape[0]), np.arange(nT - Q.shape[0])]).astype(np.int32)
     Qm = Q[idT] * 0.9
     assert np.array_equal(designs.right_rows(times, ids, Qm, idT=idT), od.right_rows(times, ids, Qm, idT=idT))
-    bad = np.r_[ids, ids[:1]]                                        # the first subject's label again at the end: not grouped
-    with pytest.raises(ValueError):
-        designs.right_rows(np.r_[times, 9.0], bad, Q)
+    if n > 1:
+        bad = np.r_[ids, ids[:1]]                                    # the first subject's label again at the end: not grouped
+        with pytest.raises(ValueError):
+            designs.right_rows(np.r_[times, 9.0], bad, Q)
 
 
 @pytest.mark.gpu
