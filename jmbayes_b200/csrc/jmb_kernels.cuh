@@ -391,6 +391,20 @@ __device__ __forceinline__ void mbox_send(double* entry, const double v0, const 
         w[2 * k + 1] = hi | (b >> 32);
     }
 }
+// one word per thread: word k (0..5) of an entry
+__device__ __forceinline__ void mbox_send_word(double* entry, const int k, const double v, const unsigned long long stamp) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    reinterpret_cast<volatile unsigned long long*>(entry)[k] = ((stamp & 0xFFFFFFFFull) << 32) | ((k & 1) ? (b >> 32) : (b & 0xFFFFFFFFull));
+}
+__device__ __forceinline__ bool mbox_recv_word(const double* entry, const int k, const unsigned long long stamp, unsigned int& half) {
+    const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(entry) + k;
+    const unsigned long long want = stamp & 0xFFFFFFFFull;
+    unsigned long long x;
+    long long spins = 0;
+    while (((x = *w) >> 32) != want) { if (++spins > 200000000LL) return false; }
+    half = (unsigned int)(x & 0xFFFFFFFFull);
+    return true;
+}
 // waits for the six words of an entry; false if they do not arrive (a peer died)
 __device__ __forceinline__ bool mbox_recv(const double* entry, const unsigned long long stamp, double (&v)[3]) {
     const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(entry);
@@ -491,7 +505,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
             s_qs[tid] = t;
         }
     };
-    if (a.phase == 0 && a.use_reduced != 2) quad_forms();
+    if (a.phase == 0) quad_forms();
     pdl_wait();                // the step kernel (partials, state) has completed
     pdl_trigger();             // the next step kernel may start its prologue (records, state and draws are final)
 
@@ -539,21 +553,28 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         // ---- fused all-reduce over peer memory: compute (local sums) and collective in one kernel ----
         const int par2 = (int)(a.stamp & 1ull);
         const long long base = ((long long)(a.slot * 2 + par2) * a.nranks);
-        if (tid < a.nranks && !a.published) mbox_send(a.peer_mbox[tid] + (base + a.rank) * kMboxEntry, s_tot[0], s_tot[1], s_tot[2], a.stamp);
+        // one thread per (peer, word): six independent 8-byte stores per peer
+        if (!a.published)
+            for (int w = tid; w < 6 * a.nranks; w += blockDim.x)
+                mbox_send_word(a.peer_mbox[w / 6] + (base + a.rank) * kMboxEntry, w % 6, s_tot[(w % 6) >> 1], a.stamp);
         // the peers' sums are collected after the quadratic forms below, which do not depend on them: their arithmetic hides
         // part of the NVLink flight
     }
 
-    if (a.use_reduced == 2) quad_forms();     // several ranks: their arithmetic hides part of the NVLink flight
     if (a.use_reduced == 2) {
         // ---- second half of the fused all-reduce: wait for every rank's stamp in this rank's mailbox, add in rank order ----
         const int par2 = (int)(a.stamp & 1ull);
         const long long base = ((long long)(a.slot * 2 + par2) * a.nranks);
-        if (tid < a.nranks) {
-            double v[3] = {0.0, 0.0, 0.0};
-            if (!mbox_recv(a.my_mbox + (base + tid) * kMboxEntry, a.stamp, v)) a.ctl->error = 3;     // a peer died: give up instead of hanging
-            s_sum[tid * 3] = v[0]; s_sum[tid * 3 + 1] = v[1]; s_sum[tid * 3 + 2] = v[2];
+        // one thread per (rank, word): the six words of an entry are awaited side by side, not one L2 round trip after the other
+        unsigned int* s_half = reinterpret_cast<unsigned int*>(s_sum + 3 * 64);          // [nranks][6] (s_sum has 384 doubles; nranks <= 64)
+        for (int w = tid; w < 6 * a.nranks; w += blockDim.x) {
+            unsigned int half = 0u;
+            if (!mbox_recv_word(a.my_mbox + (base + w / 6) * kMboxEntry, w % 6, a.stamp, half)) a.ctl->error = 3;   // a peer died: give up instead of hanging
+            s_half[w] = half;
         }
+        __syncthreads();
+        for (int v = tid; v < 3 * a.nranks; v += blockDim.x)      // value v = (rank, component): its two halves are words 2v, 2v + 1
+            s_sum[v] = __longlong_as_double((long long)((unsigned long long)s_half[2 * v] | ((unsigned long long)s_half[2 * v + 1] << 32)));
         __syncthreads();
         if (tid < 3) {
             double t = 0.0;
