@@ -87,11 +87,6 @@ struct ChainCtx {
     double* d_partials = nullptr; double* d_tmp = nullptr;  // d_tmp: n*(q+1)
     double* d_rng = nullptr;                        // [rng_chunk][n][rng_stride] draws of the b-step
     size_t rng_capacity = 0; int rng_chunk = 1;
-    // two chunk buffers: while the step kernels read chunk c, the finalize launches of chunk c carry the draws of chunk c + 1
-    // (one iteration's worth each) unless c + 1 starts a new block (sigma_b is adapted in between)
-    size_t rng_chunk_stride = 0;                    // doubles between the two buffers
-    long long pregen_chunk = -1;                    // chunk whose draws the finalize launches have produced / are producing
-    PrepArgs fin_prep{};                            // the slice the next finalize launch carries (n == 0: none)
     double* h_crec = nullptr;                       // pinned staging for the per-draw records
     double* h_par = nullptr;                        // pinned staging for the parameter block
     double* h_tmp = nullptr;                        // pinned staging n*(q+1)
@@ -1055,8 +1050,7 @@ static int launch_step(jmb_handle h, int mode) {
     a.drec = h->d_drec; a.doff = h->d_doff; a.crec = h->c->d_crec; a.coff = h->d_coff; a.rowptr = h->d_rowptr;
     a.state = h->c->d_state; a.par = h->c->d_par; a.ctl = h->c->d_ctl; a.partials = h->c->d_partials; a.eval_out = h->d_eval;
     a.n = h->n; a.subject_offset = h->subject_offset; a.mode = mode; a.subjects_per_cta = h->subjects_per_cta;
-    a.rng = h->c->d_rng + (size_t)((h->c->iter_host / std::max(h->c->rng_chunk, 1)) & 1) * h->c->rng_chunk_stride;   // this chunk's buffer
-    a.rng_chunk = h->c->rng_chunk; a.rng_stride = h->rng_stride;
+    a.rng = h->c->d_rng; a.rng_chunk = h->c->rng_chunk; a.rng_stride = h->rng_stride;
     a.trow = h->d_trow; a.eval_stride = std::max(h->n, h->nT);
     if (mode == MODE_STEP && h->kernel_mode == 3) {
         RowsArgs ra = h->ra;
@@ -1122,10 +1116,8 @@ static int launch_finalize(jmb_handle h, int phase) {
         CU(cudaFuncSetAttribute((const void*)jmb_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
         h->c->fin_attr_set = true;
     }
-    unsigned fin_grid = 1;
-    if (phase == 0 && !a.wore && h->c->fin_prep.n > 0) { a.prep = h->c->fin_prep; fin_grid += (unsigned)((h->c->fin_prep.n + 127) / 128); }
-    if (pdl_enabled()) CU(launch_pdl(jmb_finalize_kernel, dim3(fin_grid), dim3(128), a.use_smem ? fin_smem : 0, h->c->stream, h->mm, h->pl, h->c->cc, a));
-    else jmb_finalize_kernel<<<fin_grid, 128, a.use_smem ? fin_smem : 0, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
+    if (pdl_enabled()) CU(launch_pdl(jmb_finalize_kernel, dim3(1), dim3(128), a.use_smem ? fin_smem : 0, h->c->stream, h->mm, h->pl, h->c->cc, a));
+    else jmb_finalize_kernel<<<1, 128, a.use_smem ? fin_smem : 0, h->c->stream>>>(h->mm, h->pl, h->c->cc, a);
     h->launches += 1;
     CU(cudaGetLastError());
     return 0;
@@ -1267,22 +1259,19 @@ extern "C" int jmb_chain_begin(jmb_handle h, const jmb_priors* pr, const jmb_con
         if (const char* e = getenv("JMB_RNG_CHUNK")) want = std::max(1, atoi(e));
         int chunk = std::min(ct->n_block, want);
         while (chunk > 1 && ct->n_block % chunk != 0) --chunk;
-        if (2 * (size_t)chunk * per_iter > h->c->rng_capacity) {
+        if ((size_t)chunk * per_iter > h->c->rng_capacity) {
             // growing the buffer is the only place the chain start touches the allocator (a warm chain start does not)
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
-            const size_t budget = std::max<size_t>(2 * per_iter, std::min<size_t>(free_b / 4 + h->c->rng_capacity, (size_t)8 << 30));
-            while (chunk > 1 && (2 * (size_t)chunk * per_iter > budget || ct->n_block % chunk != 0)) --chunk;
-            if (2 * (size_t)chunk * per_iter > h->c->rng_capacity) {
+            const size_t budget = std::max<size_t>(per_iter, std::min<size_t>(free_b / 4 + h->c->rng_capacity, (size_t)8 << 30));
+            while (chunk > 1 && ((size_t)chunk * per_iter > budget || ct->n_block % chunk != 0)) --chunk;
+            if ((size_t)chunk * per_iter > h->c->rng_capacity) {
                 cudaFree(h->c->d_rng); h->c->d_rng = nullptr;
-                CU(cudaMalloc(&h->c->d_rng, 2 * (size_t)chunk * per_iter));
-                h->c->rng_capacity = 2 * (size_t)chunk * per_iter;
+                CU(cudaMalloc(&h->c->d_rng, (size_t)chunk * per_iter));
+                h->c->rng_capacity = (size_t)chunk * per_iter;
             }
         }
         h->c->rng_chunk = chunk;
-        h->c->rng_chunk_stride = (size_t)chunk * (size_t)n * h->rng_stride;
-        h->c->pregen_chunk = -1;
-        h->c->fin_prep = PrepArgs{};
     }
     if (launch_finalize(h, 1)) return 1;            // Cholesky factors + proposal of iteration 0
     if (launch_step(h, MODE_INIT)) return 1;        // log_pyb / log_pb at the initial b (:619-621)
@@ -1299,24 +1288,11 @@ static bool is_keep_iter(const jmb_handle h, int iter) {
 static int enqueue_iteration(jmb_handle h, float* kernel_ms) {
     const ModelMeta& mm = h->mm;
     const int i_blk = h->c->iter_host % h->c->cc.n_block;
-    const int chunk = h->c->rng_chunk;
-    const long long c_idx = h->c->iter_host / chunk;                  // chunks never straddle a block (n_block % chunk == 0)
-    PrepArgs pa{};
-    pa.Rchol = h->d_Rchol; pa.state = h->c->d_state; pa.n = h->n; pa.q = mm.d.q;
-    pa.state_stride = mm.L.state_stride; pa.rng_stride = h->rng_stride; pa.subject_offset = h->subject_offset;
-    // draws of the next chunk, one iteration's worth per finalize launch of this chunk, unless a block end lies in between
-    static const bool pregen_on = !(getenv("JMB_RNG_PREGEN") && getenv("JMB_RNG_PREGEN")[0] == '0');
-    h->c->fin_prep = PrepArgs{};
-    if (pregen_on && chunk > 1 && (i_blk / chunk + 1) * chunk < h->c->cc.n_block) {
-        const int p_in = i_blk % chunk;
-        h->c->fin_prep = pa;
-        h->c->fin_prep.rng = h->c->d_rng + (size_t)((c_idx + 1) & 1) * h->c->rng_chunk_stride + (size_t)p_in * (size_t)h->n * h->rng_stride;
-        h->c->fin_prep.iter0 = (int)((c_idx + 1) * chunk + p_in); h->c->fin_prep.count = 1;
-        if (p_in == chunk - 1) h->c->pregen_chunk = c_idx + 1;        // complete once this iteration's finalize launch has run
-    }
-    const bool have_draws = (h->c->pregen_chunk == c_idx);
-    if (i_blk % chunk == 0 && !have_draws) {       // draws for the next rng_chunk iterations (:658)
-        pa.rng = h->c->d_rng + (size_t)(c_idx & 1) * h->c->rng_chunk_stride; pa.iter0 = h->c->iter_host; pa.count = chunk;
+    if (i_blk % h->c->rng_chunk == 0) {            // draws for the next rng_chunk iterations (:658)
+        PrepArgs pa{};
+        pa.Rchol = h->d_Rchol; pa.state = h->c->d_state; pa.rng = h->c->d_rng; pa.n = h->n; pa.q = mm.d.q;
+        pa.state_stride = mm.L.state_stride; pa.rng_stride = h->rng_stride; pa.iter0 = h->c->iter_host; pa.count = h->c->rng_chunk;
+        pa.subject_offset = h->subject_offset;
         const long long tot = (long long)h->n * h->c->rng_chunk;
         const unsigned pg = (unsigned)((tot + 255) / 256);
         if (mm.d.q == 2) jmb_block_prep_kernel<2><<<pg, 256, 0, h->c->stream>>>(h->c->cc, pa);

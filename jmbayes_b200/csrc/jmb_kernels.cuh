@@ -329,53 +329,6 @@ __device__ inline void adapt_cov_dev(double* Sg, double* Hwork, int m, const dou
     for (int j = 0; j < m; ++j) Sg[j + j * m] += eps2;
 }
 
-// -------------------------------------------------------------------------------------------
-// Once per block of iterations (src/fast_LAPRWM.cpp:651-661): the random draws of the b-step.
-// The reference materialises rand_b = mvrnorm_cube(n_block, Sigma_b, sigma_b) per block (:658) and
-// all accept uniforms up front (:618); here one thread per (iteration-in-chunk, subject) writes
-// the proposal increment sqrt(sigma_b[i]) z'R_i (q doubles) and log u into the rng buffer that the
-// step kernels stream.  sigma_b only changes at block ends, so a chunk never straddles a block.
-// -------------------------------------------------------------------------------------------
-struct PrepArgs {
-    const double* Rchol;     // [n][q(q+1)/2] upper Cholesky factors of Covs$b, packed by column
-    const double* state; double* rng;
-    int n, q, state_stride, rng_stride, iter0, count;
-    long long subject_offset;
-};
-
-template <int Q>   // Q > 0: q known at compile time (draws stay in registers); Q == 0: runtime q
-__device__ __forceinline__ void prep_one(const ChainConst& cc, const PrepArgs& a, const long long t) {
-    if (t >= (long long)a.n * a.count) return;
-    const int q = Q > 0 ? Q : a.q;
-    const int k = (int)(t / a.n), s = (int)(t % a.n);
-    const uint32_t gid = (uint32_t)(a.subject_offset + s), iter = (uint32_t)(a.iter0 + k);
-    const double* R = a.Rchol + (long long)s * (q * (q + 1) / 2);
-    const double sd = sqrt(a.state[(long long)s * a.state_stride + q]);
-    double* out = a.rng + ((long long)k * a.n + s) * a.rng_stride;
-    double z[Q > 0 ? Q + 1 : JMB_MAX_Q];
-#pragma unroll
-    for (int sl = 0; sl < (Q > 0 ? (Q + 1) / 2 : JMB_MAX_Q / 2); ++sl) {
-        if (sl < (q + 1) / 2) rnorm_pair(cc.seed, cc.chain_id, gid, iter, (uint32_t)sl, ST_B_PROP, z[2 * sl], z[2 * sl + 1]);
-    }
-#pragma unroll
-    for (int j = 0; j < (Q > 0 ? Q : JMB_MAX_Q); ++j) {
-        if (j < q) {
-            const double* Rj = R + (j * (j + 1)) / 2;      // column j of the upper factor
-            double pj = 0.0;
-#pragma unroll
-            for (int l = 0; l < (Q > 0 ? Q : JMB_MAX_Q); ++l) if (l <= j) pj += z[l] * Rj[l];
-            out[j] = sd * pj;
-        }
-    }
-    out[q] = log_unif(cc.seed, cc.chain_id, gid, iter, 0u, ST_B_ACC);
-}
-
-template <int Q>
-__global__ void __launch_bounds__(256)
-jmb_block_prep_kernel(const __grid_constant__ ChainConst cc, const __grid_constant__ PrepArgs a) {
-    prep_one<Q>(cc, a, (long long)blockIdx.x * blockDim.x + threadIdx.x);
-}
-
 struct FinalizeArgs {
     double* par;
     Ctl* ctl;
@@ -397,10 +350,6 @@ struct FinalizeArgs {
     // outputs of kept iterations (device buffers laid out like jmb_chain_out)
     double* o_Bs; double* o_g; double* o_a; double* o_phi_g; double* o_phi_a; double* o_tau_Bs;
     double* o_tau_g; double* o_tau_a; double* o_tau_td; double* o_lw; double* trace;
-    // Draws of the b-step for one iteration of the NEXT chunk, produced by the CTAs 1.. of this launch (prep.count == 1; prep.n == 0:
-    // none).  They depend on nothing the step kernel writes (sigma_b only changes at block ends, and a chunk never straddles one), so
-    // these CTAs do not wait for it: they run in its tail, as its CTAs retire, and under this kernel's one-CTA serial section.
-    PrepArgs prep;
 };
 
 // survival proposal for iteration `iter`: cur + sqrt(sigma) * z' chol(Sigma)  (:659-661,732-734)
@@ -474,15 +423,6 @@ __device__ __forceinline__ bool mbox_recv(const double* entry, const unsigned lo
 __global__ void __launch_bounds__(128)
 jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ ParamLayout pl,
                     const __grid_constant__ ChainConst cc, const __grid_constant__ FinalizeArgs a) {
-    if (blockIdx.x > 0) {
-        pdl_trigger();
-        const long long t = (long long)(blockIdx.x - 1) * blockDim.x + threadIdx.x;
-        if (a.prep.q == 2) prep_one<2>(cc, a.prep, t);
-        else if (a.prep.q == 4) prep_one<4>(cc, a.prep, t);
-        else if (a.prep.q == 6) prep_one<6>(cc, a.prep, t);
-        else prep_one<0>(cc, a.prep, t);
-        return;
-    }
     __shared__ double s_sum[128 * 3];
     __shared__ double s_tot[3];
     __shared__ int s_next_iter, s_mats_changed;
@@ -770,7 +710,48 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// Once per block of iterations (src/fast_LAPRWM.cpp:651-661): the random draws of the b-step.
+// The reference materialises rand_b = mvrnorm_cube(n_block, Sigma_b, sigma_b) per block (:658) and
+// all accept uniforms up front (:618); here one thread per (iteration-in-chunk, subject) writes
+// the proposal increment sqrt(sigma_b[i]) z'R_i (q doubles) and log u into the rng buffer that the
+// step kernels stream.  sigma_b only changes at block ends, so a chunk never straddles a block.
+// -------------------------------------------------------------------------------------------
+struct PrepArgs {
+    const double* Rchol;     // [n][q(q+1)/2] upper Cholesky factors of Covs$b, packed by column
+    const double* state; double* rng;
+    int n, q, state_stride, rng_stride, iter0, count;
+    long long subject_offset;
+};
 
+template <int Q>   // Q > 0: q known at compile time (draws stay in registers); Q == 0: runtime q
+__global__ void __launch_bounds__(256)
+jmb_block_prep_kernel(const __grid_constant__ ChainConst cc, const __grid_constant__ PrepArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)a.n * a.count) return;
+    const int q = Q > 0 ? Q : a.q;
+    const int k = (int)(t / a.n), s = (int)(t % a.n);
+    const uint32_t gid = (uint32_t)(a.subject_offset + s), iter = (uint32_t)(a.iter0 + k);
+    const double* R = a.Rchol + (long long)s * (q * (q + 1) / 2);
+    const double sd = sqrt(a.state[(long long)s * a.state_stride + q]);
+    double* out = a.rng + ((long long)k * a.n + s) * a.rng_stride;
+    double z[Q > 0 ? Q + 1 : JMB_MAX_Q];
+#pragma unroll
+    for (int sl = 0; sl < (Q > 0 ? (Q + 1) / 2 : JMB_MAX_Q / 2); ++sl) {
+        if (sl < (q + 1) / 2) rnorm_pair(cc.seed, cc.chain_id, gid, iter, (uint32_t)sl, ST_B_PROP, z[2 * sl], z[2 * sl + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < (Q > 0 ? Q : JMB_MAX_Q); ++j) {
+        if (j < q) {
+            const double* Rj = R + (j * (j + 1)) / 2;      // column j of the upper factor
+            double pj = 0.0;
+#pragma unroll
+            for (int l = 0; l < (Q > 0 ? Q : JMB_MAX_Q); ++l) if (l <= j) pj += z[l] * Rj[l];
+            out[j] = sd * pj;
+        }
+    }
+    out[q] = log_unif(cc.seed, cc.chain_id, gid, iter, 0u, ST_B_ACC);
+}
 
 // per-subject Robbins-Monro update of sigma_b at the end of block `it` (:853-859, bounds_sigma :411-419)
 __global__ void __launch_bounds__(256)
