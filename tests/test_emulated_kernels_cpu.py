@@ -232,3 +232,21 @@ def test_emulated_static_kernels_match_oracle(emu, oracle, cfg, mode, G, early):
     r0 = oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"])
     assert _rel(r1["extras"]["trace_surv"], r0["extras"]["trace_surv"]) <= 1e-12
     assert np.allclose(r1["mcmc"]["b"], r0["mcmc"]["b"], rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("cfg,chunk", [("config4", "5"), ("config2", "2")])
+def test_emulated_blocks_of_several_draw_chunks_match_oracle(emu, oracle, cfg, chunk, monkeypatch):
+    """Blocks of several draw chunks (JMB_RNG_CHUNK < n_block): the draws are keyed by (iteration, subject), so the chunk length
+    must not change the chain.  Same counter-RNG specification as the oracle: the whole trajectory must agree."""
+    monkeypatch.delenv("JMB_KERNEL", raising=False)
+    monkeypatch.setenv("JMB_RNG_CHUNK", chunk)
+    c = make_cohort(cfg, n=70)
+    ctl = dict(c["control"]); ctl.update(n_burnin=40, n_iter=20, n_block=20, n_thin=5)
+    with emu.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
+        fit.set_draw(c["Data"])
+        r1 = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    oracle.set_rowsum_mode(1)
+    r0 = oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"])
+    assert _rel(r1["extras"]["trace_surv"], r0["extras"]["trace_surv"]) <= 1e-12
+    assert np.allclose(r1["mcmc"]["b"], r0["mcmc"]["b"], rtol=1e-10, atol=1e-13)
+    assert np.array_equal(r1["extras"]["accept_b"], r0["extras"]["accept_b"])
