@@ -572,7 +572,15 @@ def run_multistate(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg = info["shared_bytes_per_subject"] + info["chain_bytes_per_subject"]
-    achieved = alg * n / (k_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:      # bytes that cross HBM per launch from a committed ncu capture of this kernel, never more than the layout's
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("multistate", {}).get(info["kernel"] + ":multistate")
+        if prof:
+            traffic = (prof["dram_bytes_read"] + prof["dram_bytes_write"]) * (n / prof["subjects"])
+            traffic_src = prof["source"]
+    except Exception:
+        pass
+    achieved = (min(traffic, alg * n) if traffic else alg * n) / (k_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -581,8 +589,9 @@ def run_multistate(args):
                    "subjects_per_gpu": n, "subjects_total": n_total, "transition_rows_per_gpu": int(fit.nT), "outcomes": fit.O, "q": fit.q,
                    "terms": fit.T, "K": fit.K, "multiState": True, "parallelism": f"subject-shards x{world}", "chains_per_launch": 1,
                    "l2": "per-iteration working set %.2f GB per GPU (inputs larger than the 126 MB L2)" % (alg * n / 1e9)},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": info["kernel"] + ":multistate", "kernel_ms": k_ms, "alg_bytes_per_subject_iteration": alg,
+                     "frac_layout": alg * n / (k_ms * 1e-3) / 1e9 / peak,
                      "alg_source": "record layout (jmb_layout_info): design + per-draw records, state read/write, b-step draws",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_total, "d2h_bytes_per_step": d2h / e2e_total,
