@@ -706,7 +706,7 @@ jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant_
         __syncthreads();
         const int hi = s_mats_changed ? pl.block_par : pl.S_Bs;
         for (int j = tid; j < hi; j += blockDim.x) gpar[j] = s_par[j];
-        if (tid == 0) gpar[pl.cur_lp] = s_par[pl.cur_lp];
+        if (tid == 0 && pl.cur_lp >= hi) gpar[pl.cur_lp] = s_par[pl.cur_lp];
     }
 }
 

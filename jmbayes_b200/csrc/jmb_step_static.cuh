@@ -551,7 +551,14 @@ jmb_step_tma(const int B, const __grid_constant__ ParamLayout pl, const __grid_c
         if (more) {
             const Pending np = pend(nxt);
             if (stg) pd1 = np; else pd0 = np;
-            if (lane32 == 0 && np.staged) issue(nxt, stg);
+            if (lane32 == 0 && np.staged) {
+                // the warp's generic-proxy reads of this stage (ordered before this point by the __syncwarp above) must be ordered
+                // before the async-proxy writes of the bulk copies that re-fill it
+#if !defined(JMB_EMU)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+                issue(nxt, stg);
+            }
         }
     }
     const int grp = tid / G;
