@@ -405,21 +405,6 @@ __device__ __forceinline__ bool mbox_recv_word(const double* entry, const int k,
     half = (unsigned int)(x & 0xFFFFFFFFull);
     return true;
 }
-// waits for the six words of an entry; false if they do not arrive (a peer died)
-__device__ __forceinline__ bool mbox_recv(const double* entry, const unsigned long long stamp, double (&v)[3]) {
-    const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(entry);
-    const unsigned long long want = stamp & 0xFFFFFFFFull;
-    unsigned long long x[6];
-    long long spins = 0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        while (((x[k] = w[k]) >> 32) != want) { if (++spins > 200000000LL) return false; }
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) v[k] = __longlong_as_double((long long)((x[2 * k] & 0xFFFFFFFFull) | (x[2 * k + 1] << 32)));
-    return true;
-}
-
 __global__ void __launch_bounds__(128)
 jmb_finalize_kernel(const __grid_constant__ ModelMeta mm, const __grid_constant__ ParamLayout pl,
                     const __grid_constant__ ChainConst cc, const __grid_constant__ FinalizeArgs a) {

@@ -6,22 +6,30 @@
 //   * lane l of a group walks the hazard rows l, l + G, l + 2G, ... (row 0 = event time, 1..K quadrature,
 //     K+1..2K lower-interval quadrature) and the visit rows l, l + G, ... of every outcome, keeps its own
 //     partial sums, and the group combines them with log2(G) xor-shuffles;
-//   * everything that is per subject and not per row (state, proposal, log p(b), censoring terms, accept,
-//     write-back) is executed once per warp for 32 / G subjects instead of once per subject.
+//   * everything that is per subject and not per row (state, proposal, log p(b), accept, write-back) is executed once
+//     per warp for 32 / G subjects instead of once per subject; the censoring terms, which are per subject AND
+//     expensive, are spread over the lanes of the group (JMB_ROWS_PTBL).
 // With one lane per row (round 1) 1 100 warp instructions were issued per subject-iteration of config 4, most of
-// them replicated per-subject work and visit loops with 10 of 32 lanes active; here 480 (G = 4) .. 590 (G = 8)
-// (profiles/r2_rows_kernel.md).
+// them replicated per-subject work and visit loops with 10 of 32 lanes active; here 550 (profiles/r2_rows_kernel.md,
+// profiles/r2b_rows_kernel.md).
 //
-// Memory pipeline (a warp step covers 32 / G whole records, 18 - 37 KB: too much to double-buffer per warp):
-//   * hazard rows (80 % of the bytes): a lane-private ring of JMB_ROWS_RING stages in shared memory, filled with
-//     cp.async (LDGSTS) RING - 1 row-loop trips ahead of their use.  Every lane copies and reads only its own
-//     slots, so no barrier is involved and nothing waits in the L2 for long;
+// Work distribution: the host deals the warp steps to the (CTA, warp) slots by estimated cost (RowsArgs::order); the
+// kernel walks its slot's list, so the per-slot partial sums keep a fixed order.
+//
+// Memory pipeline (a warp step covers 32 / G whole records, 18 - 37 KB: too much to double-buffer per warp) - everything
+// from HBM arrives in shared memory ahead of its use and nothing of it passes through the L1:
+//   * hazard rows (80 % of the bytes): a ring of JMB_ROWS_RING stages per warp filled with cp.async (LDGSTS)
+//     RING - 1 row-loop trips ahead of their use, 16 bytes per copy by lane pairs (JMB_ROWS_PAIR);
 //   * "early" data of a step - record header, state, draws of the iteration, visit rows of every outcome and
-//     their per-draw linear predictors, about 1 kB per subject: one shared-memory stage per warp, filled for the
-//     warp's NEXT step by cp.async.bulk copies + an mbarrier (template parameter EARLY) as soon as the visit loops of the
-//     current step are done, i.e. a whole hazard loop ahead of its use.
+//     their per-draw linear predictors, about 1 kB per subject - for the warp's NEXT step (template parameter EARLY):
+//     1: cp.async.bulk + mbarrier into a per-group stage; 3: the same stage filled by the lanes' 16-byte cp.async;
+//     2: group slots + lane-private visit slots; 0: read in place behind an L2 prefetch.
 // An L2 prefetch of whole records one step ahead (cp.async.bulk.prefetch.L2) was measured first and evicts itself
 // (16 warps x 148 SMs x 37 KB = 87 MB in flight; DRAM reads 1.9x the compulsory bytes).
+//
+// Code size: the loop body of a step has to fit the 32 KB instruction cache of an SM.  Cold paths are out-of-line
+// functions with SCALAR arguments (a pointer or reference to a local moves it to the stack for the whole kernel); the
+// censoring code and the visit loops exist once.
 //
 // The sums over quadrature rows need the proposed-parameter hazard at the accepted b, which is only known after
 // all rows have been visited: the row loop therefore accumulates it for both the old and the proposed b (three
