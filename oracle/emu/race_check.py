@@ -37,14 +37,19 @@ for name in %(names)r:
         # the compile-time specialised kernel and the TMA-staged kernel (two-stage cp.async.bulk + mbarrier pipeline per warp)
         c = make_cohort(name, n=128)     # 2 CTAs x 8 warps x 8 subjects: 4 (16 lanes) or 8 (32 lanes) pipeline steps per warp
         ctl = dict(c["control"]); ctl.update(n_burnin=4, n_iter=2, n_block=2, n_thin=2)
-        for mode, prefix in (("direct", "static:"), ("tma", "static-tma:"), (None, "static-rows")):   # None = the default: row-strided kernel
+        # None = the default: row-strided kernel; early = its staging variant (paired ring copies, group slots / stages handed
+        # over between the lanes of a group: every variant's __syncwarp protocol is exercised)
+        for mode, early, prefix in (("direct", None, "static:"), ("tma", None, "static-tma:"), (None, None, "static-rows"),
+                                    (None, "0", "static-rows"), (None, "1", "static-rows"), (None, "2", "static-rows"), (None, "3", "static-rows")):
             if mode: os.environ["JMB_KERNEL"] = mode
             else: os.environ.pop("JMB_KERNEL", None)
+            if early is None: os.environ.pop("JMB_ROWS_EARLY", None)
+            else: os.environ["JMB_ROWS_EARLY"] = early
             with api.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
                 assert fit.layout_info()["kernel"].startswith(prefix), fit.layout_info()["kernel"]
                 fit.set_draw(c["Data"])
                 fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
-        os.environ["JMB_KERNEL"] = "generic"
+        os.environ["JMB_KERNEL"] = "generic"; os.environ.pop("JMB_ROWS_EARLY", None)
     c = make_multistate_cohort(n=24) if ms else make_cohort(name, n=24)
     ctl = dict(c["control"]); ctl.update(n_burnin=6, n_iter=4, n_block=2, n_thin=2, adaptCov=True)
     pr = dict(c["priors"]); pr.update(shrink_gammas=True, shrink_alphas=True)

@@ -250,3 +250,21 @@ def test_emulated_blocks_of_several_draw_chunks_match_oracle(emu, oracle, cfg, c
     assert _rel(r1["extras"]["trace_surv"], r0["extras"]["trace_surv"]) <= 1e-12
     assert np.allclose(r1["mcmc"]["b"], r0["mcmc"]["b"], rtol=1e-10, atol=1e-13)
     assert np.array_equal(r1["extras"]["accept_b"], r0["extras"]["accept_b"])
+
+
+def test_emulated_step_lists_do_not_change_the_chain(emu, monkeypatch):
+    """The cost-balanced step lists (longest processing time first over the (CTA, warp) slots) and the CTA-contiguous assignment of
+    equal counts walk the same chain: only the grouping of the per-slot partial sums differs."""
+    monkeypatch.delenv("JMB_KERNEL", raising=False)
+    c = make_cohort("config4", n=150)
+    ctl = dict(c["control"]); ctl.update(n_burnin=20, n_iter=10, n_block=10, n_thin=5)
+    out = {}
+    for lpt in ("1", "0"):
+        monkeypatch.setenv("JMB_ROWS_LPT", lpt)
+        with emu.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
+            assert fit.layout_info()["kernel"].startswith("static-rows")
+            fit.set_draw(c["Data"])
+            out[lpt] = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    assert _rel(out["1"]["extras"]["trace_surv"], out["0"]["extras"]["trace_surv"]) <= 1e-12
+    assert np.array_equal(out["1"]["extras"]["accept_b"], out["0"]["extras"]["accept_b"])
+    assert np.allclose(out["1"]["mcmc"]["b"], out["0"]["mcmc"]["b"], rtol=1e-12, atol=1e-14)
