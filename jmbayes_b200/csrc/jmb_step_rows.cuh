@@ -162,45 +162,16 @@ __device__ __forceinline__ double log_ptb_rows(double event, double lh, double H
     }
 }
 
-// The censoring terms of the three (survival parameters, b) pairs of a step at once - (current, new b), (proposed, old b),
-// (proposed, new b): the exponentials and logarithms are independent chains, and the term of the proposed parameters no longer
-// waits for the accept decision (which needs the first term) before it starts.
-#ifndef JMB_ROWS_PTB3
-#define JMB_ROWS_PTB3 0
-#endif
-// censoring terms evaluated lane-parallel inside the group (G >= 8)
+// censoring terms evaluated lane-parallel inside the group (G >= 8).  (Evaluating the three terms side by side on every lane,
+// and two visit rows per loop trip, were measured too: both lose more to code size than the extra independent chains gain,
+// profiles/r2b_rows_kernel.md.)
 #ifndef JMB_ROWS_PTBL
 #define JMB_ROWS_PTBL 1
 #endif
-__device__ __forceinline__ void log_ptb_rows3(const double event, const double (&lh)[3], const double (&H)[3], const double (&HL)[3], double (&out)[3]) {
-    double eH[3], eHL[3];
-    exp3(-H[0], -H[1], -H[2], eH[0], eH[1], eH[2]);
-    exp3(-HL[0], -HL[1], -HL[2], eHL[0], eHL[1], eHL[2]);
-    double lg[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double arg = (event == 2.0) ? (1.0 - eH[i]) : ((event == 3.0) ? (eHL[i] - eH[i]) : 1.0);
-        lg[i] = log(arg);
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        double r = 0.0;
-        if (event == 1.0) r = lh[i] - H[i];
-        if (event == 0.0) r = 0.0 - H[i];
-        if (event == 2.0 || event == 3.0) r = lg[i];
-        out[i] = r;
-    }
-}
 
 // GLMM log-density of this lane's visit rows (lin_predF + log_longF, src/fast_LAPRWM.cpp:67-78,168-202); lrec / lcrec point
 // at the visit rows of the design / per-draw record, in global memory or in the warp's early stage (the call sites keep
 // the two apart so that the loads compile to LDS / LDG rather than generic loads)
-// Two rows of an outcome per loop trip (rows r and r + G): their log-densities are independent dependency chains (exp / divide /
-// log of the logit and Poisson rows), evaluated side by side instead of one after the other; the sum keeps the row order.  A lane
-// without a second row re-evaluates its first one and drops the result.
-#ifndef JMB_ROWS_VIS2
-#define JMB_ROWS_VIS2 0
-#endif
 template <class Spec, int G>
 __device__ __forceinline__ double visit_rows(const double* __restrict__ lrec, const double* __restrict__ lcrec, const int* vcount,
                                              const double (&bn)[Spec::d.q], const double (&isig)[Spec::d.O], const int l) {
@@ -220,19 +191,7 @@ __device__ __forceinline__ double visit_rows(const double* __restrict__ lrec, co
             });
             return eta;
         };
-#if JMB_ROWS_VIS2
-        for (int r = l; r < v; r += 2 * G) {
-            const bool two = r + G < v;
-            const int rb = two ? r + G : r;
-            const double eta0 = eta_of(r), eta1 = eta_of(rb);
-            const double ld0 = logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta0, isig[k]);
-            const double ld1 = logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[rb], eta1, isig[k]);
-            v_pyb += ld0;
-            if (two) v_pyb += ld1;
-        }
-#else
         for (int r = l; r < v; r += G) v_pyb += logdens_static<Spec::d.fam[k], Spec::d.link[k]>(lrec[r], eta_of(r), isig[k]);
-#endif
         constexpr int lcols = Spec::L.long_cols[k];
         lrec += lcols * v;
         lcrec += v;
@@ -781,12 +740,6 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
         {
         const double event = event_t, log_u = log_u_t, pyb_old = pyb_old_t, pb_old = pb_old_t, ptb_co = ptb_co_t;
 
-        double ptb3[3] = {0.0, 0.0, 0.0};
-        constexpr bool PTB3 = JMB_ROWS_PTB3 != 0 && S == 2 && !MS;
-        if constexpr (PTB3) {
-            const double lh3[3] = {lh_cn, lh_po, lh_pn}, H3[3] = {H_cn, H_po, H_pn}, HL3[3] = {HL_cn, HL_po, HL_pn};
-            log_ptb_rows3(event, lh3, H3, HL3, ptb3);
-        }
         // The censoring term is evaluated twice - current parameters at the proposal, then (after the accept decision, :706)
         // proposed parameters at the accepted b (:735-752) - by ONE copy of its code (two exponentials and a logarithm of libm):
         // the kernel's hot loop has to fit the instruction cache.
@@ -816,11 +769,10 @@ jmb_step_rows(const int B, const __grid_constant__ ParamLayout pl, const __grid_
             ptb_cn = term(lh_cn, H_cn, lg_cn);
             accept = log_u < ((pyb_new + ptb_cn + pb_new) - cur_lp);     // :703, :706 (NaN rejects)
             ptb_p = accept ? term(lh_pn, H_pn, lg_pn) : term(lh_po, H_po, lg_po);
-        } else if constexpr (MS || PTB3 || S != 2) {
-            ptb_cn = MS ? ms_cn : (PTB3 ? ptb3[0] : log_ptb_rows<S>(event, lh_cn, H_cn, HL_cn));
+        } else if constexpr (MS || S != 2) {
+            ptb_cn = MS ? ms_cn : log_ptb_rows<S>(event, lh_cn, H_cn, HL_cn);
             accept = log_u < ((pyb_new + ptb_cn + pb_new) - cur_lp);     // :703, :706 (NaN rejects)
-            ptb_p = MS ? (accept ? ms_pn : ms_po)
-                       : (PTB3 ? (accept ? ptb3[2] : ptb3[1]) : log_ptb_rows<S>(event, accept ? lh_pn : lh_po, accept ? H_pn : H_po, 0.0));
+            ptb_p = MS ? (accept ? ms_pn : ms_po) : log_ptb_rows<S>(event, accept ? lh_pn : lh_po, accept ? H_pn : H_po, 0.0);
         } else {
 #pragma unroll 1
             for (int it = 0; it < 2; ++it) {
