@@ -365,6 +365,10 @@ int jmb_handle_s::select_kernel() {
                     const double f = (double)std::max<long long>(budget, 0) / (double)(cd + cc_);
                     cd = (long long)(cd * f) / 2 * 2; cc_ = (long long)(cc_ * f) / 2 * 2;
                 }
+                if (const char* e = getenv("JMB_ROWS_CAP")) {     // tests: a small stage, so that long visit segments are read in place
+                    const long long lim = std::max(0, atoi(e)) / 2 * 2;
+                    cd = std::min(cd, lim); cc_ = std::min(cc_, lim);
+                }
                 ra.cap_dl = (int)std::max<long long>(cd, 0); ra.cap_cl = (int)std::max<long long>(cc_, 0);
                 const int RSd = head + ra.cap_dl + ra.cap_cl;
                 rows_smem = (int)(fixed_b + 8LL * kRowsWarps * spw * RSd);

@@ -268,3 +268,22 @@ def test_emulated_step_lists_do_not_change_the_chain(emu, monkeypatch):
     assert _rel(out["1"]["extras"]["trace_surv"], out["0"]["extras"]["trace_surv"]) <= 1e-12
     assert np.array_equal(out["1"]["extras"]["accept_b"], out["0"]["extras"]["accept_b"])
     assert np.allclose(out["1"]["mcmc"]["b"], out["0"]["mcmc"]["b"], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("early", ["1", "3"])
+def test_emulated_visit_segments_beyond_the_stage_are_read_in_place(emu, oracle, early, monkeypatch):
+    """A stage too small for the longer visit segments (JMB_ROWS_CAP): those subjects read their visit rows from the record through
+    the same loop (pointer selected per subject), the others from the stage - same chain as the oracle."""
+    monkeypatch.delenv("JMB_KERNEL", raising=False)
+    monkeypatch.setenv("JMB_ROWS_G", "8"); monkeypatch.setenv("JMB_ROWS_EARLY", early); monkeypatch.setenv("JMB_ROWS_CAP", "40")
+    c = make_cohort("config4", n=70)
+    v = np.bincount(np.asarray(c["Data"]["idL"][0]).astype(int))
+    assert (6 * v[v > 0] > 40).any() and (6 * v[v > 0] <= 40).any()          # both paths are taken (6 stored doubles per visit)
+    ctl = dict(c["control"]); ctl.update(n_burnin=20, n_iter=10, n_block=10, n_thin=5)
+    with emu.Fit(c["Data"], c["Covs"]["b"], c["interval_cens"]) as fit:
+        fit.set_draw(c["Data"])
+        r1 = fit.lap_rwm_C(c["inits"], c["priors"], c["scales"], c["Covs"], ctl)
+    oracle.set_rowsum_mode(1)
+    r0 = oracle.lap_rwm_C(c["inits"], c["Data"], c["priors"], c["scales"], c["Covs"], ctl, c["interval_cens"])
+    assert _rel(r1["extras"]["trace_surv"], r0["extras"]["trace_surv"]) <= 1e-12
+    assert np.allclose(r1["mcmc"]["b"], r0["mcmc"]["b"], rtol=1e-10, atol=1e-13)
