@@ -38,6 +38,15 @@ int jmb_right_rows_mstate(int device, int32_t n, int32_t nT, int32_t K, const in
 int jmb_spline_design(int device, const double* knots, int32_t n_knots, int32_t ord, const double* x, int64_t n,
                       int32_t* off, double* vals, double* dense);
 
+/* The data frame the quadrature designs are built from (R/mvJointModelBayes.R:256-268): `dataL.id2 <- right_rows(dataL, ...)`
+ * is `data[c(ind), ]` (R/supportFuns_mvJointModelBayes.R:24), followed by `dataL.id2[[timeVar]] <- c(t(st))` (and the same for
+ * dataL.id / dataL_int.id2 with Time / TimeL / c(t(st_int))).  X [N x p] column-major = the numeric columns of the long data,
+ * rows [M] = the 0-based row indices jmb_right_rows returned, time_col = column that holds timeVar (-1: none), new_time [M] =
+ * c(t(st)).  out [M x p] column-major: out[m, c] = X[rows[m], c], except out[m, time_col] = new_time[m].  Bit-exact (a gather).
+ * model.matrix() on this frame stays in R: it is formula semantics, not arithmetic. */
+int jmb_data_rows(int device, const double* X, int64_t N, int32_t p, const int64_t* rows, int64_t M, int32_t time_col,
+                  const double* new_time, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,16 @@ __global__ void spline_band_kernel(const double* __restrict__ t, const int nk, c
     if (dense) for (int r = 0; r < ord; ++r) if (Bl[r] != 0.0 || (xv >= t[ord - 1] && xv <= t[nb])) dense[i + (long long)(o + r) * n] = Bl[r];
 }
 
+// data[c(ind), ] with the time column replaced: one thread per selected row, column-major in and out (writes coalesced over the rows,
+// reads nearly so: consecutive quadrature points of a subject select the same or neighbouring visits)
+__global__ void data_rows_kernel(const double* __restrict__ X, const long long N, const int p, const long long* __restrict__ rows, const long long M,
+                                 const int time_col, const double* __restrict__ new_time, double* __restrict__ out) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const long long r = rows[m];
+    for (int c = 0; c < p; ++c) out[m + (long long)c * M] = (c == time_col) ? new_time[m] : X[r + (long long)c * N];
+}
+
 struct Dev { void* p = nullptr; ~Dev() { if (p) cudaFree(p); } };
 
 int pick(int device) {
@@ -132,5 +142,26 @@ extern "C" int jmb_spline_design(int device, const double* knots, int32_t n_knot
     CUD(cudaMemcpy(off, d_off.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
     CUD(cudaMemcpy(vals, d_v.p, sizeof(double) * n * ord, cudaMemcpyDeviceToHost));
     if (dense) CUD(cudaMemcpy(dense, d_d.p, sizeof(double) * n * nb, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int jmb_data_rows(int device, const double* X, int64_t N, int32_t p, const int64_t* rows, int64_t M, int32_t time_col,
+                             const double* new_time, double* out) {
+    if (!X || !rows || !out) return jmb_set_error("jmb_data_rows: null argument");
+    if (N <= 0 || p <= 0 || M <= 0) return jmb_set_error("jmb_data_rows: need N, p, M > 0");
+    if (time_col >= p || time_col < -1) return jmb_set_error("jmb_data_rows: time_col out of range");
+    if (time_col >= 0 && !new_time) return jmb_set_error("jmb_data_rows: new_time required with a time column");
+    for (int64_t m = 0; m < M; ++m) if (rows[m] < 0 || rows[m] >= N) return jmb_set_error("jmb_data_rows: row index " + std::to_string(m) + " out of range");
+    if (pick(device)) return 1;
+    Dev d_x, d_r, d_t, d_o;
+    CUD(cudaMalloc(&d_x.p, sizeof(double) * N * p)); CUD(cudaMalloc(&d_r.p, sizeof(long long) * M));
+    CUD(cudaMalloc(&d_o.p, sizeof(double) * M * p));
+    CUD(cudaMemcpy(d_x.p, X, sizeof(double) * N * p, cudaMemcpyHostToDevice));
+    CUD(cudaMemcpy(d_r.p, rows, sizeof(long long) * M, cudaMemcpyHostToDevice));
+    if (time_col >= 0) { CUD(cudaMalloc(&d_t.p, sizeof(double) * M)); CUD(cudaMemcpy(d_t.p, new_time, sizeof(double) * M, cudaMemcpyHostToDevice)); }
+    data_rows_kernel<<<(unsigned)((M + 255) / 256), 256>>>((const double*)d_x.p, (long long)N, p, (const long long*)d_r.p, (long long)M, time_col,
+                                                           (const double*)d_t.p, (double*)d_o.p);
+    CUD(cudaGetLastError());
+    CUD(cudaMemcpy(out, d_o.p, sizeof(double) * M * p, cudaMemcpyDeviceToHost));
     return 0;
 }

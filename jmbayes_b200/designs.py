@@ -20,6 +20,7 @@ def _lib():
         L.jmb_right_rows.argtypes = [C.c_int, C.c_int32, C.c_int32, i64p, dp, dp, i64p]
         L.jmb_right_rows_mstate.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_int32, i64p, dp, i32p, dp, i64p]
         L.jmb_spline_design.argtypes = [C.c_int, dp, C.c_int32, C.c_int32, dp, C.c_int64, i32p, dp, dp]
+        L.jmb_data_rows.argtypes = [C.c_int, dp, C.c_int64, C.c_int32, i64p, C.c_int64, C.c_int32, dp, dp]
         _bound = True
     return L
 
@@ -68,3 +69,21 @@ def spline_design(knots, x, ord: int = 4, dense: bool = False, device: int = 0):
     _check(_lib().jmb_spline_design(int(device), _p(knots, C.c_double), knots.size, int(ord), _p(x, C.c_double), x.size,
                                     _p(off, C.c_int32), _p(vals, C.c_double), _p(D, C.c_double) if dense else None))
     return (off, vals, D) if dense else (off, vals)
+
+
+def data_rows(X, rows, time_col=None, new_time=None, device: int = 0) -> np.ndarray:
+    """``data[c(ind), ]`` with ``data[[timeVar]] <- c(t(st))`` (R/supportFuns_mvJointModelBayes.R:24, R/mvJointModelBayes.R:256-268) on
+    the numeric columns ``X`` [N, p] of the long data: the rows ``right_rows`` selected, the time column replaced by the quadrature
+    times.  Returns [M, p] (Fortran order, as R holds it)."""
+    X = np.asfortranarray(np.asarray(X, dtype=np.float64))
+    if X.ndim != 2:
+        raise ValueError("data_rows: X must be a matrix")
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    tc = -1 if time_col is None else int(time_col)
+    nt = None if time_col is None else np.ascontiguousarray(new_time, dtype=np.float64)
+    if nt is not None and nt.size != rows.size:
+        raise ValueError("data_rows: one new time per selected row")
+    out = np.zeros((rows.size, X.shape[1]), order="F")
+    _check(_lib().jmb_data_rows(int(device), _p(X, C.c_double), X.shape[0], X.shape[1], _p(rows, C.c_int64), rows.size, tc,
+                                _p(nt, C.c_double) if nt is not None else None, _p(out, C.c_double)))
+    return out

@@ -39,3 +39,11 @@ def spline_design(knots, x, ord=4):
     if inside.any():
         D[inside] = BSpline.design_matrix(x[inside], knots, ord - 1).toarray()
     return D
+
+
+def data_rows(X, rows, time_col=None, new_time=None):
+    """data[c(ind), ] (R/supportFuns_mvJointModelBayes.R:24) followed by dataL.id2[[timeVar]] <- c(t(st)) (R/mvJointModelBayes.R:257,264,268)."""
+    out = np.array(np.asarray(X, dtype=np.float64)[np.asarray(rows, dtype=np.int64)], order="F")
+    if time_col is not None:
+        out[:, time_col] = np.asarray(new_time, dtype=np.float64)
+    return out

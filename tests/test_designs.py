@@ -49,7 +49,7 @@ def test_library_exports_the_design_entry_points():
     import ctypes as C
     from jmbayes_b200 import build
     L = C.CDLL(build.build_cuda())
-    for name in ("jmb_right_rows", "jmb_right_rows_mstate", "jmb_spline_design"):
+    for name in ("jmb_right_rows", "jmb_right_rows_mstate", "jmb_spline_design", "jmb_data_rows"):
         assert hasattr(L, name), name
 
 
@@ -85,3 +85,27 @@ def test_spline_design_on_device_matches_scipy_and_the_host_path(cuda_lib):
     for r in range(4):
         rebuilt[rows, off + r] += vals[:, r]
     assert np.array_equal(rebuilt, D) and np.all(off >= 0) and np.all(off + 3 < 17)
+
+
+def test_restated_data_rows_is_the_selected_frame_with_the_new_times():
+    ids, times, Q = _long_data(50, 7, K=3)
+    rng = np.random.default_rng(7)
+    X = np.column_stack([times, rng.normal(size=times.size), (ids % 2).astype(float)])      # timeVar, a time-varying and a baseline covariate
+    rows = od.right_rows(times, ids, Q)
+    F = od.data_rows(X, rows, time_col=0, new_time=Q.ravel())
+    assert F.shape == (150, 3) and np.array_equal(F[:, 0], Q.ravel()) and np.array_equal(F[:, 1:], X[rows][:, 1:])
+    assert np.array_equal(od.data_rows(X, rows), X[rows])
+
+
+@pytest.mark.gpu
+def test_data_rows_on_device_is_bit_exact(cuda_lib):
+    from jmbayes_b200 import designs
+    ids, times, Q = _long_data(5000, 11)
+    rng = np.random.default_rng(11)
+    X = np.column_stack([times, rng.normal(size=times.size), rng.normal(size=times.size), (ids % 3).astype(float)])
+    rows = designs.right_rows(times, ids, Q)
+    got = designs.data_rows(X, rows, time_col=0, new_time=Q.ravel())
+    assert np.array_equal(got, od.data_rows(X, rows, time_col=0, new_time=Q.ravel()))
+    assert np.array_equal(designs.data_rows(X, rows), X[rows])
+    with pytest.raises(Exception):
+        designs.data_rows(X, np.r_[rows, X.shape[0]], time_col=0, new_time=np.r_[Q.ravel(), 1.0])     # row index out of range
